@@ -1,0 +1,177 @@
+"""oracle -- TEST INFRASTRUCTURE: ctypes bindings of the CPU checkers.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package.  The product (orb_slam2_aruco_b200) never does.
+
+  liboracle.so        our CPU restatement (oracle/*_oracle.cpp over oracle/cvprim*.h)
+  _ref/libref_orb.so  the reference's own src/ORBextractor.cc compiled unmodified on oracle/cvshim
+                      (built only where /root/reference exists; the prebuilt .so travels to the GPU box)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+_ref = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(quiet=True):
+    """Compile liboracle.so (always) and _ref/libref_orb.so (only if /root/reference is present)."""
+    r = subprocess.run(["make", "-C", HERE, "all", "CXX=g++"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    if not quiet:
+        print(r.stdout)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = C.CDLL(path)
+        _lib.oracle_fast_atan2.restype = C.c_float
+        _lib.oracle_fast_atan2.argtypes = [C.c_float, C.c_float]
+    return _lib
+
+
+def ref():
+    """The reference's own extractor on the shim, or None when it was never built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(HERE, "_ref", "libref_orb.so")
+        if not os.path.exists(path):
+            return None
+        _ref = C.CDLL(path)
+    return _ref
+
+
+# ---- primitives -------------------------------------------------------------------------------
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border_reflect101(src, border):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h + 2 * border, w + 2 * border), np.uint8)
+    lib().oracle_border_reflect101(_p(src), w, h, w, _p(dst), w + 2 * border, border)
+    return dst
+
+
+def gaussian_blur7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().oracle_gaussian_blur7(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), src.shape[1])
+    return dst
+
+
+def fast_nms(img, thr):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    out = np.empty((cap, 3), np.int32)
+    n = lib().oracle_fast_nms(_p(img), img.shape[1], img.shape[0], img.shape[1], int(thr), _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return float(lib().oracle_fast_atan2(float(y), float(x)))
+
+
+# ---- extractor --------------------------------------------------------------------------------
+def orb_levels(w, h, nfeatures=1000, scale=1.2, nlevels=8):
+    lw = np.empty(nlevels, np.int32); lh = np.empty(nlevels, np.int32); q = np.empty(nlevels, np.int32)
+    sf = np.empty(nlevels, np.float32)
+    lib().oracle_orb_levels(w, h, nfeatures, C.c_float(scale), nlevels, _p(lw), _p(lh), _p(q), _p(sf))
+    return lw, lh, q, sf
+
+
+def orb_pyramid_level(img, level, scale=1.2, nlevels=8):
+    img = np.ascontiguousarray(img, np.uint8)
+    lw, lh, _, _ = orb_levels(img.shape[1], img.shape[0], 1000, scale, nlevels)
+    out = np.empty((lh[level], lw[level]), np.uint8)
+    lib().oracle_orb_pyramid_level(_p(img), img.shape[1], img.shape[0], img.shape[1], C.c_float(scale), nlevels, level, _p(out))
+    return out
+
+
+def orb_candidates(img, level, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = 200000
+    out = np.empty((cap, 3), np.int32)
+    n = lib().oracle_orb_candidates(_p(img), img.shape[1], img.shape[0], img.shape[1], nfeatures, C.c_float(scale), nlevels,
+                                    ini_th, min_th, level, _p(out), cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def orb_extract(img, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+    """-> (keypoints structured array [n], descriptors uint8 [n,32])"""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = nfeatures + 3 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    if img.size == 0:
+        return kps[:0], desc[:0]
+    n = lib().oracle_orb_extract(_p(img), img.shape[1], img.shape[0], img.shape[1], nfeatures, C.c_float(scale), nlevels,
+                                 ini_th, min_th, _p(kps), _p(desc), cap)
+    assert n >= 0
+    return kps[:n].copy(), desc[:n].copy()
+
+
+def orb_extract_batch(imgs, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, nthreads=1):
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    n, h, w = imgs.shape
+    cap = nfeatures + 3 * nlevels + 64
+    kps = np.zeros((n, cap), KP_DTYPE)
+    desc = np.zeros((n, cap, 32), np.uint8)
+    counts = np.zeros(n, np.int32)
+    lib().oracle_orb_extract_batch(_p(imgs), n, w, h, w, C.c_long(w * h), nfeatures, C.c_float(scale), nlevels, ini_th, min_th,
+                                   _p(kps), _p(desc), _p(counts), cap, nthreads)
+    return kps, desc, counts
+
+
+def ref_orb_extract(img, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+    """The reference's own ORBextractor::operator() (src/ORBextractor.cc:1043) through oracle/_ref."""
+    r = ref()
+    if r is None:
+        raise RuntimeError("oracle/_ref/libref_orb.so not built (needs /root/reference)")
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = nfeatures + 3 * nlevels + 64
+    raw = np.zeros((cap, 7), np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = r.ref_orb_extract(_p(img), img.shape[1], img.shape[0], img.shape[1], nfeatures, C.c_float(scale), nlevels,
+                          ini_th, min_th, _p(raw), _p(desc), cap)
+    assert n >= 0
+    kps = np.zeros(n, KP_DTYPE)
+    for i, f in enumerate(("x", "y", "size", "angle", "response")):
+        kps[f] = raw[:n, i]
+    kps["octave"] = raw[:n, 5].astype(np.int32)
+    kps["class_id"] = raw[:n, 6].astype(np.int32)
+    return kps, desc[:n].copy()
+
+
+def ref_orb_pyramid_level(img, level, scale=1.2, nlevels=8):
+    r = ref()
+    img = np.ascontiguousarray(img, np.uint8)
+    lw, lh, _, _ = orb_levels(img.shape[1], img.shape[0], 1000, scale, nlevels)
+    out = np.empty((lh[level] + 38, lw[level] + 38), np.uint8)
+    wl = C.c_int(); hl = C.c_int()
+    r.ref_orb_pyramid_level(_p(img), img.shape[1], img.shape[0], img.shape[1], C.c_float(scale), nlevels, level, _p(out),
+                            C.byref(wl), C.byref(hl))
+    assert (wl.value, hl.value) == (lw[level], lh[level])
+    return out

@@ -1,0 +1,45 @@
+// oracle/oracle.h -- TEST INFRASTRUCTURE (CPU checker), not product code.
+// Plain-C interface of liboracle.so: the CPU restatement of the reference's per-frame front end.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// Same record as the product's b200_keypoint (include/b200slam.h) == cv::KeyPoint's 28 bytes.
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} oracle_keypoint;
+
+// ---- primitives (pinned against cv2 golden vectors) -------------------------------------------
+void oracle_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstep, uint8_t* dst, int dw, int dh, int dstep);
+void oracle_border_reflect101(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep, int border);
+void oracle_gaussian_blur7(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep);
+// returns count; xys = [cap][3] (x, y, score)
+int  oracle_fast_nms(const uint8_t* img, int w, int h, int step, int thr, int32_t* xys, int cap);
+float oracle_fast_atan2(float y, float x);
+
+// ---- extractor: restatement of ORB_SLAM2::ORBextractor (src/ORBextractor.cc:410-1132) ---------
+// level geometry: writes nlevels entries of w,h,quota; returns 0
+int oracle_orb_levels(int w, int h, int nfeatures, float scale, int nlevels, int32_t* lw, int32_t* lh, int32_t* quota,
+                      float* scale_factor);
+// pyramid level without border; out holds lw*lh bytes
+int oracle_orb_pyramid_level(const uint8_t* img, int w, int h, int stride, float scale, int nlevels, int level, uint8_t* out);
+// candidates of one level after the per-cell FAST stage (before the quadtree), level coords relative
+// to minBorder (16): xys [cap][3]; returns count or -1
+int oracle_orb_candidates(const uint8_t* img, int w, int h, int stride, int nfeatures, float scale, int nlevels,
+                          int ini_th, int min_th, int level, int32_t* xys, int cap);
+// full extractor on one frame; returns number of keypoints (or -1 if cap too small)
+int oracle_orb_extract(const uint8_t* img, int w, int h, int stride, int nfeatures, float scale, int nlevels,
+                       int ini_th, int min_th, oracle_keypoint* kps, uint8_t* desc, int cap);
+// batch version, std::thread pool over frames with nthreads threads; counts[n]; kps/desc are [n][cap]
+int oracle_orb_extract_batch(const uint8_t* imgs, int n, int w, int h, int row_stride, long frame_stride,
+                             int nfeatures, float scale, int nlevels, int ini_th, int min_th,
+                             oracle_keypoint* kps, uint8_t* desc, int32_t* counts, int cap, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
