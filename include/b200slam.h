@@ -1,0 +1,135 @@
+/* b200slam.h -- C-ABI of the B200-native ORB-SLAM2/ArUco per-frame front end.
+ *
+ * The reference (CarminLiu/ORB_SLAM2_aruco) has no FFI layer: Frame/Tracking call three C++ classes
+ * directly.  This header is the boundary a drop-in replacement exports underneath those classes
+ * (SURVEY.md section 8(b)); include/b200slam_adapters.hpp holds the source-compatible C++ classes
+ * (same names / signatures as the reference) that marshal to these entry points.
+ *
+ *   entry point                replaces (reference file:line)
+ *   -------------------------  ---------------------------------------------------------------------
+ *   b200_orb_create            ORB_SLAM2::ORBextractor::ORBextractor        include/ORBextractor.h:51-52, src/ORBextractor.cc:410-470
+ *   b200_orb_extract[_host]    ORB_SLAM2::ORBextractor::operator()          include/ORBextractor.h:59-61, src/ORBextractor.cc:1043-1105
+ *   b200_orb_get_level_info    GetLevels/GetScaleFactors/...                include/ORBextractor.h:63-83
+ *   b200_orb_get_pyramid       public member mvImagePyramid                 include/ORBextractor.h:85,  src/ORBextractor.cc:1107-1132
+ *   b200_match_bf[_host]       ORB_SLAM2::ORBmatcher::SearchByBoW(KF,F,..)  include/ORBmatcher.h:55,    src/ORBmatcher.cc:159-292
+ *                              (degenerate single-node FeatureVector == brute force; DescriptorDistance 1651-1667)
+ *   b200_match_candidates      candidate-list core of SearchByProjection/SearchForInitialization
+ *                                                                           src/ORBmatcher.cc:45-129,409-524,1332-1474
+ *   b200_aruco_create          aruco::MarkerDetector + setDictionary/setDetectionMode/setCornerRefinementMethod
+ *                                                                           Thirdparty/aruco/aruco/markerdetector.h:258,337, src/Frame.cc:129-139
+ *   b200_aruco_detect[_host]   aruco::MarkerDetector::detect                Thirdparty/aruco/aruco/markerdetector.h:276-278, markerdetector_impl.cpp:5826
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success or a
+ * negative B200_E* code and never throws; handles are opaque; output buffers are caller-allocated;
+ * `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream).  Functions without the
+ * _host suffix take DEVICE pointers and only enqueue work on `stream`; the _host variants take HOST
+ * pointers, stage through pinned memory and return after the results are in the caller's buffers.
+ * There is no CPU fallback: without a usable CUDA device every call fails with B200_ENODEV.
+ */
+#ifndef B200SLAM_H
+#define B200SLAM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK          0
+#define B200_EINVAL     -1   /* bad argument (NULL pointer, non-positive size, unknown dictionary ...)          */
+#define B200_ENODEV     -2   /* no CUDA device / wrong architecture                                            */
+#define B200_ECUDA      -3   /* a CUDA runtime call failed; see b200_last_error()                               */
+#define B200_ECAPACITY  -4   /* a batch / image larger than the handle was created for, or scratch overflow     */
+#define B200_ENOMEM     -5
+
+/* 28 bytes, identical to cv::KeyPoint (pt.x, pt.y, size, angle, response, octave, class_id). */
+typedef struct b200_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} b200_keypoint;
+
+/* One detected marker: id + 4 refined corners (x0,y0,...,x3,y3), clockwise from the marker's canonical top-left. */
+typedef struct b200_marker {
+    int32_t id;
+    float xy[8];
+} b200_marker;
+
+typedef struct b200_orb_s*   b200_orb_t;
+typedef struct b200_aruco_s* b200_aruco_t;
+
+const char* b200_last_error(void);
+/* number of CUDA kernel launches issued by this library in the calling process so far */
+int64_t b200_launch_count(void);
+
+/* ---------------------------------------------------------------- extractor ---------------------- */
+int b200_orb_create(b200_orb_t* out, int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+                    int max_width, int max_height, int max_batch, int device);
+int b200_orb_destroy(b200_orb_t h);
+/* capacity (keypoints per frame) the output buffers must provide: sum over levels of quota + slack */
+int b200_orb_max_keypoints(b200_orb_t h);
+/* per-level tables as the reference getters return them; any pointer may be NULL. Arrays hold nlevels entries. */
+int b200_orb_get_level_info(b200_orb_t h, int* nlevels, float* scale_factors, float* inv_scale_factors,
+                            float* level_sigma2, float* inv_level_sigma2, int32_t* features_per_level);
+/* Device-pointer call.  imgs: n gray u8 frames, frame f row y at imgs + f*frame_stride + y*row_stride.
+ * kps [n][cap], desc [n][cap][32], counts [n] with cap = b200_orb_max_keypoints(). */
+int b200_orb_extract(b200_orb_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
+                     b200_keypoint* kps, uint8_t* desc, int32_t* counts, void* stream);
+/* Host-pointer call (the reference-facing one): same layout, host memory, synchronous. */
+int b200_orb_extract_host(b200_orb_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
+                          b200_keypoint* kps, uint8_t* desc, int32_t* counts);
+/* Per-stage device timing for roofline reports: when enabled, every extract call records CUDA events on its
+ * stream around the four stages; b200_orb_get_stage_ms returns the last call's pyramid / fast / quadtree /
+ * describe durations in milliseconds (ms4[4]). */
+int b200_orb_set_profile(b200_orb_t h, int enable);
+int b200_orb_get_stage_ms(b200_orb_t h, float* ms4);
+/* Pyramid of frame `frame` of the LAST extract call, level `level`, with the reference's 19-px REFLECT_101
+ * border: out (host) receives (w_l+38) x (h_l+38) bytes, inner size returned in *w_l, *h_l. */
+int b200_orb_get_pyramid(b200_orb_t h, int frame, int level, uint8_t* out, int* w_l, int* h_l);
+/* Debug/validation taps of the LAST call (host buffers): FAST candidates of one level before the quadtree,
+ * xys [cap][3] = x, y (relative to the 16-px border, as in the reference) and score.  Returns count or <0. */
+int b200_orb_get_candidates(b200_orb_t h, int frame, int level, int32_t* xys, int cap);
+
+/* ---------------------------------------------------------------- matcher ------------------------ */
+/* Brute-force SearchByBoW(KeyFrame, Frame) semantics with one all-inclusive vocabulary node
+ * (src/ORBmatcher.cc:159-292): the outer, order-dependent loop runs over the reference set in index order,
+ * the inner search over the frame's descriptors that are not taken yet; accept when best <= th_low and
+ * best < ratio*second; then keep the three dominant bins of the 30-bin rotation histogram if check_ori.
+ *   ref_desc [n_ref][32], ref_angle [n_ref]           (replicated for every frame of the batch)
+ *   frame_desc [n_batch][frame_cap][32], frame_angle [n_batch][frame_cap], n_frame [n_batch]
+ *   match_ref_idx [n_batch][frame_cap]: reference index matched to each frame keypoint or -1
+ *   n_matches [n_batch]
+ * histo_factor: the reference uses 30/360 here (ORBmatcher.cc:176) and 1/30 elsewhere (417,545,1340). */
+int b200_match_bf(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
+                  const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
+                  float ratio, int th_low, int check_ori, float histo_factor,
+                  int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream);
+int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
+                       const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
+                       float ratio, int th_low, int check_ori, float histo_factor,
+                       int32_t* match_ref_idx, int32_t* n_matches, int device);
+/* Plain 256-bit Hamming distance matrix rows x cols (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1651-1667). */
+int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device);
+/* Candidate-list matching core shared by SearchByProjection / SearchForInitialization:
+ * query q (in index order) examines train descriptors cand[cand_ofs[q] .. cand_ofs[q+1]); best/second
+ * Hamming distance and the index of the best.  Host builds the lists, the device does distances.
+ *   out_best_idx [nq], out_best_dist [nq], out_second_dist [nq]  (idx -1 / dist 256 when the list is empty) */
+int b200_match_candidates_host(const uint8_t* query_desc, int nq, const uint8_t* train_desc, int nt,
+                               const int32_t* cand_ofs, const int32_t* cand, int32_t* out_best_idx,
+                               int32_t* out_best_dist, int32_t* out_second_dist, int device);
+
+/* ---------------------------------------------------------------- ArUco detector ----------------- */
+/* dict_name: "ARUCO", "ARUCO_MIP_25h7", "ARUCO_MIP_36h12", ... (Thirdparty/aruco/aruco/dictionary.cpp:367-383).
+ * Fixed configuration == what src/Frame.cc:129-139 sets: DM_NORMAL (adaptive threshold, ThresHold 7,
+ * window = max(3, 15*w/1920) made odd), CORNER_LINES refinement, minSize 0, no error correction. */
+int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_width, int max_height, int max_batch, int device);
+int b200_aruco_destroy(b200_aruco_t h);
+int b200_aruco_max_markers(b200_aruco_t h);
+/* markers [n][cap] sorted by id per frame (cap = b200_aruco_max_markers()), counts [n]. */
+int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
+                      b200_marker* markers, int32_t* counts, void* stream);
+int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
+                           b200_marker* markers, int32_t* counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SLAM_H */

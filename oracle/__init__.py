@@ -175,3 +175,30 @@ def ref_orb_pyramid_level(img, level, scale=1.2, nlevels=8):
                             C.byref(wl), C.byref(hl))
     assert (wl.value, hl.value) == (lw[level], lh[level])
     return out
+
+
+# ---- matcher ----------------------------------------------------------------------------------
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().oracle_descriptor_distance(_p(a), _p(b)))
+
+
+def search_by_bow_bf(kf_desc, kf_angle, f_desc, f_angle, nnratio=0.7, check_ori=True, factor=None):
+    """ORBmatcher::SearchByBoW(KF, F) with one all-inclusive vocabulary node -> (nmatches, matches[n_f])"""
+    kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
+    f_desc = np.ascontiguousarray(f_desc, np.uint8).reshape(-1, 32)
+    kf_angle = np.ascontiguousarray(kf_angle, np.float32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+    if factor is None:
+        factor = np.float32(30.0) / np.float32(360.0)
+    m = np.empty(len(f_desc), np.int32)
+    n = lib().oracle_search_by_bow_bf(_p(kf_desc), _p(kf_angle), len(kf_desc), _p(f_desc), _p(f_angle), len(f_desc),
+                                      C.c_float(nnratio), int(check_ori), C.c_float(factor), _p(m))
+    return int(n), m
+
+
+def match_candidates(qd, td, ofs, cand):
+    qd = np.ascontiguousarray(qd, np.uint8).reshape(-1, 32); td = np.ascontiguousarray(td, np.uint8).reshape(-1, 32)
+    ofs = np.ascontiguousarray(ofs, np.int32); cand = np.ascontiguousarray(cand, np.int32)
+    bi, bd, sd = (np.empty(len(qd), np.int32) for _ in range(3))
+    lib().oracle_match_candidates(_p(qd), len(qd), _p(td), _p(ofs), _p(cand), _p(bi), _p(bd), _p(sd))
+    return bi, bd, sd

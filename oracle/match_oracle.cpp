@@ -1,0 +1,106 @@
+// oracle/match_oracle.cpp -- TEST INFRASTRUCTURE (CPU checker), not product code.
+// Restatement of the ORBmatcher cores (reference src/ORBmatcher.cc) over plain arrays; ORBmatcher.cc itself
+// cannot be compiled here (its include closure reaches Eigen/g2o: Map.h:28 -> Converter.h:26-28).
+// "parity unpinned" by reference tests (there are none); pinned instead by known-answer
+// checks (numpy popcount, self-match distance 0) in tests/test_oracle_match.py.
+#include "oracle.h"
+#include <cmath>
+#include <vector>
+#include <cstring>
+
+namespace {
+const int TH_LOW = 50, HISTO_LENGTH = 30;   // ORBmatcher.cc:37-39
+
+// ORBmatcher::DescriptorDistance, ORBmatcher.cc:1651-1667 (SWAR popcount over 8 x 32 bit)
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t x, y;
+        memcpy(&x, a + 4 * i, 4); memcpy(&y, b + 4 * i, 4);
+        uint32_t v = x ^ y;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+// ORBmatcher::ComputeThreeMaxima, ORBmatcher.cc:1605-1646
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+}  // namespace
+
+extern "C" {
+
+int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+// SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:159-292) with one vocabulary node that holds
+// every index on both sides and a good MapPoint behind every keyframe feature.
+// matches[n_f]: keyframe index matched to frame keypoint i, or -1.  Returns nmatches.
+int oracle_search_by_bow_bf(const uint8_t* kf_desc, const float* kf_angle, int n_kf,
+                            const uint8_t* f_desc, const float* f_angle, int n_f,
+                            float nnratio, int check_ori, float factor, int32_t* matches) {
+    for (int i = 0; i < n_f; i++) matches[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int iKF = 0; iKF < n_kf; iKF++) {
+        const uint8_t* dKF = kf_desc + (size_t)iKF * 32;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int iF = 0; iF < n_f; iF++) {
+            if (matches[iF] >= 0) continue;
+            const int dist = descriptor_distance(dKF, f_desc + (size_t)iF * 32);
+            if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = iF; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= TH_LOW) {
+            if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                matches[bestIdxF] = iKF;
+                if (check_ori) {
+                    float rot = kf_angle[iKF] - f_angle[bestIdxF];
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    if (bin < 0) bin = 0;
+                    if (bin >= HISTO_LENGTH) bin = HISTO_LENGTH - 1;   // the reference asserts the range
+                    rotHist[bin].push_back(bestIdxF);
+                }
+                nmatches++;
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { matches[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// best / second-best over an explicit candidate list, the inner loop shared by SearchByProjection
+// (ORBmatcher.cc:84-116) and SearchForInitialization (437-461): strict '<' keeps the first minimum.
+void oracle_match_candidates(const uint8_t* qd, int nq, const uint8_t* td, const int32_t* ofs, const int32_t* cand,
+                             int32_t* best_idx, int32_t* best_dist, int32_t* second_dist) {
+    for (int q = 0; q < nq; q++) {
+        int b1 = 256, b2 = 256, bi = -1;
+        for (int i = ofs[q]; i < ofs[q + 1]; i++) {
+            const int d = descriptor_distance(qd + (size_t)q * 32, td + (size_t)cand[i] * 32);
+            if (d < b1) { b2 = b1; b1 = d; bi = cand[i]; }
+            else if (d < b2) b2 = d;
+        }
+        best_idx[q] = bi; best_dist[q] = b1; second_dist[q] = b2;
+    }
+}
+
+}  // extern "C"

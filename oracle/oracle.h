@@ -40,6 +40,14 @@ int oracle_orb_extract_batch(const uint8_t* imgs, int n, int w, int h, int row_s
                              int nfeatures, float scale, int nlevels, int ini_th, int min_th,
                              oracle_keypoint* kps, uint8_t* desc, int32_t* counts, int cap, int nthreads);
 
+// ---- matcher: restatement of ORB_SLAM2::ORBmatcher cores (src/ORBmatcher.cc) -------------------
+int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b);
+int oracle_search_by_bow_bf(const uint8_t* kf_desc, const float* kf_angle, int n_kf,
+                            const uint8_t* f_desc, const float* f_angle, int n_f,
+                            float nnratio, int check_ori, float factor, int32_t* matches);
+void oracle_match_candidates(const uint8_t* qd, int nq, const uint8_t* td, const int32_t* ofs, const int32_t* cand,
+                             int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
 #ifdef __cplusplus
 }
 #endif

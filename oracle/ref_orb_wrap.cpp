@@ -105,3 +105,39 @@ int ref_orb_pyramid_level(const unsigned char* img, int w, int h, int stride, fl
 }
 
 }  // extern "C"
+
+// Threaded batch driver for CPU-baseline timing: nthreads workers pull frames from a shared counter; each
+// worker runs the reference extractor with its own arena.  kps [n][cap][7] floats, desc [n][cap][32].
+// Plain pthreads + malloc here: anything allocated through this object's operator new would live in the
+// calling thread's arena, which every ref_orb_extract call rewinds.
+#include <pthread.h>
+namespace {
+struct BatchJob {
+    const unsigned char* imgs; int n, w, h, row_stride; long frame_stride;
+    int nfeatures; float scale; int nlevels, ini_th, min_th;
+    float* kps; unsigned char* desc; int* counts; int cap;
+    int next;
+};
+void* batch_worker(void* arg) {
+    BatchJob* j = (BatchJob*)arg;
+    for (;;) {
+        int f = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (f >= j->n) break;
+        j->counts[f] = ref_orb_extract(j->imgs + (size_t)f * j->frame_stride, j->w, j->h, j->row_stride, j->nfeatures, j->scale,
+                                       j->nlevels, j->ini_th, j->min_th, j->kps + (size_t)f * j->cap * 7, j->desc + (size_t)f * j->cap * 32, j->cap);
+    }
+    if (g_arena.base) { free(g_arena.base); g_arena.base = 0; g_arena.cap = 0; }   // worker threads die after the call
+    return 0;
+}
+}
+extern "C" int ref_orb_extract_batch(const unsigned char* imgs, int n, int w, int h, int row_stride, long frame_stride,
+                                     int nfeatures, float scale, int nlevels, int ini_th, int min_th,
+                                     float* kps, unsigned char* desc, int* counts, int cap, int nthreads) {
+    BatchJob job = {imgs, n, w, h, row_stride, frame_stride, nfeatures, scale, nlevels, ini_th, min_th, kps, desc, counts, cap, 0};
+    if (nthreads < 1) nthreads = 1;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], 0, batch_worker, &job);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], 0);
+    free(th);
+    return 0;
+}

@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's operator interface for the front-end hot path.
+
+Same class names, argument meaning and error behaviour as the reference's three C++ classes, on top
+of the C-ABI (include/b200slam.h); the C++ twin lives in include/b200slam_adapters.hpp.
+
+  ORBextractor   <- ORB_SLAM2::ORBextractor     (reference include/ORBextractor.h:45-111)
+  ORBmatcher     <- ORB_SLAM2::ORBmatcher       (reference include/ORBmatcher.h:38-104)
+  MarkerDetector <- aruco::MarkerDetector       (reference Thirdparty/aruco/aruco/markerdetector.h:58-410)
+
+Everything here is marshaling; all arithmetic happens in the CUDA kernels.  Batched entry points
+(`extract_batch`, `detect_batch`, `SearchByBoW_batch`) are the additions that let one call feed a B200.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, MARKER_DTYPE, B200Error, check, lib, ptr
+
+
+class ORBextractor:
+    HARRIS_SCORE = 0
+    FAST_SCORE = 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST,
+                 max_width=None, max_height=None, max_batch=1, device=0):
+        """reference: ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+        (ORBextractor.h:51-52).  max_width/max_height/max_batch size the device scratch; when omitted the
+        handle is (re)created lazily for the first image it sees."""
+        self._args = (int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST))
+        self._device = int(device)
+        self._h = None
+        self._dims = (0, 0, 0)
+        if max_width and max_height:
+            self._create(int(max_width), int(max_height), int(max_batch))
+        else:
+            # validate the parameters eagerly, like a constructor would
+            if nlevels < 1 or not scaleFactor > 1.0 or nfeatures < 0:
+                raise B200Error(_lib.EINVAL, "bad extractor parameters")
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def _create(self, w, h, b):
+        self.close()
+        hnd = C.c_void_p()
+        check(lib().b200_orb_create(C.byref(hnd), *self._args, w, h, b, self._device))
+        self._h = hnd
+        self._dims = (w, h, b)
+        self.cap = check(lib().b200_orb_max_keypoints(self._h))
+
+    def _ensure(self, w, h, b):
+        W, H, B = self._dims
+        if self._h is None or w > W or h > H or b > B:
+            self._create(max(w, W, 1), max(h, H, 1), max(b, B, 1))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib().b200_orb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference getters (ORBextractor.h:63-83) -------------------------------------------------
+    def _level_info(self):
+        self._ensure(64, 64, 1)
+        n = self._args[2]
+        sf, isf, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        q = np.empty(n, np.int32)
+        nl = C.c_int()
+        check(lib().b200_orb_get_level_info(self._h, C.addressof(nl), ptr(sf), ptr(isf), ptr(s2), ptr(is2), ptr(q)))
+        return nl.value, sf, isf, s2, is2, q
+
+    def GetLevels(self):
+        return self._args[2]
+
+    def GetScaleFactor(self):
+        return self._args[1]
+
+    def GetScaleFactors(self):
+        return self._level_info()[1]
+
+    def GetInverseScaleFactors(self):
+        return self._level_info()[2]
+
+    def GetScaleSigmaSquares(self):
+        return self._level_info()[3]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._level_info()[4]
+
+    def GetFeaturesPerLevel(self):
+        return self._level_info()[5]
+
+    @property
+    def mvImagePyramid(self):
+        """reference public member (ORBextractor.h:85): level images of the last frame; each entry is the
+        w_l x h_l view into a buffer that carries the 19-px REFLECT_101 border (ORBextractor.cc:1107-1132)."""
+        out = []
+        for level in range(self._args[2]):
+            out.append(self.pyramid_level(0, level)[19:-19, 19:-19])
+        return out
+
+    def pyramid_level(self, frame, level):
+        """bordered (h_l+38, w_l+38) level buffer of frame `frame` of the last call"""
+        W, H, _ = self._dims
+        buf = np.empty((H + 38) * (W + 38), np.uint8)
+        wl, hl = C.c_int(), C.c_int()
+        check(lib().b200_orb_get_pyramid(self._h, frame, level, ptr(buf), C.addressof(wl), C.addressof(hl)))
+        return buf[:(hl.value + 38) * (wl.value + 38)].reshape(hl.value + 38, wl.value + 38)
+
+    def set_profile(self, enable=True):
+        self._ensure(64, 64, 1)
+        check(lib().b200_orb_set_profile(self._h, int(enable)))
+
+    def stage_ms(self):
+        """(pyramid, fast, quadtree, describe) device milliseconds of the last profiled call"""
+        ms = np.zeros(4, np.float32)
+        check(lib().b200_orb_get_stage_ms(self._h, ptr(ms)))
+        return ms
+
+    def candidates(self, frame, level):
+        """debug tap: FAST candidates (x, y, score) of one level of the last call, before the quadtree"""
+        cap = 1 << 20
+        out = np.empty((cap, 3), np.int32)
+        n = check(lib().b200_orb_get_candidates(self._h, frame, level, ptr(out), cap))
+        return out[:n].copy()
+
+    # -- the operator (ORBextractor.h:59-61, ORBextractor.cc:1043-1105) -----------------------------
+    def __call__(self, image, mask=None):
+        """(keypoints, descriptors) of one gray frame.  `mask` is ignored, as in the reference
+        (ORBextractor.h:58).  Empty image => no keypoints (ORBextractor.cc:1046); non-u8 => AssertionError
+        (the reference asserts CV_8UC1, ORBextractor.cc:1050)."""
+        image = np.asarray(image)
+        if image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "image.type() == CV_8UC1"
+        kps, desc, counts = self.extract_batch(image[None])
+        n = int(counts[0])
+        return kps[0, :n].copy(), desc[0, :n].copy()
+
+    def extract_batch(self, images, out=None):
+        """images: uint8 [n, h, w] host array (row-contiguous; row/frame strides are honoured).
+        Returns host arrays kps [n, cap] (KP_DTYPE), desc [n, cap, 32], counts [n].  `out` may pass those three
+        arrays preallocated (e.g. numpy views of pinned memory, which are then written without staging)."""
+        images = np.asarray(images)
+        assert images.dtype == np.uint8 and images.ndim == 3, "images must be uint8 [n,h,w]"
+        if images.strides[2] != 1:
+            images = np.ascontiguousarray(images)
+        n, h, w = images.shape
+        self._ensure(w, h, n)
+        if out is not None:
+            kps, desc, counts = out
+            assert kps.nbytes >= n * self.cap * 28 and desc.nbytes >= n * self.cap * 32 and counts.nbytes >= n * 4
+        else:
+            kps = np.zeros((n, self.cap), KP_DTYPE)
+            desc = np.zeros((n, self.cap, 32), np.uint8)
+            counts = np.zeros(n, np.int32)
+        if n:
+            check(lib().b200_orb_extract_host(self._h, ptr(images), n, w, h, images.strides[1], images.strides[0],
+                                              ptr(kps), ptr(desc), ptr(counts)))
+        return kps, desc, counts
+
+    def extract_batch_device(self, images, kps, desc, counts, stream=None):
+        """device-resident variant: torch uint8 CUDA tensor [n,h,w] in, preallocated CUDA tensors out
+        (kps: uint8/[n,cap,28] or float32 [n,cap,7] view, desc: uint8 [n,cap,32], counts: int32 [n]);
+        only enqueues kernels on `stream` (a torch.cuda.Stream, an int handle, or None = handle stream)."""
+        n, h, w = images.shape
+        self._ensure(w, h, n)
+        s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+        check(lib().b200_orb_extract(self._h, ptr(images), n, w, h, images.stride(1), images.stride(0),
+                                     ptr(kps), ptr(desc), ptr(counts), s))
+
+
+class ORBmatcher:
+    TH_LOW = 50          # ORBmatcher.cc:37-39
+    TH_HIGH = 100
+    HISTO_LENGTH = 30
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        """reference: ORBmatcher(float nnratio=0.6, bool checkOri=true) (ORBmatcher.h:41)"""
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self._device = int(device)
+
+    @staticmethod
+    def DescriptorDistance(a, b, device=0):
+        """Hamming distance of two 32-byte descriptors (ORBmatcher.h:44, ORBmatcher.cc:1651-1667)"""
+        a = np.ascontiguousarray(a, np.uint8).reshape(1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(1, 32)
+        out = np.empty((1, 1), np.int32)
+        check(lib().b200_hamming_matrix_host(ptr(a), 1, ptr(b), 1, ptr(out), device))
+        return int(out[0, 0])
+
+    def distance_matrix(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.empty((len(a), len(b)), np.int32)
+        check(lib().b200_hamming_matrix_host(ptr(a), len(a), ptr(b), len(b), ptr(out), self._device))
+        return out
+
+    def SearchByBoW(self, kf_desc, kf_angles, f_desc, f_angles):
+        """SearchByBoW(KeyFrame, Frame, vpMapPointMatches) (ORBmatcher.h:55, ORBmatcher.cc:159-292) for the
+        case every keyframe feature owns a good MapPoint and all features share one vocabulary node (the
+        brute-force configuration of SURVEY.md section 8a).  Returns (nmatches, matches) where matches[i] is
+        the keyframe index matched to frame keypoint i or -1 (the reference's vpMapPointMatches)."""
+        f_desc = np.ascontiguousarray(f_desc, np.uint8).reshape(-1, 32)
+        f_angles = np.ascontiguousarray(f_angles, np.float32)
+        n, m = self.SearchByBoW_batch(kf_desc, kf_angles, f_desc[None], f_angles[None], np.array([len(f_desc)], np.int32))
+        return int(n[0]), m[0]
+
+    def SearchByBoW_batch(self, kf_desc, kf_angles, f_desc, f_angles, n_frame, histo_factor=None):
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
+        kf_angles = np.ascontiguousarray(kf_angles, np.float32)
+        f_desc = np.ascontiguousarray(f_desc, np.uint8)
+        f_angles = np.ascontiguousarray(f_angles, np.float32)
+        n_frame = np.ascontiguousarray(n_frame, np.int32)
+        nb, cap = f_desc.shape[0], f_desc.shape[1]
+        if histo_factor is None:
+            histo_factor = np.float32(self.HISTO_LENGTH) / np.float32(360.0)     # ORBmatcher.cc:176
+        matches = np.full((nb, cap), -1, np.int32)
+        nm = np.zeros(nb, np.int32)
+        check(lib().b200_match_bf_host(ptr(kf_desc), ptr(kf_angles), len(kf_desc), ptr(f_desc), ptr(f_angles), ptr(n_frame), nb, cap,
+                                       self.mfNNratio, self.TH_LOW, int(self.mbCheckOrientation), float(histo_factor),
+                                       ptr(matches), ptr(nm), self._device))
+        return nm, matches
+
+    def match_candidates(self, query_desc, train_desc, cand_ofs, cand):
+        """distance core of SearchByProjection / SearchForInitialization: per query the best index, best and
+        second-best distance over its candidate list (first minimum in list order wins)"""
+        query_desc = np.ascontiguousarray(query_desc, np.uint8).reshape(-1, 32)
+        train_desc = np.ascontiguousarray(train_desc, np.uint8).reshape(-1, 32)
+        cand_ofs = np.ascontiguousarray(cand_ofs, np.int32)
+        cand = np.ascontiguousarray(cand, np.int32)
+        nq = len(query_desc)
+        bi, bd, sd = (np.empty(nq, np.int32) for _ in range(3))
+        check(lib().b200_match_candidates_host(ptr(query_desc), nq, ptr(train_desc), len(train_desc), ptr(cand_ofs), ptr(cand),
+                                               ptr(bi), ptr(bd), ptr(sd), self._device))
+        return bi, bd, sd
+
+
+class Marker:
+    """aruco::Marker essentials (Thirdparty/aruco/aruco/marker.h:47-59): id + 4 corners, ordered by id"""
+    __slots__ = ("id", "corners")
+
+    def __init__(self, id, corners):
+        self.id = int(id)
+        self.corners = np.asarray(corners, np.float32).reshape(4, 2)
+
+    def __lt__(self, other):
+        return self.id < other.id
+
+    def __repr__(self):
+        return "Marker(id=%d, corners=%s)" % (self.id, self.corners.tolist())
+
+
+class MarkerDetector:
+    def __init__(self, dict_name="ALL_DICTS", max_width=None, max_height=None, max_batch=1, device=0):
+        """reference: MarkerDetector(std::string dict_name) + setDictionary (markerdetector.h:229,337); the
+        configuration is the one src/Frame.cc:129-139 applies (DM_NORMAL, CORNER_LINES)."""
+        self._dict = dict_name
+        self._device = int(device)
+        self._h = None
+        self._dims = (0, 0, 0)
+        if max_width and max_height:
+            self._create(int(max_width), int(max_height), int(max_batch))
+
+    def setDictionary(self, dict_name, error_correction_rate=0.0):
+        assert error_correction_rate == 0.0, "only error_correction_rate 0 (the reference's setting) is supported"
+        self._dict = dict_name
+        W, H, B = self._dims
+        if self._h is not None:
+            self._create(W, H, B)
+
+    def _create(self, w, h, b):
+        self.close()
+        hnd = C.c_void_p()
+        check(lib().b200_aruco_create(C.byref(hnd), self._dict.encode(), w, h, b, self._device))
+        self._h = hnd
+        self._dims = (w, h, b)
+        self.cap = check(lib().b200_aruco_max_markers(self._h))
+
+    def _ensure(self, w, h, b):
+        W, H, B = self._dims
+        if self._h is None or w > W or h > H or b > B:
+            self._create(max(w, W, 1), max(h, H, 1), max(b, B, 1))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib().b200_aruco_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def detect(self, image):
+        """std::vector<aruco::Marker> detect(const cv::Mat&) (markerdetector.h:276): markers sorted by id"""
+        image = np.asarray(image)
+        assert image.dtype == np.uint8 and image.ndim == 2
+        m, c = self.detect_batch(image[None])
+        return [Marker(r["id"], r["xy"]) for r in m[0, :c[0]]]
+
+    def detect_batch(self, images):
+        images = np.asarray(images)
+        assert images.dtype == np.uint8 and images.ndim == 3
+        if images.strides[2] != 1:
+            images = np.ascontiguousarray(images)
+        n, h, w = images.shape
+        self._ensure(w, h, n)
+        markers = np.zeros((n, self.cap), MARKER_DTYPE)
+        counts = np.zeros(n, np.int32)
+        if n:
+            check(lib().b200_aruco_detect_host(self._h, ptr(images), n, w, h, images.strides[1], images.strides[0], ptr(markers), ptr(counts)))
+        return markers, counts
+
+    def detect_batch_device(self, images, markers, counts, stream=None):
+        n, h, w = images.shape
+        self._ensure(w, h, n)
+        s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+        check(lib().b200_aruco_detect(self._h, ptr(images), n, w, h, images.stride(1), images.stride(0), ptr(markers), ptr(counts), s))

@@ -1,0 +1,33 @@
+// common.cu -- process-wide helpers of libb200slam.so: error string, launch counter, device selection.
+#include "common.h"
+#include <math.h>
+
+namespace b200 {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches(0);
+
+int host_round(float v) { return (int)lrintf(v); }        // round-half-even under the default FP environment (cvRound)
+int host_round_d(double v) { return (int)lrint(v); }
+
+int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(B200_ENODEV, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= n) return fail(B200_EINVAL, "device index out of %s", "range");
+    cudaDeviceProp p;
+    B200_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return fail(B200_ENODEV, "device is not sm_100 (%s); kernels are built for sm_100a only", p.name);
+    B200_CUDA(cudaSetDevice(device));
+    return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" {
+const char* b200_last_error(void) { return b200::g_err; }
+int64_t b200_launch_count(void) { return (int64_t)b200::g_launches.load(); }
+}

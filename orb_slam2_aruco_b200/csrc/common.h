@@ -1,0 +1,47 @@
+// common.h -- shared host/device helpers for libb200slam.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <new>
+#include <vector>
+#include "../../include/b200slam.h"
+
+namespace b200 {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define B200_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            snprintf(b200::g_err, sizeof(b200::g_err), "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return B200_ECUDA;                                                                   \
+        }                                                                                        \
+    } while (0)
+
+// count every kernel launch this library makes (bench.py reports it as gpu_launches)
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
+    do {                                                                                         \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                              \
+        b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+    } while (0)
+
+// Select the device and make sure it is a Blackwell B200-class part; no CPU fallback exists.
+int use_device(int device);
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// round-half-even of a float (cvRound semantics) on the host side
+int host_round(float v);
+int host_round_d(double v);
+
+}  // namespace b200

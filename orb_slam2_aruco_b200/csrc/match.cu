@@ -1,0 +1,341 @@
+// match.cu -- B200-native ORB descriptor matching (sm_100a): 256-bit Hamming as 4 x __popcll, best /
+// second-best ratio test, 30-bin rotation-consistency histogram.
+//
+// Behavioural contract: ORB_SLAM2::ORBmatcher (reference src/ORBmatcher.cc): DescriptorDistance
+// (1651-1667), SearchByBoW(KeyFrame,Frame) (159-292) with one all-inclusive vocabulary node (== brute
+// force), ComputeThreeMaxima (1605-1646).  Match indices are bit-identical to the CPU oracle.
+//
+// The reference's loop is greedy: reference descriptor r only looks at frame descriptors that no earlier
+// r has taken.  Split:
+//   k_match_topk     warp per (frame, r): all n_frame distances, keeps the K smallest (dist<<16|idx) keys
+//                    (frame descriptors staged once per CTA in shared memory as 4 u64 planes)
+//   k_match_resolve  warp per frame: replays r = 0..n_ref-1 in order against a "taken" bitmap using the
+//                    top-K lists (exact; a list that runs dry while a match is still possible triggers a
+//                    warp-wide rescan of the whole row), then the rotation histogram filter.
+#include "common.h"
+
+namespace b200 {
+
+constexpr int kTopK = 4;
+constexpr int kMatchWarps = 8;
+constexpr int kRefPerCta = 64;
+
+__device__ __forceinline__ int hamming256(const ulonglong4 a, const ulonglong4 b) {
+    return __popcll(a.x ^ b.x) + __popcll(a.y ^ b.y) + __popcll(a.z ^ b.z) + __popcll(a.w ^ b.w);
+}
+
+// insert key into an ascending sorted 4-list
+__device__ __forceinline__ void top4_insert(uint32_t (&t)[kTopK], uint32_t key) {
+    if (key < t[3]) {
+        t[3] = key;
+        if (t[3] < t[2]) { uint32_t s = t[2]; t[2] = t[3]; t[3] = s; }
+        if (t[2] < t[1]) { uint32_t s = t[1]; t[1] = t[2]; t[2] = s; }
+        if (t[1] < t[0]) { uint32_t s = t[0]; t[0] = t[1]; t[1] = s; }
+    }
+}
+
+__global__ void __launch_bounds__(kMatchWarps * 32)
+k_match_topk(const ulonglong4* __restrict__ ref_desc, int n_ref,
+             const ulonglong4* __restrict__ frame_desc, const int* __restrict__ n_frame, int frame_cap,
+             uint32_t* __restrict__ topk) {
+    extern __shared__ unsigned long long s_planes[];      // [4][nf_pad]
+    const int f = blockIdx.y;
+    const int nf = min(n_frame[f], frame_cap);
+    const int nf_pad = (frame_cap + 31) & ~31;
+    const ulonglong4* fd = frame_desc + (long long)f * frame_cap;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const ulonglong4 d = fd[i];
+        s_planes[i] = d.x; s_planes[nf_pad + i] = d.y; s_planes[2 * nf_pad + i] = d.z; s_planes[3 * nf_pad + i] = d.w;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r_end = min(n_ref, (int)(blockIdx.x + 1) * kRefPerCta);
+    for (int r = blockIdx.x * kRefPerCta + warp; r < r_end; r += kMatchWarps) {
+        const ulonglong4 q = ref_desc[r];
+        uint32_t t[kTopK] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        for (int i = lane; i < nf; i += 32) {
+            const int d = __popcll(q.x ^ s_planes[i]) + __popcll(q.y ^ s_planes[nf_pad + i]) +
+                          __popcll(q.z ^ s_planes[2 * nf_pad + i]) + __popcll(q.w ^ s_planes[3 * nf_pad + i]);
+            top4_insert(t, ((uint32_t)d << 16) | (uint32_t)i);
+        }
+        // K rounds of warp arg-min over the lanes' list heads
+        uint32_t* out = topk + ((long long)f * n_ref + r) * kTopK;
+#pragma unroll
+        for (int k = 0; k < kTopK; k++) {
+            uint32_t m = t[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (t[0] == m && m != 0xffffffffu) { t[0] = t[1]; t[1] = t[2]; t[2] = t[3]; t[3] = 0xffffffffu; }   // keys are unique
+            if (lane == 0) out[k] = m;
+        }
+    }
+}
+
+// ComputeThreeMaxima (ORBmatcher.cc:1605-1646)
+__device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+}
+
+constexpr int kHistoLen = 30;      // HISTO_LENGTH, ORBmatcher.cc:39
+
+__global__ void __launch_bounds__(32)
+k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict__ ref_angle, int n_ref,
+                const ulonglong4* __restrict__ frame_desc, const float* __restrict__ frame_angle,
+                const int* __restrict__ n_frame, int frame_cap, const uint32_t* __restrict__ topk,
+                float ratio, int th_low, int check_ori, float histo_factor,
+                int* __restrict__ match_ref_idx, int* __restrict__ n_matches) {
+    extern __shared__ unsigned int s_mem[];
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int nf = min(n_frame[f], frame_cap);
+    unsigned int* taken = s_mem;                               // bitmap over frame keypoints
+    const int words = (frame_cap + 31) / 32;
+    unsigned char* bin_of = reinterpret_cast<unsigned char*>(s_mem + words);   // rotation bin of each matched frame keypoint
+    __shared__ int histo[kHistoLen];
+    for (int i = lane; i < words; i += 32) taken[i] = 0;
+    if (lane < kHistoLen) histo[lane] = 0;
+    int* mout = match_ref_idx + (long long)f * frame_cap;
+    for (int i = lane; i < frame_cap; i += 32) mout[i] = -1;
+    __syncwarp();
+    const ulonglong4* fd = frame_desc + (long long)f * frame_cap;
+    const float* fa = frame_angle + (long long)f * frame_cap;
+    int nm = 0;
+    for (int r = 0; r < n_ref; r++) {
+        const uint32_t* tk = topk + ((long long)f * n_ref + r) * kTopK;
+        // first two untaken entries of the sorted list
+        uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu, last = 0xffffffffu;
+        int found = 0;
+#pragma unroll
+        for (int k = 0; k < kTopK; k++) {
+            const uint32_t key = tk[k];
+            if (key == 0xffffffffu) continue;
+            last = key;
+            const int idx = key & 0xffff;
+            if (!((taken[idx >> 5] >> (idx & 31)) & 1u)) {
+                if (found == 0) b1 = key; else if (found == 1) b2 = key;
+                found++;
+            }
+        }
+        const int list_len = min(nf, kTopK);
+        bool exact = true;
+        if (nf > kTopK) {
+            // the list may hide untaken candidates beyond its end
+            if (found == 0) exact = ((int)(last >> 16) > th_low);          // everything hidden is >= last > th_low: no match possible
+            else if (found == 1) exact = ((int)(b1 >> 16) > th_low);       // best is known; second only matters if best can match
+        }
+        (void)list_len;
+        if (!exact) {                                                       // rare: rescan the whole row, all lanes
+            const ulonglong4 q = ref_desc[r];
+            uint32_t l1 = 0xffffffffu, l2 = 0xffffffffu;
+            for (int i = lane; i < nf; i += 32) {
+                if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
+                const uint32_t key = ((uint32_t)hamming256(q, fd[i]) << 16) | (uint32_t)i;
+                if (key < l1) { l2 = l1; l1 = key; } else if (key < l2) l2 = key;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint32_t o1 = __shfl_xor_sync(0xffffffffu, l1, o), o2 = __shfl_xor_sync(0xffffffffu, l2, o);
+                const uint32_t lo = min(l1, o1), hi = max(l1, o1);
+                l2 = min(hi, min(l2, o2));
+                l1 = lo;
+            }
+            b1 = l1; b2 = l2;
+        }
+        const int d1 = b1 == 0xffffffffu ? 256 : (int)(b1 >> 16);
+        const int d2 = b2 == 0xffffffffu ? 256 : (int)(b2 >> 16);
+        if (d1 <= th_low && (float)d1 < __fmul_rn(ratio, (float)d2)) {
+            const int idx = b1 & 0xffff;
+            if (lane == 0) {
+                taken[idx >> 5] |= 1u << (idx & 31);
+                mout[idx] = r;
+                if (check_ori) {
+                    float rot = __fsub_rn(ref_angle[r], fa[idx]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, histo_factor));
+                    if (bin == kHistoLen) bin = 0;
+                    bin = max(0, min(bin, kHistoLen - 1));   // the reference asserts this range
+                    bin_of[idx] = (unsigned char)bin;
+                    histo[bin]++;
+                }
+            }
+            nm++;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(histo, kHistoLen, i1, i2, i3);
+        int removed = 0;
+        for (int i = lane; i < nf; i += 32) {
+            if (mout[i] >= 0) {
+                const int b = bin_of[i];
+                if (b != i1 && b != i2 && b != i3) { mout[i] = -1; removed++; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nm -= removed;
+    }
+    if (lane == 0) n_matches[f] = nm;
+}
+
+__global__ void k_hamming_matrix(const ulonglong4* __restrict__ a, int na, const ulonglong4* __restrict__ b, int nb, int* __restrict__ dist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j < nb && i < na) dist[(long long)i * nb + j] = hamming256(a[i], b[j]);
+}
+
+// candidate-list core: warp per query
+__global__ void __launch_bounds__(256)
+k_match_candidates(const ulonglong4* __restrict__ qd, int nq, const ulonglong4* __restrict__ td,
+                   const int* __restrict__ ofs, const int* __restrict__ cand,
+                   int* __restrict__ best_idx, int* __restrict__ best_dist, int* __restrict__ second_dist) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const ulonglong4 d = qd[q];
+    const int beg = ofs[q], end = ofs[q + 1];
+    // key = dist << 20 | position in the list: first minimum in list order wins, like the reference's strict '<'
+    uint32_t l1 = 0xffffffffu, l2 = 0xffffffffu;
+    for (int i = beg + lane; i < end; i += 32) {
+        const uint32_t key = ((uint32_t)hamming256(d, td[cand[i]]) << 20) | (uint32_t)(i - beg);
+        if (key < l1) { l2 = l1; l1 = key; } else if (key < l2) l2 = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, l1, o), o2 = __shfl_xor_sync(0xffffffffu, l2, o);
+        const uint32_t lo = min(l1, o1), hi = max(l1, o1);
+        l2 = min(hi, min(l2, o2));
+        l1 = lo;
+    }
+    if (lane == 0) {
+        best_idx[q] = l1 == 0xffffffffu ? -1 : cand[beg + (l1 & 0xfffff)];
+        best_dist[q] = l1 == 0xffffffffu ? 256 : (int)(l1 >> 20);
+        second_dist[q] = l2 == 0xffffffffu ? 256 : (int)(l2 >> 20);
+    }
+}
+
+struct MatchScratch { uint32_t* topk; size_t cap; int device; };
+static thread_local MatchScratch g_ms = {nullptr, 0, -1};
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_match_bf(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
+                  const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
+                  float ratio, int th_low, int check_ori, float histo_factor,
+                  int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream) {
+    if (n_batch < 0 || n_ref < 0 || frame_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
+    if (frame_cap > 65535) return fail(B200_ECAPACITY, "frame_cap above %s", "65535");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n_batch == 0) return B200_OK;
+    if (!n_frame || !match_ref_idx || !n_matches || (n_ref > 0 && (!ref_desc || !ref_angle)) || (frame_cap > 0 && (!frame_desc || !frame_angle)))
+        return fail(B200_EINVAL, "null %s", "pointer");
+    if (((uintptr_t)ref_desc | (uintptr_t)frame_desc) & 31) return fail(B200_EINVAL, "descriptor arrays must be %s", "32-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t need = std::max<size_t>((size_t)n_batch * std::max(n_ref, 1) * kTopK * 4, 16);
+    if (g_ms.device != device || g_ms.cap < need) {
+        if (g_ms.topk) cudaFree(g_ms.topk);
+        g_ms.topk = nullptr; g_ms.cap = 0;
+        B200_CUDA(cudaMalloc((void**)&g_ms.topk, need));
+        g_ms.cap = need; g_ms.device = device;
+    }
+    const int nf_pad = (frame_cap + 31) & ~31;
+    if (n_ref > 0 && frame_cap > 0) {
+        const size_t smem = (size_t)4 * nf_pad * 8;
+        if (smem > 200 * 1024) return fail(B200_ECAPACITY, "frame_cap too large for the %s", "shared-memory descriptor planes");
+        B200_CUDA(cudaFuncSetAttribute(k_match_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((n_ref + kRefPerCta - 1) / kRefPerCta, n_batch);
+        B200_LAUNCH(k_match_topk, grid, kMatchWarps * 32, smem, st, (const ulonglong4*)ref_desc, n_ref, (const ulonglong4*)frame_desc,
+                    n_frame, frame_cap, g_ms.topk);
+    }
+    const size_t smem2 = (size_t)((frame_cap + 31) / 32) * 4 + (size_t)frame_cap + 16;
+    B200_CUDA(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem2, 1024)));
+    B200_LAUNCH(k_match_resolve, n_batch, 32, smem2, st, (const ulonglong4*)ref_desc, ref_angle, n_ref, (const ulonglong4*)frame_desc, frame_angle,
+                n_frame, frame_cap, g_ms.topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { B200_CUDA(cudaMalloc(&p, std::max<size_t>(n, 32))); return B200_OK; }
+    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; if (n) B200_CUDA(cudaMemcpy(p, h, n, cudaMemcpyHostToDevice)); return B200_OK; }
+};
+}
+
+int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
+                       const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
+                       float ratio, int th_low, int check_ori, float histo_factor,
+                       int32_t* match_ref_idx, int32_t* n_matches, int device) {
+    if (n_batch < 0 || n_ref < 0 || frame_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n_batch == 0) return B200_OK;
+    DevBuf rd, ra, fd, fa, nf, mi, nm;
+    if ((rc = rd.upload(ref_desc, (size_t)n_ref * 32)) || (rc = ra.upload(ref_angle, (size_t)n_ref * 4)) ||
+        (rc = fd.upload(frame_desc, (size_t)n_batch * frame_cap * 32)) || (rc = fa.upload(frame_angle, (size_t)n_batch * frame_cap * 4)) ||
+        (rc = nf.upload(n_frame, (size_t)n_batch * 4)) || (rc = mi.alloc((size_t)n_batch * frame_cap * 4)) || (rc = nm.alloc((size_t)n_batch * 4)))
+        return rc;
+    if ((rc = b200_match_bf((const uint8_t*)rd.p, (const float*)ra.p, n_ref, (const uint8_t*)fd.p, (const float*)fa.p, (const int32_t*)nf.p,
+                            n_batch, frame_cap, ratio, th_low, check_ori, histo_factor, (int32_t*)mi.p, (int32_t*)nm.p, device, nullptr)))
+        return rc;
+    B200_CUDA(cudaDeviceSynchronize());
+    if (frame_cap) B200_CUDA(cudaMemcpy(match_ref_idx, mi.p, (size_t)n_batch * frame_cap * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(n_matches, nm.p, (size_t)n_batch * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device) {
+    if (na < 0 || nb < 0) return fail(B200_EINVAL, "negative %s", "size");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (na == 0 || nb == 0) return B200_OK;
+    if (!a || !b || !dist) return fail(B200_EINVAL, "null %s", "pointer");
+    DevBuf da, db, dd;
+    if ((rc = da.upload(a, (size_t)na * 32)) || (rc = db.upload(b, (size_t)nb * 32)) || (rc = dd.alloc((size_t)na * nb * 4))) return rc;
+    dim3 grid((nb + 255) / 256, na);
+    B200_LAUNCH(k_hamming_matrix, grid, 256, 0, 0, (const ulonglong4*)da.p, na, (const ulonglong4*)db.p, nb, (int*)dd.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(dist, dd.p, (size_t)na * nb * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_match_candidates_host(const uint8_t* query_desc, int nq, const uint8_t* train_desc, int nt,
+                               const int32_t* cand_ofs, const int32_t* cand, int32_t* out_best_idx,
+                               int32_t* out_best_dist, int32_t* out_second_dist, int device) {
+    if (nq < 0 || nt < 0) return fail(B200_EINVAL, "negative %s", "size");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (nq == 0) return B200_OK;
+    if (!query_desc || !cand_ofs || !out_best_idx || !out_best_dist || !out_second_dist) return fail(B200_EINVAL, "null %s", "pointer");
+    const int total = cand_ofs[nq];
+    for (int q = 0; q < nq; q++) if (cand_ofs[q + 1] < cand_ofs[q] || cand_ofs[q + 1] - cand_ofs[q] >= (1 << 20)) return fail(B200_EINVAL, "bad %s", "candidate offsets");
+    for (int i = 0; i < total; i++) if (cand[i] < 0 || cand[i] >= nt) return fail(B200_EINVAL, "candidate index out of %s", "range");
+    DevBuf dq, dt, dofs, dc, o1, o2, o3;
+    if ((rc = dq.upload(query_desc, (size_t)nq * 32)) || (rc = dt.upload(train_desc, (size_t)nt * 32)) || (rc = dofs.upload(cand_ofs, (size_t)(nq + 1) * 4)) ||
+        (rc = dc.upload(cand, (size_t)total * 4)) || (rc = o1.alloc((size_t)nq * 4)) || (rc = o2.alloc((size_t)nq * 4)) || (rc = o3.alloc((size_t)nq * 4)))
+        return rc;
+    B200_LAUNCH(k_match_candidates, (nq * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)dq.p, nq, (const ulonglong4*)dt.p, (const int*)dofs.p, (const int*)dc.p,
+                (int*)o1.p, (int*)o2.p, (int*)o3.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(out_best_idx, o1.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(out_best_dist, o2.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(out_second_dist, o3.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+}  // extern "C"

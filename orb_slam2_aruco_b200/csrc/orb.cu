@@ -1,0 +1,1162 @@
+// orb.cu -- B200-native ORB extractor (sm_100a): image pyramid, per-cell FAST-9/16 with NMS and threshold
+// fallback, quadtree keypoint distribution, intensity-centroid orientation, 7x7 Gaussian, 256-bit rBRIEF.
+//
+// Behavioural contract: ORB_SLAM2::ORBextractor (reference src/ORBextractor.cc:410-1132); results are
+// bit-identical to the CPU oracle (oracle/orb_oracle.cpp == the reference source on the cv shim).
+// All arithmetic is integer except three float32 spots that use explicitly rounded intrinsics
+// (no FMA contraction): fastAtan2, the rBRIEF rotation and the final pt*scale.
+//
+// Pipeline for a batch of n frames (everything stays in HBM/L2, 10 launches):
+//   k_pyramid x (nlevels-1)   level l from level l-1, fixed-point bilinear (ORBextractor.cc:1107-1132)
+//   k_fast                    one CTA per (cell, frame): u8 tile in smem, score of every pixel, 3x3 NMS,
+//                             ini/min threshold fallback, raster-ordered compaction (ORBextractor.cc:765-829)
+//   k_quadtree                one warp per (frame, level): DistributeOctTree (ORBextractor.cc:539-763)
+//   k_describe                one warp per keypoint: IC_Angle, 7x7 Gaussian on a 43x43 patch, rBRIEF
+//                             (ORBextractor.cc:77-147,1085-1101)
+#include "common.h"
+#include <math.h>
+#include <algorithm>
+
+namespace b200 {
+
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 19;          // EDGE_THRESHOLD, ORBextractor.cc:73
+constexpr int kMinBorder = 16;     // EDGE_THRESHOLD-3, ORBextractor.cc:771
+constexpr int kHalfPatch = 15;
+constexpr int kMaxRoi = 72;        // largest FAST cell ROI side handled (cells are 30..59 px + 6)
+
+struct LevelGeom {
+    int w, h;                 // level image size
+    int pitch;                // row pitch in the pyramid buffer (level > 0)
+    long long offset;         // byte offset of the level inside a frame's pyramid block (level > 0)
+    int quota;                // mnFeaturesPerLevel
+    int ncols, nrows, wcell, hcell;
+    int cell_base, ncells;    // cells of this level inside the frame's cell list
+    long long slot_base;      // first candidate slot of this level (entries) inside the frame's slot block
+    int nini; float hx;       // DistributeOctTree initial nodes
+    int kp_cap, kp_base;      // result capacity of this level, base inside the frame's level-result block
+    int xtab, ytab;           // offsets into the resize tables
+    float scale;              // mvScaleFactor[l]
+    float size;               // keypoint size = (int)(31*scale)
+};
+
+struct OrbGeom {
+    int nlevels;
+    int total_cells;
+    long long slots_per_frame;
+    long long pyr_frame_stride;
+    int res_per_frame;        // sum of kp_cap
+    int ini_th, min_th;
+    LevelGeom L[kMaxLevels];
+};
+
+struct CellDesc {             // one FAST call of the reference (ORBextractor.cc:789-829)
+    short level, pad;
+    short x0, y0;             // ROI origin in level coordinates
+    short rw, rh;             // ROI size (interior = ROI minus 3 px on every side)
+    short sx, sy;             // shift added to ROI-relative keypoints: j*wCell, i*hCell
+    int slot;                 // first candidate slot (relative to the frame's slot block)
+    int cap;                  // slot capacity
+};
+
+struct ResizeEntry { int ofs; short c0, c1; };
+
+__device__ signed char g_pattern[256 * 4];       // rBRIEF pairs, transposed on upload: [k(8)][coord(4)][byte i(32)] (lane-indexed => global, not constant)
+__constant__ int c_umax[16];
+
+// ------------------------------------------------------------------------------------------------
+// K1: pyramid level from the previous level.  cv::resize INTER_LINEAR u8 fixed point (SURVEY A-1).
+// One thread -> 4 horizontally adjacent output pixels (one 32-bit store; pitch is a multiple of 16).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pyramid(const uint8_t* __restrict__ src0, long long src_row_stride, long long src_frame_stride,
+          uint8_t* __restrict__ dst0, int dst_pitch, long long dst_frame_stride,
+          int sw, int sh, int dw, int dh,
+          const ResizeEntry* __restrict__ xt, const ResizeEntry* __restrict__ yt) {
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int f = blockIdx.z;
+    if (x4 >= dw || y >= dh) return;
+    const ResizeEntry ye = yt[y];
+    const uint8_t* r0 = src0 + (long long)f * src_frame_stride + (long long)ye.ofs * src_row_stride;
+    const uint8_t* r1 = src0 + (long long)f * src_frame_stride + (long long)min(ye.ofs + 1, sh - 1) * src_row_stride;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int x = x4 + i;
+        if (x < dw) {
+            const ResizeEntry xe = xt[x];
+            int sx1 = min(xe.ofs + 1, sw - 1);
+            int h0 = r0[xe.ofs] * xe.c0 + r0[sx1] * xe.c1;
+            int h1 = r1[xe.ofs] * xe.c0 + r1[sx1] * xe.c1;
+            int v = (((ye.c0 * (h0 >> 4)) >> 16) + ((ye.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)(v & 0xff) << (8 * i);
+        }
+    }
+    uint8_t* d = dst0 + (long long)f * dst_frame_stride + (long long)y * dst_pitch + x4;
+    *reinterpret_cast<uint32_t*>(d) = packed;     // pitch >= align16(dw): the tail bytes are padding
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: FAST-9/16 score, NMS, threshold fallback, ordered compaction.  One CTA per (cell, frame).
+// score(p) = max over the 16 arcs of 9 contiguous circle pixels of max(min d, -max d) - 1, d = I(p)-I(circle)
+// (the largest threshold for which p is still a corner; SURVEY A-3).  Packed s16x2 min3/max3 (DPX) evaluate
+// all 16 arcs with 2 x 22 instructions.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int v) {
+    // circle in the order of SURVEY A-3: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+    int d[16];
+    d[0]  = v - p[ 3 * pitch + 0]; d[1]  = v - p[ 3 * pitch + 1]; d[2]  = v - p[ 2 * pitch + 2]; d[3]  = v - p[ 1 * pitch + 3];
+    d[4]  = v - p[ 0 * pitch + 3]; d[5]  = v - p[-1 * pitch + 3]; d[6]  = v - p[-2 * pitch + 2]; d[7]  = v - p[-3 * pitch + 1];
+    d[8]  = v - p[-3 * pitch + 0]; d[9]  = v - p[-3 * pitch - 1]; d[10] = v - p[-2 * pitch - 2]; d[11] = v - p[-1 * pitch - 3];
+    d[12] = v - p[ 0 * pitch - 3]; d[13] = v - p[ 1 * pitch - 3]; d[14] = v - p[ 2 * pitch - 2]; d[15] = v - p[ 3 * pitch - 1];
+    unsigned e[16];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        e[j] = ((unsigned)d[j] & 0xffffu) | ((unsigned)d[j + 8] << 16);      // lo = position j, hi = position j+8
+        e[j + 8] = __byte_perm(e[j], 0, 0x1032);                             // halves swapped
+    }
+    unsigned tmin[14], tmax[14];
+#pragma unroll
+    for (int j = 0; j < 14; j++) {
+        tmin[j] = __vimin3_s16x2(e[j], e[j + 1], e[j + 2]);
+        tmax[j] = __vimax3_s16x2(e[j], e[j + 1], e[j + 2]);
+    }
+    unsigned wmin[8], wmax[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        wmin[j] = __vimin3_s16x2(tmin[j], tmin[j + 3], tmin[j + 6]);       // min of d over positions j..j+8 (lo), j+8..j+16 (hi)
+        wmax[j] = __vimax3_s16x2(tmax[j], tmax[j + 3], tmax[j + 6]);
+    }
+    unsigned a = __vimax3_s16x2(wmin[0], wmin[1], wmin[2]);
+    unsigned b = __vimax3_s16x2(wmin[3], wmin[4], wmin[5]);
+    a = __vimax3_s16x2(a, b, __vmaxs2(wmin[6], wmin[7]));
+    unsigned c = __vimin3_s16x2(wmax[0], wmax[1], wmax[2]);
+    unsigned e2 = __vimin3_s16x2(wmax[3], wmax[4], wmax[5]);
+    c = __vimin3_s16x2(c, e2, __vmins2(wmax[6], wmax[7]));
+    int maxmin = max((int)(short)(a & 0xffff), (int)(short)(a >> 16));
+    int minmax = min((int)(short)(c & 0xffff), (int)(short)(c >> 16));
+    return max(maxmin, -minmax) - 1;
+}
+
+constexpr int kFastThreads = 128;
+
+__global__ void __launch_bounds__(kFastThreads)
+k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
+       const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g,
+       const CellDesc* __restrict__ cells, uint32_t* __restrict__ slots, int* __restrict__ cellcnt) {
+    __shared__ uint8_t tile[kMaxRoi][kMaxRoi + 8];
+    __shared__ uint8_t score[kMaxRoi][kMaxRoi + 8];
+    __shared__ int row_cnt20[kMaxRoi], row_cnt7[kMaxRoi];
+    __shared__ int s_total20;
+
+    const CellDesc cd = cells[blockIdx.x];
+    const int f = blockIdx.y;
+    const LevelGeom& lg = g.L[cd.level];
+    const uint8_t* base;
+    long long pitch;
+    if (cd.level == 0) { base = img0 + (long long)f * img_frame_stride; pitch = img_row_stride; }
+    else { base = pyr + (long long)f * g.pyr_frame_stride + lg.offset; pitch = lg.pitch; }
+    base += (long long)cd.y0 * pitch + cd.x0;
+
+    const int rw = cd.rw, rh = cd.rh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // stage the ROI (coalesced along rows; one row per warp iteration) and clear the score tile
+    for (int y = warp; y < rh; y += kFastThreads / 32)
+        for (int x = lane; x < rw; x += 32) {
+            tile[y][x] = base[(long long)y * pitch + x];
+            score[y][x] = 0;
+        }
+    __syncthreads();
+
+    const int minth = g.min_th;
+    const int iw = rw - 6, ih = rh - 6;               // interior
+    for (int y = warp; y < ih; y += kFastThreads / 32) {
+        for (int x0 = 0; x0 < iw; x0 += 32) {
+            const int x = x0 + lane;
+            bool act = x < iw;
+            const uint8_t* p = &tile[y + 3][min(x, iw - 1) + 3];
+            const int v = p[0];
+            // quick reject: every arc of 9 contains one pixel of each opposite pair
+            if (act) {
+                const int lo = v - minth, hi = v + minth;
+                int a0 = p[3 * (kMaxRoi + 8)], a8 = p[-3 * (kMaxRoi + 8)], a4 = p[3], a12 = p[-3];
+                act = ((a0 > hi) | (a8 > hi) | (a0 < lo) | (a8 < lo)) & ((a4 > hi) | (a12 > hi) | (a4 < lo) | (a12 < lo));
+            }
+            if (__any_sync(0xffffffffu, act)) {
+                int s = fast_score(p, kMaxRoi + 8, v);
+                if (act && s >= minth) score[y + 3][x + 3] = (uint8_t)s;
+            }
+        }
+    }
+    __syncthreads();
+
+    // NMS (strict > over the 8 neighbours inside this ROI; outside counts 0) + per-row counts
+    const int inith = g.ini_th;
+    for (int y = warp; y < ih; y += kFastThreads / 32) {
+        int c20 = 0, c7 = 0;
+        for (int x0 = 0; x0 < iw; x0 += 32) {
+            const int x = x0 + lane;
+            bool keep = false; int s = 0;
+            if (x < iw) {
+                const uint8_t* q = &score[y + 3][x + 3];
+                s = q[0];
+                if (s) {
+                    const int P = kMaxRoi + 8;
+                    keep = s > q[-1] && s > q[1] && s > q[-P - 1] && s > q[-P] && s > q[-P + 1] && s > q[P - 1] && s > q[P] && s > q[P + 1];
+                }
+            }
+            c7 += __popc(__ballot_sync(0xffffffffu, keep));
+            c20 += __popc(__ballot_sync(0xffffffffu, keep && s >= inith));
+        }
+        if (lane == 0) { row_cnt20[y] = c20; row_cnt7[y] = c7; }
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan over rows (<= 66 rows)
+        int run20 = 0, run7 = 0;
+        for (int y0 = 0; y0 < ih; y0 += 32) {
+            int y = y0 + lane;
+            int a = y < ih ? row_cnt20[y] : 0, b = y < ih ? row_cnt7[y] : 0;
+            int sa = a, sb = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
+                if (lane >= o) { sa += ta; sb += tb; }
+            }
+            if (y < ih) { row_cnt20[y] = run20 + sa - a; row_cnt7[y] = run7 + sb - b; }
+            run20 += __shfl_sync(0xffffffffu, sa, 31);
+            run7 += __shfl_sync(0xffffffffu, sb, 31);
+        }
+        if (lane == 0) {
+            s_total20 = run20;
+            cellcnt[(long long)f * g.total_cells + blockIdx.x] = run20 > 0 ? run20 : run7;
+        }
+    }
+    __syncthreads();
+    const bool use20 = s_total20 > 0;               // fallback to minThFAST only when the cell is empty at iniThFAST
+    const int th = use20 ? inith : minth;
+    uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
+    for (int y = warp; y < ih; y += kFastThreads / 32) {
+        int ofs = use20 ? row_cnt20[y] : row_cnt7[y];
+        for (int x0 = 0; x0 < iw; x0 += 32) {
+            const int x = x0 + lane;
+            bool keep = false; int s = 0;
+            if (x < iw) {
+                const uint8_t* q = &score[y + 3][x + 3];
+                s = q[0];
+                if (s >= th) {
+                    const int P = kMaxRoi + 8;
+                    keep = s > q[-1] && s > q[1] && s > q[-P - 1] && s > q[-P] && s > q[-P + 1] && s > q[P - 1] && s > q[P] && s > q[P + 1];
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                int pos = ofs + __popc(m & ((1u << lane) - 1));
+                // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
+                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)s << 24);
+            }
+            ofs += __popc(m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: DistributeOctTree.  One warp per (frame, level).  The list logic runs redundantly (warp-uniform) on all
+// lanes; stable 4-way partitions, the initial gather and the final per-node arg-max are lane-parallel.
+// Keys are packed u32 (x | y<<12 | score<<24) living in two global scratch buffers; a node's keys are a
+// contiguous range in one of them (children are written to the other one, so no copy-back).
+// Canonical tie-break of the size-sorted phase (ORBextractor.cc:684): (count, creation sequence).
+// ------------------------------------------------------------------------------------------------
+struct QtNode {
+    short x0, x1, y0, y1;
+    int beg, end;
+    short prev, next;
+    int seq;
+    unsigned char no_more, buf, pad0, pad1;
+};
+
+constexpr int kQtWarps = 4;
+
+struct QtWarp {          // per-warp view of its shared memory
+    QtNode* pool; short* freelist; int nfree;
+    int* big_cnt; int* big_seq; short* big_id;      // children with > 1 key created in the current round
+    int* prv_cnt; int* prv_seq; short* prv_id;      // the previous round's list (the one being sorted)
+    short* order;
+    int head, tail, size, seq;
+};
+
+__device__ __forceinline__ int qt_alloc(QtWarp& w) { return w.freelist[--w.nfree]; }
+__device__ __forceinline__ void qt_free(QtWarp& w, int id, int lane) { if (lane == 0) w.freelist[w.nfree] = (short)id; w.nfree++; __syncwarp(); }
+
+__device__ __forceinline__ void qt_push_front(QtWarp& w, int id, int lane) {
+    if (lane == 0) {
+        w.pool[id].prev = -1; w.pool[id].next = (short)w.head;
+        if (w.head >= 0) w.pool[w.head].prev = (short)id;
+    }
+    if (w.head < 0) w.tail = id;
+    w.head = id; w.size++;
+    __syncwarp();
+}
+__device__ __forceinline__ void qt_push_back(QtWarp& w, int id, int lane) {
+    if (lane == 0) {
+        w.pool[id].next = -1; w.pool[id].prev = (short)w.tail;
+        if (w.tail >= 0) w.pool[w.tail].next = (short)id;
+    }
+    if (w.tail < 0) w.head = id;
+    w.tail = id; w.size++;
+    __syncwarp();
+}
+__device__ __forceinline__ int qt_erase(QtWarp& w, int id, int lane) {   // returns the successor
+    const int p = w.pool[id].prev, n = w.pool[id].next;
+    __syncwarp();
+    if (lane == 0) {
+        if (p >= 0) w.pool[p].next = (short)n;
+        if (n >= 0) w.pool[n].prev = (short)p;
+    }
+    if (p < 0) w.head = n;
+    if (n < 0) w.tail = p;
+    w.size--;
+    qt_free(w, id, lane);
+    return n;
+}
+
+// DivideNode (ORBextractor.cc:481-537): stable 4-way partition of the node's key range into the other buffer.
+// Returns the four child counts (warp-uniform) and fills child boxes.
+__device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint32_t* bufB, int lane,
+                                          int cnt[4], int& mx, int& my) {
+    const int halfX = (nd.x1 - nd.x0 + 1) >> 1;      // ceil((float)(UR.x-UL.x)/2) for non-negative ints
+    const int halfY = (nd.y1 - nd.y0 + 1) >> 1;
+    mx = nd.x0 + halfX; my = nd.y0 + halfY;
+    const uint32_t* src = nd.buf ? bufB : bufA;
+    uint32_t* dst = nd.buf ? bufA : bufB;
+    const int n = nd.end - nd.beg;
+    cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+    if (n <= 32) {                                    // common case: one register-resident pass
+        const bool valid = lane < n;
+        const uint32_t key = valid ? src[nd.beg + lane] : 0u;
+        const int q = valid ? (((int)(key & 0xfff) >= mx) + 2 * ((int)((key >> 12) & 0xfff) >= my)) : 4;
+        unsigned m[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, q == k); cnt[k] = __popc(m[k]); }
+        if (valid) {
+            int ofs = nd.beg;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { if (k < q) ofs += cnt[k]; }
+            unsigned mm = q == 0 ? m[0] : q == 1 ? m[1] : q == 2 ? m[2] : m[3];
+            dst[ofs + __popc(mm & ((1u << lane) - 1))] = key;
+        }
+    } else {
+        for (int i0 = nd.beg; i0 < nd.end; i0 += 32) {           // pass 1: counts
+            const int i = i0 + lane;
+            const bool valid = i < nd.end;
+            const uint32_t key = valid ? src[i] : 0u;
+            const int q = valid ? (((int)(key & 0xfff) >= mx) + 2 * ((int)((key >> 12) & 0xfff) >= my)) : 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cnt[k] += __popc(__ballot_sync(0xffffffffu, q == k));
+        }
+        int run[4];
+        run[0] = nd.beg; run[1] = run[0] + cnt[0]; run[2] = run[1] + cnt[1]; run[3] = run[2] + cnt[2];
+        for (int i0 = nd.beg; i0 < nd.end; i0 += 32) {           // pass 2: stable scatter
+            const int i = i0 + lane;
+            const bool valid = i < nd.end;
+            const uint32_t key = valid ? src[i] : 0u;
+            const int q = valid ? (((int)(key & 0xfff) >= mx) + 2 * ((int)((key >> 12) & 0xfff) >= my)) : 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                unsigned m = __ballot_sync(0xffffffffu, q == k);
+                if (q == k) dst[run[k] + __popc(m & ((1u << lane) - 1))] = key;
+                run[k] += __popc(m);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// create the non-empty children of `nd` at the list front in the order n1..n4 (ORBextractor.cc:606-665);
+// children with more than one key are appended to the `big` list.  Returns how many big children were added.
+__device__ __forceinline__ int qt_add_children(QtWarp& w, const QtNode nd, const int cnt[4], int mx, int my, int lane, int& nbig) {
+    int added = 0;
+    int beg = nd.beg;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int k = cnt[q];
+        if (k > 0) {
+            const int id = qt_alloc(w);
+            if (lane == 0) {
+                QtNode c;
+                c.x0 = (q & 1) ? (short)mx : nd.x0; c.x1 = (q & 1) ? nd.x1 : (short)mx;
+                c.y0 = (q & 2) ? (short)my : nd.y0; c.y1 = (q & 2) ? nd.y1 : (short)my;
+                c.beg = beg; c.end = beg + k; c.prev = c.next = -1; c.seq = w.seq;
+                c.no_more = (k == 1); c.buf = nd.buf ^ 1; c.pad0 = c.pad1 = 0;
+                w.pool[id] = c;
+                if (k > 1) { w.big_cnt[nbig] = k; w.big_seq[nbig] = w.seq; w.big_id[nbig] = (short)id; }
+            }
+            __syncwarp();
+            qt_push_front(w, id, lane);
+            w.seq++;
+            if (k > 1) { nbig++; added++; }
+        }
+        beg += k;
+    }
+    return added;
+}
+
+__global__ void __launch_bounds__(kQtWarps * 32)
+k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells,
+           const uint32_t* __restrict__ slots, const int* __restrict__ cellcnt,
+           uint32_t* __restrict__ keysA, uint32_t* __restrict__ keysB,
+           uint32_t* __restrict__ lvlres, int* __restrict__ lvlcnt, int nframes, int pool_cap, int* __restrict__ errflag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int prob = blockIdx.x * kQtWarps + warp;
+    if (prob >= nframes * g.nlevels) return;
+    // heavy levels first: problem index -> (level, frame) with the level as the slow index
+    const int level = prob / nframes, f = prob % nframes;
+    const LevelGeom& lg = g.L[level];
+
+    // carve this warp's shared memory
+    const size_t per_warp = (size_t)pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64;
+    unsigned char* sm = smem_raw + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    QtWarp w;
+    w.pool = reinterpret_cast<QtNode*>(sm); sm += (size_t)pool_cap * sizeof(QtNode);
+    w.big_cnt = reinterpret_cast<int*>(sm); sm += (size_t)pool_cap * 4;
+    w.big_seq = reinterpret_cast<int*>(sm); sm += (size_t)pool_cap * 4;
+    w.prv_cnt = reinterpret_cast<int*>(sm); sm += (size_t)pool_cap * 4;
+    w.prv_seq = reinterpret_cast<int*>(sm); sm += (size_t)pool_cap * 4;
+    w.freelist = reinterpret_cast<short*>(sm); sm += (size_t)pool_cap * 2;
+    w.big_id = reinterpret_cast<short*>(sm); sm += (size_t)pool_cap * 2;
+    w.prv_id = reinterpret_cast<short*>(sm); sm += (size_t)pool_cap * 2;
+    w.order = reinterpret_cast<short*>(sm);
+    w.head = w.tail = -1; w.size = 0; w.seq = 0; w.nfree = pool_cap;
+    for (int i = lane; i < pool_cap; i += 32) w.freelist[i] = (short)(pool_cap - 1 - i);
+    __syncwarp();
+
+    uint32_t* A = keysA + (long long)f * g.slots_per_frame + lg.slot_base;
+    uint32_t* B = keysB + (long long)f * g.slots_per_frame + lg.slot_base;
+    const uint32_t* S = slots + (long long)f * g.slots_per_frame;
+    const int* cc = cellcnt + (long long)f * g.total_cells + lg.cell_base;
+    const CellDesc* cl = cells + lg.cell_base;
+    const int N = lg.quota;
+    int* out_cnt = lvlcnt + (long long)f * g.nlevels + level;
+    uint32_t* out = lvlres + (long long)f * g.res_per_frame + lg.kp_base;
+
+    // ---- initial nodes (ORBextractor.cc:543-570): key -> node (int)(x / hX); stable gather from the cell slots
+    const int nini = lg.nini;
+    int total = 0;
+    if (nini >= 1) {
+        int run = 0;
+        for (int ni = 0; ni < nini; ni++) {
+            const int beg = run;
+            for (int c = 0; c < lg.ncells; c++) {
+                const int n = min(cc[c], cl[c].cap);
+                const uint32_t* src = S + cl[c].slot;
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool take = false; uint32_t key = 0;
+                    if (i < n) {
+                        key = src[i];
+                        take = nini == 1 || (int)__fdiv_rn((float)(key & 0xfff), lg.hx) == ni;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    if (take) A[run + __popc(m & ((1u << lane) - 1))] = key;
+                    run += __popc(m);
+                }
+            }
+            const int k = run - beg;
+            if (k > 0) {                      // empty initial nodes are erased right away (ORBextractor.cc:581-582)
+                const int id = qt_alloc(w);
+                if (lane == 0) {
+                    QtNode c;
+                    c.x0 = (short)(int)__fmul_rn(lg.hx, (float)ni); c.x1 = (short)(int)__fmul_rn(lg.hx, (float)(ni + 1));
+                    c.y0 = 0; c.y1 = (short)(lg.h - 2 * kMinBorder);
+                    c.beg = beg; c.end = run; c.prev = c.next = -1; c.seq = w.seq; c.no_more = (k == 1); c.buf = 0; c.pad0 = c.pad1 = 0;
+                    w.pool[id] = c;
+                }
+                __syncwarp();
+                qt_push_back(w, id, lane);
+                w.seq++;
+            }
+        }
+        total = run;
+    }
+    __syncwarp();
+
+    bool finish = (total == 0);
+    while (!finish) {
+        const int prev_size = w.size;
+        int nbig = 0, n_expand = 0;
+        int it = w.head;
+        while (it >= 0) {
+            const QtNode nd = w.pool[it];
+            __syncwarp();
+            if (nd.no_more) { it = nd.next; continue; }
+            if (w.nfree < 4) { if (lane == 0) atomicExch(errflag, 1); finish = true; break; }
+            int cnt[4], mx, my;
+            qt_divide(nd, A, B, lane, cnt, mx, my);
+            n_expand += qt_add_children(w, nd, cnt, mx, my, lane, nbig);
+            it = qt_erase(w, it, lane);
+        }
+        if (finish) break;
+        if (w.size >= N || w.size == prev_size) finish = true;
+        else if (w.size + n_expand * 3 > N) {
+            while (!finish) {
+                const int prev2 = w.size;
+                const int m = nbig;
+                // previous round's list -> prv_*, then order it by (count, seq) descending
+                for (int i = lane; i < m; i += 32) { w.prv_cnt[i] = w.big_cnt[i]; w.prv_seq[i] = w.big_seq[i]; w.prv_id[i] = w.big_id[i]; }
+                __syncwarp();
+                for (int i = lane; i < m; i += 32) {
+                    const int ci = w.prv_cnt[i], si = w.prv_seq[i];
+                    int rank = 0;
+                    for (int j = 0; j < m; j++) {
+                        const int cj = w.prv_cnt[j], sj = w.prv_seq[j];
+                        rank += (cj > ci) || (cj == ci && sj > si);
+                    }
+                    w.order[rank] = (short)i;
+                }
+                __syncwarp();
+                nbig = 0;
+                for (int j = 0; j < m; j++) {
+                    const int id = w.prv_id[w.order[j]];
+                    const QtNode nd = w.pool[id];
+                    __syncwarp();
+                    if (w.nfree < 4) { if (lane == 0) atomicExch(errflag, 1); finish = true; break; }
+                    int cnt[4], mx, my;
+                    qt_divide(nd, A, B, lane, cnt, mx, my);
+                    qt_add_children(w, nd, cnt, mx, my, lane, nbig);
+                    qt_erase(w, id, lane);
+                    if (w.size >= N) break;
+                }
+                if (w.size >= N || w.size == prev2) finish = true;
+            }
+        }
+    }
+
+    // ---- best response per node in list order, first maximum wins (ORBextractor.cc:742-760)
+    int nres = 0;
+    for (int it = w.head; it >= 0; it = w.pool[it].next) {
+        if (lane == 0) w.order[nres] = (short)it;
+        nres++;
+    }
+    __syncwarp();
+    if (nres > lg.kp_cap) { if (lane == 0) atomicExch(errflag, 2); nres = lg.kp_cap; }
+    for (int i = lane; i < nres; i += 32) {
+        const QtNode nd = w.pool[w.order[i]];
+        const uint32_t* src = nd.buf ? B : A;
+        uint32_t best = src[nd.beg];
+        for (int k = nd.beg + 1; k < nd.end; k++) {
+            const uint32_t key = src[k];
+            if ((key >> 24) > (best >> 24)) best = key;
+        }
+        // back to level coordinates (ORBextractor.cc:842-843)
+        out[i] = (((best & 0xfff) + kMinBorder)) | ((((best >> 12) & 0xfff) + kMinBorder) << 12) | (best & 0xff000000u);
+    }
+    if (lane == 0) *out_cnt = nres;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4+K5+K6: one warp per keypoint.  43x43 source patch -> smem; IC_Angle over the radius-15 disc;
+// separable 7x7 Gaussian (Q8 kernel 18,34,48,56,48,34,18; (V+32768)>>16) on the 37x37 region the
+// pattern can reach; 256 steered comparisons, lane i produces descriptor byte i.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDescWarps = 8;
+constexpr int kPatchR = 21;                  // 18 (max rotated pattern reach) + 3 (blur taps)
+constexpr int kPatchW = 2 * kPatchR + 1;     // 43
+constexpr int kBlurW = 37;
+constexpr int kPatchPitch = 44;
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+    return p;
+}
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {     // cv::fastAtan2, SURVEY A-4
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(kDescWarps * 32)
+k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
+           const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g,
+           const uint32_t* __restrict__ lvlres, const int* __restrict__ lvlcnt,
+           b200_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ counts, int out_cap) {
+    __shared__ uint8_t s_patch[kDescWarps][kPatchW * kPatchPitch];
+    __shared__ uint16_t s_h[kDescWarps][kPatchW * kBlurW];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.y;
+    const int k = blockIdx.x * kDescWarps + warp;            // keypoint index inside the frame (levels concatenated)
+    const int* lc = lvlcnt + (long long)f * g.nlevels;
+    int level = -1, base = 0, total = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        const int c = lc[l];
+        if (level < 0 && k < total + c) { level = l; base = total; }
+        total += c;
+    }
+    if (k == 0 && lane == 0) counts[f] = min(total, out_cap);
+    if (level < 0 || k >= out_cap) return;
+    const LevelGeom& lg = g.L[level];
+    const uint32_t key = lvlres[(long long)f * g.res_per_frame + lg.kp_base + (k - base)];
+    const int cx = key & 0xfff, cy = (key >> 12) & 0xfff, resp = key >> 24;
+
+    const uint8_t* im; long long pitch;
+    if (level == 0) { im = img0 + (long long)f * img_frame_stride; pitch = img_row_stride; }
+    else { im = pyr + (long long)f * g.pyr_frame_stride + lg.offset; pitch = lg.pitch; }
+
+    uint8_t* P = s_patch[warp];
+    for (int idx = lane; idx < kPatchW * kPatchW; idx += 32) {
+        const int r = idx / kPatchW, c = idx - r * kPatchW;
+        const int yy = reflect101(cy + r - kPatchR, lg.h), xx = reflect101(cx + c - kPatchR, lg.w);
+        P[r * kPatchPitch + c] = im[(long long)yy * pitch + xx];
+    }
+    __syncwarp();
+
+    // IC_Angle (ORBextractor.cc:77-104): lane = u + 15
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - kHalfPatch, au = abs(u);
+#pragma unroll 1
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+            if (au <= c_umax[abs(v)]) {
+                const int val = P[(v + kPatchR) * kPatchPitch + u + kPatchR];
+                m10 += u * val; m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // Gaussian: horizontal pass over 43 rows x 37 cols, vertical over 37 x 37
+    uint16_t* H = s_h[warp];
+    for (int idx = lane; idx < kPatchW * kBlurW; idx += 32) {
+        const int r = idx / kBlurW, c = idx - r * kBlurW;
+        const uint8_t* s = P + r * kPatchPitch + c;
+        H[idx] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    }
+    __syncwarp();
+    uint8_t* Bl = P;                     // the source patch is dead once H exists: reuse its storage
+    for (int idx = lane; idx < kBlurW * kBlurW; idx += 32) {
+        const uint16_t* s = H + idx;       // row r of the blurred patch uses H rows r..r+6
+        const unsigned vsum = 18u * (s[0] + s[6 * kBlurW]) + 34u * (s[kBlurW] + s[5 * kBlurW]) + 48u * (s[2 * kBlurW] + s[4 * kBlurW]) + 56u * s[3 * kBlurW];
+        Bl[idx] = (uint8_t)((vsum + 32768u) >> 16);
+    }
+    __syncwarp();
+
+    // steered BRIEF (ORBextractor.cc:107-147); canonical a,b = float(cos/sin(double(angle_rad)))
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = __double2float_rn(cos((double)ang)), b = __double2float_rn(sin((double)ang));
+    int val = 0;
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+        const float x0 = (float)__ldg(&g_pattern[(kk * 4 + 0) * 32 + lane]), y0 = (float)__ldg(&g_pattern[(kk * 4 + 1) * 32 + lane]);
+        const float x1 = (float)__ldg(&g_pattern[(kk * 4 + 2) * 32 + lane]), y1 = (float)__ldg(&g_pattern[(kk * 4 + 3) * 32 + lane]);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = Bl[(r0 + 18) * kBlurW + c0 + 18], t1 = Bl[(r1 + 18) * kBlurW + c1 + 18];
+        val |= (t0 < t1) << kk;
+    }
+    desc[((long long)f * out_cap + k) * 32 + lane] = (uint8_t)val;
+
+    // keypoint record (ORBextractor.cc:837-847,1095-1101)
+    float px = (float)cx, py = (float)cy;
+    if (level != 0) { px = __fmul_rn(px, lg.scale); py = __fmul_rn(py, lg.scale); }
+    if (lane < 7) {
+        uint32_t wv;
+        switch (lane) {
+            case 0: wv = __float_as_uint(px); break;
+            case 1: wv = __float_as_uint(py); break;
+            case 2: wv = __float_as_uint(lg.size); break;
+            case 3: wv = __float_as_uint(angle); break;
+            case 4: wv = __float_as_uint((float)resp); break;
+            case 5: wv = (uint32_t)level; break;
+            default: wv = 0xffffffffu; break;   // class_id = -1
+        }
+        reinterpret_cast<uint32_t*>(kps + (long long)f * out_cap + k)[lane] = wv;
+    }
+}
+
+}  // namespace b200
+
+// =================================================================================================
+// Host side: handle, geometry, C-ABI
+// =================================================================================================
+using namespace b200;
+
+struct b200_orb_s {
+    int device;
+    cudaStream_t stream;
+    int nfeatures, nlevels, ini_th, min_th;
+    float scale;
+    int max_w, max_h, max_batch;
+    std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    // geometry of the image size in use
+    int cur_w, cur_h;
+    OrbGeom geom;
+    std::vector<CellDesc> cells;
+    int pool_cap;
+    // device buffers
+    uint8_t* d_pyr; ResizeEntry* d_tab; CellDesc* d_cells; uint32_t* d_slots; int* d_cellcnt;
+    uint32_t *d_keysA, *d_keysB, *d_lvlres; int* d_lvlcnt; int* d_err;
+    size_t cap_pyr, cap_tab, cap_cells, cap_slots, cap_keysA, cap_keysB, cap_cellcnt, cap_lvlres;
+    // staging for the host-pointer API
+    uint8_t* d_in; size_t cap_in; uint8_t* h_in; size_t cap_hin;
+    b200_keypoint* d_kps; uint8_t* d_desc; int32_t* d_counts; size_t cap_kps, cap_desc, cap_counts;
+    uint8_t* h_out; size_t cap_hout;
+    // optional per-stage timing (b200_orb_set_profile): events around pyramid / fast / quadtree / describe
+    int profile; cudaEvent_t ev[5]; float stage_ms[4]; int stage_valid;
+    cudaStream_t copy_stream; cudaEvent_t ev_copy[2];
+    // last call (debug taps)
+    const uint8_t* last_imgs; long long last_row_stride, last_frame_stride; int last_n;
+};
+
+namespace {
+
+template <typename T> int ensure(T*& p, size_t& cap, size_t need_bytes) {
+    if (need_bytes <= cap && p) return B200_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    B200_CUDA(cudaMalloc((void**)&p, need_bytes));
+    cap = need_bytes;
+    return B200_OK;
+}
+
+// ORBextractor.cc:410-446
+void make_tables(b200_orb_s* h) {
+    const int n = h->nlevels;
+    const double scale_d = h->scale;
+    h->sf.assign(n, 1.f); h->inv_sf.assign(n, 1.f); h->sigma2.assign(n, 1.f); h->inv_sigma2.assign(n, 1.f);
+    for (int i = 1; i < n; i++) { h->sf[i] = (float)(h->sf[i - 1] * scale_d); h->sigma2[i] = h->sf[i] * h->sf[i]; }
+    for (int i = 0; i < n; i++) { h->inv_sf[i] = 1.0f / h->sf[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+    h->quota.assign(n, 0);
+    const float factor = (float)(1.0f / scale_d);
+    float nd = h->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)n));
+    int sum = 0;
+    for (int l = 0; l < n - 1; l++) { h->quota[l] = host_round(nd); sum += h->quota[l]; nd *= factor; }
+    h->quota[n - 1] = std::max(h->nfeatures - sum, 0);
+}
+
+// cv::resize INTER_LINEAR coefficient table (SURVEY A-1)
+void resize_table(int ssize, int dsize, ResizeEntry* t) {
+    const double scale = (double)ssize / dsize;
+    for (int d = 0; d < dsize; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(fx);
+        fx -= s;
+        if (s < 0) { s = 0; fx = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
+        t[d].ofs = s;
+        t[d].c0 = (short)host_round((1.f - fx) * 2048.f);
+        t[d].c1 = (short)host_round(fx * 2048.f);
+    }
+}
+
+int set_geometry(b200_orb_s* h, int w, int h_img) {
+    if (w == h->cur_w && h_img == h->cur_h) return B200_OK;
+    OrbGeom& g = h->geom;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = h->nlevels; g.ini_th = h->ini_th; g.min_th = h->min_th;
+    h->cells.clear();
+    std::vector<ResizeEntry> tab;
+    long long pyr_ofs = 0, slot = 0;
+    int res = 0, maxcap = 0;
+    for (int l = 0; l < h->nlevels; l++) {
+        LevelGeom& L = g.L[l];
+        L.w = host_round((float)w * h->inv_sf[l]);
+        L.h = host_round((float)h_img * h->inv_sf[l]);
+        if (L.w < 1 || L.h < 1) return fail(B200_EINVAL, "image too small for %s pyramid levels", "this many");
+        L.quota = h->quota[l]; L.scale = h->sf[l]; L.size = (float)(int)(31 * h->sf[l]);
+        if (l > 0) {
+            L.pitch = (int)align_up(L.w, 16); L.offset = pyr_ofs;
+            pyr_ofs += align_up((long long)L.pitch * L.h, 256);
+            L.xtab = (int)tab.size(); tab.resize(tab.size() + L.w); resize_table(g.L[l - 1].w, L.w, &tab[L.xtab]);
+            L.ytab = (int)tab.size(); tab.resize(tab.size() + L.h); resize_table(g.L[l - 1].h, L.h, &tab[L.ytab]);
+        }
+        // cells (ORBextractor.cc:771-806)
+        const int minB = kMinBorder, maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        L.ncols = (int)(width / 30.f); L.nrows = (int)(height / 30.f);
+        L.cell_base = (int)h->cells.size(); L.slot_base = slot;
+        L.nini = 0; L.hx = 1.f;
+        if (L.ncols >= 1 && L.nrows >= 1) {
+            L.wcell = (int)ceilf(width / L.ncols); L.hcell = (int)ceilf(height / L.nrows);
+            for (int i = 0; i < L.nrows; i++) {
+                const float iniY = (float)(minB + i * L.hcell);
+                float maxY = iniY + L.hcell + 6;
+                if (iniY >= maxBY - 3) continue;
+                if (maxY > maxBY) maxY = (float)maxBY;
+                for (int j = 0; j < L.ncols; j++) {
+                    const float iniX = (float)(minB + j * L.wcell);
+                    float maxX = iniX + L.wcell + 6;
+                    if (iniX >= maxBX - 6) continue;
+                    if (maxX > maxBX) maxX = (float)maxBX;
+                    CellDesc c;
+                    c.level = (short)l; c.pad = 0; c.x0 = (short)iniX; c.y0 = (short)iniY;
+                    c.rw = (short)((int)maxX - (int)iniX); c.rh = (short)((int)maxY - (int)iniY);
+                    c.sx = (short)(j * L.wcell); c.sy = (short)(i * L.hcell);
+                    if (c.rw < 7 || c.rh < 7) continue;      // cv::FAST finds nothing in ROIs without an interior
+                    if (c.rw > kMaxRoi || c.rh > kMaxRoi) return fail(B200_EINVAL, "cell ROI larger than %s", "kMaxRoi");
+                    c.slot = (int)slot;
+                    c.cap = ((c.rw - 6 + 1) / 2) * ((c.rh - 6 + 1) / 2);   // strict 3x3 maxima: at most one per 2x2 block
+                    slot += c.cap;
+                    h->cells.push_back(c);
+                }
+            }
+            const int nini = (int)roundf((float)(maxBX - minB) / (float)(maxBY - minB));
+            if (nini >= 1) { L.nini = nini; L.hx = (float)(maxBX - minB) / nini; }
+        }
+        L.ncells = (int)h->cells.size() - L.cell_base;
+        L.kp_cap = L.quota + 3 + 4 * std::max(L.nini, 1);
+        L.kp_base = res; res += L.kp_cap;
+        maxcap = std::max(maxcap, L.kp_cap);
+        if (L.w > 4095 || L.h > 4095) return fail(B200_EINVAL, "level larger than %s", "4095 px (12-bit packed coordinates)");
+    }
+    g.total_cells = (int)h->cells.size();
+    g.slots_per_frame = slot;
+    g.pyr_frame_stride = std::max<long long>(pyr_ofs, 256);
+    g.res_per_frame = res;
+    h->pool_cap = maxcap + 8;
+    if (h->pool_cap > 32000) return fail(B200_EINVAL, "nfeatures per level too large for %s", "16-bit node ids");
+
+    const size_t B = (size_t)h->max_batch;
+    int rc;
+    if ((rc = ensure(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame_stride * B))) return rc;
+    if ((rc = ensure(h->d_tab, h->cap_tab, std::max<size_t>(tab.size(), 1) * sizeof(ResizeEntry)))) return rc;
+    if ((rc = ensure(h->d_cells, h->cap_cells, std::max<size_t>(h->cells.size(), 1) * sizeof(CellDesc)))) return rc;
+    size_t slots_bytes = std::max<size_t>((size_t)g.slots_per_frame * B * 4, 4);
+    if ((rc = ensure(h->d_slots, h->cap_slots, slots_bytes))) return rc;
+    if ((rc = ensure(h->d_keysA, h->cap_keysA, slots_bytes))) return rc;
+    if ((rc = ensure(h->d_keysB, h->cap_keysB, slots_bytes))) return rc;
+    if ((rc = ensure(h->d_cellcnt, h->cap_cellcnt, std::max<size_t>((size_t)g.total_cells * B * 4, 4)))) return rc;
+    if ((rc = ensure(h->d_lvlres, h->cap_lvlres, (size_t)res * B * 4))) return rc;
+    if (!h->d_lvlcnt) B200_CUDA(cudaMalloc((void**)&h->d_lvlcnt, (size_t)kMaxLevels * B * 4));
+    if (!h->d_err) { B200_CUDA(cudaMalloc((void**)&h->d_err, 4)); B200_CUDA(cudaMemset(h->d_err, 0, 4)); }
+    if (!tab.empty()) B200_CUDA(cudaMemcpy(h->d_tab, tab.data(), tab.size() * sizeof(ResizeEntry), cudaMemcpyHostToDevice));
+    if (!h->cells.empty()) B200_CUDA(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
+    h->cur_w = w; h->cur_h = h_img;
+    return B200_OK;
+}
+
+int upload_constants() {
+    static const signed char pat[256 * 4] = {
+#include "orb_pattern.inc"
+    };
+    signed char t[256 * 4];
+    // descriptor byte i uses pairs 8i..8i+7; lane i reads [k][coord][i]
+    for (int i = 0; i < 32; i++)
+        for (int k = 0; k < 8; k++)
+            for (int c = 0; c < 4; c++) t[(k * 4 + c) * 32 + i] = pat[(8 * i + k) * 4 + c];
+    B200_CUDA(cudaMemcpyToSymbol(g_pattern, t, sizeof(t)));
+    // umax (ORBextractor.cc:454-469)
+    int umax[16];
+    const int vmax = (int)floor(kHalfPatch * sqrt(2.f) / 2 + 1), vmin = (int)ceil(kHalfPatch * sqrt(2.f) / 2);
+    for (int v = 0; v <= vmax; v++) umax[v] = host_round_d(sqrt((double)kHalfPatch * kHalfPatch - v * v));
+    for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (umax[v0] == umax[v0 + 1]) ++v0;
+        umax[v] = v0; ++v0;
+    }
+    B200_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+    return B200_OK;
+}
+
+int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long rs, long long fs,
+            b200_keypoint* kps, uint8_t* desc, int32_t* counts, int out_cap, cudaStream_t st) {
+    const OrbGeom& g = h->geom;
+    if (h->profile) B200_CUDA(cudaEventRecord(h->ev[0], st));
+    for (int l = 1; l < g.nlevels; l++) {
+        const LevelGeom& L = g.L[l];
+        const LevelGeom& Lp = g.L[l - 1];
+        const uint8_t* src = l == 1 ? imgs : h->d_pyr + Lp.offset;
+        const long long srs = l == 1 ? rs : Lp.pitch, sfs = l == 1 ? fs : g.pyr_frame_stride;
+        dim3 grid((L.w + 127) / 128, (L.h + 7) / 8, n), block(32, 8);
+        B200_LAUNCH(k_pyramid, grid, block, 0, st, src, srs, sfs, h->d_pyr + L.offset, L.pitch, g.pyr_frame_stride,
+                    Lp.w, Lp.h, L.w, L.h, h->d_tab + L.xtab, h->d_tab + L.ytab);
+    }
+    if (h->profile) B200_CUDA(cudaEventRecord(h->ev[1], st));
+    if (g.total_cells > 0) {
+        dim3 grid(g.total_cells, n);
+        B200_LAUNCH(k_fast, grid, kFastThreads, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_cells, h->d_slots, h->d_cellcnt);
+    }
+    if (h->profile) B200_CUDA(cudaEventRecord(h->ev[2], st));
+    {
+        const int nprob = n * g.nlevels;
+        const size_t per_warp = ((size_t)h->pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64 + 15) & ~(size_t)15;
+        const size_t smem = per_warp * kQtWarps;
+        B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_LAUNCH(k_quadtree, (nprob + kQtWarps - 1) / kQtWarps, kQtWarps * 32, smem, st, g, h->d_cells, h->d_slots, h->d_cellcnt,
+                    h->d_keysA, h->d_keysB, h->d_lvlres, h->d_lvlcnt, n, h->pool_cap, h->d_err);
+    }
+    if (h->profile) B200_CUDA(cudaEventRecord(h->ev[3], st));
+    {
+        dim3 grid((g.res_per_frame + kDescWarps - 1) / kDescWarps, n);
+        B200_LAUNCH(k_describe, grid, kDescWarps * 32, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_lvlres, h->d_lvlcnt, kps, desc, counts, out_cap);
+    }
+    if (h->profile) { B200_CUDA(cudaEventRecord(h->ev[4], st)); h->stage_valid = 1; }
+    B200_CUDA(cudaGetLastError());
+    h->last_imgs = imgs; h->last_row_stride = rs; h->last_frame_stride = fs; h->last_n = n;
+    (void)w; (void)hh;
+    return B200_OK;
+}
+
+int check_args(b200_orb_s* h, const void* imgs, int n, int w, int hh, long long rs, long long fs) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    if (n < 0 || w < 0 || hh < 0) return fail(B200_EINVAL, "negative %s", "size");
+    if (n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
+    if (n > 0 && w > 0 && hh > 0) {
+        if (!imgs) return fail(B200_EINVAL, "null %s", "image pointer");
+        if (rs < w || (n > 1 && fs < rs * (hh - 1) + w)) return fail(B200_EINVAL, "bad %s", "strides");
+    }
+    return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_orb_create(b200_orb_t* out, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
+                    int max_w, int max_h, int max_batch, int device) {
+    if (!out) return fail(B200_EINVAL, "null %s", "out");
+    *out = nullptr;
+    if (nfeatures < 0 || nlevels < 1 || nlevels > kMaxLevels || !(scale_factor > 1.f) || ini_th < 1 || min_th < 1 || ini_th > 254 || min_th > ini_th ||
+        max_w < 1 || max_h < 1 || max_batch < 1)
+        return fail(B200_EINVAL, "bad %s parameters", "extractor");
+    int rc = use_device(device);
+    if (rc) return rc;
+    b200_orb_s* h = new (std::nothrow) b200_orb_s();
+    if (!h) return B200_ENOMEM;
+    h->device = device; h->nfeatures = nfeatures; h->scale = scale_factor; h->nlevels = nlevels; h->ini_th = ini_th; h->min_th = min_th;
+    h->max_w = max_w; h->max_h = max_h; h->max_batch = max_batch; h->cur_w = h->cur_h = -1;
+    make_tables(h);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(B200_ECUDA, "%s failed", "cudaStreamCreate"); }
+    for (int i = 0; i < 5; i++) cudaEventCreate(&h->ev[i]);
+    cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if ((rc = upload_constants()) || (rc = set_geometry(h, max_w, max_h))) { b200_orb_destroy(h); return rc; }
+    *out = h;
+    return B200_OK;
+}
+
+int b200_orb_destroy(b200_orb_t h) {
+    if (!h) return B200_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_pyr); cudaFree(h->d_tab); cudaFree(h->d_cells); cudaFree(h->d_slots); cudaFree(h->d_cellcnt);
+    cudaFree(h->d_keysA); cudaFree(h->d_keysB); cudaFree(h->d_lvlres); cudaFree(h->d_lvlcnt); cudaFree(h->d_err);
+    cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B200_OK;
+}
+
+int b200_orb_max_keypoints(b200_orb_t h) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    // independent of the image size: quota + 3 + 4*nIni per level with nIni <= 4 covers aspect ratios up to 4.5:1
+    int cap = 0;
+    for (int l = 0; l < h->nlevels; l++) cap += h->quota[l] + 3 + 16;
+    return cap;
+}
+
+int b200_orb_get_level_info(b200_orb_t h, int* nlevels, float* sf, float* inv_sf, float* s2, float* inv_s2, int32_t* fpl) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    if (nlevels) *nlevels = h->nlevels;
+    for (int l = 0; l < h->nlevels; l++) {
+        if (sf) sf[l] = h->sf[l];
+        if (inv_sf) inv_sf[l] = h->inv_sf[l];
+        if (s2) s2[l] = h->sigma2[l];
+        if (inv_s2) inv_s2[l] = h->inv_sigma2[l];
+        if (fpl) fpl[l] = h->quota[l];
+    }
+    return B200_OK;
+}
+
+int b200_orb_extract(b200_orb_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                     b200_keypoint* kps, uint8_t* desc, int32_t* counts, void* stream) {
+    int rc = check_args(h, imgs, n, w, hh, rs, fs);
+    if (rc) return rc;
+    if (!counts || !kps || !desc) return fail(B200_EINVAL, "null %s", "output pointer");
+    if ((rc = use_device(h->device))) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (n == 0) return B200_OK;
+    if (w == 0 || hh == 0) { B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4, st)); return B200_OK; }   // empty image: no keypoints (ORBextractor.cc:1046)
+    if ((rc = set_geometry(h, w, hh))) return rc;
+    // the caller's buffers use cap = b200_orb_max_keypoints(); internally res_per_frame <= cap
+    const int cap = b200_orb_max_keypoints(h);
+    if (h->geom.res_per_frame > cap) return fail(B200_ECAPACITY, "aspect ratio beyond %s", "4.5:1");
+    // output rows use the caller-visible capacity as pitch; the internal level-result block is indexed by res_per_frame
+    if ((rc = enqueue(h, imgs, n, w, hh, rs, fs, kps, desc, counts, cap, st))) return rc;
+    return B200_OK;
+}
+
+namespace {
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+// Host-pointer call: frames go up in chunks on a copy stream while the previous chunk is being processed on the
+// compute stream (per-chunk events order the two); pinned caller buffers are used in place, pageable ones are
+// staged through the handle's pinned buffers.
+int b200_orb_extract_host(b200_orb_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                          b200_keypoint* kps, uint8_t* desc, int32_t* counts) {
+    int rc = check_args(h, imgs, n, w, hh, rs, fs);
+    if (rc) return rc;
+    if (!counts || !kps || !desc) return fail(B200_EINVAL, "null %s", "output pointer");
+    if ((rc = use_device(h->device))) return rc;
+    if (n == 0) return B200_OK;
+    if (w == 0 || hh == 0) { for (int i = 0; i < n; i++) counts[i] = 0; return B200_OK; }
+    const int cap = b200_orb_max_keypoints(h);
+    const size_t frame_bytes = (size_t)w * hh, in_bytes = frame_bytes * n;
+    const size_t kp_bytes = (size_t)n * cap * sizeof(b200_keypoint), de_bytes = (size_t)n * cap * 32, ct_bytes = (size_t)n * 4;
+    if ((rc = ensure(h->d_in, h->cap_in, in_bytes))) return rc;
+    if ((rc = ensure(h->d_kps, h->cap_kps, kp_bytes))) return rc;
+    if ((rc = ensure(h->d_desc, h->cap_desc, de_bytes))) return rc;
+    if ((rc = ensure(h->d_counts, h->cap_counts, ct_bytes))) return rc;
+    const bool in_pinned = is_pinned(imgs);
+    const bool out_pinned = is_pinned(kps) && is_pinned(desc) && is_pinned(counts);
+    if (!in_pinned && h->cap_hin < in_bytes) {
+        if (h->h_in) cudaFreeHost(h->h_in);
+        h->h_in = nullptr; h->cap_hin = 0;
+        B200_CUDA(cudaMallocHost((void**)&h->h_in, in_bytes));
+        h->cap_hin = in_bytes;
+    }
+    const size_t out_bytes = kp_bytes + de_bytes + ct_bytes;
+    if (!out_pinned && h->cap_hout < out_bytes) {
+        if (h->h_out) cudaFreeHost(h->h_out);
+        h->h_out = nullptr; h->cap_hout = 0;
+        B200_CUDA(cudaMallocHost((void**)&h->h_out, out_bytes));
+        h->cap_hout = out_bytes;
+    }
+    cudaStream_t st = h->stream, cs = h->copy_stream;
+    const int chunk = n <= 16 ? n : 32;
+    int ci = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, ci++) {
+        const int nf = std::min(chunk, n - f0);
+        uint8_t* dst = h->d_in + (size_t)f0 * frame_bytes;
+        if (in_pinned) {
+            if (fs == rs * hh)     // frames are back to back: one 2-D copy for the whole chunk
+                B200_CUDA(cudaMemcpy2DAsync(dst, w, imgs + (size_t)f0 * fs, rs, w, (size_t)hh * nf, cudaMemcpyHostToDevice, cs));
+            else
+                for (int f = 0; f < nf; f++)
+                    B200_CUDA(cudaMemcpy2DAsync(dst + (size_t)f * frame_bytes, w, imgs + (size_t)(f0 + f) * fs, rs, w, hh, cudaMemcpyHostToDevice, cs));
+        } else {
+            uint8_t* stage = h->h_in + (size_t)f0 * frame_bytes;
+            for (int f = 0; f < nf; f++) {
+                const uint8_t* src = imgs + (size_t)(f0 + f) * fs;
+                if (rs == w) memcpy(stage + (size_t)f * frame_bytes, src, frame_bytes);
+                else for (int y = 0; y < hh; y++) memcpy(stage + (size_t)f * frame_bytes + (size_t)y * w, src + (size_t)y * rs, w);
+            }
+            B200_CUDA(cudaMemcpyAsync(dst, stage, frame_bytes * nf, cudaMemcpyHostToDevice, cs));
+        }
+        cudaEvent_t ev = h->ev_copy[ci & 1];
+        B200_CUDA(cudaEventRecord(ev, cs));
+        B200_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        if ((rc = b200_orb_extract(h, dst, nf, w, hh, w, (int64_t)frame_bytes, h->d_kps + (size_t)f0 * cap, h->d_desc + (size_t)f0 * cap * 32,
+                                   h->d_counts + f0, st)))
+            return rc;
+    }
+    // (the debug taps b200_orb_get_pyramid / _get_candidates now refer to the LAST chunk)
+    uint8_t* ok = out_pinned ? (uint8_t*)kps : h->h_out;
+    uint8_t* od = out_pinned ? desc : h->h_out + kp_bytes;
+    uint8_t* oc = out_pinned ? (uint8_t*)counts : h->h_out + kp_bytes + de_bytes;
+    B200_CUDA(cudaMemcpyAsync(ok, h->d_kps, kp_bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(od, h->d_desc, de_bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(oc, h->d_counts, ct_bytes, cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (err) { cudaMemset(h->d_err, 0, 4); return fail(B200_ECAPACITY, "quadtree scratch overflow (%s)", err == 1 ? "node pool" : "result slots"); }
+    if (!out_pinned) { memcpy(kps, h->h_out, kp_bytes); memcpy(desc, h->h_out + kp_bytes, de_bytes); memcpy(counts, h->h_out + kp_bytes + de_bytes, ct_bytes); }
+    return B200_OK;
+}
+
+int b200_orb_set_profile(b200_orb_t h, int enable) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    h->profile = enable ? 1 : 0; h->stage_valid = 0;
+    return B200_OK;
+}
+
+int b200_orb_get_stage_ms(b200_orb_t h, float* ms4) {
+    if (!h || !ms4) return fail(B200_EINVAL, "null %s", "argument");
+    if (!h->stage_valid) return fail(B200_EINVAL, "no profiled call %s", "yet");
+    B200_CUDA(cudaEventSynchronize(h->ev[4]));
+    for (int i = 0; i < 4; i++) B200_CUDA(cudaEventElapsedTime(&ms4[i], h->ev[i], h->ev[i + 1]));
+    return B200_OK;
+}
+
+int b200_orb_get_pyramid(b200_orb_t h, int frame, int level, uint8_t* out, int* w_l, int* h_l) {
+    if (!h || !out) return fail(B200_EINVAL, "null %s", "argument");
+    if (!h->last_imgs || frame < 0 || frame >= h->last_n || level < 0 || level >= h->nlevels) return fail(B200_EINVAL, "no such %s", "frame/level");
+    int rc = use_device(h->device);
+    if (rc) return rc;
+    const LevelGeom& L = h->geom.L[level];
+    std::vector<uint8_t> img((size_t)L.w * L.h);
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    if (level == 0)
+        B200_CUDA(cudaMemcpy2D(img.data(), L.w, h->last_imgs + (size_t)frame * h->last_frame_stride, h->last_row_stride, L.w, L.h, cudaMemcpyDeviceToHost));
+    else
+        B200_CUDA(cudaMemcpy2D(img.data(), L.w, h->d_pyr + (size_t)frame * h->geom.pyr_frame_stride + L.offset, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    // the 19-px REFLECT_101 frame of mvImagePyramid (ORBextractor.cc:1113-1128) is never read on the mono path;
+    // it is synthesised here on demand instead of being stored in HBM
+    const int W = L.w + 2 * kEdge;
+    auto refl = [](int p, int n) { if (n == 1) return 0; while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p; return p; };
+    for (int y = 0; y < L.h + 2 * kEdge; y++) {
+        const uint8_t* s = &img[(size_t)refl(y - kEdge, L.h) * L.w];
+        for (int x = 0; x < W; x++) out[(size_t)y * W + x] = s[refl(x - kEdge, L.w)];
+    }
+    if (w_l) *w_l = L.w;
+    if (h_l) *h_l = L.h;
+    return B200_OK;
+}
+
+int b200_orb_get_candidates(b200_orb_t h, int frame, int level, int32_t* xys, int cap) {
+    if (!h || !xys) return fail(B200_EINVAL, "null %s", "argument");
+    if (!h->last_imgs || frame < 0 || frame >= h->last_n || level < 0 || level >= h->nlevels) return fail(B200_EINVAL, "no such %s", "frame/level");
+    int rc = use_device(h->device);
+    if (rc) return rc;
+    const OrbGeom& g = h->geom;
+    const LevelGeom& L = g.L[level];
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<int> cnt(std::max(L.ncells, 1));
+    if (L.ncells) B200_CUDA(cudaMemcpy(cnt.data(), h->d_cellcnt + (size_t)frame * g.total_cells + L.cell_base, (size_t)L.ncells * 4, cudaMemcpyDeviceToHost));
+    int n = 0;
+    std::vector<uint32_t> buf;
+    for (int c = 0; c < L.ncells; c++) {
+        const CellDesc& cd = h->cells[L.cell_base + c];
+        const int k = std::min(cnt[c], cd.cap);
+        if (!k) continue;
+        buf.resize(k);
+        B200_CUDA(cudaMemcpy(buf.data(), h->d_slots + (size_t)frame * g.slots_per_frame + cd.slot, (size_t)k * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < k; i++) {
+            if (n >= cap) return fail(B200_ECAPACITY, "candidate buffer too %s", "small");
+            xys[3 * n] = buf[i] & 0xfff; xys[3 * n + 1] = (buf[i] >> 12) & 0xfff; xys[3 * n + 2] = buf[i] >> 24;
+            n++;
+        }
+    }
+    return n;
+}
+
+}  // extern "C"

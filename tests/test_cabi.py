@@ -1,0 +1,59 @@
+"""CPU: the C-ABI shared library builds, loads and exports every symbol include/*.h declares; without a GPU every
+compute entry point fails loudly (B200_ENODEV) instead of falling back to a CPU path."""
+import ctypes as C
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = []
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        txt = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names += re.findall(r"\b(b200_\w+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(built_lib, n), "libb200slam.so does not export " + n
+
+
+def test_product_does_not_touch_the_oracle():
+    """the shipped path must not import, link or execute anything under oracle/"""
+    pkg = os.path.join(ROOT, "orb_slam2_aruco_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".hpp", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, re.M), f
+                assert "liboracle" not in txt and "oracle/" not in txt.replace("oracle/orb_oracle.cpp", "").replace("(oracle/", "("), f
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from orb_slam2_aruco_b200 import _lib
+    from orb_slam2_aruco_b200.api import ORBextractor, ORBmatcher
+    with pytest.raises(_lib.B200Error) as e:
+        ORBextractor(1000, 1.2, 8, 20, 7)(np.zeros((120, 160), np.uint8))
+    assert e.value.code == _lib.ENODEV
+    with pytest.raises(_lib.B200Error) as e:
+        ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.zeros(32, np.uint8))
+    assert e.value.code == _lib.ENODEV
+
+
+def test_bad_arguments_are_rejected(built_lib):
+    h = C.c_void_p()
+    assert built_lib.b200_orb_create(C.byref(h), 1000, 1.0, 8, 20, 7, 640, 480, 1, 0) == -1     # scale factor must be > 1
+    assert built_lib.b200_orb_create(None, 1000, 1.2, 8, 20, 7, 640, 480, 1, 0) == -1
+    assert built_lib.b200_orb_destroy(None) == 0
+    assert built_lib.b200_orb_max_keypoints(None) == -1

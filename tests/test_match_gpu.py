@@ -1,0 +1,87 @@
+"""GPU: CUDA matcher through the C-ABI vs the CPU restatement of ORBmatcher (bit-exact match indices)."""
+import numpy as np
+import pytest
+
+import oracle
+from orb_slam2_aruco_b200 import synth
+from orb_slam2_aruco_b200.api import ORBmatcher
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hamming_matrix(built_lib):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (37, 32)).astype(np.uint8)
+    b = rng.integers(0, 256, (53, 32)).astype(np.uint8)
+    want = np.unpackbits(a[:, None, :] ^ b[None, :, :], axis=2).sum(axis=2)
+    assert np.array_equal(ORBmatcher().distance_matrix(a, b), want)
+    assert ORBmatcher.DescriptorDistance(a[0], a[0]) == 0
+    assert ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+def _frames_desc(n, first):
+    out = []
+    for i in range(n):
+        k, d = oracle.orb_extract(synth.make_frame(first + i))
+        out.append((k, d))
+    return out
+
+
+def test_search_by_bow_bruteforce_real_descriptors(built_lib):
+    # reference set: a shifted copy of the scene; frames: the scene + two unrelated ones
+    kr, dr = oracle.orb_extract(np.roll(synth.make_frame(200), (3, 5), axis=(0, 1)))
+    frames = [oracle.orb_extract(synth.make_frame(i)) for i in (200, 200, 201)]
+    cap = max(len(k) for k, _ in frames) + 7
+    fd = np.zeros((3, cap, 32), np.uint8); fa = np.zeros((3, cap), np.float32); nf = np.zeros(3, np.int32)
+    for i, (k, d) in enumerate(frames):
+        fd[i, :len(d)] = d; fa[i, :len(k)] = k["angle"]; nf[i] = len(k)
+    for ratio, ori in ((0.7, True), (0.9, False), (0.6, True)):
+        m = ORBmatcher(ratio, ori)
+        nm, matches = m.SearchByBoW_batch(dr, kr["angle"], fd, fa, nf)
+        for i, (k, d) in enumerate(frames):
+            n2, m2 = oracle.search_by_bow_bf(dr, kr["angle"], d, k["angle"], ratio, ori)
+            assert nm[i] == n2
+            assert np.array_equal(matches[i, :len(d)], m2)
+            assert (matches[i, len(d):] == -1).all()
+    assert nm[0] > 100          # the shifted scene really matches
+
+
+def test_greedy_conflicts_and_ties(built_lib):
+    """many near-duplicate descriptors: earlier reference rows take candidates away from later ones and the
+    top-K lists run dry, which forces the rescan path"""
+    rng = np.random.default_rng(4)
+    base = rng.integers(0, 256, (8, 32)).astype(np.uint8)
+    ref = np.repeat(base, 40, axis=0)                  # 320 reference descriptors, 40 copies of each
+    frame = np.repeat(base, 25, axis=0)                # 200 frame descriptors
+    flip = rng.integers(0, 256, frame.shape) < 6       # sprinkle bit noise
+    frame = frame ^ np.packbits(rng.integers(0, 100, (200, 256)) < 3, axis=1)
+    ra = rng.uniform(0, 360, len(ref)).astype(np.float32); fa = rng.uniform(0, 360, len(frame)).astype(np.float32)
+    for ratio, ori in ((0.7, True), (1.5, False), (1.5, True)):
+        n2, m2 = oracle.search_by_bow_bf(ref, ra, frame, fa, ratio, ori)
+        n, m = ORBmatcher(ratio, ori).SearchByBoW(ref, ra, frame, fa)
+        assert n == n2 and np.array_equal(m, m2)
+
+
+def test_empty_sets(built_lib):
+    d = np.zeros((0, 32), np.uint8); a = np.zeros(0, np.float32)
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 256, (10, 32)).astype(np.uint8); xa = np.zeros(10, np.float32)
+    n, m = ORBmatcher(0.7).SearchByBoW(d, a, x, xa)
+    assert n == 0 and (m == -1).all()
+    n, m = ORBmatcher(0.7).SearchByBoW(x, xa, x[:1], xa[:1])
+    assert n == 0 or m[0] == 0      # a single candidate has bestDist2 = 256
+
+
+def test_candidate_lists(built_lib):
+    rng = np.random.default_rng(2)
+    q = rng.integers(0, 256, (300, 32)).astype(np.uint8)
+    t = rng.integers(0, 256, (500, 32)).astype(np.uint8)
+    t[:100] = q[:100] ^ np.packbits(rng.integers(0, 100, (100, 256)) < 5, axis=1)
+    lens = rng.integers(0, 60, 300)
+    lens[5] = 0
+    ofs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cand = rng.integers(0, 500, ofs[-1]).astype(np.int32)
+    got = ORBmatcher().match_candidates(q, t, ofs, cand)
+    want = oracle.match_candidates(q, t, ofs, cand)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)

@@ -1,0 +1,36 @@
+"""CPU: the restatement (oracle/orb_oracle.cpp) against the reference's own src/ORBextractor.cc compiled
+unmodified on the cv shim (oracle/_ref/libref_orb.so).  Skipped where oracle/_ref was never built."""
+import numpy as np
+import pytest
+
+import oracle
+from orb_slam2_aruco_b200 import synth
+
+pytestmark = pytest.mark.skipif(oracle.ref() is None, reason="oracle/_ref not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("idx,w,h,nf", [(2, 640, 480, 1000), (3, 640, 480, 2000), (11, 960, 540, 1000), (12, 333, 257, 500),
+                                       (13, 200, 150, 300), (14, 1280, 720, 2000)])
+def test_restatement_equals_reference(idx, w, h, nf):
+    img = synth.make_frame(idx, w, h)
+    k, d = oracle.orb_extract(img, nf)
+    k2, d2 = oracle.ref_orb_extract(img, nf)
+    assert len(k) == len(k2)
+    assert np.array_equal(k, k2)
+    assert np.array_equal(d, d2)
+
+
+def test_low_texture_and_noise():
+    rng = np.random.default_rng(5)
+    for img in (rng.integers(0, 256, (240, 320)).astype(np.uint8), (synth.make_frame(3, 320, 240) // 16 * 4 + 100).astype(np.uint8)):
+        k, d = oracle.orb_extract(img, 500)
+        k2, d2 = oracle.ref_orb_extract(img, 500)
+        assert np.array_equal(k, k2) and np.array_equal(d, d2)
+
+
+def test_pyramid_with_border_equals_reference():
+    img = synth.make_frame(4, 320, 240)
+    for level in (0, 1, 4, 7):
+        ref = oracle.ref_orb_pyramid_level(img, level)
+        mine = oracle.border_reflect101(oracle.orb_pyramid_level(img, level), 19)
+        assert np.array_equal(ref, mine)
