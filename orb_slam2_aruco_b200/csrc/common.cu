@@ -11,6 +11,12 @@ int host_round(float v) { return (int)lrintf(v); }        // round-half-even und
 int host_round_d(double v) { return (int)lrint(v); }
 
 int use_device(int device) {
+    // validated once per device (cudaGetDeviceProperties costs milliseconds); afterwards only cudaSetDevice
+    static std::atomic<int> ok_mask[64];
+    if (device >= 0 && device < 64 && ok_mask[device].load(std::memory_order_acquire)) {
+        B200_CUDA(cudaSetDevice(device));
+        return B200_OK;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -22,6 +28,7 @@ int use_device(int device) {
     B200_CUDA(cudaGetDeviceProperties(&p, device));
     if (p.major != 10) return fail(B200_ENODEV, "device is not sm_100 (%s); kernels are built for sm_100a only", p.name);
     B200_CUDA(cudaSetDevice(device));
+    if (device < 64) ok_mask[device].store(1, std::memory_order_release);
     return B200_OK;
 }
 

@@ -900,7 +900,8 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
         const int nprob = n * g.nlevels;
         const size_t per_warp = ((size_t)h->pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64 + 15) & ~(size_t)15;
         const size_t smem = per_warp * kQtWarps;
-        B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static std::atomic<size_t> qt_smem_set(0);
+        if (smem > qt_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); qt_smem_set.store(smem); }
         B200_LAUNCH(k_quadtree, (nprob + kQtWarps - 1) / kQtWarps, kQtWarps * 32, smem, st, g, h->d_cells, h->d_slots, h->d_cellcnt,
                     h->d_keysA, h->d_keysB, h->d_lvlres, h->d_lvlcnt, n, h->pool_cap, h->d_err);
     }
