@@ -202,3 +202,111 @@ def match_candidates(qd, td, ofs, cand):
     bi, bd, sd = (np.empty(len(qd), np.int32) for _ in range(3))
     lib().oracle_match_candidates(_p(qd), len(qd), _p(td), _p(ofs), _p(cand), _p(bi), _p(bd), _p(sd))
     return bi, bd, sd
+
+
+# ---- ArUco detector ---------------------------------------------------------------------------
+MARKER_DTYPE = np.dtype([("id", "<i4"), ("xy", "<f4", (8,))])
+
+
+def aruco_detect(img, dict_name="ARUCO_MIP_25h7", cap=256):
+    """aruco::MarkerDetector::detect on the reference's path -> structured array (id, xy[8]) sorted by id"""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros(cap, MARKER_DTYPE)
+    n = lib().oracle_aruco_detect(_p(img), img.shape[1], img.shape[0], img.shape[1], dict_name.encode(), _p(out), cap)
+    assert n >= 0, n
+    return out[:n].copy()
+
+
+def aruco_detect_batch(imgs, dict_name="ARUCO_MIP_25h7", cap=64, nthreads=1):
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    n, h, w = imgs.shape
+    out = np.zeros((n, cap), MARKER_DTYPE)
+    counts = np.zeros(n, np.int32)
+    r = lib().oracle_aruco_detect_batch(_p(imgs), n, w, h, w, C.c_long(w * h), dict_name.encode(), _p(out), _p(counts), cap, nthreads)
+    assert r == 0
+    return out, counts
+
+
+def aruco_stages(img, dict_name="ARUCO_MIP_25h7"):
+    """stage outputs: dict(thres, contours [list of (n,2) arrays], candidates (k,4,2), patches (k,ws,ws), prerefine, markers)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    thres = np.zeros((h, w), np.uint8)
+    maxc, maxp, maxk, cap = 20000, 2000000, 2000, 256
+    sizes = np.zeros(maxc, np.int32); pts = np.zeros((maxp, 2), np.int32); nc = C.c_int()
+    cand = np.zeros((maxk, 8), np.float32); nk = C.c_int()
+    from orb_slam2_aruco_b200 import synth
+    nbits = synth.dictionaries()[dict_name][0]
+    ws = 5 * (int(round(nbits ** 0.5)) + 2)
+    patches = np.zeros((maxk, ws, ws), np.uint8)
+    pre = np.zeros((cap, 8), np.float32)
+    out = np.zeros(cap, MARKER_DTYPE)
+    n = lib().oracle_aruco_stages(_p(img), w, h, w, dict_name.encode(), _p(thres), _p(sizes), _p(pts), maxc, maxp, C.byref(nc),
+                                  _p(cand), _p(patches), maxk, C.byref(nk), _p(pre), _p(out), cap)
+    assert n >= 0
+    contours = []
+    o = 0
+    for i in range(nc.value):
+        contours.append(pts[o:o + sizes[i]].copy()); o += sizes[i]
+    return dict(thres=thres, contours=contours, candidates=cand[:nk.value].reshape(-1, 4, 2).copy(), patches=patches[:nk.value].copy(),
+                prerefine=pre[:n].reshape(-1, 4, 2).copy(), markers=out[:n].copy())
+
+
+def adaptive_threshold(img, bs, c=7):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().oracle_adaptive_threshold(_p(img), img.shape[1], img.shape[0], _p(out), bs, c)
+    return out
+
+
+def find_contours(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    maxc, maxp = 50000, 4000000
+    sizes = np.zeros(maxc, np.int32); pts = np.zeros((maxp, 2), np.int32)
+    n = lib().oracle_find_contours(_p(img), img.shape[1], img.shape[0], _p(sizes), _p(pts), maxc, maxp)
+    out = []; o = 0
+    for i in range(n):
+        out.append(pts[o:o + sizes[i]].copy()); o += sizes[i]
+    return out
+
+
+def approx_poly(pts, eps):
+    pts = np.ascontiguousarray(pts, np.int32).reshape(-1, 2)
+    out = np.zeros((len(pts) + 4, 2), np.int32)
+    cv = C.c_int()
+    n = lib().oracle_approx_poly(_p(pts), len(pts), C.c_double(eps), _p(out), C.byref(cv))
+    return out[:n].copy(), bool(cv.value)
+
+
+def resize_half(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((img.shape[0] // 2, img.shape[1] // 2), np.uint8)
+    lib().oracle_resize_half(_p(img), img.shape[1], img.shape[0], _p(out))
+    return out
+
+
+def perspective_transform(src, dst):
+    src = np.ascontiguousarray(src, np.float32).reshape(8); dst = np.ascontiguousarray(dst, np.float32).reshape(8)
+    M = np.zeros(9, np.float64)
+    lib().oracle_perspective_transform(_p(src), _p(dst), _p(M))
+    return M.reshape(3, 3)
+
+
+def warp_perspective(img, M, size):
+    img = np.ascontiguousarray(img, np.uint8)
+    M = np.ascontiguousarray(M, np.float64)
+    out = np.empty((size, size), np.uint8)
+    lib().oracle_warp_perspective(_p(img), img.shape[1], img.shape[0], _p(out), size, _p(M))
+    return out
+
+
+def otsu(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    return int(lib().oracle_otsu(_p(img), img.shape[1], img.shape[0]))
+
+
+def solve_svd(A, b):
+    A = np.ascontiguousarray(A, np.float32); b = np.ascontiguousarray(b, np.float32).reshape(-1)
+    x = np.zeros(A.shape[1], np.float32)
+    lib().oracle_solve_svd(_p(A), _p(b), A.shape[0], A.shape[1], _p(x))
+    return x

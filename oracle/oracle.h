@@ -13,6 +13,8 @@ typedef struct {
     float x, y, size, angle, response;
     int32_t octave, class_id;
 } oracle_keypoint;
+// same record as b200_marker: id + 4 corners
+typedef struct { int32_t id; float xy[8]; } oracle_marker;
 
 // ---- primitives (pinned against cv2 golden vectors) -------------------------------------------
 void oracle_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstep, uint8_t* dst, int dw, int dh, int dstep);
@@ -47,6 +49,23 @@ int oracle_search_by_bow_bf(const uint8_t* kf_desc, const float* kf_angle, int n
                             float nnratio, int check_ori, float factor, int32_t* matches);
 void oracle_match_candidates(const uint8_t* qd, int nq, const uint8_t* td, const int32_t* ofs, const int32_t* cand,
                              int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
+// ---- ArUco detector: restatement of aruco::MarkerDetector::detect (Thirdparty/aruco/aruco) ----------
+int oracle_aruco_detect(const uint8_t* img, int w, int h, int stride, const char* dict_name, oracle_marker* out, int cap);
+int oracle_aruco_detect_batch(const uint8_t* imgs, int n, int w, int h, int row_stride, long frame_stride, const char* dict_name,
+                              oracle_marker* out, int32_t* counts, int cap, int nthreads);
+int oracle_aruco_stages(const uint8_t* img, int w, int h, int stride, const char* dict_name,
+                        uint8_t* thres, int32_t* contour_sizes, int32_t* contour_pts, int max_contours, int max_points, int32_t* n_contours,
+                        float* candidates, uint8_t* patches, int max_cand, int32_t* n_cand,
+                        float* prerefine, oracle_marker* out, int cap);
+void oracle_adaptive_threshold(const uint8_t* src, int w, int h, uint8_t* dst, int bs, int C);
+int oracle_find_contours(const uint8_t* img, int w, int h, int32_t* sizes, int32_t* pts, int max_contours, int max_points);
+int oracle_approx_poly(const int32_t* pts, int n, double eps, int32_t* out, int* convex);
+void oracle_resize_half(const uint8_t* src, int sw, int sh, uint8_t* dst);
+void oracle_perspective_transform(const float* src, const float* dst, double* M);
+void oracle_warp_perspective(const uint8_t* src, int sw, int sh, uint8_t* dst, int ds, const double* M);
+int oracle_otsu(const uint8_t* img, int w, int h);
+void oracle_solve_svd(const float* A, const float* b, int m, int n, float* x);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ Scene: blurred-noise background stretched to [30,225] + 150 random filled rectan
 quota; optionally ~20 square fiducial markers (rendered like reference
 Thirdparty/aruco/aruco/dictionary.cpp:254-284: bit 0 at the bottom-right cell, one-cell black
 border, plus a one-cell white quiet zone) with in-plane rotation and mild perspective on a jittered
-5x4 grid; finally a sigma=0.7 blur and sigma=2 Gaussian noise.
+5x4 grid (sides 50-76 px at 640 wide so that rotated quiet zones of neighbours rarely overlap); finally a sigma=0.7 blur and sigma=2 Gaussian noise.
 """
 import os
 import re
@@ -158,7 +158,7 @@ def make_frame(index, w=640, h=480, markers=0, dict_name="ARUCO_MIP_25h7", shift
         slots = rng.permutation(gx * gy)[:markers]
         cw, ch = w / gx, h / gy
         for mid, slot in zip(ids, slots):
-            side = float(rng.uniform(56 * s, min(96 * s, 0.80 * min(cw, ch))))
+            side = float(rng.uniform(50 * s, min(76 * s, 0.64 * min(cw, ch))))
             ang = float(rng.uniform(-np.pi, np.pi))
             cxm = (slot % gx + 0.5) * cw + float(rng.uniform(-0.08, 0.08)) * cw
             cym = (slot // gx + 0.5) * ch + float(rng.uniform(-0.08, 0.08)) * ch
