@@ -126,6 +126,10 @@ int b200_aruco_max_markers(b200_aruco_t h);
 /* markers [n][cap] sorted by id per frame (cap = b200_aruco_max_markers()), counts [n]. */
 int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
                       b200_marker* markers, int32_t* counts, void* stream);
+/* Validation taps of the LAST call for one frame: out4 = {borders > 70 points, convex quads, candidates after
+ * prefilterCandidates, decoded markers before de-duplication}; corners [cap][8] and ids [cap] (may be NULL) receive the
+ * prefiltered candidates in order with their decoded id (-1 = not a marker). */
+int b200_aruco_debug(b200_aruco_t h, int frame, int32_t* out4, float* corners, int32_t* ids, int cap);
 int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
                            b200_marker* markers, int32_t* counts);
 

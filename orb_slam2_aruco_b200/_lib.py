@@ -57,6 +57,7 @@ def lib():
         L.b200_aruco_destroy.argtypes = [vp]
         L.b200_aruco_max_markers.argtypes = [vp]
         L.b200_aruco_detect.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp]
+        L.b200_aruco_debug.argtypes = [vp, i32, vp, vp, vp, i32]
         L.b200_aruco_detect_host.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp]
         _lib = L
     return _lib

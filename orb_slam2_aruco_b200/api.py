@@ -318,6 +318,14 @@ class MarkerDetector:
             check(lib().b200_aruco_detect_host(self._h, ptr(images), n, w, h, images.strides[1], images.strides[0], ptr(markers), ptr(counts)))
         return markers, counts
 
+    def debug(self, frame):
+        """validation taps of the last call: (counts[4], kept corners (k,4,2), decoded ids (k,))"""
+        out4 = np.zeros(4, np.int32)
+        corners = np.zeros((256, 8), np.float32); ids = np.zeros(256, np.int32)
+        check(lib().b200_aruco_debug(self._h, frame, ptr(out4), ptr(corners), ptr(ids), 256))
+        k = int(out4[2])
+        return out4, corners[:k].reshape(-1, 4, 2).copy(), ids[:k].copy()
+
     def detect_batch_device(self, images, markers, counts, stream=None):
         n, h, w = images.shape
         self._ensure(w, h, n)

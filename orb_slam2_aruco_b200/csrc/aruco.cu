@@ -1,12 +1,1179 @@
-// aruco.cu -- B200-native ArUco marker detector (sm_100a).  Placeholder translation unit: the entry points
-// exist so that the C-ABI is complete; the kernels land in the next milestone.
+// aruco.cu -- B200-native ArUco marker detector (sm_100a).
+//
+// Behavioural contract: aruco::MarkerDetector::detect on the path the reference takes (src/Frame.cc:129-142:
+// DM_NORMAL => adaptive threshold, CORNER_LINES refinement, defaults of Thirdparty/aruco/aruco/markerdetector.h:162-200),
+// i.e. the de-obfuscated Thirdparty/aruco/aruco/markerdetector_impl.cpp + dictionary_based.cpp (anchor lines below
+// as in SURVEY.md section 8a).  Marker ids, candidate corners, warped patches and contour points are bit-identical to
+// the CPU oracle (oracle/aruco_oracle.cpp); refined corners agree within 1e-4 px (float SVD with double accumulators
+// whose summation order differs between a serial loop and a warp reduction).
+//
+// Pipeline for a batch of n frames (per-tile / per-border / per-candidate kernels, no serial raster scan):
+//   k_athresh     adaptiveThreshold MEAN_C BINARY_INV (markerdetector_impl.cpp:2984): win x win box sum in smem
+//   k_halfpyr     image pyramid by exact 1/2 (2x2 mean; odd sizes: fixed-point bilinear) (1300-1466)
+//   k_nbrmask     8-neighbour foreground mask of every pixel of the binary image
+//   k_probe       cv::findContours RETR_LIST/CHAIN_APPROX_NONE (3108) without a raster scan: every 0->1 / 1->0
+//                 transition pixel follows its border (Suzuki's successor rule on the masks) until it comes back to
+//                 itself (=> it is the border's raster-first transition, i.e. Suzuki's start; the border is recorded
+//                 with its length) or meets a transition that the raster scan would have seen earlier (=> abort)
+//   k_emit        borders longer than 70 points are followed once more and written as point lists
+//   k_quads       warp per border: cv::approxPolyDP(eps = 0.05*len, closed) + isContourConvex (3253-3292)
+//   k_prefilter   CTA per frame: candidate order = reverse discovery order, corner orientation, too-near pairs,
+//                 frame-border rejection (4349-5070)
+//   k_decode      CTA per candidate: pyramid level, getPerspectiveTransform (LU, double), warpPerspective 5-bit fixed
+//                 point, Otsu, cell vote, 4 rotations, dictionary lookup (6482-6803, dictionary_based.cpp:1062-2509)
+//   k_finalize    CTA per frame: stable sort by id, duplicate removal (8159-8311), CORNER_LINES refinement with the
+//                 float one-sided Jacobi SVD of cv::solve(DECOMP_SVD) (8979-12049)
 #include "common.h"
-using namespace b200;
-struct b200_aruco_s { int device; };
-extern "C" {
-int b200_aruco_create(b200_aruco_t* out, const char*, int, int, int, int) { if (out) *out = nullptr; return fail(B200_EINVAL, "aruco detector %s", "not built yet"); }
-int b200_aruco_destroy(b200_aruco_t) { return B200_OK; }
-int b200_aruco_max_markers(b200_aruco_t) { return 64; }
-int b200_aruco_detect(b200_aruco_t, const uint8_t*, int, int, int, int64_t, int64_t, b200_marker*, int32_t*, void*) { return fail(B200_EINVAL, "aruco detector %s", "not built yet"); }
-int b200_aruco_detect_host(b200_aruco_t, const uint8_t*, int, int, int, int64_t, int64_t, b200_marker*, int32_t*) { return fail(B200_EINVAL, "aruco detector %s", "not built yet"); }
+#include <math.h>
+#include <float.h>
+#include <algorithm>
+#include <string>
+
+namespace b200 {
+
+constexpr int kMaxCand = 256;        // convex quads per frame
+constexpr int kMaxMarkers = 64;      // output capacity per frame
+constexpr int kMaxPyr = 8;
+constexpr int kMinContour = 70;      // int(3.5*lowResMarkerSize), markerdetector_impl.cpp:3053
+constexpr int kMaxVerts = 128;
+constexpr int kMaxWarp = 50;         // warped patch side: 5*(sqrt(nbits)+2) <= 50 (64-bit dictionaries)
+
+struct ArucoGeom {
+    int w, h;
+    int bpitch;                 // pitch of the padded binary / mask images ((w+2) rounded up)
+    long long bframe;           // bytes per frame of the padded binary image
+    int win;                    // adaptive threshold window
+    int nlev;                   // pyramid levels incl. level 0
+    int lw[kMaxPyr], lh[kMaxPyr], lpitch[kMaxPyr];
+    long long loff[kMaxPyr];    // offset of level l (>=1) inside a frame's pyramid block
+    long long pyr_frame;
+    int max_contours;           // contour descriptors per frame
+    int max_points;             // contour points per frame
+    int nbits, nb, nsub, wsize; // dictionary geometry
+    int ncodes;
+};
+
+struct ContourDesc { int start; int s0; int len; int key; int off; };   // start: index into the padded binary image
+struct Candidate { int cx[4], cy[4]; int key; int contour; };
+struct Kept { float c[8]; int contour; };
+struct Decoded { int id, nrot; };
+
+__constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+__constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+// ------------------------------------------------------------------------------------------------
+// A1: adaptive threshold.  mean = rint(S/bs^2) (ties impossible for odd bs^2); out = src - mean <= -7.
+// One CTA -> 32x32 output tile; (32+2r)^2 replicate-clamped source patch in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kThrTile = 32, kThrMaxR = 7;
+
+__global__ void __launch_bounds__(256)
+k_athresh(const uint8_t* __restrict__ img, long long row_stride, long long frame_stride, const __grid_constant__ ArucoGeom g,
+          uint8_t* __restrict__ bin) {
+    __shared__ uint8_t patch[kThrTile + 2 * kThrMaxR][kThrTile + 2 * kThrMaxR + 2];
+    __shared__ uint16_t hs[kThrTile + 2 * kThrMaxR][kThrTile];
+    const int f = blockIdx.z, x0 = blockIdx.x * kThrTile, y0 = blockIdx.y * kThrTile;
+    const int bs = g.win, r = bs >> 1, side = kThrTile + 2 * r;
+    const uint8_t* src = img + (long long)f * frame_stride;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < side * side; i += 256) {
+        const int py = i / side, px = i - py * side;
+        const int yy = min(max(y0 + py - r, 0), g.h - 1), xx = min(max(x0 + px - r, 0), g.w - 1);
+        patch[py][px] = src[(long long)yy * row_stride + xx];
+    }
+    __syncthreads();
+    for (int i = tid; i < side * kThrTile; i += 256) {
+        const int py = i / kThrTile, px = i - py * kThrTile;
+        int s = 0;
+        for (int k = 0; k < bs; k++) s += patch[py][px + k];
+        hs[py][px] = (uint16_t)s;
+    }
+    __syncthreads();
+    const double scale = 1.0 / ((double)bs * bs);
+    for (int ty = threadIdx.y; ty < kThrTile; ty += 8) {
+        const int x = x0 + threadIdx.x, y = y0 + ty;
+        if (x < g.w && y < g.h) {
+            int s = 0;
+            for (int k = 0; k < bs; k++) s += hs[ty + k][threadIdx.x];
+            const int mean = min(__double2int_rn((double)s * scale), 255);
+            const int v = patch[ty + r][threadIdx.x + r];
+            bin[(long long)f * g.bframe + (long long)(y + 1) * g.bpitch + x + 1] = (v - mean <= -7) ? 1 : 0;
+        }
+    }
 }
+
+// ------------------------------------------------------------------------------------------------
+// pyramid by 1/2 (markerdetector_impl.cpp:1300-1466): cv::resize(INTER_LINEAR) == 2x2 area mean when both
+// factors are exactly 2, else the generic 11-bit fixed-point bilinear (coefficients computed in-kernel in double/float
+// exactly like the host table of the ORB pyramid).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lin_coef(int d, int ssize, int dsize, int& ofs, int& c0, int& c1) {
+    const double scale = (double)ssize / dsize;
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)s);
+    if (s < 0) { s = 0; fx = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
+    ofs = s;
+    c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f));
+    c1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+}
+
+__global__ void __launch_bounds__(256)
+k_halfpyr(const uint8_t* __restrict__ src0, long long srs, long long sfs, int sw, int sh,
+          uint8_t* __restrict__ dst0, int dpitch, long long dfs, int dw, int dh) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* s = src0 + (long long)f * sfs;
+    int v;
+    if (dw * 2 == sw && dh * 2 == sh) {
+        const uint8_t* a = s + (long long)(2 * y) * srs + 2 * x;
+        v = (a[0] + a[1] + a[srs] + a[srs + 1] + 2) >> 2;
+    } else {
+        int ox, cx0, cx1, oy, cy0, cy1;
+        lin_coef(x, sw, dw, ox, cx0, cx1);
+        lin_coef(y, sh, dh, oy, cy0, cy1);
+        const uint8_t* r0 = s + (long long)oy * srs;
+        const uint8_t* r1 = s + (long long)min(oy + 1, sh - 1) * srs;
+        const int x1 = min(ox + 1, sw - 1);
+        const int h0 = r0[ox] * cx0 + r0[x1] * cx1, h1 = r1[ox] * cx0 + r1[x1] * cx1;
+        v = (((cy0 * (h0 >> 4)) >> 16) + ((cy1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    }
+    dst0[(long long)f * dfs + (long long)y * dpitch + x] = (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A2: contours.  Directions as in OpenCV: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y down).
+// A border "step" is (pixel p, direction s back to the previous border pixel); its successor looks at directions
+// s+1, s+2, ... (counter-clockwise) for the first foreground neighbour d, moves there, s' = d+4.  A step whose sweep
+// passes the zero West (East) neighbour is where the raster scan would see a 0->1 (1->0) transition at raster
+// position pos(p) (pos(p)+1).  Suzuki starts every border at its raster-first transition.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_nbrmask(const uint8_t* __restrict__ bin, const __grid_constant__ ArucoGeom g, uint8_t* __restrict__ mask) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= g.w || y >= g.h) return;
+    const long long base = (long long)f * g.bframe + (long long)(y + 1) * g.bpitch + x + 1;
+    const uint8_t* b = bin + base;
+    int m = 0;
+    if (b[0]) {
+        const int P = g.bpitch;
+        m = (b[1] ? 1 : 0) | (b[-P + 1] ? 2 : 0) | (b[-P] ? 4 : 0) | (b[-P - 1] ? 8 : 0) | (b[-1] ? 16 : 0) | (b[P - 1] ? 32 : 0) |
+            (b[P] ? 64 : 0) | (b[P + 1] ? 128 : 0);
+    }
+    mask[base] = (uint8_t)m;
+}
+
+struct Step { int d, k; };     // direction taken and number of directions swept before it (all zero)
+__device__ __forceinline__ Step next_step(int m, int s) {
+    const unsigned r = (((unsigned)m | ((unsigned)m << 8)) >> ((s + 1) & 7)) & 0xffu;
+    Step st;
+    st.k = __ffs(r) - 1;
+    st.d = (s + 1 + st.k) & 7;
+    return st;
+}
+// raster-scan position at which this step is seen as a transition, or INT_MAX
+__device__ __forceinline__ int step_key(int pos, int s, int k) {
+    const int tw = (4 - (s + 1)) & 7, te = (0 - (s + 1)) & 7;      // sweep index of W / E
+    if (tw < k) return pos;
+    if (te < k) return pos + 1;
+    return 0x7fffffff;
+}
+
+__device__ void probe_border(const uint8_t* __restrict__ mask, const ArucoGeom& g, int P, int m0, bool hole, int f,
+                             ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts, int* __restrict__ err) {
+    // Suzuki's first neighbour search: clockwise from NW (outer) / from SE (hole)
+    int s0 = -1;
+    const int from = hole ? 7 : 3;
+    for (int i = 0; i < 7; i++) { const int d = (from - i) & 7; if (m0 & (1 << d)) { s0 = d; break; } }
+    if (s0 < 0) return;                               // isolated pixel: a one-point contour, never a marker
+    const int mykey = P + (hole ? 1 : 0);
+    int p = P, s = s0, n = 0;
+    const int deltas[8] = {1, -g.bpitch + 1, -g.bpitch, -g.bpitch - 1, -1, g.bpitch - 1, g.bpitch, g.bpitch + 1};
+    const int limit = 4 * g.max_points;
+    for (;;) {
+        const int m = n == 0 ? m0 : mask[p];
+        const Step st = next_step(m, s);
+        if (step_key(p, s, st.k) < mykey) return;                 // an earlier transition owns this border (also: a hole probe whose own step sweeps West)
+        p += deltas[st.d];
+        s = (st.d + 4) & 7;
+        n++;
+        if (p == P && s == s0) break;
+        if (n > limit) { atomicExch(err, 3); return; }
+    }
+    if (n > kMinContour) {
+        const int idx = atomicAdd(ncont + f, 1);
+        if (idx >= g.max_contours) { atomicExch(err, 4); return; }
+        const int off = atomicAdd(npts + f, n);
+        if (off + n > g.max_points) { atomicExch(err, 5); return; }
+        ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off;
+        desc[(long long)f * g.max_contours + idx] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_probe(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, ContourDesc* __restrict__ desc,
+        int* __restrict__ ncont, int* __restrict__ npts, int* __restrict__ err) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= g.w || y >= g.h) return;
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    const int P = (y + 1) * g.bpitch + x + 1;
+    const int m = mask[P];
+    if (m == 0) return;                                // background or isolated pixel
+    if (!(m & 16)) probe_border(mask, g, P, m, false, f, desc, ncont, npts, err);     // West is 0: outer-border start?
+    if (!(m & 1)) probe_border(mask, g, P, m, true, f, desc, ncont, npts, err);       // East is 0: hole-border start?
+}
+
+__global__ void __launch_bounds__(128)
+k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ desc,
+       const int* __restrict__ ncont, short2* __restrict__ pts) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(ncont[f], g.max_contours)) return;
+    const ContourDesc c = desc[(long long)f * g.max_contours + i];
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    short2* out = pts + (long long)f * g.max_points + c.off;
+    const int deltas[8] = {1, -g.bpitch + 1, -g.bpitch, -g.bpitch - 1, -1, g.bpitch - 1, g.bpitch, g.bpitch + 1};
+    int p = c.start, s = c.s0;
+    int x = c.start % g.bpitch - 1, y = c.start / g.bpitch - 1;
+    for (int n = 0; n < c.len; n++) {
+        out[n] = make_short2((short)x, (short)y);
+        const Step st = next_step(mask[p], s);
+        p += deltas[st.d]; x += c_dx[st.d]; y += c_dy[st.d];
+        s = (st.d + 4) & 7;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A3: approxPolyDP(closed) + isContourConvex, one warp per contour.  Semantics of cv2 4.13 (distance to the chord
+// SEGMENT, squared, first maximum wins); all split decisions in double like OpenCV.
+// ------------------------------------------------------------------------------------------------
+struct DMax { double v; int i; };
+__device__ __forceinline__ DMax warp_argmax_first(double v, int i) {
+    // maximum value, smallest index among equals; lanes without data pass v < 0
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    DMax r; r.v = v; r.i = i; return r;
+}
+
+constexpr int kQuadWarps = 4;
+
+__global__ void __launch_bounds__(kQuadWarps * 32)
+k_quads(const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ desc, const int* __restrict__ ncont,
+        const short2* __restrict__ pts0, Candidate* __restrict__ cand, int* __restrict__ ncand, int* __restrict__ err) {
+    __shared__ int s_vx[kQuadWarps][kMaxVerts], s_vy[kQuadWarps][kMaxVerts];
+    __shared__ int s_stack[kQuadWarps][2 * 64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.y, ci = blockIdx.x * kQuadWarps + warp;
+    if (ci >= min(ncont[f], g.max_contours)) return;
+    const ContourDesc c = desc[(long long)f * g.max_contours + ci];
+    const short2* P = pts0 + (long long)f * g.max_points + c.off;
+    const int count = c.len;
+    double eps = (double)count * 0.05;
+    eps *= eps;
+    int* vx = s_vx[warp]; int* vy = s_vy[warp]; int* stack = s_stack[warp];
+    int nv = 0, top = 0;
+    bool overflow = false;
+
+    // 1. three "go to the farthest point" hops
+    int pos = 0, rstart = 0;
+    bool le_eps = false;
+    short2 sp = make_short2(0, 0);
+    for (int hop = 0; hop < 3; hop++) {
+        pos = (pos + rstart) % count;
+        sp = P[pos];
+        double best = -1.0; int bi = 0x7fffffff;
+        for (int j = 1 + lane; j < count; j += 32) {
+            int q = pos + j; if (q >= count) q -= count;
+            const short2 pt = P[q];
+            const double dx = pt.x - sp.x, dy = pt.y - sp.y;
+            const double d = dx * dx + dy * dy;
+            if (d > best) { best = d; bi = j; }
+        }
+        const DMax r = warp_argmax_first(best, bi);
+        if (r.v > 0) rstart = r.i;
+        le_eps = !(r.v > eps);            // max_dist (>= 0) <= eps
+    }
+    // 2. initial slices (start of the last hop, farthest point from it)
+    if (!le_eps) {
+        const int s_start = pos % count, s_end = (rstart + s_start) % count;
+        stack[0] = s_end; stack[1] = s_start;      // right slice  [s_end -> s_start]
+        stack[2] = s_start; stack[3] = s_end;      // slice        [s_start -> s_end], processed first
+        top = 2;
+    } else { vx[0] = sp.x; vy[0] = sp.y; nv = 1; }
+    // 3. subdivision
+    while (top > 0) {
+        top--;
+        const int a = stack[2 * top], b = stack[2 * top + 1];
+        const short2 start_pt = P[a], end_pt = P[b];
+        int nint = b - a - 1; if (nint < 0) nint += count;         // interior points a+1 .. b-1 (cyclic)
+        bool le = true;
+        int split = 0;
+        if (nint > 0) {
+            const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+            const double seg2 = dx * dx + dy * dy;
+            double best = -1.0; int bi = 0x7fffffff;
+            for (int j = lane; j < nint; j += 32) {
+                int q = a + 1 + j; if (q >= count) q -= count;
+                const short2 pt = P[q];
+                const double px = pt.x - start_pt.x, py = pt.y - start_pt.y;
+                const double proj = px * dx + py * dy;
+                double d;
+                if (proj < 0) d = px * px + py * py;
+                else if (proj > seg2) { const double ex = pt.x - end_pt.x, ey = pt.y - end_pt.y; d = ex * ex + ey * ey; }
+                else { const double cr = py * dx - px * dy; d = cr * cr / seg2; }
+                if (d > best) { best = d; bi = j; }
+            }
+            const DMax r = warp_argmax_first(best, bi);
+            // OpenCV: max_dist starts at 0 and only strictly larger distances move the split point
+            if (r.v > 0) { split = a + 1 + r.i; if (split >= count) split -= count; le = r.v <= eps; }
+            else le = true;
+        }
+        if (le) {
+            if (nv < kMaxVerts) { if (lane == 0) { vx[nv] = start_pt.x; vy[nv] = start_pt.y; } nv++; }
+            else overflow = true;
+        } else {
+            if (top + 2 > 64) { overflow = true; break; }
+            if (lane == 0) { stack[2 * top] = split; stack[2 * top + 1] = b; stack[2 * top + 2] = a; stack[2 * top + 3] = split; }
+            top += 2;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (overflow) return;              // far more than 4 vertices: not a marker candidate
+    // 4. clean-up pass (serial, a handful of vertices) and the quad / convexity test
+    if (lane == 0) {
+        const int cnt = nv;
+        int new_count = cnt, wpos, p2 = cnt - 1;
+        int sx = vx[p2], sy = vy[p2]; if (++p2 >= cnt) p2 = 0;
+        wpos = p2;
+        int px = vx[p2], py = vy[p2]; if (++p2 >= cnt) p2 = 0;
+        for (int i = 0; i < cnt && new_count > 2; i++) {
+            const int ex = vx[p2], ey = vy[p2]; if (++p2 >= cnt) p2 = 0;
+            const double dx = ex - sx, dy = ey - sy;
+            const double dist = fabs((px - sx) * dy - (py - sy) * dx);
+            const double sip = (double)(px - sx) * (ex - px) + (double)(py - sy) * (ey - py);
+            if (dist * dist <= 0.5 * eps * (dx * dx + dy * dy) && dx != 0 && dy != 0 && sip >= 0) {
+                new_count--;
+                vx[wpos] = sx = ex; vy[wpos] = sy = ey;
+                if (++wpos >= cnt) wpos = 0;
+                px = vx[p2]; py = vy[p2]; if (++p2 >= cnt) p2 = 0;
+                i++;
+                continue;
+            }
+            vx[wpos] = sx = px; vy[wpos] = sy = py;
+            if (++wpos >= cnt) wpos = 0;
+            px = ex; py = ey;
+        }
+        if (new_count == 4) {
+            // isContourConvex on integer points
+            int prx = vx[2], pry = vy[2], cx = vx[3], cy = vy[3];
+            int dx0 = cx - prx, dy0 = cy - pry, orientation = 0;
+            bool convex = true;
+            for (int i = 0; i < 4; i++) {
+                prx = cx; pry = cy; cx = vx[i]; cy = vy[i];
+                const int dx = cx - prx, dy = cy - pry;
+                const int dxdy0 = dx * dy0, dydx0 = dy * dx0;
+                orientation |= (dydx0 > dxdy0) ? 1 : ((dydx0 < dxdy0) ? 2 : 3);
+                if (orientation == 3) { convex = false; break; }
+                dx0 = dx; dy0 = dy;
+            }
+            if (convex) {
+                const int idx = atomicAdd(ncand + f, 1);
+                if (idx < kMaxCand) {
+                    Candidate cd;
+                    for (int k = 0; k < 4; k++) { cd.cx[k] = vx[k]; cd.cy[k] = vy[k]; }
+                    cd.key = c.key; cd.contour = ci;
+                    cand[(long long)f * kMaxCand + idx] = cd;
+                } else atomicExch(err, 6);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prefilterCandidates (markerdetector_impl.cpp:4349-5070), one CTA per frame
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int perimeter_i(const float* c) {       // markerdetector_impl.cpp:11123
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int j = (i + 1) & 3;
+        const float dx = __fsub_rn(c[2 * i], c[2 * j]), dy = __fsub_rn(c[2 * i + 1], c[2 * j + 1]);
+        sum += (int)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(256)
+k_prefilter(const __grid_constant__ ArucoGeom g, const Candidate* __restrict__ cand0, const int* __restrict__ ncand,
+            Kept* __restrict__ kept0, int* __restrict__ nkept) {
+    __shared__ float s_c[kMaxCand][8];
+    __shared__ int s_contour[kMaxCand], s_perim[kMaxCand];
+    __shared__ unsigned char s_rm[kMaxCand];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = min(ncand[f], kMaxCand);
+    const Candidate* cand = cand0 + (long long)f * kMaxCand;
+    // candidate order = contour order = reverse discovery order (cv::findContours returns the newest first)
+    for (int i = tid; i < n; i += blockDim.x) {
+        const Candidate c = cand[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) rank += cand[j].key > c.key;
+        float q[8];
+        for (int k = 0; k < 4; k++) { q[2 * k] = (float)c.cx[k]; q[2 * k + 1] = (float)c.cy[k]; }
+        // consistent corner orientation (4352)
+        const double dx1 = q[2] - q[0], dy1 = q[3] - q[1], dx2 = q[4] - q[0], dy2 = q[5] - q[1];
+        const double o = (dx1 * dy2) - (dy1 * dx2);
+        if (o < 0.0) { float t = q[2]; q[2] = q[6]; q[6] = t; t = q[3]; q[3] = q[7]; q[7] = t; }
+        for (int k = 0; k < 8; k++) s_c[rank][k] = q[k];
+        s_contour[rank] = c.contour;
+        s_perim[rank] = perimeter_i(q);
+        s_rm[rank] = 0;
+    }
+    __syncthreads();
+    const float too_near = (float)g.win;
+    for (int pi = tid; pi < n * n; pi += blockDim.x) {
+        const int i = pi / n, j = pi - i * n;
+        if (j <= i) continue;
+        bool all = true;
+        for (int k = 0; k < 4 && all; k++) {
+            const float dx = __fsub_rn(s_c[i][2 * k], s_c[j][2 * k]), dy = __fsub_rn(s_c[i][2 * k + 1], s_c[j][2 * k + 1]);
+            const float d = (float)sqrt((double)dx * dx + (double)dy * dy);
+            if (!(d < too_near)) all = false;
+        }
+        if (all) { if (s_perim[i] > s_perim[j]) s_rm[j] = 1; else s_rm[i] = 1; }     // flags are only ever set: order-free
+    }
+    __syncthreads();
+    const int bx = (int)__fmul_rn(0.015f, (float)g.w), by = (int)__fmul_rn(0.015f, (float)g.h);
+    for (int i = tid; i < n; i += blockDim.x)
+        for (int k = 0; k < 4; k++) {
+            const float x = s_c[i][2 * k], y = s_c[i][2 * k + 1];
+            if (x < bx || y < by || x > g.w - bx || y > g.h - by) s_rm[i] = 1;
+        }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        Kept* kept = kept0 + (long long)f * kMaxCand;
+        for (int i = 0; i < n; i++)
+            if (!s_rm[i]) {
+                for (int k = 0; k < 8; k++) kept[m].c[k] = s_c[i][k];
+                kept[m].contour = s_contour[i];
+                m++;
+            }
+        nkept[f] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-candidate decode (markerdetector_impl.cpp:6482-6803; dictionary_based.cpp:1062-2509), one CTA per candidate
+// ------------------------------------------------------------------------------------------------
+__device__ bool lu_solve8(double* A, double* b) {           // OpenCV hal::LU with partial pivoting, double
+    const int m = 8;
+    for (int i = 0; i < m; i++) {
+        int k = i;
+        for (int j = i + 1; j < m; j++) if (fabs(A[j * m + i]) > fabs(A[k * m + i])) k = j;
+        if (fabs(A[k * m + i]) < DBL_EPSILON * 100) return false;
+        if (k != i) {
+            for (int j = i; j < m; j++) { const double t = A[i * m + j]; A[i * m + j] = A[k * m + j]; A[k * m + j] = t; }
+            const double t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        const double d = -1 / A[i * m + i];
+        for (int j = i + 1; j < m; j++) {
+            const double alpha = A[j * m + i] * d;
+            for (int c = i + 1; c < m; c++) A[j * m + c] += alpha * A[i * m + c];
+            b[j] += alpha * b[i];
+        }
+    }
+    for (int i = m - 1; i >= 0; i--) {
+        double s = b[i];
+        for (int k = i + 1; k < m; k++) s -= A[i * m + k] * b[k];
+        b[i] = s / A[i * m + i];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128)
+k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame_stride, const uint8_t* __restrict__ pyr,
+         const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, const int* __restrict__ nkept,
+         const unsigned long long* __restrict__ codes, Decoded* __restrict__ dec0) {
+    __shared__ double s_A[64], s_b[8], s_Mi[9];
+    __shared__ uint8_t s_patch[kMaxWarp * kMaxWarp];
+    __shared__ int s_hist[256], s_nz[100], s_tot[100], s_level, s_lvl, s_found[4];
+    __shared__ unsigned long long s_ids[4];
+    __shared__ int s_ok;
+    const int f = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
+    if (k >= nkept[f]) return;
+    const Kept kp = kept0[(long long)f * kMaxCand + k];
+    const int ws = g.wsize;
+    if (tid == 0) {
+        // Marker::getArea (marker.cpp:405-416) and the pyramid level (6556)
+        const float* c = kp.c;
+        const float v01x = __fsub_rn(c[2], c[0]), v01y = __fsub_rn(c[3], c[1]), v03x = __fsub_rn(c[6], c[0]), v03y = __fsub_rn(c[7], c[1]);
+        const float a1 = fabsf(__fsub_rn(__fmul_rn(v01x, v03y), __fmul_rn(v01y, v03x)));
+        const float v21x = __fsub_rn(c[2], c[4]), v21y = __fsub_rn(c[3], c[5]), v23x = __fsub_rn(c[6], c[4]), v23y = __fsub_rn(c[7], c[5]);
+        const float a2 = fabsf(__fsub_rn(__fmul_rn(v21x, v23y), __fmul_rn(v21y, v23x)));
+        const float area = __fdiv_rn(__fadd_rn(a2, a1), 2.f);
+        const float ws2 = __fmul_rn((float)ws, (float)ws);        // std::pow(float(ws), 2.f)
+        int lvl = 0;
+        double p4 = 1.0;
+        for (int p = 1; p < g.nlev; p++) {
+            p4 *= 4.0;
+            if ((double)area / p4 >= (double)ws2) lvl = p; else break;
+        }
+        s_lvl = lvl;
+        const float scale = __fdiv_rn((float)g.lw[lvl], (float)g.w);
+        float sc[8];
+        for (int i = 0; i < 8; i++) sc[i] = __fmul_rn(c[i], scale);
+        const float q = (float)(ws - 1);
+        const float dst[8] = {0.f, 0.f, q, 0.f, q, q, 0.f, q};
+        // getPerspectiveTransform: the products are formed in float (Point2f operands), the system is double
+        for (int i = 0; i < 4; i++) {
+            const float sx = sc[2 * i], sy = sc[2 * i + 1], dx = dst[2 * i], dy = dst[2 * i + 1];
+            double* r0 = s_A + i * 8; double* r1 = s_A + (i + 4) * 8;
+            r0[0] = r1[3] = sx; r0[1] = r1[4] = sy; r0[2] = r1[5] = 1;
+            r0[3] = r0[4] = r0[5] = r1[0] = r1[1] = r1[2] = 0;
+            r0[6] = (double)__fmul_rn(-sx, dx); r0[7] = (double)__fmul_rn(-sy, dx);
+            r1[6] = (double)__fmul_rn(-sx, dy); r1[7] = (double)__fmul_rn(-sy, dy);
+            s_b[i] = dx; s_b[i + 4] = dy;
+        }
+        double M[9];
+        if (lu_solve8(s_A, s_b)) { for (int i = 0; i < 8; i++) M[i] = s_b[i]; M[8] = 1.; }
+        else for (int i = 0; i < 9; i++) M[i] = 0;
+        // cv::invert 3x3
+        double d = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+        if (d != 0.) {
+            d = 1. / d;
+            s_Mi[0] = (M[4] * M[8] - M[5] * M[7]) * d; s_Mi[1] = (M[2] * M[7] - M[1] * M[8]) * d; s_Mi[2] = (M[1] * M[5] - M[2] * M[4]) * d;
+            s_Mi[3] = (M[5] * M[6] - M[3] * M[8]) * d; s_Mi[4] = (M[0] * M[8] - M[2] * M[6]) * d; s_Mi[5] = (M[2] * M[3] - M[0] * M[5]) * d;
+            s_Mi[6] = (M[3] * M[7] - M[4] * M[6]) * d; s_Mi[7] = (M[1] * M[6] - M[0] * M[7]) * d; s_Mi[8] = (M[0] * M[4] - M[1] * M[3]) * d;
+        } else for (int i = 0; i < 9; i++) s_Mi[i] = 0;
+    }
+    for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
+    if (tid < 100) { s_nz[tid] = 0; s_tot[tid] = 0; }
+    __syncthreads();
+    // warpPerspective INTER_LINEAR, BORDER_CONSTANT 0 (SURVEY A-8)
+    const int lvl = s_lvl;
+    const uint8_t* src; long long spitch; const int sw = g.lw[lvl], sh = g.lh[lvl];
+    if (lvl == 0) { src = img0 + (long long)f * frame_stride; spitch = row_stride; }
+    else { src = pyr + (long long)f * g.pyr_frame + g.loff[lvl]; spitch = g.lpitch[lvl]; }
+    for (int i = tid; i < ws * ws; i += blockDim.x) {
+        const int y = i / ws, x = i - y * ws;
+        const double X0 = s_Mi[0] * 0 + s_Mi[1] * y + s_Mi[2];
+        const double Y0 = s_Mi[3] * 0 + s_Mi[4] * y + s_Mi[5];
+        const double W0 = s_Mi[6] * 0 + s_Mi[7] * y + s_Mi[8];
+        double W = W0 + s_Mi[6] * x;
+        W = W ? 32. / W : 0;
+        const double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + s_Mi[0] * x) * W));
+        const double fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + s_Mi[3] * x) * W));
+        const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+        int sx = X >> 5, sy = Y >> 5;
+        sx = max(-32768, min(32767, sx)); sy = max(-32768, min(32767, sy));
+        const int ax = X & 31, ay = Y & 31;
+        int v = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int xx = sx + (t & 1), yy = sy + (t >> 1);
+            const int wgt = ((t & 1) ? ax : 32 - ax) * ((t >> 1) ? ay : 32 - ay) * 32;
+            if (xx >= 0 && xx < sw && yy >= 0 && yy < sh) v += src[(long long)yy * spitch + xx] * wgt;
+        }
+        const int px = (v + (1 << 14)) >> 15;
+        s_patch[i] = (uint8_t)px;
+        atomicAdd(&s_hist[px], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {       // Otsu (SURVEY A-9)
+        double mu = 0; const double scale = 1. / ((double)ws * ws);
+        for (int i = 0; i < 256; i++) mu += i * (double)s_hist[i];
+        mu *= scale;
+        double mu1 = 0, q1 = 0, max_sigma = 0; int max_val = 0;
+        for (int i = 0; i < 256; i++) {
+            const double p_i = s_hist[i] * scale;
+            mu1 *= q1;
+            q1 += p_i;
+            const double q2 = 1. - q1;
+            if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) continue;
+            mu1 = (mu1 + i * p_i) / q1;
+            const double mu2 = (mu - q1 * mu1) / q2;
+            const double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+            if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+        }
+        s_level = max_val;
+    }
+    __syncthreads();
+    const int nsub = g.nsub;
+    for (int i = tid; i < ws * ws; i += blockDim.x) {
+        const int y = i / ws, x = i - y * ws;
+        const int my = (int)__fdiv_rn(__fmul_rn((float)nsub, (float)y), (float)ws);
+        const int mx = (int)__fdiv_rn(__fmul_rn((float)nsub, (float)x), (float)ws);
+        if (s_patch[i] > s_level) atomicAdd(&s_nz[my * 10 + mx], 1);
+        atomicAdd(&s_tot[my * 10 + mx], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int nb = g.nb;
+        unsigned char bits[10][10];
+        bool ok = true;
+        for (int y = 0; y < nsub; y++) for (int x = 0; x < nsub; x++) bits[y][x] = s_nz[y * 10 + x] > s_tot[y * 10 + x] / 2;
+        for (int y = 0; y < nsub && ok; y++) {
+            const int inc = (y == 0 || y == nsub - 1) ? 1 : nsub - 1;
+            for (int x = 0; x < nsub; x += inc) if (bits[y][x]) { ok = false; break; }
+        }
+        if (ok) {
+            unsigned char in[8][8], tmp[8][8];
+            for (int y = 0; y < nb; y++) for (int x = 0; x < nb; x++) in[y][x] = bits[y + 1][x + 1];
+            for (int r = 0; r < 4; r++) {
+                unsigned long long code = 0; int b = 0;
+                for (int y = nb - 1; y >= 0; y--) for (int x = nb - 1; x >= 0; x--) code |= (unsigned long long)in[y][x] << b++;
+                s_ids[r] = code;
+                for (int i = 0; i < nb; i++) for (int j = 0; j < nb; j++) tmp[i][j] = in[nb - j - 1][i];
+                for (int i = 0; i < nb; i++) for (int j = 0; j < nb; j++) in[i][j] = tmp[i][j];
+            }
+            if (s_ids[0] == 0) ok = false;
+        }
+        s_ok = ok;
+        for (int r = 0; r < 4; r++) s_found[r] = 0x7fffffff;
+    }
+    __syncthreads();
+    Decoded out; out.id = -1; out.nrot = 0;
+    if (s_ok) {
+        for (int i = tid; i < g.ncodes; i += blockDim.x) {
+            const unsigned long long c = codes[i];
+#pragma unroll
+            for (int r = 0; r < 4; r++) if (c == s_ids[r]) atomicMin(&s_found[r], i);      // first index wins for repeated codes
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_ok) for (int r = 0; r < 4; r++) if (s_found[r] != 0x7fffffff) { out.id = s_found[r]; out.nrot = r; break; }
+        dec0[(long long)f * kMaxCand + k] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort / de-duplicate / CORNER_LINES refinement, one CTA per frame
+// ------------------------------------------------------------------------------------------------
+// cv::solve(A (m x 2), b, DECOMP_SVD) for A = [t 1]: one-sided Jacobi on the two columns + back-substitution.
+// Columns live in global scratch (a0[i], a1[i]); rhs in bb[i].  Warp-cooperative; returns x0, x1 on all lanes.
+__device__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ void svd_solve_m2(float* a0, float* a1, const float* bb, int m, int lane, float& x0, float& x1) {
+    const float eps = FLT_EPSILON * 2;
+    double W0 = 0, W1 = 0;
+    for (int k = lane; k < m; k += 32) { W0 += (double)a0[k] * a0[k]; W1 += (double)a1[k] * a1[k]; }
+    W0 = warp_sum(W0); W1 = warp_sum(W1);
+    float v00 = 1.f, v01 = 0.f, v10 = 0.f, v11 = 1.f;        // Vt rows
+    const int max_iter = max(m, 30);
+    for (int iter = 0; iter < max_iter; iter++) {
+        double p = 0;
+        for (int k = lane; k < m; k += 32) p += (double)a0[k] * a1[k];
+        p = warp_sum(p);
+        if (fabs(p) <= eps * sqrt(W0 * W1)) break;
+        p *= 2;
+        const double beta = W0 - W1, gamma = hypot(p, beta);
+        float c, s;
+        if (beta < 0) {
+            const double delta = (gamma - beta) * 0.5;
+            s = (float)sqrt(delta / gamma);
+            c = (float)(p / (gamma * s * 2));
+        } else {
+            c = (float)sqrt((gamma + beta) / (gamma * 2));
+            s = (float)(p / (gamma * c * 2));
+        }
+        double a = 0, b = 0;
+        for (int k = lane; k < m; k += 32) {
+            const float t0 = __fadd_rn(__fmul_rn(c, a0[k]), __fmul_rn(s, a1[k]));
+            const float t1 = __fadd_rn(__fmul_rn(-s, a0[k]), __fmul_rn(c, a1[k]));
+            a0[k] = t0; a1[k] = t1;
+            a += (double)t0 * t0; b += (double)t1 * t1;
+        }
+        W0 = warp_sum(a); W1 = warp_sum(b);
+        {
+            float t0 = __fadd_rn(__fmul_rn(c, v00), __fmul_rn(s, v10)), t1 = __fadd_rn(__fmul_rn(-s, v00), __fmul_rn(c, v10));
+            v00 = t0; v10 = t1;
+            t0 = __fadd_rn(__fmul_rn(c, v01), __fmul_rn(s, v11)); t1 = __fadd_rn(__fmul_rn(-s, v01), __fmul_rn(c, v11));
+            v01 = t0; v11 = t1;
+        }
+        __syncwarp();
+    }
+    double s0 = 0, s1 = 0;
+    for (int k = lane; k < m; k += 32) { s0 += (double)a0[k] * a0[k]; s1 += (double)a1[k] * a1[k]; }
+    double w0 = sqrt(warp_sum(s0)), w1 = sqrt(warp_sum(s1));
+    bool swapped = false;
+    if (w0 < w1) { const double t = w0; w0 = w1; w1 = t; swapped = true; }
+    float* u0 = swapped ? a1 : a0; float* u1 = swapped ? a0 : a1;
+    const float vt0x = swapped ? v10 : v00, vt0y = swapped ? v11 : v01, vt1x = swapped ? v00 : v10, vt1y = swapped ? v01 : v11;
+    const float wf0 = (float)w0, wf1 = (float)w1;
+    const float sc0 = (float)(w0 > FLT_MIN ? 1 / w0 : 0.), sc1 = (float)(w1 > FLT_MIN ? 1 / w1 : 0.);
+    double d0 = 0, d1 = 0;       // u_i . b with u = column / w (float), float products, double sums
+    for (int k = lane; k < m; k += 32) {
+        d0 += (double)__fmul_rn(__fmul_rn(u0[k], sc0), bb[k]);
+        d1 += (double)__fmul_rn(__fmul_rn(u1[k], sc1), bb[k]);
+    }
+    d0 = warp_sum(d0); d1 = warp_sum(d1);
+    const double threshold = ((double)wf0 + (double)wf1) * eps;
+    float r0 = 0.f, r1 = 0.f;
+    if (fabs((double)wf0) > threshold) { const double sv = d0 * (1 / (double)wf0); r0 = (float)(r0 + sv * vt0x); r1 = (float)(r1 + sv * vt0y); }
+    if (fabs((double)wf1) > threshold) { const double sv = d1 * (1 / (double)wf1); r0 = (float)(r0 + sv * vt1x); r1 = (float)(r1 + sv * vt1y); }
+    x0 = r0; x1 = r1;
+}
+
+// 2x2 system of getCrossPoint (11899-12049), same SVD path, single thread
+__device__ void svd_solve_2x2(const float A[4], const float B[2], float X[2]) {
+    float a0[2] = {A[0], A[2]}, a1[2] = {A[1], A[3]};      // columns
+    const float eps = FLT_EPSILON * 2;
+    double W0 = (double)a0[0] * a0[0] + (double)a0[1] * a0[1], W1 = (double)a1[0] * a1[0] + (double)a1[1] * a1[1];
+    float v00 = 1.f, v01 = 0.f, v10 = 0.f, v11 = 1.f;
+    for (int iter = 0; iter < 30; iter++) {
+        double p = (double)a0[0] * a1[0] + (double)a0[1] * a1[1];
+        if (fabs(p) <= eps * sqrt(W0 * W1)) break;
+        p *= 2;
+        const double beta = W0 - W1, gamma = hypot(p, beta);
+        float c, s;
+        if (beta < 0) { const double delta = (gamma - beta) * 0.5; s = (float)sqrt(delta / gamma); c = (float)(p / (gamma * s * 2)); }
+        else { c = (float)sqrt((gamma + beta) / (gamma * 2)); s = (float)(p / (gamma * c * 2)); }
+        double a = 0, b = 0;
+        for (int k = 0; k < 2; k++) {
+            const float t0 = __fadd_rn(__fmul_rn(c, a0[k]), __fmul_rn(s, a1[k])), t1 = __fadd_rn(__fmul_rn(-s, a0[k]), __fmul_rn(c, a1[k]));
+            a0[k] = t0; a1[k] = t1; a += (double)t0 * t0; b += (double)t1 * t1;
+        }
+        W0 = a; W1 = b;
+        float t0 = __fadd_rn(__fmul_rn(c, v00), __fmul_rn(s, v10)), t1 = __fadd_rn(__fmul_rn(-s, v00), __fmul_rn(c, v10));
+        v00 = t0; v10 = t1;
+        t0 = __fadd_rn(__fmul_rn(c, v01), __fmul_rn(s, v11)); t1 = __fadd_rn(__fmul_rn(-s, v01), __fmul_rn(c, v11));
+        v01 = t0; v11 = t1;
+    }
+    double w0 = sqrt((double)a0[0] * a0[0] + (double)a0[1] * a0[1]), w1 = sqrt((double)a1[0] * a1[0] + (double)a1[1] * a1[1]);
+    bool swapped = false;
+    if (w0 < w1) { const double t = w0; w0 = w1; w1 = t; swapped = true; }
+    const float* u0 = swapped ? a1 : a0; const float* u1 = swapped ? a0 : a1;
+    const float vt0x = swapped ? v10 : v00, vt0y = swapped ? v11 : v01, vt1x = swapped ? v00 : v10, vt1y = swapped ? v01 : v11;
+    const float wf0 = (float)w0, wf1 = (float)w1;
+    const float sc0 = (float)(w0 > FLT_MIN ? 1 / w0 : 0.), sc1 = (float)(w1 > FLT_MIN ? 1 / w1 : 0.);
+    const double d0 = (double)__fmul_rn(__fmul_rn(u0[0], sc0), B[0]) + (double)__fmul_rn(__fmul_rn(u0[1], sc0), B[1]);
+    const double d1 = (double)__fmul_rn(__fmul_rn(u1[0], sc1), B[0]) + (double)__fmul_rn(__fmul_rn(u1[1], sc1), B[1]);
+    const double threshold = ((double)wf0 + (double)wf1) * eps;
+    float r0 = 0.f, r1 = 0.f;
+    if (fabs((double)wf0) > threshold) { const double sv = d0 * (1 / (double)wf0); r0 = (float)(r0 + sv * vt0x); r1 = (float)(r1 + sv * vt0y); }
+    if (fabs((double)wf1) > threshold) { const double sv = d1 * (1 / (double)wf1); r0 = (float)(r0 + sv * vt1x); r1 = (float)(r1 + sv * vt1y); }
+    X[0] = r0; X[1] = r1;
+}
+
+struct FMin { float v; int i; };
+__device__ __forceinline__ FMin warp_argmin_first(float v, int i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    FMin r; r.v = v; r.i = i; return r;
+}
+
+constexpr int kFinWarps = 8;
+
+__global__ void __launch_bounds__(kFinWarps * 32)
+k_finalize(const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, const int* __restrict__ nkept,
+           const Decoded* __restrict__ dec0, const ContourDesc* __restrict__ desc0, const short2* __restrict__ pts0,
+           float* __restrict__ scratch0, b200_marker* __restrict__ out0, int* __restrict__ counts, int out_cap, int* __restrict__ err) {
+    __shared__ int s_idx[kMaxCand], s_id[kMaxCand], s_perim[kMaxCand], s_n, s_m;
+    __shared__ float s_c[kMaxCand][8];
+    __shared__ unsigned char s_rm[kMaxCand];
+    __shared__ int s_final[kMaxMarkers];
+    __shared__ int s_src[kMaxCand];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nk = min(nkept[f], kMaxCand);
+    const Kept* kept = kept0 + (long long)f * kMaxCand;
+    const Decoded* dec = dec0 + (long long)f * kMaxCand;
+    if (tid == 0) {
+        // successful candidates in candidate order, corners rotated (std::rotate(begin, begin + 4 - nRot, end), 6779)
+        int n = 0;
+        for (int k = 0; k < nk; k++) if (dec[k].id >= 0) { s_idx[n] = k; n++; }
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int k = s_idx[i];
+        const Decoded d = dec[k];
+        // stable sort by id (8159): rank = markers with a smaller id, or the same id earlier in candidate order
+        int rank = 0;
+        for (int j = 0; j < n; j++) { const int idj = dec[s_idx[j]].id; rank += (idj < d.id) || (idj == d.id && j < i); }
+        float q[8];
+        for (int c = 0; c < 4; c++) { const int s = (c + 4 - d.nrot) & 3; q[2 * c] = kept[k].c[2 * s]; q[2 * c + 1] = kept[k].c[2 * s + 1]; }
+        for (int c = 0; c < 8; c++) s_c[rank][c] = q[c];
+        s_id[rank] = d.id; s_perim[rank] = perimeter_i(q); s_rm[rank] = 0;
+        s_src[rank] = k;                      // which kept candidate (=> contour) the sorted marker came from
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // duplicate removal (8159-8311): serial flag semantics
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n && !s_rm[i]; j++)
+                if (s_id[i] == s_id[j]) { if (s_perim[i] < s_perim[j]) s_rm[i] = 1; else s_rm[j] = 1; }
+        int m = 0;
+        for (int i = 0; i < n; i++) if (!s_rm[i]) { if (m < kMaxMarkers && m < out_cap) s_final[m++] = i; else atomicExch(err, 7); }
+        s_m = m;
+        counts[f] = m;
+    }
+    __syncthreads();
+    const int m = s_m;
+    b200_marker* out = out0 + (long long)f * out_cap;
+    // CORNER_LINES refinement (8979-12049): one warp per marker
+    for (int mi = warp; mi < m; mi += kFinWarps) {
+        const int i = s_final[mi];
+        const ContourDesc cd = desc0[(long long)f * g.max_contours + kept[s_src[i]].contour];
+        const short2* cp = pts0 + (long long)f * g.max_points + cd.off;
+        const int nc = cd.len;
+        float c[8];
+        for (int k = 0; k < 8; k++) c[k] = s_c[i][k];
+        int ci[4];
+        for (int k = 0; k < 4; k++) {
+            float best = FLT_MAX; int bi = 0x7fffffff;
+            for (int j = lane; j < nc; j += 32) {
+                const float dx = __fsub_rn((float)cp[j].x, c[2 * k]), dy = __fsub_rn((float)cp[j].y, c[2 * k + 1]);
+                const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                if (d < best) { best = d; bi = j; }
+            }
+            const FMin r = warp_argmin_first(best, bi);
+            ci[k] = r.v < FLT_MAX ? r.i : -1;
+        }
+        bool inverse;
+        if ((ci[1] > ci[0]) && (ci[2] > ci[1] || ci[2] < ci[0])) inverse = false;
+        else if (ci[2] > ci[1] && ci[2] < ci[0]) inverse = false;
+        else inverse = true;
+        // the four sides as index walks (8647-8686 incl. its wrap-around quirks): side l = {first index, count}
+        float line[4][3];
+        bool ok = true;
+        float* sa0 = scratch0 + ((long long)f * g.max_points + cd.off) * 3;      // 3 floats per contour point: a0, a1, b
+        for (int l = 0; l < 4 && ok; l++) {
+            const int stop = ci[(l + 1) & 3];
+            // the reference loop `for (j = ci[l]; j != stop; j += inc) { wrap; push(pts[j]); if (j == stop) break; }` in closed
+            // form: first visited index and number of points.  Quirks kept: walking forwards the end corner is included
+            // only when it is index 0 (reached through the wrap); walking backwards index 0 is replaced by n-1 before
+            // use (pts[0] is never taken) and the end corner is included only when it is n-1.
+            const int start = ci[l];
+            int cnt = 0, first = start;
+            if (start != stop) {
+                if (!inverse) {
+                    if (stop > start) cnt = stop - start;
+                    else cnt = (nc - start) + stop + (stop == 0 ? 1 : 0);
+                } else if (start == 0) {
+                    first = nc - 1;
+                    cnt = (stop == nc - 1) ? 1 : (nc - 1 - stop);
+                } else {
+                    if (stop < start) cnt = start - stop;
+                    else cnt = start + ((stop == nc - 1) ? 1 : (nc - 1 - stop));
+                }
+            }
+            if (cnt < 2) { ok = false; break; }
+            float* a0 = sa0;                         // sides are processed one after the other: the block is reused
+            float* a1 = a0 + nc; float* bb = a1 + nc;    // every side has at most nc points
+            // bounding box
+            float minx = FLT_MAX, maxx = -FLT_MAX, miny = FLT_MAX, maxy = -FLT_MAX;
+            for (int t = lane; t < cnt; t += 32) {
+                int q;
+                if (!inverse) { q = first + t; if (q >= nc) q -= nc; }
+                else { q = first - t; if (q <= 0) q += nc - 1; }
+                const float x = (float)cp[q].x, y = (float)cp[q].y;
+                minx = fminf(minx, x); maxx = fmaxf(maxx, x); miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+                miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+            }
+            const bool xmajor = __fsub_rn(maxx, minx) > __fsub_rn(maxy, miny);
+            for (int t = lane; t < cnt; t += 32) {
+                int q;
+                if (!inverse) { q = first + t; if (q >= nc) q -= nc; }
+                else { q = first - t; if (q <= 0) q += nc - 1; }
+                const float x = (float)cp[q].x, y = (float)cp[q].y;
+                a0[t] = xmajor ? x : y; a1[t] = 1.f; bb[t] = xmajor ? y : x;
+            }
+            __syncwarp();
+            float x0, x1;
+            svd_solve_m2(a0, a1, bb, cnt, lane, x0, x1);
+            if (xmajor) { line[l][0] = x0; line[l][1] = -1.f; line[l][2] = x1; }
+            else { line[l][0] = -1.f; line[l][1] = x0; line[l][2] = x1; }
+            __syncwarp();
+        }
+        if (ok) {
+            for (int k = 0; k < 4; k++) {
+                const float* l1 = line[(k + 3) & 3]; const float* l2 = line[k];
+                const float A[4] = {l1[0], l1[1], l2[0], l2[1]}, B[2] = {-l1[2], -l2[2]};
+                float X[2];
+                svd_solve_2x2(A, B, X);
+                c[2 * k] = X[0]; c[2 * k + 1] = X[1];
+            }
+        }
+        if (lane == 0) {
+            out[mi].id = s_id[i];
+            for (int k = 0; k < 8; k++) out[mi].xy[k] = c[k];
+        }
+    }
+}
+
+}  // namespace b200
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace b200;
+
+struct b200_aruco_s {
+    int device;
+    cudaStream_t stream;
+    int max_w, max_h, max_batch;
+    int nbits, ncodes;
+    std::string dict;
+    unsigned long long* d_codes;
+    int cur_w, cur_h;
+    ArucoGeom geom;
+    uint8_t *d_bin, *d_mask, *d_pyr;
+    ContourDesc* d_desc; short2* d_pts; float* d_scratch;
+    Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
+    int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_err;
+    size_t cap_bin, cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch;
+    // staging for the host API
+    uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
+};
+
+namespace {
+
+struct DictTable { const char* name; int nbits; int n; const unsigned long long* codes; };
+#define DICT_BEGIN(NAME, NBITS, TAU, N) static const unsigned long long codes_##NAME[] = {
+#define C(x) x##ULL,
+#define DICT_END(NAME) };
+#include "aruco_dicts.inc"
+#undef DICT_BEGIN
+#undef C
+#undef DICT_END
+#define DICT_BEGIN(NAME, NBITS, TAU, N) {#NAME, NBITS, N, codes_##NAME},
+#define C(x)
+#define DICT_END(NAME)
+static const DictTable kDicts[] = {
+#include "aruco_dicts.inc"
+};
+#undef DICT_BEGIN
+#undef C
+#undef DICT_END
+
+template <typename T> int ensure_buf(T*& p, size_t& cap, size_t need) {
+    if (need <= cap && p) return B200_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    B200_CUDA(cudaMalloc((void**)&p, need));
+    cap = need;
+    return B200_OK;
+}
+
+int aruco_geometry(b200_aruco_s* h, int w, int hh) {
+    if (w == h->cur_w && hh == h->cur_h) return B200_OK;
+    ArucoGeom& g = h->geom;
+    memset(&g, 0, sizeof(g));
+    g.w = w; g.h = hh;
+    g.bpitch = (int)align_up(w + 2, 16);
+    g.bframe = (long long)g.bpitch * (hh + 2);
+    int win = std::max(3, (int)(15 * float(w) / 1920.));         // markerdetector_impl.cpp:3769-3867
+    if (win % 2 == 0) win++;
+    if (win > 2 * kThrMaxR + 1) return fail(B200_EINVAL, "image wider than %s", "the 15-px threshold window supports (1920)");
+    g.win = win;
+    g.nbits = h->nbits; g.nb = (int)sqrt((double)h->nbits); g.nsub = g.nb + 2; g.wsize = 5 * g.nsub; g.ncodes = h->ncodes;
+    // pyramid (1300-1466): halve while width > 2*warpSize
+    g.lw[0] = w; g.lh[0] = hh; g.nlev = 1;
+    {
+        int cw = w, nl = 1;
+        while (cw > 2 * g.wsize) { cw /= 2; nl++; }
+        long long off = 0;
+        for (int l = 1; l < nl && l < kMaxPyr; l++) {
+            const int lw = g.lw[l - 1] / 2, lh = g.lh[l - 1] / 2;
+            if (lw < 1 || lh < 1) break;
+            g.lw[l] = lw; g.lh[l] = lh; g.lpitch[l] = (int)align_up(lw, 16); g.loff[l] = off;
+            off += align_up((long long)g.lpitch[l] * lh, 256);
+            g.nlev = l + 1;
+        }
+        g.pyr_frame = std::max<long long>(off, 256);
+    }
+    g.max_points = w * hh;
+    g.max_contours = w * hh / (kMinContour + 1) + 1;       // borders longer than 70 points sharing w*h points
+    const size_t B = (size_t)h->max_batch;
+    int rc;
+    const size_t old_bin = h->cap_bin;
+    if ((rc = ensure_buf(h->d_bin, h->cap_bin, (size_t)g.bframe * B))) return rc;
+    if ((rc = ensure_buf(h->d_mask, h->cap_mask, (size_t)g.bframe * B))) return rc;
+    (void)old_bin;
+    B200_CUDA(cudaMemset(h->d_bin, 0, (size_t)g.bframe * B));       // the 1-px zero frame is never written afterwards
+    B200_CUDA(cudaMemset(h->d_mask, 0, (size_t)g.bframe * B));
+    if ((rc = ensure_buf(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame * B))) return rc;
+    if ((rc = ensure_buf(h->d_desc, h->cap_desc, sizeof(ContourDesc) * (size_t)g.max_contours * B))) return rc;
+    if ((rc = ensure_buf(h->d_pts, h->cap_pts, sizeof(short2) * (size_t)g.max_points * B))) return rc;
+    if ((rc = ensure_buf(h->d_scratch, h->cap_scratch, sizeof(float) * 3 * ((size_t)g.max_points * B + 64)))) return rc;
+    h->cur_w = w; h->cur_h = hh;
+    return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int max_h, int max_batch, int device) {
+    if (!out) return fail(B200_EINVAL, "null %s", "out");
+    *out = nullptr;
+    if (!dict_name || max_w < 1 || max_h < 1 || max_batch < 1) return fail(B200_EINVAL, "bad %s parameters", "detector");
+    const DictTable* dt = nullptr;
+    for (const auto& d : kDicts) if (std::string(d.name) == dict_name) dt = &d;
+    if (!dt) return fail(B200_EINVAL, "unknown dictionary '%s'", dict_name);
+    int rc = use_device(device);
+    if (rc) return rc;
+    b200_aruco_s* h = new (std::nothrow) b200_aruco_s();
+    if (!h) return B200_ENOMEM;
+    h->device = device; h->max_w = max_w; h->max_h = max_h; h->max_batch = max_batch; h->cur_w = h->cur_h = -1;
+    h->dict = dict_name; h->nbits = dt->nbits; h->ncodes = dt->n;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_codes, sizeof(unsigned long long) * dt->n) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_codes, dt->codes, sizeof(unsigned long long) * dt->n, cudaMemcpyHostToDevice) == cudaSuccess;
+    const size_t B = (size_t)max_batch;
+    ok = ok && cudaMalloc((void**)&h->d_cand, sizeof(Candidate) * kMaxCand * B) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_kept, sizeof(Kept) * kMaxCand * B) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_dec, sizeof(Decoded) * kMaxCand * B) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_ncont, 4 * B * 4 + 4) == cudaSuccess;
+    if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
+    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_err = h->d_nkept + B;
+    cudaMemset(h->d_ncont, 0, 4 * B * 4 + 4);
+    if ((rc = aruco_geometry(h, max_w, max_h))) { b200_aruco_destroy(h); return rc; }
+    *out = h;
+    return B200_OK;
+}
+
+int b200_aruco_destroy(b200_aruco_t h) {
+    if (!h) return B200_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_codes); cudaFree(h->d_bin); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont);
+    cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B200_OK;
+}
+
+int b200_aruco_max_markers(b200_aruco_t h) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    return kMaxMarkers;
+}
+
+int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                      b200_marker* markers, int32_t* counts, void* stream) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    if (n < 0 || w < 0 || hh < 0) return fail(B200_EINVAL, "negative %s", "size");
+    if (n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
+    if (n == 0) return B200_OK;
+    if (!markers || !counts) return fail(B200_EINVAL, "null %s", "output pointer");
+    int rc = use_device(h->device);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (w < 8 || hh < 8) { B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4, st)); return B200_OK; }
+    if (!imgs) return fail(B200_EINVAL, "null %s", "image pointer");
+    if (rs < w || (n > 1 && fs < rs * (hh - 1) + w)) return fail(B200_EINVAL, "bad %s", "strides");
+    if ((rc = aruco_geometry(h, w, hh))) return rc;
+    const ArucoGeom& g = h->geom;
+    B200_CUDA(cudaMemsetAsync(h->d_ncont, 0, 4 * (size_t)h->max_batch * 4, st));
+    dim3 blk(32, 8);
+    dim3 gt((w + kThrTile - 1) / kThrTile, (hh + kThrTile - 1) / kThrTile, n);
+    B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, h->d_bin);
+    for (int l = 1; l < g.nlev; l++) {
+        const uint8_t* src = l == 1 ? imgs : h->d_pyr + g.loff[l - 1];
+        const long long srs = l == 1 ? rs : g.lpitch[l - 1], sfs = l == 1 ? fs : g.pyr_frame;
+        dim3 gp((g.lw[l] + 31) / 32, (g.lh[l] + 7) / 8, n);
+        B200_LAUNCH(k_halfpyr, gp, blk, 0, st, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], h->d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
+    }
+    dim3 gm((w + 31) / 32, (hh + 7) / 8, n);
+    B200_LAUNCH(k_nbrmask, gm, blk, 0, st, h->d_bin, g, h->d_mask);
+    B200_LAUNCH(k_probe, gm, blk, 0, st, h->d_mask, g, h->d_desc, h->d_ncont, h->d_npts, h->d_err);
+    // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
+    {
+        const int grid_c = g.max_contours;
+        dim3 ge((grid_c + 127) / 128, n);
+        B200_LAUNCH(k_emit, ge, 128, 0, st, h->d_mask, g, h->d_desc, h->d_ncont, h->d_pts);
+        dim3 gq((grid_c + kQuadWarps - 1) / kQuadWarps, n);
+        B200_LAUNCH(k_quads, gq, kQuadWarps * 32, 0, st, g, h->d_desc, h->d_ncont, h->d_pts, h->d_cand, h->d_ncand, h->d_err);
+    }
+    B200_LAUNCH(k_prefilter, n, 256, 0, st, g, h->d_cand, h->d_ncand, h->d_kept, h->d_nkept);
+    dim3 gd(kMaxCand, n);
+    B200_LAUNCH(k_decode, gd, 128, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_kept, h->d_nkept, h->d_codes, h->d_dec);
+    B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, h->d_kept, h->d_nkept, h->d_dec, h->d_desc, h->d_pts, h->d_scratch,
+                markers, counts, kMaxMarkers, h->d_err);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+// validation taps of the LAST call: out4 = {borders longer than 70 points, convex quads, candidates after the prefilter, markers};
+// corners [cap][8] / ids [cap] = the prefiltered candidates in order with their decoded id (-1: not a marker)
+int b200_aruco_debug(b200_aruco_t h, int frame, int32_t* out4, float* corners, int32_t* ids, int cap) {
+    if (!h || !out4) return fail(B200_EINVAL, "null %s", "argument");
+    if (frame < 0 || frame >= h->max_batch) return fail(B200_EINVAL, "no such %s", "frame");
+    int rc = use_device(h->device);
+    if (rc) return rc;
+    B200_CUDA(cudaDeviceSynchronize());
+    const int B = h->max_batch;
+    B200_CUDA(cudaMemcpy(&out4[0], h->d_ncont + frame, 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(&out4[1], h->d_ncand + frame, 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(&out4[2], h->d_nkept + frame, 4, cudaMemcpyDeviceToHost));
+    (void)B;
+    const int nk = std::min(out4[2], kMaxCand);
+    std::vector<Kept> k(std::max(nk, 1)); std::vector<Decoded> d(std::max(nk, 1));
+    if (nk) {
+        B200_CUDA(cudaMemcpy(k.data(), h->d_kept + (size_t)frame * kMaxCand, sizeof(Kept) * nk, cudaMemcpyDeviceToHost));
+        B200_CUDA(cudaMemcpy(d.data(), h->d_dec + (size_t)frame * kMaxCand, sizeof(Decoded) * nk, cudaMemcpyDeviceToHost));
+    }
+    int nm = 0;
+    for (int i = 0; i < nk; i++) {
+        if (d[i].id >= 0) nm++;
+        if (corners && ids && i < cap) { memcpy(corners + 8 * i, k[i].c, 32); ids[i] = d[i].id; }
+    }
+    out4[3] = nm;
+    return B200_OK;
+}
+
+int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                           b200_marker* markers, int32_t* counts) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    if (n < 0 || w < 0 || hh < 0) return fail(B200_EINVAL, "negative %s", "size");
+    if (n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
+    if (n == 0) return B200_OK;
+    if (!markers || !counts || (!imgs && w > 0 && hh > 0)) return fail(B200_EINVAL, "null %s", "pointer");
+    int rc = use_device(h->device);
+    if (rc) return rc;
+    if (w < 8 || hh < 8) { for (int i = 0; i < n; i++) counts[i] = 0; return B200_OK; }
+    const size_t fb = (size_t)w * hh;
+    if ((rc = ensure_buf(h->d_in, h->cap_in, fb * n))) return rc;
+    if (h->cap_out < (size_t)n) {
+        cudaFree(h->d_out); cudaFree(h->d_counts); h->d_out = nullptr; h->d_counts = nullptr; h->cap_out = 0;
+        B200_CUDA(cudaMalloc((void**)&h->d_out, sizeof(b200_marker) * kMaxMarkers * (size_t)h->max_batch));
+        B200_CUDA(cudaMalloc((void**)&h->d_counts, 4 * (size_t)h->max_batch));
+        h->cap_out = h->max_batch;
+    }
+    cudaStream_t st = h->stream;
+    if (fs == rs * hh) B200_CUDA(cudaMemcpy2DAsync(h->d_in, w, imgs, rs, w, (size_t)hh * n, cudaMemcpyHostToDevice, st));
+    else for (int f = 0; f < n; f++) B200_CUDA(cudaMemcpy2DAsync(h->d_in + f * fb, w, imgs + (size_t)f * fs, rs, w, hh, cudaMemcpyHostToDevice, st));
+    if ((rc = b200_aruco_detect(h, h->d_in, n, w, hh, w, (int64_t)fb, h->d_out, h->d_counts, st))) return rc;
+    B200_CUDA(cudaMemcpyAsync(markers, h->d_out, sizeof(b200_marker) * kMaxMarkers * (size_t)n, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(counts, h->d_counts, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (err) {
+        cudaMemset(h->d_err, 0, 4);
+        static const char* what[] = {"", "", "", "border longer than the point budget", "too many contours", "contour point budget", "more than 256 quads", "more than 64 markers"};
+        return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 8 ? err : 0]);
+    }
+    return B200_OK;
+}
+
+}  // extern "C"
