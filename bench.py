@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- frames/s of the B200 front end on BASELINE.json's workload.
+"""bench.py -- frames/s of the B200 front end on BASELINE.json's workloads.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2|C3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C3|C2]
 
-A "step" is one pass of the hot path over one batch of synthetic frames (config C2 of BASELINE.json:
-batch=256 synthetic 640x480 frames, 1000 features, 8 levels; C3 adds ArUco + brute-force matching once built).
+A "step" is one pass of the hot path over one batch of synthetic frames:
+  C3 (default; BASELINE.json configs[2], the configuration the metric "frames/sec (extract+aruco+match)" names):
+     batch=256 640x480, ORB extract (1000 features, 8 levels) + ArUco detect (ARUCO_MIP_25h7, 20 planted markers)
+     + brute-force SearchByBoW match against a 1000-descriptor reference set
+  C2 (configs[1]): the same frames, extract only
 `value` is measured with the batch already resident in HBM (CUDA events on the launching stream, one event pair
-per step, L2 flushed between steps); `e2e` goes through the reference-facing host-pointer C-ABI call with
-pinned host buffers, H2D and D2H inside the timed region.  Multi-GPU (torchrun, one rank per GPU): frames are
-independent, every rank processes its own batch (weak scaling), results are collated on rank 0 with one NCCL
-all_gather of fixed-size slots inside the timed region; max over ranks.
+per step, L2 flushed between steps); `e2e` goes through the reference-facing host-pointer C-ABI call
+(b200_frontend_host) with pinned host buffers, H2D and D2H inside the timed region.  Multi-GPU (torchrun, one rank
+per GPU): frames are independent, every rank processes its own batch (weak scaling) and the fixed-size result slots
+are collated with NCCL all_gather inside the timed region; device time, max over ranks.
 
---impl reference times the reference's own CPU extractor (oracle/_ref: src/ORBextractor.cc compiled unmodified
-on the cv shim; falls back to the oracle port) with all host threads, on the same workload.
+--impl reference times the reference's CPU implementation on the same workload with all host threads: the
+extractor is the reference's own src/ORBextractor.cc (oracle/_ref, compiled unmodified on the cv shim; the oracle
+port when that library is absent), detector and matcher are the oracle restatements (their sources need OpenCV
+C++ libraries / Eigen that do not exist in this image).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -27,29 +33,39 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+DICT = "ARUCO_MIP_25h7"
 WORKLOADS = {
     "C2": dict(name="C2: batch=256 synthetic 640x480 gray frames, 1000 ORB features, 8 levels x1.2, FAST 20/7, extract-only",
-               batch=256, w=640, h=480, nfeatures=1000, markers=0),
+               metric="frames/sec (extract)", batch=256, w=640, h=480, nfeatures=1000, markers=0, match=False),
+    "C3": dict(name="C3: batch=256 synthetic 640x480 gray frames, extract (1000 feat, 8 levels) + ArUco (ARUCO_MIP_25h7, 20 markers/frame) "
+                    "+ brute-force match vs 1000-descriptor reference set",
+               metric="frames/sec (extract+aruco+match)", batch=256, w=640, h=480, nfeatures=1000, markers=20, match=True),
 }
-SIGMA_P = {(640, 480): 950532}      # pixels over the 8 levels
+SIGMA_P = {(640, 480): 950532}      # pixels over the 8 ORB levels
 
 
 def frames_for(wl, rank, batch=None):
-    """deterministic synthetic frames; cached under /tmp because numpy generation takes ~50 ms per frame"""
+    """deterministic synthetic frames; cached under /tmp because numpy generation takes ~50-150 ms per frame"""
     from orb_slam2_aruco_b200 import synth
     n = batch or wl["batch"]
-    path = "/tmp/b200_frames_%dx%d_m%d_r%d_n%d.npy" % (wl["w"], wl["h"], wl["markers"], rank, n)
+    path = "/tmp/b200_frames_v2_%dx%d_m%d_r%d_n%d.npy" % (wl["w"], wl["h"], wl["markers"], rank, n)
     if os.path.exists(path):
         try:
             return np.load(path)
         except Exception:
             pass
-    imgs = synth.make_batch(n, wl["w"], wl["h"], wl["markers"], first=rank * 100000)
+    imgs = synth.make_batch(n, wl["w"], wl["h"], wl["markers"], DICT, first=rank * 100000)
     try:
         np.save(path, imgs)
     except Exception:
         pass
     return imgs
+
+
+def reference_scene(wl):
+    """the frame the match reference set is extracted from: frame 0's scene shifted by (5, 3) px"""
+    from orb_slam2_aruco_b200 import synth
+    return np.roll(synth.make_frame(0, wl["w"], wl["h"], wl["markers"], DICT), (3, 5), axis=(0, 1))
 
 
 class ClockSampler(threading.Thread):
@@ -70,7 +86,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
@@ -90,23 +106,44 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_run(imgs, wl, nthreads):
-    """the reference's own extractor (oracle/_ref) or the oracle port on `imgs`; returns (seconds, kind)"""
-    import ctypes as C
+def cpu_reference_run(imgs, wl, nthreads, ref_set=None):
+    """the reference CPU path on `imgs` with nthreads threads; returns (seconds, kind, description)"""
     import oracle
     n, h, w = imgs.shape
     cap = wl["nfeatures"] + 200
     r = oracle.ref()
+    vp = C.c_void_p
     t0 = time.perf_counter()
     if r is not None:
-        kps = np.zeros((n, cap, 7), np.float32); desc = np.zeros((n, cap, 32), np.uint8); cnt = np.zeros(n, np.int32)
-        r.ref_orb_extract_batch(imgs.ctypes.data_as(C.c_void_p), n, w, h, w, C.c_long(w * h), wl["nfeatures"], C.c_float(1.2), 8, 20, 7,
-                                kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), cap, nthreads)
-        kind = "reference"
+        raw = np.zeros((n, cap, 7), np.float32); desc = np.zeros((n, cap, 32), np.uint8); cnt = np.zeros(n, np.int32)
+        r.ref_orb_extract_batch(imgs.ctypes.data_as(vp), n, w, h, w, C.c_long(w * h), wl["nfeatures"], C.c_float(1.2), 8, 20, 7,
+                                raw.ctypes.data_as(vp), desc.ctypes.data_as(vp), cnt.ctypes.data_as(vp), cap, nthreads)
+        kps28 = np.zeros((n, cap, 28), np.uint8)
+        kps28.view(np.float32).reshape(n, cap, 7)[:, :, :5] = raw[:, :, :5]
+        kind, what = "reference", "extractor = reference src/ORBextractor.cc on the cv shim (oracle/_ref)"
     else:
-        oracle.orb_extract_batch(imgs, wl["nfeatures"], nthreads=nthreads)
-        kind = "port"
-    return time.perf_counter() - t0, kind
+        k, desc, cnt = oracle.orb_extract_batch(imgs, wl["nfeatures"], nthreads=nthreads)
+        kps28 = np.ascontiguousarray(k).view(np.uint8).reshape(n, -1, 28)
+        cap = kps28.shape[1]
+        kind, what = "port", "extractor = oracle port"
+    if wl["markers"]:
+        oracle.aruco_detect_batch(imgs, DICT, nthreads=nthreads)
+        what += "; detector = oracle restatement"
+    if wl["match"] and ref_set is not None:
+        rd, ra = ref_set
+        m = np.zeros((n, cap), np.int32); nm = np.zeros(n, np.int32)
+        oracle.lib().oracle_search_by_bow_bf_batch(rd.ctypes.data_as(vp), ra.ctypes.data_as(vp), len(rd), desc.ctypes.data_as(vp),
+                                                   kps28.ctypes.data_as(vp), cnt.ctypes.data_as(vp), n, cap, C.c_float(0.7), 1,
+                                                   C.c_float(np.float32(30.0) / np.float32(360.0)), m.ctypes.data_as(vp), nm.ctypes.data_as(vp), nthreads)
+        what += "; matcher = oracle restatement"
+        kind = "port" if kind == "port" else "reference"
+    return time.perf_counter() - t0, kind, what
+
+
+def cpu_ref_set(wl):
+    import oracle
+    k, d = oracle.orb_extract(reference_scene(wl), wl["nfeatures"])
+    return np.ascontiguousarray(d[:1000]), np.ascontiguousarray(k["angle"][:1000])
 
 
 def run_reference(args, wl):
@@ -120,19 +157,19 @@ def run_reference(args, wl):
         pass
     sample = min(wl["batch"], max(32, 2 * ncores))          # bounded sample of the workload per step
     imgs = frames_for(wl, 0)[:sample]
+    ref_set = cpu_ref_set(wl) if wl["match"] else None
     for _ in range(args.warmup):
-        cpu_reference_run(imgs, wl, ncores)
-    t = 0.0
-    kind = "port"
+        cpu_reference_run(imgs, wl, ncores, ref_set)
+    t, kind, what = 0.0, "port", ""
     for _ in range(args.steps):
-        dt, kind = cpu_reference_run(imgs, wl, ncores)
+        dt, kind, what = cpu_reference_run(imgs, wl, ncores, ref_set)
         t += dt
     fps = sample * args.steps / t
-    line = {"impl": "reference", "metric": "frames/sec (extract)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": wl["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": {"workload": wl["name"]},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": kind,
-                             "sample": "%d of the %d frames per step, %d host threads" % (sample, wl["batch"], ncores)},
+                             "sample": "%d of the %d frames per step, %d host threads; %s" % (sample, wl["batch"], ncores, what)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -143,7 +180,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -154,7 +191,7 @@ def main():
     import torch
     import torch.distributed as dist
     from orb_slam2_aruco_b200 import _lib
-    from orb_slam2_aruco_b200.api import ORBextractor
+    from orb_slam2_aruco_b200.api import FrontEnd, MarkerDetector, ORBextractor, ORBmatcher
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -170,26 +207,47 @@ def main():
     B, W, H = wl["batch"], wl["w"], wl["h"]
     imgs_np = frames_for(wl, rank)
     ex = ORBextractor(wl["nfeatures"], 1.2, 8, 20, 7, W, H, B, device=local)
-    cap = ex.cap
+    det = MarkerDetector(DICT, W, H, B, device=local) if wl["markers"] else None
+    matcher = ORBmatcher(0.7, True, device=local) if wl["match"] else None
+    cap, mcap = ex.cap, 64
     d_imgs = torch.from_numpy(imgs_np).to(dev)
     d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device=dev)
     d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
     d_counts = torch.zeros((B,), dtype=torch.int32, device=dev)
-    stream = torch.cuda.Stream(device=dev)
+    d_markers = torch.zeros((B, mcap, 9), dtype=torch.float32, device=dev)
+    d_mcounts = torch.zeros((B,), dtype=torch.int32, device=dev)
+    d_match = torch.zeros((B, cap), dtype=torch.int32, device=dev)
+    d_nmatch = torch.zeros((B,), dtype=torch.int32, device=dev)
+    # reference set for the matcher: <= 1000 descriptors of the shifted scene, extracted with the CUDA extractor
+    ref_np = None
+    if wl["match"]:
+        rk, rd = ex(reference_scene(wl))
+        ref_np = (np.ascontiguousarray(rd[:1000]), np.ascontiguousarray(rk[:1000]))
+        d_rdesc = torch.from_numpy(ref_np[0]).to(dev)
+        d_rkps = torch.from_numpy(ref_np[1].view(np.uint8).reshape(-1, 28).copy()).to(dev)
+        n_ref = len(ref_np[0])
+    s_main = torch.cuda.Stream(device=dev)
+    s_aux = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    # collation on rank 0: fixed-size slots, one all_gather per step
-    gather = None
-    if world > 1:
-        gather = [torch.empty_like(d_desc) for _ in range(world)], [torch.empty_like(d_kps) for _ in range(world)], \
-                 [torch.empty_like(d_counts) for _ in range(world)]
+    outs = [d_kps, d_desc, d_counts] + ([d_markers, d_mcounts] if det else []) + ([d_match, d_nmatch] if matcher else [])
+    gather = [[torch.empty_like(t) for _ in range(world)] for t in outs] if world > 1 else None
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     def step():
-        ex.extract_batch_device(d_imgs, d_kps, d_desc, d_counts, stream)
+        if det is not None:                      # detector on its own stream, concurrently with extractor + matcher
+            ev_fork.record(s_main)
+            s_aux.wait_event(ev_fork)
+            det.detect_batch_device(d_imgs, d_markers, d_mcounts, s_aux)
+            ev_join.record(s_aux)
+        ex.extract_batch_device(d_imgs, d_kps, d_desc, d_counts, s_main)
+        if matcher is not None:
+            matcher.SearchByBoW_device(d_rdesc, d_rkps, n_ref, d_desc, d_kps, d_counts, d_match, d_nmatch, s_main)
+        if det is not None:
+            s_main.wait_event(ev_join)
         if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_gather(gather[0], d_desc)
-                dist.all_gather(gather[1], d_kps)
-                dist.all_gather(gather[2], d_counts)
+            with torch.cuda.stream(s_main):
+                for g, t in zip(gather, outs):
+                    dist.all_gather(g, t)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -210,36 +268,35 @@ def main():
     sync_all()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        with torch.cuda.stream(stream):
+        with torch.cuda.stream(s_main):
             flush.fill_(i & 0xff)          # evict the batch from L2 (not timed)
-            ev[i][0].record(stream)
+            ev[i][0].record(s_main)
         step()
-        with torch.cuda.stream(stream):
-            ev[i][1].record(stream)
-        stream.synchronize()
+        ev[i][1].record(s_main)
+        s_main.synchronize()
         stage += ex.stage_ms()
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - launches0
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(ms_steps))
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     ex.set_profile(False)
+    nkp = int(d_counts.sum().item())
+    nmk = int(d_mcounts.sum().item()) if det else 0
+    nmatch = int(d_nmatch.sum().item()) if matcher else 0
 
     # ---- end to end through the reference-facing host-pointer C-ABI (pinned buffers) ----------------
+    fe = FrontEnd(ex, det, matcher)
     h_imgs = torch.from_numpy(imgs_np).pin_memory()
-    h_kps = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
-    h_desc = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
-    h_counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
-    out = (h_kps.numpy().view(_lib.KP_DTYPE).reshape(B, cap), h_desc.numpy(), h_counts.numpy())
+    out = fe.alloc_outputs(B, pinned=True)
     for _ in range(2):
-        ex.extract_batch(h_imgs.numpy(), out=out)
+        fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ex.extract_batch(h_imgs.numpy(), out=out)
+        fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    nkp = int(h_counts.sum())
+    assert int(out["counts"].sum()) == nkp, "host path and device path disagree"
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -256,37 +313,42 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         sp = SIGMA_P.get((W, H), int(3.0942 * W * H))
-        ncand_bytes = 4 * 10000                                   # ~10k candidates x 4 B per frame (measured on this workload)
-        fast_bytes = (sp + ncand_bytes) * B                       # k_fast: every level pixel read once + candidate slots written
+        fast_bytes = (sp + 4 * 10000) * B                         # k_fast: every level pixel read once + ~10k candidate slots written / frame
         fast_ms = stage[1] / args.steps
         achieved = fast_bytes / (fast_ms / 1000.0) / 1e9
-        b_ext = 2 * sp + 60 * (nkp / B)                           # whole-extractor algorithmic bytes / frame
+        b_frame = 2 * sp + 60 * (nkp / B)                         # B_ext
+        if det:
+            b_frame += 3.333 * W * H + 36 * (nmk / B)             # B_aru
+        if matcher:
+            b_frame += 36 * (nkp / B + 1000) + 4 * (nkp / B)      # B_mat
+        d2h = B * cap * 60 + B * 4 + (B * mcap * 36 + B * 4 if det else 0) + (B * cap * 4 + B * 4 if matcher else 0)
         line = {
-            "metric": "frames/sec (extract)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": wl["metric"], "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"], "frames_per_gpu": B, "l2": "flushed between steps (256 MiB fill, untimed)",
                        "timing": "CUDA events on the launching stream, one pair per step, max over ranks",
-                       "collate": "nccl all_gather of fixed slots inside the step" if world > 1 else "none (1 GPU)"},
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
-                    "d2h_bytes_per_step": int(B * cap * 60 + B * 4), "api": "b200_orb_extract_host (pinned host buffers, chunked H2D overlap)"},
+                       "collate": "nccl all_gather of fixed result slots inside the step" if world > 1 else "none (1 GPU)"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H), "d2h_bytes_per_step": int(d2h),
+                    "api": "b200_frontend_host (pinned host buffers, chunked H2D overlapped with compute)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "ms_per_launch": fast_ms,
                          "algorithmic_bytes_per_launch": int(fast_bytes),
-                         "stage_ms": {"pyramid": stage[0] / args.steps, "fast": stage[1] / args.steps, "quadtree": stage[2] / args.steps,
-                                      "describe": stage[3] / args.steps},
-                         "whole_step": {"algorithmic_bytes_per_frame": b_ext, "achieved_gbs": fps / world * b_ext / 1e9,
-                                        "frac": fps / world * b_ext / 1e9 / peak}},
+                         "extractor_stage_ms": {"pyramid": stage[0] / args.steps, "fast": stage[1] / args.steps,
+                                                "quadtree": stage[2] / args.steps, "describe": stage[3] / args.steps},
+                         "whole_step": {"algorithmic_bytes_per_frame": b_frame, "achieved_gbs": fps / world * b_frame / 1e9,
+                                        "frac": fps / world * b_frame / 1e9 / peak}},
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
-            "keypoints_per_frame": nkp / B,
+            "per_frame": {"keypoints": nkp / B, "markers": nmk / B, "matches": nmatch / B},
         }
         if not args.no_cpu_baseline and world == 1:
-            sample = 128
-            secs, kind = cpu_reference_run(imgs_np[:sample], wl, 1)
+            sample = 96
+            ref_set = cpu_ref_set(wl) if wl["match"] else None
+            secs, kind, what = cpu_reference_run(imgs_np[:sample], wl, 1, ref_set)
             line["cpu_baseline"] = {"value": sample / secs, "unit": "frames/s", "cores": 1, "kind": kind,
-                                    "sample": "first %d of the %d frames, 1 thread" % (sample, B)}
+                                    "sample": "first %d of the %d frames, 1 thread; %s" % (sample, B, what)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

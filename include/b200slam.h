@@ -76,6 +76,17 @@ int b200_orb_extract(b200_orb_t h, const uint8_t* imgs, int n, int width, int he
 /* Host-pointer call (the reference-facing one): same layout, host memory, synchronous. */
 int b200_orb_extract_host(b200_orb_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
                           b200_keypoint* kps, uint8_t* desc, int32_t* counts);
+/* The whole per-frame front end on host buffers with ONE upload: extractor + (optional, aruco != NULL) marker
+ * detector + (optional, ref_desc != NULL) brute-force SearchByBoW against a reference set, i.e. what
+ * Frame::Frame (src/Frame.cc:91,142) and TrackReferenceKeyFrame (src/Tracking.cc:917) do on one image.
+ * Frames are uploaded in chunks that overlap with compute; detector and extractor run on separate streams.
+ * match_ref_idx [n][cap] / n_matches [n] as in b200_match_bf with th_low = 50 and the 30/360 histogram factor. */
+int b200_frontend_host(b200_orb_t orb, b200_aruco_t aruco, const uint8_t* imgs, int n, int width, int height,
+                       int64_t row_stride, int64_t frame_stride,
+                       b200_keypoint* kps, uint8_t* desc, int32_t* counts,
+                       b200_marker* markers, int32_t* marker_counts,
+                       const uint8_t* ref_desc, const b200_keypoint* ref_kps, int n_ref, float ratio, int check_ori,
+                       int32_t* match_ref_idx, int32_t* n_matches);
 /* Per-stage device timing for roofline reports: when enabled, every extract call records CUDA events on its
  * stream around the four stages; b200_orb_get_stage_ms returns the last call's pyramid / fast / quadtree /
  * describe durations in milliseconds (ms4[4]). */
@@ -102,6 +113,12 @@ int b200_match_bf(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
                   const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
                   float ratio, int th_low, int check_ori, float histo_factor,
                   int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream);
+/* Device-pointer variant that reads the angles out of b200_keypoint records, so the extractor's output buffers
+ * (kps [n][cap], desc [n][cap][32], counts [n]) feed the matcher without a repack. */
+int b200_match_bf_kp(const uint8_t* ref_desc, const b200_keypoint* ref_kps, int n_ref,
+                     const uint8_t* frame_desc, const b200_keypoint* frame_kps, const int32_t* n_frame, int n_batch, int frame_cap,
+                     float ratio, int th_low, int check_ori, float histo_factor,
+                     int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream);
 int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
                        const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
                        float ratio, int th_low, int check_ori, float histo_factor,
@@ -126,6 +143,9 @@ int b200_aruco_max_markers(b200_aruco_t h);
 /* markers [n][cap] sorted by id per frame (cap = b200_aruco_max_markers()), counts [n]. */
 int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
                       b200_marker* markers, int32_t* counts, void* stream);
+/* Waits for the handle's work on `stream` (NULL = own stream) and reports a scratch overflow of the device-pointer
+ * calls since the last check as B200_ECAPACITY. */
+int b200_aruco_check(b200_aruco_t h, void* stream);
 /* Validation taps of the LAST call for one frame: out4 = {borders > 70 points, convex quads, candidates after
  * prefilterCandidates, decoded markers before de-duplication}; corners [cap][8] and ids [cap] (may be NULL) receive the
  * prefiltered candidates in order with their decoded id (-1 = not a marker). */

@@ -7,6 +7,8 @@
 #include <cmath>
 #include <vector>
 #include <cstring>
+#include <thread>
+#include <atomic>
 
 namespace {
 const int TH_LOW = 50, HISTO_LENGTH = 30;   // ORBmatcher.cc:37-39
@@ -86,6 +88,27 @@ int oracle_search_by_bow_bf(const uint8_t* kf_desc, const float* kf_angle, int n
         }
     }
     return nmatches;
+}
+
+// batch driver for CPU-baseline timing: one reference set against n frames laid out like the extractor's output
+// (desc [n][cap][32], angles inside 28-byte keypoint records), nthreads workers
+int oracle_search_by_bow_bf_batch(const uint8_t* kf_desc, const float* kf_angle, int n_kf,
+                                  const uint8_t* f_desc, const uint8_t* f_kps28, const int32_t* n_f, int n, int cap,
+                                  float nnratio, int check_ori, float factor, int32_t* matches, int32_t* n_matches, int nthreads) {
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        std::vector<float> ang(cap);
+        for (int f; (f = next.fetch_add(1)) < n;) {
+            for (int i = 0; i < n_f[f]; i++) memcpy(&ang[i], f_kps28 + ((size_t)f * cap + i) * 28 + 12, 4);
+            n_matches[f] = oracle_search_by_bow_bf(kf_desc, kf_angle, n_kf, f_desc + (size_t)f * cap * 32, ang.data(), n_f[f], nnratio, check_ori, factor,
+                                                   matches + (size_t)f * cap);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    return 0;
 }
 
 // best / second-best over an explicit candidate list, the inner loop shared by SearchByProjection

@@ -47,6 +47,9 @@ int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b);
 int oracle_search_by_bow_bf(const uint8_t* kf_desc, const float* kf_angle, int n_kf,
                             const uint8_t* f_desc, const float* f_angle, int n_f,
                             float nnratio, int check_ori, float factor, int32_t* matches);
+int oracle_search_by_bow_bf_batch(const uint8_t* kf_desc, const float* kf_angle, int n_kf,
+                                  const uint8_t* f_desc, const uint8_t* f_kps28, const int32_t* n_f, int n, int cap,
+                                  float nnratio, int check_ori, float factor, int32_t* matches, int32_t* n_matches, int nthreads);
 void oracle_match_candidates(const uint8_t* qd, int nq, const uint8_t* td, const int32_t* ofs, const int32_t* cand,
                              int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
 

@@ -45,11 +45,14 @@ def lib():
         L.b200_orb_get_level_info.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b200_orb_extract.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp]
         L.b200_orb_extract_host.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp]
+        L.b200_frontend_host.argtypes = [vp, vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp]
+        L.b200_aruco_check.argtypes = [vp, vp]
         L.b200_orb_set_profile.argtypes = [vp, i32]
         L.b200_orb_get_stage_ms.argtypes = [vp, vp]
         L.b200_orb_get_pyramid.argtypes = [vp, i32, i32, vp, vp, vp]
         L.b200_orb_get_candidates.argtypes = [vp, i32, i32, vp, i32]
         L.b200_match_bf.argtypes = [vp, vp, i32, vp, vp, vp, i32, i32, f32, i32, i32, f32, vp, vp, i32, vp]
+        L.b200_match_bf_kp.argtypes = [vp, vp, i32, vp, vp, vp, i32, i32, f32, i32, i32, f32, vp, vp, i32, vp]
         L.b200_match_bf_host.argtypes = [vp, vp, i32, vp, vp, vp, i32, i32, f32, i32, i32, f32, vp, vp, i32]
         L.b200_hamming_matrix_host.argtypes = [vp, i32, vp, i32, vp, i32]
         L.b200_match_candidates_host.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32]

@@ -227,6 +227,16 @@ class ORBmatcher:
                                        ptr(matches), ptr(nm), self._device))
         return nm, matches
 
+    def SearchByBoW_device(self, ref_desc, ref_kps, n_ref, f_desc, f_kps, n_frame, matches, n_matches, stream=None):
+        """device-resident batch variant: all arguments are CUDA tensors laid out like the extractor's outputs
+        (desc uint8 [.., cap, 32], kps [.., cap, 7 floats], n_frame int32 [n]); only enqueues kernels"""
+        nb, cap = f_desc.shape[0], f_desc.shape[1]
+        s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+        hf = float(np.float32(self.HISTO_LENGTH) / np.float32(360.0))
+        check(lib().b200_match_bf_kp(ptr(ref_desc), ptr(ref_kps), int(n_ref), ptr(f_desc), ptr(f_kps), ptr(n_frame), nb, cap,
+                                     self.mfNNratio, self.TH_LOW, int(self.mbCheckOrientation), hf, ptr(matches), ptr(n_matches),
+                                     self._device, s))
+
     def match_candidates(self, query_desc, train_desc, cand_ofs, cand):
         """distance core of SearchByProjection / SearchForInitialization: per query the best index, best and
         second-best distance over its candidate list (first minimum in list order wins)"""
@@ -331,3 +341,55 @@ class MarkerDetector:
         self._ensure(w, h, n)
         s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
         check(lib().b200_aruco_detect(self._h, ptr(images), n, w, h, images.stride(1), images.stride(0), ptr(markers), ptr(counts), s))
+
+
+class FrontEnd:
+    """Extractor + marker detector + matcher on one upload: what Frame::Frame (reference src/Frame.cc:91,142) and
+    TrackReferenceKeyFrame (src/Tracking.cc:917) do per image, for a batch of frames through b200_frontend_host."""
+
+    def __init__(self, extractor, detector=None, matcher=None):
+        self.extractor, self.detector, self.matcher = extractor, detector, matcher
+
+    def alloc_outputs(self, n, pinned=False):
+        """host output buffers for n frames (optionally pinned through torch) -> dict of numpy arrays"""
+        if self.extractor._h is None:
+            raise B200Error(_lib.EINVAL, "create the extractor with max_width/max_height/max_batch (or run one frame) first")
+        cap = self.extractor.cap
+        mcap = 64
+
+        def mk(shape, dtype):
+            if pinned:
+                import torch
+                t = torch.zeros(int(np.prod(shape)) * np.dtype(dtype).itemsize, dtype=torch.uint8).pin_memory()
+                self._keep = getattr(self, "_keep", []) + [t]
+                return t.numpy().view(dtype).reshape(shape)
+            return np.zeros(shape, dtype)
+        return dict(kps=mk((n, cap), KP_DTYPE), desc=mk((n, cap, 32), np.uint8), counts=mk((n,), np.int32),
+                    markers=mk((n, mcap), MARKER_DTYPE), marker_counts=mk((n,), np.int32),
+                    matches=mk((n, cap), np.int32), n_matches=mk((n,), np.int32))
+
+    def process_batch(self, images, ref_desc=None, ref_kps=None, out=None):
+        images = np.asarray(images)
+        assert images.dtype == np.uint8 and images.ndim == 3
+        if images.strides[2] != 1:
+            images = np.ascontiguousarray(images)
+        n, h, w = images.shape
+        ex, det = self.extractor, self.detector
+        ex._ensure(w, h, n)
+        if det is not None:
+            det._ensure(w, h, min(n, 32) if n > 16 else n)
+        if out is None:
+            out = self.alloc_outputs(n)
+        do_match = ref_desc is not None and self.matcher is not None
+        if do_match:
+            ref_desc = np.ascontiguousarray(ref_desc, np.uint8).reshape(-1, 32)
+            ref_kps = np.ascontiguousarray(ref_kps)
+            assert ref_kps.dtype == KP_DTYPE and len(ref_kps) == len(ref_desc)
+        check(lib().b200_frontend_host(
+            ex._h, det._h if det is not None else None, ptr(images), n, w, h, images.strides[1], images.strides[0],
+            ptr(out["kps"]), ptr(out["desc"]), ptr(out["counts"]),
+            ptr(out["markers"]) if det is not None else None, ptr(out["marker_counts"]) if det is not None else None,
+            ptr(ref_desc) if do_match else None, ptr(ref_kps) if do_match else None, len(ref_desc) if do_match else 0,
+            self.matcher.mfNNratio if do_match else 0.0, int(self.matcher.mbCheckOrientation) if do_match else 0,
+            ptr(out["matches"]) if do_match else None, ptr(out["n_matches"]) if do_match else None))
+        return out

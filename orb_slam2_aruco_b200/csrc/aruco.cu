@@ -1113,6 +1113,24 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
     return B200_OK;
 }
 
+// Blocks until the handle's work on `stream` (NULL = own stream) is done and reports scratch overflows of the
+// device-pointer calls since the last check (B200_ECAPACITY), clearing the flag.
+int b200_aruco_check(b200_aruco_t h, void* stream) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    int rc = use_device(h->device);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int err = 0;
+    B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (err) {
+        B200_CUDA(cudaMemsetAsync(h->d_err, 0, 4, st));
+        static const char* what[] = {"", "", "", "border longer than the point budget", "too many contours", "contour point budget", "more than 256 quads", "more than 64 markers"};
+        return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 8 ? err : 0]);
+    }
+    return B200_OK;
+}
+
 // validation taps of the LAST call: out4 = {borders longer than 70 points, convex quads, candidates after the prefilter, markers};
 // corners [cap][8] / ids [cap] = the prefiltered candidates in order with their decoded id (-1: not a marker)
 int b200_aruco_debug(b200_aruco_t h, int frame, int32_t* out4, float* corners, int32_t* ids, int cap) {

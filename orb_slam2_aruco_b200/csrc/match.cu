@@ -88,8 +88,8 @@ __device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int&
 constexpr int kHistoLen = 30;      // HISTO_LENGTH, ORBmatcher.cc:39
 
 __global__ void __launch_bounds__(32)
-k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict__ ref_angle, int n_ref,
-                const ulonglong4* __restrict__ frame_desc, const float* __restrict__ frame_angle,
+k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict__ ref_angle, int ref_astride, int n_ref,
+                const ulonglong4* __restrict__ frame_desc, const float* __restrict__ frame_angle, int frame_astride,
                 const int* __restrict__ n_frame, int frame_cap, const uint32_t* __restrict__ topk,
                 float ratio, int th_low, int check_ori, float histo_factor,
                 int* __restrict__ match_ref_idx, int* __restrict__ n_matches) {
@@ -106,7 +106,7 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
     for (int i = lane; i < frame_cap; i += 32) mout[i] = -1;
     __syncwarp();
     const ulonglong4* fd = frame_desc + (long long)f * frame_cap;
-    const float* fa = frame_angle + (long long)f * frame_cap;
+    const float* fa = frame_angle + (long long)f * frame_cap * frame_astride;
     int nm = 0;
     for (int r = 0; r < n_ref; r++) {
         const uint32_t* tk = topk + ((long long)f * n_ref + r) * kTopK;
@@ -157,7 +157,7 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
                 taken[idx >> 5] |= 1u << (idx & 31);
                 mout[idx] = r;
                 if (check_ori) {
-                    float rot = __fsub_rn(ref_angle[r], fa[idx]);
+                    float rot = __fsub_rn(ref_angle[(long long)r * ref_astride], fa[(long long)idx * frame_astride]);
                     if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                     int bin = (int)roundf(__fmul_rn(rot, histo_factor));
                     if (bin == kHistoLen) bin = 0;
@@ -231,10 +231,10 @@ using namespace b200;
 
 extern "C" {
 
-int b200_match_bf(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
-                  const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
-                  float ratio, int th_low, int check_ori, float histo_factor,
-                  int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream) {
+static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int ref_astride, int n_ref,
+                         const uint8_t* frame_desc, const float* frame_angle, int frame_astride, const int32_t* n_frame, int n_batch, int frame_cap,
+                         float ratio, int th_low, int check_ori, float histo_factor,
+                         int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream) {
     if (n_batch < 0 || n_ref < 0 || frame_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
     if (frame_cap > 65535) return fail(B200_ECAPACITY, "frame_cap above %s", "65535");
     int rc = use_device(device);
@@ -262,10 +262,28 @@ int b200_match_bf(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
     }
     const size_t smem2 = (size_t)((frame_cap + 31) / 32) * 4 + (size_t)frame_cap + 16;
     B200_CUDA(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem2, 1024)));
-    B200_LAUNCH(k_match_resolve, n_batch, 32, smem2, st, (const ulonglong4*)ref_desc, ref_angle, n_ref, (const ulonglong4*)frame_desc, frame_angle,
-                n_frame, frame_cap, g_ms.topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches);
+    B200_LAUNCH(k_match_resolve, n_batch, 32, smem2, st, (const ulonglong4*)ref_desc, ref_angle, ref_astride, n_ref, (const ulonglong4*)frame_desc,
+                frame_angle, frame_astride, n_frame, frame_cap, g_ms.topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
+}
+
+int b200_match_bf(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
+                  const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
+                  float ratio, int th_low, int check_ori, float histo_factor,
+                  int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream) {
+    return match_bf_impl(ref_desc, ref_angle, 1, n_ref, frame_desc, frame_angle, 1, n_frame, n_batch, frame_cap, ratio, th_low, check_ori,
+                         histo_factor, match_ref_idx, n_matches, device, stream);
+}
+
+// same, with the angles read straight out of keypoint records (the extractor's output feeds the matcher unchanged)
+int b200_match_bf_kp(const uint8_t* ref_desc, const b200_keypoint* ref_kps, int n_ref,
+                     const uint8_t* frame_desc, const b200_keypoint* frame_kps, const int32_t* n_frame, int n_batch, int frame_cap,
+                     float ratio, int th_low, int check_ori, float histo_factor,
+                     int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream) {
+    const int st = (int)(sizeof(b200_keypoint) / sizeof(float));
+    return match_bf_impl(ref_desc, ref_kps ? &ref_kps->angle : nullptr, st, n_ref, frame_desc, frame_kps ? &frame_kps->angle : nullptr, st,
+                         n_frame, n_batch, frame_cap, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, device, stream);
 }
 
 namespace {

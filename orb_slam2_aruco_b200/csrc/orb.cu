@@ -721,6 +721,10 @@ struct b200_orb_s {
     uint8_t* d_in; size_t cap_in; uint8_t* h_in; size_t cap_hin;
     b200_keypoint* d_kps; uint8_t* d_desc; int32_t* d_counts; size_t cap_kps, cap_desc, cap_counts;
     uint8_t* h_out; size_t cap_hout;
+    // extra device outputs of b200_frontend_host (detector + matcher results, reference set)
+    b200_marker* d_markers; int32_t* d_mcounts; int32_t* d_match; int32_t* d_nmatch; uint8_t* d_refdesc; b200_keypoint* d_refkps;
+    size_t cap_markers, cap_mcounts, cap_match, cap_nmatch, cap_refdesc, cap_refkps;
+    cudaStream_t aux_stream; cudaEvent_t ev_aux;
     // optional per-stage timing (b200_orb_set_profile): events around pyramid / fast / quadtree / describe
     int profile; cudaEvent_t ev[5]; float stage_ms[4]; int stage_valid;
     cudaStream_t copy_stream; cudaEvent_t ev_copy[2];
@@ -950,6 +954,8 @@ int b200_orb_create(b200_orb_t* out, int nfeatures, float scale_factor, int nlev
     for (int i = 0; i < 5; i++) cudaEventCreate(&h->ev[i]);
     cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming);
     if ((rc = upload_constants()) || (rc = set_geometry(h, max_w, max_h))) { b200_orb_destroy(h); return rc; }
     *out = h;
     return B200_OK;
@@ -966,6 +972,9 @@ int b200_orb_destroy(b200_orb_t h) {
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_aux) cudaEventDestroy(h->ev_aux);
+    cudaFree(h->d_markers); cudaFree(h->d_mcounts); cudaFree(h->d_match); cudaFree(h->d_nmatch); cudaFree(h->d_refdesc); cudaFree(h->d_refkps);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B200_OK;
@@ -1018,40 +1027,69 @@ bool is_pinned(const void* p) {
 }
 }  // namespace
 
-// Host-pointer call: frames go up in chunks on a copy stream while the previous chunk is being processed on the
+// Host-pointer calls: frames go up in chunks on a copy stream while the previous chunk is being processed on the
 // compute stream (per-chunk events order the two); pinned caller buffers are used in place, pageable ones are
-// staged through the handle's pinned buffers.
-int b200_orb_extract_host(b200_orb_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
-                          b200_keypoint* kps, uint8_t* desc, int32_t* counts) {
+// staged through the handle's pinned buffers.  b200_frontend_host additionally runs the marker detector (on a
+// third stream, concurrently with the extractor) and the brute-force matcher on every chunk that has just landed:
+// one upload feeds all three stages, like Frame::Frame + Tracking do on one image in the reference
+// (src/Frame.cc:91,142; src/Tracking.cc:917).
+int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                       b200_keypoint* kps, uint8_t* desc, int32_t* counts,
+                       b200_marker* markers, int32_t* marker_counts,
+                       const uint8_t* ref_desc, const b200_keypoint* ref_kps, int n_ref, float ratio, int check_ori,
+                       int32_t* match_ref_idx, int32_t* n_matches) {
     int rc = check_args(h, imgs, n, w, hh, rs, fs);
     if (rc) return rc;
     if (!counts || !kps || !desc) return fail(B200_EINVAL, "null %s", "output pointer");
+    if (aruco && (!markers || !marker_counts)) return fail(B200_EINVAL, "null %s", "marker output pointer");
+    const bool do_match = ref_desc != nullptr;
+    if (do_match && (!ref_kps || !match_ref_idx || !n_matches || n_ref < 0)) return fail(B200_EINVAL, "bad %s", "matcher arguments");
     if ((rc = use_device(h->device))) return rc;
     if (n == 0) return B200_OK;
-    if (w == 0 || hh == 0) { for (int i = 0; i < n; i++) counts[i] = 0; return B200_OK; }
+    if (w == 0 || hh == 0) {
+        for (int i = 0; i < n; i++) { counts[i] = 0; if (aruco) marker_counts[i] = 0; if (do_match) n_matches[i] = 0; }
+        return B200_OK;
+    }
     const int cap = b200_orb_max_keypoints(h);
+    const int mcap = aruco ? b200_aruco_max_markers(aruco) : 0;
     const size_t frame_bytes = (size_t)w * hh, in_bytes = frame_bytes * n;
     const size_t kp_bytes = (size_t)n * cap * sizeof(b200_keypoint), de_bytes = (size_t)n * cap * 32, ct_bytes = (size_t)n * 4;
+    const size_t mk_bytes = (size_t)n * mcap * sizeof(b200_marker), ma_bytes = do_match ? (size_t)n * cap * 4 : 0;
     if ((rc = ensure(h->d_in, h->cap_in, in_bytes))) return rc;
     if ((rc = ensure(h->d_kps, h->cap_kps, kp_bytes))) return rc;
     if ((rc = ensure(h->d_desc, h->cap_desc, de_bytes))) return rc;
     if ((rc = ensure(h->d_counts, h->cap_counts, ct_bytes))) return rc;
+    if (aruco) {
+        if ((rc = ensure(h->d_markers, h->cap_markers, mk_bytes))) return rc;
+        if ((rc = ensure(h->d_mcounts, h->cap_mcounts, ct_bytes))) return rc;
+    }
+    if (do_match) {
+        if ((rc = ensure(h->d_match, h->cap_match, ma_bytes))) return rc;
+        if ((rc = ensure(h->d_nmatch, h->cap_nmatch, ct_bytes))) return rc;
+        if ((rc = ensure(h->d_refdesc, h->cap_refdesc, std::max<size_t>((size_t)n_ref * 32, 32)))) return rc;
+        if ((rc = ensure(h->d_refkps, h->cap_refkps, std::max<size_t>((size_t)n_ref * sizeof(b200_keypoint), 32)))) return rc;
+    }
     const bool in_pinned = is_pinned(imgs);
-    const bool out_pinned = is_pinned(kps) && is_pinned(desc) && is_pinned(counts);
+    const bool out_pinned = is_pinned(kps) && is_pinned(desc) && is_pinned(counts) && (!aruco || (is_pinned(markers) && is_pinned(marker_counts))) &&
+                            (!do_match || (is_pinned(match_ref_idx) && is_pinned(n_matches)));
     if (!in_pinned && h->cap_hin < in_bytes) {
         if (h->h_in) cudaFreeHost(h->h_in);
         h->h_in = nullptr; h->cap_hin = 0;
         B200_CUDA(cudaMallocHost((void**)&h->h_in, in_bytes));
         h->cap_hin = in_bytes;
     }
-    const size_t out_bytes = kp_bytes + de_bytes + ct_bytes;
+    const size_t out_bytes = kp_bytes + de_bytes + ct_bytes + mk_bytes + ct_bytes + ma_bytes + ct_bytes;
     if (!out_pinned && h->cap_hout < out_bytes) {
         if (h->h_out) cudaFreeHost(h->h_out);
         h->h_out = nullptr; h->cap_hout = 0;
         B200_CUDA(cudaMallocHost((void**)&h->h_out, out_bytes));
         h->cap_hout = out_bytes;
     }
-    cudaStream_t st = h->stream, cs = h->copy_stream;
+    cudaStream_t st = h->stream, cs = h->copy_stream, as = h->aux_stream;
+    if (do_match) {
+        B200_CUDA(cudaMemcpyAsync(h->d_refdesc, ref_desc, (size_t)n_ref * 32, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(h->d_refkps, ref_kps, (size_t)n_ref * sizeof(b200_keypoint), cudaMemcpyHostToDevice, st));
+    }
     const int chunk = n <= 16 ? n : 32;
     int ci = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, ci++) {
@@ -1075,23 +1113,49 @@ int b200_orb_extract_host(b200_orb_t h, const uint8_t* imgs, int n, int w, int h
         cudaEvent_t ev = h->ev_copy[ci & 1];
         B200_CUDA(cudaEventRecord(ev, cs));
         B200_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        if (aruco) {
+            B200_CUDA(cudaStreamWaitEvent(as, ev, 0));
+            if ((rc = b200_aruco_detect(aruco, dst, nf, w, hh, w, (int64_t)frame_bytes, h->d_markers + (size_t)f0 * mcap, h->d_mcounts + f0, as))) return rc;
+        }
         if ((rc = b200_orb_extract(h, dst, nf, w, hh, w, (int64_t)frame_bytes, h->d_kps + (size_t)f0 * cap, h->d_desc + (size_t)f0 * cap * 32,
                                    h->d_counts + f0, st)))
             return rc;
+        if (do_match &&
+            (rc = b200_match_bf_kp(h->d_refdesc, h->d_refkps, n_ref, h->d_desc + (size_t)f0 * cap * 32, h->d_kps + (size_t)f0 * cap, h->d_counts + f0, nf, cap,
+                                   ratio, 50, check_ori, 30.0f / 360.0f, h->d_match + (size_t)f0 * cap, h->d_nmatch + f0, h->device, st)))
+            return rc;
     }
     // (the debug taps b200_orb_get_pyramid / _get_candidates now refer to the LAST chunk)
-    uint8_t* ok = out_pinned ? (uint8_t*)kps : h->h_out;
-    uint8_t* od = out_pinned ? desc : h->h_out + kp_bytes;
-    uint8_t* oc = out_pinned ? (uint8_t*)counts : h->h_out + kp_bytes + de_bytes;
-    B200_CUDA(cudaMemcpyAsync(ok, h->d_kps, kp_bytes, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaMemcpyAsync(od, h->d_desc, de_bytes, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaMemcpyAsync(oc, h->d_counts, ct_bytes, cudaMemcpyDeviceToHost, st));
+    if (aruco) { B200_CUDA(cudaEventRecord(h->ev_aux, as)); B200_CUDA(cudaStreamWaitEvent(st, h->ev_aux, 0)); }
+    uint8_t* stage = h->h_out;
+    size_t o = 0;
+    auto down = [&](void* user, const void* dev, size_t bytes) -> int {
+        if (!bytes) return B200_OK;
+        B200_CUDA(cudaMemcpyAsync(out_pinned ? user : (void*)(stage + o), dev, bytes, cudaMemcpyDeviceToHost, st));
+        o += bytes;
+        return B200_OK;
+    };
+    if ((rc = down(kps, h->d_kps, kp_bytes)) || (rc = down(desc, h->d_desc, de_bytes)) || (rc = down(counts, h->d_counts, ct_bytes))) return rc;
+    if (aruco && ((rc = down(markers, h->d_markers, mk_bytes)) || (rc = down(marker_counts, h->d_mcounts, ct_bytes)))) return rc;
+    if (do_match && ((rc = down(match_ref_idx, h->d_match, ma_bytes)) || (rc = down(n_matches, h->d_nmatch, ct_bytes)))) return rc;
     int err = 0;
     B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     if (err) { cudaMemset(h->d_err, 0, 4); return fail(B200_ECAPACITY, "quadtree scratch overflow (%s)", err == 1 ? "node pool" : "result slots"); }
-    if (!out_pinned) { memcpy(kps, h->h_out, kp_bytes); memcpy(desc, h->h_out + kp_bytes, de_bytes); memcpy(counts, h->h_out + kp_bytes + de_bytes, ct_bytes); }
+    if (aruco && (rc = b200_aruco_check(aruco, as))) return rc;
+    if (!out_pinned) {
+        o = 0;
+        auto back = [&](void* user, size_t bytes) { if (bytes) memcpy(user, stage + o, bytes); o += bytes; };
+        back(kps, kp_bytes); back(desc, de_bytes); back(counts, ct_bytes);
+        if (aruco) { back(markers, mk_bytes); back(marker_counts, ct_bytes); }
+        if (do_match) { back(match_ref_idx, ma_bytes); back(n_matches, ct_bytes); }
+    }
     return B200_OK;
+}
+
+int b200_orb_extract_host(b200_orb_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                          b200_keypoint* kps, uint8_t* desc, int32_t* counts) {
+    return b200_frontend_host(h, nullptr, imgs, n, w, hh, rs, fs, kps, desc, counts, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr, nullptr);
 }
 
 int b200_orb_set_profile(b200_orb_t h, int enable) {
