@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-API leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     wl = WORKLOADS[args.workload]
@@ -285,18 +286,20 @@ def main():
     nmatch = int(d_nmatch.sum().item()) if matcher else 0
 
     # ---- end to end through the reference-facing host-pointer C-ABI (pinned buffers) ----------------
-    fe = FrontEnd(ex, det, matcher)
-    h_imgs = torch.from_numpy(imgs_np).pin_memory()
-    out = fe.alloc_outputs(B, pinned=True)
-    for _ in range(2):
-        fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    assert int(out["counts"].sum()) == nkp, "host path and device path disagree"
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        fe = FrontEnd(ex, det, matcher)
+        h_imgs = torch.from_numpy(imgs_np).pin_memory()
+        out = fe.alloc_outputs(B, pinned=True)
+        for _ in range(2):
+            fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        assert int(out["counts"].sum()) == nkp, "host path and device path disagree"
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)

@@ -10,11 +10,12 @@
 // Pipeline for a batch of n frames (per-tile / per-border / per-candidate kernels, no serial raster scan):
 //   k_athresh     adaptiveThreshold MEAN_C BINARY_INV (markerdetector_impl.cpp:2984): win x win box sum in smem
 //   k_halfpyr     image pyramid by exact 1/2 (2x2 mean; odd sizes: fixed-point bilinear) (1300-1466)
-//   k_nbrmask     8-neighbour foreground mask of every pixel of the binary image
-//   k_probe       cv::findContours RETR_LIST/CHAIN_APPROX_NONE (3108) without a raster scan: every 0->1 / 1->0
-//                 transition pixel follows its border (Suzuki's successor rule on the masks) until it comes back to
-//                 itself (=> it is the border's raster-first transition, i.e. Suzuki's start; the border is recorded
-//                 with its length) or meets a transition that the raster scan would have seen earlier (=> abort)
+//                 fused with the 8-neighbour foreground mask of every pixel (the binary image itself is never stored)
+//   k_probe_a/b   cv::findContours RETR_LIST/CHAIN_APPROX_NONE (3108) without a raster scan: every 0->1 / 1->0
+//                 transition pixel first looks BACK along its border (Suzuki's successor rule, inverted, on the masks) to
+//                 the previous transition; only if that one comes later in raster order (a) it walks FORWARD until it is
+//                 back at itself (=> it is the border's raster-first transition, i.e. Suzuki's start; the border is
+//                 recorded with its length) or meets a transition the raster scan would have seen earlier (=> abort) (b)
 //   k_emit        borders longer than 70 points are followed once more and written as point lists
 //   k_quads       warp per border: cv::approxPolyDP(eps = 0.05*len, closed) + isContourConvex (3253-3292)
 //   k_prefilter   CTA per frame: candidate order = reverse discovery order, corner orientation, too-near pairs,
@@ -58,46 +59,60 @@ struct Candidate { int cx[4], cy[4]; int key; int contour; };
 struct Kept { float c[8]; int contour; };
 struct Decoded { int id, nrot; };
 
-__constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-__constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 
 // ------------------------------------------------------------------------------------------------
 // A1: adaptive threshold.  mean = rint(S/bs^2) (ties impossible for odd bs^2); out = src - mean <= -7.
 // One CTA -> 32x32 output tile; (32+2r)^2 replicate-clamped source patch in shared memory.
 // ------------------------------------------------------------------------------------------------
-constexpr int kThrTile = 32, kThrMaxR = 7;
+constexpr int kThrTile = 32, kThrMaxR = 7, kThrB = kThrTile + 2;    // binary values are needed one pixel around the tile
 
 __global__ void __launch_bounds__(256)
 k_athresh(const uint8_t* __restrict__ img, long long row_stride, long long frame_stride, const __grid_constant__ ArucoGeom g,
-          uint8_t* __restrict__ bin) {
-    __shared__ uint8_t patch[kThrTile + 2 * kThrMaxR][kThrTile + 2 * kThrMaxR + 2];
-    __shared__ uint16_t hs[kThrTile + 2 * kThrMaxR][kThrTile];
-    const int f = blockIdx.z, x0 = blockIdx.x * kThrTile, y0 = blockIdx.y * kThrTile;
-    const int bs = g.win, r = bs >> 1, side = kThrTile + 2 * r;
+          uint8_t* __restrict__ mask) {
+    __shared__ uint8_t patch[kThrB + 2 * kThrMaxR][kThrB + 2 * kThrMaxR + 2];
+    __shared__ uint16_t hs[kThrB + 2 * kThrMaxR][kThrB];
+    __shared__ uint8_t bin[kThrB][kThrB + 2];
+    const int f = blockIdx.z, x0 = blockIdx.x * kThrTile - 1, y0 = blockIdx.y * kThrTile - 1;    // origin of the 34x34 binary block
+    const int bs = g.win, r = bs >> 1, side = kThrB + 2 * r;
     const uint8_t* src = img + (long long)f * frame_stride;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     for (int i = tid; i < side * side; i += 256) {
         const int py = i / side, px = i - py * side;
-        const int yy = min(max(y0 + py - r, 0), g.h - 1), xx = min(max(x0 + px - r, 0), g.w - 1);
+        const int yy = min(max(y0 + py - r, 0), g.h - 1), xx = min(max(x0 + px - r, 0), g.w - 1);     // BORDER_REPLICATE
         patch[py][px] = src[(long long)yy * row_stride + xx];
     }
     __syncthreads();
-    for (int i = tid; i < side * kThrTile; i += 256) {
-        const int py = i / kThrTile, px = i - py * kThrTile;
+    for (int i = tid; i < side * kThrB; i += 256) {
+        const int py = i / kThrB, px = i - py * kThrB;
         int s = 0;
         for (int k = 0; k < bs; k++) s += patch[py][px + k];
         hs[py][px] = (uint16_t)s;
     }
     __syncthreads();
     const double scale = 1.0 / ((double)bs * bs);
-    for (int ty = threadIdx.y; ty < kThrTile; ty += 8) {
-        const int x = x0 + threadIdx.x, y = y0 + ty;
-        if (x < g.w && y < g.h) {
+    for (int i = tid; i < kThrB * kThrB; i += 256) {
+        const int by = i / kThrB, bx = i - by * kThrB;
+        const int x = x0 + bx, y = y0 + by;
+        int v = 0;
+        if (x >= 0 && x < g.w && y >= 0 && y < g.h) {
             int s = 0;
-            for (int k = 0; k < bs; k++) s += hs[ty + k][threadIdx.x];
+            for (int k = 0; k < bs; k++) s += hs[by + k][bx];
             const int mean = min(__double2int_rn((double)s * scale), 255);
-            const int v = patch[ty + r][threadIdx.x + r];
-            bin[(long long)f * g.bframe + (long long)(y + 1) * g.bpitch + x + 1] = (v - mean <= -7) ? 1 : 0;
+            v = ((int)patch[by + r][bx + r] - mean <= -7) ? 1 : 0;
+        }
+        bin[by][bx] = (uint8_t)v;
+    }
+    __syncthreads();
+    // 8-neighbour foreground mask (bit d = neighbour in direction d: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE); 0 for background
+    for (int ty = threadIdx.y; ty < kThrTile; ty += 8) {
+        const int bx = threadIdx.x + 1, by = ty + 1;
+        const int x = x0 + bx, y = y0 + by;
+        if (x < g.w && y < g.h) {
+            int m = 0;
+            if (bin[by][bx])
+                m = bin[by][bx + 1] | (bin[by - 1][bx + 1] << 1) | (bin[by - 1][bx] << 2) | (bin[by - 1][bx - 1] << 3) | (bin[by][bx - 1] << 4) |
+                    (bin[by + 1][bx - 1] << 5) | (bin[by + 1][bx] << 6) | (bin[by + 1][bx + 1] << 7);
+            mask[(long long)f * g.bframe + (long long)(y + 1) * g.bpitch + x + 1] = (uint8_t)m;
         }
     }
 }
@@ -149,21 +164,6 @@ k_halfpyr(const uint8_t* __restrict__ src0, long long srs, long long sfs, int sw
 // passes the zero West (East) neighbour is where the raster scan would see a 0->1 (1->0) transition at raster
 // position pos(p) (pos(p)+1).  Suzuki starts every border at its raster-first transition.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_nbrmask(const uint8_t* __restrict__ bin, const __grid_constant__ ArucoGeom g, uint8_t* __restrict__ mask) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    if (x >= g.w || y >= g.h) return;
-    const long long base = (long long)f * g.bframe + (long long)(y + 1) * g.bpitch + x + 1;
-    const uint8_t* b = bin + base;
-    int m = 0;
-    if (b[0]) {
-        const int P = g.bpitch;
-        m = (b[1] ? 1 : 0) | (b[-P + 1] ? 2 : 0) | (b[-P] ? 4 : 0) | (b[-P - 1] ? 8 : 0) | (b[-1] ? 16 : 0) | (b[P - 1] ? 32 : 0) |
-            (b[P] ? 64 : 0) | (b[P + 1] ? 128 : 0);
-    }
-    mask[base] = (uint8_t)m;
-}
-
 struct Step { int d, k; };     // direction taken and number of directions swept before it (all zero)
 __device__ __forceinline__ Step next_step(int m, int s) {
     const unsigned r = (((unsigned)m | ((unsigned)m << 8)) >> ((s + 1) & 7)) & 0xffu;
@@ -180,22 +180,100 @@ __device__ __forceinline__ int step_key(int pos, int s, int k) {
     return 0x7fffffff;
 }
 
-__device__ void probe_border(const uint8_t* __restrict__ mask, const ArucoGeom& g, int P, int m0, bool hole, int f,
-                             ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts, int* __restrict__ err) {
-    // Suzuki's first neighbour search: clockwise from NW (outer) / from SE (hole)
-    int s0 = -1;
+// the step that precedes (p, s) on its border: it sits on q = p + delta[s], left q in direction d = s+4, and its own
+// back direction is the first foreground direction clockwise from d-1 (d itself when q has a single neighbour)
+__device__ __forceinline__ void prev_step(int mq, int d, int& sq, int& kq) {
+    const unsigned r = (((unsigned)mq | ((unsigned)mq << 8)) >> d) & 0xfeu;     // bit j <-> direction d+j, j = 1..7
+    const int j = r ? 31 - __clz(r) : 0;
+    sq = (d + j) & 7;
+    kq = 7 - j;                                   // zero directions swept between sq and d
+}
+
+__device__ __forceinline__ int dir_delta(int d, int pitch) {
+    // dx+1 / dy+1 of the 8 directions packed two bits each
+    const int dx = ((0x901A >> (2 * d)) & 3) - 1, dy = ((0xA901 >> (2 * d)) & 3) - 1;
+    return dy * pitch + dx;
+}
+
+// Phase A (thread per pixel): is this 0->1 (West is 0) or 1->0 (East is 0) transition possibly the raster-first transition of
+// its border?  Walk BACKWARDS along the border to the previous transition: if the raster scan sees that one earlier, no.
+// (This kills the long walks of every non-topmost pixel of a left edge.)  Survivors are compacted for phase B.
+__device__ int probe_candidate(const uint8_t* __restrict__ mask, const ArucoGeom& g, int P, int m0, bool hole, int* __restrict__ err) {
+    int s0 = -1;                                       // Suzuki's first neighbour search: clockwise from NW (outer) / SE (hole)
     const int from = hole ? 7 : 3;
     for (int i = 0; i < 7; i++) { const int d = (from - i) & 7; if (m0 & (1 << d)) { s0 = d; break; } }
-    if (s0 < 0) return;                               // isolated pixel: a one-point contour, never a marker
+    if (s0 < 0) return -1;                             // isolated pixel: a one-point contour, never a marker
     const int mykey = P + (hole ? 1 : 0);
+    {   // own step: a hole probe whose sweep also passes West belongs to the outer probe of the same pixel
+        const Step st = next_step(m0, s0);
+        if (step_key(P, s0, st.k) < mykey) return -1;
+    }
     int p = P, s = s0, n = 0;
-    const int deltas[8] = {1, -g.bpitch + 1, -g.bpitch, -g.bpitch - 1, -1, g.bpitch - 1, g.bpitch, g.bpitch + 1};
     const int limit = 4 * g.max_points;
     for (;;) {
-        const int m = n == 0 ? m0 : mask[p];
-        const Step st = next_step(m, s);
-        if (step_key(p, s, st.k) < mykey) return;                 // an earlier transition owns this border (also: a hole probe whose own step sweeps West)
-        p += deltas[st.d];
+        const int q = p + dir_delta(s, g.bpitch), d = (s + 4) & 7;
+        int sq, kq;
+        prev_step(mask[q], d, sq, kq);
+        p = q; s = sq;
+        if (p == P && s == s0) break;                  // went all the way round: the only transition of the border
+        const int key = step_key(p, s, kq);
+        if (key < mykey) return -1;
+        if (key != 0x7fffffff) break;                  // a later transition: undecided, phase B walks forwards
+        if (++n > limit) { atomicExch(err, 3); return -1; }
+    }
+    return s0;
+}
+
+__global__ void __launch_bounds__(256)
+k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, int2* __restrict__ surv, int* __restrict__ nsurv,
+          int max_surv, int* __restrict__ err) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    const int P = (y + 1) * g.bpitch + x + 1;
+    int so = -1, sh = -1;
+    if (x < g.w && y < g.h) {
+        const int m = mask[P];
+        if (m != 0) {
+            if (!(m & 16)) so = probe_candidate(mask, g, P, m, false, err);
+            if (!(m & 1)) sh = probe_candidate(mask, g, P, m, true, err);
+        }
+    }
+    // warp-aggregated append of the survivors
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int s0 = t ? sh : so;
+        const unsigned bal = __ballot_sync(0xffffffffu, s0 >= 0);
+        if (bal) {
+            int base = 0;
+            if (lane == __ffs(bal) - 1) base = atomicAdd(nsurv + f, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+            if (s0 >= 0) {
+                const int idx = base + __popc(bal & ((1u << lane) - 1));
+                if (idx < max_surv) surv[(long long)f * max_surv + idx] = make_int2(P, s0 | (t << 8));
+                else atomicExch(err, 8);
+            }
+        }
+    }
+}
+
+// Phase B (thread per survivor): walk FORWARDS until back home (=> first transition of this border: record it with its
+// length) or until a transition that the raster scan sees earlier shows up (=> abort).
+__global__ void __launch_bounds__(128)
+k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int2* __restrict__ surv, const int* __restrict__ nsurv,
+          int max_surv, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts, int* __restrict__ err) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(nsurv[f], max_surv)) return;
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    const int2 sv = surv[(long long)f * max_surv + i];
+    const int P = sv.x, s0 = sv.y & 7;
+    const int mykey = P + (sv.y >> 8);
+    const int limit = 4 * g.max_points;
+    int p = P, s = s0, n = 0;
+    for (;;) {
+        const Step st = next_step(mask[p], s);
+        if (n > 0 && step_key(p, s, st.k) < mykey) return;
+        p += dir_delta(st.d, g.bpitch);
         s = (st.d + 4) & 7;
         n++;
         if (p == P && s == s0) break;
@@ -211,19 +289,6 @@ __device__ void probe_border(const uint8_t* __restrict__ mask, const ArucoGeom& 
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_probe(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, ContourDesc* __restrict__ desc,
-        int* __restrict__ ncont, int* __restrict__ npts, int* __restrict__ err) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    if (x >= g.w || y >= g.h) return;
-    const uint8_t* mask = mask0 + (long long)f * g.bframe;
-    const int P = (y + 1) * g.bpitch + x + 1;
-    const int m = mask[P];
-    if (m == 0) return;                                // background or isolated pixel
-    if (!(m & 16)) probe_border(mask, g, P, m, false, f, desc, ncont, npts, err);     // West is 0: outer-border start?
-    if (!(m & 1)) probe_border(mask, g, P, m, true, f, desc, ncont, npts, err);       // East is 0: hole-border start?
-}
-
 __global__ void __launch_bounds__(128)
 k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ desc,
        const int* __restrict__ ncont, short2* __restrict__ pts) {
@@ -232,13 +297,13 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
     const ContourDesc c = desc[(long long)f * g.max_contours + i];
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
     short2* out = pts + (long long)f * g.max_points + c.off;
-    const int deltas[8] = {1, -g.bpitch + 1, -g.bpitch, -g.bpitch - 1, -1, g.bpitch - 1, g.bpitch, g.bpitch + 1};
     int p = c.start, s = c.s0;
     int x = c.start % g.bpitch - 1, y = c.start / g.bpitch - 1;
     for (int n = 0; n < c.len; n++) {
         out[n] = make_short2((short)x, (short)y);
         const Step st = next_step(mask[p], s);
-        p += deltas[st.d]; x += c_dx[st.d]; y += c_dy[st.d];
+        const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
+        p += dy * g.bpitch + dx; x += dx; y += dy;
         s = (st.d + 4) & 7;
     }
 }
@@ -505,7 +570,7 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
     __shared__ unsigned long long s_ids[4];
     __shared__ int s_ok;
     const int f = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
-    if (k >= nkept[f]) return;
+    if (k >= min(nkept[f], kMaxCand)) return;
     const Kept kp = kept0[(long long)f * kMaxCand + k];
     const int ws = g.wsize;
     if (tid == 0) {
@@ -936,11 +1001,11 @@ struct b200_aruco_s {
     unsigned long long* d_codes;
     int cur_w, cur_h;
     ArucoGeom geom;
-    uint8_t *d_bin, *d_mask, *d_pyr;
+    uint8_t *d_mask, *d_pyr; int2* d_surv; int max_surv;
     ContourDesc* d_desc; short2* d_pts; float* d_scratch;
     Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
-    int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_err;
-    size_t cap_bin, cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch;
+    int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_err;
+    size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
 };
@@ -1005,12 +1070,10 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     g.max_contours = w * hh / (kMinContour + 1) + 1;       // borders longer than 70 points sharing w*h points
     const size_t B = (size_t)h->max_batch;
     int rc;
-    const size_t old_bin = h->cap_bin;
-    if ((rc = ensure_buf(h->d_bin, h->cap_bin, (size_t)g.bframe * B))) return rc;
     if ((rc = ensure_buf(h->d_mask, h->cap_mask, (size_t)g.bframe * B))) return rc;
-    (void)old_bin;
-    B200_CUDA(cudaMemset(h->d_bin, 0, (size_t)g.bframe * B));       // the 1-px zero frame is never written afterwards
-    B200_CUDA(cudaMemset(h->d_mask, 0, (size_t)g.bframe * B));
+    B200_CUDA(cudaMemset(h->d_mask, 0, (size_t)g.bframe * B));       // the 1-px zero frame is never written afterwards
+    h->max_surv = std::max(1024, w * hh / 8);
+    if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int2) * (size_t)h->max_surv * B))) return rc;
     if ((rc = ensure_buf(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame * B))) return rc;
     if ((rc = ensure_buf(h->d_desc, h->cap_desc, sizeof(ContourDesc) * (size_t)g.max_contours * B))) return rc;
     if ((rc = ensure_buf(h->d_pts, h->cap_pts, sizeof(short2) * (size_t)g.max_points * B))) return rc;
@@ -1043,10 +1106,10 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     ok = ok && cudaMalloc((void**)&h->d_cand, sizeof(Candidate) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_kept, sizeof(Kept) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_dec, sizeof(Decoded) * kMaxCand * B) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&h->d_ncont, 4 * B * 4 + 4) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_ncont, 5 * B * 4 + 4) == cudaSuccess;
     if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
-    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_err = h->d_nkept + B;
-    cudaMemset(h->d_ncont, 0, 4 * B * 4 + 4);
+    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_err = h->d_nsurv + B;
+    cudaMemset(h->d_ncont, 0, 5 * B * 4 + 4);
     if ((rc = aruco_geometry(h, max_w, max_h))) { b200_aruco_destroy(h); return rc; }
     *out = h;
     return B200_OK;
@@ -1055,7 +1118,7 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
 int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_codes); cudaFree(h->d_bin); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
+    cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
     cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1083,10 +1146,10 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
     if (rs < w || (n > 1 && fs < rs * (hh - 1) + w)) return fail(B200_EINVAL, "bad %s", "strides");
     if ((rc = aruco_geometry(h, w, hh))) return rc;
     const ArucoGeom& g = h->geom;
-    B200_CUDA(cudaMemsetAsync(h->d_ncont, 0, 4 * (size_t)h->max_batch * 4, st));
+    B200_CUDA(cudaMemsetAsync(h->d_ncont, 0, 5 * (size_t)h->max_batch * 4, st));
     dim3 blk(32, 8);
     dim3 gt((w + kThrTile - 1) / kThrTile, (hh + kThrTile - 1) / kThrTile, n);
-    B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, h->d_bin);
+    B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, h->d_mask);
     for (int l = 1; l < g.nlev; l++) {
         const uint8_t* src = l == 1 ? imgs : h->d_pyr + g.loff[l - 1];
         const long long srs = l == 1 ? rs : g.lpitch[l - 1], sfs = l == 1 ? fs : g.pyr_frame;
@@ -1094,8 +1157,11 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
         B200_LAUNCH(k_halfpyr, gp, blk, 0, st, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], h->d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
     }
     dim3 gm((w + 31) / 32, (hh + 7) / 8, n);
-    B200_LAUNCH(k_nbrmask, gm, blk, 0, st, h->d_bin, g, h->d_mask);
-    B200_LAUNCH(k_probe, gm, blk, 0, st, h->d_mask, g, h->d_desc, h->d_ncont, h->d_npts, h->d_err);
+    B200_LAUNCH(k_probe_a, gm, blk, 0, st, h->d_mask, g, h->d_surv, h->d_nsurv, h->max_surv, h->d_err);
+    {
+        dim3 gb((h->max_surv + 127) / 128, n);
+        B200_LAUNCH(k_probe_b, gb, 128, 0, st, h->d_mask, g, h->d_surv, h->d_nsurv, h->max_surv, h->d_desc, h->d_ncont, h->d_npts, h->d_err);
+    }
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
     {
         const int grid_c = g.max_contours;
@@ -1125,8 +1191,8 @@ int b200_aruco_check(b200_aruco_t h, void* stream) {
     B200_CUDA(cudaStreamSynchronize(st));
     if (err) {
         B200_CUDA(cudaMemsetAsync(h->d_err, 0, 4, st));
-        static const char* what[] = {"", "", "", "border longer than the point budget", "too many contours", "contour point budget", "more than 256 quads", "more than 64 markers"};
-        return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 8 ? err : 0]);
+        static const char* what[] = {"", "", "", "border longer than the point budget", "too many contours", "contour point budget", "more than 256 quads", "more than 64 markers", "transition survivor list"};
+        return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 9 ? err : 0]);
     }
     return B200_OK;
 }
@@ -1188,8 +1254,8 @@ int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int w, in
     B200_CUDA(cudaStreamSynchronize(st));
     if (err) {
         cudaMemset(h->d_err, 0, 4);
-        static const char* what[] = {"", "", "", "border longer than the point budget", "too many contours", "contour point budget", "more than 256 quads", "more than 64 markers"};
-        return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 8 ? err : 0]);
+        static const char* what[] = {"", "", "", "border longer than the point budget", "too many contours", "contour point budget", "more than 256 quads", "more than 64 markers", "transition survivor list"};
+        return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 9 ? err : 0]);
     }
     return B200_OK;
 }

@@ -92,7 +92,7 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
                 const ulonglong4* __restrict__ frame_desc, const float* __restrict__ frame_angle, int frame_astride,
                 const int* __restrict__ n_frame, int frame_cap, const uint32_t* __restrict__ topk,
                 float ratio, int th_low, int check_ori, float histo_factor,
-                int* __restrict__ match_ref_idx, int* __restrict__ n_matches) {
+                int* __restrict__ match_ref_idx, int* __restrict__ n_matches, int stage_topk) {
     extern __shared__ unsigned int s_mem[];
     const int f = blockIdx.x, lane = threadIdx.x;
     const int nf = min(n_frame[f], frame_cap);
@@ -107,9 +107,17 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
     __syncwarp();
     const ulonglong4* fd = frame_desc + (long long)f * frame_cap;
     const float* fa = frame_angle + (long long)f * frame_cap * frame_astride;
+    // this frame's top-K lists: staged in shared memory when they fit (the loop below is a serial dependency chain)
+    const uint32_t* tk_base = topk + (long long)f * n_ref * kTopK;
+    if (stage_topk) {
+        uint32_t* s_tk = reinterpret_cast<uint32_t*>(bin_of + ((frame_cap + 15) & ~15));
+        for (int i = lane; i < n_ref * kTopK; i += 32) s_tk[i] = tk_base[i];
+        tk_base = s_tk;
+        __syncwarp();
+    }
     int nm = 0;
     for (int r = 0; r < n_ref; r++) {
-        const uint32_t* tk = topk + ((long long)f * n_ref + r) * kTopK;
+        const uint32_t* tk = tk_base + (long long)r * kTopK;
         // first two untaken entries of the sorted list
         uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu, last = 0xffffffffu;
         int found = 0;
@@ -260,10 +268,13 @@ static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int re
         B200_LAUNCH(k_match_topk, grid, kMatchWarps * 32, smem, st, (const ulonglong4*)ref_desc, n_ref, (const ulonglong4*)frame_desc,
                     n_frame, frame_cap, g_ms.topk);
     }
-    const size_t smem2 = (size_t)((frame_cap + 31) / 32) * 4 + (size_t)frame_cap + 16;
+    size_t smem2 = (size_t)((frame_cap + 31) / 32) * 4 + (size_t)((frame_cap + 15) & ~15) + 16;
+    const size_t tk_bytes = (size_t)n_ref * kTopK * 4;
+    const int stage_topk = smem2 + tk_bytes <= 160 * 1024;
+    if (stage_topk) smem2 += tk_bytes;
     B200_CUDA(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem2, 1024)));
     B200_LAUNCH(k_match_resolve, n_batch, 32, smem2, st, (const ulonglong4*)ref_desc, ref_angle, ref_astride, n_ref, (const ulonglong4*)frame_desc,
-                frame_angle, frame_astride, n_frame, frame_cap, g_ms.topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches);
+                frame_angle, frame_astride, n_frame, frame_cap, g_ms.topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, stage_topk);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

@@ -140,15 +140,26 @@ __device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int v) {
 }
 
 constexpr int kFastThreads = 128;
+constexpr int kTP = kMaxRoi + 8;            // smem tile pitch
+constexpr int kMaxInterior = kMaxRoi - 6;
 
+// One CTA per (cell, frame).  Like the reference, the cell is first examined at iniThFAST and only when that yields no
+// keypoint (after NMS) again at minThFAST (ORBextractor.cc:809-816).  Per threshold T:
+//   1. pretest every interior pixel: a 9-arc always contains two ADJACENT compass points (circle positions 0,4,8,12), so
+//      a corner needs two adjacent compass pixels both > v+T or both < v-T; survivors go to a shared-memory queue
+//   2. dense pass over the queue: full score (DPX min3/max3), stored in the score tile when >= T
+//   3. 3x3 NMS (strict >, neighbours outside the cell interior count 0) as a per-row bit mask + row counts
+// then a raster-ordered compaction of the surviving pixels into the cell's candidate slots.
 __global__ void __launch_bounds__(kFastThreads)
 k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
        const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g,
        const CellDesc* __restrict__ cells, uint32_t* __restrict__ slots, int* __restrict__ cellcnt) {
-    __shared__ uint8_t tile[kMaxRoi][kMaxRoi + 8];
-    __shared__ uint8_t score[kMaxRoi][kMaxRoi + 8];
-    __shared__ int row_cnt20[kMaxRoi], row_cnt7[kMaxRoi];
-    __shared__ int s_total20;
+    __shared__ uint8_t tile[kMaxRoi][kTP];
+    __shared__ uint8_t score[kMaxRoi][kTP];
+    __shared__ uint16_t queue[kMaxInterior * kMaxInterior];
+    __shared__ uint32_t keep[kMaxInterior][3];
+    __shared__ int row_ofs[kMaxInterior];
+    __shared__ int s_q, s_total;
 
     const CellDesc cd = cells[blockIdx.x];
     const int f = blockIdx.y;
@@ -161,99 +172,106 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
 
     const int rw = cd.rw, rh = cd.rh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // stage the ROI (coalesced along rows; one row per warp iteration) and clear the score tile
-    for (int y = warp; y < rh; y += kFastThreads / 32)
+    constexpr int NW = kFastThreads / 32;
+    for (int y = warp; y < rh; y += NW)
         for (int x = lane; x < rw; x += 32) {
             tile[y][x] = base[(long long)y * pitch + x];
             score[y][x] = 0;
         }
+    if (tid == 0) s_q = 0;
     __syncthreads();
 
-    const int minth = g.min_th;
     const int iw = rw - 6, ih = rh - 6;               // interior
-    for (int y = warp; y < ih; y += kFastThreads / 32) {
-        for (int x0 = 0; x0 < iw; x0 += 32) {
-            const int x = x0 + lane;
-            bool act = x < iw;
-            const uint8_t* p = &tile[y + 3][min(x, iw - 1) + 3];
-            const int v = p[0];
-            // quick reject: every arc of 9 contains one pixel of each opposite pair
-            if (act) {
-                const int lo = v - minth, hi = v + minth;
-                int a0 = p[3 * (kMaxRoi + 8)], a8 = p[-3 * (kMaxRoi + 8)], a4 = p[3], a12 = p[-3];
-                act = ((a0 > hi) | (a8 > hi) | (a0 < lo) | (a8 < lo)) & ((a4 > hi) | (a12 > hi) | (a4 < lo) | (a12 < lo));
-            }
-            if (__any_sync(0xffffffffu, act)) {
-                int s = fast_score(p, kMaxRoi + 8, v);
-                if (act && s >= minth) score[y + 3][x + 3] = (uint8_t)s;
-            }
-        }
-    }
-    __syncthreads();
-
-    // NMS (strict > over the 8 neighbours inside this ROI; outside counts 0) + per-row counts
-    const int inith = g.ini_th;
-    for (int y = warp; y < ih; y += kFastThreads / 32) {
-        int c20 = 0, c7 = 0;
-        for (int x0 = 0; x0 < iw; x0 += 32) {
-            const int x = x0 + lane;
-            bool keep = false; int s = 0;
-            if (x < iw) {
-                const uint8_t* q = &score[y + 3][x + 3];
-                s = q[0];
-                if (s) {
-                    const int P = kMaxRoi + 8;
-                    keep = s > q[-1] && s > q[1] && s > q[-P - 1] && s > q[-P] && s > q[-P + 1] && s > q[P - 1] && s > q[P] && s > q[P + 1];
+    const int nchunk = (iw + 31) >> 5;
+    int T = g.ini_th;
+    for (int pass = 0; pass < 2; pass++) {
+        // 1. pretest + enqueue
+        for (int y = warp; y < ih; y += NW) {
+            for (int c = 0; c < nchunk; c++) {
+                const int x = c * 32 + lane;
+                bool cand = false;
+                if (x < iw) {
+                    const uint8_t* p = &tile[y + 3][x + 3];
+                    const int v = p[0], lo = v - T, hi = v + T;
+                    const int c0 = p[3 * kTP], c4 = p[3], c8 = p[-3 * kTP], c12 = p[-3];
+                    const bool b0 = c0 > hi, b4 = c4 > hi, b8 = c8 > hi, b12 = c12 > hi;
+                    const bool d0 = c0 < lo, d4 = c4 < lo, d8 = c8 < lo, d12 = c12 < lo;
+                    cand = (b0 & b4) | (b4 & b8) | (b8 & b12) | (b12 & b0) | (d0 & d4) | (d4 & d8) | (d8 & d12) | (d12 & d0);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m) {
+                    int qb = 0;
+                    if (lane == 0) qb = atomicAdd(&s_q, __popc(m));
+                    qb = __shfl_sync(0xffffffffu, qb, 0);
+                    if (cand) queue[qb + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
                 }
             }
-            c7 += __popc(__ballot_sync(0xffffffffu, keep));
-            c20 += __popc(__ballot_sync(0xffffffffu, keep && s >= inith));
         }
-        if (lane == 0) { row_cnt20[y] = c20; row_cnt7[y] = c7; }
+        __syncthreads();
+        // 2. scores of the queued pixels
+        const int nq = s_q;
+        for (int i = tid; i < nq; i += kFastThreads) {
+            const int e = queue[i], y = e >> 8, x = e & 255;
+            const uint8_t* p = &tile[y + 3][x + 3];
+            const int sc = fast_score(p, kTP, p[0]);
+            if (sc >= T) score[y + 3][x + 3] = (uint8_t)sc;
+        }
+        __syncthreads();
+        // 3. NMS -> per-row bit masks and counts
+        int cnt = 0;
+        for (int y = warp; y < ih; y += NW) {
+            int rc = 0;
+            for (int c = 0; c < nchunk; c++) {
+                const int x = c * 32 + lane;
+                bool k = false;
+                if (x < iw) {
+                    const uint8_t* q = &score[y + 3][x + 3];
+                    const int sc = q[0];
+                    if (sc)
+                        k = sc > q[-1] && sc > q[1] && sc > q[-kTP - 1] && sc > q[-kTP] && sc > q[-kTP + 1] && sc > q[kTP - 1] && sc > q[kTP] && sc > q[kTP + 1];
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, k);
+                if (lane == 0) keep[y][c] = m;
+                rc += __popc(m);
+            }
+            if (lane == 0) row_ofs[y] = rc;
+            cnt += rc;
+        }
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        if (lane == 0 && cnt) atomicAdd(&s_total, cnt);
+        __syncthreads();
+        if (s_total > 0 || pass == 1 || g.min_th >= g.ini_th) break;
+        // nothing at iniThFAST: the whole cell again at minThFAST (a superset of the pixels examined so far)
+        T = g.min_th;
+        if (tid == 0) s_q = 0;
+        __syncthreads();
     }
-    __syncthreads();
-    if (warp == 0) {   // exclusive scan over rows (<= 66 rows)
-        int run20 = 0, run7 = 0;
+    // exclusive scan of the row counts (<= 66 rows), then ordered emission
+    if (warp == 0) {
+        int run = 0;
         for (int y0 = 0; y0 < ih; y0 += 32) {
-            int y = y0 + lane;
-            int a = y < ih ? row_cnt20[y] : 0, b = y < ih ? row_cnt7[y] : 0;
-            int sa = a, sb = b;
+            const int y = y0 + lane;
+            const int a = y < ih ? row_ofs[y] : 0;
+            int sa = a;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
-                if (lane >= o) { sa += ta; sb += tb; }
-            }
-            if (y < ih) { row_cnt20[y] = run20 + sa - a; row_cnt7[y] = run7 + sb - b; }
-            run20 += __shfl_sync(0xffffffffu, sa, 31);
-            run7 += __shfl_sync(0xffffffffu, sb, 31);
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sa, o); if (lane >= o) sa += t; }
+            if (y < ih) row_ofs[y] = run + sa - a;
+            run += __shfl_sync(0xffffffffu, sa, 31);
         }
-        if (lane == 0) {
-            s_total20 = run20;
-            cellcnt[(long long)f * g.total_cells + blockIdx.x] = run20 > 0 ? run20 : run7;
-        }
+        if (lane == 0) cellcnt[(long long)f * g.total_cells + blockIdx.x] = run;
     }
     __syncthreads();
-    const bool use20 = s_total20 > 0;               // fallback to minThFAST only when the cell is empty at iniThFAST
-    const int th = use20 ? inith : minth;
     uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
-    for (int y = warp; y < ih; y += kFastThreads / 32) {
-        int ofs = use20 ? row_cnt20[y] : row_cnt7[y];
-        for (int x0 = 0; x0 < iw; x0 += 32) {
-            const int x = x0 + lane;
-            bool keep = false; int s = 0;
-            if (x < iw) {
-                const uint8_t* q = &score[y + 3][x + 3];
-                s = q[0];
-                if (s >= th) {
-                    const int P = kMaxRoi + 8;
-                    keep = s > q[-1] && s > q[1] && s > q[-P - 1] && s > q[-P] && s > q[-P + 1] && s > q[P - 1] && s > q[P] && s > q[P + 1];
-                }
-            }
-            unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                int pos = ofs + __popc(m & ((1u << lane) - 1));
+    for (int y = warp; y < ih; y += NW) {
+        int ofs = row_ofs[y];
+        for (int c = 0; c < nchunk; c++) {
+            const unsigned m = keep[y][c];
+            if (m & (1u << lane)) {
+                const int x = c * 32 + lane;
+                const int pos = ofs + __popc(m & ((1u << lane) - 1));
                 // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
-                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)s << 24);
+                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)score[y + 3][x + 3] << 24);
             }
             ofs += __popc(m);
         }

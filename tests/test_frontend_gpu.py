@@ -39,8 +39,12 @@ def test_frontend_matches_three_oracles(built_lib):
     pin = torch.from_numpy(imgs).pin_memory()
     out2 = fe.alloc_outputs(5, pinned=True)
     fe.process_batch(pin.numpy(), rd, rk, out=out2)
-    for key in out:
+    for key in ("counts", "marker_counts", "n_matches"):
         assert np.array_equal(out[key], out2[key]), key
+    for f in range(5):                                   # slots beyond the counts are unspecified
+        n, m = int(out["counts"][f]), int(out["marker_counts"][f])
+        assert np.array_equal(out["kps"][f, :n], out2["kps"][f, :n]) and np.array_equal(out["desc"][f, :n], out2["desc"][f, :n])
+        assert np.array_equal(out["markers"][f, :m], out2["markers"][f, :m]) and np.array_equal(out["matches"][f, :n], out2["matches"][f, :n])
 
 
 def test_frontend_multi_chunk_batch(built_lib):
