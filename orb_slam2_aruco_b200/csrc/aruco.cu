@@ -199,10 +199,12 @@ __device__ __forceinline__ int dir_delta(int d, int pitch) {
 // its border?  Walk BACKWARDS along the border to the previous transition: if the raster scan sees that one earlier, no.
 // (This kills the long walks of every non-topmost pixel of a left edge.)  Survivors are compacted for phase B.
 __device__ int probe_candidate(const uint8_t* __restrict__ mask, const ArucoGeom& g, int P, int m0, bool hole, int* __restrict__ err) {
-    int s0 = -1;                                       // Suzuki's first neighbour search: clockwise from NW (outer) / SE (hole)
+    // Suzuki's first neighbour search: clockwise from NW (outer) / SE (hole) over 7 directions = highest set bit of the
+    // mask rotated so that the first direction examined sits at bit 7 (the 8th direction, W resp. E, is known to be 0)
     const int from = hole ? 7 : 3;
-    for (int i = 0; i < 7; i++) { const int d = (from - i) & 7; if (m0 & (1 << d)) { s0 = d; break; } }
-    if (s0 < 0) return -1;                             // isolated pixel: a one-point contour, never a marker
+    const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;      // bit j <-> direction from+1+j
+    if (rot == 0) return -1;                           // isolated pixel: a one-point contour, never a marker
+    const int s0 = (from + 1 + (31 - __clz(rot))) & 7;
     const int mykey = P + (hole ? 1 : 0);
     {   // own step: a hole probe whose sweep also passes West belongs to the outer probe of the same pixel
         const Step st = next_step(m0, s0);
@@ -238,22 +240,24 @@ k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
             if (!(m & 1)) sh = probe_candidate(mask, g, P, m, true, err);
         }
     }
-    // warp-aggregated append of the survivors
-    const int lane = threadIdx.x;
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        const int s0 = t ? sh : so;
-        const unsigned bal = __ballot_sync(0xffffffffu, s0 >= 0);
-        if (bal) {
-            int base = 0;
-            if (lane == __ffs(bal) - 1) base = atomicAdd(nsurv + f, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-            if (s0 >= 0) {
-                const int idx = base + __popc(bal & ((1u << lane) - 1));
-                if (idx < max_surv) surv[(long long)f * max_surv + idx] = make_int2(P, s0 | (t << 8));
-                else atomicExch(err, 8);
-            }
-        }
+    // CTA-aggregated append of the survivors: shared-memory slots, ONE global atomic per CTA
+    __shared__ int s_n, s_base;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    int slot_o = -1, slot_h = -1;
+    if (so >= 0) slot_o = atomicAdd(&s_n, 1);
+    if (sh >= 0) slot_h = atomicAdd(&s_n, 1);
+    __syncthreads();
+    if (tid == 0 && s_n) s_base = atomicAdd(nsurv + f, s_n);
+    __syncthreads();
+    if (slot_o >= 0) {
+        const int idx = s_base + slot_o;
+        if (idx < max_surv) surv[(long long)f * max_surv + idx] = make_int2(P, so); else atomicExch(err, 8);
+    }
+    if (slot_h >= 0) {
+        const int idx = s_base + slot_h;
+        if (idx < max_surv) surv[(long long)f * max_surv + idx] = make_int2(P, sh | (1 << 8)); else atomicExch(err, 8);
     }
 }
 
@@ -1072,7 +1076,7 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     int rc;
     if ((rc = ensure_buf(h->d_mask, h->cap_mask, (size_t)g.bframe * B))) return rc;
     B200_CUDA(cudaMemset(h->d_mask, 0, (size_t)g.bframe * B));       // the 1-px zero frame is never written afterwards
-    h->max_surv = std::max(1024, w * hh / 8);
+    h->max_surv = std::max(1024, w * hh / 2);          // salt-and-pepper noise: nearly every second pixel starts a tiny border
     if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int2) * (size_t)h->max_surv * B))) return rc;
     if ((rc = ensure_buf(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame * B))) return rc;
     if ((rc = ensure_buf(h->d_desc, h->cap_desc, sizeof(ContourDesc) * (size_t)g.max_contours * B))) return rc;

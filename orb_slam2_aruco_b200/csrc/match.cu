@@ -115,33 +115,47 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
         tk_base = s_tk;
         __syncwarp();
     }
+    // The reference loop is serial in r, but the only state it carries is the "taken" set, which changes on accepted
+    // matches only.  So 32 consecutive r are evaluated speculatively, one per lane, against the current set; the first
+    // lane that accepts a match (or needs the exact rescan) is committed and everything after it is re-evaluated.
     int nm = 0;
-    for (int r = 0; r < n_ref; r++) {
-        const uint32_t* tk = tk_base + (long long)r * kTopK;
-        // first two untaken entries of the sorted list
+    int r0 = 0;
+    while (r0 < n_ref) {
+        const int r = r0 + lane;
         uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu, last = 0xffffffffu;
-        int found = 0;
+        bool exact = true, accept = false;
+        if (r < n_ref) {
+            const uint32_t* tk = tk_base + (long long)r * kTopK;
+            int found = 0;
 #pragma unroll
-        for (int k = 0; k < kTopK; k++) {
-            const uint32_t key = tk[k];
-            if (key == 0xffffffffu) continue;
-            last = key;
-            const int idx = key & 0xffff;
-            if (!((taken[idx >> 5] >> (idx & 31)) & 1u)) {
-                if (found == 0) b1 = key; else if (found == 1) b2 = key;
-                found++;
+            for (int k = 0; k < kTopK; k++) {
+                const uint32_t key = tk[k];
+                if (key == 0xffffffffu) continue;
+                last = key;
+                const int idx = key & 0xffff;
+                if (!((taken[idx >> 5] >> (idx & 31)) & 1u)) {
+                    if (found == 0) b1 = key; else if (found == 1) b2 = key;
+                    found++;
+                }
+            }
+            if (nf > kTopK) {
+                // the list may hide untaken candidates beyond its end
+                if (found == 0) exact = ((int)(last >> 16) > th_low);          // everything hidden is >= last > th_low: no match possible
+                else if (found == 1) exact = ((int)(b1 >> 16) > th_low);       // best is known; second only matters if best can match
+            }
+            if (exact) {
+                const int d1 = b1 == 0xffffffffu ? 256 : (int)(b1 >> 16), d2 = b2 == 0xffffffffu ? 256 : (int)(b2 >> 16);
+                accept = d1 <= th_low && (float)d1 < __fmul_rn(ratio, (float)d2);
             }
         }
-        const int list_len = min(nf, kTopK);
-        bool exact = true;
-        if (nf > kTopK) {
-            // the list may hide untaken candidates beyond its end
-            if (found == 0) exact = ((int)(last >> 16) > th_low);          // everything hidden is >= last > th_low: no match possible
-            else if (found == 1) exact = ((int)(b1 >> 16) > th_low);       // best is known; second only matters if best can match
-        }
-        (void)list_len;
-        if (!exact) {                                                       // rare: rescan the whole row, all lanes
-            const ulonglong4 q = ref_desc[r];
+        const unsigned hot = __ballot_sync(0xffffffffu, accept || !exact);
+        if (!hot) { r0 += 32; continue; }
+        const int first = __ffs(hot) - 1;
+        const int rc = r0 + first;                                              // the reference index to commit
+        const bool need_scan = __shfl_sync(0xffffffffu, (int)!exact, first) != 0;
+        uint32_t c1 = __shfl_sync(0xffffffffu, b1, first), c2 = __shfl_sync(0xffffffffu, b2, first);
+        if (need_scan) {                                                        // rare: rescan the whole row, all lanes
+            const ulonglong4 q = ref_desc[rc];
             uint32_t l1 = 0xffffffffu, l2 = 0xffffffffu;
             for (int i = lane; i < nf; i += 32) {
                 if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
@@ -155,17 +169,17 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
                 l2 = min(hi, min(l2, o2));
                 l1 = lo;
             }
-            b1 = l1; b2 = l2;
+            c1 = l1; c2 = l2;
         }
-        const int d1 = b1 == 0xffffffffu ? 256 : (int)(b1 >> 16);
-        const int d2 = b2 == 0xffffffffu ? 256 : (int)(b2 >> 16);
+        const int d1 = c1 == 0xffffffffu ? 256 : (int)(c1 >> 16);
+        const int d2 = c2 == 0xffffffffu ? 256 : (int)(c2 >> 16);
         if (d1 <= th_low && (float)d1 < __fmul_rn(ratio, (float)d2)) {
-            const int idx = b1 & 0xffff;
+            const int idx = c1 & 0xffff;
             if (lane == 0) {
                 taken[idx >> 5] |= 1u << (idx & 31);
-                mout[idx] = r;
+                mout[idx] = rc;
                 if (check_ori) {
-                    float rot = __fsub_rn(ref_angle[(long long)r * ref_astride], fa[(long long)idx * frame_astride]);
+                    float rot = __fsub_rn(ref_angle[(long long)rc * ref_astride], fa[(long long)idx * frame_astride]);
                     if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                     int bin = (int)roundf(__fmul_rn(rot, histo_factor));
                     if (bin == kHistoLen) bin = 0;
@@ -175,8 +189,9 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
                 }
             }
             nm++;
-            __syncwarp();
         }
+        __syncwarp();
+        r0 = rc + 1;
     }
     __syncwarp();
     if (check_ori) {
