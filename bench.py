@@ -230,8 +230,13 @@ def main():
     s_main = torch.cuda.Stream(device=dev)
     s_aux = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    outs = [d_kps, d_desc, d_counts] + ([d_markers, d_mcounts] if det else []) + ([d_match, d_nmatch] if matcher else [])
-    gather = [[torch.empty_like(t) for _ in range(world)] for t in outs] if world > 1 else None
+    outs = {"kps": d_kps, "desc": d_desc, "counts": d_counts}
+    if det:
+        outs.update(markers=d_markers, marker_counts=d_mcounts)
+    if matcher:
+        outs.update(matches=d_match, n_matches=d_nmatch)
+    from orb_slam2_aruco_b200 import shard
+    collated = {}
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     def step():
@@ -245,10 +250,9 @@ def main():
             matcher.SearchByBoW_device(d_rdesc, d_rkps, n_ref, d_desc, d_kps, d_counts, d_match, d_nmatch, s_main)
         if det is not None:
             s_main.wait_event(ev_join)
-        if world > 1:
+        if world > 1:                            # every rank ends up with all B*world result slots (rank 0 is the consumer)
             with torch.cuda.stream(s_main):
-                for g, t in zip(gather, outs):
-                    dist.all_gather(g, t)
+                collated.update(shard.collate(outs, B * world))
 
     def sync_all():
         torch.cuda.synchronize(dev)

@@ -1,0 +1,255 @@
+// b200slam_adapters.hpp -- source-compatible C++ front-end classes on top of the C-ABI (include/b200slam.h).
+//
+// The reference has no FFI layer: src/Frame.cc and src/Tracking.cc call three C++ classes directly.
+// These adapters keep the reference's class names, constructor arguments and call signatures for the hot path, so
+// that Frame/Tracking compile against them unchanged, and marshal to libb200slam.so:
+//
+//   ORB_SLAM2::ORBextractor   reference include/ORBextractor.h:45-111  (operator() at :59-61, getters :63-83)
+//   ORB_SLAM2::ORBmatcher     reference include/ORBmatcher.h:38-104    (DescriptorDistance :44, constants :87-89; the
+//                             brute-force SearchByBoW core; the map-point glue of the other Search* stays host code)
+//   aruco::MarkerDetector     reference Thirdparty/aruco/aruco/markerdetector.h:58-410 (detect :276-278,
+//                             setDictionary :337, setDetectionMode :258, Params::setCornerRefinementMethod :129)
+//
+// OpenCV types: when <opencv2/core.hpp> is on the include path (a real integration) cv::Mat / cv::KeyPoint are used
+// as is.  Define B200SLAM_NO_OPENCV to get the minimal stand-ins below (used by tests/cpp/adapter_smoke.cpp, which
+// must build in an image without OpenCV).  Header only; link with -lb200slam.
+#pragma once
+#include <cassert>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "b200slam.h"
+
+#ifndef B200SLAM_NO_OPENCV
+#include <opencv2/core/core.hpp>
+#else
+namespace cv {
+struct Point2f { float x, y; Point2f(float _x = 0, float _y = 0) : x(_x), y(_y) {} };
+struct KeyPoint { Point2f pt; float size, angle, response; int octave, class_id; };
+static const int CV_8UC1_ = 0;
+#define CV_8U 0
+#define CV_8UC1 0
+// 8-bit single channel matrix owning or borrowing its pixels (enough for marshaling)
+class Mat {
+public:
+    int rows, cols; size_t step; unsigned char* data; std::vector<unsigned char> own;
+    Mat() : rows(0), cols(0), step(0), data(nullptr) {}
+    Mat(int r, int c, int, void* p, size_t s = 0) : rows(r), cols(c), step(s ? s : (size_t)c), data((unsigned char*)p) {}
+    void create(int r, int c, int) { rows = r; cols = c; step = (size_t)c; own.assign((size_t)r * c, 0); data = own.data(); }
+    void release() { rows = cols = 0; step = 0; data = nullptr; own.clear(); }
+    bool empty() const { return !data || rows * cols == 0; }
+    int type() const { return CV_8UC1; }
+    unsigned char* ptr(int y = 0) { return data + (size_t)y * step; }
+    const unsigned char* ptr(int y = 0) const { return data + (size_t)y * step; }
+};
+typedef const Mat& InputArray;
+typedef Mat& OutputArray;
+}  // namespace cv
+#endif
+
+namespace b200slam_detail {
+inline void check(int rc) { if (rc < 0) throw std::runtime_error(std::string("b200slam: ") + b200_last_error()); }
+static_assert(sizeof(b200_keypoint) == 28, "b200_keypoint must mirror cv::KeyPoint");
+}
+
+namespace ORB_SLAM2 {
+
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    // reference: ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device = 0)
+        : nfeatures_(nfeatures), scale_(scaleFactor), nlevels_(nlevels), ini_(iniThFAST), min_(minThFAST), device_(device), h_(nullptr), w_(0), ht_(0) {}
+    ~ORBextractor() { if (h_) b200_orb_destroy(h_); }
+    ORBextractor(const ORBextractor&) = delete;
+    ORBextractor& operator=(const ORBextractor&) = delete;
+
+    // Compute the ORB features and descriptors on an image; mask is ignored, exactly like the reference (ORBextractor.h:58)
+    void operator()(cv::InputArray image_, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors_) {
+#ifndef B200SLAM_NO_OPENCV
+        cv::Mat image = image_.getMat();
+#else
+        const cv::Mat& image = image_;
+#endif
+        if (image.empty()) return;                                    // ORBextractor.cc:1046
+        assert(image.type() == CV_8UC1);                              // ORBextractor.cc:1050
+        ensure(image.cols, image.rows);
+        const int cap = b200_orb_max_keypoints(h_);
+        kps_.resize(cap); desc_.resize((size_t)cap * 32);
+        int32_t n = 0;
+        b200slam_detail::check(b200_orb_extract_host(h_, image.data, 1, image.cols, image.rows, (int64_t)image.step, (int64_t)image.step * image.rows,
+                                                     kps_.data(), desc_.data(), &n));
+        keypoints.clear();
+        keypoints.resize(n);
+        static_assert(sizeof(cv::KeyPoint) == sizeof(b200_keypoint), "cv::KeyPoint layout");
+        if (n) std::memcpy((void*)keypoints.data(), kps_.data(), (size_t)n * sizeof(b200_keypoint));
+#ifndef B200SLAM_NO_OPENCV
+        if (n == 0) { descriptors_.release(); return; }
+        descriptors_.create(n, 32, CV_8U);
+        cv::Mat d = descriptors_.getMat();
+#else
+        cv::Mat& d = descriptors_;
+        if (n == 0) { d.release(); return; }
+        d.create(n, 32, CV_8U);
+#endif
+        for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), &desc_[(size_t)i * 32], 32);
+    }
+
+    int inline GetLevels() { return nlevels_; }
+    float inline GetScaleFactor() { return scale_; }
+    std::vector<float> inline GetScaleFactors() { return table(0); }
+    std::vector<float> inline GetInverseScaleFactors() { return table(1); }
+    std::vector<float> inline GetScaleSigmaSquares() { return table(2); }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return table(3); }
+
+    // reference public member mvImagePyramid (ORBextractor.h:85): filled on demand, level images incl. the 19-px border
+    std::vector<std::vector<unsigned char> > ImagePyramid(std::vector<int>* widths = nullptr, std::vector<int>* heights = nullptr) {
+        std::vector<std::vector<unsigned char> > out(nlevels_);
+        for (int l = 0; l < nlevels_; l++) {
+            out[l].resize((size_t)(w_ + 38) * (ht_ + 38));
+            int wl = 0, hl = 0;
+            b200slam_detail::check(b200_orb_get_pyramid(h_, 0, l, out[l].data(), &wl, &hl));
+            out[l].resize((size_t)(wl + 38) * (hl + 38));
+            if (widths) widths->push_back(wl);
+            if (heights) heights->push_back(hl);
+        }
+        return out;
+    }
+
+private:
+    void ensure(int w, int h) {
+        if (h_ && w <= w_ && h <= ht_) return;
+        if (h_) { b200_orb_destroy(h_); h_ = nullptr; }
+        w_ = w > w_ ? w : w_; ht_ = h > ht_ ? h : ht_;
+        b200slam_detail::check(b200_orb_create(&h_, nfeatures_, scale_, nlevels_, ini_, min_, w_, ht_, 1, device_));
+    }
+    std::vector<float> table(int which) {
+        ensure(w_ ? w_ : 64, ht_ ? ht_ : 64);
+        std::vector<float> t[4];
+        for (auto& v : t) v.resize(nlevels_);
+        b200slam_detail::check(b200_orb_get_level_info(h_, nullptr, t[0].data(), t[1].data(), t[2].data(), t[3].data(), nullptr));
+        return t[which];
+    }
+    int nfeatures_; float scale_; int nlevels_, ini_, min_, device_;
+    b200_orb_t h_; int w_, ht_;
+    std::vector<b200_keypoint> kps_; std::vector<uint8_t> desc_;
+};
+
+class ORBmatcher {
+public:
+    static const int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;      // ORBmatcher.cc:37-39
+
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0) : mfNNratio(nnratio), mbCheckOrientation(checkOri), device_(device) {}
+
+    // Computes the Hamming distance between two ORB descriptors (ORBmatcher.h:44)
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+        int32_t d = 0;
+        b200slam_detail::check(b200_hamming_matrix_host(a.ptr(0), 1, b.ptr(0), 1, &d, 0));
+        return d;
+    }
+
+    // Brute-force core of SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.h:55): every keyframe feature that
+    // owns a good MapPoint, all features in one vocabulary node.  matches[i] = keyframe index matched to frame keypoint i or -1
+    // (the caller maps indices back to MapPoint*); returns nmatches.
+    int SearchByBoW(const cv::Mat& kfDescriptors, const std::vector<cv::KeyPoint>& kfKeysUn,
+                    const cv::Mat& fDescriptors, const std::vector<cv::KeyPoint>& fKeys, std::vector<int>& matches) {
+        const int nkf = kfDescriptors.rows, nf = fDescriptors.rows;
+        std::vector<uint8_t> kd((size_t)nkf * 32), fd((size_t)nf * 32);
+        std::vector<float> ka(nkf), fa(nf);
+        for (int i = 0; i < nkf; i++) { std::memcpy(&kd[(size_t)i * 32], kfDescriptors.ptr(i), 32); ka[i] = kfKeysUn[i].angle; }
+        for (int i = 0; i < nf; i++) { std::memcpy(&fd[(size_t)i * 32], fDescriptors.ptr(i), 32); fa[i] = fKeys[i].angle; }
+        matches.assign(nf, -1);
+        int32_t n_frame = nf, nm = 0;
+        b200slam_detail::check(b200_match_bf_host(kd.data(), ka.data(), nkf, fd.data(), fa.data(), &n_frame, 1, nf, mfNNratio, TH_LOW,
+                                                  mbCheckOrientation ? 1 : 0, HISTO_LENGTH / 360.0f, matches.data(), &nm, device_));
+        return nm;
+    }
+
+    // best / second-best over explicit candidate lists: the distance core of SearchByProjection / SearchForInitialization
+    void MatchCandidates(const cv::Mat& queryDesc, const cv::Mat& trainDesc, const std::vector<int32_t>& candOfs, const std::vector<int32_t>& cand,
+                         std::vector<int32_t>& bestIdx, std::vector<int32_t>& bestDist, std::vector<int32_t>& secondDist) {
+        const int nq = queryDesc.rows, nt = trainDesc.rows;
+        std::vector<uint8_t> q((size_t)nq * 32), t((size_t)nt * 32);
+        for (int i = 0; i < nq; i++) std::memcpy(&q[(size_t)i * 32], queryDesc.ptr(i), 32);
+        for (int i = 0; i < nt; i++) std::memcpy(&t[(size_t)i * 32], trainDesc.ptr(i), 32);
+        bestIdx.resize(nq); bestDist.resize(nq); secondDist.resize(nq);
+        b200slam_detail::check(b200_match_candidates_host(q.data(), nq, t.data(), nt, candOfs.data(), cand.data(), bestIdx.data(), bestDist.data(),
+                                                          secondDist.data(), device_));
+    }
+
+protected:
+    float mfNNratio;
+    bool mbCheckOrientation;
+    int device_;
+};
+
+}  // namespace ORB_SLAM2
+
+namespace aruco {
+
+// aruco::Marker essentials (marker.h:47-59): std::vector<cv::Point2f> of 4 corners + id; ordered by id
+class Marker : public std::vector<cv::Point2f> {
+public:
+    int id;
+    float ssize;
+    Marker() : id(-1), ssize(-1) {}
+    bool operator<(const Marker& m) const { return id < m.id; }
+};
+
+class MarkerDetector {
+public:
+    enum DetectionMode { DM_NORMAL = 0, DM_FAST = 1, DM_VIDEO_FAST = 2 };
+    enum CornerRefinementMethod { CORNER_SUBPIX = 0, CORNER_LINES = 1, CORNER_NONE = 2 };
+
+    MarkerDetector() : dict_("ALL_DICTS"), h_(nullptr), w_(0), ht_(0), device_(0) {}
+    explicit MarkerDetector(const std::string& dict_name, int device = 0) : dict_(dict_name), h_(nullptr), w_(0), ht_(0), device_(device) {}
+    ~MarkerDetector() { if (h_) b200_aruco_destroy(h_); }
+    MarkerDetector(const MarkerDetector&) = delete;
+    MarkerDetector& operator=(const MarkerDetector&) = delete;
+
+    // markerdetector.h:337.  error_correction_rate must be 0 (the reference's setting, src/Frame.cc:133)
+    void setDictionary(const std::string& dict_type, float error_correction_rate = 0) {
+        if (error_correction_rate != 0) throw std::runtime_error("b200slam: only error_correction_rate = 0 is supported");
+        dict_ = dict_type;
+        if (h_) { b200_aruco_destroy(h_); h_ = nullptr; }
+    }
+    // markerdetector.h:258: only the mode the reference uses (src/Frame.cc:134)
+    void setDetectionMode(DetectionMode dm, float minMarkerSize = 0) {
+        if (dm != DM_NORMAL || minMarkerSize != 0) throw std::runtime_error("b200slam: only DM_NORMAL with minMarkerSize 0 is supported");
+    }
+    void setCornerRefinementMethod(CornerRefinementMethod m) {
+        if (m != CORNER_LINES) throw std::runtime_error("b200slam: only CORNER_LINES is supported");
+    }
+
+    // std::vector<aruco::Marker> detect(const cv::Mat& input) (markerdetector.h:276); markers sorted by id.
+    // Rvec/Tvec (IPPE pose) are not filled: the pose step stays on the host.
+    std::vector<Marker> detect(const cv::Mat& input) {
+        if (input.empty()) return std::vector<Marker>();
+        if (input.type() != CV_8UC1) throw std::runtime_error("b200slam: detect expects a CV_8UC1 image");
+        ensure(input.cols, input.rows);
+        const int cap = b200_aruco_max_markers(h_);
+        std::vector<b200_marker> m(cap);
+        int32_t n = 0;
+        b200slam_detail::check(b200_aruco_detect_host(h_, input.data, 1, input.cols, input.rows, (int64_t)input.step, (int64_t)input.step * input.rows, m.data(), &n));
+        std::vector<Marker> out(n);
+        for (int i = 0; i < n; i++) {
+            out[i].id = m[i].id;
+            for (int k = 0; k < 4; k++) out[i].push_back(cv::Point2f(m[i].xy[2 * k], m[i].xy[2 * k + 1]));
+        }
+        return out;
+    }
+
+private:
+    void ensure(int w, int h) {
+        if (h_ && w <= w_ && h <= ht_) return;
+        if (h_) { b200_aruco_destroy(h_); h_ = nullptr; }
+        w_ = w > w_ ? w : w_; ht_ = h > ht_ ? h : ht_;
+        b200slam_detail::check(b200_aruco_create(&h_, dict_.c_str(), w_, ht_, 1, device_));
+    }
+    std::string dict_;
+    b200_aruco_t h_; int w_, ht_, device_;
+};
+
+}  // namespace aruco

@@ -1,0 +1,42 @@
+// Drives the source-compatible C++ adapters (include/b200slam_adapters.hpp) the way Frame::Frame / Tracking use the
+// reference classes: extractor operator(), detector detect(), matcher SearchByBoW.  Reads a raw gray frame, writes a
+// flat binary result that tests/test_adapters_gpu.py compares with the oracle.
+#define B200SLAM_NO_OPENCV
+#include "b200slam_adapters.hpp"
+#include <cstdio>
+#include <cstdlib>
+
+int main(int argc, char** argv) {
+    if (argc < 6) { fprintf(stderr, "usage: %s in.raw w h dict out.bin\n", argv[0]); return 2; }
+    const int w = atoi(argv[2]), h = atoi(argv[3]);
+    std::vector<unsigned char> px((size_t)w * h);
+    FILE* f = fopen(argv[1], "rb");
+    if (!f || fread(px.data(), 1, px.size(), f) != px.size()) { fprintf(stderr, "cannot read frame\n"); return 2; }
+    fclose(f);
+    try {
+        cv::Mat im(h, w, CV_8UC1, px.data());
+        ORB_SLAM2::ORBextractor extractor(1000, 1.2f, 8, 20, 7);          // as in Tracking.cc:124
+        std::vector<cv::KeyPoint> keys;
+        cv::Mat desc;
+        extractor(im, cv::Mat(), keys, desc);                             // Frame.cc:203
+        aruco::MarkerDetector detector;
+        detector.setDictionary(argv[4], 0.f);                             // Frame.cc:133
+        detector.setDetectionMode(aruco::MarkerDetector::DM_NORMAL);      // Frame.cc:134
+        detector.setCornerRefinementMethod(aruco::MarkerDetector::CORNER_LINES);
+        std::vector<aruco::Marker> markers = detector.detect(im);         // Frame.cc:142
+        ORB_SLAM2::ORBmatcher matcher(0.7f, true);                        // Tracking.cc:917
+        std::vector<int> matches;
+        const int nm = matcher.SearchByBoW(desc, keys, desc, keys, matches);
+        const int dist = ORB_SLAM2::ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, desc.ptr(0)), cv::Mat(1, 32, CV_8U, desc.ptr(1)));
+        FILE* o = fopen(argv[5], "wb");
+        int hdr[4] = {(int)keys.size(), (int)markers.size(), nm, dist};
+        fwrite(hdr, 4, 4, o);
+        fwrite(keys.data(), sizeof(cv::KeyPoint), keys.size(), o);
+        for (int i = 0; i < desc.rows; i++) fwrite(desc.ptr(i), 1, 32, o);
+        for (auto& m : markers) { fwrite(&m.id, 4, 1, o); for (auto& p : m) { fwrite(&p.x, 4, 1, o); fwrite(&p.y, 4, 1, o); } }
+        fwrite(matches.data(), 4, matches.size(), o);
+        fclose(o);
+        printf("levels=%d scale0=%g keys=%zu markers=%zu matches=%d\n", extractor.GetLevels(), extractor.GetScaleFactors()[1], keys.size(), markers.size(), nm);
+    } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 1; }
+    return 0;
+}

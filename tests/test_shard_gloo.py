@@ -1,0 +1,64 @@
+"""CPU, world_size 2 over gloo: the frame sharding + result collation used for N > 1 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from orb_slam2_aruco_b200 import shard
+
+
+def test_shard_ranges_cover_the_batch():
+    for n in (0, 1, 5, 256, 2048, 8191):
+        for world in (1, 2, 4, 8):
+            spans = [shard.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == shard.shard_sizes(n, world)
+
+
+def fake_slots(lo, hi, cap=6):
+    """deterministic per-frame result slots as a function of the global frame index"""
+    idx = torch.arange(lo, hi)
+    counts = (idx % cap + 1).to(torch.int32)
+    kps = (idx[:, None, None] * 1000 + torch.arange(cap)[None, :, None] * 10 + torch.arange(7)[None, None, :]).to(torch.float32)
+    desc = ((idx[:, None, None] + torch.arange(cap)[None, :, None] * 3 + torch.arange(32)[None, None, :]) % 256).to(torch.uint8)
+    return {"counts": counts, "kps": kps, "desc": desc}
+
+
+def _worker(rank, world, port, n_frames, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard.shard_range(n_frames, world, rank)
+    got = shard.collate(fake_slots(lo, hi), n_frames)
+    want = fake_slots(0, n_frames)
+    ok = all(torch.equal(got[k], want[k]) for k in want)
+    q.put((rank, ok, int(got["counts"].shape[0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [8, 5])
+def test_collate_world2_gloo(n_frames):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res) and all(r[2] == n_frames for r in res)
+
+
+def test_collate_single_process_is_identity():
+    x = fake_slots(0, 4)
+    y = shard.collate(x, 4)
+    assert all(torch.equal(x[k], y[k]) for k in x)
