@@ -12,10 +12,11 @@
 //   k_halfpyr     image pyramid by exact 1/2 (2x2 mean; odd sizes: fixed-point bilinear) (1300-1466)
 //                 fused with the 8-neighbour foreground mask of every pixel (the binary image itself is never stored)
 //   k_probe_a/b   cv::findContours RETR_LIST/CHAIN_APPROX_NONE (3108) without a raster scan: every 0->1 / 1->0
-//                 transition pixel first looks BACK along its border (Suzuki's successor rule, inverted, on the masks) to
-//                 the previous transition; only if that one comes later in raster order (a) it walks FORWARD until it is
-//                 back at itself (=> it is the border's raster-first transition, i.e. Suzuki's start; the border is
-//                 recorded with its length) or meets a transition the raster scan would have seen earlier (=> abort) (b)
+//                 transition pixel is listed (a); persistent warps whose lanes fetch the next transition as soon as they
+//                 are free (b) first look BACK along the border (Suzuki's successor rule, inverted, on the masks) to the
+//                 previous transition and, only if that one comes later in raster order, walk FORWARD until they are back
+//                 at themselves (=> the border's raster-first transition, i.e. Suzuki's start; the border is recorded
+//                 with its length) or meet a transition the raster scan would have seen earlier (=> abort)
 //   k_emit        borders longer than 70 points are followed once more and written as point lists
 //   k_quads       warp per border: cv::approxPolyDP(eps = 0.05*len, closed) + isContourConvex (3253-3292)
 //   k_prefilter   CTA per frame: candidate order = reverse discovery order, corner orientation, too-near pairs,
@@ -195,120 +196,137 @@ __device__ __forceinline__ int dir_delta(int d, int pitch) {
     return dy * pitch + dx;
 }
 
-// Phase A (thread per pixel): is this 0->1 (West is 0) or 1->0 (East is 0) transition possibly the raster-first transition of
-// its border?  Walk BACKWARDS along the border to the previous transition: if the raster scan sees that one earlier, no.
-// (This kills the long walks of every non-topmost pixel of a left edge.)  Survivors are compacted for phase B.
-__device__ int probe_candidate(const uint8_t* __restrict__ mask, const ArucoGeom& g, int P, int m0, bool hole, int* __restrict__ err) {
-    // Suzuki's first neighbour search: clockwise from NW (outer) / SE (hole) over 7 directions = highest set bit of the
-    // mask rotated so that the first direction examined sits at bit 7 (the 8th direction, W resp. E, is known to be 0)
-    const int from = hole ? 7 : 3;
-    const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;      // bit j <-> direction from+1+j
-    if (rot == 0) return -1;                           // isolated pixel: a one-point contour, never a marker
-    const int s0 = (from + 1 + (31 - __clz(rot))) & 7;
-    const int mykey = P + (hole ? 1 : 0);
-    {   // own step: a hole probe whose sweep also passes West belongs to the outer probe of the same pixel
-        const Step st = next_step(m0, s0);
-        if (step_key(P, s0, st.k) < mykey) return -1;
-    }
-    int p = P, s = s0, n = 0;
-    const int limit = 4 * g.max_points;
-    for (;;) {
-        const int q = p + dir_delta(s, g.bpitch), d = (s + 4) & 7;
-        int sq, kq;
-        prev_step(mask[q], d, sq, kq);
-        p = q; s = sq;
-        if (p == P && s == s0) break;                  // went all the way round: the only transition of the border
-        const int key = step_key(p, s, kq);
-        if (key < mykey) return -1;
-        if (key != 0x7fffffff) break;                  // a later transition: undecided, phase B walks forwards
-        if (++n > limit) { atomicExch(err, 3); return -1; }
-    }
-    return s0;
-}
-
+// Phase A (thread per pixel): list every transition pixel -- foreground with a zero West neighbour (0->1, possible outer-border
+// start) or a zero East neighbour (1->0, possible hole-border start).  CTA-aggregated append, one global atomic per CTA.
 __global__ void __launch_bounds__(256)
-k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, int2* __restrict__ surv, int* __restrict__ nsurv,
-          int max_surv, int* __restrict__ err) {
+k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, int* __restrict__ cand, int* __restrict__ ncand,
+          int max_cand, int* __restrict__ err) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    const uint8_t* mask = mask0 + (long long)f * g.bframe;
     const int P = (y + 1) * g.bpitch + x + 1;
-    int so = -1, sh = -1;
-    if (x < g.w && y < g.h) {
-        const int m = mask[P];
-        if (m != 0) {
-            if (!(m & 16)) so = probe_candidate(mask, g, P, m, false, err);
-            if (!(m & 1)) sh = probe_candidate(mask, g, P, m, true, err);
-        }
-    }
-    // CTA-aggregated append of the survivors: shared-memory slots, ONE global atomic per CTA
+    int m = 0;
+    if (x < g.w && y < g.h) m = mask0[(long long)f * g.bframe + P];
+    const bool co = m != 0 && !(m & 16), ch = m != 0 && !(m & 1);
     __shared__ int s_n, s_base;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     if (tid == 0) s_n = 0;
     __syncthreads();
-    int slot_o = -1, slot_h = -1;
-    if (so >= 0) slot_o = atomicAdd(&s_n, 1);
-    if (sh >= 0) slot_h = atomicAdd(&s_n, 1);
+    const int k = (int)co + (int)ch;
+    int slot = 0;
+    if (k) slot = atomicAdd(&s_n, k);
     __syncthreads();
-    if (tid == 0 && s_n) s_base = atomicAdd(nsurv + f, s_n);
+    if (tid == 0 && s_n) s_base = atomicAdd(ncand + f, s_n);
     __syncthreads();
-    if (slot_o >= 0) {
-        const int idx = s_base + slot_o;
-        if (idx < max_surv) surv[(long long)f * max_surv + idx] = make_int2(P, so); else atomicExch(err, 8);
-    }
-    if (slot_h >= 0) {
-        const int idx = s_base + slot_h;
-        if (idx < max_surv) surv[(long long)f * max_surv + idx] = make_int2(P, sh | (1 << 8)); else atomicExch(err, 8);
+    if (k) {
+        int idx = s_base + slot;
+        int* out = cand + (long long)f * max_cand;
+        if (idx + k > max_cand) { atomicExch(err, 8); return; }
+        if (co) out[idx++] = P;
+        if (ch) out[idx] = P | (1 << 30);
     }
 }
 
-// Phase B (thread per survivor): walk FORWARDS until back home (=> first transition of this border: record it with its
-// length) or until a transition that the raster scan sees earlier shows up (=> abort).
+// Phase B (persistent warps, lanes fetch the next transition as soon as they are free, so no lane idles while its
+// neighbours walk long borders).  Per transition:
+//   1. BACKWARDS along the border to the previous transition: if the raster scan sees that one earlier, this cannot be the
+//      border's first transition (this removes every non-topmost pixel of a left edge after one step);
+//   2. FORWARDS until back home (=> it is Suzuki's start: the border is recorded with its length if > 70 points) or until a
+//      transition that the raster scan sees earlier shows up (=> abort).
 __global__ void __launch_bounds__(128)
-k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int2* __restrict__ surv, const int* __restrict__ nsurv,
-          int max_surv, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts, int* __restrict__ err) {
-    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= min(nsurv[f], max_surv)) return;
+k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ cand, const int* __restrict__ ncand,
+          int max_cand, int* __restrict__ nfetch, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts,
+          int* __restrict__ err) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int ns = min(ncand[f], max_cand);
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
-    const int2 sv = surv[(long long)f * max_surv + i];
-    const int P = sv.x, s0 = sv.y & 7;
-    const int mykey = P + (sv.y >> 8);
+    const int* list = cand + (long long)f * max_cand;
     const int limit = 4 * g.max_points;
-    int p = P, s = s0, n = 0;
+    int phase = 0, P = 0, s0 = 0, mykey = 0, p = 0, s = 0, n = 0;
+    bool exhausted = false;
     for (;;) {
-        const Step st = next_step(mask[p], s);
-        if (n > 0 && step_key(p, s, st.k) < mykey) return;
-        p += dir_delta(st.d, g.bpitch);
-        s = (st.d + 4) & 7;
-        n++;
-        if (p == P && s == s0) break;
-        if (n > limit) { atomicExch(err, 3); return; }
-    }
-    if (n > kMinContour) {
-        const int idx = atomicAdd(ncont + f, 1);
-        if (idx >= g.max_contours) { atomicExch(err, 4); return; }
-        const int off = atomicAdd(npts + f, n);
-        if (off + n > g.max_points) { atomicExch(err, 5); return; }
-        ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off;
-        desc[(long long)f * g.max_contours + idx] = c;
+        const bool need = phase == 0 && !exhausted;
+        const unsigned mneed = __ballot_sync(0xffffffffu, need);
+        if (mneed) {
+            const int leader = __ffs(mneed) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(nfetch + f, __popc(mneed));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                const int i = base + __popc(mneed & ((1u << lane) - 1));
+                if (i >= ns) exhausted = true;
+                else {
+                    const int e = list[i];
+                    const bool hole = (e >> 30) & 1;
+                    P = e & 0x3fffffff;
+                    const int m0 = mask[P];
+                    // Suzuki's first neighbour search: clockwise from NW (outer) / SE (hole) over 7 directions = highest set bit of
+                    // the mask rotated so that the first direction examined sits at bit 7 (W resp. E is known to be 0)
+                    const int from = hole ? 7 : 3;
+                    const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
+                    if (rot != 0) {                            // else: isolated pixel, a one-point contour
+                        s0 = (from + 1 + (31 - __clz(rot))) & 7;
+                        mykey = P + (hole ? 1 : 0);
+                        const Step st = next_step(m0, s0);
+                        // own step: a hole probe whose sweep also passes West belongs to the outer probe of the same pixel
+                        if (!(step_key(P, s0, st.k) < mykey)) { phase = 1; p = P; s = s0; n = 0; }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, phase != 0 || !exhausted)) break;
+        if (phase == 1) {
+            const int q = p + dir_delta(s, g.bpitch), d = (s + 4) & 7;
+            int sq, kq;
+            prev_step(mask[q], d, sq, kq);
+            p = q; s = sq;
+            if (p == P && s == s0) { phase = 2; n = 0; }                 // all the way round: the border's only transition
+            else {
+                const int key = step_key(p, s, kq);
+                if (key < mykey) phase = 0;
+                else if (key != 0x7fffffff) { phase = 2; p = P; s = s0; n = 0; }
+                else if (++n > limit) { atomicExch(err, 3); phase = 0; }
+            }
+        } else if (phase == 2) {
+            const Step st = next_step(mask[p], s);
+            if (n > 0 && step_key(p, s, st.k) < mykey) phase = 0;
+            else {
+                p += dir_delta(st.d, g.bpitch);
+                s = (st.d + 4) & 7;
+                n++;
+                if (p == P && s == s0) {
+                    phase = 0;
+                    if (n > kMinContour) {
+                        const int idx = atomicAdd(ncont + f, 1);
+                        if (idx >= g.max_contours) atomicExch(err, 4);
+                        else {
+                            const int off = atomicAdd(npts + f, n);
+                            if (off + n > g.max_points) atomicExch(err, 5);
+                            else { ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off; desc[(long long)f * g.max_contours + idx] = c; }
+                        }
+                    }
+                } else if (n > limit) { atomicExch(err, 3); phase = 0; }
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(128)
 k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ desc,
        const int* __restrict__ ncont, short2* __restrict__ pts) {
-    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= min(ncont[f], g.max_contours)) return;
-    const ContourDesc c = desc[(long long)f * g.max_contours + i];
+    const int f = blockIdx.y;
+    const int nc = min(ncont[f], g.max_contours);
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
-    short2* out = pts + (long long)f * g.max_points + c.off;
-    int p = c.start, s = c.s0;
-    int x = c.start % g.bpitch - 1, y = c.start / g.bpitch - 1;
-    for (int n = 0; n < c.len; n++) {
-        out[n] = make_short2((short)x, (short)y);
-        const Step st = next_step(mask[p], s);
-        const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
-        p += dy * g.bpitch + dx; x += dx; y += dy;
-        s = (st.d + 4) & 7;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+        const ContourDesc c = desc[(long long)f * g.max_contours + i];
+        short2* out = pts + (long long)f * g.max_points + c.off;
+        int p = c.start, s = c.s0;
+        int x = c.start % g.bpitch - 1, y = c.start / g.bpitch - 1;
+        for (int n = 0; n < c.len; n++) {
+            out[n] = make_short2((short)x, (short)y);
+            const Step st = next_step(mask[p], s);
+            const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
+            p += dy * g.bpitch + dx; x += dx; y += dy;
+            s = (st.d + 4) & 7;
+        }
     }
 }
 
@@ -336,8 +354,9 @@ k_quads(const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ des
     __shared__ int s_vx[kQuadWarps][kMaxVerts], s_vy[kQuadWarps][kMaxVerts];
     __shared__ int s_stack[kQuadWarps][2 * 64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.y, ci = blockIdx.x * kQuadWarps + warp;
-    if (ci >= min(ncont[f], g.max_contours)) return;
+    const int f = blockIdx.y;
+    const int ncontours = min(ncont[f], g.max_contours);
+    for (int ci = blockIdx.x * kQuadWarps + warp; ci < ncontours; ci += gridDim.x * kQuadWarps) {
     const ContourDesc c = desc[(long long)f * g.max_contours + ci];
     const short2* P = pts0 + (long long)f * g.max_points + c.off;
     const int count = c.len;
@@ -412,7 +431,7 @@ k_quads(const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ des
         __syncwarp();
     }
     __syncwarp();
-    if (overflow) return;              // far more than 4 vertices: not a marker candidate
+    if (overflow) continue;            // far more than 4 vertices: not a marker candidate
     // 4. clean-up pass (serial, a handful of vertices) and the quad / convexity test
     if (lane == 0) {
         const int cnt = nv;
@@ -461,6 +480,8 @@ k_quads(const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ des
             }
         }
     }
+    __syncwarp();
+    }   // contours of this warp
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -573,8 +594,10 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
     __shared__ int s_hist[256], s_nz[100], s_tot[100], s_level, s_lvl, s_found[4];
     __shared__ unsigned long long s_ids[4];
     __shared__ int s_ok;
-    const int f = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
-    if (k >= min(nkept[f], kMaxCand)) return;
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int nk = min(nkept[f], kMaxCand);
+    for (int k = blockIdx.x; k < nk; k += gridDim.x) {
+    __syncthreads();                                   // shared state of the previous candidate is dead
     const Kept kp = kept0[(long long)f * kMaxCand + k];
     const int ws = g.wsize;
     if (tid == 0) {
@@ -719,6 +742,7 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
         if (s_ok) for (int r = 0; r < 4; r++) if (s_found[r] != 0x7fffffff) { out.id = s_found[r]; out.nrot = r; break; }
         dec0[(long long)f * kMaxCand + k] = out;
     }
+    }   // candidates of this CTA
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1005,10 +1029,10 @@ struct b200_aruco_s {
     unsigned long long* d_codes;
     int cur_w, cur_h;
     ArucoGeom geom;
-    uint8_t *d_mask, *d_pyr; int2* d_surv; int max_surv;
+    uint8_t *d_mask, *d_pyr; int* d_surv; int max_surv;
     ContourDesc* d_desc; short2* d_pts; float* d_scratch;
     Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
-    int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_err;
+    int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_nfetch, *d_err;
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
@@ -1076,8 +1100,8 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     int rc;
     if ((rc = ensure_buf(h->d_mask, h->cap_mask, (size_t)g.bframe * B))) return rc;
     B200_CUDA(cudaMemset(h->d_mask, 0, (size_t)g.bframe * B));       // the 1-px zero frame is never written afterwards
-    h->max_surv = std::max(1024, w * hh / 2);          // salt-and-pepper noise: nearly every second pixel starts a tiny border
-    if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int2) * (size_t)h->max_surv * B))) return rc;
+    h->max_surv = std::max(1024, w * hh);              // transition list: at most two entries per foreground pixel
+    if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int) * (size_t)h->max_surv * B))) return rc;
     if ((rc = ensure_buf(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame * B))) return rc;
     if ((rc = ensure_buf(h->d_desc, h->cap_desc, sizeof(ContourDesc) * (size_t)g.max_contours * B))) return rc;
     if ((rc = ensure_buf(h->d_pts, h->cap_pts, sizeof(short2) * (size_t)g.max_points * B))) return rc;
@@ -1110,10 +1134,10 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     ok = ok && cudaMalloc((void**)&h->d_cand, sizeof(Candidate) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_kept, sizeof(Kept) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_dec, sizeof(Decoded) * kMaxCand * B) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&h->d_ncont, 5 * B * 4 + 4) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_ncont, 6 * B * 4 + 4) == cudaSuccess;
     if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
-    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_err = h->d_nsurv + B;
-    cudaMemset(h->d_ncont, 0, 5 * B * 4 + 4);
+    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_err = h->d_nfetch + B;
+    cudaMemset(h->d_ncont, 0, 6 * B * 4 + 4);
     if ((rc = aruco_geometry(h, max_w, max_h))) { b200_aruco_destroy(h); return rc; }
     *out = h;
     return B200_OK;
@@ -1150,7 +1174,7 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
     if (rs < w || (n > 1 && fs < rs * (hh - 1) + w)) return fail(B200_EINVAL, "bad %s", "strides");
     if ((rc = aruco_geometry(h, w, hh))) return rc;
     const ArucoGeom& g = h->geom;
-    B200_CUDA(cudaMemsetAsync(h->d_ncont, 0, 5 * (size_t)h->max_batch * 4, st));
+    B200_CUDA(cudaMemsetAsync(h->d_ncont, 0, 6 * (size_t)h->max_batch * 4, st));
     dim3 blk(32, 8);
     dim3 gt((w + kThrTile - 1) / kThrTile, (hh + kThrTile - 1) / kThrTile, n);
     B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, h->d_mask);
@@ -1163,19 +1187,19 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
     dim3 gm((w + 31) / 32, (hh + 7) / 8, n);
     B200_LAUNCH(k_probe_a, gm, blk, 0, st, h->d_mask, g, h->d_surv, h->d_nsurv, h->max_surv, h->d_err);
     {
-        dim3 gb((h->max_surv + 127) / 128, n);
-        B200_LAUNCH(k_probe_b, gb, 128, 0, st, h->d_mask, g, h->d_surv, h->d_nsurv, h->max_surv, h->d_desc, h->d_ncont, h->d_npts, h->d_err);
+        // enough persistent warps to fill the 148 SMs whatever the batch size
+        dim3 gb(std::max(4, std::min(64, (148 * 16 + n - 1) / n)), n);
+        B200_LAUNCH(k_probe_b, gb, 128, 0, st, h->d_mask, g, h->d_surv, h->d_nsurv, h->max_surv, h->d_nfetch, h->d_desc, h->d_ncont, h->d_npts, h->d_err);
     }
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
     {
-        const int grid_c = g.max_contours;
-        dim3 ge((grid_c + 127) / 128, n);
+        dim3 ge(4, n);
         B200_LAUNCH(k_emit, ge, 128, 0, st, h->d_mask, g, h->d_desc, h->d_ncont, h->d_pts);
-        dim3 gq((grid_c + kQuadWarps - 1) / kQuadWarps, n);
+        dim3 gq(48, n);
         B200_LAUNCH(k_quads, gq, kQuadWarps * 32, 0, st, g, h->d_desc, h->d_ncont, h->d_pts, h->d_cand, h->d_ncand, h->d_err);
     }
     B200_LAUNCH(k_prefilter, n, 256, 0, st, g, h->d_cand, h->d_ncand, h->d_kept, h->d_nkept);
-    dim3 gd(kMaxCand, n);
+    dim3 gd(40, n);
     B200_LAUNCH(k_decode, gd, 128, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_kept, h->d_nkept, h->d_codes, h->d_dec);
     B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, h->d_kept, h->d_nkept, h->d_dec, h->d_desc, h->d_pts, h->d_scratch,
                 markers, counts, kMaxMarkers, h->d_err);

@@ -140,7 +140,7 @@ __device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int v) {
 }
 
 constexpr int kFastThreads = 128;
-constexpr int kTP = kMaxRoi + 8;            // smem tile pitch
+constexpr int kTP = kMaxRoi + 8;            // smem tile pitch (bytes, multiple of 4)
 constexpr int kMaxInterior = kMaxRoi - 6;
 
 // One CTA per (cell, frame).  Like the reference, the cell is first examined at iniThFAST and only when that yields no
@@ -148,18 +148,18 @@ constexpr int kMaxInterior = kMaxRoi - 6;
 //   1. pretest every interior pixel: a 9-arc always contains two ADJACENT compass points (circle positions 0,4,8,12), so
 //      a corner needs two adjacent compass pixels both > v+T or both < v-T; survivors go to a shared-memory queue
 //   2. dense pass over the queue: full score (DPX min3/max3), stored in the score tile when >= T
-//   3. 3x3 NMS (strict >, neighbours outside the cell interior count 0) as a per-row bit mask + row counts
+//   3. 3x3 NMS (strict >, neighbours outside the cell interior count 0) of the queued pixels only -> per-row bit masks
 // then a raster-ordered compaction of the surviving pixels into the cell's candidate slots.
+// The ROI is staged with aligned 32-bit loads (the tile keeps the ROI's byte offset inside its first word).
 __global__ void __launch_bounds__(kFastThreads)
 k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
        const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g,
        const CellDesc* __restrict__ cells, uint32_t* __restrict__ slots, int* __restrict__ cellcnt) {
-    __shared__ uint8_t tile[kMaxRoi][kTP];
-    __shared__ uint8_t score[kMaxRoi][kTP];
+    __shared__ __align__(16) uint8_t tile[kMaxRoi][kTP];
+    __shared__ __align__(16) uint8_t score[kMaxRoi][kTP];
     __shared__ uint16_t queue[kMaxInterior * kMaxInterior];
-    __shared__ uint32_t keep[kMaxInterior][3];
-    __shared__ int row_ofs[kMaxInterior];
-    __shared__ int s_q, s_total;
+    __shared__ uint32_t keep[kMaxInterior * 3];
+    __shared__ int s_q, s_any;
 
     const CellDesc cd = cells[blockIdx.x];
     const int f = blockIdx.y;
@@ -173,11 +173,22 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
     const int rw = cd.rw, rh = cd.rh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kFastThreads / 32;
-    for (int y = warp; y < rh; y += NW)
-        for (int x = lane; x < rw; x += 32) {
-            tile[y][x] = base[(long long)y * pitch + x];
-            score[y][x] = 0;
+    // column offset of the ROI inside the tile: rows are fetched as aligned words when the row pitch allows it
+    int ox = 0;
+    if ((pitch & 3) == 0) {
+        ox = (int)(reinterpret_cast<uintptr_t>(base) & 3);
+        const int nwords = (ox + rw + 3) >> 2;
+        const uint8_t* b0 = base - ox;
+        for (int i = tid; i < rh * nwords; i += kFastThreads) {
+            const int y = i / nwords, wx = i - y * nwords;
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(b0 + (long long)y * pitch + 4 * wx);
+            *reinterpret_cast<uint32_t*>(&tile[y][4 * wx]) = v;
+            *reinterpret_cast<uint32_t*>(&score[y][4 * wx]) = 0u;
         }
+    } else {
+        for (int y = warp; y < rh; y += NW)
+            for (int x = lane; x < rw; x += 32) { tile[y][x] = base[(long long)y * pitch + x]; score[y][x] = 0; }
+    }
     if (tid == 0) s_q = 0;
     __syncthreads();
 
@@ -185,13 +196,15 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
     const int nchunk = (iw + 31) >> 5;
     int T = g.ini_th;
     for (int pass = 0; pass < 2; pass++) {
+        for (int i = tid; i < ih * 3; i += kFastThreads) keep[i] = 0u;
+        if (tid == 0) s_any = 0;
         // 1. pretest + enqueue
         for (int y = warp; y < ih; y += NW) {
             for (int c = 0; c < nchunk; c++) {
                 const int x = c * 32 + lane;
                 bool cand = false;
                 if (x < iw) {
-                    const uint8_t* p = &tile[y + 3][x + 3];
+                    const uint8_t* p = &tile[y + 3][ox + x + 3];
                     const int v = p[0], lo = v - T, hi = v + T;
                     const int c0 = p[3 * kTP], c4 = p[3], c8 = p[-3 * kTP], c12 = p[-3];
                     const bool b0 = c0 > hi, b4 = c4 > hi, b8 = c8 > hi, b12 = c12 > hi;
@@ -212,69 +225,53 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
         const int nq = s_q;
         for (int i = tid; i < nq; i += kFastThreads) {
             const int e = queue[i], y = e >> 8, x = e & 255;
-            const uint8_t* p = &tile[y + 3][x + 3];
+            const uint8_t* p = &tile[y + 3][ox + x + 3];
             const int sc = fast_score(p, kTP, p[0]);
-            if (sc >= T) score[y + 3][x + 3] = (uint8_t)sc;
+            if (sc >= T) score[y + 3][ox + x + 3] = (uint8_t)sc;
         }
         __syncthreads();
-        // 3. NMS -> per-row bit masks and counts
-        int cnt = 0;
-        for (int y = warp; y < ih; y += NW) {
-            int rc = 0;
-            for (int c = 0; c < nchunk; c++) {
-                const int x = c * 32 + lane;
-                bool k = false;
-                if (x < iw) {
-                    const uint8_t* q = &score[y + 3][x + 3];
-                    const int sc = q[0];
-                    if (sc)
-                        k = sc > q[-1] && sc > q[1] && sc > q[-kTP - 1] && sc > q[-kTP] && sc > q[-kTP + 1] && sc > q[kTP - 1] && sc > q[kTP] && sc > q[kTP + 1];
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, k);
-                if (lane == 0) keep[y][c] = m;
-                rc += __popc(m);
+        // 3. NMS of the queued pixels -> keep bits
+        for (int i = tid; i < nq; i += kFastThreads) {
+            const int e = queue[i], y = e >> 8, x = e & 255;
+            const uint8_t* q = &score[y + 3][ox + x + 3];
+            const int sc = q[0];
+            if (sc && sc > q[-1] && sc > q[1] && sc > q[-kTP - 1] && sc > q[-kTP] && sc > q[-kTP + 1] && sc > q[kTP - 1] && sc > q[kTP] && sc > q[kTP + 1]) {
+                atomicOr(&keep[y * 3 + (x >> 5)], 1u << (x & 31));
+                s_any = 1;
             }
-            if (lane == 0) row_ofs[y] = rc;
-            cnt += rc;
         }
-        if (tid == 0) s_total = 0;
         __syncthreads();
-        if (lane == 0 && cnt) atomicAdd(&s_total, cnt);
-        __syncthreads();
-        if (s_total > 0 || pass == 1 || g.min_th >= g.ini_th) break;
+        if (s_any || pass == 1 || g.min_th >= g.ini_th) break;
         // nothing at iniThFAST: the whole cell again at minThFAST (a superset of the pixels examined so far)
         T = g.min_th;
         if (tid == 0) s_q = 0;
         __syncthreads();
     }
-    // exclusive scan of the row counts (<= 66 rows), then ordered emission
+    // raster-ordered emission: keep words in (row, chunk) order; warp 0 scans their popcounts
     if (warp == 0) {
+        uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
+        const int nwords = ih * 3;
         int run = 0;
-        for (int y0 = 0; y0 < ih; y0 += 32) {
-            const int y = y0 + lane;
-            const int a = y < ih ? row_ofs[y] : 0;
-            int sa = a;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t m = wi < nwords ? keep[wi] : 0u;
+            const int c = __popc(m);
+            int sc = c;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sa, o); if (lane >= o) sa += t; }
-            if (y < ih) row_ofs[y] = run + sa - a;
-            run += __shfl_sync(0xffffffffu, sa, 31);
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+            int pos = run + sc - c;
+            const int y = wi / 3, ch = wi - y * 3;
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int x = ch * 32 + bit;
+                // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
+                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)score[y + 3][ox + x + 3] << 24);
+                pos++;
+            }
+            run += __shfl_sync(0xffffffffu, sc, 31);
         }
         if (lane == 0) cellcnt[(long long)f * g.total_cells + blockIdx.x] = run;
-    }
-    __syncthreads();
-    uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
-    for (int y = warp; y < ih; y += NW) {
-        int ofs = row_ofs[y];
-        for (int c = 0; c < nchunk; c++) {
-            const unsigned m = keep[y][c];
-            if (m & (1u << lane)) {
-                const int x = c * 32 + lane;
-                const int pos = ofs + __popc(m & ((1u << lane) - 1));
-                // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
-                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)score[y + 3][x + 3] << 24);
-            }
-            ofs += __popc(m);
-        }
     }
 }
 
