@@ -65,34 +65,35 @@ struct Decoded { int id, nrot; };
 // A1: adaptive threshold.  mean = rint(S/bs^2) (ties impossible for odd bs^2); out = src - mean <= -7.
 // One CTA -> 32x32 output tile; (32+2r)^2 replicate-clamped source patch in shared memory.
 // ------------------------------------------------------------------------------------------------
-constexpr int kThrTile = 32, kThrMaxR = 7, kThrB = kThrTile + 2;    // binary values are needed one pixel around the tile
+constexpr int kThrTW = 64, kThrTH = 32, kThrMaxR = 7;
+constexpr int kThrBW = kThrTW + 2, kThrBH = kThrTH + 2;             // binary values are needed one pixel around the tile
 
 __global__ void __launch_bounds__(256)
 k_athresh(const uint8_t* __restrict__ img, long long row_stride, long long frame_stride, const __grid_constant__ ArucoGeom g,
           uint8_t* __restrict__ mask) {
-    __shared__ uint8_t patch[kThrB + 2 * kThrMaxR][kThrB + 2 * kThrMaxR + 2];
-    __shared__ uint16_t hs[kThrB + 2 * kThrMaxR][kThrB];
-    __shared__ uint8_t bin[kThrB][kThrB + 2];
-    const int f = blockIdx.z, x0 = blockIdx.x * kThrTile - 1, y0 = blockIdx.y * kThrTile - 1;    // origin of the 34x34 binary block
-    const int bs = g.win, r = bs >> 1, side = kThrB + 2 * r;
+    __shared__ uint8_t patch[kThrBH + 2 * kThrMaxR][kThrBW + 2 * kThrMaxR + 2];
+    __shared__ uint16_t hs[kThrBH + 2 * kThrMaxR][kThrBW];
+    __shared__ uint8_t bin[kThrBH][kThrBW + 2];
+    const int f = blockIdx.z, x0 = blockIdx.x * kThrTW - 1, y0 = blockIdx.y * kThrTH - 1;    // origin of the 66x34 binary block
+    const int bs = g.win, r = bs >> 1, sw = kThrBW + 2 * r, sh = kThrBH + 2 * r;
     const uint8_t* src = img + (long long)f * frame_stride;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < side * side; i += 256) {
-        const int py = i / side, px = i - py * side;
+    for (int i = tid; i < sw * sh; i += 256) {
+        const int py = i / sw, px = i - py * sw;
         const int yy = min(max(y0 + py - r, 0), g.h - 1), xx = min(max(x0 + px - r, 0), g.w - 1);     // BORDER_REPLICATE
         patch[py][px] = src[(long long)yy * row_stride + xx];
     }
     __syncthreads();
-    for (int i = tid; i < side * kThrB; i += 256) {
-        const int py = i / kThrB, px = i - py * kThrB;
+    for (int i = tid; i < sh * kThrBW; i += 256) {
+        const int py = i / kThrBW, px = i - py * kThrBW;
         int s = 0;
         for (int k = 0; k < bs; k++) s += patch[py][px + k];
         hs[py][px] = (uint16_t)s;
     }
     __syncthreads();
     const double scale = 1.0 / ((double)bs * bs);
-    for (int i = tid; i < kThrB * kThrB; i += 256) {
-        const int by = i / kThrB, bx = i - by * kThrB;
+    for (int i = tid; i < kThrBH * kThrBW; i += 256) {
+        const int by = i / kThrBW, bx = i - by * kThrBW;
         const int x = x0 + bx, y = y0 + by;
         int v = 0;
         if (x >= 0 && x < g.w && y >= 0 && y < g.h) {
@@ -105,8 +106,9 @@ k_athresh(const uint8_t* __restrict__ img, long long row_stride, long long frame
     }
     __syncthreads();
     // 8-neighbour foreground mask (bit d = neighbour in direction d: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE); 0 for background
-    for (int ty = threadIdx.y; ty < kThrTile; ty += 8) {
-        const int bx = threadIdx.x + 1, by = ty + 1;
+    for (int i = tid; i < kThrTH * kThrTW; i += 256) {
+        const int ty = i / kThrTW, tx = i - ty * kThrTW;
+        const int bx = tx + 1, by = ty + 1;
         const int x = x0 + bx, y = y0 + by;
         if (x < g.w && y < g.h) {
             int m = 0;
@@ -1176,7 +1178,7 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
     const ArucoGeom& g = h->geom;
     B200_CUDA(cudaMemsetAsync(h->d_ncont, 0, 6 * (size_t)h->max_batch * 4, st));
     dim3 blk(32, 8);
-    dim3 gt((w + kThrTile - 1) / kThrTile, (hh + kThrTile - 1) / kThrTile, n);
+    dim3 gt((w + kThrTW - 1) / kThrTW, (hh + kThrTH - 1) / kThrTH, n);
     B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, h->d_mask);
     for (int l = 1; l < g.nlev; l++) {
         const uint8_t* src = l == 1 ? imgs : h->d_pyr + g.loff[l - 1];

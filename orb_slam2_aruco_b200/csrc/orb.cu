@@ -579,6 +579,7 @@ constexpr int kPatchR = 21;                  // 18 (max rotated pattern reach) +
 constexpr int kPatchW = 2 * kPatchR + 1;     // 43
 constexpr int kBlurW = 37;
 constexpr int kPatchPitch = 44;
+constexpr int kHPitch = 40;                  // u16 pitch of the horizontally filtered patch
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (p < 0) p = -p;
@@ -611,8 +612,8 @@ k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long
            const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g,
            const uint32_t* __restrict__ lvlres, const int* __restrict__ lvlcnt,
            b200_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ counts, int out_cap) {
-    __shared__ uint8_t s_patch[kDescWarps][kPatchW * kPatchPitch];
-    __shared__ uint16_t s_h[kDescWarps][kPatchW * kBlurW];
+    __shared__ __align__(16) uint8_t s_patch[kDescWarps][kPatchW * kPatchPitch + 12];     // rows of 11 words, patch column 0 word-aligned
+    __shared__ __align__(16) uint16_t s_h[kDescWarps][kPatchW * kHPitch];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
@@ -635,10 +636,30 @@ k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long
     else { im = pyr + (long long)f * g.pyr_frame_stride + lg.offset; pitch = lg.pitch; }
 
     uint8_t* P = s_patch[warp];
-    for (int idx = lane; idx < kPatchW * kPatchW; idx += 32) {
-        const int r = idx / kPatchW, c = idx - r * kPatchW;
-        const int yy = reflect101(cy + r - kPatchR, lg.h), xx = reflect101(cx + c - kPatchR, lg.w);
-        P[r * kPatchPitch + c] = im[(long long)yy * pitch + xx];
+    {
+        // 43x43 source patch, re-aligned so that patch column 0 sits on a word boundary.  Interior keypoints (the vast majority)
+        // fetch aligned 32-bit words and funnel-shift them; patches that touch the image border (or an unaligned pitch) go byte by
+        // byte through the REFLECT_101 index map.
+        const int x0 = cx - kPatchR, y0 = cy - kPatchR;
+        const uint8_t* A = im + (long long)y0 * pitch + x0;
+        const int ox = (int)(reinterpret_cast<uintptr_t>(A) & 3);
+        const bool fast = ((pitch & 3) == 0) && x0 >= 3 && y0 >= 0 && cy + kPatchR < lg.h && x0 + 47 < lg.w;
+        uint32_t* P32 = reinterpret_cast<uint32_t*>(P);
+        if (fast) {
+            const uint8_t* A0 = A - ox;
+            const int sh = 8 * ox;
+            for (int idx = lane; idx < kPatchW * 11; idx += 32) {
+                const int r = idx / 11, j = idx - r * 11;
+                const uint32_t* gw = reinterpret_cast<const uint32_t*>(A0 + (long long)r * pitch) + j;
+                P32[idx] = __funnelshift_r(gw[0], gw[1], sh);
+            }
+        } else {
+            for (int idx = lane; idx < kPatchW * kPatchW; idx += 32) {
+                const int r = idx / kPatchW, c = idx - r * kPatchW;
+                const int yy = reflect101(y0 + r, lg.h), xx = reflect101(x0 + c, lg.w);
+                P[r * kPatchPitch + c] = im[(long long)yy * pitch + xx];
+            }
+        }
     }
     __syncwarp();
 
@@ -658,18 +679,32 @@ k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // Gaussian: horizontal pass over 43 rows x 37 cols, vertical over 37 x 37
+    // Gaussian (exact integer arithmetic, so any evaluation order gives OpenCV's result): horizontal pass over 43 rows x 37
+    // cols with two dp4a per output (4 outputs per task from 3 aligned words), vertical pass over 37 x 37
     uint16_t* H = s_h[warp];
-    for (int idx = lane; idx < kPatchW * kBlurW; idx += 32) {
-        const int r = idx / kBlurW, c = idx - r * kBlurW;
-        const uint8_t* s = P + r * kPatchPitch + c;
-        H[idx] = (uint16_t)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    {
+        const uint32_t* P32 = reinterpret_cast<const uint32_t*>(P);
+        uint32_t* H32 = reinterpret_cast<uint32_t*>(H);
+        const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
+        for (int idx = lane; idx < kPatchW * 10; idx += 32) {
+            const int r = idx / 10, gq = idx - r * 10;
+            const uint32_t w0 = P32[r * 11 + gq], w1 = P32[r * 11 + gq + 1], w2 = P32[r * 11 + gq + 2];   // (+2 may run into the pad: unused lanes)
+            unsigned o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t a4 = __funnelshift_r(w0, w1, 8 * i), b4 = __funnelshift_r(w1, w2, 8 * i);
+                o[i] = __dp4a(a4, K0, __dp4a(b4, K1, 0u));
+            }
+            H32[(r * kHPitch + 4 * gq) >> 1] = o[0] | (o[1] << 16);
+            H32[((r * kHPitch + 4 * gq) >> 1) + 1] = o[2] | (o[3] << 16);
+        }
     }
     __syncwarp();
     uint8_t* Bl = P;                     // the source patch is dead once H exists: reuse its storage
     for (int idx = lane; idx < kBlurW * kBlurW; idx += 32) {
-        const uint16_t* s = H + idx;       // row r of the blurred patch uses H rows r..r+6
-        const unsigned vsum = 18u * (s[0] + s[6 * kBlurW]) + 34u * (s[kBlurW] + s[5 * kBlurW]) + 48u * (s[2 * kBlurW] + s[4 * kBlurW]) + 56u * s[3 * kBlurW];
+        const int r = idx / kBlurW, c = idx - r * kBlurW;
+        const uint16_t* s = H + r * kHPitch + c;       // row r of the blurred patch uses H rows r..r+6
+        const unsigned vsum = 18u * (s[0] + s[6 * kHPitch]) + 34u * (s[kHPitch] + s[5 * kHPitch]) + 48u * (s[2 * kHPitch] + s[4 * kHPitch]) + 56u * s[3 * kHPitch];
         Bl[idx] = (uint8_t)((vsum + 32768u) >> 16);
     }
     __syncwarp();
