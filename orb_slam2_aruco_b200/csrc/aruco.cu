@@ -587,19 +587,31 @@ __device__ bool lu_solve8(double* A, double* b) {           // OpenCV hal::LU wi
     return true;
 }
 
+constexpr int kDecodeWarps = 4;
+
 __global__ void __launch_bounds__(128)
 k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame_stride, const uint8_t* __restrict__ pyr,
          const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, const int* __restrict__ nkept,
          const unsigned long long* __restrict__ codes, Decoded* __restrict__ dec0) {
-    __shared__ double s_A[64], s_b[8], s_Mi[9];
-    __shared__ uint8_t s_patch[kMaxWarp * kMaxWarp];
-    __shared__ int s_hist[256], s_nz[100], s_tot[100], s_level, s_lvl, s_found[4];
-    __shared__ unsigned long long s_ids[4];
-    __shared__ int s_ok;
-    const int f = blockIdx.y, tid = threadIdx.x;
+    // one WARP per candidate (4 per CTA): the serial double-precision sections (8x8 LU, Otsu sweep) of different candidates
+    // overlap on the SM's four schedulers instead of idling 127 threads each
+    struct WarpState {
+        double A[64], b[8], Mi[9];
+        unsigned long long ids[4];
+        int hist[256], nz[100], tot[100], level, lvl, found[4], ok, lo, hi;
+        uint8_t patch[kMaxWarp * kMaxWarp + 4];
+    };
+    __shared__ WarpState s_ws[kDecodeWarps];
+    WarpState& S = s_ws[threadIdx.x >> 5];
+    double* s_A = S.A; double* s_b = S.b; double* s_Mi = S.Mi;
+    uint8_t* s_patch = S.patch; int* s_hist = S.hist; int* s_nz = S.nz; int* s_tot = S.tot; int* s_found = S.found;
+    unsigned long long* s_ids = S.ids;
+    int& s_level = S.level; int& s_lvl = S.lvl; int& s_ok = S.ok;
+    const int f = blockIdx.y, tid = threadIdx.x & 31;
+    constexpr int kStride = 32;
     const int nk = min(nkept[f], kMaxCand);
-    for (int k = blockIdx.x; k < nk; k += gridDim.x) {
-    __syncthreads();                                   // shared state of the previous candidate is dead
+    for (int k = blockIdx.x * kDecodeWarps + (threadIdx.x >> 5); k < nk; k += gridDim.x * kDecodeWarps) {
+    __syncwarp();                                      // shared state of the previous candidate is dead
     const Kept kp = kept0[(long long)f * kMaxCand + k];
     const int ws = g.wsize;
     if (tid == 0) {
@@ -645,15 +657,15 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
             s_Mi[6] = (M[3] * M[7] - M[4] * M[6]) * d; s_Mi[7] = (M[1] * M[6] - M[0] * M[7]) * d; s_Mi[8] = (M[0] * M[4] - M[1] * M[3]) * d;
         } else for (int i = 0; i < 9; i++) s_Mi[i] = 0;
     }
-    for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
-    if (tid < 100) { s_nz[tid] = 0; s_tot[tid] = 0; }
-    __syncthreads();
+    for (int i = tid; i < 256; i += kStride) s_hist[i] = 0;
+    for (int i = tid; i < 100; i += kStride) { s_nz[i] = 0; s_tot[i] = 0; }
+    __syncwarp();
     // warpPerspective INTER_LINEAR, BORDER_CONSTANT 0 (SURVEY A-8)
     const int lvl = s_lvl;
     const uint8_t* src; long long spitch; const int sw = g.lw[lvl], sh = g.lh[lvl];
     if (lvl == 0) { src = img0 + (long long)f * frame_stride; spitch = row_stride; }
     else { src = pyr + (long long)f * g.pyr_frame + g.loff[lvl]; spitch = g.lpitch[lvl]; }
-    for (int i = tid; i < ws * ws; i += blockDim.x) {
+    for (int i = tid; i < ws * ws; i += kStride) {
         const int y = i / ws, x = i - y * ws;
         const double X0 = s_Mi[0] * 0 + s_Mi[1] * y + s_Mi[2];
         const double Y0 = s_Mi[3] * 0 + s_Mi[4] * y + s_Mi[5];
@@ -677,13 +689,22 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
         s_patch[i] = (uint8_t)px;
         atomicAdd(&s_hist[px], 1);
     }
-    __syncthreads();
+    __syncwarp();
+    {   // occupied range of the histogram
+        int lo = 256, hi = -1;
+        for (int i = tid; i < 256; i += kStride) if (s_hist[i]) { lo = min(lo, i); hi = max(hi, i); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if (tid == 0) { S.lo = lo; S.hi = hi; }
+    }
+    __syncwarp();
     if (tid == 0) {       // Otsu (SURVEY A-9)
         double mu = 0; const double scale = 1. / ((double)ws * ws);
         for (int i = 0; i < 256; i++) mu += i * (double)s_hist[i];
         mu *= scale;
         double mu1 = 0, q1 = 0, max_sigma = 0; int max_val = 0;
-        for (int i = 0; i < 256; i++) {
+        // bins below the first / above the last occupied one cannot change the result (q1 = 0 resp. q2 < FLT_EPSILON => `continue`)
+        for (int i = S.lo; i <= S.hi; i++) {
             const double p_i = s_hist[i] * scale;
             mu1 *= q1;
             q1 += p_i;
@@ -696,16 +717,16 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
         }
         s_level = max_val;
     }
-    __syncthreads();
+    __syncwarp();
     const int nsub = g.nsub;
-    for (int i = tid; i < ws * ws; i += blockDim.x) {
+    for (int i = tid; i < ws * ws; i += kStride) {
         const int y = i / ws, x = i - y * ws;
         const int my = (int)__fdiv_rn(__fmul_rn((float)nsub, (float)y), (float)ws);
         const int mx = (int)__fdiv_rn(__fmul_rn((float)nsub, (float)x), (float)ws);
         if (s_patch[i] > s_level) atomicAdd(&s_nz[my * 10 + mx], 1);
         atomicAdd(&s_tot[my * 10 + mx], 1);
     }
-    __syncthreads();
+    __syncwarp();
     if (tid == 0) {
         const int nb = g.nb;
         unsigned char bits[10][10];
@@ -730,21 +751,21 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
         s_ok = ok;
         for (int r = 0; r < 4; r++) s_found[r] = 0x7fffffff;
     }
-    __syncthreads();
+    __syncwarp();
     Decoded out; out.id = -1; out.nrot = 0;
     if (s_ok) {
-        for (int i = tid; i < g.ncodes; i += blockDim.x) {
+        for (int i = tid; i < g.ncodes; i += kStride) {
             const unsigned long long c = codes[i];
 #pragma unroll
             for (int r = 0; r < 4; r++) if (c == s_ids[r]) atomicMin(&s_found[r], i);      // first index wins for repeated codes
         }
     }
-    __syncthreads();
+    __syncwarp();
     if (tid == 0) {
         if (s_ok) for (int r = 0; r < 4; r++) if (s_found[r] != 0x7fffffff) { out.id = s_found[r]; out.nrot = r; break; }
         dec0[(long long)f * kMaxCand + k] = out;
     }
-    }   // candidates of this CTA
+    }   // candidates of this warp
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1201,7 +1222,7 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
         B200_LAUNCH(k_quads, gq, kQuadWarps * 32, 0, st, g, h->d_desc, h->d_ncont, h->d_pts, h->d_cand, h->d_ncand, h->d_err);
     }
     B200_LAUNCH(k_prefilter, n, 256, 0, st, g, h->d_cand, h->d_ncand, h->d_kept, h->d_nkept);
-    dim3 gd(40, n);
+    dim3 gd(16, n);
     B200_LAUNCH(k_decode, gd, 128, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_kept, h->d_nkept, h->d_codes, h->d_dec);
     B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, h->d_kept, h->d_nkept, h->d_dec, h->d_desc, h->d_pts, h->d_scratch,
                 markers, counts, kMaxMarkers, h->d_err);

@@ -361,26 +361,33 @@ __device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint3
             dst[ofs + __popc(mm & ((1u << lane) - 1))] = key;
         }
     } else {
-        for (int i0 = nd.beg; i0 < nd.end; i0 += 32) {           // pass 1: counts
-            const int i = i0 + lane;
-            const bool valid = i < nd.end;
-            const uint32_t key = valid ? src[i] : 0u;
-            const int q = valid ? (((int)(key & 0xfff) >= mx) + 2 * ((int)((key >> 12) & 0xfff) >= my)) : 4;
+        // both passes fetch 4 x 32 keys per round trip (the keys live in global scratch: latency, not bandwidth, is the cost)
+        for (int i0 = nd.beg; i0 < nd.end; i0 += 128) {          // pass 1: counts
+            uint32_t key[4]; bool valid[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) cnt[k] += __popc(__ballot_sync(0xffffffffu, q == k));
+            for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u + lane; valid[u] = i < nd.end; key[u] = valid[u] ? src[i] : 0u; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int q = valid[u] ? (((int)(key[u] & 0xfff) >= mx) + 2 * ((int)((key[u] >> 12) & 0xfff) >= my)) : 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++) cnt[k] += __popc(__ballot_sync(0xffffffffu, q == k));
+            }
         }
         int run[4];
         run[0] = nd.beg; run[1] = run[0] + cnt[0]; run[2] = run[1] + cnt[1]; run[3] = run[2] + cnt[2];
-        for (int i0 = nd.beg; i0 < nd.end; i0 += 32) {           // pass 2: stable scatter
-            const int i = i0 + lane;
-            const bool valid = i < nd.end;
-            const uint32_t key = valid ? src[i] : 0u;
-            const int q = valid ? (((int)(key & 0xfff) >= mx) + 2 * ((int)((key >> 12) & 0xfff) >= my)) : 4;
+        for (int i0 = nd.beg; i0 < nd.end; i0 += 128) {          // pass 2: stable scatter
+            uint32_t key[4]; bool valid[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                unsigned m = __ballot_sync(0xffffffffu, q == k);
-                if (q == k) dst[run[k] + __popc(m & ((1u << lane) - 1))] = key;
-                run[k] += __popc(m);
+            for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u + lane; valid[u] = i < nd.end; key[u] = valid[u] ? src[i] : 0u; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int q = valid[u] ? (((int)(key[u] & 0xfff) >= mx) + 2 * ((int)((key[u] >> 12) & 0xfff) >= my)) : 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned m = __ballot_sync(0xffffffffu, q == k);
+                    if (q == k) dst[run[k] + __popc(m & ((1u << lane) - 1))] = key[u];
+                    run[k] += __popc(m);
+                }
             }
         }
     }
@@ -462,6 +469,28 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
         int run = 0;
         for (int ni = 0; ni < nini; ni++) {
             const int beg = run;
+            if (nini == 1) {
+                // one initial node (4:3 frames): all keys in cell order.  32 cells per round: every lane owns one cell (count and slot
+                // fetched in one round trip), a warp scan places the cells, then each lane copies its cell's few keys.
+                for (int c0 = 0; c0 < lg.ncells; c0 += 32) {
+                    const int c = c0 + lane;
+                    int n = 0, slot = 0;
+                    if (c < lg.ncells) { n = min(cc[c], cl[c].cap); slot = cl[c].slot; }
+                    int incl = n;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    const uint32_t* src = S + slot;
+                    uint32_t* dstp = A + run + incl - n;
+                    for (int k0 = 0; k0 < n; k0 += 4) {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) v[u] = k0 + u < n ? src[k0 + u] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) if (k0 + u < n) dstp[k0 + u] = v[u];
+                    }
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            } else
             for (int c = 0; c < lg.ncells; c++) {
                 const int n = min(cc[c], cl[c].cap);
                 const uint32_t* src = S + cl[c].slot;
