@@ -155,7 +155,7 @@ def run_reference(args, wl):
         ncores = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    sample = min(wl["batch"], max(32, 2 * ncores))          # bounded sample of the workload per step
+    sample = wl["batch"]                                   # one step = the whole batch (about a second on 16 host threads)
     imgs = frames_for(wl, 0)[:sample]
     ref_set = cpu_ref_set(wl) if wl["match"] else None
     for _ in range(args.warmup):

@@ -1177,16 +1177,19 @@ int b200_aruco_destroy(b200_aruco_t h) {
     return B200_OK;
 }
 
+int b200_aruco_batch_capacity(b200_aruco_t h) { return h ? h->max_batch : 0; }
+
 int b200_aruco_max_markers(b200_aruco_t h) {
     if (!h) return fail(B200_EINVAL, "null %s", "handle");
     return kMaxMarkers;
 }
 
-int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
-                      b200_marker* markers, int32_t* counts, void* stream) {
+// `base`: first scratch frame slot (calls that may overlap on different streams use disjoint slot ranges of the handle)
+int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                            b200_marker* markers, int32_t* counts, int base, void* stream) {
     if (!h) return fail(B200_EINVAL, "null %s", "handle");
     if (n < 0 || w < 0 || hh < 0) return fail(B200_EINVAL, "negative %s", "size");
-    if (n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
+    if (base < 0 || base + n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
     if (n == 0) return B200_OK;
     if (!markers || !counts) return fail(B200_EINVAL, "null %s", "output pointer");
     int rc = use_device(h->device);
@@ -1197,37 +1200,54 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
     if (rs < w || (n > 1 && fs < rs * (hh - 1) + w)) return fail(B200_EINVAL, "bad %s", "strides");
     if ((rc = aruco_geometry(h, w, hh))) return rc;
     const ArucoGeom& g = h->geom;
-    B200_CUDA(cudaMemsetAsync(h->d_ncont, 0, 6 * (size_t)h->max_batch * 4, st));
+    // the six per-frame counter arrays are one [6][max_batch] block: clear this call's columns
+    B200_CUDA(cudaMemset2DAsync(h->d_ncont + base, (size_t)h->max_batch * 4, 0, (size_t)n * 4, 6, st));
+    uint8_t* d_mask = h->d_mask + (size_t)base * g.bframe;
+    uint8_t* d_pyr = h->d_pyr + (size_t)base * g.pyr_frame;
+    int* d_surv = h->d_surv + (size_t)base * h->max_surv;
+    ContourDesc* d_desc = h->d_desc + (size_t)base * g.max_contours;
+    short2* d_pts = h->d_pts + (size_t)base * g.max_points;
+    float* d_scratch = h->d_scratch + 3 * (size_t)base * g.max_points;
+    Candidate* d_cand = h->d_cand + (size_t)base * kMaxCand;
+    Kept* d_kept = h->d_kept + (size_t)base * kMaxCand;
+    Decoded* d_dec = h->d_dec + (size_t)base * kMaxCand;
+    int *d_ncont = h->d_ncont + base, *d_npts = h->d_npts + base, *d_ncand = h->d_ncand + base, *d_nkept = h->d_nkept + base,
+        *d_nsurv = h->d_nsurv + base, *d_nfetch = h->d_nfetch + base;
     dim3 blk(32, 8);
     dim3 gt((w + kThrTW - 1) / kThrTW, (hh + kThrTH - 1) / kThrTH, n);
-    B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, h->d_mask);
+    B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, d_mask);
     for (int l = 1; l < g.nlev; l++) {
-        const uint8_t* src = l == 1 ? imgs : h->d_pyr + g.loff[l - 1];
+        const uint8_t* src = l == 1 ? imgs : d_pyr + g.loff[l - 1];
         const long long srs = l == 1 ? rs : g.lpitch[l - 1], sfs = l == 1 ? fs : g.pyr_frame;
         dim3 gp((g.lw[l] + 31) / 32, (g.lh[l] + 7) / 8, n);
-        B200_LAUNCH(k_halfpyr, gp, blk, 0, st, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], h->d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
+        B200_LAUNCH(k_halfpyr, gp, blk, 0, st, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
     }
     dim3 gm((w + 31) / 32, (hh + 7) / 8, n);
-    B200_LAUNCH(k_probe_a, gm, blk, 0, st, h->d_mask, g, h->d_surv, h->d_nsurv, h->max_surv, h->d_err);
+    B200_LAUNCH(k_probe_a, gm, blk, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, h->d_err);
     {
         // enough persistent warps to fill the 148 SMs whatever the batch size
         dim3 gb(std::max(4, std::min(64, (148 * 16 + n - 1) / n)), n);
-        B200_LAUNCH(k_probe_b, gb, 128, 0, st, h->d_mask, g, h->d_surv, h->d_nsurv, h->max_surv, h->d_nfetch, h->d_desc, h->d_ncont, h->d_npts, h->d_err);
+        B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
     }
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
     {
         dim3 ge(4, n);
-        B200_LAUNCH(k_emit, ge, 128, 0, st, h->d_mask, g, h->d_desc, h->d_ncont, h->d_pts);
+        B200_LAUNCH(k_emit, ge, 128, 0, st, d_mask, g, d_desc, d_ncont, d_pts);
         dim3 gq(48, n);
-        B200_LAUNCH(k_quads, gq, kQuadWarps * 32, 0, st, g, h->d_desc, h->d_ncont, h->d_pts, h->d_cand, h->d_ncand, h->d_err);
+        B200_LAUNCH(k_quads, gq, kQuadWarps * 32, 0, st, g, d_desc, d_ncont, d_pts, d_cand, d_ncand, h->d_err);
     }
-    B200_LAUNCH(k_prefilter, n, 256, 0, st, g, h->d_cand, h->d_ncand, h->d_kept, h->d_nkept);
+    B200_LAUNCH(k_prefilter, n, 256, 0, st, g, d_cand, d_ncand, d_kept, d_nkept);
     dim3 gd(16, n);
-    B200_LAUNCH(k_decode, gd, 128, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_kept, h->d_nkept, h->d_codes, h->d_dec);
-    B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, h->d_kept, h->d_nkept, h->d_dec, h->d_desc, h->d_pts, h->d_scratch,
+    B200_LAUNCH(k_decode, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec);
+    B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, d_kept, d_nkept, d_dec, d_desc, d_pts, d_scratch,
                 markers, counts, kMaxMarkers, h->d_err);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
+}
+
+int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                      b200_marker* markers, int32_t* counts, void* stream) {
+    return b200_aruco_detect_range(h, imgs, n, w, hh, rs, fs, markers, counts, 0, stream);
 }
 
 // Blocks until the handle's work on `stream` (NULL = own stream) is done and reports scratch overflows of the

@@ -45,3 +45,15 @@ int host_round(float v);
 int host_round_d(double v);
 
 }  // namespace b200
+
+// library-internal entry points (not part of include/b200slam.h): the scratch-slot aware forms used by b200_frontend_host,
+// whose chunks run on alternating stream sets
+extern "C" {
+int b200_aruco_batch_capacity(b200_aruco_t h);
+int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,
+                            b200_marker* markers, int32_t* counts, int base, void* stream);
+int b200_match_bf_kp_range(const uint8_t* ref_desc, const b200_keypoint* ref_kps, int n_ref,
+                           const uint8_t* frame_desc, const b200_keypoint* frame_kps, const int32_t* n_frame, int n_batch, int frame_cap,
+                           float ratio, int th_low, int check_ori, float histo_factor,
+                           int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream, int base, int total);
+}

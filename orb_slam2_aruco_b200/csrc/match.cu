@@ -93,12 +93,12 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
                 const int* __restrict__ n_frame, int frame_cap, const uint32_t* __restrict__ topk,
                 float ratio, int th_low, int check_ori, float histo_factor,
                 int* __restrict__ match_ref_idx, int* __restrict__ n_matches, int stage_topk) {
-    extern __shared__ unsigned int s_mem[];
+    extern __shared__ __align__(16) unsigned int s_mem[];
     const int f = blockIdx.x, lane = threadIdx.x;
     const int nf = min(n_frame[f], frame_cap);
     unsigned int* taken = s_mem;                               // bitmap over frame keypoints
     const int words = (frame_cap + 31) / 32;
-    unsigned char* bin_of = reinterpret_cast<unsigned char*>(s_mem + words);   // rotation bin of each matched frame keypoint
+    unsigned char* bin_of = reinterpret_cast<unsigned char*>(s_mem + ((words + 3) & ~3));    // 16-byte aligned sections   // rotation bin of each matched frame keypoint
     __shared__ int histo[kHistoLen];
     for (int i = lane; i < words; i += 32) taken[i] = 0;
     if (lane < kHistoLen) histo[lane] = 0;
@@ -110,9 +110,18 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
     // this frame's top-K lists: staged in shared memory when they fit (the loop below is a serial dependency chain)
     const uint32_t* tk_base = topk + (long long)f * n_ref * kTopK;
     if (stage_topk) {
-        uint32_t* s_tk = reinterpret_cast<uint32_t*>(bin_of + ((frame_cap + 15) & ~15));
-        for (int i = lane; i < n_ref * kTopK; i += 32) s_tk[i] = tk_base[i];
-        tk_base = s_tk;
+        // (uint4 copies: the lists are 16-byte records; the angles of both sides follow so that a commit never waits on HBM)
+        uint4* s_tk = reinterpret_cast<uint4*>(bin_of + ((frame_cap + 15) & ~15));
+        const uint4* g_tk = reinterpret_cast<const uint4*>(tk_base);
+        for (int i = lane; i < n_ref; i += 32) s_tk[i] = g_tk[i];
+        tk_base = reinterpret_cast<const uint32_t*>(s_tk);
+        if (check_ori) {
+            float* s_ra = reinterpret_cast<float*>(s_tk + n_ref);
+            float* s_fa = s_ra + n_ref;
+            for (int i = lane; i < n_ref; i += 32) s_ra[i] = ref_angle[(long long)i * ref_astride];
+            for (int i = lane; i < nf; i += 32) s_fa[i] = fa[(long long)i * frame_astride];
+            ref_angle = s_ra; ref_astride = 1; fa = s_fa; frame_astride = 1;
+        }
         __syncwarp();
     }
     // The reference loop is serial in r, but the only state it carries is the "taken" set, which changes on accepted
@@ -257,7 +266,9 @@ extern "C" {
 static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int ref_astride, int n_ref,
                          const uint8_t* frame_desc, const float* frame_angle, int frame_astride, const int32_t* n_frame, int n_batch, int frame_cap,
                          float ratio, int th_low, int check_ori, float histo_factor,
-                         int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream) {
+                         int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream, int base = 0, int total = 0) {
+    // base / total: this call uses the scratch slots [base, base + n_batch) of a scratch sized for `total` frames, so that calls on
+    // different streams (the chunks of b200_frontend_host) do not share top-K lists
     if (n_batch < 0 || n_ref < 0 || frame_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
     if (frame_cap > 65535) return fail(B200_ECAPACITY, "frame_cap above %s", "65535");
     int rc = use_device(device);
@@ -267,13 +278,14 @@ static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int re
         return fail(B200_EINVAL, "null %s", "pointer");
     if (((uintptr_t)ref_desc | (uintptr_t)frame_desc) & 31) return fail(B200_EINVAL, "descriptor arrays must be %s", "32-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t need = std::max<size_t>((size_t)n_batch * std::max(n_ref, 1) * kTopK * 4, 16);
+    const size_t need = std::max<size_t>((size_t)std::max(total, base + n_batch) * std::max(n_ref, 1) * kTopK * 4, 16);
     if (g_ms.device != device || g_ms.cap < need) {
         if (g_ms.topk) cudaFree(g_ms.topk);
         g_ms.topk = nullptr; g_ms.cap = 0;
         B200_CUDA(cudaMalloc((void**)&g_ms.topk, need));
         g_ms.cap = need; g_ms.device = device;
     }
+    uint32_t* topk = g_ms.topk + (size_t)base * std::max(n_ref, 1) * kTopK;
     const int nf_pad = (frame_cap + 31) & ~31;
     if (n_ref > 0 && frame_cap > 0) {
         const size_t smem = (size_t)4 * nf_pad * 8;
@@ -281,15 +293,15 @@ static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int re
         B200_CUDA(cudaFuncSetAttribute(k_match_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((n_ref + kRefPerCta - 1) / kRefPerCta, n_batch);
         B200_LAUNCH(k_match_topk, grid, kMatchWarps * 32, smem, st, (const ulonglong4*)ref_desc, n_ref, (const ulonglong4*)frame_desc,
-                    n_frame, frame_cap, g_ms.topk);
+                    n_frame, frame_cap, topk);
     }
-    size_t smem2 = (size_t)((frame_cap + 31) / 32) * 4 + (size_t)((frame_cap + 15) & ~15) + 16;
-    const size_t tk_bytes = (size_t)n_ref * kTopK * 4;
+    size_t smem2 = (size_t)((((frame_cap + 31) / 32) + 3) & ~3) * 4 + (size_t)((frame_cap + 15) & ~15) + 16;
+    const size_t tk_bytes = (size_t)n_ref * kTopK * 4 + ((size_t)n_ref + frame_cap) * 4;     // top-K lists + both angle arrays
     const int stage_topk = smem2 + tk_bytes <= 160 * 1024;
     if (stage_topk) smem2 += tk_bytes;
     B200_CUDA(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem2, 1024)));
     B200_LAUNCH(k_match_resolve, n_batch, 32, smem2, st, (const ulonglong4*)ref_desc, ref_angle, ref_astride, n_ref, (const ulonglong4*)frame_desc,
-                frame_angle, frame_astride, n_frame, frame_cap, g_ms.topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, stage_topk);
+                frame_angle, frame_astride, n_frame, frame_cap, topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, stage_topk);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -310,6 +322,15 @@ int b200_match_bf_kp(const uint8_t* ref_desc, const b200_keypoint* ref_kps, int 
     const int st = (int)(sizeof(b200_keypoint) / sizeof(float));
     return match_bf_impl(ref_desc, ref_kps ? &ref_kps->angle : nullptr, st, n_ref, frame_desc, frame_kps ? &frame_kps->angle : nullptr, st,
                          n_frame, n_batch, frame_cap, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, device, stream);
+}
+
+int b200_match_bf_kp_range(const uint8_t* ref_desc, const b200_keypoint* ref_kps, int n_ref,
+                           const uint8_t* frame_desc, const b200_keypoint* frame_kps, const int32_t* n_frame, int n_batch, int frame_cap,
+                           float ratio, int th_low, int check_ori, float histo_factor,
+                           int32_t* match_ref_idx, int32_t* n_matches, int device, void* stream, int base, int total) {
+    const int st = (int)(sizeof(b200_keypoint) / sizeof(float));
+    return match_bf_impl(ref_desc, ref_kps ? &ref_kps->angle : nullptr, st, n_ref, frame_desc, frame_kps ? &frame_kps->angle : nullptr, st,
+                         n_frame, n_batch, frame_cap, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, device, stream, base, total);
 }
 
 namespace {

@@ -23,6 +23,7 @@ constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;          // EDGE_THRESHOLD, ORBextractor.cc:73
 constexpr int kMinBorder = 16;     // EDGE_THRESHOLD-3, ORBextractor.cc:771
 constexpr int kHalfPatch = 15;
+constexpr int kFrontendChunk = 128;  // frames per upload/compute/download pipeline stage of b200_frontend_host
 constexpr int kMaxRoi = 72;        // largest FAST cell ROI side handled (cells are 30..59 px + 6)
 
 struct LevelGeom {
@@ -807,8 +808,10 @@ struct b200_orb_s {
     // optional per-stage timing (b200_orb_set_profile): events around pyramid / fast / quadtree / describe
     int profile; cudaEvent_t ev[5]; float stage_ms[4]; int stage_valid;
     cudaStream_t copy_stream; cudaEvent_t ev_copy[2];
+    cudaStream_t down_stream; cudaEvent_t ev_done[2];
+    cudaStream_t stream2, aux_stream2; cudaEvent_t ev_aux2, ev_ref;       // second stream set: odd chunks of b200_frontend_host
     // last call (debug taps)
-    const uint8_t* last_imgs; long long last_row_stride, last_frame_stride; int last_n;
+    const uint8_t* last_imgs; long long last_row_stride, last_frame_stride; int last_n, last_base;
 };
 
 namespace {
@@ -961,22 +964,30 @@ int upload_constants() {
 }
 
 int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long rs, long long fs,
-            b200_keypoint* kps, uint8_t* desc, int32_t* counts, int out_cap, cudaStream_t st) {
+            b200_keypoint* kps, uint8_t* desc, int32_t* counts, int out_cap, cudaStream_t st, int base = 0) {
+    // `base`: first scratch frame slot used by this call (calls that may run concurrently on different streams use disjoint slots)
     const OrbGeom& g = h->geom;
+    uint8_t* d_pyr = h->d_pyr + (size_t)base * g.pyr_frame_stride;
+    uint32_t* d_slots = h->d_slots + (size_t)base * g.slots_per_frame;
+    uint32_t* d_keysA = h->d_keysA + (size_t)base * g.slots_per_frame;
+    uint32_t* d_keysB = h->d_keysB + (size_t)base * g.slots_per_frame;
+    int* d_cellcnt = h->d_cellcnt + (size_t)base * g.total_cells;
+    uint32_t* d_lvlres = h->d_lvlres + (size_t)base * g.res_per_frame;
+    int* d_lvlcnt = h->d_lvlcnt + (size_t)base * g.nlevels;
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[0], st));
     for (int l = 1; l < g.nlevels; l++) {
         const LevelGeom& L = g.L[l];
         const LevelGeom& Lp = g.L[l - 1];
-        const uint8_t* src = l == 1 ? imgs : h->d_pyr + Lp.offset;
+        const uint8_t* src = l == 1 ? imgs : d_pyr + Lp.offset;
         const long long srs = l == 1 ? rs : Lp.pitch, sfs = l == 1 ? fs : g.pyr_frame_stride;
         dim3 grid((L.w + 127) / 128, (L.h + 7) / 8, n), block(32, 8);
-        B200_LAUNCH(k_pyramid, grid, block, 0, st, src, srs, sfs, h->d_pyr + L.offset, L.pitch, g.pyr_frame_stride,
+        B200_LAUNCH(k_pyramid, grid, block, 0, st, src, srs, sfs, d_pyr + L.offset, L.pitch, g.pyr_frame_stride,
                     Lp.w, Lp.h, L.w, L.h, h->d_tab + L.xtab, h->d_tab + L.ytab);
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[1], st));
     if (g.total_cells > 0) {
         dim3 grid(g.total_cells, n);
-        B200_LAUNCH(k_fast, grid, kFastThreads, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_cells, h->d_slots, h->d_cellcnt);
+        B200_LAUNCH(k_fast, grid, kFastThreads, 0, st, imgs, rs, fs, d_pyr, g, h->d_cells, d_slots, d_cellcnt);
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[2], st));
     {
@@ -985,17 +996,17 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
         const size_t smem = per_warp * kQtWarps;
         static std::atomic<size_t> qt_smem_set(0);
         if (smem > qt_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); qt_smem_set.store(smem); }
-        B200_LAUNCH(k_quadtree, (nprob + kQtWarps - 1) / kQtWarps, kQtWarps * 32, smem, st, g, h->d_cells, h->d_slots, h->d_cellcnt,
-                    h->d_keysA, h->d_keysB, h->d_lvlres, h->d_lvlcnt, n, h->pool_cap, h->d_err);
+        B200_LAUNCH(k_quadtree, (nprob + kQtWarps - 1) / kQtWarps, kQtWarps * 32, smem, st, g, h->d_cells, d_slots, d_cellcnt,
+                    d_keysA, d_keysB, d_lvlres, d_lvlcnt, n, h->pool_cap, h->d_err);
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[3], st));
     {
         dim3 grid((g.res_per_frame + kDescWarps - 1) / kDescWarps, n);
-        B200_LAUNCH(k_describe, grid, kDescWarps * 32, 0, st, imgs, rs, fs, h->d_pyr, g, h->d_lvlres, h->d_lvlcnt, kps, desc, counts, out_cap);
+        B200_LAUNCH(k_describe, grid, kDescWarps * 32, 0, st, imgs, rs, fs, d_pyr, g, d_lvlres, d_lvlcnt, kps, desc, counts, out_cap);
     }
     if (h->profile) { B200_CUDA(cudaEventRecord(h->ev[4], st)); h->stage_valid = 1; }
     B200_CUDA(cudaGetLastError());
-    h->last_imgs = imgs; h->last_row_stride = rs; h->last_frame_stride = fs; h->last_n = n;
+    h->last_imgs = imgs; h->last_row_stride = rs; h->last_frame_stride = fs; h->last_n = n; h->last_base = base;
     (void)w; (void)hh;
     return B200_OK;
 }
@@ -1033,6 +1044,10 @@ int b200_orb_create(b200_orb_t* out, int nfeatures, float scale_factor, int nlev
     for (int i = 0; i < 5; i++) cudaEventCreate(&h->ev[i]);
     cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&h->aux_stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_aux2, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_ref, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_done[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_done[1], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming);
     if ((rc = upload_constants()) || (rc = set_geometry(h, max_w, max_h))) { b200_orb_destroy(h); return rc; }
@@ -1051,6 +1066,12 @@ int b200_orb_destroy(b200_orb_t h) {
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; i++) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->down_stream) cudaStreamDestroy(h->down_stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->aux_stream2) cudaStreamDestroy(h->aux_stream2);
+    if (h->ev_aux2) cudaEventDestroy(h->ev_aux2);
+    if (h->ev_ref) cudaEventDestroy(h->ev_ref);
+    for (int i = 0; i < 2; i++) if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     cudaFree(h->d_markers); cudaFree(h->d_mcounts); cudaFree(h->d_match); cudaFree(h->d_nmatch); cudaFree(h->d_refdesc); cudaFree(h->d_refkps);
@@ -1164,12 +1185,37 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
         B200_CUDA(cudaMallocHost((void**)&h->h_out, out_bytes));
         h->cap_hout = out_bytes;
     }
-    cudaStream_t st = h->stream, cs = h->copy_stream, as = h->aux_stream;
+    if ((rc = set_geometry(h, w, hh))) return rc;
+    if (h->geom.res_per_frame > cap) return fail(B200_ECAPACITY, "aspect ratio beyond %s", "4.5:1");
+    cudaStream_t cs = h->copy_stream;
+    cudaStream_t sts[2] = {h->stream, h->stream2}, ass[2] = {h->aux_stream, h->aux_stream2};
+    cudaEvent_t ev_auxs[2] = {h->ev_aux, h->ev_aux2};
     if (do_match) {
-        B200_CUDA(cudaMemcpyAsync(h->d_refdesc, ref_desc, (size_t)n_ref * 32, cudaMemcpyHostToDevice, st));
-        B200_CUDA(cudaMemcpyAsync(h->d_refkps, ref_kps, (size_t)n_ref * sizeof(b200_keypoint), cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(h->d_refdesc, ref_desc, (size_t)n_ref * 32, cudaMemcpyHostToDevice, sts[0]));
+        B200_CUDA(cudaMemcpyAsync(h->d_refkps, ref_kps, (size_t)n_ref * sizeof(b200_keypoint), cudaMemcpyHostToDevice, sts[0]));
+        B200_CUDA(cudaEventRecord(h->ev_ref, sts[0]));
+        B200_CUDA(cudaStreamWaitEvent(sts[1], h->ev_ref, 0));
     }
-    const int chunk = n <= 16 ? n : 32;
+    // host staging layout (pageable outputs): the seven result arrays back to back
+    const size_t o_kps = 0, o_desc = o_kps + kp_bytes, o_cnt = o_desc + de_bytes, o_mk = o_cnt + ct_bytes, o_mc = o_mk + mk_bytes,
+                 o_ma = o_mc + ct_bytes, o_nm = o_ma + ma_bytes;
+    uint8_t* stage_out = h->h_out;
+    cudaStream_t ds = h->down_stream;
+    auto down = [&](void* user, size_t stage_ofs, const void* dev, size_t first_byte, size_t bytes) -> int {
+        if (!bytes) return B200_OK;
+        void* dst = out_pinned ? (void*)((uint8_t*)user + first_byte) : (void*)(stage_out + stage_ofs + first_byte);
+        B200_CUDA(cudaMemcpyAsync(dst, (const uint8_t*)dev + first_byte, bytes, cudaMemcpyDeviceToHost, ds));
+        return B200_OK;
+    };
+    static const int env_chunk = [] { const char* e = getenv("B200_FRONTEND_CHUNK"); return e ? atoi(e) : 0; }();
+    // chunk: frames per pipeline stage.  Small chunks multiply the latency-bound kernels (quadtree, contour walk, greedy resolve take
+    // as long for 32 frames as for 256), large ones expose the first upload: half the batch, at most kFrontendChunk
+    const int chunk = env_chunk > 0 ? env_chunk : (n <= 16 ? n : std::min(kFrontendChunk, std::max(32, (n + 1) / 2)));
+    // detector scratch slots: the whole batch when the handle is large enough, else two alternating chunk-sized regions, else one region
+    // (then every detector call is serialised on the first auxiliary stream)
+    const int acap = aruco ? b200_aruco_batch_capacity(aruco) : 0;
+    const int amode = !aruco ? 0 : acap >= n ? 2 : acap >= 2 * chunk ? 1 : 0;
+    if (aruco && acap < std::min(chunk, n)) return fail(B200_ECAPACITY, "detector handle smaller than one pipeline chunk (%s frames)", "128");
     int ci = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, ci++) {
         const int nf = std::min(chunk, n - f0);
@@ -1189,45 +1235,49 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
             }
             B200_CUDA(cudaMemcpyAsync(dst, stage, frame_bytes * nf, cudaMemcpyHostToDevice, cs));
         }
+        // even and odd chunks use different stream sets and disjoint scratch slots (base = f0): the latency-bound tail of one
+        // chunk (quadtree, contour following, greedy resolve) overlaps the dense kernels of the next
+        cudaStream_t st = sts[ci & 1], as = ass[amode ? (ci & 1) : 0];
+        const int abase = amode == 2 ? f0 : amode == 1 ? (ci & 1) * chunk : 0;
         cudaEvent_t ev = h->ev_copy[ci & 1];
         B200_CUDA(cudaEventRecord(ev, cs));
         B200_CUDA(cudaStreamWaitEvent(st, ev, 0));
         if (aruco) {
             B200_CUDA(cudaStreamWaitEvent(as, ev, 0));
-            if ((rc = b200_aruco_detect(aruco, dst, nf, w, hh, w, (int64_t)frame_bytes, h->d_markers + (size_t)f0 * mcap, h->d_mcounts + f0, as))) return rc;
+            if ((rc = b200_aruco_detect_range(aruco, dst, nf, w, hh, w, (int64_t)frame_bytes, h->d_markers + (size_t)f0 * mcap, h->d_mcounts + f0, abase, as))) return rc;
+            B200_CUDA(cudaEventRecord(ev_auxs[ci & 1], as));
+            B200_CUDA(cudaStreamWaitEvent(ds, ev_auxs[ci & 1], 0));
         }
-        if ((rc = b200_orb_extract(h, dst, nf, w, hh, w, (int64_t)frame_bytes, h->d_kps + (size_t)f0 * cap, h->d_desc + (size_t)f0 * cap * 32,
-                                   h->d_counts + f0, st)))
+        if ((rc = enqueue(h, dst, nf, w, hh, w, (long long)frame_bytes, h->d_kps + (size_t)f0 * cap, h->d_desc + (size_t)f0 * cap * 32,
+                          h->d_counts + f0, cap, st, f0)))
             return rc;
         if (do_match &&
-            (rc = b200_match_bf_kp(h->d_refdesc, h->d_refkps, n_ref, h->d_desc + (size_t)f0 * cap * 32, h->d_kps + (size_t)f0 * cap, h->d_counts + f0, nf, cap,
-                                   ratio, 50, check_ori, 30.0f / 360.0f, h->d_match + (size_t)f0 * cap, h->d_nmatch + f0, h->device, st)))
+            (rc = b200_match_bf_kp_range(h->d_refdesc, h->d_refkps, n_ref, h->d_desc + (size_t)f0 * cap * 32, h->d_kps + (size_t)f0 * cap, h->d_counts + f0, nf, cap,
+                                         ratio, 50, check_ori, 30.0f / 360.0f, h->d_match + (size_t)f0 * cap, h->d_nmatch + f0, h->device, st, f0, n)))
             return rc;
+        // this chunk's result slots go home on the download stream while the next chunk is being processed
+        B200_CUDA(cudaEventRecord(h->ev_done[ci & 1], st));
+        B200_CUDA(cudaStreamWaitEvent(ds, h->ev_done[ci & 1], 0));
+        if ((rc = down(kps, o_kps, h->d_kps, (size_t)f0 * cap * sizeof(b200_keypoint), (size_t)nf * cap * sizeof(b200_keypoint))) ||
+            (rc = down(desc, o_desc, h->d_desc, (size_t)f0 * cap * 32, (size_t)nf * cap * 32)) ||
+            (rc = down(counts, o_cnt, h->d_counts, (size_t)f0 * 4, (size_t)nf * 4))) return rc;
+        if (aruco && ((rc = down(markers, o_mk, h->d_markers, (size_t)f0 * mcap * sizeof(b200_marker), (size_t)nf * mcap * sizeof(b200_marker))) ||
+                      (rc = down(marker_counts, o_mc, h->d_mcounts, (size_t)f0 * 4, (size_t)nf * 4)))) return rc;
+        if (do_match && ((rc = down(match_ref_idx, o_ma, h->d_match, (size_t)f0 * cap * 4, (size_t)nf * cap * 4)) ||
+                         (rc = down(n_matches, o_nm, h->d_nmatch, (size_t)f0 * 4, (size_t)nf * 4)))) return rc;
     }
     // (the debug taps b200_orb_get_pyramid / _get_candidates now refer to the LAST chunk)
-    if (aruco) { B200_CUDA(cudaEventRecord(h->ev_aux, as)); B200_CUDA(cudaStreamWaitEvent(st, h->ev_aux, 0)); }
-    uint8_t* stage = h->h_out;
-    size_t o = 0;
-    auto down = [&](void* user, const void* dev, size_t bytes) -> int {
-        if (!bytes) return B200_OK;
-        B200_CUDA(cudaMemcpyAsync(out_pinned ? user : (void*)(stage + o), dev, bytes, cudaMemcpyDeviceToHost, st));
-        o += bytes;
-        return B200_OK;
-    };
-    if ((rc = down(kps, h->d_kps, kp_bytes)) || (rc = down(desc, h->d_desc, de_bytes)) || (rc = down(counts, h->d_counts, ct_bytes))) return rc;
-    if (aruco && ((rc = down(markers, h->d_markers, mk_bytes)) || (rc = down(marker_counts, h->d_mcounts, ct_bytes)))) return rc;
-    if (do_match && ((rc = down(match_ref_idx, h->d_match, ma_bytes)) || (rc = down(n_matches, h->d_nmatch, ct_bytes)))) return rc;
+    // the download stream has waited for every chunk of both stream sets: the error flags are final when it drains
     int err = 0;
-    B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, ds));
+    B200_CUDA(cudaStreamSynchronize(ds));
     if (err) { cudaMemset(h->d_err, 0, 4); return fail(B200_ECAPACITY, "quadtree scratch overflow (%s)", err == 1 ? "node pool" : "result slots"); }
-    if (aruco && (rc = b200_aruco_check(aruco, as))) return rc;
+    if (aruco && (rc = b200_aruco_check(aruco, ds))) return rc;
     if (!out_pinned) {
-        o = 0;
-        auto back = [&](void* user, size_t bytes) { if (bytes) memcpy(user, stage + o, bytes); o += bytes; };
-        back(kps, kp_bytes); back(desc, de_bytes); back(counts, ct_bytes);
-        if (aruco) { back(markers, mk_bytes); back(marker_counts, ct_bytes); }
-        if (do_match) { back(match_ref_idx, ma_bytes); back(n_matches, ct_bytes); }
+        auto back = [&](void* user, size_t ofs, size_t bytes) { if (bytes) memcpy(user, stage_out + ofs, bytes); };
+        back(kps, o_kps, kp_bytes); back(desc, o_desc, de_bytes); back(counts, o_cnt, ct_bytes);
+        if (aruco) { back(markers, o_mk, mk_bytes); back(marker_counts, o_mc, ct_bytes); }
+        if (do_match) { back(match_ref_idx, o_ma, ma_bytes); back(n_matches, o_nm, ct_bytes); }
     }
     return B200_OK;
 }
@@ -1262,7 +1312,7 @@ int b200_orb_get_pyramid(b200_orb_t h, int frame, int level, uint8_t* out, int* 
     if (level == 0)
         B200_CUDA(cudaMemcpy2D(img.data(), L.w, h->last_imgs + (size_t)frame * h->last_frame_stride, h->last_row_stride, L.w, L.h, cudaMemcpyDeviceToHost));
     else
-        B200_CUDA(cudaMemcpy2D(img.data(), L.w, h->d_pyr + (size_t)frame * h->geom.pyr_frame_stride + L.offset, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+        B200_CUDA(cudaMemcpy2D(img.data(), L.w, h->d_pyr + (size_t)(h->last_base + frame) * h->geom.pyr_frame_stride + L.offset, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
     // the 19-px REFLECT_101 frame of mvImagePyramid (ORBextractor.cc:1113-1128) is never read on the mono path;
     // it is synthesised here on demand instead of being stored in HBM
     const int W = L.w + 2 * kEdge;
@@ -1285,7 +1335,7 @@ int b200_orb_get_candidates(b200_orb_t h, int frame, int level, int32_t* xys, in
     const LevelGeom& L = g.L[level];
     B200_CUDA(cudaStreamSynchronize(h->stream));
     std::vector<int> cnt(std::max(L.ncells, 1));
-    if (L.ncells) B200_CUDA(cudaMemcpy(cnt.data(), h->d_cellcnt + (size_t)frame * g.total_cells + L.cell_base, (size_t)L.ncells * 4, cudaMemcpyDeviceToHost));
+    if (L.ncells) B200_CUDA(cudaMemcpy(cnt.data(), h->d_cellcnt + (size_t)(h->last_base + frame) * g.total_cells + L.cell_base, (size_t)L.ncells * 4, cudaMemcpyDeviceToHost));
     int n = 0;
     std::vector<uint32_t> buf;
     for (int c = 0; c < L.ncells; c++) {
@@ -1293,7 +1343,7 @@ int b200_orb_get_candidates(b200_orb_t h, int frame, int level, int32_t* xys, in
         const int k = std::min(cnt[c], cd.cap);
         if (!k) continue;
         buf.resize(k);
-        B200_CUDA(cudaMemcpy(buf.data(), h->d_slots + (size_t)frame * g.slots_per_frame + cd.slot, (size_t)k * 4, cudaMemcpyDeviceToHost));
+        B200_CUDA(cudaMemcpy(buf.data(), h->d_slots + (size_t)(h->last_base + frame) * g.slots_per_frame + cd.slot, (size_t)k * 4, cudaMemcpyDeviceToHost));
         for (int i = 0; i < k; i++) {
             if (n >= cap) return fail(B200_ECAPACITY, "candidate buffer too %s", "small");
             xys[3 * n] = buf[i] & 0xfff; xys[3 * n + 1] = (buf[i] >> 12) & 0xfff; xys[3 * n + 2] = buf[i] >> 24;
