@@ -14,6 +14,7 @@
 //   k_describe                one warp per keypoint: IC_Angle, 7x7 Gaussian on a 43x43 patch, rBRIEF
 //                             (ORBextractor.cc:77-147,1085-1101)
 #include "common.h"
+#include <cuda.h>          // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through the runtime (no -lcuda)
 #include <math.h>
 #include <algorithm>
 
@@ -37,6 +38,7 @@ struct LevelGeom {
     int nini; float hx;       // DistributeOctTree initial nodes
     int kp_cap, kp_base;      // result capacity of this level, base inside the frame's level-result block
     int xtab, ytab;           // offsets into the resize tables
+    int box_w, box_h;         // TMA box of k_fast: (largest cell ROI of the level + 15 columns of alignment slack) rounded up to 16 x largest ROI height
     float scale;              // mvScaleFactor[l]
     float size;               // keypoint size = (int)(31*scale)
 };
@@ -100,162 +102,241 @@ k_pyramid(const uint8_t* __restrict__ src0, long long src_row_stride, long long 
 
 // ------------------------------------------------------------------------------------------------
 // K2: FAST-9/16 score, NMS, threshold fallback, ordered compaction.  One CTA per (cell, frame).
-// score(p) = max over the 16 arcs of 9 contiguous circle pixels of max(min d, -max d) - 1, d = I(p)-I(circle)
-// (the largest threshold for which p is still a corner; SURVEY A-3).  Packed s16x2 min3/max3 (DPX) evaluate
-// all 16 arcs with 2 x 22 instructions.
+// score(p) = max over the 16 arcs of 9 contiguous circle pixels of max(min d, -max d) - 1, d = I(circle) - I(p)
+// (the largest threshold for which p is still a corner; SURVEY A-3).
+//
+// The cell's ROI arrives in shared memory as ONE TMA box (cp.async.bulk.tensor.3d: x, y, frame; per-level tensor maps;
+// out-of-image bytes read as zero and are never used).  The box starts at the ROI's x rounded down to 16: a u8 tensor map
+// only accepts 16-byte aligned inner coordinates (anything else raises an illegal-instruction fault, tools/tma_probe.cu).  All arithmetic runs in packed s16x2 registers, the one SIMD width sm_100a executes natively (VIADD.16x2,
+// VIMNMX[3].S16x2; the u8x4 video instructions are emulated with 5-8 LOP3/IADD each).
+//
+// Per threshold T (iniThFAST, then minThFAST only when the cell has no keypoint after NMS, ORBextractor.cc:809-816):
+//   1. pretest, one thread per aligned 4-pixel group: the five words (centre, N, S and the two row neighbours) are split
+//      into even / odd pixel pairs (PRMT).  A 9-arc always contains two ADJACENT compass points (circle positions 0,4,8,12),
+//      one of N/S and one of E/W, so a corner needs min(max(N,S), max(E,W)) > v+T or max(min(N,S), min(E,W)) < v-T:
+//      12 packed instructions per pixel pair.  Survivors go to the warp's private queue (no atomics, no CTA barrier)
+//   2. every thread scores TWO queued pixels at once, one per s16x2 half: 2 x 40 min3/max3 give all 16 arcs of both
+//      polarities; scores >= T are written to the byte score tile and the pixel goes to the warp's corner queue
+//   3. 3x3 NMS (strict >, neighbours outside the cell interior count 0) over the corner queues -> per-row bit masks
+// then a raster-ordered compaction of the surviving pixels into the cell's candidate slots.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int fast_score(const uint8_t* p, int pitch, int v) {
-    // circle in the order of SURVEY A-3: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-    int d[16];
-    d[0]  = v - p[ 3 * pitch + 0]; d[1]  = v - p[ 3 * pitch + 1]; d[2]  = v - p[ 2 * pitch + 2]; d[3]  = v - p[ 1 * pitch + 3];
-    d[4]  = v - p[ 0 * pitch + 3]; d[5]  = v - p[-1 * pitch + 3]; d[6]  = v - p[-2 * pitch + 2]; d[7]  = v - p[-3 * pitch + 1];
-    d[8]  = v - p[-3 * pitch + 0]; d[9]  = v - p[-3 * pitch - 1]; d[10] = v - p[-2 * pitch - 2]; d[11] = v - p[-1 * pitch - 3];
-    d[12] = v - p[ 0 * pitch - 3]; d[13] = v - p[ 1 * pitch - 3]; d[14] = v - p[ 2 * pitch - 2]; d[15] = v - p[ 3 * pitch - 1];
-    unsigned e[16];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        e[j] = ((unsigned)d[j] & 0xffffu) | ((unsigned)d[j + 8] << 16);      // lo = position j, hi = position j+8
-        e[j + 8] = __byte_perm(e[j], 0, 0x1032);                             // halves swapped
-    }
-    unsigned tmin[14], tmax[14];
-#pragma unroll
-    for (int j = 0; j < 14; j++) {
-        tmin[j] = __vimin3_s16x2(e[j], e[j + 1], e[j + 2]);
-        tmax[j] = __vimax3_s16x2(e[j], e[j + 1], e[j + 2]);
-    }
-    unsigned wmin[8], wmax[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        wmin[j] = __vimin3_s16x2(tmin[j], tmin[j + 3], tmin[j + 6]);       // min of d over positions j..j+8 (lo), j+8..j+16 (hi)
-        wmax[j] = __vimax3_s16x2(tmax[j], tmax[j + 3], tmax[j + 6]);
-    }
-    unsigned a = __vimax3_s16x2(wmin[0], wmin[1], wmin[2]);
-    unsigned b = __vimax3_s16x2(wmin[3], wmin[4], wmin[5]);
-    a = __vimax3_s16x2(a, b, __vmaxs2(wmin[6], wmin[7]));
-    unsigned c = __vimin3_s16x2(wmax[0], wmax[1], wmax[2]);
-    unsigned e2 = __vimin3_s16x2(wmax[3], wmax[4], wmax[5]);
-    c = __vimin3_s16x2(c, e2, __vmins2(wmax[6], wmax[7]));
-    int maxmin = max((int)(short)(a & 0xffff), (int)(short)(a >> 16));
-    int minmax = min((int)(short)(c & 0xffff), (int)(short)(c >> 16));
-    return max(maxmin, -minmax) - 1;
+constexpr int kFastThreads = 128;
+constexpr int kFastWarps = kFastThreads / 32;
+
+struct FastSmemGeom {                        // dynamic shared memory carve-up, sized by the host for the largest box in use
+    int tile_bytes;                          // max over levels of box_w * box_h, rounded up to 128
+    int qcap;                                // pixel-queue entries per warp
+    int keepw;                               // keep words
+};
+
+struct FastMaps { CUtensorMap m[kMaxLevels]; };     // level 0: the caller's frames; level l > 0: that level inside the pyramid buffer
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned pair_e(unsigned w) { return __byte_perm(w, 0, 0x4240); }      // pixels 0, 2 of a word as u16x2
+__device__ __forceinline__ unsigned pair_o(unsigned w) { return __byte_perm(w, 0, 0x4341); }      // pixels 1, 3
+__device__ __forceinline__ unsigned sh16(unsigned lo, unsigned hi) { return __byte_perm(lo, hi, 0x5432); }   // (lo.hi16, hi.lo16)
+
+// compass pretest of one pixel pair: non-zero halves are pixels that can still be a corner at threshold T
+__device__ __forceinline__ unsigned fast_pretest_pair(unsigned V, unsigned N, unsigned S, unsigned E, unsigned W, unsigned Tp, unsigned Tn) {
+    const unsigned a = __vmins2(__vmaxs2(N, S), __vmaxs2(E, W)), b = __vmaxs2(__vmins2(N, S), __vmins2(E, W));
+    const unsigned hi = __vadd2(V, Tp), lo = __vadd2(V, Tn);
+    return (a ^ __vmins2(a, hi)) | (b ^ __vmaxs2(b, lo));
 }
 
-constexpr int kFastThreads = 128;
-constexpr int kTP = kMaxRoi + 8;            // smem tile pitch (bytes, multiple of 4)
-constexpr int kMaxInterior = kMaxRoi - 6;
+// all 16 arcs of 9 for two pixels: d[j] = circle_j - centre (s16x2), returns max(maxmin, -minmax) - 1 per half
+__device__ __forceinline__ unsigned fast_score_pair(const unsigned (&d)[16]) {
+    unsigned t1[16], u1[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        t1[j] = __vimin3_s16x2(d[j], d[(j + 1) & 15], d[(j + 2) & 15]);
+        u1[j] = __vimax3_s16x2(d[j], d[(j + 1) & 15], d[(j + 2) & 15]);
+    }
+    unsigned t2[16], u2[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        t2[j] = __vimin3_s16x2(t1[j], t1[(j + 3) & 15], t1[(j + 6) & 15]);       // min of d over positions j..j+8
+        u2[j] = __vimax3_s16x2(u1[j], u1[(j + 3) & 15], u1[(j + 6) & 15]);
+    }
+    unsigned a = __vimax3_s16x2(t2[0], t2[1], t2[2]), b = __vimax3_s16x2(t2[3], t2[4], t2[5]), c = __vimax3_s16x2(t2[6], t2[7], t2[8]);
+    unsigned e = __vimax3_s16x2(t2[9], t2[10], t2[11]), f = __vimax3_s16x2(t2[12], t2[13], t2[14]);
+    a = __vimax3_s16x2(a, b, c); e = __vimax3_s16x2(e, f, t2[15]);
+    const unsigned maxmin = __vmaxs2(a, e);
+    a = __vimin3_s16x2(u2[0], u2[1], u2[2]); b = __vimin3_s16x2(u2[3], u2[4], u2[5]); c = __vimin3_s16x2(u2[6], u2[7], u2[8]);
+    e = __vimin3_s16x2(u2[9], u2[10], u2[11]); f = __vimin3_s16x2(u2[12], u2[13], u2[14]);
+    a = __vimin3_s16x2(a, b, c); e = __vimin3_s16x2(e, f, u2[15]);
+    const unsigned minmax = __vmins2(a, e);
+    return __vadd2(__vmaxs2(maxmin, __vneg2(minmax)), 0xffffffffu);
+}
 
-// One CTA per (cell, frame).  Like the reference, the cell is first examined at iniThFAST and only when that yields no
-// keypoint (after NMS) again at minThFAST (ORBextractor.cc:809-816).  Per threshold T:
-//   1. pretest every interior pixel: a 9-arc always contains two ADJACENT compass points (circle positions 0,4,8,12), so
-//      a corner needs two adjacent compass pixels both > v+T or both < v-T; survivors go to a shared-memory queue
-//   2. dense pass over the queue: full score (DPX min3/max3), stored in the score tile when >= T
-//   3. 3x3 NMS (strict >, neighbours outside the cell interior count 0) of the queued pixels only -> per-row bit masks
-// then a raster-ordered compaction of the surviving pixels into the cell's candidate slots.
-// The ROI is staged with aligned 32-bit loads (the tile keeps the ROI's byte offset inside its first word).
 __global__ void __launch_bounds__(kFastThreads)
 k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
-       const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g,
+       const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ FastMaps maps,
+       const FastSmemGeom sg, int tma_level0, int scratch_base,
        const CellDesc* __restrict__ cells, uint32_t* __restrict__ slots, int* __restrict__ cellcnt) {
-    __shared__ __align__(16) uint8_t tile[kMaxRoi][kTP];
-    __shared__ __align__(16) uint8_t score[kMaxRoi][kTP];
-    __shared__ uint16_t queue[kMaxInterior * kMaxInterior];
-    __shared__ uint32_t keep[kMaxInterior * 3];
-    __shared__ int s_q, s_any;
+    extern __shared__ __align__(1024) unsigned char fs_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_any;
+    __shared__ int s_nc[kFastWarps];
 
     const CellDesc cd = cells[blockIdx.x];
     const int f = blockIdx.y;
     const LevelGeom& lg = g.L[cd.level];
-    const uint8_t* base;
-    long long pitch;
-    if (cd.level == 0) { base = img0 + (long long)f * img_frame_stride; pitch = img_row_stride; }
-    else { base = pyr + (long long)f * g.pyr_frame_stride + lg.offset; pitch = lg.pitch; }
-    base += (long long)cd.y0 * pitch + cd.x0;
+    const int tp = lg.box_w;                                                            // tile pitch (bytes)
+    uint8_t* tile = fs_raw;                                                             // [box_h][tp], column = ox + ROI column
+    uint8_t* score = fs_raw + sg.tile_bytes;                                            // same geometry
+    uint16_t* q_all = reinterpret_cast<uint16_t*>(fs_raw + 2 * sg.tile_bytes);          // per-warp pixel queues: y << 8 | tile column
+    uint32_t* keep = reinterpret_cast<uint32_t*>(q_all + kFastWarps * sg.qcap);
 
     const int rw = cd.rw, rh = cd.rh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kFastThreads / 32;
-    // column offset of the ROI inside the tile: rows are fetched as aligned words when the row pitch allows it
-    int ox = 0;
-    if ((pitch & 3) == 0) {
-        ox = (int)(reinterpret_cast<uintptr_t>(base) & 3);
-        const int nwords = (ox + rw + 3) >> 2;
-        const uint8_t* b0 = base - ox;
-        for (int i = tid; i < rh * nwords; i += kFastThreads) {
-            const int y = i / nwords, wx = i - y * nwords;
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(b0 + (long long)y * pitch + 4 * wx);
-            *reinterpret_cast<uint32_t*>(&tile[y][4 * wx]) = v;
-            *reinterpret_cast<uint32_t*>(&score[y][4 * wx]) = 0u;
+    const bool use_tma = cd.level > 0 || tma_level0;
+    const int ox = cd.x0 & 15;                        // level rows start 16-byte aligned, so this is the ROI's offset inside its aligned box
+    if (use_tma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar)), "r"(lg.box_w * lg.box_h) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&maps.m[cd.level])), "r"((int)cd.x0 - ox), "r"((int)cd.y0),
+                            "r"(cd.level > 0 ? scratch_base + f : f), "r"(smem_u32(&s_bar)) : "memory");
         }
     } else {
-        for (int y = warp; y < rh; y += NW)
-            for (int x = lane; x < rw; x += 32) { tile[y][x] = base[(long long)y * pitch + x]; score[y][x] = 0; }
+        // caller frames whose pointer / strides are not 16-byte multiples cannot be described by a tensor map: byte-wise staging
+        const uint8_t* base = img0 + (long long)f * img_frame_stride + (long long)cd.y0 * img_row_stride + cd.x0;
+        for (int y = warp; y < rh; y += kFastWarps)
+            for (int x = lane; x < rw; x += 32) tile[y * tp + ox + x] = base[(long long)y * img_row_stride + x];
     }
-    if (tid == 0) s_q = 0;
-    __syncthreads();
-
+    {   // meanwhile: clear the score tile
+        uint4* sc4 = reinterpret_cast<uint4*>(score);
+        for (int i = tid; i < (rh * tp) >> 4; i += kFastThreads) sc4[i] = make_uint4(0u, 0u, 0u, 0u);      // tp is a multiple of 16
+    }
     const int iw = rw - 6, ih = rh - 6;               // interior
-    const int nchunk = (iw + 31) >> 5;
+    const int tc0 = ox + 3, tc1 = tc0 + iw;           // interior tile columns [tc0, tc1)
+    const int g_lo = tc0 >> 2, ngroups = ((tc1 - 1) >> 2) - g_lo + 1;      // aligned 4-pixel groups that hold interior pixels
+    // pretest lane mapping: lane -> (row inside the warp's row block, group); fixed for the whole kernel
+    const int rpi = 32 / min(ngroups, 32);            // rows per warp iteration
+    const int my_sub = lane / ngroups, my_g = g_lo + lane - my_sub * ngroups;
+    const bool my_on = my_sub < rpi;
+    // validity of the four pixels of my group (tile columns 4g .. 4g+3 inside [tc0, tc1)) as half-word masks
+    unsigned valid_e = 0, valid_o = 0;
+    {
+        const int c = 4 * my_g;
+        if (c >= tc0 && c < tc1) valid_e |= 0x0000ffffu;
+        if (c + 2 >= tc0 && c + 2 < tc1) valid_e |= 0xffff0000u;
+        if (c + 1 >= tc0 && c + 1 < tc1) valid_o |= 0x0000ffffu;
+        if (c + 3 >= tc0 && c + 3 < tc1) valid_o |= 0xffff0000u;
+    }
+    uint16_t* q = q_all + warp * sg.qcap;
+    if (use_tma) {
+        __syncthreads();                              // the barrier word is initialised before anybody polls it
+        asm volatile("{\n.reg .pred p;\nFAST_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra FAST_DONE;\nbra FAST_WAIT;\nFAST_DONE:\n}"
+                     :: "r"(smem_u32(&s_bar)) : "memory");
+    } else __syncthreads();
+
     int T = g.ini_th;
     for (int pass = 0; pass < 2; pass++) {
         for (int i = tid; i < ih * 3; i += kFastThreads) keep[i] = 0u;
         if (tid == 0) s_any = 0;
-        // 1. pretest + enqueue
-        for (int y = warp; y < ih; y += NW) {
-            for (int c = 0; c < nchunk; c++) {
-                const int x = c * 32 + lane;
-                bool cand = false;
-                if (x < iw) {
-                    const uint8_t* p = &tile[y + 3][ox + x + 3];
-                    const int v = p[0], lo = v - T, hi = v + T;
-                    const int c0 = p[3 * kTP], c4 = p[3], c8 = p[-3 * kTP], c12 = p[-3];
-                    const bool b0 = c0 > hi, b4 = c4 > hi, b8 = c8 > hi, b12 = c12 > hi;
-                    const bool d0 = c0 < lo, d4 = c4 < lo, d8 = c8 < lo, d12 = c12 < lo;
-                    cand = (b0 & b4) | (b4 & b8) | (b8 & b12) | (b12 & b0) | (d0 & d4) | (d4 & d8) | (d8 & d12) | (d12 & d0);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, cand);
-                if (m) {
-                    int qb = 0;
-                    if (lane == 0) qb = atomicAdd(&s_q, __popc(m));
-                    qb = __shfl_sync(0xffffffffu, qb, 0);
-                    if (cand) queue[qb + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
-                }
+        const unsigned Tp = (unsigned)T * 0x10001u, Tn = (unsigned)(0x10000 - T) * 0x10001u;
+        // 1. pretest + enqueue (warp-private queue)
+        int nq = 0;
+        for (int y0 = warp * rpi; y0 < ih; y0 += kFastWarps * rpi) {
+            const int y = y0 + my_sub;
+            unsigned me = 0, mo = 0;
+            if (my_on && y < ih) {
+                const uint32_t* r = reinterpret_cast<const uint32_t*>(tile + (y + 3) * tp) + my_g;
+                const int rp = tp >> 2;
+                const uint32_t wl = r[-1], wc = r[0], wr = r[1], wn = r[-3 * rp], ws = r[3 * rp];
+                const unsigned ce = pair_e(wc), co = pair_o(wc), le = pair_e(wl), lo = pair_o(wl), re = pair_e(wr), ro = pair_o(wr);
+                // even pixels (0, 2): west = odd pair of the left word, east = (pixel 3, pixel 5)
+                me = fast_pretest_pair(ce, pair_e(wn), pair_e(ws), sh16(co, ro), lo, Tp, Tn) & valid_e;
+                // odd pixels (1, 3): west = (pixel -2, pixel 0), east = even pair of the right word
+                mo = fast_pretest_pair(co, pair_o(wn), pair_o(ws), re, sh16(le, ce), Tp, Tn) & valid_o;
+            }
+            const bool p0 = (me & 0xffffu) != 0, p1 = (mo & 0xffffu) != 0, p2 = (me >> 16) != 0, p3 = (mo >> 16) != 0;
+            const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
+            if (b0 | b1 | b2 | b3) {
+                const unsigned lt = (1u << lane) - 1;
+                const int ent = (y << 8) | (4 * my_g);
+                const int o1 = nq + __popc(b0), o2 = o1 + __popc(b1), o3 = o2 + __popc(b2);
+                if (p0) q[nq + __popc(b0 & lt)] = (uint16_t)ent;
+                if (p1) q[o1 + __popc(b1 & lt)] = (uint16_t)(ent + 1);
+                if (p2) q[o2 + __popc(b2 & lt)] = (uint16_t)(ent + 2);
+                if (p3) q[o3 + __popc(b3 & lt)] = (uint16_t)(ent + 3);
+                nq = o3 + __popc(b3);
             }
         }
-        __syncthreads();
-        // 2. scores of the queued pixels
-        const int nq = s_q;
-        for (int i = tid; i < nq; i += kFastThreads) {
-            const int e = queue[i], y = e >> 8, x = e & 255;
-            const uint8_t* p = &tile[y + 3][ox + x + 3];
-            const int sc = fast_score(p, kTP, p[0]);
-            if (sc >= T) score[y + 3][ox + x + 3] = (uint8_t)sc;
+        __syncwarp();
+        // 2. scores, two queued pixels per thread (the second one of an odd tail repeats the first)
+        int nc = 0;
+        for (int i0 = 0; i0 < nq; i0 += 64) {
+            const int i = i0 + 2 * lane;
+            const bool on = i < nq;
+            int s0 = 0, s1 = 0, ea = 0, eb = 0;
+            if (on) {
+                ea = q[i]; eb = i + 1 < nq ? q[i + 1] : ea;
+                const uint8_t* pa = tile + ((ea >> 8) + 3) * tp + (ea & 255);
+                const uint8_t* pb = tile + ((eb >> 8) + 3) * tp + (eb & 255);
+                // circle: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+                unsigned d[16];
+#define B200_LD2(j, off) d[j] = (unsigned)pa[off] | ((unsigned)pb[off] << 16)
+                B200_LD2(0, 3 * tp); B200_LD2(1, 3 * tp + 1); B200_LD2(2, 2 * tp + 2); B200_LD2(3, tp + 3);
+                B200_LD2(4, 3); B200_LD2(5, -tp + 3); B200_LD2(6, -2 * tp + 2); B200_LD2(7, -3 * tp + 1);
+                B200_LD2(8, -3 * tp); B200_LD2(9, -3 * tp - 1); B200_LD2(10, -2 * tp - 2); B200_LD2(11, -tp - 3);
+                B200_LD2(12, -3); B200_LD2(13, tp - 3); B200_LD2(14, 2 * tp - 2); B200_LD2(15, 3 * tp - 1);
+#undef B200_LD2
+                const unsigned nV = __vneg2((unsigned)pa[0] | ((unsigned)pb[0] << 16));
+#pragma unroll
+                for (int j = 0; j < 16; j++) d[j] = __vadd2(d[j], nV);
+                const unsigned sc2 = fast_score_pair(d);
+                s0 = (int)(short)(sc2 & 0xffffu); s1 = (int)sc2 >> 16;
+                if (i + 1 >= nq) s1 = 0;
+            }
+            const bool k0 = s0 >= T, k1 = s1 >= T;
+            if (k0) score[((ea >> 8) + 3) * tp + (ea & 255)] = (uint8_t)s0;
+            if (k1) score[((eb >> 8) + 3) * tp + (eb & 255)] = (uint8_t)s1;
+            // corners overwrite the head of the queue (entries below i0 + 64 have been consumed; nc <= i0 + 64 always)
+            const unsigned c0 = __ballot_sync(0xffffffffu, k0), c1 = __ballot_sync(0xffffffffu, k1);
+            const unsigned lt = (1u << lane) - 1;
+            const int o1 = nc + __popc(c0);
+            __syncwarp();
+            if (k0) q[nc + __popc(c0 & lt)] = (uint16_t)ea;
+            if (k1) q[o1 + __popc(c1 & lt)] = (uint16_t)eb;
+            nc = o1 + __popc(c1);
+            __syncwarp();
         }
+        if (lane == 0) s_nc[warp] = nc;
         __syncthreads();
-        // 3. NMS of the queued pixels -> keep bits
-        for (int i = tid; i < nq; i += kFastThreads) {
-            const int e = queue[i], y = e >> 8, x = e & 255;
-            const uint8_t* q = &score[y + 3][ox + x + 3];
-            const int sc = q[0];
-            if (sc && sc > q[-1] && sc > q[1] && sc > q[-kTP - 1] && sc > q[-kTP] && sc > q[-kTP + 1] && sc > q[kTP - 1] && sc > q[kTP] && sc > q[kTP + 1]) {
-                atomicOr(&keep[y * 3 + (x >> 5)], 1u << (x & 31));
-                s_any = 1;
+        // 3. NMS of the corners -> keep bits (bit index = interior column); the warps share all four corner lists
+        for (int w = 0; w < kFastWarps; w++) {
+            const int ncw = s_nc[w];
+            const uint16_t* qc = q_all + w * sg.qcap;
+            for (int i = tid; i < ncw; i += kFastThreads) {
+                const int e = qc[i], y = e >> 8, c = e & 255;
+                const uint8_t* sp = score + (y + 3) * tp + c;
+                const int sc = sp[0];
+                if (sc > sp[-1] && sc > sp[1] && sc > sp[-tp - 1] && sc > sp[-tp] && sc > sp[-tp + 1] && sc > sp[tp - 1] && sc > sp[tp] && sc > sp[tp + 1]) {
+                    const int x = c - tc0;
+                    atomicOr(&keep[y * 3 + (x >> 5)], 1u << (x & 31));
+                    s_any = 1;
+                }
             }
         }
         __syncthreads();
         if (s_any || pass == 1 || g.min_th >= g.ini_th) break;
-        // nothing at iniThFAST: the whole cell again at minThFAST (a superset of the pixels examined so far)
+        // nothing at iniThFAST: the whole cell again at minThFAST (a superset of the pixels examined so far; the scores already
+        // in the tile stay valid)
         T = g.min_th;
-        if (tid == 0) s_q = 0;
-        __syncthreads();
     }
     // raster-ordered emission: keep words in (row, chunk) order; warp 0 scans their popcounts
     if (warp == 0) {
         uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
-        const int nwords = ih * 3;
+        const int nkw = ih * 3;
         int run = 0;
-        for (int w0 = 0; w0 < nwords; w0 += 32) {
+        for (int w0 = 0; w0 < nkw; w0 += 32) {
             const int wi = w0 + lane;
-            uint32_t m = wi < nwords ? keep[wi] : 0u;
+            uint32_t m = wi < nkw ? keep[wi] : 0u;
             const int c = __popc(m);
             int sc = c;
 #pragma unroll
@@ -267,7 +348,7 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
                 m &= m - 1;
                 const int x = ch * 32 + bit;
                 // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
-                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)score[y + 3][ox + x + 3] << 24);
+                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)score[(y + 3) * tp + tc0 + x] << 24);
                 pos++;
             }
             run += __shfl_sync(0xffffffffu, sc, 31);
@@ -793,6 +874,7 @@ struct b200_orb_s {
     OrbGeom geom;
     std::vector<CellDesc> cells;
     int pool_cap;
+    FastSmemGeom fsg; size_t fast_smem; FastMaps maps;      // maps.m[l > 0]: level l of the pyramid buffer; m[0] is encoded per call
     // device buffers
     uint8_t* d_pyr; ResizeEntry* d_tab; CellDesc* d_cells; uint32_t* d_slots; int* d_cellcnt;
     uint32_t *d_keysA, *d_keysB, *d_lvlres; int* d_lvlcnt; int* d_err;
@@ -822,6 +904,26 @@ template <typename T> int ensure(T*& p, size_t& cap, size_t need_bytes) {
     p = nullptr; cap = 0;
     B200_CUDA(cudaMalloc((void**)&p, need_bytes));
     cap = need_bytes;
+    return B200_OK;
+}
+
+// 3-D u8 tensor map (x, y, frame) with a box of box_w x box_h x 1 for the TMA tile loads of k_fast
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_tile_map(CUtensorMap* m, const void* base, int w, int hgt, int nframes, long long row_stride, long long frame_stride, int box_w, int box_h) {
+    static EncodeTiledFn encode = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    if (!encode) return fail(B200_ECUDA, "driver entry point %s not found", "cuTensorMapEncodeTiled");
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)hgt, (cuuint64_t)std::max(nframes, 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u}, estr[3] = {1u, 1u, 1u};
+    const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200_ECUDA, "cuTensorMapEncodeTiled %s", "failed");
     return B200_OK;
 }
 
@@ -916,6 +1018,25 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
         if (L.w > 4095 || L.h > 4095) return fail(B200_EINVAL, "level larger than %s", "4095 px (12-bit packed coordinates)");
     }
     g.total_cells = (int)h->cells.size();
+    {   // TMA boxes and the shared-memory carve-up of k_fast
+        FastSmemGeom& sgm = h->fsg;
+        sgm.tile_bytes = 128; sgm.qcap = 8; sgm.keepw = 3;
+        for (int l = 0; l < h->nlevels; l++) {
+            LevelGeom& L = g.L[l];
+            int mrw = 7, mrh = 7;
+            for (int c = 0; c < L.ncells; c++) {
+                const CellDesc& cd = h->cells[L.cell_base + c];
+                mrw = std::max(mrw, (int)cd.rw); mrh = std::max(mrh, (int)cd.rh);
+                const int iw = cd.rw - 6, ih = cd.rh - 6, tc0 = (cd.x0 & 15) + 3, ng = ((tc0 + iw - 1) >> 2) - (tc0 >> 2) + 1, rpi = 32 / std::min(ng, 32);
+                const int rows_w = (ih + kFastWarps * rpi - 1) / (kFastWarps * rpi) * rpi;          // rows one warp pretests
+                sgm.qcap = std::max(sgm.qcap, (rows_w * 4 * ng + 7) & ~7);
+                sgm.keepw = std::max(sgm.keepw, ih * 3);
+            }
+            L.box_w = (int)align_up(mrw + 15, 16); L.box_h = mrh;
+            sgm.tile_bytes = std::max(sgm.tile_bytes, (int)align_up((long long)L.box_w * L.box_h, 128));
+        }
+        h->fast_smem = (size_t)2 * sgm.tile_bytes + (size_t)kFastWarps * sgm.qcap * 2 + (size_t)sgm.keepw * 4;
+    }
     g.slots_per_frame = slot;
     g.pyr_frame_stride = std::max<long long>(pyr_ofs, 256);
     g.res_per_frame = res;
@@ -937,6 +1058,10 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
     if (!h->d_err) { B200_CUDA(cudaMalloc((void**)&h->d_err, 4)); B200_CUDA(cudaMemset(h->d_err, 0, 4)); }
     if (!tab.empty()) B200_CUDA(cudaMemcpy(h->d_tab, tab.data(), tab.size() * sizeof(ResizeEntry), cudaMemcpyHostToDevice));
     if (!h->cells.empty()) B200_CUDA(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
+    for (int l = 1; l < h->nlevels; l++) {
+        const LevelGeom& L = g.L[l];
+        if ((rc = make_tile_map(&h->maps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, L.box_w, L.box_h))) return rc;
+    }
     h->cur_w = w; h->cur_h = h_img;
     return B200_OK;
 }
@@ -987,7 +1112,15 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[1], st));
     if (g.total_cells > 0) {
         dim3 grid(g.total_cells, n);
-        B200_LAUNCH(k_fast, grid, kFastThreads, 0, st, imgs, rs, fs, d_pyr, g, h->d_cells, d_slots, d_cellcnt);
+        static std::atomic<size_t> fast_smem_set(0);
+        if (h->fast_smem > 48 * 1024 && h->fast_smem > fast_smem_set.load()) {
+            B200_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem)); fast_smem_set.store(h->fast_smem);
+        }
+        // level 0 = the caller's frames: a tensor map needs a 16-byte aligned pointer and strides (else k_fast stages level 0 byte-wise)
+        const long long fs0 = n > 1 ? fs : align_up(rs * (long long)g.L[0].h, 16);
+        const int tma0 = ((reinterpret_cast<uintptr_t>(imgs) | (uintptr_t)rs | (uintptr_t)fs0) & 15) == 0;
+        if (tma0) { int rc = make_tile_map(&h->maps.m[0], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, g.L[0].box_w, g.L[0].box_h); if (rc) return rc; }
+        B200_LAUNCH(k_fast, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[2], st));
     {
