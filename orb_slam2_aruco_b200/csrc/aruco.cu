@@ -42,9 +42,10 @@ constexpr int kMaxWarp = 50;         // warped patch side: 5*(sqrt(nbits)+2) <= 
 
 struct ArucoGeom {
     int w, h;
-    int bpitch;                 // pitch of the padded binary / mask images ((w+2) rounded up)
+    int bpitch;                 // pitch of the padded mask images ((w + 2*kMaskPad) rounded up to 16)
     long long bframe;           // bytes per frame of the padded binary image
     int win;                    // adaptive threshold window
+    unsigned mean_mul;          // ceil(2^24 / win^2)
     int nlev;                   // pyramid levels incl. level 0
     int lw[kMaxPyr], lh[kMaxPyr], lpitch[kMaxPyr];
     long long loff[kMaxPyr];    // offset of level l (>=1) inside a frame's pyramid block
@@ -62,61 +63,105 @@ struct Decoded { int id, nrot; };
 
 
 // ------------------------------------------------------------------------------------------------
-// A1: adaptive threshold.  mean = rint(S/bs^2) (ties impossible for odd bs^2); out = src - mean <= -7.
-// One CTA -> 32x32 output tile; (32+2r)^2 replicate-clamped source patch in shared memory.
+// A1: adaptive threshold fused with the 8-neighbour foreground mask.  mean = rint(S/bs^2) (ties impossible for odd
+// bs^2) computed as ((S + bs^2/2) * M) >> 24 with M = ceil(2^24 / bs^2) (exact for S <= 255 * 225, checked by the host
+// at handle creation); out = src - mean <= -7.
+// One CTA -> 64x32 mask tile.  The replicate-clamped source patch is staged with aligned 32-bit loads (patch column 0 =
+// image column 64*bx - 8), window sums are separable running sums (u16), the 66x34 binary block sits 3 bytes into its
+// rows so that the four-pixel output groups are word aligned, and the masks of four pixels are built with byte-parallel
+// integer arithmetic (values 0/1 never carry between bytes) and stored as one word.
+// Mask layout in HBM: pixel (x, y) at byte (y + 1) * bpitch + x + kMaskPad; everything around the image stays zero.
 // ------------------------------------------------------------------------------------------------
 constexpr int kThrTW = 64, kThrTH = 32, kThrMaxR = 7;
 constexpr int kThrBW = kThrTW + 2, kThrBH = kThrTH + 2;             // binary values are needed one pixel around the tile
+constexpr int kThrPP = 80;                                          // patch pitch: columns 64*bx - 8 .. 64*bx + 71
+constexpr int kThrHP = 68;                                          // u16 pitch of the horizontal sums
+constexpr int kThrBP = 72;                                          // byte pitch of the binary block (column c at byte c + 3)
+constexpr int kMaskPad = 4;
 
 __global__ void __launch_bounds__(256)
 k_athresh(const uint8_t* __restrict__ img, long long row_stride, long long frame_stride, const __grid_constant__ ArucoGeom g,
           uint8_t* __restrict__ mask) {
-    __shared__ uint8_t patch[kThrBH + 2 * kThrMaxR][kThrBW + 2 * kThrMaxR + 2];
-    __shared__ uint16_t hs[kThrBH + 2 * kThrMaxR][kThrBW];
-    __shared__ uint8_t bin[kThrBH][kThrBW + 2];
+    __shared__ __align__(16) uint8_t patch[(kThrBH + 2 * kThrMaxR) * kThrPP];
+    __shared__ __align__(16) uint16_t hs[(kThrBH + 2 * kThrMaxR) * kThrHP];
+    __shared__ __align__(16) uint8_t bin[kThrBH * kThrBP];
     const int f = blockIdx.z, x0 = blockIdx.x * kThrTW - 1, y0 = blockIdx.y * kThrTH - 1;    // origin of the 66x34 binary block
-    const int bs = g.win, r = bs >> 1, sw = kThrBW + 2 * r, sh = kThrBH + 2 * r;
+    const int bs = g.win, r = bs >> 1, sh = kThrBH + 2 * r;
     const uint8_t* src = img + (long long)f * frame_stride;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < sw * sh; i += 256) {
-        const int py = i / sw, px = i - py * sw;
-        const int yy = min(max(y0 + py - r, 0), g.h - 1), xx = min(max(x0 + px - r, 0), g.w - 1);     // BORDER_REPLICATE
-        patch[py][px] = src[(long long)yy * row_stride + xx];
+    const int xa = blockIdx.x * kThrTW - 8;                          // image column of patch column 0
+    // ---- patch rows y0 - r .. y0 + 33 + r, columns xa .. xa + 79 (BORDER_REPLICATE)
+    {
+        const bool words_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)row_stride) & 3) == 0;
+        const int w_lo = (7 - r) >> 2, w_hi = (72 + r) >> 2;        // words that hold columns 7 - r .. 72 + r
+        const int nw = w_hi - w_lo + 1;
+        for (int i = tid; i < sh * 32; i += 256) {                  // (row, word) with a power-of-two row length
+            const int py = i >> 5, wx = w_lo + (i & 31);
+            if ((i & 31) >= nw) continue;
+            const int yy = min(max(y0 + py - r, 0), g.h - 1);
+            const uint8_t* row = src + (long long)yy * row_stride;
+            const int gx = xa + 4 * wx;
+            uint32_t v;
+            if (words_ok && gx >= 0 && gx + 3 < g.w) v = *reinterpret_cast<const uint32_t*>(row + gx);
+            else {
+                v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) v |= (uint32_t)row[min(max(gx + k, 0), g.w - 1)] << (8 * k);
+            }
+            *reinterpret_cast<uint32_t*>(&patch[py * kThrPP + 4 * wx]) = v;
+        }
     }
     __syncthreads();
-    for (int i = tid; i < sh * kThrBW; i += 256) {
-        const int py = i / kThrBW, px = i - py * kThrBW;
+    // ---- horizontal running sums: hs[row][c] = sum of patch[row][c + 7 - r .. c + 7 + r], c = 0..65 (6 segments of 11)
+    for (int i = tid; i < sh * 6; i += 256) {
+        const int py = i / 6, c0 = (i - py * 6) * 11;
+        const uint8_t* p = &patch[py * kThrPP + c0 + 7 - r];
+        uint16_t* o = &hs[py * kThrHP + c0];
         int s = 0;
-        for (int k = 0; k < bs; k++) s += patch[py][px + k];
-        hs[py][px] = (uint16_t)s;
+        for (int k = 0; k < bs; k++) s += p[k];
+        o[0] = (uint16_t)s;
+#pragma unroll
+        for (int c = 1; c < 11; c++) { s += p[c + bs - 1] - p[c - 1]; o[c] = (uint16_t)s; }
     }
     __syncthreads();
-    const double scale = 1.0 / ((double)bs * bs);
-    for (int i = tid; i < kThrBH * kThrBW; i += 256) {
-        const int by = i / kThrBW, bx = i - by * kThrBW;
-        const int x = x0 + bx, y = y0 + by;
-        int v = 0;
-        if (x >= 0 && x < g.w && y >= 0 && y < g.h) {
+    // ---- vertical running sums, mean, threshold: bin[y][c], 3 row segments (12, 11, 11) per column
+    {
+        const int half = (bs * bs) >> 1;
+        const unsigned M = g.mean_mul;
+        for (int i = tid; i < kThrBW * 3; i += 256) {
+            const int seg = i / kThrBW, c = i - seg * kThrBW;
+            const int yb0 = seg == 0 ? 0 : 1 + 11 * seg, yb1 = seg == 2 ? kThrBH : 12 + 11 * seg;     // 0..12, 12..23, 23..34
+            const uint16_t* hcol = &hs[yb0 * kThrHP + c];
             int s = 0;
-            for (int k = 0; k < bs; k++) s += hs[by + k][bx];
-            const int mean = min(__double2int_rn((double)s * scale), 255);
-            v = ((int)patch[by + r][bx + r] - mean <= -7) ? 1 : 0;
+            for (int k = 0; k < bs; k++) s += hcol[k * kThrHP];
+            const int x = x0 + c;
+            const bool xin = x >= 0 && x < g.w;
+            for (int yb = yb0; yb < yb1; yb++) {
+                const int mean = (int)(((unsigned)(s + half) * M) >> 24);
+                const int y = y0 + yb;
+                const int v = patch[(yb + r) * kThrPP + c + 7];
+                bin[yb * kThrBP + c + 3] = (uint8_t)((xin && y >= 0 && y < g.h && v + 7 <= mean) ? 1 : 0);
+                if (yb + 1 < yb1) s += hcol[(yb - yb0 + bs) * kThrHP] - hcol[(yb - yb0) * kThrHP];
+            }
         }
-        bin[by][bx] = (uint8_t)v;
     }
     __syncthreads();
-    // 8-neighbour foreground mask (bit d = neighbour in direction d: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE); 0 for background
-    for (int i = tid; i < kThrTH * kThrTW; i += 256) {
-        const int ty = i / kThrTW, tx = i - ty * kThrTW;
-        const int bx = tx + 1, by = ty + 1;
-        const int x = x0 + bx, y = y0 + by;
-        if (x < g.w && y < g.h) {
-            int m = 0;
-            if (bin[by][bx])
-                m = bin[by][bx + 1] | (bin[by - 1][bx + 1] << 1) | (bin[by - 1][bx] << 2) | (bin[by - 1][bx - 1] << 3) | (bin[by][bx - 1] << 4) |
-                    (bin[by + 1][bx - 1] << 5) | (bin[by + 1][bx] << 6) | (bin[by + 1][bx + 1] << 7);
-            mask[(long long)f * g.bframe + (long long)(y + 1) * g.bpitch + x + 1] = (uint8_t)m;
-        }
+    // ---- 8-neighbour foreground mask (bit d = neighbour in direction d: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE); 0 for background.
+    // Output pixels (tx, ty) = binary block (tx + 1, ty + 1) = bytes tx + 4 of row ty + 1: group k = word k + 1.
+    for (int i = tid; i < kThrTH * (kThrTW / 4); i += 256) {
+        const int ty = i >> 4, k = i & 15;
+        const int y = y0 + 1 + ty, x = x0 + 1 + 4 * k;
+        if (y >= g.h || x >= g.w) continue;
+        const uint32_t* rn = reinterpret_cast<const uint32_t*>(&bin[ty * kThrBP]) + k;          // row above: words k, k+1, k+2
+        const uint32_t* rc = rn + kThrBP / 4;
+        const uint32_t* rs = rc + kThrBP / 4;
+        const uint32_t n0 = rn[0], n1 = rn[1], n2 = rn[2], c0 = rc[0], c1 = rc[1], c2 = rc[2], s0 = rs[0], s1 = rs[1], s2 = rs[2];
+        const uint32_t W = __funnelshift_r(c0, c1, 24), E = __funnelshift_r(c1, c2, 8);
+        const uint32_t NW = __funnelshift_r(n0, n1, 24), NE = __funnelshift_r(n1, n2, 8);
+        const uint32_t SW = __funnelshift_r(s0, s1, 24), SE = __funnelshift_r(s1, s2, 8);
+        uint32_t m = E + 2u * NE + 4u * n1 + 8u * NW + 16u * W + 32u * SW + 64u * s1 + 128u * SE;
+        m &= c1 * 255u;                                              // bytes of c1 are 0/1: 0x01 -> 0xff
+        *reinterpret_cast<uint32_t*>(mask + (long long)f * g.bframe + (long long)(y + 1) * g.bpitch + x + kMaskPad) = m;
     }
 }
 
@@ -204,7 +249,7 @@ __global__ void __launch_bounds__(256)
 k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, int* __restrict__ cand, int* __restrict__ ncand,
           int max_cand, int* __restrict__ err) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    const int P = (y + 1) * g.bpitch + x + 1;
+    const int P = (y + 1) * g.bpitch + x + kMaskPad;
     int m = 0;
     if (x < g.w && y < g.h) m = mask0[(long long)f * g.bframe + P];
     const bool co = m != 0 && !(m & 16), ch = m != 0 && !(m & 1);
@@ -321,7 +366,7 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
         const ContourDesc c = desc[(long long)f * g.max_contours + i];
         short2* out = pts + (long long)f * g.max_points + c.off;
         int p = c.start, s = c.s0;
-        int x = c.start % g.bpitch - 1, y = c.start / g.bpitch - 1;
+        int x = c.start % g.bpitch - kMaskPad, y = c.start / g.bpitch - 1;
         for (int n = 0; n < c.len; n++) {
             out[n] = make_short2((short)x, (short)y);
             const Step st = next_step(mask[p], s);
@@ -1095,12 +1140,18 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     ArucoGeom& g = h->geom;
     memset(&g, 0, sizeof(g));
     g.w = w; g.h = hh;
-    g.bpitch = (int)align_up(w + 2, 16);
+    g.bpitch = (int)align_up(w + 2 * kMaskPad, 16);
     g.bframe = (long long)g.bpitch * (hh + 2);
     int win = std::max(3, (int)(15 * float(w) / 1920.));         // markerdetector_impl.cpp:3769-3867
     if (win % 2 == 0) win++;
     if (win > 2 * kThrMaxR + 1) return fail(B200_EINVAL, "image wider than %s", "the 15-px threshold window supports (1920)");
     g.win = win;
+    {   // rint(S / win^2) as a multiply-shift: verified exhaustively for every reachable window sum
+        const int a = win * win, half = a / 2;
+        g.mean_mul = (unsigned)(((1ull << 24) + a - 1) / a);
+        for (int S = 0; S <= 255 * a; S++)
+            if ((int)(((unsigned long long)(unsigned)(S + half) * g.mean_mul) >> 24) != (S + half) / a) return fail(B200_EINVAL, "mean multiplier inexact for window %s", "size");
+    }
     g.nbits = h->nbits; g.nb = (int)sqrt((double)h->nbits); g.nsub = g.nb + 2; g.wsize = 5 * g.nsub; g.ncodes = h->ncodes;
     // pyramid (1300-1466): halve while width > 2*warpSize
     g.lw[0] = w; g.lh[0] = hh; g.nlev = 1;

@@ -16,7 +16,7 @@
 
 namespace b200 {
 
-constexpr int kTopK = 4;
+constexpr int kTopK = 8;             // list length per reference row: long enough that the exact rescan stays rare even when most rows match
 constexpr int kMatchWarps = 8;
 constexpr int kRefPerCta = 64;
 
@@ -24,13 +24,13 @@ __device__ __forceinline__ int hamming256(const ulonglong4 a, const ulonglong4 b
     return __popcll(a.x ^ b.x) + __popcll(a.y ^ b.y) + __popcll(a.z ^ b.z) + __popcll(a.w ^ b.w);
 }
 
-// insert key into an ascending sorted 4-list
-__device__ __forceinline__ void top4_insert(uint32_t (&t)[kTopK], uint32_t key) {
-    if (key < t[3]) {
-        t[3] = key;
-        if (t[3] < t[2]) { uint32_t s = t[2]; t[2] = t[3]; t[3] = s; }
-        if (t[2] < t[1]) { uint32_t s = t[1]; t[1] = t[2]; t[2] = s; }
-        if (t[1] < t[0]) { uint32_t s = t[0]; t[0] = t[1]; t[1] = s; }
+// insert key into an ascending sorted K-list
+__device__ __forceinline__ void topk_insert(uint32_t (&t)[kTopK], uint32_t key) {
+    if (key < t[kTopK - 1]) {
+        t[kTopK - 1] = key;
+#pragma unroll
+        for (int k = kTopK - 1; k > 0; k--)
+            if (t[k] < t[k - 1]) { const uint32_t s = t[k - 1]; t[k - 1] = t[k]; t[k] = s; }
     }
 }
 
@@ -52,11 +52,13 @@ k_match_topk(const ulonglong4* __restrict__ ref_desc, int n_ref,
     const int r_end = min(n_ref, (int)(blockIdx.x + 1) * kRefPerCta);
     for (int r = blockIdx.x * kRefPerCta + warp; r < r_end; r += kMatchWarps) {
         const ulonglong4 q = ref_desc[r];
-        uint32_t t[kTopK] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        uint32_t t[kTopK];
+#pragma unroll
+        for (int k = 0; k < kTopK; k++) t[k] = 0xffffffffu;
         for (int i = lane; i < nf; i += 32) {
             const int d = __popcll(q.x ^ s_planes[i]) + __popcll(q.y ^ s_planes[nf_pad + i]) +
                           __popcll(q.z ^ s_planes[2 * nf_pad + i]) + __popcll(q.w ^ s_planes[3 * nf_pad + i]);
-            top4_insert(t, ((uint32_t)d << 16) | (uint32_t)i);
+            topk_insert(t, ((uint32_t)d << 16) | (uint32_t)i);
         }
         // K rounds of warp arg-min over the lanes' list heads
         uint32_t* out = topk + ((long long)f * n_ref + r) * kTopK;
@@ -65,7 +67,11 @@ k_match_topk(const ulonglong4* __restrict__ ref_desc, int n_ref,
             uint32_t m = t[0];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (t[0] == m && m != 0xffffffffu) { t[0] = t[1]; t[1] = t[2]; t[2] = t[3]; t[3] = 0xffffffffu; }   // keys are unique
+            if (t[0] == m && m != 0xffffffffu) {                      // keys are unique: exactly one lane pops its head
+#pragma unroll
+                for (int j = 0; j + 1 < kTopK; j++) t[j] = t[j + 1];
+                t[kTopK - 1] = 0xffffffffu;
+            }
             if (lane == 0) out[k] = m;
         }
     }
@@ -113,10 +119,10 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
         // (uint4 copies: the lists are 16-byte records; the angles of both sides follow so that a commit never waits on HBM)
         uint4* s_tk = reinterpret_cast<uint4*>(bin_of + ((frame_cap + 15) & ~15));
         const uint4* g_tk = reinterpret_cast<const uint4*>(tk_base);
-        for (int i = lane; i < n_ref; i += 32) s_tk[i] = g_tk[i];
+        for (int i = lane; i < n_ref * (kTopK / 4); i += 32) s_tk[i] = g_tk[i];
         tk_base = reinterpret_cast<const uint32_t*>(s_tk);
         if (check_ori) {
-            float* s_ra = reinterpret_cast<float*>(s_tk + n_ref);
+            float* s_ra = reinterpret_cast<float*>(s_tk + n_ref * (kTopK / 4));
             float* s_fa = s_ra + n_ref;
             for (int i = lane; i < n_ref; i += 32) s_ra[i] = ref_angle[(long long)i * ref_astride];
             for (int i = lane; i < nf; i += 32) s_fa[i] = fa[(long long)i * frame_astride];
@@ -125,25 +131,37 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
         __syncwarp();
     }
     // The reference loop is serial in r, but the only state it carries is the "taken" set, which changes on accepted
-    // matches only.  So 32 consecutive r are evaluated speculatively, one per lane, against the current set; the first
-    // lane that accepts a match (or needs the exact rescan) is committed and everything after it is re-evaluated.
+    // matches only.  So 32 consecutive r are evaluated speculatively, one per lane, against the current set.  The lanes are
+    // then committed in order: the first lane that accepts a match (or needs the exact rescan) is resolved, and only the
+    // later lanes whose top-K list contains the frame keypoint just taken are re-evaluated (from registers); everybody
+    // else's verdict is still what the serial loop would have computed.
     int nm = 0;
-    int r0 = 0;
-    while (r0 < n_ref) {
+    for (int r0 = 0; r0 < n_ref; r0 += 32) {
         const int r = r0 + lane;
-        uint32_t b1 = 0xffffffffu, b2 = 0xffffffffu, last = 0xffffffffu;
-        bool exact = true, accept = false;
+        uint32_t key[kTopK];
+#pragma unroll
+        for (int k = 0; k < kTopK; k++) key[k] = 0xffffffffu;
         if (r < n_ref) {
-            const uint32_t* tk = tk_base + (long long)r * kTopK;
+#pragma unroll
+            for (int k4 = 0; k4 < kTopK / 4; k4++) {
+                const uint4 v = reinterpret_cast<const uint4*>(tk_base + (long long)r * kTopK)[k4];
+                key[4 * k4] = v.x; key[4 * k4 + 1] = v.y; key[4 * k4 + 2] = v.z; key[4 * k4 + 3] = v.w;
+            }
+        }
+        uint32_t b1, b2;
+        bool exact, accept;
+        auto evaluate = [&]() {
+            b1 = 0xffffffffu; b2 = 0xffffffffu; exact = true; accept = false;
+            if (r >= n_ref) return;
+            uint32_t last = 0xffffffffu;
             int found = 0;
 #pragma unroll
             for (int k = 0; k < kTopK; k++) {
-                const uint32_t key = tk[k];
-                if (key == 0xffffffffu) continue;
-                last = key;
-                const int idx = key & 0xffff;
+                if (key[k] == 0xffffffffu) continue;
+                last = key[k];
+                const int idx = key[k] & 0xffff;
                 if (!((taken[idx >> 5] >> (idx & 31)) & 1u)) {
-                    if (found == 0) b1 = key; else if (found == 1) b2 = key;
+                    if (found == 0) b1 = key[k]; else if (found == 1) b2 = key[k];
                     found++;
                 }
             }
@@ -156,51 +174,63 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
                 const int d1 = b1 == 0xffffffffu ? 256 : (int)(b1 >> 16), d2 = b2 == 0xffffffffu ? 256 : (int)(b2 >> 16);
                 accept = d1 <= th_low && (float)d1 < __fmul_rn(ratio, (float)d2);
             }
-        }
-        const unsigned hot = __ballot_sync(0xffffffffu, accept || !exact);
-        if (!hot) { r0 += 32; continue; }
-        const int first = __ffs(hot) - 1;
-        const int rc = r0 + first;                                              // the reference index to commit
-        const bool need_scan = __shfl_sync(0xffffffffu, (int)!exact, first) != 0;
-        uint32_t c1 = __shfl_sync(0xffffffffu, b1, first), c2 = __shfl_sync(0xffffffffu, b2, first);
-        if (need_scan) {                                                        // rare: rescan the whole row, all lanes
-            const ulonglong4 q = ref_desc[rc];
-            uint32_t l1 = 0xffffffffu, l2 = 0xffffffffu;
-            for (int i = lane; i < nf; i += 32) {
-                if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
-                const uint32_t key = ((uint32_t)hamming256(q, fd[i]) << 16) | (uint32_t)i;
-                if (key < l1) { l2 = l1; l1 = key; } else if (key < l2) l2 = key;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const uint32_t o1 = __shfl_xor_sync(0xffffffffu, l1, o), o2 = __shfl_xor_sync(0xffffffffu, l2, o);
-                const uint32_t lo = min(l1, o1), hi = max(l1, o1);
-                l2 = min(hi, min(l2, o2));
-                l1 = lo;
-            }
-            c1 = l1; c2 = l2;
-        }
-        const int d1 = c1 == 0xffffffffu ? 256 : (int)(c1 >> 16);
-        const int d2 = c2 == 0xffffffffu ? 256 : (int)(c2 >> 16);
-        if (d1 <= th_low && (float)d1 < __fmul_rn(ratio, (float)d2)) {
-            const int idx = c1 & 0xffff;
-            if (lane == 0) {
-                taken[idx >> 5] |= 1u << (idx & 31);
-                mout[idx] = rc;
-                if (check_ori) {
-                    float rot = __fsub_rn(ref_angle[(long long)rc * ref_astride], fa[(long long)idx * frame_astride]);
-                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                    int bin = (int)roundf(__fmul_rn(rot, histo_factor));
-                    if (bin == kHistoLen) bin = 0;
-                    bin = max(0, min(bin, kHistoLen - 1));   // the reference asserts this range
-                    bin_of[idx] = (unsigned char)bin;
-                    histo[bin]++;
+        };
+        evaluate();
+        unsigned pending = 0xffffffffu;                                         // lanes not yet passed by the serial order
+        for (;;) {
+            const unsigned hot = __ballot_sync(0xffffffffu, accept || !exact) & pending;
+            if (!hot) break;
+            const int first = __ffs(hot) - 1;
+            const int rc = r0 + first;                                          // the reference index to commit
+            pending = first == 31 ? 0u : (0xffffffffu << (first + 1));
+            const bool need_scan = __shfl_sync(0xffffffffu, (int)!exact, first) != 0;
+            uint32_t c1 = __shfl_sync(0xffffffffu, b1, first), c2 = __shfl_sync(0xffffffffu, b2, first);
+            if (need_scan) {                                                    // rare: rescan the whole row, all lanes
+                const ulonglong4 q = ref_desc[rc];
+                uint32_t l1 = 0xffffffffu, l2 = 0xffffffffu;
+                for (int i = lane; i < nf; i += 32) {
+                    if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
+                    const uint32_t k2 = ((uint32_t)hamming256(q, fd[i]) << 16) | (uint32_t)i;
+                    if (k2 < l1) { l2 = l1; l1 = k2; } else if (k2 < l2) l2 = k2;
                 }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint32_t o1 = __shfl_xor_sync(0xffffffffu, l1, o), o2 = __shfl_xor_sync(0xffffffffu, l2, o);
+                    const uint32_t lo = min(l1, o1), hi = max(l1, o1);
+                    l2 = min(hi, min(l2, o2));
+                    l1 = lo;
+                }
+                c1 = l1; c2 = l2;
             }
-            nm++;
+            const int d1 = c1 == 0xffffffffu ? 256 : (int)(c1 >> 16);
+            const int d2 = c2 == 0xffffffffu ? 256 : (int)(c2 >> 16);
+            if (d1 <= th_low && (float)d1 < __fmul_rn(ratio, (float)d2)) {
+                const int idx = c1 & 0xffff;
+                if (lane == 0) {
+                    taken[idx >> 5] |= 1u << (idx & 31);
+                    mout[idx] = rc;
+                    if (check_ori) {
+                        float rot = __fsub_rn(ref_angle[(long long)rc * ref_astride], fa[(long long)idx * frame_astride]);
+                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                        int bin = (int)roundf(__fmul_rn(rot, histo_factor));
+                        if (bin == kHistoLen) bin = 0;
+                        bin = max(0, min(bin, kHistoLen - 1));   // the reference asserts this range
+                        bin_of[idx] = (unsigned char)bin;
+                        histo[bin]++;
+                    }
+                }
+                nm++;
+                __syncwarp();
+                // later rows that listed this keypoint see a different candidate set now
+                bool touched = false;
+#pragma unroll
+                for (int k = 0; k < kTopK; k++) touched |= (int)(key[k] & 0xffff) == idx;
+                touched = touched && ((pending >> lane) & 1u);
+                if (touched) evaluate();
+            }
+            if (!pending) break;
         }
         __syncwarp();
-        r0 = rc + 1;
     }
     __syncwarp();
     if (check_ori) {

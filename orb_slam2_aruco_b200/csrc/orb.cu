@@ -71,33 +71,41 @@ __constant__ int c_umax[16];
 // K1: pyramid level from the previous level.  cv::resize INTER_LINEAR u8 fixed point (SURVEY A-1).
 // One thread -> 4 horizontally adjacent output pixels (one 32-bit store; pitch is a multiple of 16).
 // ------------------------------------------------------------------------------------------------
+constexpr int kPyrRows = 8;          // output rows per thread: the four column entries are fetched once and reused
+
 __global__ void __launch_bounds__(256)
 k_pyramid(const uint8_t* __restrict__ src0, long long src_row_stride, long long src_frame_stride,
           uint8_t* __restrict__ dst0, int dst_pitch, long long dst_frame_stride,
           int sw, int sh, int dw, int dh,
           const ResizeEntry* __restrict__ xt, const ResizeEntry* __restrict__ yt) {
     const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
     const int f = blockIdx.z;
-    if (x4 >= dw || y >= dh) return;
-    const ResizeEntry ye = yt[y];
-    const uint8_t* r0 = src0 + (long long)f * src_frame_stride + (long long)ye.ofs * src_row_stride;
-    const uint8_t* r1 = src0 + (long long)f * src_frame_stride + (long long)min(ye.ofs + 1, sh - 1) * src_row_stride;
-    uint32_t packed = 0;
+    if (x4 >= dw) return;
+    int o0[4], o1[4], c0[4], c1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        int x = x4 + i;
-        if (x < dw) {
-            const ResizeEntry xe = xt[x];
-            int sx1 = min(xe.ofs + 1, sw - 1);
-            int h0 = r0[xe.ofs] * xe.c0 + r0[sx1] * xe.c1;
-            int h1 = r1[xe.ofs] * xe.c0 + r1[sx1] * xe.c1;
-            int v = (((ye.c0 * (h0 >> 4)) >> 16) + ((ye.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            packed |= (uint32_t)(v & 0xff) << (8 * i);
-        }
+        const ResizeEntry xe = xt[min(x4 + i, dw - 1)];          // columns past the level width land in the row padding
+        o0[i] = xe.ofs; o1[i] = min(xe.ofs + 1, sw - 1); c0[i] = xe.c0; c1[i] = xe.c1;
     }
-    uint8_t* d = dst0 + (long long)f * dst_frame_stride + (long long)y * dst_pitch + x4;
-    *reinterpret_cast<uint32_t*>(d) = packed;     // pitch >= align16(dw): the tail bytes are padding
+    const uint8_t* sf = src0 + (long long)f * src_frame_stride;
+    uint8_t* df = dst0 + (long long)f * dst_frame_stride + x4;
+#pragma unroll 2
+    for (int j = 0; j < kPyrRows; j++) {
+        const int y = (blockIdx.y * kPyrRows + j) * 8 + threadIdx.y;
+        if (y >= dh) break;
+        const ResizeEntry ye = yt[y];
+        const uint8_t* r0 = sf + (long long)ye.ofs * src_row_stride;
+        const uint8_t* r1 = sf + (long long)min(ye.ofs + 1, sh - 1) * src_row_stride;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int h0 = r0[o0[i]] * c0[i] + r0[o1[i]] * c1[i];
+            const int h1 = r1[o0[i]] * c0[i] + r1[o1[i]] * c1[i];
+            const int v = (((ye.c0 * (h0 >> 4)) >> 16) + ((ye.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)v << (8 * i);
+        }
+        *reinterpret_cast<uint32_t*>(df + (long long)y * dst_pitch) = packed;     // pitch >= align16(dw): the tail bytes are padding
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -168,6 +176,8 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&d)[16]) {
     return __vadd2(__vmaxs2(maxmin, __vneg2(minmax)), 0xffffffffu);
 }
 
+// TP: tile pitch in bytes = TMA box width, a compile-time constant so that every circle offset is an immediate
+template <int TP>
 __global__ void __launch_bounds__(kFastThreads)
 k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
        const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ FastMaps maps,
@@ -181,7 +191,7 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
     const CellDesc cd = cells[blockIdx.x];
     const int f = blockIdx.y;
     const LevelGeom& lg = g.L[cd.level];
-    const int tp = lg.box_w;                                                            // tile pitch (bytes)
+    constexpr int tp = TP;
     uint8_t* tile = fs_raw;                                                             // [box_h][tp], column = ox + ROI column
     uint8_t* score = fs_raw + sg.tile_bytes;                                            // same geometry
     uint16_t* q_all = reinterpret_cast<uint16_t*>(fs_raw + 2 * sg.tile_bytes);          // per-warp pixel queues: y << 8 | tile column
@@ -195,7 +205,7 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar)), "r"(lg.box_w * lg.box_h) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar)), "r"(TP * lg.box_h) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                          :: "r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&maps.m[cd.level])), "r"((int)cd.x0 - ox), "r"((int)cd.y0),
                             "r"(cd.level > 0 ? scratch_base + f : f), "r"(smem_u32(&s_bar)) : "memory");
@@ -681,16 +691,25 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4+K5+K6: one warp per keypoint.  43x43 source patch -> smem; IC_Angle over the radius-15 disc;
-// separable 7x7 Gaussian (Q8 kernel 18,34,48,56,48,34,18; (V+32768)>>16) on the 37x37 region the
-// pattern can reach; 256 steered comparisons, lane i produces descriptor byte i.
+// K4+K5+K6: one warp per keypoint.  The 43x43 source patch arrives as one TMA box (64 x 43 bytes starting at the
+// patch's x rounded down to 16; patches that touch the image border go byte by byte through the REFLECT_101 map).
+//   IC_Angle over the radius-15 disc: per (row, 4-pixel word) two dp4a (u-weighted sum and plain row sum) on the word
+//     masked to the disc; fastAtan2 in explicitly rounded float ops
+//   7x7 Gaussian (Q8 kernel 18,34,48,56,48,34,18; (V+32768)>>16; exact integer arithmetic, so any evaluation order
+//     gives OpenCV's result) on the 37x37 region the pattern can reach: horizontal pass with dp4a (4 outputs from 3
+//     words), stored TRANSPOSED as u16 so that the vertical pass is dp2a over row pairs (2 outputs from 4 words)
+//   256 steered comparisons, lane i produces descriptor byte i; a, b = float(cos/sin(double(angle_rad))) from an
+//     fdlibm-style double kernel (quadrant reduction with a two-part pi/2, degree-13/14 polynomials)
 // ------------------------------------------------------------------------------------------------
-constexpr int kDescWarps = 8;
+constexpr int kDescWarps = 4;
 constexpr int kPatchR = 21;                  // 18 (max rotated pattern reach) + 3 (blur taps)
 constexpr int kPatchW = 2 * kPatchR + 1;     // 43
 constexpr int kBlurW = 37;
-constexpr int kPatchPitch = 44;
-constexpr int kHPitch = 40;                  // u16 pitch of the horizontally filtered patch
+constexpr int kPatchPitch = 64;              // = TMA box width: patch column 0 sits at byte ox = x0 & 15
+constexpr int kHTPitch = 44;                 // u16 pitch of the transposed horizontally filtered patch: HT[c][r]
+constexpr int kHTCols = 40;
+
+struct DescMaps { CUtensorMap m[kMaxLevels]; };
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (p < 0) p = -p;
@@ -718,15 +737,57 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {     // cv::f
     return a;
 }
 
+// sin and cos of x in [0, 2 pi + eps] in double, error below one ulp (fdlibm kernels after a quadrant reduction)
+__device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
+    const double k = rint(x * 6.36619772367581382433e-01);
+    double r = __fma_rn(-k, 1.57079632679489655800e+00, x);
+    r = __fma_rn(-k, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = __fma_rn(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = __fma_rn(z, ps, 2.75573137070700676789e-06);
+    ps = __fma_rn(z, ps, -1.98412698298579493134e-04);
+    ps = __fma_rn(z, ps, 8.33333333332248946124e-03);
+    ps = __fma_rn(z, ps, -1.66666666666666324348e-01);
+    const double sr = __fma_rn(r * z, ps, r);
+    double pc = __fma_rn(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = __fma_rn(z, pc, -2.75573143513906633035e-07);
+    pc = __fma_rn(z, pc, 2.48015872894767294178e-05);
+    pc = __fma_rn(z, pc, -1.38888888888741095749e-03);
+    pc = __fma_rn(z, pc, 4.16666666666666019037e-02);
+    const double cr = __fma_rn(z * z, pc, __fma_rn(z, -0.5, 1.0));
+    const int q = (int)k & 3;
+    sn = (q & 1) ? cr : sr; cs = (q & 1) ? sr : cr;
+    if (q & 2) sn = -sn;
+    if (q == 1 || q == 2) cs = -cs;
+}
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {          // unsigned pixels x signed coefficients
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(kDescWarps * 32)
 k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
-           const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g,
+           const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ DescMaps maps,
+           int tma_level0, int scratch_base,
            const uint32_t* __restrict__ lvlres, const int* __restrict__ lvlcnt,
            b200_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ counts, int out_cap) {
-    __shared__ __align__(16) uint8_t s_patch[kDescWarps][kPatchW * kPatchPitch + 12];     // rows of 11 words, patch column 0 word-aligned
-    __shared__ __align__(16) uint16_t s_h[kDescWarps][kPatchW * kHPitch];
+    __shared__ __align__(128) uint8_t s_patch[kDescWarps][(kPatchW * kPatchPitch + 127) / 128 * 128];       // TMA destinations: 128-byte aligned
+    __shared__ __align__(16) uint16_t s_ht[kDescWarps][kHTCols * kHTPitch];
+    __shared__ uint32_t s_disc[31 * 8];                       // byte masks of the radius-15 disc: row v + 15, word j <-> u = -15 + 4j .. -12 + 4j
+    __shared__ __align__(8) unsigned long long s_bar[kDescWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 31 * 8; i += kDescWarps * 32) {
+        const int um = c_umax[abs((i >> 3) - 15)];
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int u = -15 + 4 * (i & 7) + k; if (abs(u) <= um) m |= 0xffu << (8 * k); }
+        s_disc[i] = m;
+    }
+    __syncthreads();
+
     const int f = blockIdx.y;
     const int k = blockIdx.x * kDescWarps + warp;            // keypoint index inside the frame (levels concatenated)
     const int* lc = lvlcnt + (long long)f * g.nlevels;
@@ -742,108 +803,116 @@ k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long
     const uint32_t key = lvlres[(long long)f * g.res_per_frame + lg.kp_base + (k - base)];
     const int cx = key & 0xfff, cy = (key >> 12) & 0xfff, resp = key >> 24;
 
-    const uint8_t* im; long long pitch;
-    if (level == 0) { im = img0 + (long long)f * img_frame_stride; pitch = img_row_stride; }
-    else { im = pyr + (long long)f * g.pyr_frame_stride + lg.offset; pitch = lg.pitch; }
-
     uint8_t* P = s_patch[warp];
-    {
-        // 43x43 source patch, re-aligned so that patch column 0 sits on a word boundary.  Interior keypoints (the vast majority)
-        // fetch aligned 32-bit words and funnel-shift them; patches that touch the image border (or an unaligned pitch) go byte by
-        // byte through the REFLECT_101 index map.
-        const int x0 = cx - kPatchR, y0 = cy - kPatchR;
-        const uint8_t* A = im + (long long)y0 * pitch + x0;
-        const int ox = (int)(reinterpret_cast<uintptr_t>(A) & 3);
-        const bool fast = ((pitch & 3) == 0) && x0 >= 3 && y0 >= 0 && cy + kPatchR < lg.h && x0 + 47 < lg.w;
-        uint32_t* P32 = reinterpret_cast<uint32_t*>(P);
-        if (fast) {
-            const uint8_t* A0 = A - ox;
-            const int sh = 8 * ox;
-            for (int idx = lane; idx < kPatchW * 11; idx += 32) {
-                const int r = idx / 11, j = idx - r * 11;
-                const uint32_t* gw = reinterpret_cast<const uint32_t*>(A0 + (long long)r * pitch) + j;
-                P32[idx] = __funnelshift_r(gw[0], gw[1], sh);
-            }
-        } else {
-            for (int idx = lane; idx < kPatchW * kPatchW; idx += 32) {
-                const int r = idx / kPatchW, c = idx - r * kPatchW;
-                const int yy = reflect101(y0 + r, lg.h), xx = reflect101(x0 + c, lg.w);
-                P[r * kPatchPitch + c] = im[(long long)yy * pitch + xx];
-            }
+    const int x0 = cx - kPatchR, y0 = cy - kPatchR;
+    const int ox = x0 & 15;
+    if ((level > 0 || tma_level0) && x0 >= 0 && y0 >= 0 && cx + kPatchR < lg.w && cy + kPatchR < lg.h) {
+        const uint32_t bar = smem_u32(&s_bar[warp]);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(kPatchPitch * kPatchW) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(smem_u32(P)), "l"(reinterpret_cast<uint64_t>(&maps.m[level])), "r"(x0 - ox), "r"(y0),
+                            "r"(level > 0 ? scratch_base + f : f), "r"(bar) : "memory");
         }
+        __syncwarp();
+        asm volatile("{\n.reg .pred p;\nDESC_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra DESC_DONE;\nbra DESC_WAIT;\nDESC_DONE:\n}"
+                     :: "r"(bar) : "memory");
+    } else {
+        const uint8_t* im; long long pitch;
+        if (level == 0) { im = img0 + (long long)f * img_frame_stride; pitch = img_row_stride; }
+        else { im = pyr + (long long)f * g.pyr_frame_stride + lg.offset; pitch = lg.pitch; }
+        for (int idx = lane; idx < kPatchW * kPatchW; idx += 32) {
+            const int r = idx / kPatchW, c = idx - r * kPatchW;
+            const int yy = reflect101(y0 + r, lg.h), xx = reflect101(x0 + c, lg.w);
+            P[r * kPatchPitch + ox + c] = im[(long long)yy * pitch + xx];
+        }
+        __syncwarp();
     }
-    __syncwarp();
+    const uint32_t* P32 = reinterpret_cast<const uint32_t*>(P);
+    const int sh8 = 8 * (ox & 3);
 
-    // IC_Angle (ORBextractor.cc:77-104): lane = u + 15
+    // IC_Angle (ORBextractor.cc:77-104): task = (row v, word j); the word holds u = -15 + 4j .. -12 + 4j of that row
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - kHalfPatch, au = abs(u);
-#pragma unroll 1
-        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = P[(v + kPatchR) * kPatchPitch + u + kPatchR];
-                m10 += u * val; m01 += v * val;
-            }
+    {
+        const int wb = (ox + kPatchR - kHalfPatch) >> 2;                 // word of patch column 6 (u = -15) ...
+        const int sh = 8 * ((ox + kPatchR - kHalfPatch) & 3);            // ... and its byte inside that word
+        for (int t = lane; t < 31 * 8; t += 32) {
+            const int v = (t >> 3) - kHalfPatch, j = t & 7;
+            const uint32_t* w = P32 + (v + kPatchR) * (kPatchPitch / 4) + wb + j;
+            const uint32_t px = __funnelshift_r(w[0], w[1], sh) & s_disc[t];
+            const int u0 = -kHalfPatch + 4 * j;
+            const int ucoef = (u0 & 0xff) | (((u0 + 1) & 0xff) << 8) | (((u0 + 2) & 0xff) << 16) | (((u0 + 3) & 0xff) << 24);
+            m10 = dp4a_us(px, ucoef, m10);
+            m01 += v * (int)__dp4a(px, 0x01010101u, 0u);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // Gaussian (exact integer arithmetic, so any evaluation order gives OpenCV's result): horizontal pass over 43 rows x 37
-    // cols with two dp4a per output (4 outputs per task from 3 aligned words), vertical pass over 37 x 37
-    uint16_t* H = s_h[warp];
+    // Gaussian, horizontal pass over 43 rows x 40 columns (37 used): task = (row, group of 4 outputs); HT[c][r] = sum_k K[k] P[r][c + k]
+    uint16_t* HT = s_ht[warp];
     {
-        const uint32_t* P32 = reinterpret_cast<const uint32_t*>(P);
-        uint32_t* H32 = reinterpret_cast<uint32_t*>(H);
         const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
+        const int wb = ox >> 2;
         for (int idx = lane; idx < kPatchW * 10; idx += 32) {
             const int r = idx / 10, gq = idx - r * 10;
-            const uint32_t w0 = P32[r * 11 + gq], w1 = P32[r * 11 + gq + 1], w2 = P32[r * 11 + gq + 2];   // (+2 may run into the pad: unused lanes)
-            unsigned o[4];
+            const uint32_t* w = P32 + r * (kPatchPitch / 4) + wb + gq;
+            const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];                  // (the last word may lie past the patch: unused bytes)
+            const uint32_t w0 = __funnelshift_r(a0, a1, sh8), w1 = __funnelshift_r(a1, a2, sh8), w2 = __funnelshift_r(a2, a3, sh8);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const uint32_t a4 = __funnelshift_r(w0, w1, 8 * i), b4 = __funnelshift_r(w1, w2, 8 * i);
-                o[i] = __dp4a(a4, K0, __dp4a(b4, K1, 0u));
+                HT[(4 * gq + i) * kHTPitch + r] = (uint16_t)__dp4a(a4, K0, __dp4a(b4, K1, 0u));
             }
-            H32[(r * kHPitch + 4 * gq) >> 1] = o[0] | (o[1] << 16);
-            H32[((r * kHPitch + 4 * gq) >> 1) + 1] = o[2] | (o[3] << 16);
         }
     }
     __syncwarp();
-    uint8_t* Bl = P;                     // the source patch is dead once H exists: reuse its storage
-    for (int idx = lane; idx < kBlurW * kBlurW; idx += 32) {
-        const int r = idx / kBlurW, c = idx - r * kBlurW;
-        const uint16_t* s = H + r * kHPitch + c;       // row r of the blurred patch uses H rows r..r+6
-        const unsigned vsum = 18u * (s[0] + s[6 * kHPitch]) + 34u * (s[kHPitch] + s[5 * kHPitch]) + 48u * (s[2 * kHPitch] + s[4 * kHPitch]) + 56u * s[3 * kHPitch];
-        Bl[idx] = (uint8_t)((vsum + 32768u) >> 16);
+    // vertical pass: task = (column c, row pair p): Bl[2p][c], Bl[2p + 1][c] from HT[c][2p .. 2p + 7] (four aligned words)
+    uint8_t* Bl = P;                     // the source patch is dead once HT exists: reuse its storage
+    {
+        const unsigned K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8), K6 = 18u, K6h = 18u << 24;
+        const uint32_t* HT32 = reinterpret_cast<const uint32_t*>(HT);
+        for (int t = lane; t < kBlurW * 19; t += 32) {
+            const int c = t / 19, p = t - c * 19;
+            const uint32_t* w = HT32 + c * (kHTPitch / 2) + p;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+            unsigned e = __dp2a_lo(w0, K01, 32768u); e = __dp2a_lo(w1, K23, e); e = __dp2a_lo(w2, K45, e); e = __dp2a_lo(w3, K6, e);
+            unsigned o = __dp2a_lo(sh16(w0, w1), K01, 32768u); o = __dp2a_lo(sh16(w1, w2), K23, o); o = __dp2a_lo(sh16(w2, w3), K45, o); o = __dp2a_hi(w3, K6h, o);
+            Bl[(2 * p) * kBlurW + c] = (uint8_t)(e >> 16);
+            if (2 * p + 1 < kBlurW) Bl[(2 * p + 1) * kBlurW + c] = (uint8_t)(o >> 16);
+        }
     }
     __syncwarp();
 
     // steered BRIEF (ORBextractor.cc:107-147); canonical a,b = float(cos/sin(double(angle_rad)))
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
     const float ang = __fmul_rn(angle, factorPI);
-    const float a = __double2float_rn(cos((double)ang)), b = __double2float_rn(sin((double)ang));
+    double sd, cd;
+    sincos_small((double)ang, sd, cd);
+    const float a = __double2float_rn(cd), b = __double2float_rn(sd);
     int val = 0;
 #pragma unroll
     for (int kk = 0; kk < 8; kk++) {
-        const float x0 = (float)__ldg(&g_pattern[(kk * 4 + 0) * 32 + lane]), y0 = (float)__ldg(&g_pattern[(kk * 4 + 1) * 32 + lane]);
-        const float x1 = (float)__ldg(&g_pattern[(kk * 4 + 2) * 32 + lane]), y1 = (float)__ldg(&g_pattern[(kk * 4 + 3) * 32 + lane]);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const float px0 = (float)__ldg(&g_pattern[(kk * 4 + 0) * 32 + lane]), py0 = (float)__ldg(&g_pattern[(kk * 4 + 1) * 32 + lane]);
+        const float px1 = (float)__ldg(&g_pattern[(kk * 4 + 2) * 32 + lane]), py1 = (float)__ldg(&g_pattern[(kk * 4 + 3) * 32 + lane]);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, b), __fmul_rn(py0, a))), c0 = __float2int_rn(__fsub_rn(__fmul_rn(px0, a), __fmul_rn(py0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, b), __fmul_rn(py1, a))), c1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, a), __fmul_rn(py1, b)));
         const int t0 = Bl[(r0 + 18) * kBlurW + c0 + 18], t1 = Bl[(r1 + 18) * kBlurW + c1 + 18];
         val |= (t0 < t1) << kk;
     }
     desc[((long long)f * out_cap + k) * 32 + lane] = (uint8_t)val;
 
     // keypoint record (ORBextractor.cc:837-847,1095-1101)
-    float px = (float)cx, py = (float)cy;
-    if (level != 0) { px = __fmul_rn(px, lg.scale); py = __fmul_rn(py, lg.scale); }
+    float kx = (float)cx, ky = (float)cy;
+    if (level != 0) { kx = __fmul_rn(kx, lg.scale); ky = __fmul_rn(ky, lg.scale); }
     if (lane < 7) {
         uint32_t wv;
         switch (lane) {
-            case 0: wv = __float_as_uint(px); break;
-            case 1: wv = __float_as_uint(py); break;
+            case 0: wv = __float_as_uint(kx); break;
+            case 1: wv = __float_as_uint(ky); break;
             case 2: wv = __float_as_uint(lg.size); break;
             case 3: wv = __float_as_uint(angle); break;
             case 4: wv = __float_as_uint((float)resp); break;
@@ -874,7 +943,7 @@ struct b200_orb_s {
     OrbGeom geom;
     std::vector<CellDesc> cells;
     int pool_cap;
-    FastSmemGeom fsg; size_t fast_smem; FastMaps maps;      // maps.m[l > 0]: level l of the pyramid buffer; m[0] is encoded per call
+    FastSmemGeom fsg; size_t fast_smem; FastMaps maps; DescMaps dmaps;      // maps.m[l > 0]: level l of the pyramid buffer; m[0] is encoded per call
     // device buffers
     uint8_t* d_pyr; ResizeEntry* d_tab; CellDesc* d_cells; uint32_t* d_slots; int* d_cellcnt;
     uint32_t *d_keysA, *d_keysB, *d_lvlres; int* d_lvlcnt; int* d_err;
@@ -1033,7 +1102,14 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
                 sgm.keepw = std::max(sgm.keepw, ih * 3);
             }
             L.box_w = (int)align_up(mrw + 15, 16); L.box_h = mrh;
-            sgm.tile_bytes = std::max(sgm.tile_bytes, (int)align_up((long long)L.box_w * L.box_h, 128));
+        }
+        // one tile pitch for all levels (k_fast is instantiated for 64, 80 and 96 bytes)
+        int tp = 64;
+        for (int l = 0; l < h->nlevels; l++) tp = std::max(tp, g.L[l].box_w);
+        tp = tp <= 64 ? 64 : tp <= 80 ? 80 : 96;
+        for (int l = 0; l < h->nlevels; l++) {
+            g.L[l].box_w = tp;
+            sgm.tile_bytes = std::max(sgm.tile_bytes, (int)align_up((long long)tp * g.L[l].box_h, 128));
         }
         h->fast_smem = (size_t)2 * sgm.tile_bytes + (size_t)kFastWarps * sgm.qcap * 2 + (size_t)sgm.keepw * 4;
     }
@@ -1061,6 +1137,7 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
     for (int l = 1; l < h->nlevels; l++) {
         const LevelGeom& L = g.L[l];
         if ((rc = make_tile_map(&h->maps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, L.box_w, L.box_h))) return rc;
+        if ((rc = make_tile_map(&h->dmaps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, kPatchPitch, kPatchW))) return rc;
     }
     h->cur_w = w; h->cur_h = h_img;
     return B200_OK;
@@ -1099,28 +1176,33 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
     int* d_cellcnt = h->d_cellcnt + (size_t)base * g.total_cells;
     uint32_t* d_lvlres = h->d_lvlres + (size_t)base * g.res_per_frame;
     int* d_lvlcnt = h->d_lvlcnt + (size_t)base * g.nlevels;
+    int tma0_used = 0;
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[0], st));
     for (int l = 1; l < g.nlevels; l++) {
         const LevelGeom& L = g.L[l];
         const LevelGeom& Lp = g.L[l - 1];
         const uint8_t* src = l == 1 ? imgs : d_pyr + Lp.offset;
         const long long srs = l == 1 ? rs : Lp.pitch, sfs = l == 1 ? fs : g.pyr_frame_stride;
-        dim3 grid((L.w + 127) / 128, (L.h + 7) / 8, n), block(32, 8);
+        dim3 grid((L.w + 127) / 128, (L.h + 8 * kPyrRows - 1) / (8 * kPyrRows), n), block(32, 8);
         B200_LAUNCH(k_pyramid, grid, block, 0, st, src, srs, sfs, d_pyr + L.offset, L.pitch, g.pyr_frame_stride,
                     Lp.w, Lp.h, L.w, L.h, h->d_tab + L.xtab, h->d_tab + L.ytab);
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[1], st));
     if (g.total_cells > 0) {
         dim3 grid(g.total_cells, n);
-        static std::atomic<size_t> fast_smem_set(0);
-        if (h->fast_smem > 48 * 1024 && h->fast_smem > fast_smem_set.load()) {
-            B200_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem)); fast_smem_set.store(h->fast_smem);
-        }
         // level 0 = the caller's frames: a tensor map needs a 16-byte aligned pointer and strides (else k_fast stages level 0 byte-wise)
         const long long fs0 = n > 1 ? fs : align_up(rs * (long long)g.L[0].h, 16);
         const int tma0 = ((reinterpret_cast<uintptr_t>(imgs) | (uintptr_t)rs | (uintptr_t)fs0) & 15) == 0;
-        if (tma0) { int rc = make_tile_map(&h->maps.m[0], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, g.L[0].box_w, g.L[0].box_h); if (rc) return rc; }
-        B200_LAUNCH(k_fast, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
+        if (tma0) {
+            int rc = make_tile_map(&h->maps.m[0], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, g.L[0].box_w, g.L[0].box_h);
+            if (!rc) rc = make_tile_map(&h->dmaps.m[0], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, kPatchPitch, kPatchW);
+            if (rc) return rc;
+        }
+        tma0_used = tma0;
+        const int tp = g.L[0].box_w;
+        if (tp == 64) B200_LAUNCH(k_fast<64>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
+        else if (tp == 80) B200_LAUNCH(k_fast<80>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
+        else B200_LAUNCH(k_fast<96>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[2], st));
     {
@@ -1135,7 +1217,7 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[3], st));
     {
         dim3 grid((g.res_per_frame + kDescWarps - 1) / kDescWarps, n);
-        B200_LAUNCH(k_describe, grid, kDescWarps * 32, 0, st, imgs, rs, fs, d_pyr, g, d_lvlres, d_lvlcnt, kps, desc, counts, out_cap);
+        B200_LAUNCH(k_describe, grid, kDescWarps * 32, 0, st, imgs, rs, fs, d_pyr, g, h->dmaps, tma0_used, base, d_lvlres, d_lvlcnt, kps, desc, counts, out_cap);
     }
     if (h->profile) { B200_CUDA(cudaEventRecord(h->ev[4], st)); h->stage_valid = 1; }
     B200_CUDA(cudaGetLastError());
