@@ -243,21 +243,24 @@ __device__ __forceinline__ int dir_delta(int d, int pitch) {
     return dy * pitch + dx;
 }
 
-// Phase A (thread per pixel): list every transition pixel -- foreground with a zero West neighbour (0->1, possible outer-border
-// start) or a zero East neighbour (1->0, possible hole-border start).  CTA-aggregated append, one global atomic per CTA.
+// Phase A (thread per aligned 4-pixel word of the mask image): list every transition pixel -- foreground with a zero West
+// neighbour (0->1, possible outer-border start) or a zero East neighbour (1->0, possible hole-border start).  The tests
+// run byte-parallel on the word; transitions are sparse, so the few hits are appended with a CTA-aggregated atomic.
+// (A foreground pixel without any neighbour has mask 0 like the background: a one-point contour, never a candidate.)
 __global__ void __launch_bounds__(256)
 k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, int* __restrict__ cand, int* __restrict__ ncand,
           int max_cand, int* __restrict__ err) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
     const int P = (y + 1) * g.bpitch + x + kMaskPad;
-    int m = 0;
-    if (x < g.w && y < g.h) m = mask0[(long long)f * g.bframe + P];
-    const bool co = m != 0 && !(m & 16), ch = m != 0 && !(m & 1);
+    uint32_t m = 0;
+    if (x < g.w && y < g.h) m = *reinterpret_cast<const uint32_t*>(mask0 + (long long)f * g.bframe + P);     // bytes past the width are zero
+    const uint32_t nz = (((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u;          // bit 7 of every non-zero byte
+    const uint32_t co = nz & ~((m & 0x10101010u) << 3), ch = nz & ~((m & 0x01010101u) << 7);
     __shared__ int s_n, s_base;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     if (tid == 0) s_n = 0;
     __syncthreads();
-    const int k = (int)co + (int)ch;
+    const int k = __popc(co) + __popc(ch);
     int slot = 0;
     if (k) slot = atomicAdd(&s_n, k);
     __syncthreads();
@@ -267,27 +270,48 @@ k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
         int idx = s_base + slot;
         int* out = cand + (long long)f * max_cand;
         if (idx + k > max_cand) { atomicExch(err, 8); return; }
-        if (co) out[idx++] = P;
-        if (ch) out[idx] = P | (1 << 30);
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            if (co & (0x80u << (8 * b))) out[idx++] = P + b;
+            if (ch & (0x80u << (8 * b))) out[idx++] = (P + b) | (1 << 30);
+        }
     }
 }
 
+// exclusive prefix sums of the (clamped) transition counts: the frames' lists become one work queue for phase B
+__global__ void __launch_bounds__(32)
+k_probe_prefix(const int* __restrict__ ncand, int max_cand, int nframes, int* __restrict__ pref) {
+    const int lane = threadIdx.x;
+    int run = 0;
+    for (int f0 = 0; f0 < nframes; f0 += 32) {
+        const int f = f0 + lane;
+        const int n = f < nframes ? min(ncand[f], max_cand) : 0;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (f < nframes) pref[f] = run + incl - n;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) pref[nframes] = run;
+}
+
 // Phase B (persistent warps, lanes fetch the next transition as soon as they are free, so no lane idles while its
-// neighbours walk long borders).  Per transition:
+// neighbours walk long borders; the transition lists of ALL frames of the call form one queue, so the tail of one frame
+// is filled with the next frame's work).  Per transition:
 //   1. BACKWARDS along the border to the previous transition: if the raster scan sees that one earlier, this cannot be the
 //      border's first transition (this removes every non-topmost pixel of a left edge after one step);
 //   2. FORWARDS until back home (=> it is Suzuki's start: the border is recorded with its length if > 70 points) or until a
 //      transition that the raster scan sees earlier shows up (=> abort).
 __global__ void __launch_bounds__(128)
-k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ cand, const int* __restrict__ ncand,
-          int max_cand, int* __restrict__ nfetch, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts,
+k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ cand, const int* __restrict__ pref,
+          int nframes, int max_cand, int* __restrict__ nfetch, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts,
           int* __restrict__ err) {
-    const int f = blockIdx.y, lane = threadIdx.x & 31;
-    const int ns = min(ncand[f], max_cand);
-    const uint8_t* mask = mask0 + (long long)f * g.bframe;
-    const int* list = cand + (long long)f * max_cand;
+    const int lane = threadIdx.x & 31;
+    const int total = pref[nframes];
+    int fw = 0, lo_w = 0, hi_w = pref[1];                 // warp-uniform window: the frame the queue head is in (the head only moves forward)
     const int limit = 4 * g.max_points;
-    int phase = 0, P = 0, s0 = 0, mykey = 0, p = 0, s = 0, n = 0;
+    const uint8_t* mask = mask0;
+    int f = 0, phase = 0, P = 0, s0 = 0, mykey = 0, p = 0, s = 0, n = 0;
     bool exhausted = false;
     for (;;) {
         const bool need = phase == 0 && !exhausted;
@@ -295,13 +319,18 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
         if (mneed) {
             const int leader = __ffs(mneed) - 1;
             int base = 0;
-            if (lane == leader) base = atomicAdd(nfetch + f, __popc(mneed));
+            if (lane == leader) base = atomicAdd(nfetch, __popc(mneed));
             base = __shfl_sync(0xffffffffu, base, leader);
+            if (base < total) while (base >= hi_w) { fw++; lo_w = hi_w; hi_w = pref[fw + 1]; }
             if (need) {
                 const int i = base + __popc(mneed & ((1u << lane) - 1));
-                if (i >= ns) exhausted = true;
+                if (i >= total) exhausted = true;
                 else {
-                    const int e = list[i];
+                    int fl = fw, lo = lo_w, hi = hi_w;
+                    while (i >= hi) { fl++; lo = hi; hi = pref[fl + 1]; }          // the warp's batch straddles a frame boundary
+                    f = fl;
+                    mask = mask0 + (long long)f * g.bframe;
+                    const int e = cand[(long long)f * max_cand + (i - lo)];
                     const bool hole = (e >> 30) & 1;
                     P = e & 0x3fffffff;
                     const int m0 = mask[P];
@@ -1101,6 +1130,7 @@ struct b200_aruco_s {
     ContourDesc* d_desc; short2* d_pts; float* d_scratch;
     Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
     int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_nfetch, *d_err;
+    int* d_pref;                 // prefix sums of the transition counts (one work queue per call; calls on disjoint slot ranges use disjoint parts)
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
@@ -1212,6 +1242,7 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
     h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_err = h->d_nfetch + B;
     cudaMemset(h->d_ncont, 0, 6 * B * 4 + 4);
+    if (cudaMalloc((void**)&h->d_pref, (2 * B + 2) * 4) != cudaSuccess) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
     if ((rc = aruco_geometry(h, max_w, max_h))) { b200_aruco_destroy(h); return rc; }
     *out = h;
     return B200_OK;
@@ -1221,7 +1252,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_pref);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1273,12 +1304,13 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
         dim3 gp((g.lw[l] + 31) / 32, (g.lh[l] + 7) / 8, n);
         B200_LAUNCH(k_halfpyr, gp, blk, 0, st, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
     }
-    dim3 gm((w + 31) / 32, (hh + 7) / 8, n);
+    dim3 gm((w + 127) / 128, (hh + 7) / 8, n);
     B200_LAUNCH(k_probe_a, gm, blk, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, h->d_err);
     {
-        // enough persistent warps to fill the 148 SMs whatever the batch size
-        dim3 gb(std::max(4, std::min(64, (148 * 16 + n - 1) / n)), n);
-        B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
+        // one work queue over all frames; persistent CTAs, all resident at once (148 SMs x 16 CTAs of 128 threads)
+        B200_LAUNCH(k_probe_prefix, 1, 32, 0, st, d_nsurv, h->max_surv, n, h->d_pref + 2 * base);
+        const int ctas = std::max(4, std::min(148 * 16, n * 64));
+        B200_LAUNCH(k_probe_b, ctas, 128, 0, st, d_mask, g, d_surv, h->d_pref + 2 * base, n, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
     }
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
     {
