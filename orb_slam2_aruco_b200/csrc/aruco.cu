@@ -278,98 +278,110 @@ k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
     }
 }
 
-// exclusive prefix sums of the (clamped) transition counts: the frames' lists become one work queue for phase B
-__global__ void __launch_bounds__(32)
-k_probe_prefix(const int* __restrict__ ncand, int max_cand, int nframes, int* __restrict__ pref) {
-    const int lane = threadIdx.x;
-    int run = 0;
-    for (int f0 = 0; f0 < nframes; f0 += 32) {
-        const int f = f0 + lane;
-        const int n = f < nframes ? min(ncand[f], max_cand) : 0;
-        int incl = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (f < nframes) pref[f] = run + incl - n;
-        run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) pref[nframes] = run;
-}
-
-// Phase B (persistent warps, lanes fetch the next transition as soon as they are free, so no lane idles while its
-// neighbours walk long borders; the transition lists of ALL frames of the call form one queue, so the tail of one frame
-// is filled with the next frame's work).  Per transition:
-//   1. BACKWARDS along the border to the previous transition: if the raster scan sees that one earlier, this cannot be the
-//      border's first transition (this removes every non-topmost pixel of a left edge after one step);
-//   2. FORWARDS until back home (=> it is Suzuki's start: the border is recorded with its length if > 70 points) or until a
-//      transition that the raster scan sees earlier shows up (=> abort).
-__global__ void __launch_bounds__(128)
-k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ cand, const int* __restrict__ pref,
-          int nframes, int max_cand, int* __restrict__ nfetch, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts,
-          int* __restrict__ err) {
-    const int lane = threadIdx.x & 31;
-    const int total = pref[nframes];
-    int fw = 0, lo_w = 0, hi_w = pref[1];                 // warp-uniform window: the frame the queue head is in (the head only moves forward)
+// Phase B1 (thread per transition, grid-stride inside a frame; every lane runs the same code): the probe's own step, then
+// BACKWARDS along the border (Suzuki's successor rule, inverted, on the masks) to the previous transition.  If the raster
+// scan sees that one earlier, this transition cannot be the border's first one (this removes every non-topmost pixel of a
+// left edge after one step).  Survivors are appended to the second list with one atomic per warp.
+__global__ void __launch_bounds__(256)
+k_probe_b1(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ cand, const int* __restrict__ ncand,
+           int max_cand, int* __restrict__ surv, int* __restrict__ nsurv, int* __restrict__ err) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int ns = min(ncand[f], max_cand);
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    const int* list = cand + (long long)f * max_cand;
+    int* out = surv + (long long)f * max_cand;
     const int limit = 4 * g.max_points;
-    const uint8_t* mask = mask0;
-    int f = 0, phase = 0, P = 0, s0 = 0, mykey = 0, p = 0, s = 0, n = 0;
-    bool exhausted = false;
-    for (;;) {
-        const bool need = phase == 0 && !exhausted;
-        const unsigned mneed = __ballot_sync(0xffffffffu, need);
-        if (mneed) {
-            const int leader = __ffs(mneed) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(nfetch, __popc(mneed));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base < total) while (base >= hi_w) { fw++; lo_w = hi_w; hi_w = pref[fw + 1]; }
-            if (need) {
-                const int i = base + __popc(mneed & ((1u << lane) - 1));
-                if (i >= total) exhausted = true;
-                else {
-                    int fl = fw, lo = lo_w, hi = hi_w;
-                    while (i >= hi) { fl++; lo = hi; hi = pref[fl + 1]; }          // the warp's batch straddles a frame boundary
-                    f = fl;
-                    mask = mask0 + (long long)f * g.bframe;
-                    const int e = cand[(long long)f * max_cand + (i - lo)];
-                    const bool hole = (e >> 30) & 1;
-                    P = e & 0x3fffffff;
-                    const int m0 = mask[P];
-                    // Suzuki's first neighbour search: clockwise from NW (outer) / SE (hole) over 7 directions = highest set bit of
-                    // the mask rotated so that the first direction examined sits at bit 7 (W resp. E is known to be 0)
-                    const int from = hole ? 7 : 3;
-                    const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
-                    if (rot != 0) {                            // else: isolated pixel, a one-point contour
-                        s0 = (from + 1 + (31 - __clz(rot))) & 7;
-                        mykey = P + (hole ? 1 : 0);
-                        const Step st = next_step(m0, s0);
-                        // own step: a hole probe whose sweep also passes West belongs to the outer probe of the same pixel
-                        if (!(step_key(P, s0, st.k) < mykey)) { phase = 1; p = P; s = s0; n = 0; }
+    for (int i0 = blockIdx.x * blockDim.x; i0 < ns; i0 += gridDim.x * blockDim.x) {        // warp-uniform trip count
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        int e = 0;
+        if (i < ns) {
+            e = list[i];
+            const bool hole = (e >> 30) & 1;
+            const int P = e & 0x3fffffff;
+            const int m0 = mask[P];
+            // Suzuki's first neighbour search: clockwise from NW (outer) / SE (hole) over 7 directions = highest set bit of
+            // the mask rotated so that the first direction examined sits at bit 7 (W resp. E is known to be 0)
+            const int from = hole ? 7 : 3;
+            const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
+            if (rot != 0) {                                // else: isolated pixel, a one-point contour
+                const int s0 = (from + 1 + (31 - __clz(rot))) & 7;
+                const int mykey = P + (hole ? 1 : 0);
+                const Step st = next_step(m0, s0);
+                // own step: a hole probe whose sweep also passes West belongs to the outer probe of the same pixel
+                if (!(step_key(P, s0, st.k) < mykey)) {
+                    int p = P, s = s0, n = 0;
+                    for (;;) {
+                        const int q = p + dir_delta(s, g.bpitch), d = (s + 4) & 7;
+                        int sq, kq;
+                        prev_step(mask[q], d, sq, kq);
+                        p = q; s = sq;
+                        if (p == P && s == s0) { keep = true; break; }             // all the way round: the border's only transition
+                        const int key = step_key(p, s, kq);
+                        if (key < mykey) break;
+                        if (key != 0x7fffffff) { keep = true; break; }
+                        if (++n > limit) { atomicExch(err, 3); break; }
                     }
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, phase != 0 || !exhausted)) break;
-        if (phase == 1) {
-            const int q = p + dir_delta(s, g.bpitch), d = (s + 4) & 7;
-            int sq, kq;
-            prev_step(mask[q], d, sq, kq);
-            p = q; s = sq;
-            if (p == P && s == s0) { phase = 2; n = 0; }                 // all the way round: the border's only transition
-            else {
-                const int key = step_key(p, s, kq);
-                if (key < mykey) phase = 0;
-                else if (key != 0x7fffffff) { phase = 2; p = P; s = s0; n = 0; }
-                else if (++n > limit) { atomicExch(err, 3); phase = 0; }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(nsurv + f, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) out[base + __popc(m & ((1u << lane) - 1))] = e;
+        }
+    }
+}
+
+// Phase B2 (persistent warps over the survivors; lanes refill in batches so that the refill code runs rarely and every lane
+// spends its iterations in the same loop body): FORWARDS until back home (=> it is Suzuki's start: the border is recorded
+// with its length if > 70 points) or until a transition that the raster scan sees earlier shows up (=> abort).
+__global__ void __launch_bounds__(128)
+k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ surv, const int* __restrict__ nsurv,
+          int max_cand, int* __restrict__ nfetch, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts,
+          int* __restrict__ err) {
+    const int f = blockIdx.x, lane = threadIdx.x & 31;
+    const int ns = min(nsurv[f], max_cand);
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    const int* list = surv + (long long)f * max_cand;
+    const int limit = 4 * g.max_points;
+    int P = 0, s0 = 0, mykey = 0, p = 0, s = 0, n = 0;
+    bool busy = false, exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        // refill when a quarter of the lanes is idle (or nobody is walking any more)
+        if (!exhausted && (__popc(idle) >= 8 || idle == 0xffffffffu)) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(nfetch + f, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(idle) >= ns) exhausted = true;                // warp-uniform: the list is (about to be) empty
+            if (!busy) {
+                const int i = base + __popc(idle & ((1u << lane) - 1));
+                if (i < ns) {
+                    const int e = list[i];
+                    const bool hole = (e >> 30) & 1;
+                    P = e & 0x3fffffff;
+                    const int m0 = mask[P];
+                    const int from = hole ? 7 : 3;
+                    const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
+                    s0 = (from + 1 + (31 - __clz(rot))) & 7;                // rot != 0: phase B1 kept it
+                    mykey = P + (hole ? 1 : 0);
+                    p = P; s = s0; n = 0; busy = true;
+                }
             }
-        } else if (phase == 2) {
+        }
+        if (!__any_sync(0xffffffffu, busy)) { if (exhausted) break; else continue; }
+        if (busy) {
             const Step st = next_step(mask[p], s);
-            if (n > 0 && step_key(p, s, st.k) < mykey) phase = 0;
+            if (n > 0 && step_key(p, s, st.k) < mykey) busy = false;
             else {
                 p += dir_delta(st.d, g.bpitch);
                 s = (st.d + 4) & 7;
                 n++;
                 if (p == P && s == s0) {
-                    phase = 0;
+                    busy = false;
                     if (n > kMinContour) {
                         const int idx = atomicAdd(ncont + f, 1);
                         if (idx >= g.max_contours) atomicExch(err, 4);
@@ -379,7 +391,7 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
                             else { ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off; desc[(long long)f * g.max_contours + idx] = c; }
                         }
                     }
-                } else if (n > limit) { atomicExch(err, 3); phase = 0; }
+                } else if (n > limit) { atomicExch(err, 3); busy = false; }
             }
         }
     }
@@ -1130,7 +1142,7 @@ struct b200_aruco_s {
     ContourDesc* d_desc; short2* d_pts; float* d_scratch;
     Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
     int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_nfetch, *d_err;
-    int* d_pref;                 // prefix sums of the transition counts (one work queue per call; calls on disjoint slot ranges use disjoint parts)
+    int* d_surv2; int* d_nsurv2; size_t cap_surv2;      // transitions that survive the backward check (phase B1)
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
@@ -1206,6 +1218,7 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     B200_CUDA(cudaMemset(h->d_mask, 0, (size_t)g.bframe * B));       // the 1-px zero frame is never written afterwards
     h->max_surv = std::max(1024, w * hh);              // transition list: at most two entries per foreground pixel
     if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int) * (size_t)h->max_surv * B))) return rc;
+    if ((rc = ensure_buf(h->d_surv2, h->cap_surv2, sizeof(int) * (size_t)h->max_surv * B))) return rc;
     if ((rc = ensure_buf(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame * B))) return rc;
     if ((rc = ensure_buf(h->d_desc, h->cap_desc, sizeof(ContourDesc) * (size_t)g.max_contours * B))) return rc;
     if ((rc = ensure_buf(h->d_pts, h->cap_pts, sizeof(short2) * (size_t)g.max_points * B))) return rc;
@@ -1238,11 +1251,10 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     ok = ok && cudaMalloc((void**)&h->d_cand, sizeof(Candidate) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_kept, sizeof(Kept) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_dec, sizeof(Decoded) * kMaxCand * B) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&h->d_ncont, 6 * B * 4 + 4) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_ncont, 7 * B * 4 + 4) == cudaSuccess;
     if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
-    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_err = h->d_nfetch + B;
-    cudaMemset(h->d_ncont, 0, 6 * B * 4 + 4);
-    if (cudaMalloc((void**)&h->d_pref, (2 * B + 2) * 4) != cudaSuccess) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
+    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_nsurv2 = h->d_nfetch + B; h->d_err = h->d_nsurv2 + B;
+    cudaMemset(h->d_ncont, 0, 7 * B * 4 + 4);
     if ((rc = aruco_geometry(h, max_w, max_h))) { b200_aruco_destroy(h); return rc; }
     *out = h;
     return B200_OK;
@@ -1252,7 +1264,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_pref);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1282,11 +1294,12 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     if (rs < w || (n > 1 && fs < rs * (hh - 1) + w)) return fail(B200_EINVAL, "bad %s", "strides");
     if ((rc = aruco_geometry(h, w, hh))) return rc;
     const ArucoGeom& g = h->geom;
-    // the six per-frame counter arrays are one [6][max_batch] block: clear this call's columns
-    B200_CUDA(cudaMemset2DAsync(h->d_ncont + base, (size_t)h->max_batch * 4, 0, (size_t)n * 4, 6, st));
+    // the seven per-frame counter arrays are one [7][max_batch] block: clear this call's columns
+    B200_CUDA(cudaMemset2DAsync(h->d_ncont + base, (size_t)h->max_batch * 4, 0, (size_t)n * 4, 7, st));
     uint8_t* d_mask = h->d_mask + (size_t)base * g.bframe;
     uint8_t* d_pyr = h->d_pyr + (size_t)base * g.pyr_frame;
     int* d_surv = h->d_surv + (size_t)base * h->max_surv;
+    int* d_surv2 = h->d_surv2 + (size_t)base * h->max_surv;
     ContourDesc* d_desc = h->d_desc + (size_t)base * g.max_contours;
     short2* d_pts = h->d_pts + (size_t)base * g.max_points;
     float* d_scratch = h->d_scratch + 3 * (size_t)base * g.max_points;
@@ -1294,7 +1307,7 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     Kept* d_kept = h->d_kept + (size_t)base * kMaxCand;
     Decoded* d_dec = h->d_dec + (size_t)base * kMaxCand;
     int *d_ncont = h->d_ncont + base, *d_npts = h->d_npts + base, *d_ncand = h->d_ncand + base, *d_nkept = h->d_nkept + base,
-        *d_nsurv = h->d_nsurv + base, *d_nfetch = h->d_nfetch + base;
+        *d_nsurv = h->d_nsurv + base, *d_nfetch = h->d_nfetch + base, *d_nsurv2 = h->d_nsurv2 + base;
     dim3 blk(32, 8);
     dim3 gt((w + kThrTW - 1) / kThrTW, (hh + kThrTH - 1) / kThrTH, n);
     B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, d_mask);
@@ -1307,10 +1320,11 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     dim3 gm((w + 127) / 128, (hh + 7) / 8, n);
     B200_LAUNCH(k_probe_a, gm, blk, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, h->d_err);
     {
-        // one work queue over all frames; persistent CTAs, all resident at once (148 SMs x 16 CTAs of 128 threads)
-        B200_LAUNCH(k_probe_prefix, 1, 32, 0, st, d_nsurv, h->max_surv, n, h->d_pref + 2 * base);
-        const int ctas = std::max(4, std::min(148 * 16, n * 64));
-        B200_LAUNCH(k_probe_b, ctas, 128, 0, st, d_mask, g, d_surv, h->d_pref + 2 * base, n, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
+        dim3 g1(16, n);
+        B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err);
+        // persistent CTAs, about one wave of 148 SMs x 16 CTAs; frames are the fast grid index
+        dim3 gb(n, std::max(1, std::min(64, (148 * 16) / n)));
+        B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
     }
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
     {
