@@ -53,6 +53,13 @@ typedef struct b200_marker {
     float xy[8];
 } b200_marker;
 
+/* Marker pose (aruco::Marker::Rvec / Tvec, Thirdparty/aruco/aruco/marker.h:47-59): both IPPE solutions, the one with the
+ * smaller reprojection error first, and both errors (their ratio is the quality test of src/Frame.cc:155-177). */
+typedef struct b200_marker_pose {
+    float rvec[3], tvec[3], err1;
+    float rvec2[3], tvec2[3], err2;
+} b200_marker_pose;
+
 typedef struct b200_orb_s*   b200_orb_t;
 typedef struct b200_aruco_s* b200_aruco_t;
 
@@ -152,6 +159,19 @@ int b200_aruco_check(b200_aruco_t h, void* stream);
 int b200_aruco_debug(b200_aruco_t h, int frame, int32_t* out4, float* corners, int32_t* ids, int cap);
 int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
                            b200_marker* markers, int32_t* counts);
+
+
+/* ---------------------------------------------------------------- marker pose -------------------- */
+/* aruco::Marker::calculateExtrinsics(markerSizeMeters, CameraMatrix, Distorsion) (Thirdparty/aruco/aruco/marker.cpp:322-343)
+ * == aruco::solvePnP -> IPPE::PoseSolver::solveGeneric (Thirdparty/aruco/aruco/ippe.cpp:72-169) for every marker of a
+ * batch: markers [n_batch][marker_cap] and counts [n_batch] as written by b200_aruco_detect (device pointers),
+ * cam9 = fx fy cx cy k1 k2 p1 p2 k3 (HOST pointer: the reference's float camera matrix and distortion vector),
+ * poses [n_batch][marker_cap] (device).  marker_size <= 0 or fx/fy == 0 -> B200_EINVAL (marker.cpp:309-333 throws). */
+int b200_aruco_pose(const b200_marker* markers, const int32_t* counts, int n_batch, int marker_cap, float marker_size,
+                    const float* cam9, b200_marker_pose* poses, int device, void* stream);
+/* Same for a host array of n_markers markers (the adapter's detect(image, cameraParams, markerSize) and aruco::solvePnP). */
+int b200_aruco_pose_host(const b200_marker* markers, int n_markers, float marker_size, const float* cam9,
+                         b200_marker_pose* poses, int device);
 
 #ifdef __cplusplus
 }

@@ -189,13 +189,74 @@ protected:
 
 namespace aruco {
 
-// aruco::Marker essentials (marker.h:47-59): std::vector<cv::Point2f> of 4 corners + id; ordered by id
+// aruco::CameraParameters essentials (cameraparameters.h:46-60): float camera matrix (fx fy cx cy) and distortion k1 k2 p1 p2 k3
+class CameraParameters {
+public:
+    float fx, fy, cx, cy, dist[5];
+    int width, height;                     // CamSize
+    CameraParameters() : fx(0), fy(0), cx(0), cy(0), dist{0, 0, 0, 0, 0}, width(-1), height(-1) {}
+    // setParams(cv::Mat cameraMatrix, cv::Mat distorsionCoeff, cv::Size size) (cameraparameters.h:83), on plain numbers
+    void setParams(float fx_, float fy_, float cx_, float cy_, const float* distorsion, int ndist, int w, int h) {
+        fx = fx_; fy = fy_; cx = cx_; cy = cy_;
+        for (int i = 0; i < 5; i++) dist[i] = (distorsion && i < ndist) ? distorsion[i] : 0.f;
+        width = w; height = h;
+    }
+#ifndef B200SLAM_NO_OPENCV
+    void setParams(const cv::Mat& K, const cv::Mat& D, cv::Size size) {
+        cv::Mat k32, d32;
+        K.convertTo(k32, CV_32F); D.convertTo(d32, CV_32F);
+        float d[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < (int)d32.total() && i < 5; i++) d[i] = d32.ptr<float>(0)[i];
+        setParams(k32.at<float>(0, 0), k32.at<float>(1, 1), k32.at<float>(0, 2), k32.at<float>(1, 2), d, 5, size.width, size.height);
+    }
+#endif
+    bool isValid() const { return fx != 0 && fy != 0; }
+    void cam9(float* out) const { out[0] = fx; out[1] = fy; out[2] = cx; out[3] = cy; for (int i = 0; i < 5; i++) out[4 + i] = dist[i]; }
+};
+
+// aruco::Marker essentials (marker.h:47-59): std::vector<cv::Point2f> of 4 corners + id + ssize + Rvec/Tvec; ordered by id
 class Marker : public std::vector<cv::Point2f> {
 public:
     int id;
     float ssize;
-    Marker() : id(-1), ssize(-1) {}
+#ifndef B200SLAM_NO_OPENCV
+    cv::Mat Rvec, Tvec;                    // 3x1 CV_32F once calculateExtrinsics ran (marker.cpp:337-338)
+#else
+    float Rvec[3], Tvec[3];
+#endif
+    float pose2_rvec[3], pose2_tvec[3], err1, err2;      // the second IPPE solution and both reprojection errors (Frame.cc:155-177)
+    Marker() : id(-1), ssize(-1), err1(-1), err2(-1) {
+#ifdef B200SLAM_NO_OPENCV
+        for (int i = 0; i < 3; i++) Rvec[i] = Tvec[i] = 0;
+#endif
+        for (int i = 0; i < 3; i++) pose2_rvec[i] = pose2_tvec[i] = 0;
+    }
     bool operator<(const Marker& m) const { return id < m.id; }
+    bool isValid() const { return id != -1 && size() == 4; }
+
+    // void calculateExtrinsics(float markerSize, const CameraParameters& CP, bool setYPerpendicular = false) (marker.h:98-99)
+    void calculateExtrinsics(float markerSizeMeters, const CameraParameters& CP, bool setYPerpendicular = false, int device = 0) {
+        if (!isValid()) throw std::runtime_error("!isValid(): invalid marker. It is not possible to calculate extrinsics");
+        if (markerSizeMeters <= 0) throw std::runtime_error("markerSize<=0: invalid markerSize");
+        if (!CP.isValid()) throw std::runtime_error("!CP.isValid(): invalid camera parameters. It is not possible to calculate extrinsics");
+        if (setYPerpendicular) throw std::runtime_error("b200slam: setYPerpendicular is not on the reference's path (src/Frame.cc:142)");
+        b200_marker m; m.id = id;
+        for (int k = 0; k < 4; k++) { m.xy[2 * k] = (*this)[k].x; m.xy[2 * k + 1] = (*this)[k].y; }
+        float cam[9]; CP.cam9(cam);
+        b200_marker_pose p;
+        b200slam_detail::check(b200_aruco_pose_host(&m, 1, markerSizeMeters, cam, &p, device));
+        setPose(p, markerSizeMeters);
+    }
+    void setPose(const b200_marker_pose& p, float markerSizeMeters) {
+#ifndef B200SLAM_NO_OPENCV
+        Rvec.create(3, 1, CV_32F); Tvec.create(3, 1, CV_32F);
+        for (int i = 0; i < 3; i++) { Rvec.at<float>(i) = p.rvec[i]; Tvec.at<float>(i) = p.tvec[i]; }
+#else
+        for (int i = 0; i < 3; i++) { Rvec[i] = p.rvec[i]; Tvec[i] = p.tvec[i]; }
+#endif
+        for (int i = 0; i < 3; i++) { pose2_rvec[i] = p.rvec2[i]; pose2_tvec[i] = p.tvec2[i]; }
+        err1 = p.err1; err2 = p.err2; ssize = markerSizeMeters;
+    }
 };
 
 class MarkerDetector {
@@ -224,10 +285,16 @@ public:
     }
 
     // std::vector<aruco::Marker> detect(const cv::Mat& input) (markerdetector.h:276); markers sorted by id.
-    // Rvec/Tvec (IPPE pose) are not filled: the pose step stays on the host.
-    std::vector<Marker> detect(const cv::Mat& input) {
+    std::vector<Marker> detect(const cv::Mat& input) { return detect(input, CameraParameters(), -1.f); }
+
+    // std::vector<aruco::Marker> detect(const cv::Mat& input, const CameraParameters& camParams, float markerSizeMeters,
+    //                                   bool setYPerpendicular = false) (markerdetector.h:277-278) -- the call of src/Frame.cc:142.
+    // With valid camera parameters and a positive marker size every marker gets Rvec / Tvec / ssize
+    // (markerdetector_impl.cpp:8772 -> marker.cpp:322-343 -> ippe.cpp:90-100), computed on the device for all markers at once.
+    std::vector<Marker> detect(const cv::Mat& input, const CameraParameters& camParams, float markerSizeMeters, bool setYPerpendicular = false) {
         if (input.empty()) return std::vector<Marker>();
         if (input.type() != CV_8UC1) throw std::runtime_error("b200slam: detect expects a CV_8UC1 image");
+        if (setYPerpendicular) throw std::runtime_error("b200slam: setYPerpendicular is not on the reference's path (src/Frame.cc:142)");
         ensure(input.cols, input.rows);
         const int cap = b200_aruco_max_markers(h_);
         std::vector<b200_marker> m(cap);
@@ -237,6 +304,12 @@ public:
         for (int i = 0; i < n; i++) {
             out[i].id = m[i].id;
             for (int k = 0; k < 4; k++) out[i].push_back(cv::Point2f(m[i].xy[2 * k], m[i].xy[2 * k + 1]));
+        }
+        if (n > 0 && camParams.isValid() && markerSizeMeters > 0) {
+            float cam[9]; camParams.cam9(cam);
+            std::vector<b200_marker_pose> p(n);
+            b200slam_detail::check(b200_aruco_pose_host(m.data(), n, markerSizeMeters, cam, p.data(), device_));
+            for (int i = 0; i < n; i++) out[i].setPose(p[i], markerSizeMeters);
         }
         return out;
     }

@@ -70,6 +70,10 @@ void oracle_warp_perspective(const uint8_t* src, int sw, int sh, uint8_t* dst, i
 int oracle_otsu(const uint8_t* img, int w, int h);
 void oracle_solve_svd(const float* A, const float* b, int m, int n, float* x);
 
+// ---- marker pose: restatement of aruco::Marker::calculateExtrinsics / IPPE (Thirdparty/aruco/aruco/ippe.cpp) ----------
+// corners [4][2], cam9 = fx fy cx cy k1 k2 p1 p2 k3, out14 = rvec1[3] tvec1[3] err1 rvec2[3] tvec2[3] err2
+void oracle_ippe_marker_pose(const float* corners, float msize, const double* cam9, double* out14);
+
 #ifdef __cplusplus
 }
 #endif

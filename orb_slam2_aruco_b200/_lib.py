@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(HERE, "libb200slam.so")
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])
 MARKER_DTYPE = np.dtype([("id", "<i4"), ("xy", "<f4", (8,))])
-assert KP_DTYPE.itemsize == 28 and MARKER_DTYPE.itemsize == 36
+POSE_DTYPE = np.dtype([("rvec", "<f4", (3,)), ("tvec", "<f4", (3,)), ("err1", "<f4"), ("rvec2", "<f4", (3,)), ("tvec2", "<f4", (3,)), ("err2", "<f4")])
+assert KP_DTYPE.itemsize == 28 and MARKER_DTYPE.itemsize == 36 and POSE_DTYPE.itemsize == 56
 
 OK, EINVAL, ENODEV, ECUDA, ECAPACITY, ENOMEM = 0, -1, -2, -3, -4, -5
 _NAMES = {0: "B200_OK", -1: "B200_EINVAL", -2: "B200_ENODEV", -3: "B200_ECUDA", -4: "B200_ECAPACITY", -5: "B200_ENOMEM"}
@@ -62,6 +63,8 @@ def lib():
         L.b200_aruco_detect.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp]
         L.b200_aruco_debug.argtypes = [vp, i32, vp, vp, vp, i32]
         L.b200_aruco_detect_host.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp]
+        L.b200_aruco_pose.argtypes = [vp, vp, i32, i32, f32, vp, vp, i32, vp]
+        L.b200_aruco_pose_host.argtypes = [vp, i32, f32, vp, vp, i32]
         _lib = L
     return _lib
 

@@ -251,13 +251,36 @@ class ORBmatcher:
         return bi, bd, sd
 
 
+class CameraParameters:
+    """aruco::CameraParameters essentials (Thirdparty/aruco/aruco/cameraparameters.h): 3x3 camera matrix + distortion
+    (k1 k2 p1 p2 [k3]), both float like the reference's mK / mDistCoef (src/Frame.cc:132)."""
+
+    def __init__(self, camera_matrix, distortion=None, cam_size=None):
+        K = np.asarray(camera_matrix, np.float32).reshape(3, 3)
+        d = np.zeros(5, np.float32)
+        if distortion is not None:
+            dd = np.asarray(distortion, np.float32).ravel()
+            d[:min(5, len(dd))] = dd[:5]
+        self.CameraMatrix, self.Distorsion, self.CamSize = K, d, cam_size
+
+    def isValid(self):
+        return self.CameraMatrix[0, 0] != 0 and self.CameraMatrix[1, 1] != 0
+
+    def cam9(self):
+        K = self.CameraMatrix
+        return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2], *self.Distorsion], np.float32)
+
+
 class Marker:
-    """aruco::Marker essentials (Thirdparty/aruco/aruco/marker.h:47-59): id + 4 corners, ordered by id"""
-    __slots__ = ("id", "corners")
+    """aruco::Marker essentials (Thirdparty/aruco/aruco/marker.h:47-59): id + 4 corners, ordered by id; Rvec / Tvec / ssize
+    once extrinsics have been computed (marker.cpp:322-343), plus the second IPPE solution and both reprojection errors"""
+    __slots__ = ("id", "corners", "Rvec", "Tvec", "ssize", "Rvec2", "Tvec2", "err1", "err2")
 
     def __init__(self, id, corners):
         self.id = int(id)
         self.corners = np.asarray(corners, np.float32).reshape(4, 2)
+        self.Rvec = self.Tvec = self.Rvec2 = self.Tvec2 = None
+        self.ssize, self.err1, self.err2 = -1.0, None, None
 
     def __lt__(self, other):
         return self.id < other.id
@@ -308,12 +331,31 @@ class MarkerDetector:
         except Exception:
             pass
 
-    def detect(self, image):
-        """std::vector<aruco::Marker> detect(const cv::Mat&) (markerdetector.h:276): markers sorted by id"""
+    def detect(self, image, camera_params=None, marker_size=-1.0):
+        """std::vector<aruco::Marker> detect(const cv::Mat&, const CameraParameters&, float markerSizeMeters)
+        (markerdetector.h:276-278): markers sorted by id; with valid camera parameters and a positive marker size the
+        extrinsics of every marker are filled in (markerdetector_impl.cpp:8772 -> marker.cpp:322-343)"""
         image = np.asarray(image)
         assert image.dtype == np.uint8 and image.ndim == 2
         m, c = self.detect_batch(image[None])
-        return [Marker(r["id"], r["xy"]) for r in m[0, :c[0]]]
+        out = [Marker(r["id"], r["xy"]) for r in m[0, :c[0]]]
+        if camera_params is not None and camera_params.isValid() and marker_size > 0 and out:
+            poses = self.estimate_poses(m[0, :c[0]], marker_size, camera_params)
+            for mk, p in zip(out, poses):
+                mk.Rvec, mk.Tvec, mk.Rvec2, mk.Tvec2 = p["rvec"].copy(), p["tvec"].copy(), p["rvec2"].copy(), p["tvec2"].copy()
+                mk.err1, mk.err2, mk.ssize = float(p["err1"]), float(p["err2"]), float(marker_size)
+        return out
+
+    def estimate_poses(self, markers, marker_size, camera_params):
+        """both IPPE poses + reprojection errors of an array of markers (aruco::solvePnP, ippe.cpp:72-88; the ratio
+        err1 / err2 < 0.7 is the reference's test for a good marker, src/Frame.cc:172-174)"""
+        from ._lib import POSE_DTYPE
+        markers = np.ascontiguousarray(markers)
+        assert markers.dtype == MARKER_DTYPE
+        poses = np.zeros(len(markers), POSE_DTYPE)
+        cam = np.ascontiguousarray(camera_params.cam9(), np.float32)
+        check(lib().b200_aruco_pose_host(ptr(markers), len(markers), float(marker_size), ptr(cam), ptr(poses), self._device))
+        return poses
 
     def detect_batch(self, images):
         images = np.asarray(images)
@@ -377,7 +419,7 @@ class FrontEnd:
         ex, det = self.extractor, self.detector
         ex._ensure(w, h, n)
         if det is not None:
-            det._ensure(w, h, min(n, 32) if n > 16 else n)
+            det._ensure(w, h, n)
         if out is None:
             out = self.alloc_outputs(n)
         do_match = ref_desc is not None and self.matcher is not None

@@ -23,7 +23,10 @@ int main(int argc, char** argv) {
         detector.setDictionary(argv[4], 0.f);                             // Frame.cc:133
         detector.setDetectionMode(aruco::MarkerDetector::DM_NORMAL);      // Frame.cc:134
         detector.setCornerRefinementMethod(aruco::MarkerDetector::CORNER_LINES);
-        std::vector<aruco::Marker> markers = detector.detect(im);         // Frame.cc:142
+        aruco::CameraParameters cam;                                      // Frame.cc:132: setParams(mK, mDistCoef, Size(1280,720))
+        const float distortion[5] = {0.2624f, -0.9531f, -0.0054f, 0.0026f, 1.1633f};
+        cam.setParams(517.3f, 516.5f, 318.6f, 255.3f, distortion, 5, 1280, 720);
+        std::vector<aruco::Marker> markers = detector.detect(im, cam, 0.187f);   // Frame.cc:142 (mMarkerSize = 0.187, Frame.cc:131)
         ORB_SLAM2::ORBmatcher matcher(0.7f, true);                        // Tracking.cc:917
         std::vector<int> matches;
         const int nm = matcher.SearchByBoW(desc, keys, desc, keys, matches);
@@ -35,6 +38,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < desc.rows; i++) fwrite(desc.ptr(i), 1, 32, o);
         for (auto& m : markers) { fwrite(&m.id, 4, 1, o); for (auto& p : m) { fwrite(&p.x, 4, 1, o); fwrite(&p.y, 4, 1, o); } }
         fwrite(matches.data(), 4, matches.size(), o);
+        for (auto& m : markers) { fwrite(m.Rvec, 4, 3, o); fwrite(m.Tvec, 4, 3, o); fwrite(&m.err1, 4, 1, o); fwrite(&m.err2, 4, 1, o); fwrite(&m.ssize, 4, 1, o); }
         fclose(o);
         printf("levels=%d scale0=%g keys=%zu markers=%zu matches=%d\n", extractor.GetLevels(), extractor.GetScaleFactors()[1], keys.size(), markers.size(), nm);
     } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 1; }

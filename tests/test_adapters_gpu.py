@@ -42,7 +42,8 @@ def test_adapters_match_oracle(built_lib, tmp_path):
     kps = np.frombuffer(buf[o:o + 28 * nk], KP_DTYPE); o += 28 * nk
     desc = np.frombuffer(buf[o:o + 32 * nk], np.uint8).reshape(nk, 32); o += 32 * nk
     mk = np.frombuffer(buf[o:o + 36 * nmk], oracle.MARKER_DTYPE); o += 36 * nmk
-    matches = np.frombuffer(buf[o:o + 4 * nk], np.int32)
+    matches = np.frombuffer(buf[o:o + 4 * nk], np.int32); o += 4 * nk
+    poses = np.frombuffer(buf[o:o + 36 * nmk], np.float32).reshape(nmk, 9)       # Rvec Tvec err1 err2 ssize
     k2, d2 = oracle.orb_extract(img)
     assert nk == len(k2) and np.array_equal(desc, d2)
     for name in k2.dtype.names:
@@ -52,3 +53,12 @@ def test_adapters_match_oracle(built_lib, tmp_path):
     n2, m2 = oracle.search_by_bow_bf(d2, k2["angle"], d2, k2["angle"], 0.7, True)
     assert nm == n2 and np.array_equal(matches, m2)
     assert dist == oracle.descriptor_distance(d2[0], d2[1])
+    # detect(image, cameraParams, markerSize) (src/Frame.cc:142): extrinsics of every marker against the IPPE oracle
+    import ctypes as C
+    cam9 = np.array([np.float32(v) for v in (517.3, 516.5, 318.6, 255.3, 0.2624, -0.9531, -0.0054, 0.0026, 1.1633)], np.float64)
+    for i in range(nmk):
+        out14 = np.zeros(14)
+        oracle.lib().oracle_ippe_marker_pose(np.ascontiguousarray(mk["xy"][i]).ctypes.data_as(C.c_void_p), C.c_float(0.187),
+                                             cam9.ctypes.data_as(C.c_void_p), out14.ctypes.data_as(C.c_void_p))
+        assert np.abs(poses[i, :6] - out14[:6]).max() <= 2e-6 * max(1, np.abs(out14[:6]).max())
+        assert poses[i, 6] <= poses[i, 7] and poses[i, 8] == np.float32(0.187)
