@@ -1323,8 +1323,11 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
         dim3 g1(16, n);
         B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err);
         // persistent CTAs; frames are the fast grid index.  A border occupies ONE lane for its whole length and every step is a dependent
-        // load, so the kernel is latency bound: measured at 256 frames, 1 / 2 / 4 / 6 / 9 CTAs per frame -> 1.47 / 1.01 / 0.80 / 0.75 / 0.77 ms
-        dim3 gb(n, std::max(1, std::min(64, (148 * 11) / n)));
+        // load, so the kernel is latency bound: measured alone at 256 frames, 1 / 2 / 4 / 6 / 9 CTAs per frame -> 1.47 / 1.01 / 0.80 / 0.75 / 0.77 ms.
+        // Its CTAs hold their SM slots for the whole kernel, so next to the extractor's dense kernels the best step time is at ~3 per frame
+        // (5.09 ms with 11, 4.75 ms with 3, detector stream at high priority)
+        static const int env_gb = [] { const char* e = getenv("B200_PROBE_CTAS"); return e ? atoi(e) : 0; }();
+        dim3 gb(n, env_gb > 0 ? env_gb : std::max(1, std::min(64, (148 * 6) / n)));
         B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
     }
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit

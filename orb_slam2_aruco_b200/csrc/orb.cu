@@ -1260,10 +1260,16 @@ int b200_orb_create(b200_orb_t* out, int nfeatures, float scale_factor, int nlev
     cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&h->aux_stream2, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_aux2, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_ref, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_done[1], cudaEventDisableTiming);
-    cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    {   // the detector's kernels are latency bound (contour walks, per-candidate serial sections): they get the higher priority so that
+        // they start early and the extractor's dense kernels fill the remaining SM slots (measured: 5.09 -> 4.95 ms per 256-frame step)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi);
+        cudaStreamCreateWithPriority(&h->aux_stream2, cudaStreamNonBlocking, hi);
+    }
     cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming);
     if ((rc = upload_constants()) || (rc = set_geometry(h, max_w, max_h))) { b200_orb_destroy(h); return rc; }
     *out = h;
