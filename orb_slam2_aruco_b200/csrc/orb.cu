@@ -266,7 +266,7 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
             const bool p0 = (me & 0xffffu) != 0, p1 = (mo & 0xffffu) != 0, p2 = (me >> 16) != 0, p3 = (mo >> 16) != 0;
             const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
             const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
-            if (b0 | b1 | b2 | b3) {
+            if (b0 | b1 | b2 | b3) {            // (a scan of per-lane counts instead of four ballots measured 5 % slower)
                 const unsigned lt = (1u << lane) - 1;
                 const int ent = (y << 8) | (4 * my_g);
                 const int o1 = nq + __popc(b0), o2 = o1 + __popc(b1), o3 = o2 + __popc(b2);
@@ -1438,8 +1438,10 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
     const int amode = !aruco ? 0 : acap >= n ? 2 : acap >= 2 * chunk ? 1 : 0;
     if (aruco && acap < std::min(chunk, n)) return fail(B200_ECAPACITY, "detector handle smaller than one pipeline chunk (%s frames)", "128");
     int ci = 0;
-    for (int f0 = 0; f0 < n; f0 += chunk, ci++) {
-        const int nf = std::min(chunk, n - f0);
+    // the first chunk is small so that compute starts after a short upload; the second one completes the regular grid
+    const int first = (env_chunk <= 0 && chunk >= 64 && n > chunk) ? chunk / 4 : chunk;
+    for (int f0 = 0, nf = 0; f0 < n; f0 += nf, ci++) {
+        nf = std::min(ci == 0 ? first : (ci == 1 && first != chunk) ? chunk - first : chunk, n - f0);
         uint8_t* dst = h->d_in + (size_t)f0 * frame_bytes;
         if (in_pinned) {
             if (fs == rs * hh)     // frames are back to back: one 2-D copy for the whole chunk
