@@ -106,6 +106,19 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, wl, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None when no capture matches"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t[kernel]
+        if e["workload"] == wl["name"].split(":")[0] and e["batch"] == batch:
+            return int(e["dram_bytes_read"] + e["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_run(imgs, wl, nthreads, ref_set=None):
     """the reference CPU path on `imgs` with nthreads threads; returns (seconds, kind, description)"""
     import oracle
@@ -342,7 +355,7 @@ def main():
                     "api": "b200_frontend_host (pinned host buffers, chunked H2D overlapped with compute)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "ms_per_launch": fast_ms,
+                         "traffic": ncu_traffic("k_fast", wl, B), "peak_source": peak_src, "ms_per_launch": fast_ms,
                          "algorithmic_bytes_per_launch": int(fast_bytes),
                          "extractor_stage_ms": {"pyramid": stage[0] / args.steps, "fast": stage[1] / args.steps,
                                                 "quadtree": stage[2] / args.steps, "describe": stage[3] / args.steps},

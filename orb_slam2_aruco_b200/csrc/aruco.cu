@@ -673,14 +673,46 @@ __device__ bool lu_solve8(double* A, double* b) {           // OpenCV hal::LU wi
     return true;
 }
 
+// Otsu threshold of every warped patch (cv::threshold THRESH_OTSU, dictionary_based.cpp:1127; SURVEY A-9): the sweep is a serial
+// double-precision recurrence, so it runs one thread per candidate on the histograms k_decode<0> left in global memory.
+__global__ void __launch_bounds__(128)
+k_otsu(const __grid_constant__ ArucoGeom g, const int* __restrict__ nkept, const uint16_t* __restrict__ g_hist, int* __restrict__ g_level) {
+    const int f = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= min(nkept[f], kMaxCand)) return;
+    const uint16_t* hist = g_hist + ((long long)f * kMaxCand + k) * 256;
+    const int ws = g.wsize;
+    int lo = 256, hi = -1;
+    double mu = 0; const double scale = 1. / ((double)ws * ws);
+    for (int i = 0; i < 256; i++) { const int c = hist[i]; if (c) { lo = min(lo, i); hi = i; } mu += i * (double)c; }
+    mu *= scale;
+    double mu1 = 0, q1 = 0, max_sigma = 0; int max_val = 0;
+    // bins below the first / above the last occupied one cannot change the result (q1 = 0 resp. q2 < FLT_EPSILON => `continue`)
+    for (int i = lo; i <= hi; i++) {
+        const double p_i = hist[i] * scale;
+        mu1 *= q1;
+        q1 += p_i;
+        const double q2 = 1. - q1;
+        if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) continue;
+        mu1 = (mu1 + i * p_i) / q1;
+        const double mu2 = (mu - q1 * mu1) / q2;
+        const double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    g_level[(long long)f * kMaxCand + k] = max_val;
+}
+
 constexpr int kDecodeWarps = 4;
 
+// PHASE 0: pyramid level, homography, warped patch + its histogram -> global scratch;  (k_otsu: one THREAD per candidate runs the
+// serial Otsu sweep, 32 candidates per warp instead of one lane of 32);  PHASE 1: threshold, cell votes, codes, dictionary lookup.
+template <int PHASE>
 __global__ void __launch_bounds__(128)
 k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame_stride, const uint8_t* __restrict__ pyr,
          const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, const int* __restrict__ nkept,
-         const unsigned long long* __restrict__ codes, Decoded* __restrict__ dec0) {
-    // one WARP per candidate (4 per CTA): the serial double-precision sections (8x8 LU, Otsu sweep) of different candidates
-    // overlap on the SM's four schedulers instead of idling 127 threads each
+         const unsigned long long* __restrict__ codes, Decoded* __restrict__ dec0,
+         uint8_t* __restrict__ g_patch, uint16_t* __restrict__ g_hist, int* __restrict__ g_level) {
+    // one WARP per candidate (4 per CTA): the serial double-precision section (8x8 LU) of different candidates
+    // overlaps on the SM's four schedulers instead of idling 127 threads each
     struct WarpState {
         double A[64], b[8], Mi[9];
         unsigned long long ids[4];
@@ -700,6 +732,8 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
     __syncwarp();                                      // shared state of the previous candidate is dead
     const Kept kp = kept0[(long long)f * kMaxCand + k];
     const int ws = g.wsize;
+    uint8_t* gp = g_patch + ((long long)f * kMaxCand + k) * (kMaxWarp * kMaxWarp);
+    if (PHASE == 0) {
     if (tid == 0) {
         // Marker::getArea (marker.cpp:405-416) and the pyramid level (6556)
         const float* c = kp.c;
@@ -776,33 +810,15 @@ k_decode(const uint8_t* __restrict__ img0, long long row_stride, long long frame
         atomicAdd(&s_hist[px], 1);
     }
     __syncwarp();
-    {   // occupied range of the histogram
-        int lo = 256, hi = -1;
-        for (int i = tid; i < 256; i += kStride) if (s_hist[i]) { lo = min(lo, i); hi = max(hi, i); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-        if (tid == 0) { S.lo = lo; S.hi = hi; }
+    uint16_t* gh = g_hist + ((long long)f * kMaxCand + k) * 256;
+    for (int i = tid; i < 256; i += kStride) gh[i] = (uint16_t)s_hist[i];
+    for (int i = tid; i < (ws * ws + 3) / 4; i += kStride) reinterpret_cast<uint32_t*>(gp)[i] = reinterpret_cast<const uint32_t*>(s_patch)[i];
+    continue;
     }
-    __syncwarp();
-    if (tid == 0) {       // Otsu (SURVEY A-9)
-        double mu = 0; const double scale = 1. / ((double)ws * ws);
-        for (int i = 0; i < 256; i++) mu += i * (double)s_hist[i];
-        mu *= scale;
-        double mu1 = 0, q1 = 0, max_sigma = 0; int max_val = 0;
-        // bins below the first / above the last occupied one cannot change the result (q1 = 0 resp. q2 < FLT_EPSILON => `continue`)
-        for (int i = S.lo; i <= S.hi; i++) {
-            const double p_i = s_hist[i] * scale;
-            mu1 *= q1;
-            q1 += p_i;
-            const double q2 = 1. - q1;
-            if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) continue;
-            mu1 = (mu1 + i * p_i) / q1;
-            const double mu2 = (mu - q1 * mu1) / q2;
-            const double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
-            if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
-        }
-        s_level = max_val;
-    }
+    // ---- PHASE 1
+    for (int i = tid; i < (ws * ws + 3) / 4; i += kStride) reinterpret_cast<uint32_t*>(s_patch)[i] = reinterpret_cast<const uint32_t*>(gp)[i];
+    for (int i = tid; i < 100; i += kStride) { s_nz[i] = 0; s_tot[i] = 0; }
+    if (tid == 0) s_level = g_level[(long long)f * kMaxCand + k];
     __syncwarp();
     const int nsub = g.nsub;
     for (int i = tid; i < ws * ws; i += kStride) {
@@ -1142,7 +1158,8 @@ struct b200_aruco_s {
     ContourDesc* d_desc; short2* d_pts; float* d_scratch;
     Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
     int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_nfetch, *d_err;
-    int* d_surv2; int* d_nsurv2; size_t cap_surv2;      // transitions that survive the backward check (phase B1)
+    int* d_surv2; int* d_nsurv2; size_t cap_surv2;
+    uint8_t* d_wpatch; uint16_t* d_whist; int* d_wlevel;    // warped patches, their histograms and Otsu levels: [B][256][...]      // transitions that survive the backward check (phase B1)
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
@@ -1251,6 +1268,9 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     ok = ok && cudaMalloc((void**)&h->d_cand, sizeof(Candidate) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_kept, sizeof(Kept) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_dec, sizeof(Decoded) * kMaxCand * B) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_wpatch, (size_t)kMaxWarp * kMaxWarp * kMaxCand * B) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_whist, sizeof(uint16_t) * 256 * kMaxCand * B) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_wlevel, sizeof(int) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_ncont, 7 * B * 4 + 4) == cudaSuccess;
     if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
     h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_nsurv2 = h->d_nfetch + B; h->d_err = h->d_nsurv2 + B;
@@ -1264,7 +1284,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1339,7 +1359,12 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     }
     B200_LAUNCH(k_prefilter, n, 256, 0, st, g, d_cand, d_ncand, d_kept, d_nkept);
     dim3 gd(16, n);
-    B200_LAUNCH(k_decode, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec);
+    uint8_t* d_wpatch = h->d_wpatch + (size_t)base * kMaxCand * kMaxWarp * kMaxWarp;
+    uint16_t* d_whist = h->d_whist + (size_t)base * kMaxCand * 256;
+    int* d_wlevel = h->d_wlevel + (size_t)base * kMaxCand;
+    B200_LAUNCH(k_decode<0>, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec, d_wpatch, d_whist, d_wlevel);
+    B200_LAUNCH(k_otsu, dim3(kMaxCand / 128, n), 128, 0, st, g, d_nkept, d_whist, d_wlevel);
+    B200_LAUNCH(k_decode<1>, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec, d_wpatch, d_whist, d_wlevel);
     B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, d_kept, d_nkept, d_dec, d_desc, d_pts, d_scratch,
                 markers, counts, kMaxMarkers, h->d_err);
     B200_CUDA(cudaGetLastError());
