@@ -57,7 +57,8 @@ k_match_topk(const ulonglong4* __restrict__ ref_desc, int n_ref,
         for (int k = 0; k < kTopK; k++) t[k] = 0xffffffffu;
         for (int i = lane; i < nf; i += 32) {
             // (ncu: XU pipe, where POPC runs, 90 % busy, ALU 50 %.  Carry-save trees that trade POPC for LOP3 were measured: 8 -> 4 POPC is
-            // 15 % slower (ALU pipe saturates), 8 -> 5 POPC is a wash)
+            // 15 % slower (ALU pipe saturates), 8 -> 5 POPC is a wash; skipping the last 64 bits when the first 192 already exceed dstar
+            // (6 POPC for almost every pair) does not change the time either)
             const int d = __popcll(q.x ^ s_planes[i]) + __popcll(q.y ^ s_planes[nf_pad + i]) +
                           __popcll(q.z ^ s_planes[2 * nf_pad + i]) + __popcll(q.w ^ s_planes[3 * nf_pad + i]);
             // distances >= dstar are all equivalent for the accept rule (see match_bf_impl): only the few closer ones are listed
