@@ -294,6 +294,7 @@ def main():
         ev[i][1].record(s_main)
         s_main.synchronize()
         stage += ex.stage_ms()
+        stage_frames = ex.stage_frames()
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - launches0
@@ -334,7 +335,8 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         sp = SIGMA_P.get((W, H), int(3.0942 * W * H))
-        fast_bytes = (sp + 4 * 10000) * B                         # k_fast: every level pixel read once + ~10k candidate slots written / frame
+        fast_bytes = (sp + 4 * 10000) * stage_frames              # k_fast: every level pixel read once + ~10k candidate slots written / frame,
+                                                                  # for the frames of the timed launch (large batches run as two half-batch launches)
         fast_ms = stage[1] / args.steps
         achieved = fast_bytes / (fast_ms / 1000.0) / 1e9
         b_frame = 2 * sp + 60 * (nkp / B)                         # B_ext
@@ -355,8 +357,8 @@ def main():
                     "api": "b200_frontend_host (pinned host buffers, chunked H2D overlapped with compute)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("k_fast", wl, B), "peak_source": peak_src, "ms_per_launch": fast_ms,
-                         "algorithmic_bytes_per_launch": int(fast_bytes),
+                         "traffic": ncu_traffic("k_fast", wl, stage_frames), "peak_source": peak_src, "ms_per_launch": fast_ms,
+                         "algorithmic_bytes_per_launch": int(fast_bytes), "frames_per_launch": int(stage_frames),
                          "extractor_stage_ms": {"pyramid": stage[0] / args.steps, "fast": stage[1] / args.steps,
                                                 "quadtree": stage[2] / args.steps, "describe": stage[3] / args.steps},
                          "whole_step": {"algorithmic_bytes_per_frame": b_frame, "achieved_gbs": fps / world * b_frame / 1e9,

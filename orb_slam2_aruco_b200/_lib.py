@@ -50,6 +50,7 @@ def lib():
         L.b200_aruco_check.argtypes = [vp, vp]
         L.b200_orb_set_profile.argtypes = [vp, i32]
         L.b200_orb_get_stage_ms.argtypes = [vp, vp]
+        L.b200_orb_get_stage_frames.argtypes = [vp]
         L.b200_orb_get_pyramid.argtypes = [vp, i32, i32, vp, vp, vp]
         L.b200_orb_get_candidates.argtypes = [vp, i32, i32, vp, i32]
         L.b200_match_bf.argtypes = [vp, vp, i32, vp, vp, vp, i32, i32, f32, i32, i32, f32, vp, vp, i32, vp]

@@ -121,6 +121,10 @@ class ORBextractor:
         check(lib().b200_orb_get_stage_ms(self._h, ptr(ms)))
         return ms
 
+    def stage_frames(self):
+        """frames the profiled launches of the last call processed (large batches run as two halves)"""
+        return check(lib().b200_orb_get_stage_frames(self._h))
+
     def candidates(self, frame, level):
         """debug tap: FAST candidates (x, y, score) of one level of the last call, before the quadtree"""
         cap = 1 << 20
