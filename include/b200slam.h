@@ -99,7 +99,7 @@ int b200_frontend_host(b200_orb_t orb, b200_aruco_t aruco, const uint8_t* imgs, 
  * describe durations in milliseconds (ms4[4]). */
 int b200_orb_set_profile(b200_orb_t h, int enable);
 int b200_orb_get_stage_ms(b200_orb_t h, float* ms4);
-/* number of frames the profiled launches of the last call processed (large batches run as two halves: the second half is timed) */
+/* number of frames the profiled launches of the last call processed */
 int b200_orb_get_stage_frames(b200_orb_t h);
 /* Pyramid of frame `frame` of the LAST extract call, level `level`, with the reference's 19-px REFLECT_101
  * border: out (host) receives (w_l+38) x (h_l+38) bytes, inner size returned in *w_l, *h_l. */
