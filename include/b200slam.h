@@ -175,6 +175,25 @@ int b200_aruco_pose(const b200_marker* markers, const int32_t* counts, int n_bat
 int b200_aruco_pose_host(const b200_marker* markers, int n_markers, float marker_size, const float* cam9,
                          b200_marker_pose* poses, int device);
 
+
+/* ---------------------------------------------------------------- frame grid -------- */
+/* Frame::UndistortKeyPoints (src/Frame.cc:357-388): kps / kps_un [n_batch][cap] device records, counts [n_batch] device,
+ * cam9 = fx fy cx cy k1 k2 p1 p2 k3 (HOST).  k1 == 0 copies the keypoints like the reference. */
+int b200_frame_undistort(const b200_keypoint* kps, const int32_t* counts, int n_batch, int cap, const float* cam9,
+                         b200_keypoint* kps_un, int device, void* stream);
+/* Frame::ComputeImageBounds (src/Frame.cc:418-447): bounds4 = mnMinX mnMaxX mnMinY mnMaxY (HOST output). */
+int b200_frame_image_bounds(int width, int height, const float* cam9, float* bounds4, int device);
+/* Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:183-198, 332-343): the 64 x 48 grid of every frame as a CSR list,
+ * cell = ix * 48 + iy (mGrid[ix][iy]); cell_start [n_batch][64*48 + 1], cell_items [n_batch][cap] (keypoint indices in push order). */
+int b200_frame_assign_grid(const b200_keypoint* kps_un, const int32_t* counts, int n_batch, int cap, const float* bounds4,
+                           int32_t* cell_start, int32_t* cell_items, int device, void* stream);
+/* Frame::GetFeaturesInArea (src/Frame.cc:280-330) for n_queries windows of ONE frame (its kps_un / cell_start / cell_items rows):
+ * queries_xyr [n][3] = x y r, query_levels [n][2] = minLevel maxLevel; out_idx [n][row_cap] in the reference's visit order,
+ * out_count [n] (may exceed row_cap: then the row is truncated). */
+int b200_frame_features_in_area(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                const float* queries_xyr, const int32_t* query_levels, int n_queries,
+                                int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,13 @@ void oracle_solve_svd(const float* A, const float* b, int m, int n, float* x);
 // corners [4][2], cam9 = fx fy cx cy k1 k2 p1 p2 k3, out14 = rvec1[3] tvec1[3] err1 rvec2[3] tvec2[3] err2
 void oracle_ippe_marker_pose(const float* corners, float msize, const double* cam9, double* out14);
 
+// ---- frame grid: restatement of Frame::UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc) ----
+void oracle_undistort_keypoints(const oracle_keypoint* in, int n, const double* cam9, oracle_keypoint* out);
+void oracle_image_bounds(int w, int h, const double* cam9, float* bounds4);
+void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, int32_t* cell_start, int32_t* cell_items);
+int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                            float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

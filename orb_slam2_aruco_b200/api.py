@@ -439,3 +439,35 @@ class FrontEnd:
             self.matcher.mfNNratio if do_match else 0.0, int(self.matcher.mbCheckOrientation) if do_match else 0,
             ptr(out["matches"]) if do_match else None, ptr(out["n_matches"]) if do_match else None))
         return out
+
+
+class FrameGrid:
+    """Frame::UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid / GetFeaturesInArea (reference src/Frame.cc:357-388,
+    418-447, 183-198, 280-330) on device buffers (torch tensors or raw device addresses): the step between the extractor and
+    every SearchByProjection, so that candidate lists for b200_match_candidates are built without a host round trip."""
+    COLS, ROWS = 64, 48
+
+    def __init__(self, width, height, camera_params, device=0):
+        self._device = int(device)
+        self.cam9 = np.ascontiguousarray(camera_params.cam9(), np.float32)
+        self.bounds = np.zeros(4, np.float32)                 # mnMinX mnMaxX mnMinY mnMaxY
+        check(lib().b200_frame_image_bounds(int(width), int(height), ptr(self.cam9), ptr(self.bounds), self._device))
+
+    def undistort(self, kps, counts, kps_un, stream=None):
+        """kps, kps_un: [B][cap] keypoint records on the device; counts [B] int32 on the device"""
+        B, cap = int(kps.shape[0]), int(kps.shape[1])
+        s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+        check(lib().b200_frame_undistort(ptr(kps), ptr(counts), B, cap, ptr(self.cam9), ptr(kps_un), self._device, s))
+
+    def assign(self, kps_un, counts, cell_start, cell_items, stream=None):
+        """cell_start [B][64*48+1], cell_items [B][cap] int32 on the device"""
+        B, cap = int(kps_un.shape[0]), int(kps_un.shape[1])
+        s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+        check(lib().b200_frame_assign_grid(ptr(kps_un), ptr(counts), B, cap, ptr(self.bounds), ptr(cell_start), ptr(cell_items), self._device, s))
+
+    def features_in_area(self, kps_un_f, cell_start_f, cell_items_f, queries_xyr, query_levels, out_idx, out_count, stream=None):
+        """one frame's rows; queries_xyr [n][3] float32, query_levels [n][2] int32, out_idx [n][row_cap], out_count [n] (device)"""
+        n, row_cap = int(queries_xyr.shape[0]), int(out_idx.shape[1])
+        s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+        check(lib().b200_frame_features_in_area(ptr(kps_un_f), ptr(cell_start_f), ptr(cell_items_f), ptr(self.bounds), ptr(queries_xyr),
+                                                ptr(query_levels), n, ptr(out_idx), ptr(out_count), row_cap, self._device, s))
