@@ -41,7 +41,12 @@ WORKLOADS = {
                     "+ brute-force match vs 1000-descriptor reference set",
                metric="frames/sec (extract+aruco+match)", batch=256, w=640, h=480, nfeatures=1000, markers=20, match=True),
 }
-SIGMA_P = {(640, 480): 950532}      # pixels over the 8 ORB levels
+WORKLOADS["C4"] = dict(name="C4: 256 of the 2048 synthetic 1280x720 frames per GPU, extract (2000 feat, 8 levels) + ArUco (ARUCO_MIP_25h7, 20 markers/frame) "
+                            "+ brute-force match vs 1000-descriptor reference set",
+                       metric="frames/sec (extract+aruco+match)", batch=256, w=1280, h=720, nfeatures=2000, markers=20, match=True, frames_distinct=32)
+WORKLOADS["C5"] = dict(name="C5: 128 of the 8192 synthetic 1920x1080 frames per GPU, extract (4000 feat, 8 levels) + ArUco + brute-force match",
+                       metric="frames/sec (extract+aruco+match)", batch=128, w=1920, h=1080, nfeatures=4000, markers=20, match=True, frames_distinct=16)
+SIGMA_P = {(640, 480): 950532, (1280, 720): 2853088, (1920, 1080): 6419321}      # pixels over the 8 ORB levels
 
 
 def frames_for(wl, rank, batch=None):
@@ -54,7 +59,10 @@ def frames_for(wl, rank, batch=None):
             return np.load(path)
         except Exception:
             pass
-    imgs = synth.make_batch(n, wl["w"], wl["h"], wl["markers"], DICT, first=rank * 100000)
+    distinct = min(n, wl.get("frames_distinct", n))          # the large workloads repeat a few distinct frames (numpy generation is slow)
+    imgs = synth.make_batch(distinct, wl["w"], wl["h"], wl["markers"], DICT, first=rank * 100000)
+    if distinct < n:
+        imgs = np.concatenate([imgs] * ((n + distinct - 1) // distinct))[:n]
     try:
         np.save(path, imgs)
     except Exception:
@@ -335,7 +343,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         sp = SIGMA_P.get((W, H), int(3.0942 * W * H))
-        fast_bytes = (sp + 4 * 10000) * stage_frames              # k_fast: every level pixel read once + ~10k candidate slots written / frame,
+        fast_bytes = (sp + 4 * int(10000 * W * H / 307200)) * stage_frames              # k_fast: every level pixel read once + ~10k candidate slots written / frame,
                                                                   # for the frames of the timed launch (large batches run as two half-batch launches)
         fast_ms = stage[1] / args.steps
         achieved = fast_bytes / (fast_ms / 1000.0) / 1e9

@@ -60,3 +60,32 @@ def test_frontend_multi_chunk_batch(built_lib):
         for key in ("counts", "marker_counts", "n_matches"):
             assert np.array_equal(out[key][4 * rep:4 * rep + 4], out[key][:4]), key
         assert np.array_equal(out["desc"][4 * rep:4 * rep + 4], out["desc"][:4])
+
+
+def test_full_size_c3_batch_properties(built_lib):
+    """BASELINE config[2] size (256 x 640x480, 20 markers, match vs 1000 descriptors) through b200_frontend_host: idempotence,
+    size-independent properties and spot checks of three frames against the three oracles"""
+    imgs = synth.make_batch(256, markers=20, first=2000)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, 256)
+    fe = FrontEnd(ex, MarkerDetector("ARUCO_MIP_25h7", 640, 480, 256), ORBmatcher(0.7, True))
+    rk, rd = ex(np.roll(imgs[0], (3, 5), axis=(0, 1)))
+    rd, rk = np.ascontiguousarray(rd[:1000]), np.ascontiguousarray(rk[:1000])
+    out = {k: v.copy() for k, v in fe.process_batch(imgs, rd, rk).items()}
+    out2 = fe.process_batch(imgs, rd, rk)
+    for key in ("counts", "marker_counts", "n_matches"):
+        assert np.array_equal(out[key], out2[key]), key                   # deterministic (slots past the counts are unspecified)
+    for f in range(256):
+        n, m = int(out["counts"][f]), int(out["marker_counts"][f])
+        assert out["kps"][f, :n].tobytes() == out2["kps"][f, :n].tobytes() and np.array_equal(out["desc"][f, :n], out2["desc"][f, :n])
+        assert np.array_equal(out["matches"][f, :n], out2["matches"][f, :n])
+        assert np.array_equal(out["markers"][f, :m]["id"], out2["markers"][f, :m]["id"])
+        assert np.abs(out["markers"][f, :m]["xy"] - out2["markers"][f, :m]["xy"]).max() <= 1e-4, (f, np.abs(out["markers"][f, :m]["xy"] - out2["markers"][f, :m]["xy"]).max())
+    assert (out["counts"] > 900).all() and (out["marker_counts"] >= 12).all() and (out["marker_counts"] <= 20).all()
+    for f in range(256):
+        m = out["markers"][f, :out["marker_counts"][f]]
+        assert (np.diff(m["id"]) > 0).all()                               # sorted by id, de-duplicated
+        mt = out["matches"][f, :out["counts"][f]]
+        used = mt[mt >= 0]
+        assert len(used) == out["n_matches"][f] and len(np.unique(used)) == len(used)       # a reference row matches at most once
+    check({k: v[[0, 127, 255]] for k, v in out.items()}, imgs[[0, 127, 255]], rd, rk)
+    assert out["n_matches"][0] > 100
