@@ -583,20 +583,35 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
                     }
                     run += __shfl_sync(0xffffffffu, incl, 31);
                 }
-            } else
-            for (int c = 0; c < lg.ncells; c++) {
-                const int n = min(cc[c], cl[c].cap);
-                const uint32_t* src = S + cl[c].slot;
-                for (int i0 = 0; i0 < n; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool take = false; uint32_t key = 0;
-                    if (i < n) {
-                        key = src[i];
-                        take = nini == 1 || (int)__fdiv_rn((float)(key & 0xfff), lg.hx) == ni;
+            } else {
+                // several initial nodes (16:9 frames have two): node ni takes the keys with (int)(x / hX) == ni in cell order.  Same
+                // lane-per-cell scheme, run once per node: a counting sweep is not needed because the nodes are filled one after the
+                // other (run continues where the previous node ended)
+                for (int c0 = 0; c0 < lg.ncells; c0 += 32) {
+                    const int c = c0 + lane;
+                    int n = 0, slot = 0;
+                    if (c < lg.ncells) { n = min(cc[c], cl[c].cap); slot = cl[c].slot; }
+                    const uint32_t* src = S + slot;
+                    int mine = 0;
+                    for (int k0 = 0; k0 < n; k0 += 4) {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) v[u] = k0 + u < n ? src[k0 + u] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) mine += (k0 + u < n) && (int)__fdiv_rn((float)(v[u] & 0xfff), lg.hx) == ni;
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, take);
-                    if (take) A[run + __popc(m & ((1u << lane) - 1))] = key;
-                    run += __popc(m);
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    uint32_t* dstp = A + run + incl - mine;
+                    for (int k0 = 0; k0 < n; k0 += 4) {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) v[u] = k0 + u < n ? src[k0 + u] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) if ((k0 + u < n) && (int)__fdiv_rn((float)(v[u] & 0xfff), lg.hx) == ni) *dstp++ = v[u];
+                    }
+                    run += __shfl_sync(0xffffffffu, incl, 31);
                 }
             }
             const int k = run - beg;
