@@ -1461,7 +1461,9 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
         nf = std::min(ci == 0 ? first : (ci == 1 && first != chunk) ? chunk - first : chunk, n - f0);
         uint8_t* dst = h->d_in + (size_t)f0 * frame_bytes;
         if (in_pinned) {
-            if (fs == rs * hh)     // frames are back to back: one 2-D copy for the whole chunk
+            if (fs == rs * hh && rs == w)     // densely packed frames: one flat copy for the whole chunk
+                B200_CUDA(cudaMemcpyAsync(dst, imgs + (size_t)f0 * fs, frame_bytes * nf, cudaMemcpyHostToDevice, cs));
+            else if (fs == rs * hh)           // frames are back to back: one 2-D copy for the whole chunk
                 B200_CUDA(cudaMemcpy2DAsync(dst, w, imgs + (size_t)f0 * fs, rs, w, (size_t)hh * nf, cudaMemcpyHostToDevice, cs));
             else
                 for (int f = 0; f < nf; f++)
