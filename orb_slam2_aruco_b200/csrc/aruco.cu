@@ -8,21 +8,24 @@
 // whose summation order differs between a serial loop and a warp reduction).
 //
 // Pipeline for a batch of n frames (per-tile / per-border / per-candidate kernels, no serial raster scan):
-//   k_athresh     adaptiveThreshold MEAN_C BINARY_INV (markerdetector_impl.cpp:2984): win x win box sum in smem
-//   k_halfpyr     image pyramid by exact 1/2 (2x2 mean; odd sizes: fixed-point bilinear) (1300-1466)
+//   k_athresh     adaptiveThreshold MEAN_C BINARY_INV (markerdetector_impl.cpp:2984): separable running box sums in smem,
 //                 fused with the 8-neighbour foreground mask of every pixel (the binary image itself is never stored)
-//   k_probe_a/b   cv::findContours RETR_LIST/CHAIN_APPROX_NONE (3108) without a raster scan: every 0->1 / 1->0
-//                 transition pixel is listed (a); persistent warps whose lanes fetch the next transition as soon as they
-//                 are free (b) first look BACK along the border (Suzuki's successor rule, inverted, on the masks) to the
-//                 previous transition and, only if that one comes later in raster order, walk FORWARD until they are back
-//                 at themselves (=> the border's raster-first transition, i.e. Suzuki's start; the border is recorded
-//                 with its length) or meet a transition the raster scan would have seen earlier (=> abort)
+//   k_halfpyr     image pyramid by exact 1/2 (2x2 mean; odd sizes: fixed-point bilinear) (1300-1466)
+//   k_probe_a     cv::findContours RETR_LIST/CHAIN_APPROX_NONE (3108) without a raster scan: every 0->1 / 1->0 transition
+//                 pixel is listed (byte-parallel tests on mask words)
+//   k_probe_b1    every transition looks BACK along its border (Suzuki's successor rule, inverted, on the masks) to the previous
+//                 transition and survives only if that one comes later in raster order
+//   k_probe_b     persistent lanes walk the survivors FORWARD until they are back at themselves (=> the border's raster-first
+//                 transition, i.e. Suzuki's start; the border is recorded with its length) or meet a transition the raster scan
+//                 would have seen earlier (=> abort)
 //   k_emit        borders longer than 70 points are followed once more and written as point lists
 //   k_quads       warp per border: cv::approxPolyDP(eps = 0.05*len, closed) + isContourConvex (3253-3292)
 //   k_prefilter   CTA per frame: candidate order = reverse discovery order, corner orientation, too-near pairs,
 //                 frame-border rejection (4349-5070)
-//   k_decode      CTA per candidate: pyramid level, getPerspectiveTransform (LU, double), warpPerspective 5-bit fixed
-//                 point, Otsu, cell vote, 4 rotations, dictionary lookup (6482-6803, dictionary_based.cpp:1062-2509)
+//   k_decode<0>   warp per candidate: pyramid level, getPerspectiveTransform (LU, double), warpPerspective 5-bit fixed point,
+//                 histogram (6482-6803)
+//   k_otsu        thread per candidate: the serial double-precision Otsu sweep (dictionary_based.cpp:1127)
+//   k_decode<1>   warp per candidate: threshold, cell vote, 4 rotations, dictionary lookup (dictionary_based.cpp:1062-2509)
 //   k_finalize    CTA per frame: stable sort by id, duplicate removal (8159-8311), CORNER_LINES refinement with the
 //                 float one-sided Jacobi SVD of cv::solve(DECOMP_SVD) (8979-12049)
 #include "common.h"
