@@ -49,6 +49,16 @@ def test_no_cpu_fallback_without_gpu(built_lib):
     with pytest.raises(_lib.B200Error) as e:
         ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.zeros(32, np.uint8))
     assert e.value.code == _lib.ENODEV
+    # the widened rows (marker pose, frame grid) fail the same way: nothing computes on the CPU
+    from orb_slam2_aruco_b200.api import CameraParameters, FrameGrid, MarkerDetector
+    cp = CameraParameters([[500, 0, 320], [0, 500, 240], [0, 0, 1]], [0.1, 0, 0, 0, 0])
+    mk = np.zeros(1, _lib.MARKER_DTYPE)
+    with pytest.raises(_lib.B200Error) as e:
+        MarkerDetector("ARUCO_MIP_25h7").estimate_poses(mk, 0.1, cp)
+    assert e.value.code == _lib.ENODEV
+    with pytest.raises(_lib.B200Error) as e:
+        FrameGrid(640, 480, cp)
+    assert e.value.code == _lib.ENODEV
 
 
 def test_bad_arguments_are_rejected(built_lib):
