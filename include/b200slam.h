@@ -132,6 +132,14 @@ int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_re
                        const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
                        float ratio, int th_low, int check_ori, float histo_factor,
                        int32_t* match_ref_idx, int32_t* n_matches, int device);
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:409-524) on arrays:
+ * undistorted keypoints + descriptors of both frames (HOST), bounds4 = mnMinX mnMaxX mnMinY mnMaxY of the frames
+ * (b200_frame_image_bounds), prev_matched [n1][2] in/out (vbPrevMatched), matches12 [n1] out (vnMatches12; -1 = none).
+ * Candidates come from the device feature grid of F2 (GetFeaturesInArea at level 0), the sequential accept / steal / rotation
+ * histogram logic is replayed in order.  Returns nmatches (>= 0) or a negative error. */
+int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8_t* desc1, int n1,
+                                       const b200_keypoint* kps2_un, const uint8_t* desc2, int n2, const float* bounds4,
+                                       float* prev_matched, int window, float ratio, int check_ori, int32_t* matches12, int device);
 /* Plain 256-bit Hamming distance matrix rows x cols (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1651-1667). */
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device);
 /* Candidate-list matching core shared by SearchByProjection / SearchForInitialization:

@@ -167,6 +167,27 @@ public:
         return nm;
     }
 
+    // int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12,
+    //                             int windowSize = 10) (ORBmatcher.h:63-64, ORBmatcher.cc:409-524) on what it reads from the two frames:
+    // mvKeysUn + mDescriptors of both and the image bounds mnMinX, mnMaxX, mnMinY, mnMaxY (Frame.h:191-194) behind F2's grid.
+    int SearchForInitialization(const std::vector<cv::KeyPoint>& keysUn1, const cv::Mat& desc1,
+                                const std::vector<cv::KeyPoint>& keysUn2, const cv::Mat& desc2, const float bounds[4],
+                                std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10) {
+        const int n1 = (int)keysUn1.size(), n2 = (int)keysUn2.size();
+        std::vector<uint8_t> d1((size_t)n1 * 32), d2((size_t)n2 * 32);
+        for (int i = 0; i < n1; i++) std::memcpy(&d1[(size_t)i * 32], desc1.ptr(i), 32);
+        for (int i = 0; i < n2; i++) std::memcpy(&d2[(size_t)i * 32], desc2.ptr(i), 32);
+        std::vector<float> prev((size_t)n1 * 2);
+        for (int i = 0; i < n1; i++) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+        vnMatches12.assign(n1, -1);
+        static_assert(sizeof(cv::KeyPoint) == sizeof(b200_keypoint), "cv::KeyPoint layout");
+        const int nm = b200_match_for_initialization_host((const b200_keypoint*)keysUn1.data(), d1.data(), n1, (const b200_keypoint*)keysUn2.data(), d2.data(), n2,
+                                                          bounds, prev.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0, vnMatches12.data(), device_);
+        b200slam_detail::check(nm);
+        for (int i = 0; i < n1; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+        return nm;
+    }
+
     // best / second-best over explicit candidate lists: the distance core of SearchByProjection / SearchForInitialization
     void MatchCandidates(const cv::Mat& queryDesc, const cv::Mat& trainDesc, const std::vector<int32_t>& candOfs, const std::vector<int32_t>& cand,
                          std::vector<int32_t>& bestIdx, std::vector<int32_t>& bestDist, std::vector<int32_t>& secondDist) {

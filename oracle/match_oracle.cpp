@@ -127,3 +127,61 @@ void oracle_match_candidates(const uint8_t* qd, int nq, const uint8_t* td, const
 }
 
 }  // extern "C"
+
+// ---- SearchForInitialization (src/ORBmatcher.cc:409-524) on plain arrays ------------------------------------------
+// F1 / F2 = undistorted keypoints + descriptors; F2's grid comes from the frame oracle (AssignFeaturesToGrid / GetFeaturesInArea).
+// prev_matched [n1][2] is read and updated like vbPrevMatched; matches12 [n1] receives vnMatches12; returns nmatches.
+extern "C" void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, int32_t* cell_start, int32_t* cell_items);
+extern "C" int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                       float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
+extern "C" int oracle_search_for_initialization(const oracle_keypoint* k1, const uint8_t* d1, int n1, const oracle_keypoint* k2, const uint8_t* d2, int n2,
+                                                const float* bounds4, float* prev_matched, int window, float nnratio, int check_ori, int32_t* matches12) {
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<std::vector<int> > rotHist(HISTO_LENGTH);
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> matched_dist(n2, 0x7fffffff), matches21(n2, -1);
+    std::vector<int32_t> cs(64 * 48 + 1), ci(n2 > 0 ? n2 : 1), cand(n2 > 0 ? n2 : 1);
+    oracle_assign_grid(k2, n2, bounds4, cs.data(), ci.data());
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = k1[i1].octave;
+        if (level1 > 0) continue;
+        const int nc = oracle_features_in_area(k2, cs.data(), ci.data(), bounds4, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window, level1, level1,
+                                               cand.data(), n2);
+        if (nc == 0) continue;
+        int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            const int dist = descriptor_distance(d1 + 32 * (size_t)i1, d2 + 32 * (size_t)i2);
+            if (matched_dist[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2;
+                matches21[bestIdx2] = i1;
+                matched_dist[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) {
+                    float rot = k1[i1].angle - k2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist.data(), HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++) if (matches12[i1] >= 0) { prev_matched[2 * i1] = k2[matches12[i1]].x; prev_matched[2 * i1 + 1] = k2[matches12[i1]].y; }
+    return nmatches;
+}

@@ -275,6 +275,20 @@ class CameraParameters:
         return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2], *self.Distorsion], np.float32)
 
 
+def search_for_initialization(kps1_un, desc1, kps2_un, desc2, bounds4, prev_matched, window=100, nnratio=0.9, check_ori=True, device=0):
+    """ORBmatcher(0.9, true).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, 100) (src/Tracking.cc:606-607,
+    src/ORBmatcher.cc:409-524) on arrays -> (nmatches, vnMatches12, updated vbPrevMatched)"""
+    k1, k2 = np.ascontiguousarray(kps1_un), np.ascontiguousarray(kps2_un)
+    assert k1.dtype == KP_DTYPE and k2.dtype == KP_DTYPE
+    d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+    prev = np.ascontiguousarray(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.full(len(k1), -1, np.int32)
+    b = np.ascontiguousarray(bounds4, np.float32)
+    n = check(lib().b200_match_for_initialization_host(ptr(k1), ptr(d1), len(k1), ptr(k2), ptr(d2), len(k2), ptr(b), ptr(prev), int(window),
+                                                       float(nnratio), int(bool(check_ori)), ptr(m12), int(device)))
+    return n, m12, prev
+
+
 class Marker:
     """aruco::Marker essentials (Thirdparty/aruco/aruco/marker.h:47-59): id + 4 corners, ordered by id; Rvec / Tvec / ssize
     once extrinsics have been computed (marker.cpp:322-343), plus the second IPPE solution and both reprojection errors"""

@@ -288,6 +288,111 @@ k_match_candidates(const ulonglong4* __restrict__ qd, int nq, const ulonglong4* 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SearchForInitialization (ORBmatcher.cc:409-524): level-0 keypoints of F1 look for their match among the level-0 keypoints of
+// F2 inside a window around vbPrevMatched.  The candidate rows come from the frame grid (GetFeaturesInArea, frame.cu) in the
+// reference's visit order; distances of all rows are computed in parallel; the accept / steal / histogram logic, which is
+// strictly sequential in i1 (vMatchedDistance and vnMatches21 carry state), is replayed by one warp.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_init_queries(const b200_keypoint* __restrict__ k1, int n1, const float* __restrict__ prev, float window, float* __restrict__ q3, int* __restrict__ lv2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const bool on = k1[i].octave <= 0;                    // level1 > 0: skipped by the reference (ORBmatcher.cc:425-427)
+    q3[3 * i] = prev[2 * i]; q3[3 * i + 1] = prev[2 * i + 1]; q3[3 * i + 2] = on ? window : -1.f;      // r < 0: no feature passes |d| < r
+    lv2[2 * i] = 0; lv2[2 * i + 1] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_init_dist(const ulonglong4* __restrict__ d1, int n1, const ulonglong4* __restrict__ d2, const int* __restrict__ cand, const int* __restrict__ cnt,
+            int row_cap, int* __restrict__ dist) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= n1) return;
+    const int n = min(cnt[q], row_cap);
+    if (n == 0) return;
+    const ulonglong4 a = d1[q];
+    for (int j = lane; j < n; j += 32) dist[(long long)q * row_cap + j] = hamming256(a, d2[cand[(long long)q * row_cap + j]]);
+}
+
+__global__ void __launch_bounds__(32)
+k_init_resolve(const b200_keypoint* __restrict__ k1, int n1, const b200_keypoint* __restrict__ k2, int n2,
+               const int* __restrict__ cand, const int* __restrict__ cnt, const int* __restrict__ dist, int row_cap,
+               float ratio, int th_low, int check_ori, float* __restrict__ prev, int* __restrict__ m12, int* __restrict__ m21, int* __restrict__ mdist,
+               unsigned char* __restrict__ rotbin, int* __restrict__ result /* nmatches, overflow flag */) {
+    __shared__ int histo[kHistoLen];
+    const int lane = threadIdx.x;
+    if (lane < kHistoLen) histo[lane] = 0;
+    for (int i = lane; i < n1; i += 32) { m12[i] = -1; rotbin[i] = 255; }
+    for (int i = lane; i < n2; i += 32) { m21[i] = -1; mdist[i] = 0x7fffffff; }
+    __syncwarp();
+    int nmatches = 0, overflow = 0;
+    const float factor = __fdiv_rn(1.0f, (float)kHistoLen);                 // the reference's 1.0f / HISTO_LENGTH (ORBmatcher.cc:417)
+    for (int i1 = 0; i1 < n1; i1++) {
+        if (k1[i1].octave > 0) continue;
+        const int n = cnt[i1];
+        if (n > row_cap) overflow = 1;
+        const int nn = min(n, row_cap);
+        if (nn == 0) continue;
+        // key = dist << 20 | position in the row: strict '<' of the reference == first minimum in visit order
+        unsigned long long l1 = ~0ull, l2 = ~0ull;
+        for (int j = lane; j < nn; j += 32) {
+            const int d = dist[(long long)i1 * row_cap + j], i2 = cand[(long long)i1 * row_cap + j];
+            if (mdist[i2] <= d) continue;
+            const unsigned long long key = ((unsigned long long)d << 20) | (unsigned)j;
+            if (key < l1) { l2 = l1; l1 = key; } else if (key < l2) l2 = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, l1, o), o2 = __shfl_xor_sync(0xffffffffu, l2, o);
+            const unsigned long long lo = min(l1, o1), hi = max(l1, o1);
+            l2 = min(hi, min(l2, o2));
+            l1 = lo;
+        }
+        if (l1 == ~0ull) continue;
+        const int best = (int)(l1 >> 20);
+        const bool has2 = l2 != ~0ull;
+        const int best2 = has2 ? (int)(l2 >> 20) : 0x7fffffff;
+        if (best <= th_low && (float)best < __fmul_rn((float)best2, ratio)) {
+            const int i2 = cand[(long long)i1 * row_cap + (int)(l1 & 0xfffff)];
+            const int old = m21[i2];
+            __syncwarp();                                                  // everybody has read the old owner before lane 0 replaces it
+            if (old >= 0) nmatches--;
+            nmatches++;
+            if (lane == 0) {
+                if (old >= 0) m12[old] = -1;                               // steal (ORBmatcher.cc:467-471)
+                m12[i1] = i2; m21[i2] = i1; mdist[i2] = best;
+                if (check_ori) {
+                    float rot = __fsub_rn(k1[i1].angle, k2[i2].angle);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, factor));
+                    if (bin == kHistoLen) bin = 0;
+                    bin = max(0, min(bin, kHistoLen - 1));
+                    rotbin[i1] = (unsigned char)bin;
+                    histo[bin]++;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (check_ori) {
+        int a, b, c;
+        three_maxima(histo, kHistoLen, a, b, c);
+        int removed = 0;
+        for (int i = lane; i < n1; i += 32) {
+            const int bin = rotbin[i];
+            if (bin != 255 && bin != a && bin != b && bin != c && m12[i] >= 0) { m12[i] = -1; removed++; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nmatches -= removed;
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32) if (m12[i] >= 0) { prev[2 * i] = k2[m12[i]].x; prev[2 * i + 1] = k2[m12[i]].y; }
+    if (lane == 0) { result[0] = nmatches; result[1] = overflow; }
+}
+
 struct MatchScratch { uint32_t* topk; size_t cap; int device; };
 static thread_local MatchScratch g_ms = {nullptr, 0, -1};
 
@@ -402,6 +507,43 @@ int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_re
     if (frame_cap) B200_CUDA(cudaMemcpy(match_ref_idx, mi.p, (size_t)n_batch * frame_cap * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(n_matches, nm.p, (size_t)n_batch * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
+}
+
+int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8_t* desc1, int n1,
+                                       const b200_keypoint* kps2_un, const uint8_t* desc2, int n2, const float* bounds4,
+                                       float* prev_matched, int window, float ratio, int check_ori, int32_t* matches12, int device) {
+    if (n1 < 0 || n2 < 0 || window < 0) return fail(B200_EINVAL, "negative %s", "size");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n1 == 0) return 0;
+    if (!kps1_un || !desc1 || !prev_matched || !matches12 || !bounds4 || (n2 > 0 && (!kps2_un || !desc2))) return fail(B200_EINVAL, "null %s", "pointer");
+    if (n2 == 0) { for (int i = 0; i < n1; i++) matches12[i] = -1; return 0; }
+    const int row_cap = std::min(n2, 4096);
+    DevBuf k1, d1, k2, d2, un_cnt, cs, ci, prev, q3, lv2, cand, cnt, dist, m12, m21, mdist, rotbin, res;
+    if ((rc = k1.upload(kps1_un, (size_t)n1 * sizeof(b200_keypoint))) || (rc = d1.upload(desc1, (size_t)n1 * 32)) ||
+        (rc = k2.upload(kps2_un, (size_t)n2 * sizeof(b200_keypoint))) || (rc = d2.upload(desc2, (size_t)n2 * 32)) ||
+        (rc = un_cnt.upload(&n2, 4)) || (rc = cs.alloc((size_t)(64 * 48 + 1) * 4)) || (rc = ci.alloc((size_t)n2 * 4)) ||
+        (rc = prev.upload(prev_matched, (size_t)n1 * 8)) || (rc = q3.alloc((size_t)n1 * 12)) || (rc = lv2.alloc((size_t)n1 * 8)) ||
+        (rc = cand.alloc((size_t)n1 * row_cap * 4)) || (rc = cnt.alloc((size_t)n1 * 4)) || (rc = dist.alloc((size_t)n1 * row_cap * 4)) ||
+        (rc = m12.alloc((size_t)n1 * 4)) || (rc = m21.alloc((size_t)n2 * 4)) || (rc = mdist.alloc((size_t)n2 * 4)) || (rc = rotbin.alloc((size_t)n1)) ||
+        (rc = res.alloc(8)))
+        return rc;
+    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)un_cnt.p, 1, n2, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
+    B200_LAUNCH(k_init_queries, (n1 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k1.p, n1, (const float*)prev.p, (float)window, (float*)q3.p, (int*)lv2.p);
+    if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
+                                          (const int32_t*)lv2.p, n1, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+        return rc;
+    B200_LAUNCH(k_init_dist, (n1 * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)d1.p, n1, (const ulonglong4*)d2.p, (const int*)cand.p, (const int*)cnt.p,
+                row_cap, (int*)dist.p);
+    B200_LAUNCH(k_init_resolve, 1, 32, 0, 0, (const b200_keypoint*)k1.p, n1, (const b200_keypoint*)k2.p, n2, (const int*)cand.p, (const int*)cnt.p,
+                (const int*)dist.p, row_cap, ratio, 50, check_ori, (float*)prev.p, (int*)m12.p, (int*)m21.p, (int*)mdist.p, (unsigned char*)rotbin.p, (int*)res.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    int r2[2] = {0, 0};
+    B200_CUDA(cudaMemcpy(r2, res.p, 8, cudaMemcpyDeviceToHost));
+    if (r2[1]) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
+    B200_CUDA(cudaMemcpy(matches12, m12.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(prev_matched, prev.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost));
+    return r2[0];
 }
 
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device) {

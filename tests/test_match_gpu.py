@@ -85,3 +85,35 @@ def test_candidate_lists(built_lib):
     want = oracle.match_candidates(q, t, ofs, cand)
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
+
+
+def test_search_for_initialization_matches_oracle(built_lib):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:409-524): two views of one scene (second one shifted), windowed
+    candidates from the device feature grid, sequential accept / steal / histogram logic; and a second call that continues
+    from the updated vbPrevMatched like Tracking::MonocularInitialization does"""
+    import ctypes as C
+    from orb_slam2_aruco_b200 import synth
+    from orb_slam2_aruco_b200.api import ORBextractor, search_for_initialization
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    a = synth.make_frame(70)
+    vp = C.c_void_p
+    bounds = np.array([0, 640, 0, 480], np.float32)
+    for shift, window in (((4, 7), 100), ((25, 12), 30), ((1, 1), 10)):
+        b = np.roll(a, shift, axis=(0, 1))
+        k1, d1 = ex(a); k2, d2 = ex(b)
+        prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+        for rep in range(2):
+            want_prev = prev.copy(); want = np.zeros(len(k1), np.int32)
+            nw = oracle.lib().oracle_search_for_initialization(np.ascontiguousarray(k1).ctypes.data_as(vp), np.ascontiguousarray(d1).ctypes.data_as(vp), len(k1),
+                                                               np.ascontiguousarray(k2).ctypes.data_as(vp), np.ascontiguousarray(d2).ctypes.data_as(vp), len(k2),
+                                                               bounds.ctypes.data_as(vp), want_prev.ctypes.data_as(vp), window, C.c_float(0.9), 1,
+                                                               want.ctypes.data_as(vp))
+            n, m12, new_prev = search_for_initialization(k1, d1, k2, d2, bounds, prev, window, 0.9, True)
+            assert n == nw and np.array_equal(m12, want) and np.array_equal(new_prev, want_prev)
+            assert (m12[k1["octave"] > 0] == -1).all()
+            prev = new_prev
+        if window >= 30:
+            assert n > 40                               # the shifted view really matches
+    n, m12, _ = search_for_initialization(k1[:0], d1[:0], k2, d2, bounds, prev[:0])
+    assert n == 0 and len(m12) == 0
+    ex.close()
