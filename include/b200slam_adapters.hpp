@@ -167,6 +167,24 @@ public:
         return nm;
     }
 
+    // Brute-force core of SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (ORBmatcher.h:56,
+    // ORBmatcher.cc:526-659): strict bestDist1 < TH_LOW, histogram factor 1.0f / HISTO_LENGTH; matches12[idx1] = index in KF2 or -1.
+    int SearchByBoW_KF(const cv::Mat& desc1, const std::vector<cv::KeyPoint>& keysUn1, const cv::Mat& desc2, const std::vector<cv::KeyPoint>& keysUn2,
+                       std::vector<int>& matches12) {
+        const int n1 = desc1.rows, n2 = desc2.rows;
+        std::vector<uint8_t> d1((size_t)n1 * 32), d2((size_t)n2 * 32);
+        std::vector<float> a1(n1), a2(n2);
+        for (int i = 0; i < n1; i++) { std::memcpy(&d1[(size_t)i * 32], desc1.ptr(i), 32); a1[i] = keysUn1[i].angle; }
+        for (int i = 0; i < n2; i++) { std::memcpy(&d2[(size_t)i * 32], desc2.ptr(i), 32); a2[i] = keysUn2[i].angle; }
+        std::vector<int> m21(n2 > 0 ? n2 : 1, -1);
+        int32_t n_frame = n2, nm = 0;
+        b200slam_detail::check(b200_match_bf_host(d1.data(), a1.data(), n1, d2.data(), a2.data(), &n_frame, 1, n2, mfNNratio, TH_LOW - 1,
+                                                  mbCheckOrientation ? 1 : 0, 1.0f / HISTO_LENGTH, m21.data(), &nm, device_));
+        matches12.assign(n1, -1);
+        for (int i2 = 0; i2 < n2; i2++) if (m21[i2] >= 0) matches12[m21[i2]] = i2;
+        return nm;
+    }
+
     // int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12,
     //                             int windowSize = 10) (ORBmatcher.h:63-64, ORBmatcher.cc:409-524) on what it reads from the two frames:
     // mvKeysUn + mDescriptors of both and the image bounds mnMinX, mnMaxX, mnMinY, mnMaxY (Frame.h:191-194) behind F2's grid.

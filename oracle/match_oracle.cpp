@@ -185,3 +185,47 @@ extern "C" int oracle_search_for_initialization(const oracle_keypoint* k1, const
     for (int i1 = 0; i1 < n1; i1++) if (matches12[i1] >= 0) { prev_matched[2 * i1] = k2[matches12[i1]].x; prev_matched[2 * i1 + 1] = k2[matches12[i1]].y; }
     return nmatches;
 }
+
+// ---- SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (src/ORBmatcher.cc:526-659) with one vocabulary node that holds every
+// index on both sides and a good MapPoint behind every feature: strict bestDist1 < TH_LOW, factor 1.0f/HISTO_LENGTH (upstream),
+// vbMatched2 greedy.  matches12[n1] = index in KF2 or -1; returns nmatches.
+extern "C" int oracle_search_by_bow_kfkf_bf(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
+                                            float nnratio, int check_ori, int32_t* matches12) {
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<char> matched2(n2, 0);
+    std::vector<std::vector<int> > rotHist(HISTO_LENGTH);
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    for (int idx1 = 0; idx1 < n1; idx1++) {
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int idx2 = 0; idx2 < n2; idx2++) {
+            if (matched2[idx2]) continue;
+            const int dist = descriptor_distance(d1 + 32 * (size_t)idx1, d2 + 32 * (size_t)idx2);
+            if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 < TH_LOW) {
+            if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                matches12[idx1] = bestIdx2;
+                matched2[bestIdx2] = 1;
+                if (check_ori) {
+                    float rot = a1[idx1] - a2[bestIdx2];
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(idx1);
+                }
+                nmatches++;
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist.data(), HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}

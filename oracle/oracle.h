@@ -81,6 +81,9 @@ void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, 
 int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                             float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 
+// SearchByBoW(KeyFrame*, KeyFrame*) (src/ORBmatcher.cc:526-659), one all-inclusive vocabulary node; matches12 [n1] out; returns nmatches
+int oracle_search_by_bow_kfkf_bf(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
+                                 float nnratio, int check_ori, int32_t* matches12);
 // SearchForInitialization (src/ORBmatcher.cc:409-524) on arrays; prev_matched [n1][2] in/out, matches12 [n1] out; returns nmatches
 int oracle_search_for_initialization(const oracle_keypoint* k1, const uint8_t* d1, int n1, const oracle_keypoint* k2, const uint8_t* d2, int n2,
                                      const float* bounds4, float* prev_matched, int window, float nnratio, int check_ori, int32_t* matches12);

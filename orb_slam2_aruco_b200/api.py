@@ -215,6 +215,25 @@ class ORBmatcher:
         n, m = self.SearchByBoW_batch(kf_desc, kf_angles, f_desc[None], f_angles[None], np.array([len(f_desc)], np.int32))
         return int(n[0]), m[0]
 
+    def SearchByBoW_KF(self, desc1, angles1, desc2, angles2):
+        """SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (ORBmatcher.h:56, ORBmatcher.cc:526-659) for one all-inclusive
+        vocabulary node and good MapPoints everywhere: strict bestDist1 < TH_LOW and the upstream factor 1.0f / HISTO_LENGTH.
+        Returns (nmatches, matches12) with matches12[idx1] = index in KF2 or -1.  Same greedy kernel as SearchByBoW (KF1 rows are
+        the sequential side, KF2 features the ones that get taken); only the direction of the answer differs."""
+        d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        a2 = np.ascontiguousarray(angles2, np.float32)
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
+        a1 = np.ascontiguousarray(angles1, np.float32)
+        m21 = np.full((1, max(len(d2), 1)), -1, np.int32)
+        nm = np.zeros(1, np.int32)
+        nf = np.array([len(d2)], np.int32)
+        check(lib().b200_match_bf_host(ptr(d1), ptr(a1), len(d1), ptr(d2), ptr(a2), ptr(nf), 1, len(d2), self.mfNNratio, self.TH_LOW - 1,
+                                       int(self.mbCheckOrientation), float(np.float32(1.0) / np.float32(self.HISTO_LENGTH)), ptr(m21), ptr(nm), self._device))
+        m12 = np.full(len(d1), -1, np.int32)
+        idx2 = np.nonzero(m21[0, :len(d2)] >= 0)[0]
+        m12[m21[0, idx2]] = idx2
+        return int(nm[0]), m12
+
     def SearchByBoW_batch(self, kf_desc, kf_angles, f_desc, f_angles, n_frame, histo_factor=None):
         kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
         kf_angles = np.ascontiguousarray(kf_angles, np.float32)

@@ -117,3 +117,27 @@ def test_search_for_initialization_matches_oracle(built_lib):
     n, m12, _ = search_for_initialization(k1[:0], d1[:0], k2, d2, bounds, prev[:0])
     assert n == 0 and len(m12) == 0
     ex.close()
+
+
+def test_search_by_bow_keyframe_pair_matches_oracle(built_lib):
+    """SearchByBoW(KeyFrame*, KeyFrame*) (ORBmatcher.cc:526-659), brute-force node: strict < TH_LOW, factor 1/HISTO_LENGTH"""
+    import ctypes as C
+    from orb_slam2_aruco_b200 import synth
+    from orb_slam2_aruco_b200.api import ORBextractor
+    vp = C.c_void_p
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    a = synth.make_frame(80)
+    k1, d1 = ex(a); k2, d2 = ex(np.roll(a, (3, 5), axis=(0, 1)))
+    rng = np.random.default_rng(8)
+    base = rng.integers(0, 256, (8, 32)).astype(np.uint8)
+    dup1 = np.repeat(base, 30, axis=0); dup2 = np.repeat(base, 20, axis=0) ^ np.packbits(rng.integers(0, 100, (160, 256)) < 3, axis=1)
+    cases = [(d1, k1["angle"], d2, k2["angle"]), (dup1, rng.uniform(0, 360, 240).astype(np.float32), dup2, rng.uniform(0, 360, 160).astype(np.float32))]
+    for da, aa, db, ab in cases:
+        for ratio, ori in ((0.6, True), (0.8, False), (1.5, True)):
+            want = np.zeros(len(da), np.int32)
+            nw = oracle.lib().oracle_search_by_bow_kfkf_bf(np.ascontiguousarray(da).ctypes.data_as(vp), np.ascontiguousarray(aa).ctypes.data_as(vp), len(da),
+                                                           np.ascontiguousarray(db).ctypes.data_as(vp), np.ascontiguousarray(ab).ctypes.data_as(vp), len(db),
+                                                           C.c_float(ratio), int(ori), want.ctypes.data_as(vp))
+            n, m12 = ORBmatcher(ratio, ori).SearchByBoW_KF(da, aa, db, ab)
+            assert n == nw and np.array_equal(m12, want), (ratio, ori)
+    ex.close()
