@@ -167,6 +167,36 @@ public:
         return nm;
     }
 
+    // One projected map point of SearchByProjection: where it lands in the frame, how far to look, in which pyramid levels, and what it
+    // looks like.  The projection itself (pose, MapPoint::mTrackProjX / GetWorldPos, RadiusByViewingCos, th * mvScaleFactors[level]) is
+    // the reference's host glue and stays with the caller.
+    struct ProjectedPoint { float x, y, radius; int minLevel, maxLevel; const unsigned char* descriptor; float angle; bool observed; };
+
+    // SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (mode 0, ORBmatcher.h:48, ORBmatcher.cc:45-129) and
+    // SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (mode 1, ORBmatcher.h:52, ORBmatcher.cc:1332-1474) on
+    // projected points.  occupied[i] = "F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0" (in/out);
+    // assign[i] = index into `points` now held by frame keypoint i, or -1; returns nmatches.
+    int SearchByProjection(const std::vector<cv::KeyPoint>& keysUn, const cv::Mat& descriptors, const float bounds[4], std::vector<unsigned char>& occupied,
+                           const std::vector<ProjectedPoint>& points, int mode, std::vector<int>& assign) {
+        const int n = (int)keysUn.size(), nq = (int)points.size();
+        std::vector<uint8_t> d((size_t)n * 32), qd((size_t)nq * 32), qo(nq);
+        for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], descriptors.ptr(i), 32);
+        std::vector<float> q3((size_t)nq * 3), qa(nq);
+        std::vector<int32_t> lv((size_t)nq * 2);
+        for (int q = 0; q < nq; q++) {
+            q3[3 * q] = points[q].x; q3[3 * q + 1] = points[q].y; q3[3 * q + 2] = points[q].radius;
+            lv[2 * q] = points[q].minLevel; lv[2 * q + 1] = points[q].maxLevel;
+            std::memcpy(&qd[(size_t)q * 32], points[q].descriptor, 32); qa[q] = points[q].angle; qo[q] = points[q].observed ? 1 : 0;
+        }
+        occupied.resize(n, 0);
+        assign.assign(n, -1);
+        static_assert(sizeof(cv::KeyPoint) == sizeof(b200_keypoint), "cv::KeyPoint layout");
+        const int nm = b200_match_by_projection_host((const b200_keypoint*)keysUn.data(), d.data(), n, bounds, occupied.data(), q3.data(), lv.data(), qd.data(),
+                                                     qa.data(), qo.data(), nq, mode, mfNNratio, mbCheckOrientation ? 1 : 0, assign.data(), device_);
+        b200slam_detail::check(nm);
+        return nm;
+    }
+
     // Brute-force core of SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (ORBmatcher.h:56,
     // ORBmatcher.cc:526-659): strict bestDist1 < TH_LOW, histogram factor 1.0f / HISTO_LENGTH; matches12[idx1] = index in KF2 or -1.
     int SearchByBoW_KF(const cv::Mat& desc1, const std::vector<cv::KeyPoint>& keysUn1, const cv::Mat& desc2, const std::vector<cv::KeyPoint>& keysUn2,

@@ -229,3 +229,58 @@ extern "C" int oracle_search_by_bow_kfkf_bf(const uint8_t* d1, const float* a1, 
     }
     return nmatches;
 }
+
+// ---- SearchByProjection on arrays -----------------------------------------------------------------------------------------
+// The geometry (projection of the map points, radius, level window) is host glue in the reference and is passed in ready-made:
+// query q = (x, y, radius, minLevel, maxLevel, descriptor, angle, observed).  `occupied[i2]` is the reference's
+// "F.mvpMapPoints[i2] && F.mvpMapPoints[i2]->Observations() > 0" and is updated when an observed point is assigned.
+//   mode 0: SearchByProjection(Frame&, const vector<MapPoint*>&, th)          (src/ORBmatcher.cc:45-129): best / second with their
+//           levels, bestDist <= TH_HIGH, rejected when both lie in the same level and bestDist > ratio * bestDist2
+//   mode 1: SearchByProjection(Frame& Current, const Frame& Last, th, mono)   (src/ORBmatcher.cc:1332-1474): best only,
+//           bestDist <= TH_HIGH, rotation histogram with factor 1.0f / HISTO_LENGTH over the assigned frame indices
+// assign[n2] = query index assigned to frame keypoint i2 or -1 (F.mvpMapPoints[bestIdx] = pMP); returns nmatches.
+extern "C" int oracle_search_by_projection(const oracle_keypoint* k2, const uint8_t* d2, int n2, const float* bounds4, uint8_t* occupied,
+                                           const float* q_xyr, const int32_t* q_lev, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed, int nq,
+                                           int mode, float nnratio, int check_ori, int32_t* assign) {
+    const int TH_HIGH = 100;
+    for (int i = 0; i < n2; i++) assign[i] = -1;
+    int nmatches = 0;
+    std::vector<int32_t> cs(64 * 48 + 1), ci(n2 > 0 ? n2 : 1), cand(n2 > 0 ? n2 : 1);
+    oracle_assign_grid(k2, n2, bounds4, cs.data(), ci.data());
+    std::vector<std::vector<int> > rotHist(HISTO_LENGTH);
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int q = 0; q < nq; q++) {
+        const int nc = oracle_features_in_area(k2, cs.data(), ci.data(), bounds4, q_xyr[3 * q], q_xyr[3 * q + 1], q_xyr[3 * q + 2], q_lev[2 * q], q_lev[2 * q + 1],
+                                               cand.data(), n2);
+        if (nc == 0) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            if (occupied[idx]) continue;
+            const int dist = descriptor_distance(q_desc + 32 * (size_t)q, d2 + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = k2[idx].octave; bestIdx = idx; }
+            else if (mode == 0 && dist < bestDist2) { bestLevel2 = k2[idx].octave; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (mode == 0 && bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            assign[bestIdx] = q;
+            if (q_observed[q]) occupied[bestIdx] = 1;
+            nmatches++;
+            if (mode == 1 && check_ori) {
+                float rot = q_angle[q] - k2[bestIdx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx);
+            }
+        }
+    }
+    if (mode == 1 && check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist.data(), HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { assign[idx] = -1; nmatches--; }
+    }
+    return nmatches;
+}

@@ -393,6 +393,89 @@ k_init_resolve(const b200_keypoint* __restrict__ k1, int n1, const b200_keypoint
     if (lane == 0) { result[0] = nmatches; result[1] = overflow; }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SearchByProjection on ready-made projections (the geometry is host glue in the reference):
+//   mode 0  SearchByProjection(Frame&, const vector<MapPoint*>&, th)        (ORBmatcher.cc:45-129)
+//   mode 1  SearchByProjection(Frame& Current, const Frame& Last, th, mono)  (ORBmatcher.cc:1332-1474)
+// Candidate rows (frame grid, frame.cu) and all distances (k_init_dist) are computed in parallel; one warp replays the queries in
+// order because an assigned, observed map point hides its frame keypoint from every later query.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_proj_resolve(const b200_keypoint* __restrict__ k2, int n2, const int* __restrict__ cand, const int* __restrict__ cnt, const int* __restrict__ dist, int row_cap,
+               const float* __restrict__ q_angle, const unsigned char* __restrict__ q_observed, int nq, int mode, float ratio, int th_high, int check_ori,
+               unsigned char* __restrict__ occupied, int* __restrict__ assign, int* __restrict__ ent_bin, int* __restrict__ ent_idx,
+               int* __restrict__ result /* nmatches, overflow flag */) {
+    __shared__ int histo[kHistoLen];
+    const int lane = threadIdx.x;
+    if (lane < kHistoLen) histo[lane] = 0;
+    for (int i = lane; i < n2; i += 32) assign[i] = -1;
+    __syncwarp();
+    int nmatches = 0, overflow = 0, nent = 0;
+    const float factor = __fdiv_rn(1.0f, (float)kHistoLen);
+    for (int q = 0; q < nq; q++) {
+        const int n = cnt[q];
+        if (n > row_cap) overflow = 1;
+        const int nn = min(n, row_cap);
+        if (nn == 0) continue;
+        unsigned long long l1 = ~0ull, l2 = ~0ull;
+        for (int j = lane; j < nn; j += 32) {
+            const int i2 = cand[(long long)q * row_cap + j];
+            if (occupied[i2]) continue;
+            const unsigned long long key = ((unsigned long long)dist[(long long)q * row_cap + j] << 20) | (unsigned)j;
+            if (key < l1) { l2 = l1; l1 = key; } else if (key < l2) l2 = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, l1, o), o2 = __shfl_xor_sync(0xffffffffu, l2, o);
+            const unsigned long long lo = min(l1, o1), hi = max(l1, o1);
+            l2 = min(hi, min(l2, o2));
+            l1 = lo;
+        }
+        if (l1 == ~0ull) continue;
+        const int best = (int)(l1 >> 20);
+        if (best > th_high) continue;
+        const int i2 = cand[(long long)q * row_cap + (int)(l1 & 0xfffff)];
+        if (mode == 0 && l2 != ~0ull) {
+            // ratio only when best and second lie in the same pyramid level (ORBmatcher.cc:118-121)
+            const int best2 = (int)(l2 >> 20), j2 = cand[(long long)q * row_cap + (int)(l2 & 0xfffff)];
+            if (k2[i2].octave == k2[j2].octave && (float)best > __fmul_rn(ratio, (float)best2)) continue;
+        }
+        nmatches++;
+        if (lane == 0) {
+            assign[i2] = q;
+            if (q_observed[q]) occupied[i2] = 1;
+            if (mode == 1 && check_ori) {
+                float rot = __fsub_rn(q_angle[q], k2[i2].angle);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, factor));
+                if (bin == kHistoLen) bin = 0;
+                bin = max(0, min(bin, kHistoLen - 1));
+                ent_bin[nent] = bin; ent_idx[nent] = i2;
+                histo[bin]++;
+            }
+        }
+        nent++;
+        __syncwarp();
+    }
+    __syncwarp();
+    if (mode == 1 && check_ori) {
+        int a, b, c;
+        three_maxima(histo, kHistoLen, a, b, c);
+        // every histogram entry outside the three strongest bins clears its frame keypoint and is subtracted, even when the same keypoint
+        // was pushed twice (ORBmatcher.cc:1459-1467); entries are independent, so the order does not matter
+        int removed = 0;
+        for (int e = lane; e < nent; e += 32) {
+            const int bin = ent_bin[e];
+            if (bin != a && bin != b && bin != c) { assign[ent_idx[e]] = -1; removed++; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nmatches -= removed;
+    }
+    if (lane == 0) { result[0] = nmatches; result[1] = overflow; }
+}
+
 struct MatchScratch { uint32_t* topk; size_t cap; int device; };
 static thread_local MatchScratch g_ms = {nullptr, 0, -1};
 
@@ -543,6 +626,43 @@ int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8
     if (r2[1]) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
     B200_CUDA(cudaMemcpy(matches12, m12.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(prev_matched, prev.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost));
+    return r2[0];
+}
+
+int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_frame, const float* bounds4, uint8_t* occupied,
+                                  const float* q_xyr, const int32_t* q_levels, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed,
+                                  int n_queries, int mode, float ratio, int check_ori, int32_t* assign, int device) {
+    if (n_frame < 0 || n_queries < 0 || (mode != 0 && mode != 1)) return fail(B200_EINVAL, "bad %s", "sizes or mode");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n_frame > 0 && (!kps_un || !desc || !occupied || !assign || !bounds4)) return fail(B200_EINVAL, "null %s", "frame pointer");
+    for (int i = 0; i < n_frame; i++) assign[i] = -1;
+    if (n_queries == 0 || n_frame == 0) return 0;
+    if (!q_xyr || !q_levels || !q_desc || !q_angle || !q_observed) return fail(B200_EINVAL, "null %s", "query pointer");
+    const int row_cap = std::min(n_frame, 4096);
+    DevBuf k2, d2, ncnt, cs, ci, occ, q3, lv2, qd, qa, qo, cand, cnt, dist, asg, eb, ei, res;
+    if ((rc = k2.upload(kps_un, (size_t)n_frame * sizeof(b200_keypoint))) || (rc = d2.upload(desc, (size_t)n_frame * 32)) || (rc = ncnt.upload(&n_frame, 4)) ||
+        (rc = cs.alloc((size_t)(64 * 48 + 1) * 4)) || (rc = ci.alloc((size_t)n_frame * 4)) || (rc = occ.upload(occupied, (size_t)n_frame)) ||
+        (rc = q3.upload(q_xyr, (size_t)n_queries * 12)) || (rc = lv2.upload(q_levels, (size_t)n_queries * 8)) || (rc = qd.upload(q_desc, (size_t)n_queries * 32)) ||
+        (rc = qa.upload(q_angle, (size_t)n_queries * 4)) || (rc = qo.upload(q_observed, (size_t)n_queries)) ||
+        (rc = cand.alloc((size_t)n_queries * row_cap * 4)) || (rc = cnt.alloc((size_t)n_queries * 4)) || (rc = dist.alloc((size_t)n_queries * row_cap * 4)) ||
+        (rc = asg.alloc((size_t)n_frame * 4)) || (rc = eb.alloc((size_t)n_queries * 4)) || (rc = ei.alloc((size_t)n_queries * 4)) || (rc = res.alloc(8)))
+        return rc;
+    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_frame, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
+    if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
+                                          (const int32_t*)lv2.p, n_queries, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+        return rc;
+    B200_LAUNCH(k_init_dist, (n_queries * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)qd.p, n_queries, (const ulonglong4*)d2.p, (const int*)cand.p,
+                (const int*)cnt.p, row_cap, (int*)dist.p);
+    B200_LAUNCH(k_proj_resolve, 1, 32, 0, 0, (const b200_keypoint*)k2.p, n_frame, (const int*)cand.p, (const int*)cnt.p, (const int*)dist.p, row_cap,
+                (const float*)qa.p, (const unsigned char*)qo.p, n_queries, mode, ratio, 100, check_ori, (unsigned char*)occ.p, (int*)asg.p, (int*)eb.p, (int*)ei.p,
+                (int*)res.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    int r2[2] = {0, 0};
+    B200_CUDA(cudaMemcpy(r2, res.p, 8, cudaMemcpyDeviceToHost));
+    if (r2[1]) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
+    B200_CUDA(cudaMemcpy(assign, asg.p, (size_t)n_frame * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(occupied, occ.p, (size_t)n_frame, cudaMemcpyDeviceToHost));
     return r2[0];
 }
 

@@ -141,3 +141,36 @@ def test_search_by_bow_keyframe_pair_matches_oracle(built_lib):
             n, m12 = ORBmatcher(ratio, ori).SearchByBoW_KF(da, aa, db, ab)
             assert n == nw and np.array_equal(m12, want), (ratio, ori)
     ex.close()
+
+
+def test_search_by_projection_modes_match_oracle(built_lib):
+    """SearchByProjection(Frame, mapPoints, th) and SearchByProjection(Current, Last, th, mono) on ready-made projections: the map
+    points are the keypoints of a second view whose positions are perturbed, so that windows overlap and assignments compete"""
+    import ctypes as C
+    from orb_slam2_aruco_b200 import synth
+    from orb_slam2_aruco_b200.api import ORBextractor, search_by_projection
+    vp = C.c_void_p
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(vp)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    a = synth.make_frame(90)
+    kf, df = ex(a)
+    kq, dq = ex(np.roll(a, (2, 3), axis=(0, 1)))
+    rng = np.random.default_rng(12)
+    sf = 1.2 ** kq["octave"].astype(np.float32)
+    bounds = np.array([0, 640, 0, 480], np.float32)
+    for mode, ratio, ori in ((0, 0.8, True), (0, 0.6, False), (1, 0.9, True), (1, 0.9, False)):
+        nq = len(kq)
+        xyr = np.stack([kq["x"] - 3 + rng.normal(0, 2, nq), kq["y"] - 2 + rng.normal(0, 2, nq),
+                        (rng.choice([2.5, 4.0], nq) if mode == 0 else np.full(nq, 7.0)) * sf], 1).astype(np.float32)
+        lev = (np.stack([kq["octave"] - 1, kq["octave"]], 1) if mode == 0 else np.stack([kq["octave"] - 1, kq["octave"] + 1], 1)).astype(np.int32)
+        observed = (rng.random(nq) < 0.8).astype(np.uint8)
+        occupied = (rng.random(len(kf)) < 0.1).astype(np.uint8)
+        want_occ = occupied.copy(); want = np.zeros(len(kf), np.int32)
+        nw = oracle.lib().oracle_search_by_projection(P(kf), P(df), len(kf), P(bounds), P(want_occ), P(xyr), P(lev), P(dq), P(kq["angle"].copy()), P(observed), nq,
+                                                      mode, C.c_float(ratio), int(ori), P(want))
+        n, assign, occ = search_by_projection(kf, df, bounds, occupied, xyr, lev, dq, kq["angle"].copy(), observed, mode, ratio, ori)
+        assert n == nw and np.array_equal(assign, want) and np.array_equal(occ, want_occ), (mode, ratio, ori)
+        assert n > 300
+    n, assign, occ = search_by_projection(kf, df, bounds, np.zeros(len(kf), np.uint8), np.zeros((0, 3)), np.zeros((0, 2)), np.zeros((0, 32)), np.zeros(0), np.zeros(0), 0)
+    assert n == 0 and (assign == -1).all()
+    ex.close()
