@@ -179,7 +179,7 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&d)[16]) {
 
 // TP: tile pitch in bytes = TMA box width, a compile-time constant so that every circle offset is an immediate
 template <int TP>
-__global__ void __launch_bounds__(kFastThreads)
+__global__ void __launch_bounds__(kFastThreads, 10)
 k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
        const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ FastMaps maps,
        const FastSmemGeom sg, int tma_level0, int scratch_base,
