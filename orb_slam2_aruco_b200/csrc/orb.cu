@@ -7,7 +7,7 @@
 // (no FMA contraction): fastAtan2, the rBRIEF rotation and the final pt*scale.
 //
 // Pipeline for a batch of n frames (everything stays in HBM/L2, 10 launches):
-//   k_pyramid x (nlevels-1)   level l from level l-1, fixed-point bilinear (ORBextractor.cc:1107-1132)
+//   k_pyramid_tma x (nlevels-1)   level l from level l-1, fixed-point bilinear, source tile by TMA (ORBextractor.cc:1107-1132)
 //   k_fast                    one CTA per (cell, frame): u8 tile in smem, score of every pixel, 3x3 NMS,
 //                             ini/min threshold fallback, raster-ordered compaction (ORBextractor.cc:765-829)
 //   k_quadtree                one warp per (frame, level): DistributeOctTree (ORBextractor.cc:539-763)
@@ -39,6 +39,7 @@ struct LevelGeom {
     int nini; float hx;       // DistributeOctTree initial nodes
     int kp_cap, kp_base;      // result capacity of this level, base inside the frame's level-result block
     int xtab, ytab;           // offsets into the resize tables
+    int pbox_w, pbox_h;       // TMA box of k_pyramid_tma over the SOURCE level (l - 1): largest source region one 128 x 64 output tile reads
     int box_w, box_h;         // TMA box of k_fast: (largest cell ROI of the level + 15 columns of alignment slack) rounded up to 16 x largest ROI height
     float scale;              // mvScaleFactor[l]
     float size;               // keypoint size = (int)(31*scale)
@@ -72,6 +73,8 @@ __constant__ int c_umax[16];
 // K1: pyramid level from the previous level.  cv::resize INTER_LINEAR u8 fixed point (SURVEY A-1).
 // One thread -> 4 horizontally adjacent output pixels (one 32-bit store; pitch is a multiple of 16).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 constexpr int kPyrRows = 8;          // output rows per thread: the four column entries are fetched once and reused
 
 __global__ void __launch_bounds__(256)
@@ -109,6 +112,57 @@ k_pyramid(const uint8_t* __restrict__ src0, long long src_row_stride, long long 
     }
 }
 
+// Same arithmetic, source tile staged by TMA: the 128 x 64 output tile of a CTA needs a source region of about 156 x 79 pixels, fetched
+// as ONE box (cp.async.bulk.tensor.3d) whose x starts at the first source column rounded down to 16 (u8 tensor maps only take 16-byte
+// aligned inner coordinates); the four taps of every output pixel then come from shared memory.
+__global__ void __launch_bounds__(256)
+k_pyramid_tma(const __grid_constant__ CUtensorMap smap, int zbase, int box_w, int box_h,
+              uint8_t* __restrict__ dst0, int dst_pitch, long long dst_frame_stride, int sw, int sh, int dw, int dh,
+              const ResizeEntry* __restrict__ xt, const ResizeEntry* __restrict__ yt) {
+    extern __shared__ __align__(1024) unsigned char pt_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * (8 * kPyrRows);
+    const int xs0 = xt[x0].ofs & ~15, ys0 = yt[y0].ofs;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar)), "r"(box_w * box_h) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     :: "r"(smem_u32(pt_raw)), "l"(reinterpret_cast<uint64_t>(&smap)), "r"(xs0), "r"(ys0), "r"(zbase + f), "r"(smem_u32(&s_bar)) : "memory");
+    }
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    int o0[4], o1[4], c0[4], c1[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const ResizeEntry xe = xt[min(x4 + i, dw - 1)];          // columns past the level width land in the row padding
+        o0[i] = xe.ofs - xs0; o1[i] = min(xe.ofs + 1, sw - 1) - xs0; c0[i] = xe.c0; c1[i] = xe.c1;
+    }
+    __syncthreads();                                             // the barrier word is initialised before anybody polls it
+    asm volatile("{\n.reg .pred p;\nPYR_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra PYR_DONE;\nbra PYR_WAIT;\nPYR_DONE:\n}"
+                 :: "r"(smem_u32(&s_bar)) : "memory");
+    if (x4 >= dw) return;
+    uint8_t* df = dst0 + (long long)f * dst_frame_stride + x4;
+#pragma unroll 2
+    for (int j = 0; j < kPyrRows; j++) {
+        const int y = y0 + j * 8 + threadIdx.y;
+        if (y >= dh) break;
+        const ResizeEntry ye = yt[y];
+        const uint8_t* r0 = pt_raw + (ye.ofs - ys0) * box_w;
+        const uint8_t* r1 = pt_raw + (min(ye.ofs + 1, sh - 1) - ys0) * box_w;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int h0 = r0[o0[i]] * c0[i] + r0[o1[i]] * c1[i];
+            const int h1 = r1[o0[i]] * c0[i] + r1[o1[i]] * c1[i];
+            const int v = (((ye.c0 * (h0 >> 4)) >> 16) + ((ye.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)v << (8 * i);
+        }
+        *reinterpret_cast<uint32_t*>(df + (long long)y * dst_pitch) = packed;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: FAST-9/16 score, NMS, threshold fallback, ordered compaction.  One CTA per (cell, frame).
 // score(p) = max over the 16 arcs of 9 contiguous circle pixels of max(min d, -max d) - 1, d = I(circle) - I(p)
@@ -140,7 +194,6 @@ struct FastSmemGeom {                        // dynamic shared memory carve-up, 
 
 struct FastMaps { CUtensorMap m[kMaxLevels]; };     // level 0: the caller's frames; level l > 0: that level inside the pyramid buffer
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned pair_e(unsigned w) { return __byte_perm(w, 0, 0x4240); }      // pixels 0, 2 of a word as u16x2
 __device__ __forceinline__ unsigned pair_o(unsigned w) { return __byte_perm(w, 0, 0x4341); }      // pixels 1, 3
 __device__ __forceinline__ unsigned sh16(unsigned lo, unsigned hi) { return __byte_perm(lo, hi, 0x5432); }   // (lo.hi16, hi.lo16)
@@ -959,7 +1012,7 @@ struct b200_orb_s {
     OrbGeom geom;
     std::vector<CellDesc> cells;
     int pool_cap;
-    FastSmemGeom fsg; size_t fast_smem; FastMaps maps; DescMaps dmaps;      // maps.m[l > 0]: level l of the pyramid buffer; m[0] is encoded per call
+    FastSmemGeom fsg; size_t fast_smem; FastMaps maps; DescMaps dmaps; FastMaps pmaps;      // pmaps.m[l]: source level l - 1 with level l's pyramid box      // maps.m[l > 0]: level l of the pyramid buffer; m[0] is encoded per call
     // device buffers
     uint8_t* d_pyr; ResizeEntry* d_tab; CellDesc* d_cells; uint32_t* d_slots; int* d_cellcnt;
     uint32_t *d_keysA, *d_keysB, *d_lvlres; int* d_lvlcnt; int* d_err;
@@ -1062,6 +1115,19 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
             pyr_ofs += align_up((long long)L.pitch * L.h, 256);
             L.xtab = (int)tab.size(); tab.resize(tab.size() + L.w); resize_table(g.L[l - 1].w, L.w, &tab[L.xtab]);
             L.ytab = (int)tab.size(); tab.resize(tab.size() + L.h); resize_table(g.L[l - 1].h, L.h, &tab[L.ytab]);
+            {   // source box of k_pyramid_tma: the largest source region a 128 x 64 output tile touches
+                const int sw = g.L[l - 1].w, sh = g.L[l - 1].h;
+                int bw = 16, bh = 1;
+                for (int x0 = 0; x0 < L.w; x0 += 128) {
+                    const int xs0 = tab[L.xtab + x0].ofs & ~15, xs1 = std::min(tab[L.xtab + std::min(x0 + 127, L.w - 1)].ofs + 1, sw - 1);
+                    bw = std::max(bw, xs1 - xs0 + 1);
+                }
+                for (int y0 = 0; y0 < L.h; y0 += 8 * kPyrRows) {
+                    const int ys0 = tab[L.ytab + y0].ofs, ys1 = std::min(tab[L.ytab + std::min(y0 + 8 * kPyrRows - 1, L.h - 1)].ofs + 1, sh - 1);
+                    bh = std::max(bh, ys1 - ys0 + 1);
+                }
+                L.pbox_w = (int)align_up(bw, 16); L.pbox_h = bh;
+            }
         }
         // cells (ORBextractor.cc:771-806)
         const int minB = kMinBorder, maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
@@ -1154,6 +1220,9 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
         const LevelGeom& L = g.L[l];
         if ((rc = make_tile_map(&h->maps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, L.box_w, L.box_h))) return rc;
         if ((rc = make_tile_map(&h->dmaps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, kPatchPitch, kPatchW))) return rc;
+        if (l + 1 < h->nlevels && g.L[l + 1].pbox_w <= 256 && g.L[l + 1].pbox_h <= 256 &&
+            (rc = make_tile_map(&h->pmaps.m[l + 1], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, g.L[l + 1].pbox_w, g.L[l + 1].pbox_h)))
+            return rc;
     }
     h->cur_w = w; h->cur_h = h_img;
     return B200_OK;
@@ -1193,6 +1262,7 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
     uint32_t* d_lvlres = h->d_lvlres + (size_t)base * g.res_per_frame;
     int* d_lvlcnt = h->d_lvlcnt + (size_t)base * g.nlevels;
     int tma0_used = 0;
+    static const bool pyr_no_tma = getenv("B200_PYRAMID_NO_TMA") != nullptr;
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[0], st));
     for (int l = 1; l < g.nlevels; l++) {
         const LevelGeom& L = g.L[l];
@@ -1200,8 +1270,20 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
         const uint8_t* src = l == 1 ? imgs : d_pyr + Lp.offset;
         const long long srs = l == 1 ? rs : Lp.pitch, sfs = l == 1 ? fs : g.pyr_frame_stride;
         dim3 grid((L.w + 127) / 128, (L.h + 8 * kPyrRows - 1) / (8 * kPyrRows), n), block(32, 8);
-        B200_LAUNCH(k_pyramid, grid, block, 0, st, src, srs, sfs, d_pyr + L.offset, L.pitch, g.pyr_frame_stride,
-                    Lp.w, Lp.h, L.w, L.h, h->d_tab + L.xtab, h->d_tab + L.ytab);
+        // the source tile comes through TMA when it can be described by a tensor map (pyramid levels always; the caller's frames when
+        // pointer and strides are 16-byte multiples), else the taps are read from global memory
+        bool tma = L.pbox_w <= 256 && L.pbox_h <= 256 && !pyr_no_tma;
+        if (tma && l == 1) {
+            const long long fs0 = n > 1 ? fs : align_up(rs * (long long)g.L[0].h, 16);
+            tma = ((reinterpret_cast<uintptr_t>(imgs) | (uintptr_t)rs | (uintptr_t)fs0) & 15) == 0;
+            if (tma) { int rc = make_tile_map(&h->pmaps.m[1], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, L.pbox_w, L.pbox_h); if (rc) return rc; }
+        }
+        if (tma)
+            B200_LAUNCH(k_pyramid_tma, grid, block, (size_t)L.pbox_w * L.pbox_h, st, h->pmaps.m[l], l == 1 ? 0 : base, L.pbox_w, L.pbox_h,
+                        d_pyr + L.offset, L.pitch, g.pyr_frame_stride, Lp.w, Lp.h, L.w, L.h, h->d_tab + L.xtab, h->d_tab + L.ytab);
+        else
+            B200_LAUNCH(k_pyramid, grid, block, 0, st, src, srs, sfs, d_pyr + L.offset, L.pitch, g.pyr_frame_stride,
+                        Lp.w, Lp.h, L.w, L.h, h->d_tab + L.xtab, h->d_tab + L.ytab);
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[1], st));
     if (g.total_cells > 0) {
