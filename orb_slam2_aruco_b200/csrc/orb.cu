@@ -483,8 +483,9 @@ __device__ __forceinline__ int qt_erase(QtWarp& w, int id, int lane) {   // retu
 
 // DivideNode (ORBextractor.cc:481-537): stable 4-way partition of the node's key range into the other buffer.
 // Returns the four child counts (warp-uniform) and fills child boxes.
+// `pre` (valid when has_pre): this node's keys, one per lane, fetched while the previous node was being divided (nodes of at most 32 keys)
 __device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint32_t* bufB, int lane,
-                                          int cnt[4], int& mx, int& my) {
+                                          int cnt[4], int& mx, int& my, uint32_t pre = 0u, bool has_pre = false) {
     const int halfX = (nd.x1 - nd.x0 + 1) >> 1;      // ceil((float)(UR.x-UL.x)/2) for non-negative ints
     const int halfY = (nd.y1 - nd.y0 + 1) >> 1;
     mx = nd.x0 + halfX; my = nd.y0 + halfY;
@@ -494,7 +495,7 @@ __device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint3
     cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
     if (n <= 32) {                                    // common case: one register-resident pass
         const bool valid = lane < n;
-        const uint32_t key = valid ? src[nd.beg + lane] : 0u;
+        const uint32_t key = has_pre ? pre : (valid ? src[nd.beg + lane] : 0u);
         const int q = valid ? (((int)(key & 0xfff) >= mx) + 2 * ((int)((key >> 12) & 0xfff) >= my)) : 4;
         unsigned m[4];
 #pragma unroll
@@ -538,6 +539,17 @@ __device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint3
         }
     }
     __syncwarp();
+}
+
+// start fetching the keys of node `id` (if it is small enough for the register path): the load is in flight while the current node is divided
+__device__ __forceinline__ bool qt_prefetch(const QtWarp& w, int id, const uint32_t* bufA, const uint32_t* bufB, int lane, uint32_t& key) {
+    key = 0u;
+    if (id < 0) return false;
+    const QtNode nd = w.pool[id];
+    const int n = nd.end - nd.beg;
+    if (n > 32) return false;
+    if (lane < n) key = (nd.buf ? bufB : bufA)[nd.beg + lane];
+    return true;
 }
 
 // create the non-empty children of `nd` at the list front in the order n1..n4 (ORBextractor.cc:606-665);
@@ -691,15 +703,20 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
         const int prev_size = w.size;
         int nbig = 0, n_expand = 0;
         int it = w.head;
+        while (it >= 0 && w.pool[it].no_more) it = w.pool[it].next;
+        uint32_t pre; bool has_pre = qt_prefetch(w, it, A, B, lane, pre);
         while (it >= 0) {
             const QtNode nd = w.pool[it];
             __syncwarp();
-            if (nd.no_more) { it = nd.next; continue; }
             if (w.nfree < 4) { if (lane == 0) atomicExch(errflag, 1); finish = true; break; }
+            int nx = nd.next;                                   // the next node that can still be divided: its keys are requested now
+            while (nx >= 0 && w.pool[nx].no_more) nx = w.pool[nx].next;
+            uint32_t pre_n; const bool has_n = qt_prefetch(w, nx, A, B, lane, pre_n);
             int cnt[4], mx, my;
-            qt_divide(nd, A, B, lane, cnt, mx, my);
+            qt_divide(nd, A, B, lane, cnt, mx, my, pre, has_pre);
             n_expand += qt_add_children(w, nd, cnt, mx, my, lane, nbig);
-            it = qt_erase(w, it, lane);
+            qt_erase(w, it, lane);
+            it = nx; pre = pre_n; has_pre = has_n;
         }
         if (finish) break;
         if (w.size >= N || w.size == prev_size) finish = true;
@@ -721,15 +738,18 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
                 }
                 __syncwarp();
                 nbig = 0;
+                uint32_t pre; bool has_pre = qt_prefetch(w, m > 0 ? w.prv_id[w.order[0]] : -1, A, B, lane, pre);
                 for (int j = 0; j < m; j++) {
                     const int id = w.prv_id[w.order[j]];
                     const QtNode nd = w.pool[id];
                     __syncwarp();
                     if (w.nfree < 4) { if (lane == 0) atomicExch(errflag, 1); finish = true; break; }
+                    uint32_t pre_n; const bool has_n = qt_prefetch(w, j + 1 < m ? w.prv_id[w.order[j + 1]] : -1, A, B, lane, pre_n);
                     int cnt[4], mx, my;
-                    qt_divide(nd, A, B, lane, cnt, mx, my);
+                    qt_divide(nd, A, B, lane, cnt, mx, my, pre, has_pre);
                     qt_add_children(w, nd, cnt, mx, my, lane, nbig);
                     qt_erase(w, id, lane);
+                    pre = pre_n; has_pre = has_n;
                     if (w.size >= N) break;
                 }
                 if (w.size >= N || w.size == prev2) finish = true;
