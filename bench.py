@@ -77,13 +77,48 @@ def reference_scene(wl):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in-process (a sample every ~2 ms), nvidia-smi as a fallback"""
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.stop_flag, self.rows = gpu, False, []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu))
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(gpu):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if gpu < len(ids) and ids[gpu].strip().isdigit():
+                return int(ids[gpu])
+        return gpu
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self.stop_flag:
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    r = int(get_reasons(self.handle))
+                    self.rows.append([str(sm), str(self.sm_max)] + [("Active" if r & bits[k] else "Not Active") for k in
+                                                                       ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
@@ -103,7 +138,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def peaks():
