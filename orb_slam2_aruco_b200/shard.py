@@ -36,3 +36,20 @@ def collate(local, n_frames, group=None):
         dist.all_gather(parts, t.contiguous(), group=group)
         out[name] = torch.cat([p[:s] for p, s in zip(parts, sizes)], 0)
     return out
+
+
+def collate_into(local, out, group=None, async_op=False):
+    """Equal-sized shards (the batch divides evenly, as in weak scaling): one all_gather_into_tensor per output array straight into
+    the preallocated `out[name]` of shape [world * n_local, ...] -- rank-major order IS global frame order, so there is no temporary
+    and no concatenation.  With async_op=True the collectives are only enqueued (they wait for the work already on the current
+    stream and then overlap whatever is enqueued next); the returned handles' .wait() makes the current stream wait for them."""
+    works = []
+    for name, t in local.items():
+        w = dist.all_gather_into_tensor(out[name].view(-1), t.contiguous().view(-1), group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
+    return works
+
+
+def alloc_collated(local, world):
+    return {name: torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for name, t in local.items()}

@@ -38,6 +38,13 @@ def _worker(rank, world, port, n_frames, q):
     got = shard.collate(fake_slots(lo, hi), n_frames)
     want = fake_slots(0, n_frames)
     ok = all(torch.equal(got[k], want[k]) for k in want)
+    if n_frames % world == 0:                    # equal shards: the allocation-free path bench.py uses, synchronous and asynchronous
+        local = fake_slots(lo, hi)
+        for async_op in (False, True):
+            out = shard.alloc_collated(local, world)
+            for w in shard.collate_into(local, out, async_op=async_op):
+                w.wait()
+            ok = ok and all(torch.equal(out[k], want[k]) for k in want)
     q.put((rank, ok, int(got["counts"].shape[0])))
     dist.barrier()
     dist.destroy_process_group()
