@@ -142,14 +142,16 @@ int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8
                                        float* prev_matched, int window, float ratio, int check_ori, int32_t* matches12, int device);
 /* ORBmatcher::SearchByProjection on ready-made projections (the projection of the map points is host glue in the reference):
  *   mode 0  SearchByProjection(Frame&, const vector<MapPoint*>&, th)          (src/ORBmatcher.cc:45-129, Tracking::SearchLocalPoints)
- *   mode 1  SearchByProjection(Frame& Current, const Frame& Last, th, mono)    (src/ORBmatcher.cc:1332-1474, TrackWithMotionModel)
+ *   mode 1  SearchByProjection(Frame& Current, const Frame& Last, th, mono)    (src/ORBmatcher.cc:1332-1474, TrackWithMotionModel); with
+ *           th_high = ORBdist also SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1476-1603, Relocalization)
  * Frame side (HOST): undistorted keypoints, descriptors, bounds4, occupied [n_frame] in/out = "mvpMapPoints[i] && Observations() > 0".
  * Query q (HOST): q_xyr [n][3] = projected x, y and the search radius (already scaled), q_levels [n][2] = minLevel maxLevel of
  * GetFeaturesInArea, q_desc [n][32], q_angle [n] (mode 1 histogram), q_observed [n] = the map point's Observations() > 0.
+ * th_high: accept bestDist <= th_high (<= 0: TH_HIGH = 100).
  * assign [n_frame] out = query index assigned to that frame keypoint or -1 (F.mvpMapPoints[bestIdx] = pMP).  Returns nmatches. */
 int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_frame, const float* bounds4, uint8_t* occupied,
                                   const float* q_xyr, const int32_t* q_levels, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed,
-                                  int n_queries, int mode, float ratio, int check_ori, int32_t* assign, int device);
+                                  int n_queries, int mode, float ratio, int check_ori, int th_high, int32_t* assign, int device);
 /* Plain 256-bit Hamming distance matrix rows x cols (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1651-1667). */
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device);
 /* Candidate-list matching core shared by SearchByProjection / SearchForInitialization:

@@ -174,10 +174,11 @@ public:
 
     // SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th) (mode 0, ORBmatcher.h:48, ORBmatcher.cc:45-129) and
     // SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (mode 1, ORBmatcher.h:52, ORBmatcher.cc:1332-1474) on
-    // projected points.  occupied[i] = "F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0" (in/out);
+    // projected points; mode 1 with thHigh = ORBdist is SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1476-1603).
+    // occupied[i] = "F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0" (in/out);
     // assign[i] = index into `points` now held by frame keypoint i, or -1; returns nmatches.
     int SearchByProjection(const std::vector<cv::KeyPoint>& keysUn, const cv::Mat& descriptors, const float bounds[4], std::vector<unsigned char>& occupied,
-                           const std::vector<ProjectedPoint>& points, int mode, std::vector<int>& assign) {
+                           const std::vector<ProjectedPoint>& points, int mode, std::vector<int>& assign, int thHigh = TH_HIGH) {
         const int n = (int)keysUn.size(), nq = (int)points.size();
         std::vector<uint8_t> d((size_t)n * 32), qd((size_t)nq * 32), qo(nq);
         for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], descriptors.ptr(i), 32);
@@ -192,7 +193,7 @@ public:
         assign.assign(n, -1);
         static_assert(sizeof(cv::KeyPoint) == sizeof(b200_keypoint), "cv::KeyPoint layout");
         const int nm = b200_match_by_projection_host((const b200_keypoint*)keysUn.data(), d.data(), n, bounds, occupied.data(), q3.data(), lv.data(), qd.data(),
-                                                     qa.data(), qo.data(), nq, mode, mfNNratio, mbCheckOrientation ? 1 : 0, assign.data(), device_);
+                                                     qa.data(), qo.data(), nq, mode, mfNNratio, mbCheckOrientation ? 1 : 0, thHigh, assign.data(), device_);
         b200slam_detail::check(nm);
         return nm;
     }

@@ -241,8 +241,8 @@ extern "C" int oracle_search_by_bow_kfkf_bf(const uint8_t* d1, const float* a1, 
 // assign[n2] = query index assigned to frame keypoint i2 or -1 (F.mvpMapPoints[bestIdx] = pMP); returns nmatches.
 extern "C" int oracle_search_by_projection(const oracle_keypoint* k2, const uint8_t* d2, int n2, const float* bounds4, uint8_t* occupied,
                                            const float* q_xyr, const int32_t* q_lev, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed, int nq,
-                                           int mode, float nnratio, int check_ori, int32_t* assign) {
-    const int TH_HIGH = 100;
+                                           int mode, float nnratio, int check_ori, int th_high, int32_t* assign) {
+    const int TH_HIGH = th_high > 0 ? th_high : 100;          // ORBdist of the relocalisation variant (ORBmatcher.cc:1559), else TH_HIGH
     for (int i = 0; i < n2; i++) assign[i] = -1;
     int nmatches = 0;
     std::vector<int32_t> cs(64 * 48 + 1), ci(n2 > 0 ? n2 : 1), cand(n2 > 0 ? n2 : 1);

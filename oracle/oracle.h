@@ -88,7 +88,7 @@ int oracle_search_by_bow_kfkf_bf(const uint8_t* d1, const float* a1, int n1, con
 // on ready-made projections; occupied [n2] in/out, assign [n2] out; returns nmatches
 int oracle_search_by_projection(const oracle_keypoint* k2, const uint8_t* d2, int n2, const float* bounds4, uint8_t* occupied,
                                 const float* q_xyr, const int32_t* q_lev, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed, int nq,
-                                int mode, float nnratio, int check_ori, int32_t* assign);
+                                int mode, float nnratio, int check_ori, int th_high, int32_t* assign);
 // SearchForInitialization (src/ORBmatcher.cc:409-524) on arrays; prev_matched [n1][2] in/out, matches12 [n1] out; returns nmatches
 int oracle_search_for_initialization(const oracle_keypoint* k1, const uint8_t* d1, int n1, const oracle_keypoint* k2, const uint8_t* d2, int n2,
                                      const float* bounds4, float* prev_matched, int window, float nnratio, int check_ori, int32_t* matches12);

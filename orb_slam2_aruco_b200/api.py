@@ -308,9 +308,9 @@ def search_for_initialization(kps1_un, desc1, kps2_un, desc2, bounds4, prev_matc
     return n, m12, prev
 
 
-def search_by_projection(kps_un, desc, bounds4, occupied, q_xyr, q_levels, q_desc, q_angle, q_observed, mode, nnratio=0.8, check_ori=True, device=0):
+def search_by_projection(kps_un, desc, bounds4, occupied, q_xyr, q_levels, q_desc, q_angle, q_observed, mode, nnratio=0.8, check_ori=True, th_high=100, device=0):
     """SearchByProjection(Frame, mapPoints, th) (mode 0, ORBmatcher.cc:45-129) / SearchByProjection(Current, Last, th, mono) (mode 1,
-    ORBmatcher.cc:1332-1474) on ready-made projections -> (nmatches, assign[n_frame], updated occupied)"""
+    ORBmatcher.cc:1332-1474; with th_high = ORBdist the relocalisation variant :1476-1603) on ready-made projections -> (nmatches, assign[n_frame], updated occupied)"""
     k = np.ascontiguousarray(kps_un); assert k.dtype == KP_DTYPE
     d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
     occ = np.ascontiguousarray(occupied, np.uint8).copy()
@@ -319,7 +319,7 @@ def search_by_projection(kps_un, desc, bounds4, occupied, q_xyr, q_levels, q_des
     assign = np.full(len(k), -1, np.int32)
     b = np.ascontiguousarray(bounds4, np.float32)
     n = check(lib().b200_match_by_projection_host(ptr(k), ptr(d), len(k), ptr(b), ptr(occ), ptr(q3), ptr(lv), ptr(qd), ptr(qa), ptr(qo), len(q3), int(mode),
-                                                  float(nnratio), int(bool(check_ori)), ptr(assign), int(device)))
+                                                  float(nnratio), int(bool(check_ori)), int(th_high), ptr(assign), int(device)))
     return n, assign, occ
 
 

@@ -631,7 +631,8 @@ int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8
 
 int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_frame, const float* bounds4, uint8_t* occupied,
                                   const float* q_xyr, const int32_t* q_levels, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed,
-                                  int n_queries, int mode, float ratio, int check_ori, int32_t* assign, int device) {
+                                  int n_queries, int mode, float ratio, int check_ori, int th_high, int32_t* assign, int device) {
+    if (th_high <= 0) th_high = 100;                            // TH_HIGH, ORBmatcher.cc:38
     if (n_frame < 0 || n_queries < 0 || (mode != 0 && mode != 1)) return fail(B200_EINVAL, "bad %s", "sizes or mode");
     int rc = use_device(device);
     if (rc) return rc;
@@ -655,7 +656,7 @@ int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* de
     B200_LAUNCH(k_init_dist, (n_queries * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)qd.p, n_queries, (const ulonglong4*)d2.p, (const int*)cand.p,
                 (const int*)cnt.p, row_cap, (int*)dist.p);
     B200_LAUNCH(k_proj_resolve, 1, 32, 0, 0, (const b200_keypoint*)k2.p, n_frame, (const int*)cand.p, (const int*)cnt.p, (const int*)dist.p, row_cap,
-                (const float*)qa.p, (const unsigned char*)qo.p, n_queries, mode, ratio, 100, check_ori, (unsigned char*)occ.p, (int*)asg.p, (int*)eb.p, (int*)ei.p,
+                (const float*)qa.p, (const unsigned char*)qo.p, n_queries, mode, ratio, th_high, check_ori, (unsigned char*)occ.p, (int*)asg.p, (int*)eb.p, (int*)ei.p,
                 (int*)res.p);
     B200_CUDA(cudaDeviceSynchronize());
     int r2[2] = {0, 0};

@@ -158,7 +158,7 @@ def test_search_by_projection_modes_match_oracle(built_lib):
     rng = np.random.default_rng(12)
     sf = 1.2 ** kq["octave"].astype(np.float32)
     bounds = np.array([0, 640, 0, 480], np.float32)
-    for mode, ratio, ori in ((0, 0.8, True), (0, 0.6, False), (1, 0.9, True), (1, 0.9, False)):
+    for mode, ratio, ori, th_high in ((0, 0.8, True, 100), (0, 0.6, False, 100), (1, 0.9, True, 100), (1, 0.9, False, 100), (1, 0.9, True, 64)):
         nq = len(kq)
         xyr = np.stack([kq["x"] - 3 + rng.normal(0, 2, nq), kq["y"] - 2 + rng.normal(0, 2, nq),
                         (rng.choice([2.5, 4.0], nq) if mode == 0 else np.full(nq, 7.0)) * sf], 1).astype(np.float32)
@@ -167,8 +167,8 @@ def test_search_by_projection_modes_match_oracle(built_lib):
         occupied = (rng.random(len(kf)) < 0.1).astype(np.uint8)
         want_occ = occupied.copy(); want = np.zeros(len(kf), np.int32)
         nw = oracle.lib().oracle_search_by_projection(P(kf), P(df), len(kf), P(bounds), P(want_occ), P(xyr), P(lev), P(dq), P(kq["angle"].copy()), P(observed), nq,
-                                                      mode, C.c_float(ratio), int(ori), P(want))
-        n, assign, occ = search_by_projection(kf, df, bounds, occupied, xyr, lev, dq, kq["angle"].copy(), observed, mode, ratio, ori)
+                                                      mode, C.c_float(ratio), int(ori), th_high, P(want))
+        n, assign, occ = search_by_projection(kf, df, bounds, occupied, xyr, lev, dq, kq["angle"].copy(), observed, mode, ratio, ori, th_high)
         assert n == nw and np.array_equal(assign, want) and np.array_equal(occ, want_occ), (mode, ratio, ori)
         assert n > 300
     n, assign, occ = search_by_projection(kf, df, bounds, np.zeros(len(kf), np.uint8), np.zeros((0, 3)), np.zeros((0, 2)), np.zeros((0, 32)), np.zeros(0), np.zeros(0), 0)
