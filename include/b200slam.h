@@ -62,6 +62,7 @@ typedef struct b200_marker_pose {
 
 typedef struct b200_orb_s*   b200_orb_t;
 typedef struct b200_aruco_s* b200_aruco_t;
+typedef struct b200_voc_s*   b200_voc_t;
 
 const char* b200_last_error(void);
 /* number of CUDA kernel launches issued by this library in the calling process so far */
@@ -213,6 +214,21 @@ int b200_frame_assign_grid(const b200_keypoint* kps_un, const int32_t* counts, i
 int b200_frame_features_in_area(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                                 const float* queries_xyr, const int32_t* query_levels, int n_queries,
                                 int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream);
+
+
+/* ---------------------------------------------------------------- bag of words ------- */
+/* A DBoW2 vocabulary tree in the node order of TemplatedVocabulary::loadFromTextFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1425):
+ * node 0 is the root, nodes 1 .. n_nodes-1 follow in file order with parent [i] (< i), is_leaf [i], node_desc [i][32] and node_weight [i]
+ * (entries 0 are ignored); children keep file order and word ids are assigned in order of leaf appearance, like the reference. */
+int b200_voc_create(b200_voc_t* out, int k, int L, int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* node_desc,
+                    const double* node_weight, int device);
+int b200_voc_destroy(b200_voc_t h);
+int b200_voc_num_words(b200_voc_t h);
+/* TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) (:1218-1259) for n descriptors (device, 32-byte aligned):
+ * word_id [n], weight [n] (WordValue = double), node_id [n] = the node at level L - levelsup (0 when that level is <= 0), device outputs.
+ * Frame::ComputeBoW (src/Frame.cc:348-355) builds mBowVec / mFeatVec from these (b200slam_adapters.hpp: transform). */
+int b200_voc_transform(b200_voc_t h, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id, void* stream);
+int b200_voc_transform_host(b200_voc_t h, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id);
 
 #ifdef __cplusplus
 }

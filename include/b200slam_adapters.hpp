@@ -15,7 +15,11 @@
 // must build in an image without OpenCV).  Header only; link with -lb200slam.
 #pragma once
 #include <cassert>
+#include <cmath>
 #include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -252,6 +256,83 @@ public:
 protected:
     float mfNNratio;
     bool mbCheckOrientation;
+    int device_;
+};
+
+}  // namespace ORB_SLAM2
+
+// DBoW2 containers the reference fills in Frame::ComputeBoW (Thirdparty/DBoW2/DBoW2/BowVector.h:52, FeatureVector.h:21-22)
+namespace DBoW2 {
+typedef unsigned int WordId;
+typedef unsigned int NodeId;
+typedef double WordValue;
+typedef std::map<WordId, WordValue> BowVector;
+typedef std::map<NodeId, std::vector<unsigned int> > FeatureVector;
+}  // namespace DBoW2
+
+namespace ORB_SLAM2 {
+
+// ORB_SLAM2::ORBVocabulary (include/ORBVocabulary.h:31 = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>): the two calls the reference
+// makes, loadFromTextFile (System.cc:80) and transform(features, BowVector, FeatureVector, 4) (Frame.cc:353, KeyFrame.cc ComputeBoW).
+// The per-descriptor tree descent runs on the device (b200_voc_transform); the two std::maps are assembled from its output arrays
+// exactly like TemplatedVocabulary::transform does for TF_IDF weighting + L1 scoring (TemplatedVocabulary.h:1145-1194).
+class ORBVocabulary {
+public:
+    explicit ORBVocabulary(int device = 0) : h_(nullptr), device_(device) {}
+    ~ORBVocabulary() { if (h_) b200_voc_destroy(h_); }
+    ORBVocabulary(const ORBVocabulary&) = delete;
+    ORBVocabulary& operator=(const ORBVocabulary&) = delete;
+
+    bool loadFromTextFile(const std::string& filename) {          // TemplatedVocabulary.h:1338-1425
+        std::ifstream f(filename.c_str());
+        if (!f.good()) return false;
+        std::string s;
+        std::getline(f, s);
+        std::stringstream ss(s);
+        int k = -1, L = -1, n1 = -1, n2 = -1;
+        ss >> k >> L >> n1 >> n2;
+        if (k < 0 || k > 20 || L < 1 || L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) return false;
+        std::vector<int32_t> parent(1, 0);
+        std::vector<uint8_t> leaf(1, 0), desc(32, 0);
+        std::vector<double> weight(1, 0.0);
+        while (std::getline(f, s)) {
+            if (s.empty()) continue;
+            std::stringstream sn(s);
+            int pid = 0, is_leaf = 0;
+            sn >> pid >> is_leaf;
+            parent.push_back(pid); leaf.push_back(is_leaf > 0 ? 1 : 0);
+            for (int i = 0; i < 32; i++) { int v = 0; sn >> v; desc.push_back((uint8_t)v); }
+            double w = 0; sn >> w; weight.push_back(w);
+        }
+        if (h_) { b200_voc_destroy(h_); h_ = nullptr; }
+        return b200_voc_create(&h_, k, L, (int)parent.size(), parent.data(), leaf.data(), desc.data(), weight.data(), device_) == B200_OK;
+    }
+    bool empty() const { return h_ == nullptr; }
+    unsigned int size() const { return h_ ? (unsigned int)b200_voc_num_words(h_) : 0u; }
+
+    // void transform(const std::vector<TDescriptor>& features, BowVector& v, FeatureVector& fv, int levelsup) const (TemplatedVocabulary.h:1127)
+    // with the descriptors as the rows of mDescriptors (Converter::toDescriptorVector only splits the matrix into rows)
+    void transform(const cv::Mat& descriptors, DBoW2::BowVector& v, DBoW2::FeatureVector& fv, int levelsup) const {
+        v.clear(); fv.clear();
+        if (empty()) return;
+        const int n = descriptors.rows;
+        std::vector<uint8_t> d((size_t)n * 32);
+        for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], descriptors.ptr(i), 32);
+        std::vector<int32_t> word(n), node(n);
+        std::vector<double> weight(n);
+        b200slam_detail::check(b200_voc_transform_host(h_, d.data(), n, levelsup, word.data(), weight.data(), node.data()));
+        for (int i = 0; i < n; i++)
+            if (weight[i] > 0) {                                   // not stopped
+                v[(DBoW2::WordId)word[i]] += weight[i];           // BowVector::addWeight
+                fv[(DBoW2::NodeId)node[i]].push_back((unsigned int)i);
+            }
+        double norm = 0.0;                                         // BowVector::normalize(L1)
+        for (DBoW2::BowVector::iterator it = v.begin(); it != v.end(); ++it) norm += std::fabs(it->second);
+        if (norm > 0.0) for (DBoW2::BowVector::iterator it = v.begin(); it != v.end(); ++it) it->second /= norm;
+    }
+
+private:
+    b200_voc_t h_;
     int device_;
 };
 

@@ -93,6 +93,12 @@ int oracle_search_by_projection(const oracle_keypoint* k2, const uint8_t* d2, in
 int oracle_search_for_initialization(const oracle_keypoint* k1, const uint8_t* d1, int n1, const oracle_keypoint* k2, const uint8_t* d2, int n2,
                                      const float* bounds4, float* prev_matched, int window, float nnratio, int check_ori, int32_t* matches12);
 
+// ---- bag of words: restatement of DBoW2 TemplatedVocabulary::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259) ----------
+void oracle_voc_transform(const int32_t* parent, const uint8_t* is_leaf, const uint8_t* node_desc, const double* node_weight, int n_nodes, int L,
+                          const uint8_t* feat, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id);
+void oracle_voc_vectors(const int32_t* word_id, const double* weight, const int32_t* node_id, int n,
+                        int32_t* bow_words, double* bow_values, int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_items, int32_t* counts2);
+
 #ifdef __cplusplus
 }
 #endif

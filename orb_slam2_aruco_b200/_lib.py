@@ -68,6 +68,11 @@ def lib():
         L.b200_aruco_detect_host.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp]
         L.b200_aruco_pose.argtypes = [vp, vp, i32, i32, f32, vp, vp, i32, vp]
         L.b200_aruco_pose_host.argtypes = [vp, i32, f32, vp, vp, i32]
+        L.b200_voc_create.argtypes = [C.POINTER(vp), i32, i32, i32, vp, vp, vp, vp, i32]
+        L.b200_voc_destroy.argtypes = [vp]
+        L.b200_voc_num_words.argtypes = [vp]
+        L.b200_voc_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+        L.b200_voc_transform_host.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.b200_frame_undistort.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
         L.b200_frame_image_bounds.argtypes = [i32, i32, vp, vp, i32]
         L.b200_frame_assign_grid.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, vp]

@@ -519,3 +519,72 @@ class FrameGrid:
         s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
         check(lib().b200_frame_features_in_area(ptr(kps_un_f), ptr(cell_start_f), ptr(cell_items_f), ptr(self.bounds), ptr(queries_xyr),
                                                 ptr(query_levels), n, ptr(out_idx), ptr(out_count), row_cap, self._device, s))
+
+
+class ORBVocabulary:
+    """DBoW2 vocabulary tree (ORB_SLAM2::ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>, reference
+    include/ORBVocabulary.h:31): loadFromTextFile (TemplatedVocabulary.h:1338-1425) and transform (:1127-1259) for the configuration
+    of ORBvoc.txt (TF_IDF weighting, L1 scoring).  The per-descriptor descent runs on the device; BowVector / FeatureVector (host
+    std::maps in the reference) are assembled from its three output arrays."""
+
+    def __init__(self, k, L, parent, is_leaf, node_desc, node_weight, device=0):
+        self.k, self.L = int(k), int(L)
+        self.parent = np.ascontiguousarray(parent, np.int32)
+        self.is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        self.node_desc = np.ascontiguousarray(node_desc, np.uint8).reshape(-1, 32)
+        self.node_weight = np.ascontiguousarray(node_weight, np.float64)
+        assert len(self.parent) == len(self.is_leaf) == len(self.node_desc) == len(self.node_weight)
+        self._device = int(device)
+        h = C.c_void_p()
+        check(lib().b200_voc_create(C.byref(h), self.k, self.L, len(self.parent), ptr(self.parent), ptr(self.is_leaf), ptr(self.node_desc),
+                                    ptr(self.node_weight), self._device))
+        self._h = h
+
+    @classmethod
+    def loadFromTextFile(cls, path, device=0):
+        """the text format of ORBvoc.txt: 'k L scoring weighting', then one node per line: parent isLeaf d0 .. d31 weight"""
+        with open(path) as fh:
+            k, L, n1, n2 = [int(v) for v in fh.readline().split()[:4]]
+            if k < 0 or k > 20 or L < 1 or L > 10 or n1 < 0 or n1 > 5 or n2 < 0 or n2 > 3:
+                raise ValueError("Vocabulary loading failure: This is not a correct text file!")
+            rows = np.loadtxt(fh, dtype=np.float64, ndmin=2)
+        parent = np.concatenate([[0], rows[:, 0]]).astype(np.int32)
+        leaf = np.concatenate([[0], rows[:, 1] > 0]).astype(np.uint8)
+        desc = np.concatenate([np.zeros((1, 32)), rows[:, 2:34]]).astype(np.uint8)
+        weight = np.concatenate([[0.0], rows[:, 34]])
+        return cls(k, L, parent, leaf, desc, weight, device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib().b200_voc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return check(lib().b200_voc_num_words(self._h))
+
+    def descend(self, descriptors, levelsup=4):
+        """(word_id, weight, node_id) per descriptor: transform(feature, id, weight, &nid, levelsup)"""
+        d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        w = np.zeros(len(d), np.int32); wt = np.zeros(len(d), np.float64); nid = np.zeros(len(d), np.int32)
+        check(lib().b200_voc_transform_host(self._h, ptr(d), len(d), int(levelsup), ptr(w), ptr(wt), ptr(nid)))
+        return w, wt, nid
+
+    def transform(self, descriptors, levelsup=4):
+        """transform(features, BowVector&, FeatureVector&, levelsup) (Frame::ComputeBoW, src/Frame.cc:348-355) ->
+        (BowVector as {word: value}, FeatureVector as {node: [feature indices]}), both in ascending key order like the std::maps"""
+        w, wt, nid = self.descend(descriptors, levelsup)
+        bow, fv = {}, {}
+        for i in range(len(w)):
+            if wt[i] > 0:                                   # not stopped
+                bow[int(w[i])] = bow.get(int(w[i]), 0.0) + float(wt[i])
+                fv.setdefault(int(nid[i]), []).append(i)
+        norm = sum(abs(v) for _, v in sorted(bow.items()))  # BowVector::normalize(L1), summed in key order
+        if norm > 0.0:
+            bow = {k2: v / norm for k2, v in bow.items()}
+        return dict(sorted(bow.items())), dict(sorted(fv.items()))

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200slam.so")
-SOURCES = ["common.cu", "orb.cu", "match.cu", "aruco.cu", "pose.cu", "frame.cu"]
+SOURCES = ["common.cu", "orb.cu", "match.cu", "aruco.cu", "pose.cu", "frame.cu", "bow.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false"]
 

@@ -30,6 +30,9 @@ int main(int argc, char** argv) {
         ORB_SLAM2::ORBmatcher matcher(0.7f, true);                        // Tracking.cc:917
         std::vector<int> matches;
         const int nm = matcher.SearchByBoW(desc, keys, desc, keys, matches);
+        ORB_SLAM2::ORBVocabulary voc;                                     // System.cc:80; no vocabulary file here: empty() like an unloaded one
+        DBoW2::BowVector bowv; DBoW2::FeatureVector featv;
+        voc.transform(desc, bowv, featv, 4);                             // Frame.cc:353 (no-op while empty)
         const int dist = ORB_SLAM2::ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, desc.ptr(0)), cv::Mat(1, 32, CV_8U, desc.ptr(1)));
         FILE* o = fopen(argv[5], "wb");
         int hdr[4] = {(int)keys.size(), (int)markers.size(), nm, dist};
