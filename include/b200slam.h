@@ -141,6 +141,14 @@ int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_re
 int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8_t* desc1, int n1,
                                        const b200_keypoint* kps2_un, const uint8_t* desc2, int n2, const float* bounds4,
                                        float* prev_matched, int window, float ratio, int check_ori, int32_t* matches12, int device);
+/* ORBmatcher::SearchByBoW over the two FeatureVectors (b200_voc_transform), merge-walked on the host into n_groups common vocabulary nodes:
+ *   mode 0  SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)        (include/ORBmatcher.h:55, src/ORBmatcher.cc:159-292)   out [n_c]: out[idxF] = idxKF
+ *   mode 1  SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)     (include/ORBmatcher.h:56, src/ORBmatcher.cc:526-659)   out [n_q]: out[idx1] = idx2
+ * Group g: query features q_idx[grp_q_ofs[g] .. grp_q_ofs[g+1]) (node order, only those with a good MapPoint) against candidate features
+ * c_idx[grp_c_ofs[g] .. grp_c_ofs[g+1]) (mode 1: only those with a good MapPoint).  HOST pointers.  th_low <= 0: TH_LOW = 50.  Returns nmatches. */
+int b200_match_by_bow_host(const uint8_t* q_desc, const float* q_angle, int n_q, const uint8_t* c_desc, const float* c_angle, int n_c,
+                           const int32_t* grp_q_ofs, const int32_t* q_idx, const int32_t* grp_c_ofs, const int32_t* c_idx, int n_groups,
+                           int mode, float ratio, int th_low, int check_ori, int32_t* out, int device);
 /* ORBmatcher::SearchByProjection on ready-made projections (the projection of the map points is host glue in the reference):
  *   mode 0  SearchByProjection(Frame&, const vector<MapPoint*>&, th)          (src/ORBmatcher.cc:45-129, Tracking::SearchLocalPoints)
  *   mode 1  SearchByProjection(Frame& Current, const Frame& Last, th, mono)    (src/ORBmatcher.cc:1332-1474, TrackWithMotionModel); with

@@ -57,6 +57,15 @@ inline void check(int rc) { if (rc < 0) throw std::runtime_error(std::string("b2
 static_assert(sizeof(b200_keypoint) == 28, "b200_keypoint must mirror cv::KeyPoint");
 }
 
+// DBoW2 containers the reference fills in Frame::ComputeBoW (Thirdparty/DBoW2/DBoW2/BowVector.h:52, FeatureVector.h:21-22)
+namespace DBoW2 {
+typedef unsigned int WordId;
+typedef unsigned int NodeId;
+typedef double WordValue;
+typedef std::map<WordId, WordValue> BowVector;
+typedef std::map<NodeId, std::vector<unsigned int> > FeatureVector;
+}  // namespace DBoW2
+
 namespace ORB_SLAM2 {
 
 class ORBextractor {
@@ -202,6 +211,23 @@ public:
         return nm;
     }
 
+    // int SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint*> &vpMapPointMatches) (ORBmatcher.h:55, ORBmatcher.cc:159-292) on what it
+    // reads: pKF->mFeatVec / F.mFeatVec, the descriptors and undistorted keypoints of both, and kfGood[i] = "vpMapPointsKF[i] && !isBad()".
+    // matches[idxF] = keyframe index whose MapPoint the frame keypoint receives, or -1; returns nmatches.
+    int SearchByBoW(const cv::Mat& kfDescriptors, const std::vector<cv::KeyPoint>& kfKeysUn, const std::vector<bool>& kfGood,
+                    const DBoW2::FeatureVector& kfFeatVec, const cv::Mat& fDescriptors, const std::vector<cv::KeyPoint>& fKeysUn,
+                    const DBoW2::FeatureVector& fFeatVec, std::vector<int>& matches) {
+        return byBoW(0, kfDescriptors, kfKeysUn, &kfGood, kfFeatVec, fDescriptors, fKeysUn, nullptr, fFeatVec, matches);
+    }
+
+    // int SearchByBoW(KeyFrame *pKF1, KeyFrame* pKF2, std::vector<MapPoint*> &vpMatches12) (ORBmatcher.h:56, ORBmatcher.cc:526-659) with the
+    // two feature vectors; good1 / good2 = the keyframes' map points that exist and are not bad.  matches12[idx1] = index in KF2 or -1.
+    int SearchByBoW_KF(const cv::Mat& desc1, const std::vector<cv::KeyPoint>& keysUn1, const std::vector<bool>& good1, const DBoW2::FeatureVector& featVec1,
+                       const cv::Mat& desc2, const std::vector<cv::KeyPoint>& keysUn2, const std::vector<bool>& good2, const DBoW2::FeatureVector& featVec2,
+                       std::vector<int>& matches12) {
+        return byBoW(1, desc1, keysUn1, &good1, featVec1, desc2, keysUn2, &good2, featVec2, matches12);
+    }
+
     // Brute-force core of SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (ORBmatcher.h:56,
     // ORBmatcher.cc:526-659): strict bestDist1 < TH_LOW, histogram factor 1.0f / HISTO_LENGTH; matches12[idx1] = index in KF2 or -1.
     int SearchByBoW_KF(const cv::Mat& desc1, const std::vector<cv::KeyPoint>& keysUn1, const cv::Mat& desc2, const std::vector<cv::KeyPoint>& keysUn2,
@@ -254,21 +280,41 @@ public:
     }
 
 protected:
+    // the merge walk over common vocabulary nodes (ORBmatcher.cc:185-279 / 547-632) builds the groups of b200_match_by_bow_host
+    int byBoW(int mode, const cv::Mat& desc1, const std::vector<cv::KeyPoint>& keys1, const std::vector<bool>* good1, const DBoW2::FeatureVector& fv1,
+              const cv::Mat& desc2, const std::vector<cv::KeyPoint>& keys2, const std::vector<bool>* good2, const DBoW2::FeatureVector& fv2,
+              std::vector<int>& out) {
+        const int n1 = desc1.rows, n2 = desc2.rows;
+        std::vector<uint8_t> d1((size_t)n1 * 32), d2((size_t)n2 * 32);
+        std::vector<float> a1(n1), a2(n2);
+        for (int i = 0; i < n1; i++) { std::memcpy(&d1[(size_t)i * 32], desc1.ptr(i), 32); a1[i] = keys1[i].angle; }
+        for (int i = 0; i < n2; i++) { std::memcpy(&d2[(size_t)i * 32], desc2.ptr(i), 32); a2[i] = keys2[i].angle; }
+        std::vector<int32_t> gq(1, 0), gc(1, 0), qi, ci;
+        DBoW2::FeatureVector::const_iterator it1 = fv1.begin(), it2 = fv2.begin();
+        while (it1 != fv1.end() && it2 != fv2.end()) {
+            if (it1->first == it2->first) {
+                for (unsigned int i : it1->second) if (!good1 || (*good1)[i]) qi.push_back((int32_t)i);
+                for (unsigned int i : it2->second) if (!good2 || (*good2)[i]) ci.push_back((int32_t)i);
+                gq.push_back((int32_t)qi.size()); gc.push_back((int32_t)ci.size());
+                ++it1; ++it2;
+            } else if (it1->first < it2->first) it1 = fv1.lower_bound(it2->first);
+            else it2 = fv2.lower_bound(it1->first);
+        }
+        out.assign(mode == 0 ? n2 : n1, -1);
+        std::vector<int32_t> o(out.size() + 1, -1);
+        const int nm = b200_match_by_bow_host(d1.data(), a1.data(), n1, d2.data(), a2.data(), n2, gq.data(), qi.data(), gc.data(), ci.data(), (int)gq.size() - 1,
+                                              mode, mfNNratio, TH_LOW, mbCheckOrientation ? 1 : 0, o.data(), device_);
+        b200slam_detail::check(nm);
+        for (size_t i = 0; i < out.size(); i++) out[i] = o[i];
+        return nm;
+    }
+
     float mfNNratio;
     bool mbCheckOrientation;
     int device_;
 };
 
 }  // namespace ORB_SLAM2
-
-// DBoW2 containers the reference fills in Frame::ComputeBoW (Thirdparty/DBoW2/DBoW2/BowVector.h:52, FeatureVector.h:21-22)
-namespace DBoW2 {
-typedef unsigned int WordId;
-typedef unsigned int NodeId;
-typedef double WordValue;
-typedef std::map<WordId, WordValue> BowVector;
-typedef std::map<NodeId, std::vector<unsigned int> > FeatureVector;
-}  // namespace DBoW2
 
 namespace ORB_SLAM2 {
 

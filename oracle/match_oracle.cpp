@@ -284,3 +284,110 @@ extern "C" int oracle_search_by_projection(const oracle_keypoint* k2, const uint
     }
     return nmatches;
 }
+
+// ---- SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:159-292) over REAL feature vectors ------------------------------
+// FeatureVectors as sorted arrays (nodes [nn], start [nn + 1], items): the merge walk over common vocabulary nodes, the greedy
+// vpMapPointMatches and the rotation histogram (factor HISTO_LENGTH / 360) follow the reference statement by statement.
+// kf_valid [n_kf] = "vpMapPointsKF[i] && !isBad()".  matches [n_f] = keyframe index or -1; returns nmatches.
+extern "C" int oracle_search_by_bow_nodes(const uint8_t* dkf, const float* akf, const uint8_t* kf_valid, const int32_t* kf_nodes, const int32_t* kf_start,
+                                          const int32_t* kf_items, int kf_nn, const uint8_t* df, const float* af, int n_f, const int32_t* f_nodes,
+                                          const int32_t* f_start, const int32_t* f_items, int f_nn, float nnratio, int check_ori, int32_t* matches) {
+    for (int i = 0; i < n_f; i++) matches[i] = -1;
+    int nmatches = 0;
+    std::vector<std::vector<int> > rotHist(HISTO_LENGTH);
+    const float factor = HISTO_LENGTH / 360.0f;
+    int a = 0, b = 0;
+    while (a < kf_nn && b < f_nn) {
+        if (kf_nodes[a] == f_nodes[b]) {
+            for (int iKF = kf_start[a]; iKF < kf_start[a + 1]; iKF++) {
+                const int realIdxKF = kf_items[iKF];
+                if (!kf_valid[realIdxKF]) continue;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = f_start[b]; iF < f_start[b + 1]; iF++) {
+                    const int realIdxF = f_items[iF];
+                    if (matches[realIdxF] >= 0) continue;
+                    const int dist = descriptor_distance(dkf + 32 * (size_t)realIdxKF, df + 32 * (size_t)realIdxF);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        matches[bestIdxF] = realIdxKF;
+                        if (check_ori) {
+                            float rot = akf[realIdxKF] - af[bestIdxF];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(bestIdxF);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (kf_nodes[a] < f_nodes[b]) { while (a < kf_nn && kf_nodes[a] < f_nodes[b]) a++; }      // lower_bound
+        else { while (b < f_nn && f_nodes[b] < kf_nodes[a]) b++; }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist.data(), HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { matches[idx] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// ---- SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (src/ORBmatcher.cc:526-659) over real feature vectors; matches12 [n1] out ---------
+extern "C" int oracle_search_by_bow_kfkf_nodes(const uint8_t* d1, const float* a1, const uint8_t* valid1, int n1, const int32_t* nodes1, const int32_t* start1,
+                                               const int32_t* items1, int nn1, const uint8_t* d2, const float* a2, const uint8_t* valid2, int n2,
+                                               const int32_t* nodes2, const int32_t* start2, const int32_t* items2, int nn2, float nnratio, int check_ori,
+                                               int32_t* matches12) {
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<bool> vbMatched2(n2, false);
+    std::vector<std::vector<int> > rotHist(HISTO_LENGTH);
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = start1[a]; i1 < start1[a + 1]; i1++) {
+                const int idx1 = items1[i1];
+                if (!valid1[idx1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = start2[b]; i2 < start2[b + 1]; i2++) {
+                    const int idx2 = items2[i2];
+                    if (vbMatched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = descriptor_distance(d1 + 32 * (size_t)idx1, d2 + 32 * (size_t)idx2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        matches12[idx1] = bestIdx2;
+                        vbMatched2[bestIdx2] = true;
+                        if (check_ori) {
+                            float rot = a1[idx1] - a2[bestIdx2];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(idx1);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (nodes1[a] < nodes2[b]) { while (a < nn1 && nodes1[a] < nodes2[b]) a++; }
+        else { while (b < nn2 && nodes2[b] < nodes1[a]) b++; }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist.data(), HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { matches12[idx] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}

@@ -81,6 +81,15 @@ void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, 
 int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                             float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 
+// SearchByBoW(KeyFrame*, Frame&) (src/ORBmatcher.cc:159-292) over real FeatureVectors given as sorted arrays (nodes, start, items); matches [n_f] out
+int oracle_search_by_bow_nodes(const uint8_t* dkf, const float* akf, const uint8_t* kf_valid, const int32_t* kf_nodes, const int32_t* kf_start,
+                               const int32_t* kf_items, int kf_nn, const uint8_t* df, const float* af, int n_f, const int32_t* f_nodes,
+                               const int32_t* f_start, const int32_t* f_items, int f_nn, float nnratio, int check_ori, int32_t* matches);
+// SearchByBoW(KeyFrame*, KeyFrame*) (src/ORBmatcher.cc:526-659) over real FeatureVectors; matches12 [n1] out
+int oracle_search_by_bow_kfkf_nodes(const uint8_t* d1, const float* a1, const uint8_t* valid1, int n1, const int32_t* nodes1, const int32_t* start1,
+                                    const int32_t* items1, int nn1, const uint8_t* d2, const float* a2, const uint8_t* valid2, int n2,
+                                    const int32_t* nodes2, const int32_t* start2, const int32_t* items2, int nn2, float nnratio, int check_ori,
+                                    int32_t* matches12);
 // SearchByBoW(KeyFrame*, KeyFrame*) (src/ORBmatcher.cc:526-659), one all-inclusive vocabulary node; matches12 [n1] out; returns nmatches
 int oracle_search_by_bow_kfkf_bf(const uint8_t* d1, const float* a1, int n1, const uint8_t* d2, const float* a2, int n2,
                                  float nnratio, int check_ori, int32_t* matches12);

@@ -234,6 +234,43 @@ class ORBmatcher:
         m12[m21[0, idx2]] = idx2
         return int(nm[0]), m12
 
+    @staticmethod
+    def common_node_groups(featvec_q, valid_q, featvec_c, valid_c=None):
+        """The merge walk of SearchByBoW over two FeatureVectors ({node: [feature indices]}, ascending nodes like the std::map;
+        ORBmatcher.cc:185-279): one group per common node.  Query features without a good MapPoint are dropped here (the reference
+        `continue`s on them), and in the KeyFrame-KeyFrame form (valid_c given) so are such candidates.
+        Returns (grp_q_ofs, q_idx, grp_c_ofs, c_idx) for b200_match_by_bow_host."""
+        gq, gc, qi, ci = [0], [0], [], []
+        for node in sorted(set(featvec_q) & set(featvec_c)):
+            qs = [i for i in featvec_q[node] if valid_q is None or valid_q[i]]
+            cs = [i for i in featvec_c[node] if valid_c is None or valid_c[i]]
+            qi += qs; ci += cs
+            gq.append(len(qi)); gc.append(len(ci))
+        a = lambda v: np.asarray(v, np.int32)
+        return a(gq), a(qi), a(gc), a(ci)
+
+    def _by_bow(self, mode, d1, a1, d2, a2, groups):
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32)
+        d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        a1 = np.ascontiguousarray(a1, np.float32)
+        a2 = np.ascontiguousarray(a2, np.float32)
+        gq, qi, gc, ci = (np.ascontiguousarray(g, np.int32) for g in groups)
+        out = np.full(max(len(d2) if mode == 0 else len(d1), 1), -1, np.int32)
+        n = check(lib().b200_match_by_bow_host(ptr(d1), ptr(a1), len(d1), ptr(d2), ptr(a2), len(d2), ptr(gq), ptr(qi), ptr(gc), ptr(ci), len(gq) - 1,
+                                               mode, self.mfNNratio, self.TH_LOW, int(self.mbCheckOrientation), ptr(out), self._device))
+        return n, out[:len(d2) if mode == 0 else len(d1)]
+
+    def SearchByBoW_nodes(self, kf_desc, kf_angles, kf_valid, kf_featvec, f_desc, f_angles, f_featvec):
+        """SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (ORBmatcher.h:55, ORBmatcher.cc:159-292) with the real FeatureVectors
+        (ORBVocabulary.transform): per common node, every keyframe feature with a good MapPoint (kf_valid) takes its best free frame
+        feature of the same node.  Returns (nmatches, matches) with matches[idxF] = keyframe index or -1."""
+        return self._by_bow(0, kf_desc, kf_angles, f_desc, f_angles, self.common_node_groups(kf_featvec, kf_valid, f_featvec))
+
+    def SearchByBoW_KF_nodes(self, desc1, angles1, valid1, featvec1, desc2, angles2, valid2, featvec2):
+        """SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (ORBmatcher.h:56, ORBmatcher.cc:526-659) with the real FeatureVectors.
+        Returns (nmatches, matches12) with matches12[idx1] = index in KF2 or -1."""
+        return self._by_bow(1, desc1, angles1, desc2, angles2, self.common_node_groups(featvec1, valid1, featvec2, valid2))
+
     def SearchByBoW_batch(self, kf_desc, kf_angles, f_desc, f_angles, n_frame, histo_factor=None):
         kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
         kf_angles = np.ascontiguousarray(kf_angles, np.float32)

@@ -476,6 +476,90 @@ k_proj_resolve(const b200_keypoint* __restrict__ k2, int n2, const int* __restri
     if (lane == 0) { result[0] = nmatches; result[1] = overflow; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SearchByBoW over real FeatureVectors: the host merge-walks the two vectors (ORBmatcher.cc:185-279 / 547-632) into GROUPS, one per common
+// vocabulary node: a run of query features (already filtered to good map points, in node order) and a run of candidate features.
+//   mode 0  SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)   '<= TH_LOW', factor 30/360, out[idxF] = idxKF    (ORBmatcher.cc:159-292)
+//   mode 1  SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)      '<  TH_LOW', factor 1/30,   out[idx1]  = idx2     (ORBmatcher.cc:526-659)
+// All (query, candidate) distances of a group are independent -> k_bow_dist; the taken flags make the accept loop sequential -> one warp.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bow_dist(const ulonglong4* __restrict__ dq, const ulonglong4* __restrict__ dc, const int* __restrict__ q_idx, const int* __restrict__ q_grp,
+           const int* __restrict__ grp_c_ofs, const int* __restrict__ c_idx, const int* __restrict__ q_dofs, int nq, int* __restrict__ dist) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int g = q_grp[q], c0 = grp_c_ofs[g], n = grp_c_ofs[g + 1] - c0, o = q_dofs[q];
+    if (n == 0) return;
+    const ulonglong4 a = dq[q_idx[q]];
+    for (int j = lane; j < n; j += 32) dist[o + j] = hamming256(a, dc[c_idx[c0 + j]]);
+}
+
+__global__ void __launch_bounds__(32)
+k_bow_resolve(const float* __restrict__ q_angle, const float* __restrict__ c_angle, const int* __restrict__ q_idx, const int* __restrict__ q_grp,
+              const int* __restrict__ grp_c_ofs, const int* __restrict__ c_idx, const int* __restrict__ q_dofs, const int* __restrict__ dist, int nq,
+              int mode, float ratio, int th_low, int check_ori, unsigned char* __restrict__ taken, int n_out, int* __restrict__ out,
+              int* __restrict__ ent_bin, int* __restrict__ ent_idx, int* __restrict__ result) {
+    __shared__ int histo[kHistoLen];
+    const int lane = threadIdx.x;
+    if (lane < kHistoLen) histo[lane] = 0;
+    for (int i = lane; i < n_out; i += 32) out[i] = -1;
+    __syncwarp();
+    int nmatches = 0, nent = 0;
+    // HISTO_LENGTH / 360.0f (ORBmatcher.cc:176) against 1.0f / HISTO_LENGTH (ORBmatcher.cc:541)
+    const float factor = mode == 0 ? __fdiv_rn((float)kHistoLen, 360.0f) : __fdiv_rn(1.0f, (float)kHistoLen);
+    const int limit = mode == 0 ? th_low : th_low - 1;
+    for (int q = 0; q < nq; q++) {
+        const int g = q_grp[q], c0 = grp_c_ofs[g], n = grp_c_ofs[g + 1] - c0, o = q_dofs[q];
+        unsigned long long l1 = ~0ull, l2 = ~0ull;
+        for (int j = lane; j < n; j += 32) {
+            if (taken[c_idx[c0 + j]]) continue;
+            const unsigned long long key = ((unsigned long long)dist[o + j] << 32) | (unsigned)j;
+            if (key < l1) { l2 = l1; l1 = key; } else if (key < l2) l2 = key;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, l1, s), o2 = __shfl_xor_sync(0xffffffffu, l2, s);
+            const unsigned long long lo = min(l1, o1), hi = max(l1, o1);
+            l2 = min(hi, min(l2, o2));
+            l1 = lo;
+        }
+        if (l1 == ~0ull) continue;
+        const int best = (int)(l1 >> 32), best2 = l2 != ~0ull ? (int)(l2 >> 32) : 256;
+        if (best > limit || !((float)best < __fmul_rn(ratio, (float)best2))) continue;
+        const int ic = c_idx[c0 + (int)(l1 & 0xffffffffu)], iq = q_idx[q];
+        nmatches++;
+        if (lane == 0) {
+            taken[ic] = 1;
+            if (mode == 0) out[ic] = iq; else out[iq] = ic;
+            if (check_ori) {
+                float rot = __fsub_rn(q_angle[iq], c_angle[ic]);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, factor));
+                if (bin == kHistoLen) bin = 0;
+                bin = max(0, min(bin, kHistoLen - 1));
+                ent_bin[nent] = bin; ent_idx[nent] = mode == 0 ? ic : iq;
+                histo[bin]++;
+            }
+        }
+        nent++;
+        __syncwarp();
+    }
+    __syncwarp();
+    if (check_ori) {
+        int a, b, c;
+        three_maxima(histo, kHistoLen, a, b, c);
+        int removed = 0;
+        for (int e = lane; e < nent; e += 32) {
+            const int bin = ent_bin[e];
+            if (bin != a && bin != b && bin != c) { out[ent_idx[e]] = -1; removed++; }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, s);
+        nmatches -= removed;
+    }
+    if (lane == 0) result[0] = nmatches;
+}
+
 struct MatchScratch { uint32_t* topk; size_t cap; int device; };
 static thread_local MatchScratch g_ms = {nullptr, 0, -1};
 
@@ -665,6 +749,52 @@ int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* de
     B200_CUDA(cudaMemcpy(assign, asg.p, (size_t)n_frame * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(occupied, occ.p, (size_t)n_frame, cudaMemcpyDeviceToHost));
     return r2[0];
+}
+
+int b200_match_by_bow_host(const uint8_t* q_desc, const float* q_angle, int n_q, const uint8_t* c_desc, const float* c_angle, int n_c,
+                           const int32_t* grp_q_ofs, const int32_t* q_idx, const int32_t* grp_c_ofs, const int32_t* c_idx, int n_groups,
+                           int mode, float ratio, int th_low, int check_ori, int32_t* out, int device) {
+    if (th_low <= 0) th_low = 50;                               // TH_LOW, ORBmatcher.cc:39
+    if (n_q < 0 || n_c < 0 || n_groups < 0 || (mode != 0 && mode != 1)) return fail(B200_EINVAL, "bad %s", "sizes or mode");
+    int rc = use_device(device);
+    if (rc) return rc;
+    const int n_out = mode == 0 ? n_c : n_q;
+    if (n_out > 0 && !out) return fail(B200_EINVAL, "null %s", "output pointer");
+    for (int i = 0; i < n_out; i++) out[i] = -1;
+    if (n_groups == 0 || n_q == 0 || n_c == 0) return 0;
+    if (!q_desc || !q_angle || !c_desc || !c_angle || !grp_q_ofs || !q_idx || !grp_c_ofs || !c_idx) return fail(B200_EINVAL, "null %s", "pointer");
+    if (grp_q_ofs[0] != 0 || grp_c_ofs[0] != 0) return fail(B200_EINVAL, "group offsets must start at %s", "0");
+    const int nq = grp_q_ofs[n_groups], nc = grp_c_ofs[n_groups];
+    std::vector<int32_t> q_grp((size_t)std::max(nq, 0)), q_dofs((size_t)std::max(nq, 0) + 1);
+    long long total = 0;
+    for (int g = 0; g < n_groups; g++) {
+        if (grp_q_ofs[g + 1] < grp_q_ofs[g] || grp_c_ofs[g + 1] < grp_c_ofs[g]) return fail(B200_EINVAL, "group offsets must be %s", "non-decreasing");
+        const int cn = grp_c_ofs[g + 1] - grp_c_ofs[g];
+        for (int q = grp_q_ofs[g]; q < grp_q_ofs[g + 1]; q++) { q_grp[q] = g; q_dofs[q] = (int32_t)total; total += cn; }
+        if (total >= (1ll << 31)) return fail(B200_ECAPACITY, "more than %s (query, candidate) pairs", "2^31");
+    }
+    if (nq == 0 || nc == 0) return 0;
+    q_dofs[nq] = (int32_t)total;
+    for (int i = 0; i < nq; i++) if (q_idx[i] < 0 || q_idx[i] >= n_q) return fail(B200_EINVAL, "query index out of %s", "range");
+    for (int i = 0; i < nc; i++) if (c_idx[i] < 0 || c_idx[i] >= n_c) return fail(B200_EINVAL, "candidate index out of %s", "range");
+    DevBuf dq, aq, dc, ac, gco, qi, ci, qg, qo, dist, taken, o, eb, ei, res;
+    if ((rc = dq.upload(q_desc, (size_t)n_q * 32)) || (rc = aq.upload(q_angle, (size_t)n_q * 4)) || (rc = dc.upload(c_desc, (size_t)n_c * 32)) ||
+        (rc = ac.upload(c_angle, (size_t)n_c * 4)) || (rc = gco.upload(grp_c_ofs, (size_t)(n_groups + 1) * 4)) || (rc = qi.upload(q_idx, (size_t)nq * 4)) ||
+        (rc = ci.upload(c_idx, (size_t)nc * 4)) || (rc = qg.upload(q_grp.data(), (size_t)nq * 4)) || (rc = qo.upload(q_dofs.data(), (size_t)(nq + 1) * 4)) ||
+        (rc = dist.alloc((size_t)std::max(total, 1ll) * 4)) || (rc = taken.alloc((size_t)n_c)) || (rc = o.alloc((size_t)n_out * 4)) ||
+        (rc = eb.alloc((size_t)nq * 4)) || (rc = ei.alloc((size_t)nq * 4)) || (rc = res.alloc(8)))
+        return rc;
+    B200_CUDA(cudaMemsetAsync(taken.p, 0, (size_t)n_c, 0));
+    B200_LAUNCH(k_bow_dist, (nq * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)dq.p, (const ulonglong4*)dc.p, (const int*)qi.p, (const int*)qg.p,
+                (const int*)gco.p, (const int*)ci.p, (const int*)qo.p, nq, (int*)dist.p);
+    B200_LAUNCH(k_bow_resolve, 1, 32, 0, 0, (const float*)aq.p, (const float*)ac.p, (const int*)qi.p, (const int*)qg.p, (const int*)gco.p, (const int*)ci.p,
+                (const int*)qo.p, (const int*)dist.p, nq, mode, ratio, th_low, check_ori, (unsigned char*)taken.p, n_out, (int*)o.p, (int*)eb.p, (int*)ei.p,
+                (int*)res.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    int r = 0;
+    B200_CUDA(cudaMemcpy(&r, res.p, 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(out, o.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost));
+    return r;
 }
 
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device) {

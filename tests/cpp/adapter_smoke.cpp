@@ -33,6 +33,14 @@ int main(int argc, char** argv) {
         ORB_SLAM2::ORBVocabulary voc;                                     // System.cc:80; no vocabulary file here: empty() like an unloaded one
         DBoW2::BowVector bowv; DBoW2::FeatureVector featv;
         voc.transform(desc, bowv, featv, 4);                             // Frame.cc:353 (no-op while empty)
+        // SearchByBoW through FeatureVectors (ORBmatcher.cc:159-292): one node holding every feature must reproduce the brute-force answer
+        DBoW2::FeatureVector one;
+        for (int i = 0; i < desc.rows; i++) one[5].push_back((unsigned)i);
+        std::vector<int> matches_fv, matches12;
+        const int nm_fv = matcher.SearchByBoW(desc, keys, std::vector<bool>(keys.size(), true), one, desc, keys, one, matches_fv);
+        if (nm_fv != nm || matches_fv != matches) { fprintf(stderr, "node-wise SearchByBoW differs from brute force\n"); return 1; }
+        matcher.SearchByBoW_KF(desc, keys, std::vector<bool>(keys.size(), true), one, desc, keys, std::vector<bool>(keys.size(), true), one, matches12);
+        if (matches12.size() != keys.size()) { fprintf(stderr, "SearchByBoW_KF size\n"); return 1; }
         const int dist = ORB_SLAM2::ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, desc.ptr(0)), cv::Mat(1, 32, CV_8U, desc.ptr(1)));
         FILE* o = fopen(argv[5], "wb");
         int hdr[4] = {(int)keys.size(), (int)markers.size(), nm, dist};

@@ -125,3 +125,93 @@ def test_cuda_descent_matches_oracle(built_lib, tmp_path, k, L, irregular, level
     for j, node in enumerate(fn[:c2[1]]):
         assert fv[int(node)] == fi[fs[j]:fs[j + 1]].tolist()
     voc.close(); ex.close()
+
+
+def _fv_arrays(fv):
+    """{node: [indices]} -> the oracle's sorted arrays (nodes, start, items)"""
+    nodes = np.array(sorted(fv), np.int32)
+    start = np.zeros(len(nodes) + 1, np.int32)
+    items = []
+    for j, nd in enumerate(nodes):
+        items += list(fv[int(nd)])
+        start[j + 1] = len(items)
+    return nodes, start, np.array(items if items else [0], np.int32)
+
+
+def oracle_bow_nodes(mode, d1, a1, v1, fv1, d2, a2, v2, fv2, ratio, ori):
+    d1 = np.ascontiguousarray(d1); d2 = np.ascontiguousarray(d2)
+    a1 = np.ascontiguousarray(a1, np.float32); a2 = np.ascontiguousarray(a2, np.float32)
+    v1 = np.ascontiguousarray(v1, np.uint8); v2 = np.ascontiguousarray(v2, np.uint8)
+    n1, s1, i1 = _fv_arrays(fv1); n2, s2, i2 = _fv_arrays(fv2)
+    if mode == 0:
+        out = np.zeros(max(len(d2), 1), np.int32)
+        n = oracle.lib().oracle_search_by_bow_nodes(P(d1), P(a1), P(v1), P(n1), P(s1), P(i1), len(n1), P(d2), P(a2), len(d2), P(n2), P(s2), P(i2), len(n2),
+                                                    C.c_float(ratio), int(ori), P(out))
+        return n, out[:len(d2)]
+    out = np.zeros(max(len(d1), 1), np.int32)
+    n = oracle.lib().oracle_search_by_bow_kfkf_nodes(P(d1), P(a1), P(v1), len(d1), P(n1), P(s1), P(i1), len(n1), P(d2), P(a2), P(v2), len(d2), P(n2), P(s2), P(i2),
+                                                     len(n2), C.c_float(ratio), int(ori), P(out))
+    return n, out[:len(d1)]
+
+
+def test_node_oracles_reduce_to_single_node_oracles():
+    """one all-inclusive node + good map points everywhere: the node-wise restatements must equal the brute-force ones that the
+    extractor / matcher parity tests already pin"""
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 256, (12, 32)).astype(np.uint8)
+    d1 = np.repeat(base, 25, axis=0) ^ np.packbits(rng.integers(0, 100, (300, 256)) < 4, axis=1)
+    d2 = np.repeat(base, 20, axis=0) ^ np.packbits(rng.integers(0, 100, (240, 256)) < 4, axis=1)
+    a1 = rng.uniform(0, 360, 300).astype(np.float32); a2 = rng.uniform(0, 360, 240).astype(np.float32)
+    fv1 = {7: list(range(300))}; fv2 = {7: list(range(240))}
+    one1 = np.ones(300, np.uint8); one2 = np.ones(240, np.uint8)
+    for ratio, ori in ((0.6, True), (0.9, False), (1.5, True)):
+        n, m = oracle_bow_nodes(0, d1, a1, one1, fv1, d2, a2, one2, fv2, ratio, ori)
+        nb, mb = oracle.search_by_bow_bf(d1, a1, d2, a2, ratio, ori)
+        assert n == nb and np.array_equal(m, mb)
+        n, m = oracle_bow_nodes(1, d1, a1, one1, fv1, d2, a2, one2, fv2, ratio, ori)
+        want = np.zeros(300, np.int32)
+        nw = oracle.lib().oracle_search_by_bow_kfkf_bf(P(d1), P(a1), 300, P(d2), P(a2), 240, C.c_float(ratio), int(ori), P(want))
+        assert n == nw and np.array_equal(m, want)
+    # disjoint nodes never match; a node present on one side only is skipped by the lower_bound branches
+    n, m = oracle_bow_nodes(0, d1, a1, one1, {1: list(range(150)), 5: list(range(150, 300))}, d2, a2, one2, {2: list(range(100)), 6: list(range(100, 240))}, 0.9, True)
+    assert n == 0 and (m == -1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,L,levelsup", [(10, 3, 2), (6, 4, 2), (10, 3, 1)])
+def test_search_by_bow_over_feature_vectors_matches_oracle(built_lib, k, L, levelsup):
+    """SearchByBoW(KF, F) (ORBmatcher.cc:159-292) and SearchByBoW(KF, KF) (ORBmatcher.cc:526-659) with the FeatureVectors of a
+    vocabulary, random good-MapPoint masks; bit-exact against the node-wise oracles"""
+    from orb_slam2_aruco_b200 import synth
+    from orb_slam2_aruco_b200.api import ORBVocabulary, ORBextractor, ORBmatcher
+    rng = np.random.default_rng(300 + k + L)
+    tree = make_tree(rng, k, L)
+    voc = ORBVocabulary(k, L, *tree)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    img = synth.make_frame(96)
+    k1, d1 = ex(img); k2, d2 = ex(np.roll(img, (2, 3), axis=(0, 1)))
+    # near-duplicates of keyframe descriptors on the frame side so that ties and second-best rejections occur inside nodes
+    extra = d1[rng.integers(0, len(d1), 200)] ^ np.packbits(rng.integers(0, 100, (200, 256)) < 2, axis=1)
+    d2 = np.concatenate([d2, extra]); a2 = np.concatenate([k2["angle"], rng.uniform(0, 360, 200).astype(np.float32)])
+    a1 = k1["angle"]
+    _, fv1 = voc.transform(d1, levelsup); _, fv2 = voc.transform(d2, levelsup)
+    assert len(set(fv1) & set(fv2)) > 1
+    v1 = (rng.random(len(d1)) < 0.8).astype(np.uint8); v2 = (rng.random(len(d2)) < 0.8).astype(np.uint8)
+    total = 0
+    for ratio, ori in ((0.6, True), (0.75, False), (0.9, True), (1.5, True)):
+        m = ORBmatcher(ratio, ori)
+        n, got = m.SearchByBoW_nodes(d1, a1, v1, fv1, d2, a2, fv2)
+        nw, want = oracle_bow_nodes(0, d1, a1, v1, fv1, d2, a2, v2, fv2, ratio, ori)
+        assert n == nw and np.array_equal(got, want), (ratio, ori)
+        total += n
+        n, got = m.SearchByBoW_KF_nodes(d1, a1, v1, fv1, d2, a2, v2, fv2)
+        nw, want = oracle_bow_nodes(1, d1, a1, v1, fv1, d2, a2, v2, fv2, ratio, ori)
+        assert n == nw and np.array_equal(got, want), (ratio, ori)
+        total += n
+    assert total > 50
+    # empty sides
+    n, got = ORBmatcher(0.9, True).SearchByBoW_nodes(d1, a1, v1, fv1, d2[:0], a2[:0], {})
+    assert n == 0 and len(got) == 0
+    n, got = ORBmatcher(0.9, True).SearchByBoW_KF_nodes(d1, a1, np.zeros_like(v1), fv1, d2, a2, v2, fv2)
+    assert n == 0 and (got == -1).all()
+    voc.close(); ex.close()
