@@ -149,6 +149,11 @@ int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8
 int b200_match_by_bow_host(const uint8_t* q_desc, const float* q_angle, int n_q, const uint8_t* c_desc, const float* c_angle, int n_c,
                            const int32_t* grp_q_ofs, const int32_t* q_idx, const int32_t* grp_c_ofs, const int32_t* c_idx, int n_groups,
                            int mode, float ratio, int th_low, int check_ori, int32_t* out, int device);
+/* MapPoint::ComputeDistinctiveDescriptors (include/MapPoint.h:75, src/MapPoint.cc:271-331) for n_points map points at once.  desc [ofs[n_points]][32]:
+ * the observing keyframes' descriptor rows (bad keyframes already dropped), map point p owning rows ofs[p] .. ofs[p+1]).  best_idx [n_points] out: the
+ * row (relative to ofs[p]) with the least median distance to the rest, first minimum; -1 for a point without observations (the reference returns
+ * without touching mDescriptor).  out_desc [n_points][32] (may be NULL): the chosen descriptor (zeros where best_idx = -1).  HOST pointers. */
+int b200_distinctive_descriptors_host(const uint8_t* desc, const int32_t* ofs, int n_points, int32_t* best_idx, uint8_t* out_desc, int device);
 /* ORBmatcher::SearchByProjection on ready-made projections (the projection of the map points is host glue in the reference):
  *   mode 0  SearchByProjection(Frame&, const vector<MapPoint*>&, th)          (src/ORBmatcher.cc:45-129, Tracking::SearchLocalPoints)
  *   mode 1  SearchByProjection(Frame& Current, const Frame& Last, th, mono)    (src/ORBmatcher.cc:1332-1474, TrackWithMotionModel); with

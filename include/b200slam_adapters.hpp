@@ -279,6 +279,20 @@ public:
                                                           secondDist.data(), device_));
     }
 
+    // void MapPoint::ComputeDistinctiveDescriptors() (MapPoint.h:75, MapPoint.cc:271-331) for many map points at once: vDescriptors[p] = the
+    // descriptor rows of the good keyframes observing point p.  best[p] = BestIdx (-1: no observation, mDescriptor stays as it is).
+    void ComputeDistinctiveDescriptors(const std::vector<std::vector<cv::Mat> >& vDescriptors, std::vector<int>& best) {
+        std::vector<int32_t> ofs(1, 0);
+        std::vector<uint8_t> rows;
+        for (const auto& v : vDescriptors) {
+            for (const cv::Mat& d : v) rows.insert(rows.end(), d.ptr(0), d.ptr(0) + 32);
+            ofs.push_back((int32_t)(rows.size() / 32));
+        }
+        std::vector<int32_t> b(vDescriptors.size() + 1, -1);
+        b200slam_detail::check(b200_distinctive_descriptors_host(rows.data(), ofs.data(), (int)vDescriptors.size(), b.data(), nullptr, device_));
+        best.assign(b.begin(), b.begin() + vDescriptors.size());
+    }
+
 protected:
     // the merge walk over common vocabulary nodes (ORBmatcher.cc:185-279 / 547-632) builds the groups of b200_match_by_bow_host
     int byBoW(int mode, const cv::Mat& desc1, const std::vector<cv::KeyPoint>& keys1, const std::vector<bool>* good1, const DBoW2::FeatureVector& fv1,

@@ -4,6 +4,8 @@
 // "parity unpinned" by reference tests (there are none); pinned instead by known-answer
 // checks (numpy popcount, self-match distance 0) in tests/test_oracle_match.py.
 #include "oracle.h"
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <vector>
 #include <cstring>
@@ -390,4 +392,28 @@ extern "C" int oracle_search_by_bow_kfkf_nodes(const uint8_t* d1, const float* a
         }
     }
     return nmatches;
+}
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:271-331): index of the observation with the least median distance -----------
+// desc [n][32] = vDescriptors in observation order.  Returns BestIdx, or -1 for n == 0 (the reference returns early, mDescriptor untouched).
+extern "C" int oracle_distinctive_descriptor(const uint8_t* desc, int n) {
+    if (n <= 0) return -1;
+    const size_t N = (size_t)n;
+    std::vector<float> Distances(N * N);
+    for (size_t i = 0; i < N; i++) {
+        Distances[i * N + i] = 0;
+        for (size_t j = i + 1; j < N; j++) {
+            const int distij = descriptor_distance(desc + 32 * i, desc + 32 * j);
+            Distances[i * N + j] = (float)distij;
+            Distances[j * N + i] = (float)distij;
+        }
+    }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (size_t i = 0; i < N; i++) {
+        std::vector<int> vDists(Distances.begin() + i * N, Distances.begin() + (i + 1) * N);
+        std::sort(vDists.begin(), vDists.end());
+        const int median = vDists[(size_t)(0.5 * (N - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = (int)i; }
+    }
+    return BestIdx;
 }

@@ -81,6 +81,8 @@ void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, 
 int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                             float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:271-331): BestIdx over desc [n][32], -1 when n == 0
+int oracle_distinctive_descriptor(const uint8_t* desc, int n);
 // SearchByBoW(KeyFrame*, Frame&) (src/ORBmatcher.cc:159-292) over real FeatureVectors given as sorted arrays (nodes, start, items); matches [n_f] out
 int oracle_search_by_bow_nodes(const uint8_t* dkf, const float* akf, const uint8_t* kf_valid, const int32_t* kf_nodes, const int32_t* kf_start,
                                const int32_t* kf_items, int kf_nn, const uint8_t* df, const float* af, int n_f, const int32_t* f_nodes,

@@ -271,6 +271,19 @@ class ORBmatcher:
         Returns (nmatches, matches12) with matches12[idx1] = index in KF2 or -1."""
         return self._by_bow(1, desc1, angles1, desc2, angles2, self.common_node_groups(featvec1, valid1, featvec2, valid2))
 
+    def ComputeDistinctiveDescriptors(self, observations):
+        """MapPoint::ComputeDistinctiveDescriptors (MapPoint.h:75, MapPoint.cc:271-331) for a list of map points: observations[p] is the
+        [N_p, 32] array of the descriptors of the keyframes observing point p (bad keyframes dropped).  Returns (best_idx [P] with -1 for
+        a point without observations, descriptors [P, 32])."""
+        obs = [np.ascontiguousarray(o, np.uint8).reshape(-1, 32) for o in observations]
+        ofs = np.zeros(len(obs) + 1, np.int32)
+        ofs[1:] = np.cumsum([len(o) for o in obs])
+        desc = np.concatenate(obs) if obs and ofs[-1] else np.zeros((1, 32), np.uint8)
+        best = np.full(max(len(obs), 1), -1, np.int32)
+        out = np.zeros((max(len(obs), 1), 32), np.uint8)
+        check(lib().b200_distinctive_descriptors_host(ptr(desc), ptr(ofs), len(obs), ptr(best), ptr(out), self._device))
+        return best[:len(obs)], out[:len(obs)]
+
     def SearchByBoW_batch(self, kf_desc, kf_angles, f_desc, f_angles, n_frame, histo_factor=None):
         kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
         kf_angles = np.ascontiguousarray(kf_angles, np.float32)
@@ -615,7 +628,11 @@ class ORBVocabulary:
     def transform(self, descriptors, levelsup=4):
         """transform(features, BowVector&, FeatureVector&, levelsup) (Frame::ComputeBoW, src/Frame.cc:348-355) ->
         (BowVector as {word: value}, FeatureVector as {node: [feature indices]}), both in ascending key order like the std::maps"""
-        w, wt, nid = self.descend(descriptors, levelsup)
+        return self.vectors(*self.descend(descriptors, levelsup))
+
+    @staticmethod
+    def vectors(w, wt, nid):
+        """BowVector::addWeight / FeatureVector::addFeature / normalize(L1) over per-feature (word, weight, node) (TemplatedVocabulary.h:1159-1190)"""
         bow, fv = {}, {}
         for i in range(len(w)):
             if wt[i] > 0:                                   # not stopped

@@ -560,6 +560,55 @@ k_bow_resolve(const float* __restrict__ q_angle, const float* __restrict__ c_ang
     if (lane == 0) result[0] = nmatches;
 }
 
+// ------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:271-331), batched over map points: the observation whose MEDIAN Hamming
+// distance to all observations of the point (itself included, vDists[0.5 * (N - 1)] of the sorted row) is smallest; first minimum wins.
+// One warp per map point.  Row i: lane j holds d(i, j) (N <= 32: in a register, descriptors loaded once; larger N: u16 row buffer in shared
+// memory) and the k-th smallest value is found by bisection on the value range 0..256 with ballot / popc counts - no sort.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMedoidWarps = 4;
+
+__global__ void __launch_bounds__(kMedoidWarps * 32)
+k_distinctive(const ulonglong4* __restrict__ desc, const int* __restrict__ ofs, int n_points, int row_cap, int* __restrict__ best_idx,
+              ulonglong4* __restrict__ out_desc) {
+    extern __shared__ unsigned short s_row[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = blockIdx.x * kMedoidWarps + wid;
+    if (p >= n_points) return;
+    const int o = ofs[p], n = ofs[p + 1] - o;
+    if (n <= 0) { if (lane == 0) best_idx[p] = -1; return; }
+    const int k = (n - 1) >> 1;                                         // (int)(0.5 * (N - 1))
+    unsigned short* row = s_row + (size_t)wid * row_cap;
+    int best_med = 0x7fffffff, best = 0;
+    ulonglong4 mine = make_ulonglong4(0, 0, 0, 0);
+    if (n <= 32 && lane < n) mine = desc[o + lane];
+    for (int i = 0; i < n; i++) {
+        const ulonglong4 a = desc[o + i];                               // uniform address: one broadcast load
+        int d = 0x7fff;
+        if (n <= 32) { if (lane < n) d = hamming256(a, mine); }
+        else {
+            for (int j = lane; j < n; j += 32) row[j] = (unsigned short)hamming256(a, desc[o + j]);
+            __syncwarp();
+        }
+        int lo = 0, hi = 256;                                           // smallest v with #(d <= v) >= k + 1
+        while (lo < hi) {
+            const int v = (lo + hi) >> 1;
+            int cnt;
+            if (n <= 32) cnt = __popc(__ballot_sync(0xffffffffu, d <= v));
+            else {
+                cnt = 0;
+                for (int j = lane; j < n; j += 32) cnt += row[j] <= v;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+            }
+            if (cnt >= k + 1) hi = v; else lo = v + 1;
+        }
+        if (lo < best_med) { best_med = lo; best = i; }
+        __syncwarp();
+    }
+    if (lane == 0) { best_idx[p] = best; if (out_desc) out_desc[p] = desc[o + best]; }
+}
+
 struct MatchScratch { uint32_t* topk; size_t cap; int device; };
 static thread_local MatchScratch g_ms = {nullptr, 0, -1};
 
@@ -795,6 +844,36 @@ int b200_match_by_bow_host(const uint8_t* q_desc, const float* q_angle, int n_q,
     B200_CUDA(cudaMemcpy(&r, res.p, 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(out, o.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost));
     return r;
+}
+
+int b200_distinctive_descriptors_host(const uint8_t* desc, const int32_t* ofs, int n_points, int32_t* best_idx, uint8_t* out_desc, int device) {
+    if (n_points < 0) return fail(B200_EINVAL, "negative %s", "size");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n_points == 0) return B200_OK;
+    if (!ofs || !best_idx) return fail(B200_EINVAL, "null %s", "pointer");
+    int max_n = 0;
+    for (int p = 0; p < n_points; p++) {
+        if (ofs[p + 1] < ofs[p] || ofs[0] != 0) return fail(B200_EINVAL, "bad %s", "observation offsets");
+        max_n = std::max(max_n, ofs[p + 1] - ofs[p]);
+    }
+    const int total = ofs[n_points];
+    if (total > 0 && !desc) return fail(B200_EINVAL, "null %s", "descriptor pointer");
+    const int row_cap = max_n > 32 ? (max_n + 7) / 8 * 8 : 0;
+    const size_t smem = (size_t)kMedoidWarps * row_cap * 2;
+    if (smem > 200 * 1024) return fail(B200_ECAPACITY, "more than %s observations of one map point", "25600");
+    DevBuf dd, dofs, db, dout;
+    if ((rc = dd.upload(desc, (size_t)std::max(total, 1) * 32)) || (rc = dofs.upload(ofs, (size_t)(n_points + 1) * 4)) || (rc = db.alloc((size_t)n_points * 4)) ||
+        (out_desc && (rc = dout.alloc((size_t)n_points * 32))))
+        return rc;
+    if (out_desc) B200_CUDA(cudaMemsetAsync(dout.p, 0, (size_t)n_points * 32, 0));
+    if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_LAUNCH(k_distinctive, (n_points + kMedoidWarps - 1) / kMedoidWarps, kMedoidWarps * 32, smem, 0, (const ulonglong4*)dd.p, (const int*)dofs.p, n_points,
+                row_cap, (int*)db.p, out_desc ? (ulonglong4*)dout.p : nullptr);
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(best_idx, db.p, (size_t)n_points * 4, cudaMemcpyDeviceToHost));
+    if (out_desc) B200_CUDA(cudaMemcpy(out_desc, dout.p, (size_t)n_points * 32, cudaMemcpyDeviceToHost));
+    return B200_OK;
 }
 
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device) {

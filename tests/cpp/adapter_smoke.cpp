@@ -41,6 +41,14 @@ int main(int argc, char** argv) {
         if (nm_fv != nm || matches_fv != matches) { fprintf(stderr, "node-wise SearchByBoW differs from brute force\n"); return 1; }
         matcher.SearchByBoW_KF(desc, keys, std::vector<bool>(keys.size(), true), one, desc, keys, std::vector<bool>(keys.size(), true), one, matches12);
         if (matches12.size() != keys.size()) { fprintf(stderr, "SearchByBoW_KF size\n"); return 1; }
+        // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:271-331): {a, a, b} -> the duplicated descriptor (index 0) has median 0
+        if (desc.rows >= 2) {
+            std::vector<std::vector<cv::Mat> > obs(2);
+            obs[0].push_back(cv::Mat(1, 32, CV_8U, desc.ptr(0))); obs[0].push_back(cv::Mat(1, 32, CV_8U, desc.ptr(0))); obs[0].push_back(cv::Mat(1, 32, CV_8U, desc.ptr(1)));
+            std::vector<int> best;
+            matcher.ComputeDistinctiveDescriptors(obs, best);
+            if (best.size() != 2 || best[0] != 0 || best[1] != -1) { fprintf(stderr, "ComputeDistinctiveDescriptors: %d %d\n", best[0], best[1]); return 1; }
+        }
         const int dist = ORB_SLAM2::ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, desc.ptr(0)), cv::Mat(1, 32, CV_8U, desc.ptr(1)));
         FILE* o = fopen(argv[5], "wb");
         int hdr[4] = {(int)keys.size(), (int)markers.size(), nm, dist};

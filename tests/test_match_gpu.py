@@ -174,3 +174,27 @@ def test_search_by_projection_modes_match_oracle(built_lib):
     n, assign, occ = search_by_projection(kf, df, bounds, np.zeros(len(kf), np.uint8), np.zeros((0, 3)), np.zeros((0, 2)), np.zeros((0, 32)), np.zeros(0), np.zeros(0), 0)
     assert n == 0 and (assign == -1).all()
     ex.close()
+
+
+def test_distinctive_descriptors_match_oracle(built_lib):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:271-331), batched: register path (N <= 32) and shared-memory rows (N > 32)"""
+    import ctypes as C
+    rng = np.random.default_rng(17)
+    sizes = [0, 1, 2, 3, 5, 8, 31, 32, 33, 64, 100, 257] + rng.integers(1, 40, 300).tolist()
+    obs = []
+    for n in sizes:
+        base = rng.integers(0, 256, (3, 32)).astype(np.uint8)
+        obs.append(np.ascontiguousarray(base[rng.integers(0, 3, n)] ^ np.packbits(rng.integers(0, 100, (n, 256)) < 5, axis=1)) if n else np.zeros((0, 32), np.uint8))
+    obs.append(np.repeat(rng.integers(0, 256, (1, 32)).astype(np.uint8), 40, axis=0))          # all medians tie at 0
+    m = ORBmatcher(0.7, True)
+    best, desc = m.ComputeDistinctiveDescriptors(obs)
+    f = oracle.lib().oracle_distinctive_descriptor
+    for p, o in enumerate(obs):
+        want = f(o.ctypes.data_as(C.c_void_p), len(o))
+        assert best[p] == want, (p, len(o))
+        assert np.array_equal(desc[p], o[want] if want >= 0 else np.zeros(32, np.uint8))
+    small = [o for o in obs if len(o) <= 32]                                                   # a batch that never needs the row buffer
+    b2, _ = m.ComputeDistinctiveDescriptors(small)
+    assert np.array_equal(b2, [f(o.ctypes.data_as(C.c_void_p), len(o)) for o in small])
+    b3, d3 = m.ComputeDistinctiveDescriptors([])
+    assert len(b3) == 0 and len(d3) == 0
