@@ -5,6 +5,7 @@ this package.  The product (orb_slam2_aruco_b200) never does.
 
   liboracle.so        our CPU restatement (oracle/*_oracle.cpp over oracle/cvprim*.h)
   _ref/libref_orb.so  the reference's own src/ORBextractor.cc compiled unmodified on oracle/cvshim
+  _ref/libref_match.so  the reference's own src/ORBmatcher.cc compiled unmodified on oracle/matchshim
                       (built only where /root/reference exists; the prebuilt .so travels to the GPU box)
 """
 import ctypes as C
@@ -56,6 +57,20 @@ def ref():
             return None
         _ref = C.CDLL(path)
     return _ref
+
+
+_ref_match = None
+
+
+def ref_match():
+    """The reference's own src/ORBmatcher.cc on oracle/matchshim (oracle/ref_match_wrap.cpp), or None when it was never built."""
+    global _ref_match
+    if _ref_match is None:
+        path = os.path.join(HERE, "_ref", "libref_match.so")
+        if not os.path.exists(path):
+            return None
+        _ref_match = C.CDLL(path)
+    return _ref_match
 
 
 # ---- primitives -------------------------------------------------------------------------------

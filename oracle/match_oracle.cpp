@@ -1,8 +1,9 @@
 // oracle/match_oracle.cpp -- TEST INFRASTRUCTURE (CPU checker), not product code.
-// Restatement of the ORBmatcher cores (reference src/ORBmatcher.cc) over plain arrays; ORBmatcher.cc itself
-// cannot be compiled here (its include closure reaches Eigen/g2o: Map.h:28 -> Converter.h:26-28).
-// "parity unpinned" by reference tests (there are none); pinned instead by known-answer
-// checks (numpy popcount, self-match distance 0) in tests/test_oracle_match.py.
+// Restatement of the ORBmatcher cores (reference src/ORBmatcher.cc) over plain arrays.  The reference ships no tests;
+// this file is pinned by the reference ITSELF: src/ORBmatcher.cc compiles unmodified on oracle/matchshim into oracle/_ref/libref_match.so
+// (oracle/ref_match_wrap.cpp), and tests/test_oracle_match_vs_ref.py demands equality - live where /root/reference exists, and everywhere by
+// replaying tests/golden/match_ref.npz.  Known-answer checks (numpy popcount, self-match distance 0) stay in tests/test_oracle_match.py.
+// Not reachable that way: ComputeDistinctiveDescriptors (src/MapPoint.cc needs the real classes) - pinned by a numpy definition.
 #include "oracle.h"
 #include <algorithm>
 #include <climits>

@@ -198,3 +198,38 @@ def test_distinctive_descriptors_match_oracle(built_lib):
     assert np.array_equal(b2, [f(o.ctypes.data_as(C.c_void_p), len(o)) for o in small])
     b3, d3 = m.ComputeDistinctiveDescriptors([])
     assert len(b3) == 0 and len(d3) == 0
+
+
+def test_reference_golden_vectors(built_lib, golden_dir):
+    """tests/golden/match_ref.npz: answers of the reference's OWN src/ORBmatcher.cc (oracle/_ref/libref_match.so, written by
+    tests/golden/make_match_golden.py) for DescriptorDistance, both SearchByBoW over feature vectors, SearchForInitialization and the three
+    Tracking-thread SearchByProjection variants (on the grid queries the reference itself made) - the CUDA path must give the same bits"""
+    import os
+    import match_cases as mc
+    from orb_slam2_aruco_b200.api import search_by_projection, search_for_initialization
+    g = mc.load_golden(os.path.join(golden_dir, "match_ref.npz"))
+    d = g["dist"]
+    assert np.array_equal(np.diagonal(ORBmatcher().distance_matrix(d["a"], d["b"])), d["d"])
+    c = g["bow"]
+    fv1 = mc.fv_dict(c["n1"], c["s1"], c["i1"]); fv2 = mc.fv_dict(c["n2"], c["s2"], c["i2"])
+    for run in c["runs"]:
+        m = ORBmatcher(float(run["cfg"][0]), bool(run["cfg"][1]))
+        n, got = m.SearchByBoW_nodes(c["d1"], c["a1"], c["v1"], fv1, c["d2"], c["a2"], fv2)
+        assert n == run["n"] and np.array_equal(got, run["matches"])
+        n, got = m.SearchByBoW_KF_nodes(c["d1"], c["a1"], c["v1"], fv1, c["d2"], c["a2"], c["v2"], fv2)
+        assert n == run["n_kfkf"] and np.array_equal(got, run["matches12"])
+    c = g["init"]
+    prev = None
+    for j, run in enumerate(c["runs"]):
+        prev = c["prev"] if j % 2 == 0 else prev
+        n, m12, prev = search_for_initialization(c["k1"], c["d1"], c["k2"], c["d2"], mc.BOUNDS, prev, int(run["cfg"][0]), float(run["cfg"][1]), bool(run["cfg"][2]))
+        assert n == run["n"] and np.array_equal(m12, run["matches12"]) and np.array_equal(prev, run["prev"])
+    for kind in ("points", "last", "reloc"):
+        c = g[kind]
+        for run in c["runs"]:
+            occ, qd, qa, qo, mode = mc.projection_queries(kind, c, run["q_mp"])
+            ratio = float(run["cfg"][1]) if kind == "points" else 0.9
+            ori = True if kind == "points" else bool(run["cfg"][-1])
+            th_high = int(run["cfg"][1]) if kind == "reloc" else 100
+            n, assign, _ = search_by_projection(c["k2"], c["d2"], mc.BOUNDS, occ, run["q_xyr"], run["q_lev"], qd, qa, qo, mode, ratio, ori, th_high)
+            assert n == run["n"] and np.array_equal(assign, mc.expected_assign(run["assign"], run["q_mp"])), (kind, run["cfg"])
