@@ -39,6 +39,11 @@ def main():
         n, m = mc.run_bow(R, "ref", c, ratio, ori)
         n2, m2 = mc.run_bow_kfkf(R, "ref", c, ratio, ori)
         put("bow.%d" % j, dict(cfg=np.array([ratio, ori]), n=np.int32(n), matches=m, n_kfkf=np.int32(n2), matches12=m2))
+    c1 = mc.one_node(c)                                       # brute force = one node, every MapPoint good (the benched configuration)
+    for j, (ratio, ori) in enumerate(BOW_CONFIGS):
+        n, m = mc.run_bow(R, "ref", c1, ratio, ori)
+        n2, m2 = mc.run_bow_kfkf(R, "ref", c1, ratio, ori)
+        put("bf.%d" % j, dict(cfg=np.array([ratio, ori]), n=np.int32(n), matches=m, n_kfkf=np.int32(n2), matches12=m2))
     c = mc.init_inputs()
     put("init", c)
     for j, (window, ratio, ori) in enumerate(INIT_CONFIGS):

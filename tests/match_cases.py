@@ -70,6 +70,14 @@ def bow_inputs(seed=31):
     return dict(d1=d1, a1=a1, v1=v1, n1=n1, s1=s1, i1=i1, d2=d2, a2=a2, v2=v2, n2=n2, s2=s2, i2=i2)
 
 
+def one_node(c):
+    """the same descriptors with ONE all-inclusive vocabulary node and good MapPoints everywhere: the brute-force configuration of the bench"""
+    n1, n2 = len(c["d1"]), len(c["d2"])
+    one = np.array([7], np.int32)
+    return dict(c, v1=np.ones(n1, np.uint8), v2=np.ones(n2, np.uint8), n1=one, s1=np.array([0, n1], np.int32), i1=np.arange(n1, dtype=np.int32),
+                n2=one, s2=np.array([0, n2], np.int32), i2=np.arange(n2, dtype=np.int32))
+
+
 def init_inputs(shift=(4, 7)):
     k1, d1, k2, d2 = two_views(70, shift)
     return dict(k1=k1, d1=d1, k2=k2, d2=d2, prev=A(np.stack([k1["x"], k1["y"]], 1), np.float32))

@@ -218,6 +218,12 @@ def test_reference_golden_vectors(built_lib, golden_dir):
         assert n == run["n"] and np.array_equal(got, run["matches"])
         n, got = m.SearchByBoW_KF_nodes(c["d1"], c["a1"], c["v1"], fv1, c["d2"], c["a2"], c["v2"], fv2)
         assert n == run["n_kfkf"] and np.array_equal(got, run["matches12"])
+    for run in g["bf"]["runs"]:                               # the benched brute-force kernels (k_match_topk + k_match_resolve)
+        m = ORBmatcher(float(run["cfg"][0]), bool(run["cfg"][1]))
+        n, got = m.SearchByBoW(c["d1"], c["a1"], c["d2"], c["a2"])
+        assert n == run["n"] and np.array_equal(got[:len(c["d2"])], run["matches"])
+        n, got = m.SearchByBoW_KF(c["d1"], c["a1"], c["d2"], c["a2"])
+        assert n == run["n_kfkf"] and np.array_equal(got, run["matches12"])
     c = g["init"]
     prev = None
     for j, run in enumerate(c["runs"]):

@@ -33,6 +33,19 @@ def test_search_by_bow_over_feature_vectors(golden):
         assert run["n"] > 50 and run["n_kfkf"] > 50
 
 
+def test_brute_force_configuration(golden):
+    """one node + all MapPoints good: the reference's answers against the single-node oracle entry points the bench and the GPU tests use"""
+    import ctypes as C
+    c = golden["bow"]
+    for run in golden["bf"]["runs"]:
+        ratio, ori = float(run["cfg"][0]), int(run["cfg"][1])
+        n, m = oracle.search_by_bow_bf(c["d1"], c["a1"], c["d2"], c["a2"], ratio, bool(ori))
+        assert n == run["n"] and np.array_equal(m, run["matches"])
+        want = np.zeros(len(c["d1"]), np.int32)
+        n = oracle.lib().oracle_search_by_bow_kfkf_bf(mc.P(c["d1"]), mc.P(c["a1"]), len(c["d1"]), mc.P(c["d2"]), mc.P(c["a2"]), len(c["d2"]), C.c_float(ratio), ori, mc.P(want))
+        assert n == run["n_kfkf"] and np.array_equal(want, run["matches12"])
+
+
 def test_search_for_initialization(golden):
     c = golden["init"]
     prev = None
