@@ -26,7 +26,7 @@
 
 using namespace std;                 // the real closure gets this from Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:36
 
-struct RefTrace { std::vector<float> xyr; std::vector<int> levels; std::vector<int> mp; };
+struct RefTrace { std::vector<float> xyr; std::vector<int> levels; std::vector<int> mp; int lastPredicted = 0; };
 extern RefTrace g_ref_trace;
 
 namespace ORB_SLAM2 {
@@ -62,6 +62,7 @@ public:
         const float ratio = maxDistance / currentDist;
         int nScale = (int)ceil(log(ratio) / p->mfLogScaleFactor);
         if (nScale < 0) nScale = 0; else if (nScale >= p->mnScaleLevels) nScale = p->mnScaleLevels - 1;
+        g_ref_trace.lastPredicted = nScale;                                                           // the KeyFrame queries below record it
         return nScale;
     }
     bool IsInKeyFrame(KeyFrame* pKF) { return observations.count(pKF) != 0; }
@@ -147,7 +148,14 @@ public:
     cv::Mat GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
     cv::Mat GetCameraCenter() { return -GetRotation().t() * GetTranslation(); }
     bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
-    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const { return grid.query(x, y, r, -1, -1); }
+    // src/KeyFrame.cc:416-458: no level window; every caller filters kpLevel to [predicted - 1, predicted] afterwards and calls
+    // PredictScale right before, so the trace stores that window with the query
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const {
+        g_ref_trace.xyr.push_back(x); g_ref_trace.xyr.push_back(y); g_ref_trace.xyr.push_back(r);
+        g_ref_trace.levels.push_back(g_ref_trace.lastPredicted - 1); g_ref_trace.levels.push_back(g_ref_trace.lastPredicted);
+        g_ref_trace.mp.push_back(-1);
+        return grid.query(x, y, r, -1, -1);
+    }
 };
 
 }  // namespace ORB_SLAM2

@@ -230,3 +230,184 @@ int ref_search_by_projection_reloc(const oracle_keypoint* k2, const uint8_t* d2,
 }
 
 }  // extern "C"
+
+// ---- the KeyFrame-side searches (local mapping / loop closing threads) ------------------------------------------------------------------------
+// Shared argument blocks.  Keyframe: undistorted keypoints, descriptors, bounds4 (integers in the reference's KeyFrame, include/KeyFrame.h:211-214),
+// cam4 = fx fy cx cy, pose T (row-major 4x4, Tcw).  Map point list: state 0 = NULL / 1 = good / 2 = bad / 3 = good and already in the keyframe
+// (an observation of it / a member of spAlreadyFound), world position, mean viewing direction, descriptor, mfMinDistance / mfMaxDistance, Observations().
+namespace {
+void set_keyframe(KeyFrame& kf, const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* cam4, const float* T) {
+    kf.N = n; kf.mvKeysUn = keys_from(k, n); kf.mvKeys = kf.mvKeysUn; kf.mDescriptors = desc_mat(d, n);
+    kf.mvuRight.assign(n, -1.0f); kf.mvDepth.assign(n, -1.0f);
+    kf.mvpMapPoints.assign(n, (MapPoint*)NULL);
+    std::vector<float> inv;
+    scale_pyramid(kf.mvScaleFactors, kf.mvLevelSigma2, kf.mvInvLevelSigma2, 8, 1.2f);
+    kf.mnMinX = (int)bounds4[0]; kf.mnMaxX = (int)bounds4[1]; kf.mnMinY = (int)bounds4[2]; kf.mnMaxY = (int)bounds4[3];
+    kf.fx = cam4[0]; kf.fy = cam4[1]; kf.cx = cam4[2]; kf.cy = cam4[3];
+    if (T) kf.Tcw = mat44(T);
+    kf.grid.build(kf.mvKeysUn, bounds4);
+}
+void set_points(std::vector<MapPoint>& pts, int n_mp, const uint8_t* state, const float* pos, const float* normal, const uint8_t* desc, const float* minmax,
+                const int32_t* nobs) {
+    pts.assign(n_mp, MapPoint());
+    for (int m = 0; m < n_mp; m++) {
+        pts[m].id = m; pts[m].bad = state[m] == 2; pts[m].worldPos = vec3(pos + 3 * m); pts[m].normal = normal ? vec3(normal + 3 * m) : cv::Mat();
+        pts[m].descriptor = desc_row(desc, m); pts[m].minDistance = minmax[2 * m]; pts[m].maxDistance = minmax[2 * m + 1]; pts[m].nObs = nobs ? nobs[m] : 1;
+    }
+}
+// the points a keyframe holds before the call: held_state [n] 0 none / 1 good / 2 bad, held_nobs [n]; their ids are 1000000 + feature index
+void hold_points(KeyFrame& kf, std::vector<MapPoint>& held, const uint8_t* held_state, const int32_t* held_nobs) {
+    held.assign(kf.N, MapPoint());
+    for (int i = 0; i < kf.N; i++) if (held_state[i]) {
+        held[i].id = 1000000 + i; held[i].bad = held_state[i] == 2; held[i].nObs = held_nobs ? held_nobs[i] : 1; held[i].observations[&kf] = i;
+        kf.mvpMapPoints[i] = &held[i];
+    }
+}
+int dump_trace_all(float* q_xyr, int32_t* q_lev, int32_t* q_mp, int cap) {       // every query, also those that found nothing (q_mp = -1)
+    int n = 0;
+    for (size_t i = 0; i < g_ref_trace.mp.size(); i++, n++) if (n < cap) {
+        for (int j = 0; j < 3; j++) q_xyr[3 * n + j] = g_ref_trace.xyr[3 * i + j];
+        q_lev[2 * n] = g_ref_trace.levels[2 * i]; q_lev[2 * n + 1] = g_ref_trace.levels[2 * i + 1];
+        q_mp[n] = g_ref_trace.mp[i];
+    }
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+// SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo = false) (src/ORBmatcher.cc:661-829), monocular keyframes.  has_mp* [n]: the
+// feature already owns a MapPoint (skipped).  FeatureVectors as in ref_search_by_bow_nodes.  F12 row-major 3x3.  matches12 [n1] out (-1 none): the
+// pairs (i, matches12[i]) in ascending i are vMatchedPairs.
+int ref_search_for_triangulation(const oracle_keypoint* k1, const uint8_t* d1, const uint8_t* has_mp1, int n1, const int32_t* nodes1, const int32_t* start1,
+                                 const int32_t* items1, int nn1, const float* T1, const oracle_keypoint* k2, const uint8_t* d2, const uint8_t* has_mp2, int n2,
+                                 const int32_t* nodes2, const int32_t* start2, const int32_t* items2, int nn2, const float* T2, const float* bounds4,
+                                 const float* cam4, const float* F12, int check_ori, int32_t* matches12) {
+    KeyFrame a, b;
+    set_keyframe(a, k1, d1, n1, bounds4, cam4, T1); set_keyframe(b, k2, d2, n2, bounds4, cam4, T2);
+    a.mFeatVec = featvec(nodes1, start1, items1, nn1); b.mFeatVec = featvec(nodes2, start2, items2, nn2);
+    MapPoint some;
+    for (int i = 0; i < n1; i++) if (has_mp1[i]) a.mvpMapPoints[i] = &some;
+    for (int i = 0; i < n2; i++) if (has_mp2[i]) b.mvpMapPoints[i] = &some;
+    std::vector<std::pair<size_t, size_t> > pairs;
+    ORBmatcher matcher(0.6f, check_ori != 0);                                                     // LocalMapping.cc:230 ORBmatcher matcher(0.6,false)
+    const int n = matcher.SearchForTriangulation(&a, &b, cv::Mat(3, 3, CV_32F, (void*)F12).clone(), pairs, false);
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    for (size_t j = 0; j < pairs.size(); j++) matches12[pairs[j].first] = (int32_t)pairs[j].second;
+    return n;
+}
+
+// Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:831-981).  held_* = the keyframe's own points before the call.  Per map point m out:
+// fused_idx [n_mp] = keyframe feature it ended up with (-1 none / not visible in the state) and action [n_mp]: 0 nothing visible, 1 added as a new observation,
+// 2 pMP->Replace(pMPinKF) (the keyframe's point survives), 3 pMPinKF->Replace(pMP).  Returns nFused (which also counts matches to a bad keyframe point).
+int ref_fuse(const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* cam4, const float* T, const uint8_t* held_state,
+             const int32_t* held_nobs, int n_mp, const uint8_t* mp_state, const float* mp_pos, const float* mp_normal, const uint8_t* mp_desc,
+             const float* mp_minmax, const int32_t* mp_nobs, float th, int32_t* fused_idx, int32_t* action, float* q_xyr, int32_t* q_lev, int32_t* q_mp,
+             int32_t* n_queries) {
+    KeyFrame kf;
+    set_keyframe(kf, k, d, n, bounds4, cam4, T);
+    std::vector<MapPoint> held, pts;
+    hold_points(kf, held, held_state, held_nobs);
+    set_points(pts, n_mp, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, mp_nobs);
+    KeyFrame other;
+    std::vector<MapPoint*> vp(n_mp, (MapPoint*)NULL);
+    for (int m = 0; m < n_mp; m++) {
+        if (mp_state[m]) vp[m] = &pts[m];
+        if (mp_state[m] == 3) pts[m].observations[&kf] = 0;                                        // IsInKeyFrame(pKF)
+    }
+    ORBmatcher matcher(0.6f, true);                                                               // LocalMapping.cc:851 ORBmatcher matcher;
+    clear_trace();
+    const int nf = matcher.Fuse(&kf, vp, th);
+    for (int m = 0; m < n_mp; m++) {
+        fused_idx[m] = -1; action[m] = 0;
+        if (mp_state[m] == 1 && pts[m].observations.count(&kf)) { fused_idx[m] = (int32_t)pts[m].observations[&kf]; action[m] = 1; }
+    }
+    // Replace() calls: the keyframe's own point i is named by its feature index, a point o of this call that was added earlier by -3 - o
+    for (int m = 0; m < n_mp; m++) if (pts[m].replaced) {
+        const int other = pts[m].replaced->id;
+        if (other >= 1000000) { fused_idx[m] = other - 1000000; action[m] = 2; }                  // pMP->Replace(pMPinKF), the keyframe's own point
+        else if (other < m) { fused_idx[m] = -3 - other; action[m] = 2; }                         // pMP->Replace(pMPinKF), pMPinKF added earlier in this call
+        else { fused_idx[other] = -3 - m; action[other] = 3; }                                    // pMPinKF->Replace(pMP) in the later point's turn
+    }
+    for (int i = 0; i < n; i++) if (held[i].replaced) { fused_idx[held[i].replaced->id] = i; action[held[i].replaced->id] = 3; }
+    *n_queries = dump_trace_all(q_xyr, q_lev, q_mp, n_mp);
+    return nf;
+}
+
+// Fuse(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, th, vpReplacePoint) (src/ORBmatcher.cc:983-1104, loop closing).  S = row-major 4x4 Sim3.
+// replace_idx [n_mp] out = keyframe feature whose point vpReplacePoint[m] names (-1 none); added_idx [n_mp] = feature the point was added to (-1 none).
+int ref_fuse_sim3(const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* cam4, const float* S, const uint8_t* held_state,
+                  int n_mp, const uint8_t* mp_state, const float* mp_pos, const float* mp_normal, const uint8_t* mp_desc, const float* mp_minmax, float th,
+                  int32_t* replace_idx, int32_t* added_idx, float* q_xyr, int32_t* q_lev, int32_t* q_mp, int32_t* n_queries) {
+    KeyFrame kf;
+    set_keyframe(kf, k, d, n, bounds4, cam4, NULL);
+    std::vector<MapPoint> held, pts;
+    hold_points(kf, held, held_state, NULL);
+    set_points(pts, n_mp, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, NULL);
+    std::vector<MapPoint*> vp(n_mp), vrep(n_mp, (MapPoint*)NULL);
+    // state 3: the point IS one of the keyframe's good points (member of pKF->GetMapPoints()): hand the keyframe's own pointer in
+    int next_held = 0;
+    for (int m = 0; m < n_mp; m++) {
+        vp[m] = &pts[m];
+        if (mp_state[m] == 3) {
+            while (next_held < n && held_state[next_held] != 1) next_held++;
+            if (next_held < n) { MapPoint& h = held[next_held++]; h.worldPos = pts[m].worldPos; h.normal = pts[m].normal; h.descriptor = pts[m].descriptor;
+                                 h.minDistance = pts[m].minDistance; h.maxDistance = pts[m].maxDistance; vp[m] = &h; }
+        }
+    }
+    ORBmatcher matcher(0.8f, true);                                                               // LoopClosing.cc:1076 ORBmatcher matcher(0.8)
+    clear_trace();
+    const int nf = matcher.Fuse(&kf, mat44(S), vp, th, vrep);
+    for (int m = 0; m < n_mp; m++) {
+        replace_idx[m] = !vrep[m] ? -1 : vrep[m]->id >= 1000000 ? vrep[m]->id - 1000000 : -3 - vrep[m]->id;   // -3 - o: point o, added earlier in this call
+        added_idx[m] = (vp[m] == &pts[m] && pts[m].observations.count(&kf)) ? (int32_t)pts[m].observations[&kf] : -1;
+    }
+    *n_queries = dump_trace_all(q_xyr, q_lev, q_mp, n_mp);
+    return nf;
+}
+
+// SearchByProjection(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, th) (src/ORBmatcher.cc:294-407, loop closing).
+// matched [n] in/out: -1 none, >= 0 index into vpPoints, -2 some other point.
+int ref_search_by_projection_loop(const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* cam4, const float* S, int n_mp,
+                                  const uint8_t* mp_state, const float* mp_pos, const float* mp_normal, const uint8_t* mp_desc, const float* mp_minmax, int th,
+                                  int32_t* matched, float* q_xyr, int32_t* q_lev, int32_t* q_mp, int32_t* n_queries) {
+    KeyFrame kf;
+    set_keyframe(kf, k, d, n, bounds4, cam4, NULL);
+    std::vector<MapPoint> pts;
+    set_points(pts, n_mp, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, NULL);
+    MapPoint other; other.id = -2;
+    std::vector<MapPoint*> vp(n_mp), vm(n, (MapPoint*)NULL);
+    for (int m = 0; m < n_mp; m++) vp[m] = &pts[m];
+    for (int i = 0; i < n; i++) if (matched[i] >= 0) vm[i] = &pts[matched[i]]; else if (matched[i] == -2) vm[i] = &other;
+    ORBmatcher matcher(0.75f, true);                                                              // LoopClosing.cc:493 ORBmatcher matcher(0.75,true)
+    clear_trace();
+    const int nm = matcher.SearchByProjection(&kf, mat44(S), vp, vm, th);
+    for (int i = 0; i < n; i++) matched[i] = vm[i] ? vm[i]->id : -1;
+    *n_queries = dump_trace_all(q_xyr, q_lev, q_mp, n_mp);
+    return nm;
+}
+
+// SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (src/ORBmatcher.cc:1106-1330).  Feature i of keyframe x owns point state mpx_state[i]
+// (0 none / 1 good / 2 bad) with position / descriptor / distances.  matches12 [n1] in/out: index of the KF2 feature whose point is matched, -1 none.
+int ref_search_by_sim3(const oracle_keypoint* k1, const uint8_t* d1, int n1, const float* T1, const uint8_t* mp1_state, const float* mp1_pos,
+                       const uint8_t* mp1_desc, const float* mp1_minmax, const oracle_keypoint* k2, const uint8_t* d2, int n2, const float* T2,
+                       const uint8_t* mp2_state, const float* mp2_pos, const uint8_t* mp2_desc, const float* mp2_minmax, const float* bounds4,
+                       const float* cam4, float s12, const float* R12, const float* t12, float th, int32_t* matches12, float* q_xyr, int32_t* q_lev,
+                       int32_t* q_mp, int32_t* n_queries) {
+    KeyFrame a, b;
+    set_keyframe(a, k1, d1, n1, bounds4, cam4, T1); set_keyframe(b, k2, d2, n2, bounds4, cam4, T2);
+    std::vector<MapPoint> p1, p2;
+    set_points(p1, n1, mp1_state, mp1_pos, NULL, mp1_desc, mp1_minmax, NULL); set_points(p2, n2, mp2_state, mp2_pos, NULL, mp2_desc, mp2_minmax, NULL);
+    for (int i = 0; i < n1; i++) if (mp1_state[i]) { a.mvpMapPoints[i] = &p1[i]; p1[i].observations[&a] = i; }
+    for (int i = 0; i < n2; i++) { p2[i].id = 2000000 + i; if (mp2_state[i]) { b.mvpMapPoints[i] = &p2[i]; p2[i].observations[&b] = i; } }
+    std::vector<MapPoint*> vm(n1, (MapPoint*)NULL);
+    for (int i = 0; i < n1; i++) if (matches12[i] >= 0) vm[i] = &p2[matches12[i]];
+    ORBmatcher matcher(0.75f, true);                                                              // LoopClosing.cc:398 ORBmatcher matcher(0.75,true)
+    clear_trace();
+    const int nf = matcher.SearchBySim3(&a, &b, vm, s12, cv::Mat(3, 3, CV_32F, (void*)R12).clone(), cv::Mat(3, 1, CV_32F, (void*)t12).clone(), th);
+    for (int i = 0; i < n1; i++) matches12[i] = vm[i] ? vm[i]->id - 2000000 : -1;
+    *n_queries = dump_trace_all(q_xyr, q_lev, q_mp, n1 + n2);
+    return nf;
+}
+
+}  // extern "C"
