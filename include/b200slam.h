@@ -162,10 +162,33 @@ int b200_distinctive_descriptors_host(const uint8_t* desc, const int32_t* ofs, i
  * Query q (HOST): q_xyr [n][3] = projected x, y and the search radius (already scaled), q_levels [n][2] = minLevel maxLevel of
  * GetFeaturesInArea, q_desc [n][32], q_angle [n] (mode 1 histogram), q_observed [n] = the map point's Observations() > 0.
  * th_high: accept bestDist <= th_high (<= 0: TH_HIGH = 100).
+ * The loop-closing SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (include/ORBmatcher.h:52, src/ORBmatcher.cc:294-407) is mode 1 with
+ * check_ori = 0, th_high = TH_LOW (50), q_levels = (nPredictedLevel - 1, nPredictedLevel), occupied = "vpMatched[i] != NULL", q_observed = 1.
  * assign [n_frame] out = query index assigned to that frame keypoint or -1 (F.mvpMapPoints[bestIdx] = pMP).  Returns nmatches. */
 int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_frame, const float* bounds4, uint8_t* occupied,
                                   const float* q_xyr, const int32_t* q_levels, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed,
                                   int n_queries, int mode, float ratio, int check_ori, int th_high, int32_t* assign, int device);
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo = false) (include/ORBmatcher.h:66-67, src/ORBmatcher.cc:661-829)
+ * for monocular keyframes.  The host merge-walks the two FeatureVectors into n_groups common vocabulary nodes exactly as for
+ * b200_match_by_bow_host, but keeps only the features WITHOUT a MapPoint on both sides (q_idx: KF1, c_idx: KF2).  F12 row-major 3x3,
+ * epipole2 = (ex, ey) of camera 1 in image 2 (:668-674, host glue), scale_factors / level_sigma2 [nlevels] of KF2 (mvScaleFactors, mvLevelSigma2).
+ * matches12 [n1] out: the KF2 feature paired with KF1 feature i or -1; the pairs in ascending i are vMatchedPairs.  th_low <= 0: TH_LOW = 50.
+ * HOST pointers.  Returns nmatches. */
+int b200_match_for_triangulation_host(const b200_keypoint* kps1_un, const uint8_t* desc1, int n1, const b200_keypoint* kps2_un, const uint8_t* desc2, int n2,
+                                      const int32_t* grp_q_ofs, const int32_t* q_idx, const int32_t* grp_c_ofs, const int32_t* c_idx, int n_groups,
+                                      const float* F12, const float* epipole2, const float* scale_factors, const float* level_sigma2, int nlevels,
+                                      int check_ori, int th_low, int32_t* matches12, int device);
+/* The keyframe search shared by ORBmatcher::Fuse (include/ORBmatcher.h:76, src/ORBmatcher.cc:831-981), Fuse(pKF, Scw, ...) (include/ORBmatcher.h:79,
+ * src/ORBmatcher.cc:983-1104) and SearchBySim3 (include/ORBmatcher.h:70-71, src/ORBmatcher.cc:1106-1330): for every projected map point the most
+ * similar keyframe feature inside its window.  The search does not depend on what earlier points did to the keyframe, so all queries run at once;
+ * projecting the points (pose, depth, viewing-angle and scale tests, PredictScale) and applying the outcome to MapPoint / KeyFrame objects stay
+ * host glue.  Query q: q_xyr = (u, v, radius), q_level = nPredictedLevel (candidates are limited to levels [q_level - 1, q_level]), q_desc.
+ * chi2 > 0: Fuse's reprojection gate, a candidate is skipped when ((u - x)^2 + (v - y)^2) * inv_level_sigma2[octave] > chi2 (5.99 monocular).
+ * best_idx / best_dist [n_queries] out: feature index and Hamming distance of the first minimum in GetFeaturesInArea order (-1 / 256 when no
+ * candidate qualifies); the caller applies bestDist <= TH_LOW (Fuse) or TH_HIGH (SearchBySim3).  HOST pointers. */
+int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_kf, const float* bounds4, const float* q_xyr, const int32_t* q_level,
+                              const uint8_t* q_desc, int n_queries, const float* inv_level_sigma2, int nlevels, double chi2, int32_t* best_idx,
+                              int32_t* best_dist, int device);
 /* Plain 256-bit Hamming distance matrix rows x cols (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1651-1667). */
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device);
 /* Candidate-list matching core shared by SearchByProjection / SearchForInitialization:

@@ -14,7 +14,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, kfgeom
 from ._lib import KP_DTYPE, MARKER_DTYPE, B200Error, check, lib, ptr
 
 
@@ -322,6 +322,145 @@ class ORBmatcher:
         check(lib().b200_match_candidates_host(ptr(query_desc), nq, ptr(train_desc), len(train_desc), ptr(cand_ofs), ptr(cand),
                                                ptr(bi), ptr(bd), ptr(sd), self._device))
         return bi, bd, sd
+
+
+    # ---- KeyFrame-side members (local mapping / loop closing threads): geometry glue in kfgeom.py, searches on the device ---------------------
+    def kf_radius_search(self, kps_un, desc, bounds4, q_xyr, q_level, q_desc, chi2=0.0, scale_factor=1.2, nlevels=8):
+        """best keyframe feature per projected point (b200_match_kf_radius_host) -> (best_idx, best_dist)"""
+        k = np.ascontiguousarray(kps_un); assert k.dtype == KP_DTYPE
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        q3 = np.ascontiguousarray(q_xyr, np.float32).reshape(-1, 3); ql = np.ascontiguousarray(q_level, np.int32)
+        qd = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(bounds4, np.float32)
+        inv = np.ascontiguousarray(kfgeom.pyramid(scale_factor, nlevels)[2], np.float32)
+        bi = np.full(max(len(q3), 1), -1, np.int32); bd = np.full(max(len(q3), 1), 256, np.int32)
+        check(lib().b200_match_kf_radius_host(ptr(k), ptr(d), len(k), ptr(b), ptr(q3), ptr(ql), ptr(qd), len(q3), ptr(inv), int(nlevels), C.c_double(chi2),
+                                              ptr(bi), ptr(bd), self._device))
+        return bi[:len(q3)], bd[:len(q3)]
+
+    def SearchForTriangulation(self, kps1_un, desc1, has_mp1, featvec1, T1, kps2_un, desc2, has_mp2, featvec2, T2, cam4, F12, scale_factor=1.2, nlevels=8):
+        """SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo=false) (ORBmatcher.h:66-67, ORBmatcher.cc:661-829), monocular keyframes.
+        has_mp*: the feature already owns a MapPoint; featvec*: {node: [feature indices]}; T*: Tcw.  Returns (nmatches, matches12) - the pairs
+        (i, matches12[i]) with matches12[i] >= 0, in ascending i, are vMatchedPairs."""
+        k1, k2 = np.ascontiguousarray(kps1_un), np.ascontiguousarray(kps2_un)
+        assert k1.dtype == KP_DTYPE and k2.dtype == KP_DTYPE
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        free1 = ~np.asarray(has_mp1, bool); free2 = ~np.asarray(has_mp2, bool)
+        gq, qi, gc, ci = (np.ascontiguousarray(g, np.int32) for g in self.common_node_groups(featvec1, free1, featvec2, free2))
+        sf, s2, _, _ = kfgeom.pyramid(scale_factor, nlevels)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); e = kfgeom.epipole(T1, T2, cam4)
+        m12 = np.full(max(len(k1), 1), -1, np.int32)
+        n = check(lib().b200_match_for_triangulation_host(ptr(k1), ptr(d1), len(k1), ptr(k2), ptr(d2), len(k2), ptr(gq), ptr(qi), ptr(gc), ptr(ci), len(gq) - 1,
+                                                          ptr(F), ptr(e), ptr(sf), ptr(s2), int(nlevels), int(self.mbCheckOrientation), self.TH_LOW, ptr(m12),
+                                                          self._device))
+        return n, m12[:len(k1)]
+
+    def Fuse(self, kps_un, desc, bounds4, cam4, Tcw, held_state, held_nobs, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, mp_nobs, th=3.0):
+        """Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th = 3.0) (ORBmatcher.h:76, ORBmatcher.cc:831-981) on arrays.  Keyframe: features,
+        pose, held_state [n] 0 none / 1 good / 2 bad point at that feature with held_nobs observations.  Map point m: mp_state 0 NULL / 1 good / 2 bad /
+        3 already observed by the keyframe, position, normal, descriptor, (mfMinDistance, mfMaxDistance), Observations().
+        Returns (nFused, fused_idx, action): action 1 = added as a new observation of feature fused_idx, 2 = pMP->Replace(pMPinKF), 3 =
+        pMPinKF->Replace(pMP); fused_idx names the keyframe feature, or -3 - o when pMPinKF is point o of this call that was added earlier."""
+        st = np.asarray(mp_state, np.uint8); nobs = np.asarray(mp_nobs, np.int32).copy()
+        hs = np.asarray(held_state, np.uint8); hn = np.asarray(held_nobs, np.int32)
+        valid, q3, level = kfgeom.project_points(kfgeom.pose_from_T(Tcw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
+        valid &= (st == 1)
+        qs = np.nonzero(valid)[0]
+        bi, bd = self.kf_radius_search(kps_un, desc, bounds4, q3[qs], level[qs], np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs], chi2=5.99)
+        # the outcome, applied in list order exactly as the reference does on its objects (ORBmatcher.cc:957-976)
+        holder = np.where(hs > 0, -2, -1).astype(np.int64); own_bad = hs == 2
+        bad = st == 2
+        fused = np.full(len(st), -1, np.int32); action = np.zeros(len(st), np.int32)
+        nf = 0
+        for m, idx, dist in zip(qs, bi, bd):
+            if bad[m] or dist > self.TH_LOW:
+                continue
+            h = holder[idx]
+            if h == -2:
+                if not own_bad[idx]:
+                    if hn[idx] > nobs[m]:
+                        bad[m] = True; fused[m], action[m] = idx, 2
+                    else:
+                        own_bad[idx] = True; fused[m], action[m] = idx, 3
+            elif h >= 0:
+                if not bad[h]:
+                    if nobs[h] > nobs[m]:
+                        bad[m] = True; fused[m], action[m] = -3 - h, 2
+                    else:
+                        bad[h] = True; fused[m], action[m] = -3 - h, 3
+            else:
+                holder[idx] = m; nobs[m] += 1; fused[m], action[m] = idx, 1
+            nf += 1
+        return nf, fused, action
+
+    def FuseSim3(self, kps_un, desc, bounds4, cam4, Scw, held_state, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, th=4.0):
+        """Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint) (ORBmatcher.h:79,
+        ORBmatcher.cc:983-1104).  mp_state 1 good / 2 bad / 3 one of the keyframe's own good points.  Returns (nFused, replace_idx, added_idx):
+        replace_idx[m] = keyframe feature whose point vpReplacePoint[m] names (-3 - o: point o added earlier in this call), added_idx[m] = feature the
+        point became an observation of."""
+        st = np.asarray(mp_state, np.uint8); hs = np.asarray(held_state, np.uint8)
+        valid, q3, level = kfgeom.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
+        valid &= (st != 2) & (st != 3)
+        qs = np.nonzero(valid)[0]
+        bi, bd = self.kf_radius_search(kps_un, desc, bounds4, q3[qs], level[qs], np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs])
+        holder = np.where(hs > 0, -2, -1).astype(np.int64)
+        rep = np.full(len(st), -1, np.int32); add = np.full(len(st), -1, np.int32)
+        nf = 0
+        for m, idx, dist in zip(qs, bi, bd):
+            if idx < 0 or dist > self.TH_LOW:
+                continue
+            if holder[idx] == -2:
+                if hs[idx] != 2:
+                    rep[m] = idx
+            elif holder[idx] >= 0:
+                rep[m] = -3 - holder[idx]
+            else:
+                holder[idx] = m; add[m] = idx
+            nf += 1
+        return nf, rep, add
+
+    def SearchByProjectionLoop(self, kps_un, desc, bounds4, cam4, Scw, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, matched, th=10):
+        """SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th) (ORBmatcher.h:52,
+        ORBmatcher.cc:294-407).  matched [n] = vpMatched before the call (-1 none, >= 0 index into vpPoints, -2 another point).  A matched keyframe
+        feature is hidden from every later point, so the queries are replayed in order by the projection resolve kernel
+        (b200_match_by_projection_host, mode 1 without the rotation histogram, TH_LOW).  Returns (nmatches, vpMatched after the call)."""
+        st = np.asarray(mp_state, np.uint8); matched = np.asarray(matched, np.int32).copy()
+        valid, q3, level = kfgeom.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, int(th))
+        found = np.zeros(len(st), bool); found[matched[matched >= 0]] = True
+        valid &= (st != 2) & ~found
+        qs = np.nonzero(valid)[0]
+        lv = np.stack([level[qs] - 1, level[qs]], 1).astype(np.int32)
+        n, assign, _ = search_by_projection(kps_un, desc, bounds4, (matched != -1).astype(np.uint8), q3[qs], lv, np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs],
+                                            np.zeros(len(qs), np.float32), np.ones(len(qs), np.uint8), 1, check_ori=False, th_high=self.TH_LOW, device=self._device)
+        hit = assign >= 0
+        matched[hit] = qs[assign[hit]]
+        return n, matched
+
+    def SearchBySim3(self, kps1_un, desc1, T1, mp1_state, mp1_pos, mp1_desc, mp1_minmax, kps2_un, desc2, T2, mp2_state, mp2_pos, mp2_desc, mp2_minmax,
+                     bounds4, cam4, matches12, s12, R12, t12, th=7.5):
+        """SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (ORBmatcher.h:70-71, ORBmatcher.cc:1106-1330).  Feature i of keyframe x owns a map point
+        with state mpx_state[i] (0 none / 1 good / 2 bad).  matches12 [n1]: KF2 feature whose point is already matched to KF1 feature i (-1 none).
+        Both directions are searched on the device, the agreement check (:1311-1327) is two gathers.  Returns (nFound, matches12 after the call)."""
+        st1, st2 = np.asarray(mp1_state, np.uint8), np.asarray(mp2_state, np.uint8)
+        m12 = np.asarray(matches12, np.int32).copy()
+        n1, n2 = len(st1), len(st2)
+        done1 = m12 >= 0
+        done2 = np.zeros(n2, bool)
+        j = m12[done1]; done2[j[st2[j] > 0]] = True                  # GetIndexInKeyFrame(pKF2) >= 0 only when that KF2 feature holds the point
+        sR12, sR21, t21 = kfgeom.sim3_between(s12, R12, t12)
+        v1, q1, l1 = kfgeom.project_points_sim3(kfgeom.pose_from_T(T1), sR21, t21, cam4, bounds4, mp1_pos, mp1_minmax, th)
+        v2, q2, l2 = kfgeom.project_points_sim3(kfgeom.pose_from_T(T2), sR12, np.asarray(t12, np.float32).reshape(3), cam4, bounds4, mp2_pos, mp2_minmax, th)
+        v1 &= (st1 == 1) & ~done1; v2 &= (st2 == 1) & ~done2
+        a, b = np.nonzero(v1)[0], np.nonzero(v2)[0]
+        bi1, bd1 = self.kf_radius_search(kps2_un, desc2, bounds4, q1[a], l1[a], np.asarray(mp1_desc, np.uint8).reshape(-1, 32)[a])
+        bi2, bd2 = self.kf_radius_search(kps1_un, desc1, bounds4, q2[b], l2[b], np.asarray(mp2_desc, np.uint8).reshape(-1, 32)[b])
+        vn1 = np.full(n1, -1, np.int64); vn2 = np.full(n2, -1, np.int64)
+        ok = (bi1 >= 0) & (bd1 <= self.TH_HIGH); vn1[a[ok]] = bi1[ok]
+        ok = (bi2 >= 0) & (bd2 <= self.TH_HIGH); vn2[b[ok]] = bi2[ok]
+        i1 = np.nonzero(vn1 >= 0)[0]
+        agree = i1[vn2[vn1[i1]] == i1]
+        m12[agree] = vn1[agree]
+        return len(agree), m12
 
 
 class CameraParameters:

@@ -609,6 +609,123 @@ k_distinctive(const ulonglong4* __restrict__ desc, const int* __restrict__ ofs, 
     if (lane == 0) { best_idx[p] = best; if (out_desc) out_desc[p] = desc[o + best]; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SearchForTriangulation (ORBmatcher.cc:661-829), monocular.  The reference never sets vbMatched2, so every KF1 feature is independent: its
+// answer is the candidate of the same vocabulary node with the least distance among those that pass (dist <= TH_LOW, far enough from the
+// epipole, close enough to the epipolar line), the LAST one in node order on ties ('dist > bestDist -> continue' lets an equal distance
+// replace).  Warp per KF1 feature; groups as in SearchByBoW (features that already own a MapPoint dropped on both sides).
+// ------------------------------------------------------------------------------------------------
+struct TriangGeom { float F[9]; float ex, ey; float sf[16]; float sigma2[16]; };
+
+__global__ void __launch_bounds__(256)
+k_triang(const b200_keypoint* __restrict__ k1, const ulonglong4* __restrict__ d1, const b200_keypoint* __restrict__ k2, const ulonglong4* __restrict__ d2,
+         const int* __restrict__ q_idx, const int* __restrict__ q_grp, const int* __restrict__ grp_c_ofs, const int* __restrict__ c_idx, int nq,
+         const TriangGeom g, int th_low, int* __restrict__ m12, unsigned char* __restrict__ rotbin) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int i1 = q_idx[q], grp = q_grp[q], c0 = grp_c_ofs[grp], n = grp_c_ofs[grp + 1] - c0;
+    const b200_keypoint kp1 = k1[i1];
+    const ulonglong4 a = d1[i1];
+    // epipolar line in the second image l = x1' F12 (CheckDistEpipolarLine, ORBmatcher.cc:139-157)
+    const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F[0]), __fmul_rn(kp1.y, g.F[3])), g.F[6]);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F[1]), __fmul_rn(kp1.y, g.F[4])), g.F[7]);
+    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, g.F[2]), __fmul_rn(kp1.y, g.F[5])), g.F[8]);
+    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    uint32_t best = 0xffffffffu;                                  // dist << 20 | (0xfffff - position): least distance, last position
+    if (den != 0.0f)
+        for (int j = lane; j < n; j += 32) {
+            const int i2 = c_idx[c0 + j];
+            const int dist = hamming256(a, d2[i2]);
+            if (dist > th_low) continue;
+            const b200_keypoint kp2 = k2[i2];
+            const int oct = max(0, min(kp2.octave, 15));
+            const float dex = __fsub_rn(g.ex, kp2.x), dey = __fsub_rn(g.ey, kp2.y);
+            if (__fadd_rn(__fmul_rn(dex, dex), __fmul_rn(dey, dey)) < __fmul_rn(100.0f, g.sf[oct])) continue;
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            if (!((double)dsqr < __dmul_rn(3.84, (double)g.sigma2[oct]))) continue;
+            best = min(best, ((uint32_t)dist << 20) | (uint32_t)(0xfffff - j));
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+        int i2 = -1, bin = 255;
+        if (best != 0xffffffffu) {
+            i2 = c_idx[c0 + (0xfffff - (int)(best & 0xfffff))];
+            float rot = __fsub_rn(kp1.angle, k2[i2].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            bin = (int)roundf(__fmul_rn(rot, __fdiv_rn(1.0f, (float)kHistoLen)));
+            if (bin == kHistoLen) bin = 0;
+            bin = max(0, min(bin, kHistoLen - 1));
+        }
+        m12[i1] = i2; rotbin[i1] = (unsigned char)bin;
+    }
+}
+
+// rotation histogram over the accepted pairs (ORBmatcher.cc:740-750, 776-794) and the count; one CTA
+__global__ void __launch_bounds__(256)
+k_triang_finish(int* __restrict__ m12, const unsigned char* __restrict__ rotbin, int n1, int check_ori, int* __restrict__ result) {
+    __shared__ int histo[kHistoLen];
+    __shared__ int keep[3];
+    __shared__ int total;
+    if (threadIdx.x < kHistoLen) histo[threadIdx.x] = 0;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    if (check_ori) {
+        for (int i = threadIdx.x; i < n1; i += blockDim.x) if (m12[i] >= 0) atomicAdd(&histo[rotbin[i]], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) three_maxima(histo, kHistoLen, keep[0], keep[1], keep[2]);
+        __syncthreads();
+    }
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+        if (m12[i] < 0) continue;
+        const int bin = rotbin[i];
+        if (check_ori && bin != keep[0] && bin != keep[1] && bin != keep[2]) m12[i] = -1; else cnt++;
+    }
+    atomicAdd(&total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) result[0] = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Best keyframe feature of a radius query: the inner loop shared by Fuse (ORBmatcher.cc:906-955), Fuse(Scw) (:1063-1082) and SearchBySim3
+// (:1196-1217, :1276-1297).  These searches do not depend on what earlier points did to the keyframe, so all queries run at once; the
+// candidates come from the keyframe's feature grid with the level window [predicted - 1, predicted] (k_features_in_area), the optional gate is
+// Fuse's reprojection test e2 * invSigma2[level] > chi2.  Strict '<' of the reference == first minimum in grid visit order.  Warp per query.
+// ------------------------------------------------------------------------------------------------
+struct LevelTable { float inv_sigma2[16]; };
+
+__global__ void __launch_bounds__(256)
+k_radius_best(const b200_keypoint* __restrict__ k, const ulonglong4* __restrict__ d, const float* __restrict__ q3, const ulonglong4* __restrict__ qd,
+              const int* __restrict__ cand, const int* __restrict__ cnt, int row_cap, int nq, const LevelTable lt, double chi2,
+              int* __restrict__ best_idx, int* __restrict__ best_dist, int* __restrict__ overflow) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int n = cnt[q];
+    if (n > row_cap && lane == 0) *overflow = 1;
+    const int nn = min(n, row_cap);
+    const float u = q3[3 * q], v = q3[3 * q + 1];
+    const ulonglong4 a = qd[q];
+    uint32_t best = 0xffffffffu;                                  // dist << 20 | position in the row
+    for (int j = lane; j < nn; j += 32) {
+        const int idx = cand[(long long)q * row_cap + j];
+        if (chi2 > 0.0) {
+            const b200_keypoint kp = k[idx];
+            const float ex = __fsub_rn(u, kp.x), ey = __fsub_rn(v, kp.y);
+            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            if ((double)__fmul_rn(e2, lt.inv_sigma2[max(0, min(kp.octave, 15))]) > chi2) continue;
+        }
+        best = min(best, ((uint32_t)hamming256(a, d[idx]) << 20) | (uint32_t)j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+        best_idx[q] = best == 0xffffffffu ? -1 : cand[(long long)q * row_cap + (int)(best & 0xfffff)];
+        best_dist[q] = best == 0xffffffffu ? 256 : (int)(best >> 20);
+    }
+}
+
 struct MatchScratch { uint32_t* topk; size_t cap; int device; };
 static thread_local MatchScratch g_ms = {nullptr, 0, -1};
 
@@ -912,6 +1029,94 @@ int b200_match_candidates_host(const uint8_t* query_desc, int nq, const uint8_t*
     B200_CUDA(cudaMemcpy(out_best_idx, o1.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(out_best_dist, o2.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(out_second_dist, o3.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_match_for_triangulation_host(const b200_keypoint* kps1_un, const uint8_t* desc1, int n1, const b200_keypoint* kps2_un, const uint8_t* desc2, int n2,
+                                      const int32_t* grp_q_ofs, const int32_t* q_idx, const int32_t* grp_c_ofs, const int32_t* c_idx, int n_groups,
+                                      const float* F12, const float* epipole2, const float* scale_factors, const float* level_sigma2, int nlevels,
+                                      int check_ori, int th_low, int32_t* matches12, int device) {
+    if (th_low <= 0) th_low = 50;                               // TH_LOW, ORBmatcher.cc:39
+    if (n1 < 0 || n2 < 0 || n_groups < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n1 > 0 && !matches12) return fail(B200_EINVAL, "null %s", "output pointer");
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    if (n_groups == 0 || n1 == 0 || n2 == 0) return 0;
+    if (!kps1_un || !desc1 || !kps2_un || !desc2 || !grp_q_ofs || !q_idx || !grp_c_ofs || !c_idx || !F12 || !epipole2 || !scale_factors || !level_sigma2)
+        return fail(B200_EINVAL, "null %s", "pointer");
+    if (grp_q_ofs[0] != 0 || grp_c_ofs[0] != 0) return fail(B200_EINVAL, "group offsets must start at %s", "0");
+    const int nq = grp_q_ofs[n_groups], nc = grp_c_ofs[n_groups];
+    std::vector<int32_t> q_grp((size_t)std::max(nq, 0));
+    for (int g = 0; g < n_groups; g++) {
+        if (grp_q_ofs[g + 1] < grp_q_ofs[g] || grp_c_ofs[g + 1] < grp_c_ofs[g]) return fail(B200_EINVAL, "group offsets must be %s", "non-decreasing");
+        if (grp_c_ofs[g + 1] - grp_c_ofs[g] >= (1 << 20)) return fail(B200_ECAPACITY, "more than %s candidates in one vocabulary node", "2^20");
+        for (int q = grp_q_ofs[g]; q < grp_q_ofs[g + 1]; q++) q_grp[q] = g;
+    }
+    if (nq == 0 || nc == 0) return 0;
+    for (int i = 0; i < nq; i++) if (q_idx[i] < 0 || q_idx[i] >= n1) return fail(B200_EINVAL, "query index out of %s", "range");
+    for (int i = 0; i < nc; i++) if (c_idx[i] < 0 || c_idx[i] >= n2) return fail(B200_EINVAL, "candidate index out of %s", "range");
+    TriangGeom g;
+    for (int i = 0; i < 9; i++) g.F[i] = F12[i];
+    g.ex = epipole2[0]; g.ey = epipole2[1];
+    for (int i = 0; i < 16; i++) { g.sf[i] = scale_factors[std::min(i, nlevels - 1)]; g.sigma2[i] = level_sigma2[std::min(i, nlevels - 1)]; }
+    DevBuf k1, d1, k2, d2, qi, qg, gco, ci, m12, rb, res;
+    if ((rc = k1.upload(kps1_un, (size_t)n1 * sizeof(b200_keypoint))) || (rc = d1.upload(desc1, (size_t)n1 * 32)) ||
+        (rc = k2.upload(kps2_un, (size_t)n2 * sizeof(b200_keypoint))) || (rc = d2.upload(desc2, (size_t)n2 * 32)) || (rc = qi.upload(q_idx, (size_t)nq * 4)) ||
+        (rc = qg.upload(q_grp.data(), (size_t)nq * 4)) || (rc = gco.upload(grp_c_ofs, (size_t)(n_groups + 1) * 4)) || (rc = ci.upload(c_idx, (size_t)nc * 4)) ||
+        (rc = m12.alloc((size_t)n1 * 4)) || (rc = rb.alloc((size_t)n1)) || (rc = res.alloc(4)))
+        return rc;
+    B200_CUDA(cudaMemsetAsync(m12.p, 0xff, (size_t)n1 * 4, 0));
+    B200_CUDA(cudaMemsetAsync(rb.p, 0xff, (size_t)n1, 0));
+    B200_LAUNCH(k_triang, (nq * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k1.p, (const ulonglong4*)d1.p, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p,
+                (const int*)qi.p, (const int*)qg.p, (const int*)gco.p, (const int*)ci.p, nq, g, th_low, (int*)m12.p, (unsigned char*)rb.p);
+    B200_LAUNCH(k_triang_finish, 1, 256, 0, 0, (int*)m12.p, (const unsigned char*)rb.p, n1, check_ori, (int*)res.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    int r = 0;
+    B200_CUDA(cudaMemcpy(&r, res.p, 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(matches12, m12.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
+    return r;
+}
+
+int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_kf, const float* bounds4, const float* q_xyr, const int32_t* q_level,
+                              const uint8_t* q_desc, int n_queries, const float* inv_level_sigma2, int nlevels, double chi2, int32_t* best_idx,
+                              int32_t* best_dist, int device) {
+    if (n_kf < 0 || n_queries < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n_queries == 0) return B200_OK;
+    if (!best_idx || !best_dist) return fail(B200_EINVAL, "null %s", "output pointer");
+    for (int q = 0; q < n_queries; q++) { best_idx[q] = -1; best_dist[q] = 256; }
+    if (n_kf == 0) return B200_OK;
+    if (!kps_un || !desc || !bounds4 || !q_xyr || !q_level || !q_desc || (chi2 > 0 && !inv_level_sigma2)) return fail(B200_EINVAL, "null %s", "pointer");
+    std::vector<int32_t> lv((size_t)n_queries * 2);
+    for (int q = 0; q < n_queries; q++) {
+        if (q_level[q] < 0 || q_level[q] >= nlevels) return fail(B200_EINVAL, "predicted level out of %s", "range");
+        lv[2 * q] = q_level[q] - 1; lv[2 * q + 1] = q_level[q];         // kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel -> continue
+    }
+    LevelTable lt;
+    for (int i = 0; i < 16; i++) lt.inv_sigma2[i] = inv_level_sigma2 ? inv_level_sigma2[std::min(i, nlevels - 1)] : 1.0f;
+    const int row_cap = std::min(n_kf, 4096);
+    DevBuf k2, d2, ncnt, cs, ci, q3, lv2, qd, cand, cnt, bi, bd, ovf;
+    if ((rc = k2.upload(kps_un, (size_t)n_kf * sizeof(b200_keypoint))) || (rc = d2.upload(desc, (size_t)n_kf * 32)) || (rc = ncnt.upload(&n_kf, 4)) ||
+        (rc = cs.alloc((size_t)(64 * 48 + 1) * 4)) || (rc = ci.alloc((size_t)n_kf * 4)) || (rc = q3.upload(q_xyr, (size_t)n_queries * 12)) ||
+        (rc = lv2.upload(lv.data(), (size_t)n_queries * 8)) || (rc = qd.upload(q_desc, (size_t)n_queries * 32)) ||
+        (rc = cand.alloc((size_t)n_queries * row_cap * 4)) || (rc = cnt.alloc((size_t)n_queries * 4)) || (rc = bi.alloc((size_t)n_queries * 4)) ||
+        (rc = bd.alloc((size_t)n_queries * 4)) || (rc = ovf.alloc(4)))
+        return rc;
+    B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, 0));
+    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
+    if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
+                                          (const int32_t*)lv2.p, n_queries, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+        return rc;
+    B200_LAUNCH(k_radius_best, (n_queries * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)q3.p,
+                (const ulonglong4*)qd.p, (const int*)cand.p, (const int*)cnt.p, row_cap, n_queries, lt, chi2, (int*)bi.p, (int*)bd.p, (int*)ovf.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    int o = 0;
+    B200_CUDA(cudaMemcpy(&o, ovf.p, 4, cudaMemcpyDeviceToHost));
+    if (o) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
+    B200_CUDA(cudaMemcpy(best_idx, bi.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(best_dist, bd.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
 }
 

@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import match_cases as mc
+import match_cases2 as m2
 import oracle
 
 BOW_CONFIGS = [(0.6, 1), (0.75, 0), (0.9, 1), (1.5, 1)]
@@ -20,6 +21,46 @@ INIT_CONFIGS = [(100, 0.9, 1), (30, 0.9, 1), (10, 0.7, 0)]
 POINTS_CONFIGS = [(1.0, 0.8), (3.0, 0.8), (5.0, 0.6)]
 LAST_CONFIGS = [(7.0, 1), (15.0, 1), (15.0, 0)]
 RELOC_CONFIGS = [(10.0, 100, 1), (3.0, 64, 1), (10.0, 100, 0)]
+# match_ref2.npz: the KeyFrame-side members
+TRI_CONFIGS = [0, 1]
+FUSE_CONFIGS = [3.0, 6.0]
+FUSE_SIM3_CONFIGS = [4.0, 10.0]
+LOOP_CONFIGS = [10, 4]
+SIM3_CONFIGS = [7.5, 3.0]
+
+
+def main2(R):
+    out = {}
+
+    def put(prefix, d):
+        for k, v in d.items():
+            out[prefix + "." + k] = v
+
+    c = m2.triangulation_inputs()
+    put("tri", c)
+    for j, ori in enumerate(TRI_CONFIGS):
+        n, m = m2.run_triangulation(R, "ref", c, ori)
+        put("tri.%d" % j, dict(cfg=np.array([ori]), n=np.int32(n), matches12=m))
+    c = m2.keyframe_points_inputs()
+    put("fuse", c)
+    for j, th in enumerate(FUSE_CONFIGS):
+        n, idx, act, qx, ql, qm = m2.run_fuse(R, "ref", c, th)
+        put("fuse.%d" % j, dict(cfg=np.array([th]), n=np.int32(n), fused_idx=idx, action=act, q_xyr=qx, q_lev=ql, q_mp=qm))
+    c = m2.keyframe_points_inputs(seed=54, sim3=True)
+    put("scw", c)
+    for j, (th, th2) in enumerate(zip(FUSE_SIM3_CONFIGS, LOOP_CONFIGS)):
+        n, rep, add, qx, ql, qm = m2.run_fuse_sim3(R, "ref", c, th)
+        n2, matched, qx2, ql2, qm2 = m2.run_loop(R, "ref", c, th2)
+        put("scw.%d" % j, dict(cfg=np.array([th, th2]), n=np.int32(n), replace_idx=rep, added_idx=add, q_xyr=qx, q_lev=ql, q_mp=qm,
+                               n_loop=np.int32(n2), matched=matched, q_xyr_loop=qx2, q_lev_loop=ql2, q_mp_loop=qm2))
+    c = m2.sim3_inputs()
+    put("sim3", c)
+    for j, th in enumerate(SIM3_CONFIGS):
+        n, m12, qx, ql, qm = m2.run_sim3(R, "ref", c, th)
+        put("sim3.%d" % j, dict(cfg=np.array([th]), n=np.int32(n), matches12=m12, q_xyr=qx, q_lev=ql, q_mp=qm))
+    path = os.path.join(HERE, "match_ref2.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes;", len(out), "arrays")
 
 
 def main():
@@ -27,6 +68,7 @@ def main():
     if R is None:
         raise SystemExit("oracle/_ref/libref_match.so not built (needs /root/reference): make -C oracle ref")
     mc.NFEATURES = 500
+    main2(R)
     out = {}
 
     def put(prefix, d):

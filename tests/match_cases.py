@@ -239,7 +239,7 @@ def load_golden(path):
         else:
             case["runs"].setdefault(".".join(parts[1:-1]), {})[parts[-1]] = g[key]
     for case in cases.values():
-        for name in ("k1", "k2", "k_last", "k_kf"):
+        for name in ("k1", "k2", "k_last", "k_kf", "k"):
             if name in case:
                 case[name] = A(case[name]).view(KP).reshape(-1) if case[name].dtype != KP else A(case[name])
         case["runs"] = [case["runs"][k] for k in sorted(case["runs"])]

@@ -189,3 +189,39 @@ def run_sim3(L, prefix, c, th):
         n = L.ref_search_by_sim3(*args, P(qx), P(ql), P(qm), P(nq))
         return n, m12, qx[:nq[0]], ql[:nq[0]], qm[:nq[0]]
     return L.oracle_search_by_sim3(*args), m12
+
+
+# ---- replay of tests/golden/match_ref2.npz through the product's ORBmatcher mirror -----------------------------------------------------------
+def fv_of(c, side):
+    return mc.fv_dict(c["n" + side], c["s" + side], c["i" + side])
+
+
+def replay_product(M, golden):
+    """M = orb_slam2_aruco_b200.api.ORBmatcher (device searches) or the same object with its two device calls swapped for the oracle's (CPU test
+    of the host glue).  Every answer is compared with what the reference's own ORBmatcher.cc returned for the same inputs."""
+    c = golden["tri"]
+    for run in c["runs"]:
+        M.mbCheckOrientation = bool(run["cfg"][0])
+        n, m12 = M.SearchForTriangulation(c["k1"], c["d1"], c["has1"], fv_of(c, "1"), c["T1"], c["k2"], c["d2"], c["has2"], fv_of(c, "2"), c["T2"], CAM4, c["F12"])
+        assert n == run["n"] and np.array_equal(m12, run["matches12"]) and n > 30
+    c = golden["fuse"]
+    for run in c["runs"]:
+        n, idx, act = M.Fuse(c["k"], c["d"], BOUNDS, CAM4, c["T"], c["held_state"], c["held_nobs"], c["mp_state"], c["mp_pos"], c["mp_normal"], c["mp_desc"],
+                             c["mp_minmax"], c["mp_nobs"], float(run["cfg"][0]))
+        assert n == run["n"] and np.array_equal(idx, run["fused_idx"]) and np.array_equal(act, run["action"])
+        assert all((run["action"] == a).sum() > 5 for a in (1, 2, 3))
+    c = golden["scw"]
+    for run in c["runs"]:
+        st = np.where(c["mp_state"] == 0, 1, c["mp_state"]).astype(np.uint8)
+        n, rep, add = M.FuseSim3(c["k"], c["d"], BOUNDS, CAM4, c["T"], c["held_state"], st, c["mp_pos"], c["mp_normal"], c["mp_desc"], c["mp_minmax"],
+                                 float(run["cfg"][0]))
+        assert n == run["n"] and np.array_equal(rep, run["replace_idx"]) and np.array_equal(add, run["added_idx"]) and n > 100
+        st = np.where(c["mp_state"] == 2, 2, 1).astype(np.uint8)
+        n, matched = M.SearchByProjectionLoop(c["k"], c["d"], BOUNDS, CAM4, c["T"], st, c["mp_pos"], c["mp_normal"], c["mp_desc"], c["mp_minmax"],
+                                              loop_matched(c), int(run["cfg"][1]))
+        assert n == run["n_loop"] and np.array_equal(matched, run["matched"]) and n > 50
+    c = golden["sim3"]
+    for run in c["runs"]:
+        n, m12 = M.SearchBySim3(c["k1"], c["d1"], c["T1"], c["st1"], c["p1"], c["d1"], c["mm1"], c["k2"], c["d2"], c["T2"], c["st2"], c["p2"], c["d2"], c["mm2"],
+                                BOUNDS, CAM4, c["m12"], float(c["s12"]), c["R12"], c["t12"], float(run["cfg"][0]))
+        assert n == run["n"] and np.array_equal(m12, run["matches12"]) and n > 50
