@@ -22,6 +22,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 #include "b200slam.h"
 
@@ -291,6 +292,86 @@ public:
         std::vector<int32_t> b(vDescriptors.size() + 1, -1);
         b200slam_detail::check(b200_distinctive_descriptors_host(rows.data(), ofs.data(), (int)vDescriptors.size(), b.data(), nullptr, device_));
         best.assign(b.begin(), b.begin() + vDescriptors.size());
+    }
+
+    // int SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo)
+    // (ORBmatcher.h:66-67, ORBmatcher.cc:661-829) for monocular keyframes on what it reads: undistorted keypoints, descriptors, "the feature already
+    // has a MapPoint" flags and FeatureVectors of both keyframes, F12 (row-major 3x3), the epipole of camera 1 in image 2 (:668-674) and
+    // pKF2->mvScaleFactors / mvLevelSigma2.  Returns nmatches and fills vMatchedPairs like the reference (ascending first index).
+    int SearchForTriangulation(const std::vector<cv::KeyPoint>& keysUn1, const cv::Mat& desc1, const std::vector<bool>& hasMapPoint1, const DBoW2::FeatureVector& featVec1,
+                               const std::vector<cv::KeyPoint>& keysUn2, const cv::Mat& desc2, const std::vector<bool>& hasMapPoint2, const DBoW2::FeatureVector& featVec2,
+                               const float F12[9], float ex, float ey, const std::vector<float>& scaleFactors2, const std::vector<float>& levelSigma2_2,
+                               std::vector<std::pair<size_t, size_t> >& vMatchedPairs) {
+        const int n1 = desc1.rows, n2 = desc2.rows;
+        std::vector<uint8_t> d1((size_t)n1 * 32), d2((size_t)n2 * 32);
+        for (int i = 0; i < n1; i++) std::memcpy(&d1[(size_t)i * 32], desc1.ptr(i), 32);
+        for (int i = 0; i < n2; i++) std::memcpy(&d2[(size_t)i * 32], desc2.ptr(i), 32);
+        std::vector<int32_t> gq(1, 0), gc(1, 0), qi, ci;
+        DBoW2::FeatureVector::const_iterator it1 = featVec1.begin(), it2 = featVec2.begin();
+        while (it1 != featVec1.end() && it2 != featVec2.end()) {
+            if (it1->first == it2->first) {
+                for (unsigned int i : it1->second) if (!hasMapPoint1[i]) qi.push_back((int32_t)i);
+                for (unsigned int i : it2->second) if (!hasMapPoint2[i]) ci.push_back((int32_t)i);
+                gq.push_back((int32_t)qi.size()); gc.push_back((int32_t)ci.size());
+                ++it1; ++it2;
+            } else if (it1->first < it2->first) it1 = featVec1.lower_bound(it2->first);
+            else it2 = featVec2.lower_bound(it1->first);
+        }
+        const float e2[2] = {ex, ey};
+        std::vector<int32_t> m12((size_t)n1 + 1, -1);
+        static_assert(sizeof(cv::KeyPoint) == sizeof(b200_keypoint), "cv::KeyPoint layout");
+        const int nm = b200_match_for_triangulation_host((const b200_keypoint*)keysUn1.data(), d1.data(), n1, (const b200_keypoint*)keysUn2.data(), d2.data(), n2,
+                                                         gq.data(), qi.data(), gc.data(), ci.data(), (int)gq.size() - 1, F12, e2, scaleFactors2.data(),
+                                                         levelSigma2_2.data(), (int)scaleFactors2.size(), mbCheckOrientation ? 1 : 0, TH_LOW, m12.data(), device_);
+        b200slam_detail::check(nm);
+        vMatchedPairs.clear();
+        vMatchedPairs.reserve(nm);
+        for (int i = 0; i < n1; i++) if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
+        return nm;
+    }
+
+    // The keyframe search inside Fuse(KeyFrame*, vpMapPoints, th) (ORBmatcher.h:76, ORBmatcher.cc:831-981), Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)
+    // (ORBmatcher.h:79, :983-1104) and SearchBySim3 (ORBmatcher.h:70-71, :1106-1330).  Those functions keep their own statements up to
+    // "const float radius = th*pKF->mvScaleFactors[nPredictedLevel]" (they are cv::Mat algebra on one point), push a RadiusQuery instead of calling
+    // GetFeaturesInArea, and after ONE SearchInRadius call run their "if(bestDist<=TH_LOW) ..." statements over the answers in list order: the search
+    // itself never depends on what earlier points did to the keyframe.  chi2 > 0 adds Fuse's reprojection gate (5.99, monocular; invLevelSigma2 =
+    // pKF->mvInvLevelSigma2).  bestIdx[q] = -1 / bestDist[q] = 256 when no feature qualifies.
+    struct RadiusQuery { float u, v, radius; int predictedLevel; const unsigned char* descriptor; };
+    void SearchInRadius(const std::vector<cv::KeyPoint>& keysUn, const cv::Mat& descriptors, const float bounds[4], const std::vector<RadiusQuery>& queries,
+                        const std::vector<float>& invLevelSigma2, double chi2, std::vector<int>& bestIdx, std::vector<int>& bestDist) {
+        const int n = (int)keysUn.size(), nq = (int)queries.size();
+        std::vector<uint8_t> d((size_t)n * 32), qd((size_t)nq * 32);
+        for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], descriptors.ptr(i), 32);
+        std::vector<float> q3((size_t)nq * 3);
+        std::vector<int32_t> ql(nq), bi((size_t)nq + 1, -1), bd((size_t)nq + 1, 256);
+        for (int q = 0; q < nq; q++) {
+            q3[3 * q] = queries[q].u; q3[3 * q + 1] = queries[q].v; q3[3 * q + 2] = queries[q].radius; ql[q] = queries[q].predictedLevel;
+            std::memcpy(&qd[(size_t)q * 32], queries[q].descriptor, 32);
+        }
+        static_assert(sizeof(cv::KeyPoint) == sizeof(b200_keypoint), "cv::KeyPoint layout");
+        b200slam_detail::check(b200_match_kf_radius_host((const b200_keypoint*)keysUn.data(), d.data(), n, bounds, q3.data(), ql.data(), qd.data(), nq,
+                                                         invLevelSigma2.data(), (int)invLevelSigma2.size(), chi2, bi.data(), bd.data(), device_));
+        bestIdx.assign(bi.begin(), bi.begin() + nq);
+        bestDist.assign(bd.begin(), bd.begin() + nq);
+    }
+
+    // int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th)
+    // (ORBmatcher.h:52, ORBmatcher.cc:294-407) on projected points: here a matched feature hides itself from every later point, so the queries are
+    // replayed in order by the projection resolve kernel.  matchedBefore[i] = "vpMatched[i] != NULL"; assign[i] = index into `queries` newly
+    // matched to keyframe feature i or -1 (the caller stores vpMatched[i] = that point); returns nmatches.
+    int SearchByProjectionLoop(const std::vector<cv::KeyPoint>& keysUn, const cv::Mat& descriptors, const float bounds[4], const std::vector<bool>& matchedBefore,
+                               const std::vector<RadiusQuery>& queries, std::vector<int>& assign) {
+        std::vector<ProjectedPoint> pts(queries.size());
+        for (size_t q = 0; q < queries.size(); q++)
+            pts[q] = ProjectedPoint{queries[q].u, queries[q].v, queries[q].radius, queries[q].predictedLevel - 1, queries[q].predictedLevel, queries[q].descriptor, 0.f, true};
+        std::vector<unsigned char> occ(matchedBefore.size());
+        for (size_t i = 0; i < occ.size(); i++) occ[i] = matchedBefore[i] ? 1 : 0;
+        const bool ori = mbCheckOrientation;
+        mbCheckOrientation = false;                                 // no rotation histogram in this member (ORBmatcher.cc:294-407)
+        int nm;
+        try { nm = SearchByProjection(keysUn, descriptors, bounds, occ, pts, 1, assign, TH_LOW); } catch (...) { mbCheckOrientation = ori; throw; }
+        mbCheckOrientation = ori;
+        return nm;
     }
 
 protected:

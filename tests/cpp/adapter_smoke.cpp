@@ -49,6 +49,29 @@ int main(int argc, char** argv) {
             matcher.ComputeDistinctiveDescriptors(obs, best);
             if (best.size() != 2 || best[0] != 0 || best[1] != -1) { fprintf(stderr, "ComputeDistinctiveDescriptors: %d %d\n", best[0], best[1]); return 1; }
         }
+        // the KeyFrame-side members on a keyframe matched against itself: every feature must find itself
+        {
+            const float bounds[4] = {0.f, (float)w, 0.f, (float)h};
+            const std::vector<float> sf = extractor.GetScaleFactors(), s2 = extractor.GetScaleSigmaSquares(), is2 = extractor.GetInverseScaleSigmaSquares();
+            std::vector<ORB_SLAM2::ORBmatcher::RadiusQuery> qs(keys.size());
+            for (size_t i = 0; i < keys.size(); i++)
+                qs[i] = ORB_SLAM2::ORBmatcher::RadiusQuery{keys[i].pt.x, keys[i].pt.y, 3.0f * sf[keys[i].octave], keys[i].octave, desc.ptr((int)i)};
+            std::vector<int> bi, bd;
+            matcher.SearchInRadius(keys, desc, bounds, qs, is2, 5.99, bi, bd);                  // Fuse (ORBmatcher.cc:906-955)
+            for (size_t i = 0; i < keys.size(); i++)
+                if (bi[i] != (int)i || bd[i] != 0) { fprintf(stderr, "SearchInRadius: feature %zu -> %d (dist %d)\n", i, bi[i], bd[i]); return 1; }
+            std::vector<int> assign;
+            const int nl = matcher.SearchByProjectionLoop(keys, desc, bounds, std::vector<bool>(keys.size(), false), qs, assign);      // ORBmatcher.cc:294-407
+            if (nl != (int)keys.size()) { fprintf(stderr, "SearchByProjectionLoop: %d of %zu\n", nl, keys.size()); return 1; }
+            for (size_t i = 0; i < keys.size(); i++) if (assign[i] != (int)i) { fprintf(stderr, "SearchByProjectionLoop: feature %zu -> %d\n", i, assign[i]); return 1; }
+            // F12 of a pure image shift s = (5, 3): the epipolar line of x1 is the line through x1 along s, which contains x2 = x1
+            const float F12[9] = {0.f, 0.f, 0.03f, 0.f, 0.f, -0.05f, -0.03f, 0.05f, 0.f};
+            std::vector<std::pair<size_t, size_t> > pairs;
+            const int nt = matcher.SearchForTriangulation(keys, desc, std::vector<bool>(keys.size(), false), one, keys, desc, std::vector<bool>(keys.size(), false), one,
+                                                          F12, -5000.f, -5000.f, sf, s2, pairs);                                         // ORBmatcher.cc:661-829
+            if (nt != (int)keys.size() || pairs.size() != keys.size()) { fprintf(stderr, "SearchForTriangulation: %d of %zu\n", nt, keys.size()); return 1; }
+            for (size_t i = 0; i < pairs.size(); i++) if (pairs[i].first != i || pairs[i].second != i) { fprintf(stderr, "SearchForTriangulation: pair %zu\n", i); return 1; }
+        }
         const int dist = ORB_SLAM2::ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, desc.ptr(0)), cv::Mat(1, 32, CV_8U, desc.ptr(1)));
         FILE* o = fopen(argv[5], "wb");
         int hdr[4] = {(int)keys.size(), (int)markers.size(), nm, dist};
