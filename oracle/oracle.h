@@ -110,6 +110,27 @@ void oracle_voc_transform(const int32_t* parent, const uint8_t* is_leaf, const u
 void oracle_voc_vectors(const int32_t* word_id, const double* weight, const int32_t* node_id, int n,
                         int32_t* bow_words, double* bow_values, int32_t* fv_nodes, int32_t* fv_start, int32_t* fv_items, int32_t* counts2);
 
+// ---- KeyFrame-side ORBmatcher members (oracle/match2_oracle.cpp; argument lists = the ref_* wrappers of oracle/ref_match_wrap.cpp minus the trace) ----
+void oracle_kf_radius_search(const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* q_xyr, const int32_t* q_level,
+                             const uint8_t* q_desc, int nq, float scale_factor, int nlevels, double chi2, int32_t* best_idx, int32_t* best_dist);
+int oracle_search_for_triangulation(const oracle_keypoint* k1, const uint8_t* d1, const uint8_t* has_mp1, int n1, const int32_t* nodes1, const int32_t* start1,
+                                    const int32_t* items1, int nn1, const float* T1, const oracle_keypoint* k2, const uint8_t* d2, const uint8_t* has_mp2, int n2,
+                                    const int32_t* nodes2, const int32_t* start2, const int32_t* items2, int nn2, const float* T2, const float* bounds4,
+                                    const float* cam4, const float* F12, int check_ori, int32_t* matches12);
+int oracle_fuse(const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* cam4, const float* T, const uint8_t* held_state,
+                const int32_t* held_nobs, int n_mp, const uint8_t* mp_state, const float* mp_pos, const float* mp_normal, const uint8_t* mp_desc,
+                const float* mp_minmax, const int32_t* mp_nobs, float th, int32_t* fused_idx, int32_t* action);
+int oracle_fuse_sim3(const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* cam4, const float* S, const uint8_t* held_state,
+                     int n_mp, const uint8_t* mp_state, const float* mp_pos, const float* mp_normal, const uint8_t* mp_desc, const float* mp_minmax, float th,
+                     int32_t* replace_idx, int32_t* added_idx);
+int oracle_search_by_projection_loop(const oracle_keypoint* k, const uint8_t* d, int n, const float* bounds4, const float* cam4, const float* S, int n_mp,
+                                     const uint8_t* mp_state, const float* mp_pos, const float* mp_normal, const uint8_t* mp_desc, const float* mp_minmax, int th,
+                                     int32_t* matched);
+int oracle_search_by_sim3(const oracle_keypoint* k1, const uint8_t* d1, int n1, const float* T1, const uint8_t* mp1_state, const float* mp1_pos,
+                          const uint8_t* mp1_desc, const float* mp1_minmax, const oracle_keypoint* k2, const uint8_t* d2, int n2, const float* T2,
+                          const uint8_t* mp2_state, const float* mp2_pos, const uint8_t* mp2_desc, const float* mp2_minmax, const float* bounds4,
+                          const float* cam4, float s12, const float* R12, const float* t12, float th, int32_t* matches12);
+
 #ifdef __cplusplus
 }
 #endif
