@@ -188,10 +188,16 @@ def cpu_reference_run(imgs, wl, nthreads, ref_set=None):
     if wl["match"] and ref_set is not None:
         rd, ra = ref_set
         m = np.zeros((n, cap), np.int32); nm = np.zeros(n, np.int32)
-        oracle.lib().oracle_search_by_bow_bf_batch(rd.ctypes.data_as(vp), ra.ctypes.data_as(vp), len(rd), desc.ctypes.data_as(vp),
-                                                   kps28.ctypes.data_as(vp), cnt.ctypes.data_as(vp), n, cap, C.c_float(0.7), 1,
-                                                   C.c_float(np.float32(30.0) / np.float32(360.0)), m.ctypes.data_as(vp), nm.ctypes.data_as(vp), nthreads)
-        what += "; matcher = oracle restatement"
+        rm = oracle.ref_match()
+        if rm is not None and hasattr(rm, "ref_search_by_bow_bf_batch"):
+            rm.ref_search_by_bow_bf_batch(rd.ctypes.data_as(vp), ra.ctypes.data_as(vp), len(rd), desc.ctypes.data_as(vp), kps28.ctypes.data_as(vp),
+                                          cnt.ctypes.data_as(vp), n, cap, C.c_float(0.7), 1, m.ctypes.data_as(vp), nm.ctypes.data_as(vp), nthreads)
+            what += "; matcher = reference src/ORBmatcher.cc SearchByBoW on stand-in headers (oracle/_ref)"
+        else:
+            oracle.lib().oracle_search_by_bow_bf_batch(rd.ctypes.data_as(vp), ra.ctypes.data_as(vp), len(rd), desc.ctypes.data_as(vp),
+                                                       kps28.ctypes.data_as(vp), cnt.ctypes.data_as(vp), n, cap, C.c_float(0.7), 1,
+                                                       C.c_float(np.float32(30.0) / np.float32(360.0)), m.ctypes.data_as(vp), nm.ctypes.data_as(vp), nthreads)
+            what += "; matcher = oracle restatement"
         kind = "port" if kind == "port" else "reference"
     return time.perf_counter() - t0, kind, what
 

@@ -4,7 +4,9 @@
 // matcher made (so the product path can be given the very same projections).  Used by tests/test_oracle_vs_ref.py to pin oracle/match_oracle.cpp
 // and by tests/golden/make_match_golden.py to write tests/golden/match_ref.npz, which travels to the GPU box.
 #include "ORBmatcher.h"          // the reference's own header (slam_types.h is force-included in front of it)
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 RefTrace g_ref_trace;
 namespace ORB_SLAM2 {
@@ -408,6 +410,43 @@ int ref_search_by_sim3(const oracle_keypoint* k1, const uint8_t* d1, int n1, con
     for (int i = 0; i < n1; i++) matches12[i] = vm[i] ? vm[i]->id - 2000000 : -1;
     *n_queries = dump_trace_all(q_xyr, q_lev, q_mp, n1 + n2);
     return nf;
+}
+
+// batch driver for the CPU reference arm of bench.py: the reference's own SearchByBoW(KeyFrame*, Frame&, ...) with one all-inclusive vocabulary node
+// (== brute force) for one reference set against n frames laid out like the extractor's output (desc [n][cap][32], angles inside
+// 28-byte keypoint records), nthreads workers (the member touches no shared state).  Same argument list as oracle_search_by_bow_bf_batch.
+int ref_search_by_bow_bf_batch(const uint8_t* kf_desc, const float* kf_angle, int n_kf, const uint8_t* f_desc, const uint8_t* f_kps28, const int32_t* n_f, int n,
+                               int cap, float nnratio, int check_ori, int32_t* matches, int32_t* n_matches, int nthreads) {
+    KeyFrame kf;
+    kf.N = n_kf; kf.mvKeysUn = keys_from_angles(kf_angle, n_kf); kf.mvKeys = kf.mvKeysUn; kf.mDescriptors = desc_mat(kf_desc, n_kf);
+    std::vector<unsigned int> all_kf(n_kf);
+    for (int i = 0; i < n_kf; i++) all_kf[i] = i;
+    kf.mFeatVec[7] = all_kf;
+    std::vector<MapPoint> pts(n_kf);
+    kf.mvpMapPoints.assign(n_kf, (MapPoint*)NULL);
+    for (int i = 0; i < n_kf; i++) { pts[i].id = i; kf.mvpMapPoints[i] = &pts[i]; }
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (int f; (f = next.fetch_add(1)) < n;) {
+            const int nf = n_f[f];
+            Frame F;
+            F.N = nf; F.mvKeys.resize(nf);
+            for (int i = 0; i < nf; i++) memcpy(&F.mvKeys[i].angle, f_kps28 + ((size_t)f * cap + i) * 28 + 12, 4);
+            F.mvKeysUn = F.mvKeys; F.mDescriptors = desc_mat(f_desc + (size_t)f * cap * 32, nf);
+            std::vector<unsigned int> all_f(nf);
+            for (int i = 0; i < nf; i++) all_f[i] = i;
+            F.mFeatVec[7] = all_f;
+            std::vector<MapPoint*> vp;
+            ORBmatcher matcher(nnratio, check_ori != 0);
+            n_matches[f] = matcher.SearchByBoW(&kf, F, vp);
+            for (int i = 0; i < nf; i++) matches[(size_t)f * cap + i] = vp[i] ? vp[i]->id : -1;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    return 0;
 }
 
 }  // extern "C"

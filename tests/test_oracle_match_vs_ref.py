@@ -112,3 +112,26 @@ def test_golden_file_is_current(golden):
     run = c["runs"][0]
     n, asg, qx, ql, qm = mc.ref_last(R, c, float(run["cfg"][0]), int(run["cfg"][1]))
     assert n == run["n"] and np.array_equal(asg, run["assign"]) and np.array_equal(qx, run["q_xyr"]) and np.array_equal(qm, run["q_mp"])
+
+
+@pytest.mark.skipif(oracle.ref_match() is None, reason="oracle/_ref/libref_match.so not built (needs /root/reference)")
+def test_reference_arm_batch_matcher_equals_oracle_batch_matcher():
+    """bench.py --impl reference times the reference's own SearchByBoW (one node) through ref_search_by_bow_bf_batch; the oracle's batch driver, which
+    the GPU tests and smoke() check the CUDA matcher against, gives the same matches on extractor-shaped buffers"""
+    import ctypes as C
+    from orb_slam2_aruco_b200 import synth
+    vp = C.c_void_p
+    imgs = synth.make_batch(3, 640, 480, markers=20, first=3)
+    k, desc, cnt = oracle.orb_extract_batch(imgs, 1000, nthreads=3)
+    kps28 = np.ascontiguousarray(k).view(np.uint8).reshape(3, -1, 28); cap = kps28.shape[1]
+    rk, rd = oracle.orb_extract(np.roll(imgs[0], (3, 5), axis=(0, 1)), 1000)
+    rd = np.ascontiguousarray(rd); ra = np.ascontiguousarray(rk["angle"])
+    m1 = np.zeros((3, cap), np.int32); n1 = np.zeros(3, np.int32); m2 = m1.copy(); n2 = n1.copy()
+    oracle.ref_match().ref_search_by_bow_bf_batch(rd.ctypes.data_as(vp), ra.ctypes.data_as(vp), len(rd), desc.ctypes.data_as(vp), kps28.ctypes.data_as(vp),
+                                                  cnt.ctypes.data_as(vp), 3, cap, C.c_float(0.7), 1, m1.ctypes.data_as(vp), n1.ctypes.data_as(vp), 2)
+    oracle.lib().oracle_search_by_bow_bf_batch(rd.ctypes.data_as(vp), ra.ctypes.data_as(vp), len(rd), desc.ctypes.data_as(vp), kps28.ctypes.data_as(vp),
+                                               cnt.ctypes.data_as(vp), 3, cap, C.c_float(0.7), 1, C.c_float(np.float32(30.0) / np.float32(360.0)),
+                                               m2.ctypes.data_as(vp), n2.ctypes.data_as(vp), 2)
+    assert np.array_equal(n1, n2) and n1[0] > 300
+    for f in range(3):
+        assert np.array_equal(m1[f, :cnt[f]], m2[f, :cnt[f]])
