@@ -189,6 +189,18 @@ int b200_match_for_triangulation_host(const b200_keypoint* kps1_un, const uint8_
 int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_kf, const float* bounds4, const float* q_xyr, const int32_t* q_level,
                               const uint8_t* q_desc, int n_queries, const float* inv_level_sigma2, int nlevels, double chi2, int32_t* best_idx,
                               int32_t* best_dist, int device);
+/* The projection front of those members and of SearchByProjection(pKF, Scw, ...) for n map points at once (src/ORBmatcher.cc:318-366, 848-898,
+ * 1006-1061; per direction of SearchBySim3 :1158-1195 / :1238-1275), in the reference's cv::Mat CV_32F arithmetic.  Rcw / tcw / Ow: rotation (row-major
+ * 3x3), translation and camera centre of the keyframe (for the Scw overloads the decomposed Sim3, :302-307).  sR / tt non-NULL: SearchBySim3 - the point
+ * goes world -> camera a (Rcw, tcw) -> camera b = sR * p + tt, its distance is |p_b| and there is no viewing-angle test (Ow, normal unused).
+ * pos [n][3], normal [n][3] (NULL: no viewing-angle test), minmax [n][2] = mfMinDistance, mfMaxDistance.  scale_factors [nlevels];
+ * level_thresholds [nlevels - 1]: the largest float ratio mfMaxDistance / dist for which MapPoint::PredictScale still answers level k, found by the
+ * caller with its own libm (bisection over float bit patterns), so that the device reproduces the host's ceil(logf(ratio) / logf(scaleFactor)).
+ * valid [n] out: 0 when one of the reference's tests discards the point; q_xyr [n][3] = (u, v, th * scale_factors[level]); level [n] = nPredictedLevel.
+ * HOST pointers. */
+int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, const float* sR, const float* tt, const float* cam4, const float* bounds4,
+                         const float* pos, const float* normal, const float* minmax, int n, float th, const float* scale_factors,
+                         const float* level_thresholds, int nlevels, uint8_t* valid, float* q_xyr, int32_t* level, int device);
 /* Plain 256-bit Hamming distance matrix rows x cols (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1651-1667). */
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device);
 /* Candidate-list matching core shared by SearchByProjection / SearchForInitialization:

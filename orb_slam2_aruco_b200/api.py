@@ -324,7 +324,23 @@ class ORBmatcher:
         return bi, bd, sd
 
 
-    # ---- KeyFrame-side members (local mapping / loop closing threads): geometry glue in kfgeom.py, searches on the device ---------------------
+    # ---- KeyFrame-side members (local mapping / loop closing threads): per-call glue in kfgeom.py, projection and searches on the device ---------------------
+    def project_points(self, pose, cam4, bounds4, pos, normal, minmax, th, sim3=None, scale_factor=1.2, nlevels=8):
+        """the projection front of Fuse / Fuse(Scw) / SearchByProjection(Scw) / SearchBySim3 for all points at once (b200_kf_project_host).
+        pose = (R, t, Ow) of the keyframe; sim3 = (sR, t) for SearchBySim3's second transform.  Returns (valid bool [N], q_xyr [N, 3], level [N])."""
+        R, t, Ow = (np.ascontiguousarray(a, np.float32) for a in pose)
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3); mm = np.ascontiguousarray(minmax, np.float32).reshape(-1, 2)
+        nrm = None if normal is None else np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+        sR, tt = (None, None) if sim3 is None else (np.ascontiguousarray(sim3[0], np.float32), np.ascontiguousarray(sim3[1], np.float32))
+        cam = np.ascontiguousarray(cam4, np.float32); b = np.ascontiguousarray(bounds4, np.float32)
+        sf = np.ascontiguousarray(kfgeom.pyramid(scale_factor, nlevels)[0], np.float32)
+        thr = np.ascontiguousarray(kfgeom.level_thresholds(float(scale_factor), int(nlevels)), np.float32)
+        n = len(pos)
+        valid = np.zeros(max(n, 1), np.uint8); q3 = np.zeros((max(n, 1), 3), np.float32); level = np.zeros(max(n, 1), np.int32)
+        check(lib().b200_kf_project_host(ptr(R), ptr(t), ptr(Ow), ptr(sR), ptr(tt), ptr(cam), ptr(b), ptr(pos), ptr(nrm), ptr(mm), n, float(th), ptr(sf), ptr(thr),
+                                         int(nlevels), ptr(valid), ptr(q3), ptr(level), self._device))
+        return valid[:n].astype(bool), q3[:n], level[:n]
+
     def kf_radius_search(self, kps_un, desc, bounds4, q_xyr, q_level, q_desc, chi2=0.0, scale_factor=1.2, nlevels=8):
         """best keyframe feature per projected point (b200_match_kf_radius_host) -> (best_idx, best_dist)"""
         k = np.ascontiguousarray(kps_un); assert k.dtype == KP_DTYPE
@@ -363,7 +379,7 @@ class ORBmatcher:
         pMPinKF->Replace(pMP); fused_idx names the keyframe feature, or -3 - o when pMPinKF is point o of this call that was added earlier."""
         st = np.asarray(mp_state, np.uint8); nobs = np.asarray(mp_nobs, np.int32).copy()
         hs = np.asarray(held_state, np.uint8); hn = np.asarray(held_nobs, np.int32)
-        valid, q3, level = kfgeom.project_points(kfgeom.pose_from_T(Tcw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
+        valid, q3, level = self.project_points(kfgeom.pose_from_T(Tcw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
         valid &= (st == 1)
         qs = np.nonzero(valid)[0]
         bi, bd = self.kf_radius_search(kps_un, desc, bounds4, q3[qs], level[qs], np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs], chi2=5.99)
@@ -399,7 +415,7 @@ class ORBmatcher:
         replace_idx[m] = keyframe feature whose point vpReplacePoint[m] names (-3 - o: point o added earlier in this call), added_idx[m] = feature the
         point became an observation of."""
         st = np.asarray(mp_state, np.uint8); hs = np.asarray(held_state, np.uint8)
-        valid, q3, level = kfgeom.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
+        valid, q3, level = self.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
         valid &= (st != 2) & (st != 3)
         qs = np.nonzero(valid)[0]
         bi, bd = self.kf_radius_search(kps_un, desc, bounds4, q3[qs], level[qs], np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs])
@@ -425,7 +441,7 @@ class ORBmatcher:
         feature is hidden from every later point, so the queries are replayed in order by the projection resolve kernel
         (b200_match_by_projection_host, mode 1 without the rotation histogram, TH_LOW).  Returns (nmatches, vpMatched after the call)."""
         st = np.asarray(mp_state, np.uint8); matched = np.asarray(matched, np.int32).copy()
-        valid, q3, level = kfgeom.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, int(th))
+        valid, q3, level = self.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, int(th))
         found = np.zeros(len(st), bool); found[matched[matched >= 0]] = True
         valid &= (st != 2) & ~found
         qs = np.nonzero(valid)[0]
@@ -448,8 +464,8 @@ class ORBmatcher:
         done2 = np.zeros(n2, bool)
         j = m12[done1]; done2[j[st2[j] > 0]] = True                  # GetIndexInKeyFrame(pKF2) >= 0 only when that KF2 feature holds the point
         sR12, sR21, t21 = kfgeom.sim3_between(s12, R12, t12)
-        v1, q1, l1 = kfgeom.project_points_sim3(kfgeom.pose_from_T(T1), sR21, t21, cam4, bounds4, mp1_pos, mp1_minmax, th)
-        v2, q2, l2 = kfgeom.project_points_sim3(kfgeom.pose_from_T(T2), sR12, np.asarray(t12, np.float32).reshape(3), cam4, bounds4, mp2_pos, mp2_minmax, th)
+        v1, q1, l1 = self.project_points(kfgeom.pose_from_T(T1), cam4, bounds4, mp1_pos, None, mp1_minmax, th, sim3=(sR21, t21))
+        v2, q2, l2 = self.project_points(kfgeom.pose_from_T(T2), cam4, bounds4, mp2_pos, None, mp2_minmax, th, sim3=(sR12, np.asarray(t12, np.float32).reshape(3)))
         v1 &= (st1 == 1) & ~done1; v2 &= (st2 == 1) & ~done2
         a, b = np.nonzero(v1)[0], np.nonzero(v2)[0]
         bi1, bd1 = self.kf_radius_search(kps2_un, desc2, bounds4, q1[a], l1[a], np.asarray(mp1_desc, np.uint8).reshape(-1, 32)[a])

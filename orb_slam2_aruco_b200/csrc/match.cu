@@ -726,6 +726,60 @@ k_radius_best(const b200_keypoint* __restrict__ k, const ulonglong4* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The projection front of Fuse (ORBmatcher.cc:848-898), Fuse(Scw) (:1006-1061), SearchByProjection(pKF, Scw, ...) (:318-366) and of each direction of
+// SearchBySim3 (:1158-1195 / :1238-1275) for all map points at once: thread per point, the reference's statements in its cv::Mat CV_32F arithmetic
+// (3-term products accumulate in double and are stored as float; sums, differences and the pinhole model are float; norm / dot in double).
+// MapPoint::PredictScale (MapPoint.cc:403-435) is ceil(logf(ratio) / logf(scaleFactor)), monotone in ratio: the host finds, with ITS libm, the
+// largest float ratio that still yields level n (b200_kf_project_host's level_thresholds), and the level is the number of thresholds below the
+// ratio - the same integers as the host's logf without a device logf.
+// ------------------------------------------------------------------------------------------------
+struct ProjGeom {
+    float R[9], t[3], Ow[3], sR[9], tt[3];
+    float fx, fy, cx, cy, min_x, max_x, min_y, max_y, th;
+    float sf[16], thr[16];
+    int nlevels, sim3, has_normal;
+};
+
+__device__ __forceinline__ float dot3_f(const float* a, float b0, float b1, float b2) {
+    return __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn((double)a[0], (double)b0), __dmul_rn((double)a[1], (double)b1)), __dmul_rn((double)a[2], (double)b2)));
+}
+__device__ __forceinline__ double dot3_d(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return __dadd_rn(__dadd_rn(__dmul_rn((double)a0, (double)b0), __dmul_rn((double)a1, (double)b1)), __dmul_rn((double)a2, (double)b2));
+}
+
+__global__ void __launch_bounds__(256)
+k_kf_project(const float* __restrict__ pos, const float* __restrict__ normal, const float* __restrict__ minmax, int n, const ProjGeom g,
+             unsigned char* __restrict__ valid, float* __restrict__ q3, int* __restrict__ level) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float X = pos[3 * i], Y = pos[3 * i + 1], Z = pos[3 * i + 2];
+    float p0 = __fadd_rn(dot3_f(g.R, X, Y, Z), g.t[0]), p1 = __fadd_rn(dot3_f(g.R + 3, X, Y, Z), g.t[1]), p2 = __fadd_rn(dot3_f(g.R + 6, X, Y, Z), g.t[2]);
+    if (g.sim3) {
+        const float a0 = p0, a1 = p1, a2 = p2;
+        p0 = __fadd_rn(dot3_f(g.sR, a0, a1, a2), g.tt[0]); p1 = __fadd_rn(dot3_f(g.sR + 3, a0, a1, a2), g.tt[1]); p2 = __fadd_rn(dot3_f(g.sR + 6, a0, a1, a2), g.tt[2]);
+    }
+    bool ok = !(p2 < 0.0f);                                       // depth must be positive
+    const float invz = __fdiv_rn(1.0f, p2);
+    const float u = __fadd_rn(__fmul_rn(g.fx, __fmul_rn(p0, invz)), g.cx), v = __fadd_rn(__fmul_rn(g.fy, __fmul_rn(p1, invz)), g.cy);
+    ok = ok && u >= g.min_x && u < g.max_x && v >= g.min_y && v < g.max_y;      // KeyFrame::IsInImage
+    const float max_d = __fmul_rn(1.2f, minmax[2 * i + 1]), min_d = __fmul_rn(0.8f, minmax[2 * i]);  // GetMax/MinDistanceInvariance
+    float dist;
+    if (g.sim3) dist = __double2float_rn(__dsqrt_rn(dot3_d(p0, p1, p2, p0, p1, p2)));
+    else {
+        const float o0 = __fsub_rn(X, g.Ow[0]), o1 = __fsub_rn(Y, g.Ow[1]), o2 = __fsub_rn(Z, g.Ow[2]);
+        dist = __double2float_rn(__dsqrt_rn(dot3_d(o0, o1, o2, o0, o1, o2)));
+        if (g.has_normal && dot3_d(o0, o1, o2, normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]) < __dmul_rn(0.5, (double)dist)) ok = false;   // 60 degrees
+    }
+    if (dist < min_d || dist > max_d) ok = false;
+    const float ratio = __fdiv_rn(minmax[2 * i + 1], dist);
+    int lv = 0;
+    for (int k = 0; k < g.nlevels - 1; k++) lv += ratio > g.thr[k];
+    valid[i] = ok ? 1 : 0;
+    q3[3 * i] = u; q3[3 * i + 1] = v; q3[3 * i + 2] = __fmul_rn(g.th, g.sf[lv]);
+    level[i] = lv;
+}
+
 struct MatchScratch { uint32_t* topk; size_t cap; int device; };
 static thread_local MatchScratch g_ms = {nullptr, 0, -1};
 
@@ -1117,6 +1171,37 @@ int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, 
     if (o) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
     B200_CUDA(cudaMemcpy(best_idx, bi.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(best_dist, bd.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, const float* sR, const float* tt, const float* cam4, const float* bounds4,
+                         const float* pos, const float* normal, const float* minmax, int n, float th, const float* scale_factors,
+                         const float* level_thresholds, int nlevels, uint8_t* valid, float* q_xyr, int32_t* level, int device) {
+    if (n < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n == 0) return B200_OK;
+    if (!Rcw || !tcw || !cam4 || !bounds4 || !pos || !minmax || !scale_factors || (nlevels > 1 && !level_thresholds) || !valid || !q_xyr || !level ||
+        (!sR && !Ow) || (sR && !tt))
+        return fail(B200_EINVAL, "null %s", "pointer");
+    ProjGeom g;
+    memset(&g, 0, sizeof(g));
+    for (int i = 0; i < 9; i++) { g.R[i] = Rcw[i]; if (sR) g.sR[i] = sR[i]; }
+    for (int i = 0; i < 3; i++) { g.t[i] = tcw[i]; if (Ow) g.Ow[i] = Ow[i]; if (sR) g.tt[i] = tt[i]; }
+    g.fx = cam4[0]; g.fy = cam4[1]; g.cx = cam4[2]; g.cy = cam4[3];
+    g.min_x = (float)(int)bounds4[0]; g.max_x = (float)(int)bounds4[1]; g.min_y = (float)(int)bounds4[2]; g.max_y = (float)(int)bounds4[3];   // int members of KeyFrame
+    g.th = th; g.nlevels = nlevels; g.sim3 = sR ? 1 : 0; g.has_normal = normal ? 1 : 0;
+    for (int i = 0; i < nlevels; i++) g.sf[i] = scale_factors[i];
+    for (int i = 0; i + 1 < nlevels; i++) g.thr[i] = level_thresholds[i];
+    DevBuf dp, dn, dm, dv, dq, dl;
+    if ((rc = dp.upload(pos, (size_t)n * 12)) || (normal && (rc = dn.upload(normal, (size_t)n * 12))) || (rc = dm.upload(minmax, (size_t)n * 8)) ||
+        (rc = dv.alloc((size_t)n)) || (rc = dq.alloc((size_t)n * 12)) || (rc = dl.alloc((size_t)n * 4)))
+        return rc;
+    B200_LAUNCH(k_kf_project, (n + 255) / 256, 256, 0, 0, (const float*)dp.p, (const float*)dn.p, (const float*)dm.p, n, g, (unsigned char*)dv.p, (float*)dq.p, (int*)dl.p);
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(valid, dv.p, (size_t)n, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(q_xyr, dq.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(level, dl.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
 }
 

@@ -1,8 +1,10 @@
-"""Host glue of the KeyFrame-side ORBmatcher members: the projection of map points into a keyframe as the reference computes it with cv::Mat
-on CV_32F (src/ORBmatcher.cc:294-358, 831-895, 983-1061, 1106-1195): matrix products accumulate in double and are stored as float, sums and
-differences are float, MapPoint::PredictScale (src/MapPoint.cc:403-435) goes through the C library's logf like the reference's std::log(float).
-Everything here is O(points) arithmetic that prepares the radius queries for b200_match_kf_radius_host / b200_match_by_projection_host; the
-searches themselves run on the device."""
+"""Host glue of the KeyFrame-side ORBmatcher members: the per-CALL quantities the reference computes once before its loop over map points, in
+its cv::Mat CV_32F arithmetic (matrix products accumulate in double and are stored as float): pose decomposition (src/ORBmatcher.cc:302-307,
+831-841), the Sim3 pair of SearchBySim3 (:1123-1126), the epipole of SearchForTriangulation (:668-674), the scale pyramid tables, and the
+PredictScale thresholds.  Everything per POINT (projection, tests, predicted level, radius: k_kf_project; grid queries and Hamming search:
+k_features_in_area, k_radius_best, k_proj_resolve) runs on the device."""
+import functools
+import struct
 import ctypes
 import ctypes.util
 
@@ -22,6 +24,29 @@ def pyramid(scale_factor=1.2, nlevels=8):
         sf[i] = sf[i - 1] * f
         s2[i] = sf[i] * sf[i]
     return sf, s2, (f32(1.0) / s2).astype(f32), f32(_libm.logf(float(f)))
+
+
+@functools.lru_cache(maxsize=8)
+def level_thresholds(scale_factor=1.2, nlevels=8):
+    """MapPoint::PredictScale (src/MapPoint.cc:403-435) is ceil(logf(ratio) / logf(scaleFactor)) clamped to [0, nlevels): monotone in ratio.
+    thresholds[n] = the largest float ratio that still yields a level <= n, found by bisection over float bit patterns with THIS host's logf (the
+    one the reference would call), so that level = #(ratio > thresholds[n]) equals the reference's integer without a device logf."""
+    log_sf = f32(_libm.logf(float(f32(scale_factor))))
+
+    def level(bits):
+        r = struct.unpack("<f", struct.pack("<I", bits))[0]
+        return int(np.ceil(f32(f32(_libm.logf(r)) / log_sf)))
+    out = np.zeros(max(nlevels - 1, 1), f32)
+    for n in range(nlevels - 1):
+        lo, hi = 0x00800000, 0x7f000000                           # smallest normal float (level far below 0) .. 2^127 (far above any level)
+        while hi - lo > 1:
+            mid = (lo + hi) // 2
+            if level(mid) <= n:
+                lo = mid
+            else:
+                hi = mid
+        out[n] = struct.unpack("<f", struct.pack("<I", lo))[0]
+    return out
 
 
 def _mul_points(M, X):
@@ -58,76 +83,6 @@ def pose_from_S(S):
     R = (sR.astype(np.float64) / np.float64(scw)).astype(f32)
     t = (S[:3, 3].astype(np.float64) / np.float64(scw)).astype(f32)
     return R, t, _mul_points(-R.T, t[None])[0]
-
-
-def predict_scale(max_distance, dist, log_sf, nlevels):
-    """MapPoint::PredictScale, element-wise; entries with a non-positive or non-finite ratio get level 0 (they are discarded by the callers' tests)"""
-    with np.errstate(all="ignore"):
-        ratio = (np.asarray(max_distance, f32) / np.asarray(dist, f32)).astype(f32)
-    out = np.zeros(len(ratio), np.int32)
-    for i, r in enumerate(ratio):
-        if not np.isfinite(r) or r <= 0:
-            continue
-        n = int(np.ceil(f32(f32(_libm.logf(float(r))) / log_sf)))
-        out[i] = min(max(n, 0), nlevels - 1)
-    return out
-
-
-def _pixel(pc, cam4):
-    cam4 = np.asarray(cam4, f32)
-    with np.errstate(all="ignore"):
-        invz = (f32(1.0) / pc[:, 2]).astype(f32)
-        u = cam4[0] * (pc[:, 0] * invz) + cam4[2]
-        v = cam4[1] * (pc[:, 1] * invz) + cam4[3]
-    return u.astype(f32), v.astype(f32), invz
-
-
-def _in_image(u, v, bounds4):
-    b = [f32(int(x)) for x in np.asarray(bounds4, f32)]           # KeyFrame keeps mnMinX .. mnMaxY as int (include/KeyFrame.h:211-214)
-    return (u >= b[0]) & (u < b[1]) & (v >= b[2]) & (v < b[3])
-
-
-def project_points(pose, cam4, bounds4, pos, normal, minmax, th, scale_factor=1.2, nlevels=8):
-    """the part of Fuse / Fuse(Scw) / SearchByProjection(Scw) between "Get 3D Coords" and GetFeaturesInArea for all points at once.
-    pose = (R, t, Ow).  Returns (valid [N] bool, q_xyr [N, 3] float32, level [N] int32); rows with valid = False were discarded by one of the tests."""
-    R, t, Ow = pose
-    pos = np.ascontiguousarray(pos, f32).reshape(-1, 3); normal = np.ascontiguousarray(normal, f32).reshape(-1, 3)
-    minmax = np.ascontiguousarray(minmax, f32).reshape(-1, 2)
-    sf, _, _, log_sf = pyramid(scale_factor, nlevels)
-    pc = (_mul_points(R, pos) + t).astype(f32)
-    valid = ~(pc[:, 2] < 0)
-    u, v, _ = _pixel(pc, cam4)
-    valid &= _in_image(u, v, bounds4)
-    maxd, mind = f32(1.2) * minmax[:, 1], f32(0.8) * minmax[:, 0]
-    PO = (pos - Ow).astype(f32)
-    dist = np.sqrt(_dot_rows(PO, PO)).astype(f32)
-    valid &= ~(dist < mind) & ~(dist > maxd)
-    valid &= ~(_dot_rows(PO, normal) < 0.5 * dist.astype(np.float64))
-    level = np.zeros(len(pos), np.int32)
-    idx = np.nonzero(valid)[0]
-    level[idx] = predict_scale(minmax[idx, 1], dist[idx], log_sf, nlevels)
-    radius = (f32(th) * sf[level]).astype(f32)
-    return valid, np.ascontiguousarray(np.stack([u, v, radius], 1), f32), level
-
-
-def project_points_sim3(pose_a, sR, tt, cam4, bounds4, pos, minmax, th, scale_factor=1.2, nlevels=8):
-    """one direction of SearchBySim3 (src/ORBmatcher.cc:1158-1195): world point -> camera a -> camera b = sR * p + tt -> pixel in keyframe b"""
-    R, t, _ = pose_a
-    pos = np.ascontiguousarray(pos, f32).reshape(-1, 3); minmax = np.ascontiguousarray(minmax, f32).reshape(-1, 2)
-    sf, _, _, log_sf = pyramid(scale_factor, nlevels)
-    pa = (_mul_points(R, pos) + t).astype(f32)
-    pb = (_mul_points(sR, pa) + tt).astype(f32)
-    valid = ~(pb[:, 2] < 0)
-    u, v, _ = _pixel(pb, cam4)
-    valid &= _in_image(u, v, bounds4)
-    maxd, mind = f32(1.2) * minmax[:, 1], f32(0.8) * minmax[:, 0]
-    dist = np.sqrt(_dot_rows(pb, pb)).astype(f32)
-    valid &= ~(dist < mind) & ~(dist > maxd)
-    level = np.zeros(len(pos), np.int32)
-    idx = np.nonzero(valid)[0]
-    level[idx] = predict_scale(minmax[idx, 1], dist[idx], log_sf, nlevels)
-    radius = (f32(th) * sf[level]).astype(f32)
-    return valid, np.ascontiguousarray(np.stack([u, v, radius], 1), f32), level
 
 
 def sim3_between(s12, R12, t12):

@@ -191,6 +191,83 @@ def run_sim3(L, prefix, c, th):
     return L.oracle_search_by_sim3(*args), m12
 
 
+# ---- numpy model of the device projection kernel (k_kf_project): the reference's per-point statements in cv::Mat CV_32F arithmetic.  Used by the CPU
+# ---- tests to pin that arithmetic to the queries the reference itself made, and as the projection of the oracle-backed test double ------------
+from orb_slam2_aruco_b200 import kfgeom  # noqa: E402
+
+f32 = np.float32
+
+
+def predict_scale(max_distance, dist, log_sf, nlevels):
+    """MapPoint::PredictScale (src/MapPoint.cc:403-435) element by element through libm's logf, the way the reference evaluates it"""
+    with np.errstate(all="ignore"):
+        ratio = (np.asarray(max_distance, f32) / np.asarray(dist, f32)).astype(f32)
+    out = np.zeros(len(ratio), np.int32)
+    for i, r in enumerate(ratio):
+        if not np.isfinite(r) or r <= 0:
+            continue
+        n = int(np.ceil(f32(f32(kfgeom._libm.logf(float(r))) / log_sf)))
+        out[i] = min(max(n, 0), nlevels - 1)
+    return out
+
+
+def _pixel(pc, cam4):
+    cam4 = np.asarray(cam4, f32)
+    with np.errstate(all="ignore"):
+        invz = (f32(1.0) / pc[:, 2]).astype(f32)
+        u = cam4[0] * (pc[:, 0] * invz) + cam4[2]
+        v = cam4[1] * (pc[:, 1] * invz) + cam4[3]
+    return u.astype(f32), v.astype(f32), invz
+
+
+def _in_image(u, v, bounds4):
+    b = [f32(int(x)) for x in np.asarray(bounds4, f32)]           # KeyFrame keeps mnMinX .. mnMaxY as int (include/KeyFrame.h:211-214)
+    return (u >= b[0]) & (u < b[1]) & (v >= b[2]) & (v < b[3])
+
+
+def host_project_points(pose, cam4, bounds4, pos, normal, minmax, th, scale_factor=1.2, nlevels=8):
+    """the part of Fuse / Fuse(Scw) / SearchByProjection(Scw) between "Get 3D Coords" and GetFeaturesInArea for all points at once.
+    pose = (R, t, Ow).  Returns (valid [N] bool, q_xyr [N, 3] float32, level [N] int32); rows with valid = False were discarded by one of the tests."""
+    R, t, Ow = pose
+    pos = np.ascontiguousarray(pos, f32).reshape(-1, 3); normal = np.ascontiguousarray(normal, f32).reshape(-1, 3)
+    minmax = np.ascontiguousarray(minmax, f32).reshape(-1, 2)
+    sf, _, _, log_sf = kfgeom.pyramid(scale_factor, nlevels)
+    pc = (kfgeom._mul_points(R, pos) + t).astype(f32)
+    valid = ~(pc[:, 2] < 0)
+    u, v, _ = _pixel(pc, cam4)
+    valid &= _in_image(u, v, bounds4)
+    maxd, mind = f32(1.2) * minmax[:, 1], f32(0.8) * minmax[:, 0]
+    PO = (pos - Ow).astype(f32)
+    dist = np.sqrt(kfgeom._dot_rows(PO, PO)).astype(f32)
+    valid &= ~(dist < mind) & ~(dist > maxd)
+    valid &= ~(kfgeom._dot_rows(PO, normal) < 0.5 * dist.astype(np.float64))
+    level = np.zeros(len(pos), np.int32)
+    idx = np.nonzero(valid)[0]
+    level[idx] = predict_scale(minmax[idx, 1], dist[idx], log_sf, nlevels)
+    radius = (f32(th) * sf[level]).astype(f32)
+    return valid, np.ascontiguousarray(np.stack([u, v, radius], 1), f32), level
+
+
+def host_project_points_sim3(pose_a, sR, tt, cam4, bounds4, pos, minmax, th, scale_factor=1.2, nlevels=8):
+    """one direction of SearchBySim3 (src/ORBmatcher.cc:1158-1195): world point -> camera a -> camera b = sR * p + tt -> pixel in keyframe b"""
+    R, t, _ = pose_a
+    pos = np.ascontiguousarray(pos, f32).reshape(-1, 3); minmax = np.ascontiguousarray(minmax, f32).reshape(-1, 2)
+    sf, _, _, log_sf = kfgeom.pyramid(scale_factor, nlevels)
+    pa = (kfgeom._mul_points(R, pos) + t).astype(f32)
+    pb = (kfgeom._mul_points(sR, pa) + tt).astype(f32)
+    valid = ~(pb[:, 2] < 0)
+    u, v, _ = _pixel(pb, cam4)
+    valid &= _in_image(u, v, bounds4)
+    maxd, mind = f32(1.2) * minmax[:, 1], f32(0.8) * minmax[:, 0]
+    dist = np.sqrt(kfgeom._dot_rows(pb, pb)).astype(f32)
+    valid &= ~(dist < mind) & ~(dist > maxd)
+    level = np.zeros(len(pos), np.int32)
+    idx = np.nonzero(valid)[0]
+    level[idx] = predict_scale(minmax[idx, 1], dist[idx], log_sf, nlevels)
+    radius = (f32(th) * sf[level]).astype(f32)
+    return valid, np.ascontiguousarray(np.stack([u, v, radius], 1), f32), level
+
+
 # ---- replay of tests/golden/match_ref2.npz through the product's ORBmatcher mirror -----------------------------------------------------------
 def fv_of(c, side):
     return mc.fv_dict(c["n" + side], c["s" + side], c["i" + side])

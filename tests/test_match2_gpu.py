@@ -86,3 +86,32 @@ def test_fuse_and_sim3_match_oracle_on_full_size_keyframes(built_lib):
         got = M.SearchBySim3(c["k1"], c["d1"], c["T1"], c["st1"], c["p1"], c["d1"], c["mm1"], c["k2"], c["d2"], c["T2"], c["st2"], c["p2"], c["d2"], c["mm2"],
                              mc.BOUNDS, mc.CAM4, c["m12"], float(c["s12"]), c["R12"], c["t12"], th)
         assert got[0] == want[0] and np.array_equal(got[1], want[1]) and got[0] > 100
+
+
+def test_device_projection_equals_the_reference_arithmetic(golden, built_lib):
+    """k_kf_project against the numpy model of the reference's cv::Mat statements (itself pinned bit for bit to the queries the reference made, CPU test)
+    and directly against those traced queries"""
+    M = ORBmatcher()
+    for seed, sim3 in ((4, False), (6, True)):
+        c = m2.keyframe_points_inputs(seed=seed, sim3=sim3)
+        pose = kfgeom.pose_from_S(c["T"]) if sim3 else kfgeom.pose_from_T(c["T"])
+        for th in (3.0, 10.0):
+            v, q3, lv = M.project_points(pose, mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], th)
+            wv, wq, wl = m2.host_project_points(pose, mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], th)
+            assert np.array_equal(v, wv) and v.sum() > 500 and (~v).sum() > 50
+            assert np.array_equal(q3[v].view(np.uint32), wq[v].view(np.uint32)) and np.array_equal(lv[v], wl[v])
+    c = m2.sim3_inputs(seed=8)
+    sR12, sR21, t21 = kfgeom.sim3_between(c["s12"], c["R12"], c["t12"])
+    for T, sR, tt, pos, mm in ((c["T1"], sR21, t21, c["p1"], c["mm1"]), (c["T2"], sR12, c["t12"], c["p2"], c["mm2"])):
+        v, q3, lv = M.project_points(kfgeom.pose_from_T(T), mc.CAM4, mc.BOUNDS, pos, None, mm, 7.5, sim3=(sR, tt))
+        wv, wq, wl = m2.host_project_points_sim3(kfgeom.pose_from_T(T), sR, tt, mc.CAM4, mc.BOUNDS, pos, mm, 7.5)
+        assert np.array_equal(v, wv) and v.sum() > 500
+        assert np.array_equal(q3[v].view(np.uint32), wq[v].view(np.uint32)) and np.array_equal(lv[v], wl[v])
+    # the traced queries of the reference's own Fuse
+    g = golden["fuse"]
+    for run in g["runs"]:
+        v, q3, lv = M.project_points(kfgeom.pose_from_T(g["T"]), mc.CAM4, mc.BOUNDS, g["mp_pos"], g["mp_normal"], g["mp_minmax"], float(run["cfg"][0]))
+        qs = np.nonzero(v & (g["mp_state"] == 1))[0]
+        assert np.array_equal(q3[qs].view(np.uint32), A(run["q_xyr"], np.float32).view(np.uint32)) and np.array_equal(lv[qs], run["q_lev"][:, 1])
+    v, q3, lv = M.project_points(kfgeom.pose_from_T(g["T"]), mc.CAM4, mc.BOUNDS, g["mp_pos"][:0], g["mp_normal"][:0], g["mp_minmax"][:0], 3.0)
+    assert len(v) == 0

@@ -1,8 +1,9 @@
 """CPU: the KeyFrame-side matcher members (SearchForTriangulation, Fuse, Fuse(Scw), loop-closing SearchByProjection, SearchBySim3).
  * oracle/match2_oracle.cpp against the reference's OWN src/ORBmatcher.cc: replay of tests/golden/match_ref2.npz (answers of
    oracle/_ref/libref_match.so, written by tests/golden/make_match_golden.py) everywhere, live on full-size cases where oracle/_ref exists;
- * the product's host glue (orb_slam2_aruco_b200/kfgeom.py: projections, PredictScale, search radii) against the grid queries the reference made,
-   bit for bit, and the ORBmatcher mirror's sequential outcome logic with its two device searches swapped for the oracle's."""
+ * the arithmetic of the device projection kernel k_kf_project, as a numpy model (tests/match_cases2.py host_project_points, on the product's per-call
+   glue orb_slam2_aruco_b200/kfgeom.py), against the grid queries the reference made, bit for bit; the PredictScale threshold table against libm;
+ * the ORBmatcher mirror's sequential outcome logic with its device calls swapped for CPU models (a test double, not a product path)."""
 import ctypes as C
 import os
 
@@ -54,26 +55,26 @@ def _same_queries(valid, q3, level, run, suffix=""):
     return qs
 
 
-def test_host_glue_makes_the_reference_s_queries(golden):
+def test_projection_model_makes_the_reference_s_queries(golden):
     c = golden["fuse"]
     for run in c["runs"]:
-        valid, q3, level = kfgeom.project_points(kfgeom.pose_from_T(c["T"]), mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], float(run["cfg"][0]))
+        valid, q3, level = m2.host_project_points(kfgeom.pose_from_T(c["T"]), mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], float(run["cfg"][0]))
         # Fuse skips NULL / bad / already observed points; a point Replace()d earlier in the same call cannot come again (each is listed once)
         assert len(_same_queries(valid & (c["mp_state"] == 1), q3, level, run)) > 300
     c = golden["scw"]
     for run in c["runs"]:
         pose = kfgeom.pose_from_S(c["T"])
-        valid, q3, level = kfgeom.project_points(pose, mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], float(run["cfg"][0]))
+        valid, q3, level = m2.host_project_points(pose, mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], float(run["cfg"][0]))
         _same_queries(valid & (c["mp_state"] != 2) & (c["mp_state"] != 3), q3, level, run)
-        valid, q3, level = kfgeom.project_points(pose, mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], int(run["cfg"][1]))
+        valid, q3, level = m2.host_project_points(pose, mc.CAM4, mc.BOUNDS, c["mp_pos"], c["mp_normal"], c["mp_minmax"], int(run["cfg"][1]))
         found = np.zeros(len(valid), bool); lm = m2.loop_matched(c); found[lm[lm >= 0]] = True
         _same_queries(valid & (c["mp_state"] != 2) & ~found, q3, level, run, "_loop")
     c = golden["sim3"]
     for run in c["runs"]:
         th = float(run["cfg"][0])
         sR12, sR21, t21 = kfgeom.sim3_between(c["s12"], c["R12"], c["t12"])
-        v1, q1, l1 = kfgeom.project_points_sim3(kfgeom.pose_from_T(c["T1"]), sR21, t21, mc.CAM4, mc.BOUNDS, c["p1"], c["mm1"], th)
-        v2, q2, l2 = kfgeom.project_points_sim3(kfgeom.pose_from_T(c["T2"]), sR12, c["t12"], mc.CAM4, mc.BOUNDS, c["p2"], c["mm2"], th)
+        v1, q1, l1 = m2.host_project_points_sim3(kfgeom.pose_from_T(c["T1"]), sR21, t21, mc.CAM4, mc.BOUNDS, c["p1"], c["mm1"], th)
+        v2, q2, l2 = m2.host_project_points_sim3(kfgeom.pose_from_T(c["T2"]), sR12, c["t12"], mc.CAM4, mc.BOUNDS, c["p2"], c["mm2"], th)
         done1 = c["m12"] >= 0
         done2 = np.zeros(len(v2), bool); j = c["m12"][done1]; done2[j[c["st2"][j] > 0]] = True
         a = np.nonzero(v1 & (c["st1"] == 1) & ~done1)[0]; b = np.nonzero(v2 & (c["st2"] == 1) & ~done2)[0]
@@ -92,6 +93,11 @@ class _OracleSearches(api.ORBmatcher):
         oracle.lib().oracle_kf_radius_search(P(k), P(d), len(k), P(A(bounds4, np.float32)), P(q3), P(ql), P(qd), len(q3), C.c_float(scale_factor), nlevels,
                                              C.c_double(chi2), P(bi), P(bd))
         return bi[:len(q3)], bd[:len(q3)]
+
+    def project_points(self, pose, cam4, bounds4, pos, normal, minmax, th, sim3=None, scale_factor=1.2, nlevels=8):
+        if sim3 is None:
+            return m2.host_project_points(pose, cam4, bounds4, pos, normal, minmax, th, scale_factor, nlevels)
+        return m2.host_project_points_sim3(pose, sim3[0], sim3[1], cam4, bounds4, pos, minmax, th, scale_factor, nlevels)
 
     def SearchForTriangulation(self, k1, d1, has1, fv1, T1, k2, d2, has2, fv2, T2, cam4, F12, scale_factor=1.2, nlevels=8):
         # the triangulation entry point is one device call; its host part is the group building and the epipole, checked here against the oracle's
@@ -148,3 +154,19 @@ def test_golden_file_is_current(golden):
     c = golden["sim3"]; run = c["runs"][0]
     n, m12, qx, ql, qm = m2.run_sim3(R, "ref", c, float(run["cfg"][0]))
     assert n == run["n"] and np.array_equal(m12, run["matches12"]) and np.array_equal(qx, run["q_xyr"])
+
+
+def test_predict_scale_thresholds_equal_libm():
+    """level = #(ratio > threshold) is MapPoint::PredictScale evaluated with this host's logf, for every ratio: random ones and the neighbourhoods
+    of the thresholds, where a non-monotone logf would show"""
+    thr = kfgeom.level_thresholds(1.2, 8)
+    log_sf = kfgeom.pyramid(1.2, 8)[3]
+    rng = np.random.default_rng(0)
+    r = np.exp(rng.uniform(-3, 4, 20000)).astype(np.float32)
+    near = np.concatenate([(t.view(np.uint32) + np.arange(-300, 301).astype(np.uint32)).view(np.float32) for t in thr.reshape(-1, 1)])
+    r = np.concatenate([r, near, np.array([0.0, np.inf, np.nan], np.float32)])
+    want = m2.predict_scale(r, np.ones(len(r), np.float32), log_sf, 8)
+    got = (r[:, None] > thr[None, :]).sum(1)
+    ok = np.isfinite(r) & (r > 0)
+    assert np.array_equal(got[ok], want[ok])
+    assert got[-3] == 0 and got[-1] == 0                           # ratio 0 / NaN: level 0 (such points fail the distance tests anyway)
