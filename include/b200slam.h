@@ -201,6 +201,15 @@ int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, 
 int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, const float* sR, const float* tt, const float* cam4, const float* bounds4,
                          const float* pos, const float* normal, const float* minmax, int n, float th, const float* scale_factors,
                          const float* level_thresholds, int nlevels, uint8_t* valid, float* q_xyr, int32_t* level, int device);
+/* Projection and search in ONE call (k_kf_project -> k_features_in_area -> k_radius_best without a host round trip): what Fuse, Fuse(Scw) and each direction
+ * of SearchBySim3 do per map point up to "if(bestDist<=TH_...)".  Arguments as b200_kf_project_host and b200_match_kf_radius_host; q_desc [n][32];
+ * skip [n] (may be NULL): 1 = the reference `continue`s on this point before projecting it (NULL, bad, already in the keyframe / already found).
+ * valid [n] out: the point reached GetFeaturesInArea; best_idx / best_dist [n] out (-1 / 256 for discarded points and empty windows);
+ * q_xyr [n][3] and level [n] out (may be NULL; discarded points report (0, 0, -1)).  HOST pointers. */
+int b200_kf_search_points_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_kf, const float* bounds4, const float* Rcw, const float* tcw, const float* Ow,
+                               const float* sR, const float* tt, const float* cam4, const float* pos, const float* normal, const float* minmax, const uint8_t* q_desc,
+                               const uint8_t* skip, int n, float th, const float* scale_factors, const float* inv_level_sigma2, const float* level_thresholds,
+                               int nlevels, double chi2, uint8_t* valid, int32_t* best_idx, int32_t* best_dist, float* q_xyr, int32_t* level, int device);
 /* Plain 256-bit Hamming distance matrix rows x cols (ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1651-1667). */
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device);
 /* Candidate-list matching core shared by SearchByProjection / SearchForInitialization:

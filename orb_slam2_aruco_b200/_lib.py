@@ -64,6 +64,7 @@ def lib():
         L.b200_match_for_triangulation_host.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, i32]
         L.b200_match_kf_radius_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp, i32, C.c_double, vp, vp, i32]
         L.b200_kf_project_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp, i32, vp, vp, vp, i32]
+        L.b200_kf_search_points_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp, vp, i32, C.c_double, vp, vp, vp, vp, vp, i32]
         L.b200_match_candidates_host.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32]
         L.b200_aruco_create.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32, i32, i32]
         L.b200_aruco_destroy.argtypes = [vp]

@@ -341,6 +341,29 @@ class ORBmatcher:
                                          int(nlevels), ptr(valid), ptr(q3), ptr(level), self._device))
         return valid[:n].astype(bool), q3[:n], level[:n]
 
+    def search_points(self, kps_un, desc, bounds4, pose, cam4, pos, normal, minmax, q_desc, skip, th, chi2=0.0, sim3=None, scale_factor=1.2, nlevels=8):
+        """projection + keyframe search of all points in one device call (b200_kf_search_points_host): what Fuse / Fuse(Scw) / one direction of
+        SearchBySim3 do per point up to `if(bestDist<=TH_...)`.  skip[i]: the reference `continue`s on point i before projecting it.
+        Returns (valid bool [N], best_idx [N], best_dist [N])."""
+        k = np.ascontiguousarray(kps_un); assert k.dtype == KP_DTYPE
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        R, t, Ow = (np.ascontiguousarray(a, np.float32) for a in pose)
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3); mm = np.ascontiguousarray(minmax, np.float32).reshape(-1, 2)
+        nrm = None if normal is None else np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+        sR, tt = (None, None) if sim3 is None else (np.ascontiguousarray(sim3[0], np.float32), np.ascontiguousarray(sim3[1], np.float32))
+        qd = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32); sk = np.ascontiguousarray(skip, np.uint8)
+        cam = np.ascontiguousarray(cam4, np.float32); b = np.ascontiguousarray(bounds4, np.float32)
+        sf, _, inv, _ = kfgeom.pyramid(scale_factor, nlevels)
+        sf = np.ascontiguousarray(sf, np.float32); inv = np.ascontiguousarray(inv, np.float32)
+        thr = np.ascontiguousarray(kfgeom.level_thresholds(float(scale_factor), int(nlevels)), np.float32)
+        n = len(pos)
+        assert len(qd) == n and len(sk) == n and len(mm) == n
+        valid = np.zeros(max(n, 1), np.uint8); bi = np.full(max(n, 1), -1, np.int32); bd = np.full(max(n, 1), 256, np.int32)
+        check(lib().b200_kf_search_points_host(ptr(k), ptr(d), len(k), ptr(b), ptr(R), ptr(t), ptr(Ow), ptr(sR), ptr(tt), ptr(cam), ptr(pos), ptr(nrm), ptr(mm), ptr(qd),
+                                               ptr(sk), n, float(th), ptr(sf), ptr(inv), ptr(thr), int(nlevels), C.c_double(chi2), ptr(valid), ptr(bi), ptr(bd),
+                                               None, None, self._device))
+        return valid[:n].astype(bool), bi[:n], bd[:n]
+
     def kf_radius_search(self, kps_un, desc, bounds4, q_xyr, q_level, q_desc, chi2=0.0, scale_factor=1.2, nlevels=8):
         """best keyframe feature per projected point (b200_match_kf_radius_host) -> (best_idx, best_dist)"""
         k = np.ascontiguousarray(kps_un); assert k.dtype == KP_DTYPE
@@ -379,10 +402,8 @@ class ORBmatcher:
         pMPinKF->Replace(pMP); fused_idx names the keyframe feature, or -3 - o when pMPinKF is point o of this call that was added earlier."""
         st = np.asarray(mp_state, np.uint8); nobs = np.asarray(mp_nobs, np.int32).copy()
         hs = np.asarray(held_state, np.uint8); hn = np.asarray(held_nobs, np.int32)
-        valid, q3, level = self.project_points(kfgeom.pose_from_T(Tcw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
-        valid &= (st == 1)
-        qs = np.nonzero(valid)[0]
-        bi, bd = self.kf_radius_search(kps_un, desc, bounds4, q3[qs], level[qs], np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs], chi2=5.99)
+        valid, bi, bd = self.search_points(kps_un, desc, bounds4, kfgeom.pose_from_T(Tcw), cam4, mp_pos, mp_normal, mp_minmax, mp_desc, st != 1, th, chi2=5.99)
+        qs = np.nonzero(valid)[0]; bi, bd = bi[qs], bd[qs]
         # the outcome, applied in list order exactly as the reference does on its objects (ORBmatcher.cc:957-976)
         holder = np.where(hs > 0, -2, -1).astype(np.int64); own_bad = hs == 2
         bad = st == 2
@@ -415,10 +436,8 @@ class ORBmatcher:
         replace_idx[m] = keyframe feature whose point vpReplacePoint[m] names (-3 - o: point o added earlier in this call), added_idx[m] = feature the
         point became an observation of."""
         st = np.asarray(mp_state, np.uint8); hs = np.asarray(held_state, np.uint8)
-        valid, q3, level = self.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, th)
-        valid &= (st != 2) & (st != 3)
-        qs = np.nonzero(valid)[0]
-        bi, bd = self.kf_radius_search(kps_un, desc, bounds4, q3[qs], level[qs], np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs])
+        valid, bi, bd = self.search_points(kps_un, desc, bounds4, kfgeom.pose_from_S(Scw), cam4, mp_pos, mp_normal, mp_minmax, mp_desc, (st == 2) | (st == 3), th)
+        qs = np.nonzero(valid)[0]; bi, bd = bi[qs], bd[qs]
         holder = np.where(hs > 0, -2, -1).astype(np.int64)
         rep = np.full(len(st), -1, np.int32); add = np.full(len(st), -1, np.int32)
         nf = 0
@@ -464,12 +483,12 @@ class ORBmatcher:
         done2 = np.zeros(n2, bool)
         j = m12[done1]; done2[j[st2[j] > 0]] = True                  # GetIndexInKeyFrame(pKF2) >= 0 only when that KF2 feature holds the point
         sR12, sR21, t21 = kfgeom.sim3_between(s12, R12, t12)
-        v1, q1, l1 = self.project_points(kfgeom.pose_from_T(T1), cam4, bounds4, mp1_pos, None, mp1_minmax, th, sim3=(sR21, t21))
-        v2, q2, l2 = self.project_points(kfgeom.pose_from_T(T2), cam4, bounds4, mp2_pos, None, mp2_minmax, th, sim3=(sR12, np.asarray(t12, np.float32).reshape(3)))
-        v1 &= (st1 == 1) & ~done1; v2 &= (st2 == 1) & ~done2
+        v1, bi1, bd1 = self.search_points(kps2_un, desc2, bounds4, kfgeom.pose_from_T(T1), cam4, mp1_pos, None, mp1_minmax, mp1_desc, (st1 != 1) | done1, th,
+                                          sim3=(sR21, t21))
+        v2, bi2, bd2 = self.search_points(kps1_un, desc1, bounds4, kfgeom.pose_from_T(T2), cam4, mp2_pos, None, mp2_minmax, mp2_desc, (st2 != 1) | done2, th,
+                                          sim3=(sR12, np.asarray(t12, np.float32).reshape(3)))
         a, b = np.nonzero(v1)[0], np.nonzero(v2)[0]
-        bi1, bd1 = self.kf_radius_search(kps2_un, desc2, bounds4, q1[a], l1[a], np.asarray(mp1_desc, np.uint8).reshape(-1, 32)[a])
-        bi2, bd2 = self.kf_radius_search(kps1_un, desc1, bounds4, q2[b], l2[b], np.asarray(mp2_desc, np.uint8).reshape(-1, 32)[b])
+        bi1, bd1, bi2, bd2 = bi1[a], bd1[a], bi2[b], bd2[b]
         vn1 = np.full(n1, -1, np.int64); vn2 = np.full(n2, -1, np.int64)
         ok = (bi1 >= 0) & (bd1 <= self.TH_HIGH); vn1[a[ok]] = bi1[ok]
         ok = (bi2 >= 0) & (bd2 <= self.TH_HIGH); vn2[b[ok]] = bi2[ok]

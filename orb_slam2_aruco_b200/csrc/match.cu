@@ -750,7 +750,8 @@ __device__ __forceinline__ double dot3_d(float a0, float a1, float a2, float b0,
 
 __global__ void __launch_bounds__(256)
 k_kf_project(const float* __restrict__ pos, const float* __restrict__ normal, const float* __restrict__ minmax, int n, const ProjGeom g,
-             unsigned char* __restrict__ valid, float* __restrict__ q3, int* __restrict__ level) {
+             unsigned char* __restrict__ valid, float* __restrict__ q3, int* __restrict__ level,
+             const unsigned char* __restrict__ skip = nullptr, int* __restrict__ lv2 = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float X = pos[3 * i], Y = pos[3 * i + 1], Z = pos[3 * i + 2];
@@ -775,9 +776,14 @@ k_kf_project(const float* __restrict__ pos, const float* __restrict__ normal, co
     const float ratio = __fdiv_rn(minmax[2 * i + 1], dist);
     int lv = 0;
     for (int k = 0; k < g.nlevels - 1; k++) lv += ratio > g.thr[k];
+    if (skip && skip[i]) ok = false;                              // the reference `continue`s on this point before projecting (NULL, bad, already found ...)
     valid[i] = ok ? 1 : 0;
-    q3[3 * i] = u; q3[3 * i + 1] = v; q3[3 * i + 2] = __fmul_rn(g.th, g.sf[lv]);
     level[i] = lv;
+    if (lv2) {
+        // feeding k_features_in_area directly: the level window of the callers' filter, and an empty window (radius < 0) for discarded points
+        lv2[2 * i] = lv - 1; lv2[2 * i + 1] = lv;
+        q3[3 * i] = ok ? u : 0.0f; q3[3 * i + 1] = ok ? v : 0.0f; q3[3 * i + 2] = ok ? __fmul_rn(g.th, g.sf[lv]) : -1.0f;
+    } else { q3[3 * i] = u; q3[3 * i + 1] = v; q3[3 * i + 2] = __fmul_rn(g.th, g.sf[lv]); }
 }
 
 struct MatchScratch { uint32_t* topk; size_t cap; int device; };
@@ -1174,17 +1180,9 @@ int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, 
     return B200_OK;
 }
 
-int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, const float* sR, const float* tt, const float* cam4, const float* bounds4,
-                         const float* pos, const float* normal, const float* minmax, int n, float th, const float* scale_factors,
-                         const float* level_thresholds, int nlevels, uint8_t* valid, float* q_xyr, int32_t* level, int device) {
-    if (n < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
-    int rc = use_device(device);
-    if (rc) return rc;
-    if (n == 0) return B200_OK;
-    if (!Rcw || !tcw || !cam4 || !bounds4 || !pos || !minmax || !scale_factors || (nlevels > 1 && !level_thresholds) || !valid || !q_xyr || !level ||
-        (!sR && !Ow) || (sR && !tt))
-        return fail(B200_EINVAL, "null %s", "pointer");
-    ProjGeom g;
+static int fill_proj_geom(ProjGeom& g, const float* Rcw, const float* tcw, const float* Ow, const float* sR, const float* tt, const float* cam4, const float* bounds4,
+                          const float* normal, float th, const float* scale_factors, const float* level_thresholds, int nlevels) {
+    if (!Rcw || !tcw || !cam4 || !bounds4 || !scale_factors || (nlevels > 1 && !level_thresholds) || (!sR && !Ow) || (sR && !tt)) return fail(B200_EINVAL, "null %s", "pointer");
     memset(&g, 0, sizeof(g));
     for (int i = 0; i < 9; i++) { g.R[i] = Rcw[i]; if (sR) g.sR[i] = sR[i]; }
     for (int i = 0; i < 3; i++) { g.t[i] = tcw[i]; if (Ow) g.Ow[i] = Ow[i]; if (sR) g.tt[i] = tt[i]; }
@@ -1193,6 +1191,67 @@ int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, co
     g.th = th; g.nlevels = nlevels; g.sim3 = sR ? 1 : 0; g.has_normal = normal ? 1 : 0;
     for (int i = 0; i < nlevels; i++) g.sf[i] = scale_factors[i];
     for (int i = 0; i + 1 < nlevels; i++) g.thr[i] = level_thresholds[i];
+    return B200_OK;
+}
+
+int b200_kf_search_points_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_kf, const float* bounds4, const float* Rcw, const float* tcw, const float* Ow,
+                               const float* sR, const float* tt, const float* cam4, const float* pos, const float* normal, const float* minmax, const uint8_t* q_desc,
+                               const uint8_t* skip, int n, float th, const float* scale_factors, const float* inv_level_sigma2, const float* level_thresholds,
+                               int nlevels, double chi2, uint8_t* valid, int32_t* best_idx, int32_t* best_dist, float* q_xyr, int32_t* level, int device) {
+    if (n < 0 || n_kf < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n == 0) return B200_OK;
+    if (!pos || !minmax || !q_desc || !valid || !best_idx || !best_dist || (n_kf > 0 && (!kps_un || !desc)) || (chi2 > 0 && !inv_level_sigma2))
+        return fail(B200_EINVAL, "null %s", "pointer");
+    ProjGeom g;
+    if ((rc = fill_proj_geom(g, Rcw, tcw, Ow, sR, tt, cam4, bounds4, normal, th, scale_factors, level_thresholds, nlevels))) return rc;
+    LevelTable lt;
+    for (int i = 0; i < 16; i++) lt.inv_sigma2[i] = inv_level_sigma2 ? inv_level_sigma2[std::min(i, nlevels - 1)] : 1.0f;
+    const int row_cap = std::max(1, std::min(n_kf, 4096));
+    DevBuf dp, dn, dm, dsk, dv, dq, dl, dl2, k2, d2, ncnt, cs, ci, qd, cand, cnt, bi, bd, ovf;
+    if ((rc = dp.upload(pos, (size_t)n * 12)) || (normal && (rc = dn.upload(normal, (size_t)n * 12))) || (rc = dm.upload(minmax, (size_t)n * 8)) ||
+        (skip && (rc = dsk.upload(skip, (size_t)n))) || (rc = dv.alloc((size_t)n)) || (rc = dq.alloc((size_t)n * 12)) || (rc = dl.alloc((size_t)n * 4)) ||
+        (rc = dl2.alloc((size_t)n * 8)) || (rc = qd.upload(q_desc, (size_t)n * 32)) || (rc = bi.alloc((size_t)n * 4)) || (rc = bd.alloc((size_t)n * 4)) || (rc = ovf.alloc(4)))
+        return rc;
+    B200_LAUNCH(k_kf_project, (n + 255) / 256, 256, 0, 0, (const float*)dp.p, (const float*)dn.p, (const float*)dm.p, n, g, (unsigned char*)dv.p, (float*)dq.p, (int*)dl.p,
+                (const unsigned char*)dsk.p, (int*)dl2.p);
+    if (n_kf > 0) {
+        if ((rc = k2.upload(kps_un, (size_t)n_kf * sizeof(b200_keypoint))) || (rc = d2.upload(desc, (size_t)n_kf * 32)) || (rc = ncnt.upload(&n_kf, 4)) ||
+            (rc = cs.alloc((size_t)(64 * 48 + 1) * 4)) || (rc = ci.alloc((size_t)n_kf * 4)) || (rc = cand.alloc((size_t)n * row_cap * 4)) || (rc = cnt.alloc((size_t)n * 4)))
+            return rc;
+        B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, 0));
+        if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
+        if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)dq.p,
+                                              (const int32_t*)dl2.p, n, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+            return rc;
+        B200_LAUNCH(k_radius_best, (n * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)dq.p, (const ulonglong4*)qd.p,
+                    (const int*)cand.p, (const int*)cnt.p, row_cap, n, lt, chi2, (int*)bi.p, (int*)bd.p, (int*)ovf.p);
+    }
+    B200_CUDA(cudaDeviceSynchronize());
+    if (n_kf > 0) {
+        int o = 0;
+        B200_CUDA(cudaMemcpy(&o, ovf.p, 4, cudaMemcpyDeviceToHost));
+        if (o) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
+        B200_CUDA(cudaMemcpy(best_idx, bi.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        B200_CUDA(cudaMemcpy(best_dist, bd.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    } else for (int i = 0; i < n; i++) { best_idx[i] = -1; best_dist[i] = 256; }
+    B200_CUDA(cudaMemcpy(valid, dv.p, (size_t)n, cudaMemcpyDeviceToHost));
+    if (q_xyr) B200_CUDA(cudaMemcpy(q_xyr, dq.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    if (level) B200_CUDA(cudaMemcpy(level, dl.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, const float* sR, const float* tt, const float* cam4, const float* bounds4,
+                         const float* pos, const float* normal, const float* minmax, int n, float th, const float* scale_factors,
+                         const float* level_thresholds, int nlevels, uint8_t* valid, float* q_xyr, int32_t* level, int device) {
+    if (n < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (n == 0) return B200_OK;
+    if (!pos || !minmax || !valid || !q_xyr || !level) return fail(B200_EINVAL, "null %s", "pointer");
+    ProjGeom g;
+    if ((rc = fill_proj_geom(g, Rcw, tcw, Ow, sR, tt, cam4, bounds4, normal, th, scale_factors, level_thresholds, nlevels))) return rc;
     DevBuf dp, dn, dm, dv, dq, dl;
     if ((rc = dp.upload(pos, (size_t)n * 12)) || (normal && (rc = dn.upload(normal, (size_t)n * 12))) || (rc = dm.upload(minmax, (size_t)n * 8)) ||
         (rc = dv.alloc((size_t)n)) || (rc = dq.alloc((size_t)n * 12)) || (rc = dl.alloc((size_t)n * 4)))

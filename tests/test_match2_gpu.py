@@ -115,3 +115,20 @@ def test_device_projection_equals_the_reference_arithmetic(golden, built_lib):
         assert np.array_equal(q3[qs].view(np.uint32), A(run["q_xyr"], np.float32).view(np.uint32)) and np.array_equal(lv[qs], run["q_lev"][:, 1])
     v, q3, lv = M.project_points(kfgeom.pose_from_T(g["T"]), mc.CAM4, mc.BOUNDS, g["mp_pos"][:0], g["mp_normal"][:0], g["mp_minmax"][:0], 3.0)
     assert len(v) == 0
+
+
+def test_fused_projection_and_search_equals_the_two_steps(built_lib):
+    M = ORBmatcher()
+    c = m2.keyframe_points_inputs(seed=4)
+    pose = kfgeom.pose_from_T(c["T"])
+    skip = c["mp_state"] != 1
+    for chi2, nrm in ((5.99, c["mp_normal"]), (0.0, None)):
+        v, q3, lv = M.project_points(pose, mc.CAM4, mc.BOUNDS, c["mp_pos"], nrm, c["mp_minmax"], 3.0)
+        v &= ~skip
+        qs = np.nonzero(v)[0]
+        wi, wd = M.kf_radius_search(c["k"], c["d"], mc.BOUNDS, q3[qs], lv[qs], c["mp_desc"][qs], chi2=chi2)
+        fv, bi, bd = M.search_points(c["k"], c["d"], mc.BOUNDS, pose, mc.CAM4, c["mp_pos"], nrm, c["mp_minmax"], c["mp_desc"], skip, 3.0, chi2=chi2)
+        assert np.array_equal(fv, v) and np.array_equal(bi[qs], wi) and np.array_equal(bd[qs], wd) and (wi >= 0).sum() > 200
+        assert (bi[~v] == -1).all() and (bd[~v] == 256).all()
+    fv, bi, bd = M.search_points(c["k"][:0], c["d"][:0], mc.BOUNDS, pose, mc.CAM4, c["mp_pos"], None, c["mp_minmax"], c["mp_desc"], skip, 3.0)
+    assert (bi == -1).all() and fv.sum() > 300

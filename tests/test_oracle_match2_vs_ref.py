@@ -99,6 +99,14 @@ class _OracleSearches(api.ORBmatcher):
             return m2.host_project_points(pose, cam4, bounds4, pos, normal, minmax, th, scale_factor, nlevels)
         return m2.host_project_points_sim3(pose, sim3[0], sim3[1], cam4, bounds4, pos, minmax, th, scale_factor, nlevels)
 
+    def search_points(self, kps_un, desc, bounds4, pose, cam4, pos, normal, minmax, q_desc, skip, th, chi2=0.0, sim3=None, scale_factor=1.2, nlevels=8):
+        valid, q3, level = self.project_points(pose, cam4, bounds4, pos, normal, minmax, th, sim3, scale_factor, nlevels)
+        valid = valid & ~np.asarray(skip, bool)
+        qs = np.nonzero(valid)[0]
+        bi = np.full(len(valid), -1, np.int32); bd = np.full(len(valid), 256, np.int32)
+        bi[qs], bd[qs] = self.kf_radius_search(kps_un, desc, bounds4, q3[qs], level[qs], A(q_desc, np.uint8)[qs], chi2, scale_factor, nlevels)
+        return valid, bi, bd
+
     def SearchForTriangulation(self, k1, d1, has1, fv1, T1, k2, d2, has2, fv2, T2, cam4, F12, scale_factor=1.2, nlevels=8):
         # the triangulation entry point is one device call; its host part is the group building and the epipole, checked here against the oracle's
         gq, qi, gc, ci = self.common_node_groups(fv1, ~np.asarray(has1, bool), fv2, ~np.asarray(has2, bool))
