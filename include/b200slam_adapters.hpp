@@ -355,6 +355,55 @@ public:
         bestDist.assign(bd.begin(), bd.begin() + nq);
     }
 
+    // MapPoint::PredictScale (MapPoint.cc:403-435) as a threshold table for the device projection: thresholds[n] = the largest float ratio
+    // mfMaxDistance / dist that still yields a level <= n with THIS host's std::log(float), by bisection over float bit patterns.
+    static std::vector<float> PredictScaleThresholds(float scaleFactor, int nlevels) {
+        const float logSf = std::log(scaleFactor);
+        std::vector<float> thr(nlevels > 1 ? nlevels - 1 : 0);
+        for (int n = 0; n + 1 < nlevels; n++) {
+            uint32_t lo = 0x00800000u, hi = 0x7f000000u;
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                float r; std::memcpy(&r, &mid, 4);
+                if ((int)std::ceil(std::log(r) / logSf) <= n) lo = mid; else hi = mid;
+            }
+            std::memcpy(&thr[n], &lo, 4);
+        }
+        return thr;
+    }
+
+    // Projection + search of a whole map point list in one device call (b200_kf_search_points_host): the loop bodies of Fuse (ORBmatcher.cc:846-955),
+    // Fuse(Scw) (:1004-1082) and of each direction of SearchBySim3 (:1151-1217, :1231-1297) up to "if(bestDist<=TH_...)", evaluated with the
+    // reference's cv::Mat CV_32F roundings.  R / t / Ow: rotation (row-major), translation and centre of the keyframe camera (for Scw the
+    // decomposed Sim3, :302-307); sR / tt: NULL, or SearchBySim3's second transform (then Ow and the normals are unused).  skip: the reference
+    // `continue`s on the point before projecting it.  Afterwards the caller runs the reference's outcome statements over (valid, bestIdx, bestDist)
+    // in list order.  mfMinDistance / mfMaxDistance are the MapPoint members behind Get{Min,Max}DistanceInvariance() (MapPoint.cc:391-401).
+    struct MapPointView { float pos[3]; float normal[3]; float minDistance, maxDistance; const unsigned char* descriptor; bool skip; };
+    void SearchPoints(const std::vector<cv::KeyPoint>& keysUn, const cv::Mat& descriptors, const float bounds[4], const float R[9], const float t[3], const float Ow[3],
+                      const float* sR, const float* tt, const float cam4[4], const std::vector<MapPointView>& points, bool useNormals, float th,
+                      const std::vector<float>& scaleFactors, const std::vector<float>& invLevelSigma2, double chi2,
+                      std::vector<bool>& valid, std::vector<int>& bestIdx, std::vector<int>& bestDist) {
+        const int n = (int)keysUn.size(), np = (int)points.size(), nl = (int)scaleFactors.size();
+        std::vector<uint8_t> d((size_t)n * 32), qd((size_t)np * 32), sk(np), v((size_t)np + 1, 0);
+        for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], descriptors.ptr(i), 32);
+        std::vector<float> pos((size_t)np * 3), nrm((size_t)np * 3), mm((size_t)np * 2);
+        for (int i = 0; i < np; i++) {
+            for (int j = 0; j < 3; j++) { pos[3 * i + j] = points[i].pos[j]; nrm[3 * i + j] = points[i].normal[j]; }
+            mm[2 * i] = points[i].minDistance; mm[2 * i + 1] = points[i].maxDistance; sk[i] = points[i].skip ? 1 : 0;
+            std::memcpy(&qd[(size_t)i * 32], points[i].descriptor, 32);
+        }
+        const std::vector<float> thr = PredictScaleThresholds(nl > 1 ? scaleFactors[1] : 1.2f, nl);
+        std::vector<int32_t> bi((size_t)np + 1, -1), bd((size_t)np + 1, 256);
+        static_assert(sizeof(cv::KeyPoint) == sizeof(b200_keypoint), "cv::KeyPoint layout");
+        b200slam_detail::check(b200_kf_search_points_host((const b200_keypoint*)keysUn.data(), d.data(), n, bounds, R, t, Ow, sR, tt, cam4, pos.data(),
+                                                          useNormals ? nrm.data() : nullptr, mm.data(), qd.data(), sk.data(), np, th, scaleFactors.data(),
+                                                          invLevelSigma2.data(), thr.data(), nl, chi2, v.data(), bi.data(), bd.data(), nullptr, nullptr, device_));
+        valid.assign(np, false);
+        for (int i = 0; i < np; i++) valid[i] = v[i] != 0;
+        bestIdx.assign(bi.begin(), bi.begin() + np);
+        bestDist.assign(bd.begin(), bd.begin() + np);
+    }
+
     // int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th)
     // (ORBmatcher.h:52, ORBmatcher.cc:294-407) on projected points: here a matched feature hides itself from every later point, so the queries are
     // replayed in order by the projection resolve kernel.  matchedBefore[i] = "vpMatched[i] != NULL"; assign[i] = index into `queries` newly

@@ -3,6 +3,7 @@
 // flat binary result that tests/test_adapters_gpu.py compares with the oracle.
 #define B200SLAM_NO_OPENCV
 #include "b200slam_adapters.hpp"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -64,6 +65,30 @@ int main(int argc, char** argv) {
             const int nl = matcher.SearchByProjectionLoop(keys, desc, bounds, std::vector<bool>(keys.size(), false), qs, assign);      // ORBmatcher.cc:294-407
             if (nl != (int)keys.size()) { fprintf(stderr, "SearchByProjectionLoop: %d of %zu\n", nl, keys.size()); return 1; }
             for (size_t i = 0; i < keys.size(); i++) if (assign[i] != (int)i) { fprintf(stderr, "SearchByProjectionLoop: feature %zu -> %d\n", i, assign[i]); return 1; }
+            // Fuse's loop body in one call (ORBmatcher.cc:846-955): every keypoint back-projected to depth 4 under the identity pose, with
+            // mfMaxDistance chosen so that PredictScale answers the keypoint's own level, must come back to its own feature
+            {
+                const float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0}, Ow[3] = {0, 0, 0}, cam4[4] = {517.3f, 516.5f, 318.6f, 255.3f};
+                std::vector<ORB_SLAM2::ORBmatcher::MapPointView> pts(keys.size());
+                for (size_t i = 0; i < keys.size(); i++) {
+                    ORB_SLAM2::ORBmatcher::MapPointView& p = pts[i];
+                    p.pos[0] = (keys[i].pt.x - cam4[2]) / cam4[0] * 4.f; p.pos[1] = (keys[i].pt.y - cam4[3]) / cam4[1] * 4.f; p.pos[2] = 4.f;
+                    const float dist = std::sqrt(p.pos[0] * p.pos[0] + p.pos[1] * p.pos[1] + p.pos[2] * p.pos[2]);
+                    p.normal[0] = 0.f; p.normal[1] = 0.f; p.normal[2] = 1.f;
+                    p.maxDistance = dist * std::pow(1.2f, (float)keys[i].octave - 0.5f); p.minDistance = 0.01f;
+                    p.descriptor = desc.ptr((int)i); p.skip = (i % 7) == 3;
+                }
+                std::vector<bool> valid; std::vector<int> bi2, bd2;
+                matcher.SearchPoints(keys, desc, bounds, R, t, Ow, nullptr, nullptr, cam4, pts, true, 3.0f, sf, is2, 5.99, valid, bi2, bd2);
+                for (size_t i = 0; i < keys.size(); i++) {
+                    const bool skipped = (i % 7) == 3;
+                    if (valid[i] == skipped || (!skipped && (bi2[i] != (int)i || bd2[i] != 0)) || (skipped && bi2[i] != -1)) {
+                        fprintf(stderr, "SearchPoints: point %zu valid %d -> %d (dist %d)\n", i, (int)valid[i], bi2[i], bd2[i]); return 1;
+                    }
+                }
+                const std::vector<float> thr = ORB_SLAM2::ORBmatcher::PredictScaleThresholds(1.2f, 8);
+                if (thr.size() != 7 || thr[0] != 1.0f || !(thr[1] > 1.19f && thr[1] < 1.21f)) { fprintf(stderr, "PredictScaleThresholds\n"); return 1; }
+            }
             // F12 of a pure image shift s = (5, 3): the epipolar line of x1 is the line through x1 along s, which contains x2 = x1
             const float F12[9] = {0.f, 0.f, 0.03f, 0.f, 0.f, -0.05f, -0.03f, 0.05f, 0.f};
             std::vector<std::pair<size_t, size_t> > pairs;
