@@ -73,6 +73,38 @@ def ref_match():
     return _ref_match
 
 
+_ref_dict = None
+
+
+def ref_dict():
+    """The reference's own dictionary.cpp / dictionary_based.cpp / markerlabeler.cpp on oracle/arucoshim (oracle/ref_dict_wrap.cpp), or None when never built."""
+    global _ref_dict
+    if _ref_dict is None:
+        path = os.path.join(HERE, "_ref", "libref_dict.so")
+        if not os.path.exists(path):
+            return None
+        _ref_dict = C.CDLL(path)
+    return _ref_dict
+
+
+def decode_patch(patch, dict_name="ARUCO_MIP_25h7", impl=None):
+    """decode stage on one canonical patch -> (ok, id, nrot); impl = ref_dict() for the reference's own code, default the oracle restatement"""
+    patch = np.ascontiguousarray(patch, np.uint8)
+    i = C.c_int32(-1); r = C.c_int32(-1)
+    f = lib().oracle_aruco_decode_patch if impl is None else impl.ref_dictionary_detect
+    ok = f(_p(patch), patch.shape[0], dict_name.encode(), C.byref(i), C.byref(r))
+    return (1, i.value, r.value) if ok == 1 else (0, -1, -1)
+
+
+def dictionary_codes(dict_name, impl=None):
+    """(nbits, tau, codes by id) of a dictionary from the oracle / product table or (impl = ref_dict()) from the reference's dictionary.cpp"""
+    codes = np.zeros(8192, np.uint64); nb = C.c_int32(); tau = C.c_int32()
+    f = lib().oracle_dictionary_codes if impl is None else impl.ref_dictionary_codes
+    n = f(dict_name.encode(), _p(codes), len(codes), C.byref(nb), C.byref(tau))
+    assert 0 <= n <= len(codes), n
+    return nb.value, tau.value, codes[:n].copy()
+
+
 # ---- primitives -------------------------------------------------------------------------------
 def resize_linear(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)

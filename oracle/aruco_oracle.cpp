@@ -345,6 +345,27 @@ int oracle_aruco_stages(const uint8_t* img, int w, int h, int stride, const char
     return n;
 }
 
+// the decode stage alone (DictionaryBased::detect, dictionary_based.cpp:1062-2509): one size x size canonical patch -> 1 and (id, nRotations), or 0.
+// Pinned against the reference's own dictionary_based.cpp / dictionary.cpp (oracle/_ref/libref_dict.so, tests/test_oracle_dict_vs_ref.py).
+int oracle_aruco_decode_patch(const uint8_t* patch, int size, const char* dict_name, int32_t* id, int32_t* nrot) {
+    const Dict* d = find_dict(dict_name);
+    if (!d) return -2;
+    std::vector<u8> p(patch, patch + (size_t)size * size);
+    int i = -1, r = -1;
+    const bool ok = decode_patch(p, size, *d, i, r);
+    *id = ok ? i : -1; *nrot = ok ? r : -1;
+    return ok ? 1 : 0;
+}
+// the code table of a dictionary as the oracle and the product hold it (both include csrc/aruco_dicts.inc): codes [cap] by id; returns the highest id + 1
+int oracle_dictionary_codes(const char* dict_name, uint64_t* codes, int cap, int32_t* nbits, int32_t* tau) {
+    const Dict* d = find_dict(dict_name);
+    if (!d) return -2;
+    *nbits = d->nbits; *tau = d->tau;
+    int n = 0;                                                    // ids run to the length of the list; an id whose code repeats an earlier one stays 0
+    for (auto& kv : d->code_id) { if (kv.second < cap) codes[kv.second] = kv.first; if (kv.second + 1 > n) n = kv.second + 1; }
+    return n;
+}
+
 // ---- primitive taps for the golden tests -------------------------------------------------------
 void oracle_adaptive_threshold(const uint8_t* src, int w, int h, uint8_t* dst, int bs, int C) { adaptive_threshold_mean_inv(src, w, h, w, dst, w, bs, C); }
 int oracle_find_contours(const uint8_t* img, int w, int h, int32_t* sizes, int32_t* pts, int max_contours, int max_points) {

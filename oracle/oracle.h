@@ -61,6 +61,8 @@ int oracle_aruco_stages(const uint8_t* img, int w, int h, int stride, const char
                         uint8_t* thres, int32_t* contour_sizes, int32_t* contour_pts, int max_contours, int max_points, int32_t* n_contours,
                         float* candidates, uint8_t* patches, int max_cand, int32_t* n_cand,
                         float* prerefine, oracle_marker* out, int cap);
+int oracle_aruco_decode_patch(const uint8_t* patch, int size, const char* dict_name, int32_t* id, int32_t* nrot);
+int oracle_dictionary_codes(const char* dict_name, uint64_t* codes, int cap, int32_t* nbits, int32_t* tau);
 void oracle_adaptive_threshold(const uint8_t* src, int w, int h, uint8_t* dst, int bs, int C);
 int oracle_find_contours(const uint8_t* img, int w, int h, int32_t* sizes, int32_t* pts, int max_contours, int max_points);
 int oracle_approx_poly(const int32_t* pts, int n, double eps, int32_t* out, int* convex);
