@@ -73,6 +73,27 @@ def ref_match():
     return _ref_match
 
 
+_ref_voc = None
+
+
+def ref_voc():
+    """The reference's own vendored DBoW2 on oracle/vocshim (oracle/ref_voc_wrap.cpp), or None when it was never built."""
+    global _ref_voc
+    if _ref_voc is None:
+        path = os.path.join(HERE, "_ref", "libref_voc.so")
+        if not os.path.exists(path):
+            return None
+        _ref_voc = C.CDLL(path)
+        _ref_voc.ref_voc_load.restype = C.c_void_p
+        _ref_voc.ref_voc_load.argtypes = [C.c_char_p]
+        _ref_voc.ref_voc_free.argtypes = [C.c_void_p]
+        _ref_voc.ref_voc_size.argtypes = [C.c_void_p]
+        _ref_voc.ref_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        _ref_voc.ref_voc_score.restype = C.c_double
+        _ref_voc.ref_voc_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return _ref_voc
+
+
 _ref_dict = None
 
 

@@ -48,6 +48,10 @@ public:
         buf.reset(new std::vector<uchar>((size_t)r * step, 0));
         data = buf->data();
     }
+    // create / release / zeros: used by the vendored DBoW2 (FORB.cpp), which shares this stand-in through oracle/vocshim
+    void create(int r, int c, int t) { if (!(data && r == rows && c == cols && t == tp)) alloc(r, c, t); }
+    void release() { rows = cols = 0; step = 0; data = 0; buf.reset(); }
+    static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
     int type() const { return tp; }
     bool empty() const { return data == 0 || rows * cols == 0; }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
