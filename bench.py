@@ -183,8 +183,16 @@ def cpu_reference_run(imgs, wl, nthreads, ref_set=None):
         cap = kps28.shape[1]
         kind, what = "port", "extractor = oracle port"
     if wl["markers"]:
-        oracle.aruco_detect_batch(imgs, DICT, nthreads=nthreads)
-        what += "; detector = oracle restatement"
+        ra_lib = oracle.ref_aruco()
+        if ra_lib is not None:
+            mk = np.zeros((n, 256), oracle.MARKER_DTYPE); mc = np.zeros(n, np.int32)
+            ra_lib.ref_aruco_detect_batch(imgs.ctypes.data_as(vp), n, w, h, w, C.c_long(w * h), DICT.encode(), mk.ctypes.data_as(vp), mc.ctypes.data_as(vp),
+                                          256, nthreads)
+            what += "; detector = reference Thirdparty/aruco markerdetector_impl.cpp & co. on the cv shim (oracle/_ref)"
+        else:
+            oracle.aruco_detect_batch(imgs, DICT, nthreads=nthreads)
+            what += "; detector = oracle restatement"
+            kind = "port"
     if wl["match"] and ref_set is not None:
         rd, ra = ref_set
         m = np.zeros((n, cap), np.int32); nm = np.zeros(n, np.int32)

@@ -73,6 +73,28 @@ def ref_match():
     return _ref_match
 
 
+_ref_aruco = None
+
+
+def ref_aruco():
+    """The reference's own marker detector (markerdetector_impl.cpp & co. on oracle/arucoshim, oracle/ref_aruco_wrap.cpp), or None when never built."""
+    global _ref_aruco
+    if _ref_aruco is None:
+        path = os.path.join(HERE, "_ref", "libref_aruco.so")
+        if not os.path.exists(path):
+            return None
+        _ref_aruco = C.CDLL(path)
+    return _ref_aruco
+
+
+def ref_aruco_detect(img, dict_name="ARUCO_MIP_25h7", cap=256):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros(cap, MARKER_DTYPE)
+    n = ref_aruco().ref_aruco_detect(_p(img), img.shape[1], img.shape[0], img.shape[1], dict_name.encode(), _p(out), cap)
+    assert 0 <= n <= cap
+    return out[:n].copy()
+
+
 _ref_voc = None
 
 

@@ -1,0 +1,77 @@
+// oracle/ref_aruco_wrap.cpp -- TEST INFRASTRUCTURE.  C entry point around the reference's OWN marker detector: Thirdparty/aruco/aruco/markerdetector.cpp,
+// markerdetector_impl.cpp (the whole MarkerDetector_Impl::detect: pyramid, adaptive threshold, contours, quad test, candidate filter, warp, identification,
+// de-duplication, CORNER_LINES refinement), marker.cpp, markerlabeler.cpp, dictionary.cpp, dictionary_based.cpp and debug.cpp, compiled unmodified from
+// /root/reference against oracle/arucoshim into oracle/_ref/libref_aruco.so (oracle/Makefile).  The control flow is the reference's, statement for
+// statement; the OpenCV primitives it calls (adaptiveThreshold, findContours, approxPolyDP, isContourConvex, resize, getPerspectiveTransform,
+// warpPerspective, threshold, solve) are the cv2-pinned restatements of oracle/cvprim_aruco.h.  Configured exactly as src/Frame.cc:133-139 does.
+// Pins oracle/aruco_oracle.cpp (tests/test_oracle_aruco_vs_ref.py, tests/golden/aruco_ref.npz).
+// cameraparameters.cpp and ippe.cpp (pose algebra: Rodrigues, inv, SVD) are not compiled: detect() runs without camera parameters here, as the pose is a
+// separate row of the scope table (oracle/ippe_oracle.cpp, pinned to cv2's IPPE); the few members the linked sources name are defined below.
+#include <atomic>
+#include <thread>
+#include "cameraparameters.h"
+#include "ippe.h"
+#include "markerdetector.h"
+#include "markermap.h"
+#include "../oracle.h"
+
+namespace aruco {
+CameraParameters::CameraParameters() {}
+CameraParameters::CameraParameters(const CameraParameters& CI) : CameraMatrix(CI.CameraMatrix), Distorsion(CI.Distorsion), CamSize(CI.CamSize) {}
+void CameraParameters::resize(cv::Size) { throw std::runtime_error("CameraParameters::resize is not part of the stand-in (detect runs without camera parameters)"); }
+void solvePnP(const std::vector<cv::Point3f>&, const std::vector<cv::Point2f>&, cv::InputArray, cv::InputArray, cv::Mat&, cv::Mat&) {
+    throw std::runtime_error("aruco::solvePnP (ippe.cpp) is not part of the stand-in");
+}
+// Dictionary::createMarkerMap (dictionary.cpp) names these; it is never called
+MarkerMap::MarkerMap() {}
+Marker3DInfo::Marker3DInfo() {}
+Marker3DInfo::Marker3DInfo(int _id) : id(_id) {}
+}  // namespace aruco
+
+namespace {
+void configure(aruco::MarkerDetector& det, const char* dict_name) {     // src/Frame.cc:133-139
+    det.setDictionary(std::string(dict_name));
+    det.setDetectionMode(aruco::DetectionMode::DM_NORMAL);
+    det.getParameters().setCornerRefinementMethod(aruco::CornerRefinementMethod::CORNER_LINES);
+}
+int run(aruco::MarkerDetector& det, const uint8_t* img, int w, int h, int stride, oracle_marker* out, int cap) {
+    cv::Mat m(h, w, CV_8UC1, (void*)img, (size_t)stride);
+    std::vector<aruco::Marker> ms = det.detect(m);
+    int n = 0;
+    for (size_t i = 0; i < ms.size(); i++, n++) {
+        if (n >= cap) continue;
+        out[n].id = ms[i].id;
+        for (int k = 0; k < 4; k++) { out[n].xy[2 * k] = ms[i][k].x; out[n].xy[2 * k + 1] = ms[i][k].y; }
+    }
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+// aruco::MarkerDetector::detect(image) with the reference's settings (src/Frame.cc:133-139: setDictionary(name), DM_NORMAL, CORNER_LINES).
+// out [cap]: id + 4 corners per marker in the order the reference returns them; returns the number of markers.
+int ref_aruco_detect(const uint8_t* img, int w, int h, int stride, const char* dict_name, oracle_marker* out, int cap) {
+    aruco::MarkerDetector det;
+    configure(det, dict_name);
+    return run(det, img, w, h, stride, out, cap);
+}
+
+// batch driver for the CPU reference arm of bench.py: one detector object per worker thread (the reference keeps one static instance, src/Frame.cc:41),
+// frames handed out dynamically.  Same argument list as oracle_aruco_detect_batch.
+int ref_aruco_detect_batch(const uint8_t* imgs, int n, int w, int h, int row_stride, long frame_stride, const char* dict_name, oracle_marker* out,
+                           int32_t* counts, int cap, int nthreads) {
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        aruco::MarkerDetector det;
+        configure(det, dict_name);
+        for (int f; (f = next.fetch_add(1)) < n;) counts[f] = run(det, imgs + (size_t)f * frame_stride, w, h, row_stride, out + (size_t)f * cap, cap);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+"""CPU: the marker detector oracle (oracle/aruco_oracle.cpp) against the reference's OWN detector - Thirdparty/aruco/aruco/markerdetector.cpp,
+markerdetector_impl.cpp (all of MarkerDetector_Impl::detect), marker.cpp, markerlabeler.cpp, dictionary.cpp, dictionary_based.cpp compiled unmodified
+into oracle/_ref/libref_aruco.so on oracle/arucoshim and configured as src/Frame.cc:133-139.  Same markers, same order, same ids and bit-identical
+refined corners.  Golden replay everywhere (tests/golden/aruco_ref.npz), live on more frames where oracle/_ref exists."""
+import os
+
+import numpy as np
+import pytest
+
+import aruco_ref_cases as ac
+import oracle
+from orb_slam2_aruco_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "aruco_ref.npz"))
+
+
+def test_oracle_replays_the_reference(golden):
+    total = 0
+    for j, case in enumerate(ac.CASES):
+        got = oracle.aruco_detect(ac.frame(case), case["dict"])
+        assert np.array_equal(got["id"], golden["c%d.id" % j]), case
+        assert np.array_equal(got["xy"].view(np.uint32), golden["c%d.xy" % j].view(np.uint32)), case       # refined corners: identical float bits
+        total += len(got)
+        assert len(got) >= case["markers"] - 4
+    assert total > 100
+
+
+@pytest.mark.skipif(oracle.ref_aruco() is None, reason="oracle/_ref/libref_aruco.so not built (needs /root/reference)")
+def test_live_reference():
+    n = 0
+    for seed, w, h, name in [(400, 640, 480, "ARUCO_MIP_25h7"), (401, 640, 480, "ARUCO_MIP_25h7"), (402, 640, 480, "ARUCO"), (403, 1280, 720, "ARUCO_MIP_25h7"),
+                             (404, 640, 480, "ARUCO_MIP_36h12"), (405, 640, 480, "ARUCO_MIP_25h7"), (406, 800, 600, "ARUCO_MIP_25h7"), (407, 1920, 1080, "ARUCO")]:
+        img = np.ascontiguousarray(synth.make_frame(seed, w, h, markers=20, dict_name=name))
+        a = oracle.ref_aruco_detect(img, name); b = oracle.aruco_detect(img, name)
+        assert np.array_equal(a["id"], b["id"]) and np.array_equal(a["xy"].view(np.uint32), b["xy"].view(np.uint32)), (seed, w, h, name)
+        n += len(a)
+    assert n > 130
+    # frames without markers, flat frames, a frame of pure noise
+    for img in (np.zeros((240, 320), np.uint8), np.full((240, 320), 200, np.uint8), np.random.default_rng(1).integers(0, 256, (480, 640)).astype(np.uint8),
+                np.ascontiguousarray(synth.make_frame(410, markers=0))):
+        a = oracle.ref_aruco_detect(img); b = oracle.aruco_detect(img)
+        assert np.array_equal(a["id"], b["id"]) and np.array_equal(a["xy"].view(np.uint32), b["xy"].view(np.uint32))
+
+
+@pytest.mark.skipif(oracle.ref_aruco() is None, reason="oracle/_ref/libref_aruco.so not built (needs /root/reference)")
+def test_golden_file_is_current(golden):
+    case = ac.CASES[0]
+    m = oracle.ref_aruco_detect(ac.frame(case), case["dict"])
+    assert np.array_equal(m["id"], golden["c0.id"]) and np.array_equal(m["xy"].view(np.uint32), golden["c0.xy"].view(np.uint32))
