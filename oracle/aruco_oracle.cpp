@@ -3,11 +3,14 @@
 // Restatement of aruco::MarkerDetector::detect on the path the reference takes (src/Frame.cc:129-142:
 // DM_NORMAL => THRES_ADAPTIVE, CORNER_LINES => minSize 0, defaults of markerdetector.h:162-200), following
 // the de-obfuscated Thirdparty/aruco/aruco/markerdetector_impl.cpp + dictionary_based.cpp statement by
-// statement (anchor lines as in SURVEY.md section 8a / Appendix B).  The aruco sources cannot be compiled here
-// (they need the OpenCV imgproc/calib3d C++ libraries), so this file is "parity unpinned" by the reference's
-// own tests (it has none); it is pinned by (1) cv2 golden vectors for every OpenCV primitive (cvprim_aruco.h),
-// (2) a stage-by-stage cross-check against a python script that drives the real cv2 primitives in the same
-// order (tests/golden/aruco_pipeline.npz) and (3) known answers: planted marker ids/corners.
+// statement (anchor lines as in SURVEY.md section 8a / Appendix B).  The reference has no tests of its own; this
+// file is pinned by (0) the reference's OWN detector sources, compiled unmodified on oracle/arucoshim into
+// oracle/_ref/libref_aruco.so (oracle/ref_aruco_wrap.cpp): same markers, ids and bit-identical refined corners on
+// every frame tried (tests/test_oracle_aruco_vs_ref.py, tests/golden/aruco_ref.npz), and its decode stage and
+// dictionary tables by oracle/_ref/libref_dict.so (tests/test_oracle_dict_vs_ref.py); (1) cv2 golden vectors for
+// every OpenCV primitive (cvprim_aruco.h, which the compiled reference runs on as well), (2) a stage-by-stage
+// cross-check against a python script that drives the real cv2 primitives in the same order
+// (tests/golden/aruco_pipeline.npz) and (3) known answers: planted marker ids/corners.
 //
 // Canonical choices where the reference is not deterministic: std::sort of markers with equal ids
 // (markerdetector_impl.cpp:8159) is taken as a stable sort in detection order.

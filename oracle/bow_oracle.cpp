@@ -8,6 +8,8 @@
 //                                           ORBvoc.txt configuration): v.addWeight per word, then v.normalize(L1); fv.addFeature(nid, i)
 //   FORB::distance                          Thirdparty/DBoW2/DBoW2/FORB.cpp:81-101
 // The reference snapshot carries no vocabulary file, so the tests build synthetic trees in the text file's node order.
+// Pinned by the reference's OWN vendored DBoW2, compiled unmodified on oracle/vocshim into oracle/_ref/libref_voc.so (oracle/ref_voc_wrap.cpp):
+// identical word ids, node ids, feature order and TF-IDF / L1 doubles (tests/test_oracle_voc_vs_ref.py, tests/golden/voc_ref.npz).
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
