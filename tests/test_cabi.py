@@ -67,3 +67,24 @@ def test_bad_arguments_are_rejected(built_lib):
     assert built_lib.b200_orb_create(None, 1000, 1.2, 8, 20, 7, 640, 480, 1, 0) == -1
     assert built_lib.b200_orb_destroy(None) == 0
     assert built_lib.b200_orb_max_keypoints(None) == -1
+
+
+def test_keyframe_side_entry_points_validate_and_refuse_without_gpu(built_lib):
+    """b200_match_for_triangulation_host / b200_match_kf_radius_host / b200_kf_project_host / b200_kf_search_points_host: sizes are checked before the
+    device is touched (B200_EINVAL = -1), and with valid sizes nothing computes on the CPU (B200_ENODEV)"""
+    import torch
+    from orb_slam2_aruco_b200 import _lib
+    L = built_lib
+    z = np.zeros(64, np.float32); zi = np.zeros(64, np.int32); zb = np.zeros(64, np.uint8)
+    p = lambda a: a.ctypes.data
+    assert L.b200_match_kf_radius_host(None, None, -1, None, None, None, None, 0, None, 8, C.c_double(0), None, None, 0) == _lib.EINVAL
+    assert L.b200_match_kf_radius_host(None, None, 0, None, None, None, None, 1, None, 17, C.c_double(0), None, None, 0) == _lib.EINVAL      # nlevels > 16
+    assert L.b200_kf_project_host(None, None, None, None, None, None, None, None, None, None, -1, 3.0, None, None, 8, None, None, None, 0) == _lib.EINVAL
+    assert L.b200_kf_search_points_host(None, None, 0, None, None, None, None, None, None, None, None, None, None, None, None, 1, 3.0, None, None, None, 0,
+                                        C.c_double(0), None, None, None, None, None, 0) == _lib.EINVAL
+    assert L.b200_match_for_triangulation_host(None, None, 1, None, None, 1, None, None, None, None, -1, None, None, None, None, 8, 1, 50, None, 0) == _lib.EINVAL
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert L.b200_match_kf_radius_host(p(z), p(zb), 1, p(z), p(z), p(zi), p(zb), 1, p(z), 8, C.c_double(5.99), p(zi), p(zi), 0) == _lib.ENODEV
+    assert L.b200_kf_project_host(p(z), p(z), p(z), None, None, p(z), p(z), p(z), None, p(z), 1, 3.0, p(z), p(z), 8, p(zb), p(z), p(zi), 0) == _lib.ENODEV
+    assert L.b200_match_for_triangulation_host(p(z), p(zb), 1, p(z), p(zb), 1, p(zi), p(zi), p(zi), p(zi), 1, p(z), p(z), p(z), p(z), 8, 1, 50, p(zi), 0) == _lib.ENODEV
