@@ -432,7 +432,7 @@ def main():
             "per_frame": {"keypoints": nkp / B, "markers": nmk / B, "matches": nmatch / B},
         }
         if not args.no_cpu_baseline and world == 1:
-            sample = min(B, 256)                              # ~10 s of single-thread CPU work at 640x480
+            sample = max(16, min(B, 256 * 640 * 480 // (W * H)))    # ~10 s of single-thread CPU work whatever the frame size
             ref_set = cpu_ref_set(wl) if wl["match"] else None
             secs, kind, what = cpu_reference_run(imgs_np[:sample], wl, 1, ref_set)
             line["cpu_baseline"] = {"value": sample / secs, "unit": "frames/s", "cores": 1, "kind": kind,
