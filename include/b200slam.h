@@ -163,7 +163,8 @@ int b200_distinctive_descriptors_host(const uint8_t* desc, const int32_t* ofs, i
  * GetFeaturesInArea, q_desc [n][32], q_angle [n] (mode 1 histogram), q_observed [n] = the map point's Observations() > 0.
  * th_high: accept bestDist <= th_high (<= 0: TH_HIGH = 100).
  * The loop-closing SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (include/ORBmatcher.h:52, src/ORBmatcher.cc:294-407) is mode 1 with
- * check_ori = 0, th_high = TH_LOW (50), q_levels = (nPredictedLevel - 1, nPredictedLevel), occupied = "vpMatched[i] != NULL", q_observed = 1.
+ * check_ori = 0, th_high = TH_LOW (50), q_levels = (nPredictedLevel - 1, nPredictedLevel), occupied = "vpMatched[i] != NULL", q_observed = 1;
+ * pass mode 2 for it: mode 1 with the keyframe's grid origin (b200_keyframe_features_in_area).
  * assign [n_frame] out = query index assigned to that frame keypoint or -1 (F.mvpMapPoints[bestIdx] = pMP).  Returns nmatches. */
 int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_frame, const float* bounds4, uint8_t* occupied,
                                   const float* q_xyr, const int32_t* q_levels, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed,
@@ -271,6 +272,12 @@ int b200_frame_assign_grid(const b200_keypoint* kps_un, const int32_t* counts, i
 int b200_frame_features_in_area(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                                 const float* queries_xyr, const int32_t* query_levels, int n_queries,
                                 int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream);
+/* KeyFrame::GetFeaturesInArea (include/KeyFrame.h:106, src/KeyFrame.cc:672-718): the same search, but the window is laid over the grid from the
+ * keyframe's INT mnMinX / mnMinY (truncated copies of the frame's float bounds, include/KeyFrame.h:211-214) with the frame's float cell size.
+ * Identical to b200_frame_features_in_area when the bounds are integers (no distortion).  query_levels as there ((-1, -1) = no level filter). */
+int b200_keyframe_features_in_area(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                   const float* queries_xyr, const int32_t* query_levels, int n_queries,
+                                   int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream);
 
 
 /* ---------------------------------------------------------------- bag of words ------- */

@@ -418,7 +418,8 @@ public:
         const bool ori = mbCheckOrientation;
         mbCheckOrientation = false;                                 // no rotation histogram in this member (ORBmatcher.cc:294-407)
         int nm;
-        try { nm = SearchByProjection(keysUn, descriptors, bounds, occ, pts, 1, assign, TH_LOW); } catch (...) { mbCheckOrientation = ori; throw; }
+        try { nm = SearchByProjection(keysUn, descriptors, bounds, occ, pts, 2 /* mode 1 over KeyFrame::GetFeaturesInArea's grid origin */, assign, TH_LOW); }
+        catch (...) { mbCheckOrientation = ori; throw; }
         mbCheckOrientation = ori;
         return nm;
     }

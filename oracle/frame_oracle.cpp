@@ -68,16 +68,33 @@ void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, 
 }
 
 // GetFeaturesInArea: returns the number of indices written to out (visit order of the reference: ix, iy, position in cell)
+static int features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4, float min_x, float min_y,
+                            float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
+
 int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                             float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
+    return features_in_area(un, cell_start, cell_items, bounds4, bounds4[0], bounds4[2], x, y, r, min_level, max_level, out, cap);
+}
+
+// KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:672-718): the window is placed from the keyframe's INT mnMinX / mnMinY (include/KeyFrame.h:211-214, truncated
+// copies of the frame's float bounds) while the cell size is the frame's float mfGridElementWidthInv / HeightInv; no level arguments (pass -1, -1)
+int oracle_keyframe_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                     float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
+    return features_in_area(un, cell_start, cell_items, bounds4, (float)(int)bounds4[0], (float)(int)bounds4[2], x, y, r, min_level, max_level, out, cap);
+}
+
+}  // extern "C"
+
+static int features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4, float min_x, float min_y,
+                            float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
     const float inv_w = 64.f / (bounds4[1] - bounds4[0]), inv_h = 48.f / (bounds4[3] - bounds4[2]);
-    const int c0 = (int)floor((x - bounds4[0] - r) * inv_w) > 0 ? (int)floor((x - bounds4[0] - r) * inv_w) : 0;
+    const int c0 = (int)floor((x - min_x - r) * inv_w) > 0 ? (int)floor((x - min_x - r) * inv_w) : 0;
     if (c0 >= 64) return 0;
-    int c1 = (int)ceil((x - bounds4[0] + r) * inv_w); if (c1 > 63) c1 = 63;
+    int c1 = (int)ceil((x - min_x + r) * inv_w); if (c1 > 63) c1 = 63;
     if (c1 < 0) return 0;
-    const int r0 = (int)floor((y - bounds4[2] - r) * inv_h) > 0 ? (int)floor((y - bounds4[2] - r) * inv_h) : 0;
+    const int r0 = (int)floor((y - min_y - r) * inv_h) > 0 ? (int)floor((y - min_y - r) * inv_h) : 0;
     if (r0 >= 48) return 0;
-    int r1 = (int)ceil((y - bounds4[2] + r) * inv_h); if (r1 > 47) r1 = 47;
+    int r1 = (int)ceil((y - min_y + r) * inv_h); if (r1 > 47) r1 = 47;
     if (r1 < 0) return 0;
     const bool check = (min_level > 0) || (max_level >= 0);
     int n = 0;
@@ -91,5 +108,3 @@ int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start
             }
     return n;
 }
-
-}  // extern "C"

@@ -89,7 +89,7 @@ struct KFGrid {
     KFGrid(const oracle_keypoint* k_, const uint8_t* d_, int n_, const float* b) : k(k_), d(d_), n(n_), b4(b), cs(64 * 48 + 1), ci(n_ > 0 ? n_ : 1), cand(n_ > 0 ? n_ : 1) {
         oracle_assign_grid(k, n, b4, cs.data(), ci.data());
     }
-    int query(float x, float y, float r) { return oracle_features_in_area(k, cs.data(), ci.data(), b4, x, y, r, -1, -1, cand.data(), n); }
+    int query(float x, float y, float r) { return oracle_keyframe_features_in_area(k, cs.data(), ci.data(), b4, x, y, r, -1, -1, cand.data(), n); }      // KeyFrame.cc:672-718
     bool in_image(float x, float y) const { return x >= (float)(int)b4[0] && x < (float)(int)b4[1] && y >= (float)(int)b4[2] && y < (float)(int)b4[3]; }
 };
 

@@ -135,6 +135,8 @@ void oracle_match_candidates(const uint8_t* qd, int nq, const uint8_t* td, const
 // F1 / F2 = undistorted keypoints + descriptors; F2's grid comes from the frame oracle (AssignFeaturesToGrid / GetFeaturesInArea).
 // prev_matched [n1][2] is read and updated like vbPrevMatched; matches12 [n1] receives vnMatches12; returns nmatches.
 extern "C" void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, int32_t* cell_start, int32_t* cell_items);
+extern "C" int oracle_keyframe_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                                float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 extern "C" int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                                        float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 extern "C" int oracle_search_for_initialization(const oracle_keypoint* k1, const uint8_t* d1, int n1, const oracle_keypoint* k2, const uint8_t* d2, int n2,
@@ -246,6 +248,8 @@ extern "C" int oracle_search_by_projection(const oracle_keypoint* k2, const uint
                                            const float* q_xyr, const int32_t* q_lev, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed, int nq,
                                            int mode, float nnratio, int check_ori, int th_high, int32_t* assign) {
     const int TH_HIGH = th_high > 0 ? th_high : 100;          // ORBdist of the relocalisation variant (ORBmatcher.cc:1559), else TH_HIGH
+    const bool keyframe = mode == 2;                          // mode 2: mode 1 over KeyFrame::GetFeaturesInArea (SearchByProjection(KeyFrame*, Scw, ...), :294-407)
+    if (keyframe) mode = 1;
     for (int i = 0; i < n2; i++) assign[i] = -1;
     int nmatches = 0;
     std::vector<int32_t> cs(64 * 48 + 1), ci(n2 > 0 ? n2 : 1), cand(n2 > 0 ? n2 : 1);
@@ -253,8 +257,8 @@ extern "C" int oracle_search_by_projection(const oracle_keypoint* k2, const uint
     std::vector<std::vector<int> > rotHist(HISTO_LENGTH);
     const float factor = 1.0f / HISTO_LENGTH;
     for (int q = 0; q < nq; q++) {
-        const int nc = oracle_features_in_area(k2, cs.data(), ci.data(), bounds4, q_xyr[3 * q], q_xyr[3 * q + 1], q_xyr[3 * q + 2], q_lev[2 * q], q_lev[2 * q + 1],
-                                               cand.data(), n2);
+        const int nc = (keyframe ? oracle_keyframe_features_in_area : oracle_features_in_area)(k2, cs.data(), ci.data(), bounds4, q_xyr[3 * q], q_xyr[3 * q + 1],
+                                                                                              q_xyr[3 * q + 2], q_lev[2 * q], q_lev[2 * q + 1], cand.data(), n2);
         if (nc == 0) continue;
         int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
         for (int c = 0; c < nc; c++) {

@@ -83,10 +83,11 @@ struct RefGrid {
         cellStart.assign(64 * 48 + 1, 0); cellItems.assign(k.size() + 1, 0);
         oracle_assign_grid((const oracle_keypoint*)keysUn.data(), (int)keysUn.size(), bounds, cellStart.data(), cellItems.data());
     }
-    std::vector<size_t> query(float x, float y, float r, int minLevel, int maxLevel) const {
+    std::vector<size_t> query(float x, float y, float r, int minLevel, int maxLevel, bool keyframe = false) const {
         std::vector<int32_t> out(keysUn.size() + 1);
-        const int n = oracle_features_in_area((const oracle_keypoint*)keysUn.data(), cellStart.data(), cellItems.data(), bounds, x, y, r, minLevel, maxLevel,
-                                              out.data(), (int)keysUn.size());
+        const int n = (keyframe ? oracle_keyframe_features_in_area : oracle_features_in_area)((const oracle_keypoint*)keysUn.data(), cellStart.data(),
+                                                                                             cellItems.data(), bounds, x, y, r, minLevel, maxLevel, out.data(),
+                                                                                             (int)keysUn.size());
         return std::vector<size_t>(out.begin(), out.begin() + std::min(n, (int)keysUn.size()));
     }
 };
@@ -154,7 +155,7 @@ public:
         g_ref_trace.xyr.push_back(x); g_ref_trace.xyr.push_back(y); g_ref_trace.xyr.push_back(r);
         g_ref_trace.levels.push_back(g_ref_trace.lastPredicted - 1); g_ref_trace.levels.push_back(g_ref_trace.lastPredicted);
         g_ref_trace.mp.push_back(-1);
-        return grid.query(x, y, r, -1, -1);
+        return grid.query(x, y, r, -1, -1, true);                  // from the int mnMinX / mnMinY (src/KeyFrame.cc:677-689)
     }
 };
 

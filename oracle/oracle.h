@@ -82,6 +82,8 @@ void oracle_image_bounds(int w, int h, const double* cam9, float* bounds4);
 void oracle_assign_grid(const oracle_keypoint* un, int n, const float* bounds4, int32_t* cell_start, int32_t* cell_items);
 int oracle_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
                             float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
+int oracle_keyframe_features_in_area(const oracle_keypoint* un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                            float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:271-331): BestIdx over desc [n][32], -1 when n == 0
 int oracle_distinctive_descriptor(const uint8_t* desc, int n);

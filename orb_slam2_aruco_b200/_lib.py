@@ -83,6 +83,7 @@ def lib():
         L.b200_frame_image_bounds.argtypes = [i32, i32, vp, vp, i32]
         L.b200_frame_assign_grid.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, vp]
         L.b200_frame_features_in_area.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
+        L.b200_keyframe_features_in_area.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
         _lib = L
     return _lib
 

@@ -458,7 +458,7 @@ class ORBmatcher:
         """SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th) (ORBmatcher.h:52,
         ORBmatcher.cc:294-407).  matched [n] = vpMatched before the call (-1 none, >= 0 index into vpPoints, -2 another point).  A matched keyframe
         feature is hidden from every later point, so the queries are replayed in order by the projection resolve kernel
-        (b200_match_by_projection_host, mode 1 without the rotation histogram, TH_LOW).  Returns (nmatches, vpMatched after the call)."""
+        (b200_match_by_projection_host, mode 2 = mode 1 over the keyframe's grid origin, without the rotation histogram, TH_LOW).  Returns (nmatches, vpMatched after the call)."""
         st = np.asarray(mp_state, np.uint8); matched = np.asarray(matched, np.int32).copy()
         valid, q3, level = self.project_points(kfgeom.pose_from_S(Scw), cam4, bounds4, mp_pos, mp_normal, mp_minmax, int(th))
         found = np.zeros(len(st), bool); found[matched[matched >= 0]] = True
@@ -466,7 +466,7 @@ class ORBmatcher:
         qs = np.nonzero(valid)[0]
         lv = np.stack([level[qs] - 1, level[qs]], 1).astype(np.int32)
         n, assign, _ = search_by_projection(kps_un, desc, bounds4, (matched != -1).astype(np.uint8), q3[qs], lv, np.asarray(mp_desc, np.uint8).reshape(-1, 32)[qs],
-                                            np.zeros(len(qs), np.float32), np.ones(len(qs), np.uint8), 1, check_ori=False, th_high=self.TH_LOW, device=self._device)
+                                            np.zeros(len(qs), np.float32), np.ones(len(qs), np.uint8), 2, check_ori=False, th_high=self.TH_LOW, device=self._device)
         hit = assign >= 0
         matched[hit] = qs[assign[hit]]
         return n, matched

@@ -220,9 +220,9 @@ int b200_frame_assign_grid(const b200_keypoint* kps_un, const int32_t* counts, i
     return B200_OK;
 }
 
-int b200_frame_features_in_area(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
-                                const float* queries_xyr, const int32_t* query_levels, int n_queries,
-                                int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream) {
+static int features_in_area_impl(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                 const float* queries_xyr, const int32_t* query_levels, int n_queries,
+                                 int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream, bool keyframe_origin) {
     if (n_queries < 0 || row_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
     if (!bounds4 || !(bounds4[1] > bounds4[0]) || !(bounds4[3] > bounds4[2])) return fail(B200_EINVAL, "bad image %s", "bounds");
     int rc = use_device(device);
@@ -230,10 +230,25 @@ int b200_frame_features_in_area(const b200_keypoint* kps_un, const int32_t* cell
     if (n_queries == 0) return B200_OK;
     if (!kps_un || !cell_start || !cell_items || !queries_xyr || !query_levels || !out_idx || !out_count) return fail(B200_EINVAL, "null %s", "pointer");
     const float inv_w = (float)kGridCols / (bounds4[1] - bounds4[0]), inv_h = (float)kGridRows / (bounds4[3] - bounds4[2]);
-    B200_LAUNCH(k_features_in_area, (n_queries * 32 + 127) / 128, 128, 0, (cudaStream_t)stream, kps_un, cell_start, cell_items, bounds4[0], bounds4[2],
+    // KeyFrame keeps mnMinX / mnMinY as int (include/KeyFrame.h:211-214, truncated from the frame's float bounds) while the cell size stays the frame's
+    // float mfGridElementWidthInv: its queries are laid over the grid from the truncated origin (src/KeyFrame.cc:677-689)
+    const float min_x = keyframe_origin ? (float)(int)bounds4[0] : bounds4[0], min_y = keyframe_origin ? (float)(int)bounds4[2] : bounds4[2];
+    B200_LAUNCH(k_features_in_area, (n_queries * 32 + 127) / 128, 128, 0, (cudaStream_t)stream, kps_un, cell_start, cell_items, min_x, min_y,
                 inv_w, inv_h, queries_xyr, query_levels, n_queries, out_idx, out_count, row_cap);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
+}
+
+int b200_frame_features_in_area(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                const float* queries_xyr, const int32_t* query_levels, int n_queries,
+                                int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream) {
+    return features_in_area_impl(kps_un, cell_start, cell_items, bounds4, queries_xyr, query_levels, n_queries, out_idx, out_count, row_cap, device, stream, false);
+}
+
+int b200_keyframe_features_in_area(const b200_keypoint* kps_un, const int32_t* cell_start, const int32_t* cell_items, const float* bounds4,
+                                   const float* queries_xyr, const int32_t* query_levels, int n_queries,
+                                   int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream) {
+    return features_in_area_impl(kps_un, cell_start, cell_items, bounds4, queries_xyr, query_levels, n_queries, out_idx, out_count, row_cap, device, stream, true);
 }
 
 }  // extern "C"

@@ -943,7 +943,9 @@ int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* de
                                   const float* q_xyr, const int32_t* q_levels, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed,
                                   int n_queries, int mode, float ratio, int check_ori, int th_high, int32_t* assign, int device) {
     if (th_high <= 0) th_high = 100;                            // TH_HIGH, ORBmatcher.cc:38
-    if (n_frame < 0 || n_queries < 0 || (mode != 0 && mode != 1)) return fail(B200_EINVAL, "bad %s", "sizes or mode");
+    if (n_frame < 0 || n_queries < 0 || mode < 0 || mode > 2) return fail(B200_EINVAL, "bad %s", "sizes or mode");
+    const bool keyframe = mode == 2;                            // SearchByProjection(KeyFrame*, Scw, ...): mode 1 over KeyFrame::GetFeaturesInArea
+    if (keyframe) mode = 1;
     int rc = use_device(device);
     if (rc) return rc;
     if (n_frame > 0 && (!kps_un || !desc || !occupied || !assign || !bounds4)) return fail(B200_EINVAL, "null %s", "frame pointer");
@@ -960,8 +962,9 @@ int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* de
         (rc = asg.alloc((size_t)n_frame * 4)) || (rc = eb.alloc((size_t)n_queries * 4)) || (rc = ei.alloc((size_t)n_queries * 4)) || (rc = res.alloc(8)))
         return rc;
     if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_frame, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
-    if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
-                                          (const int32_t*)lv2.p, n_queries, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+    if ((rc = (keyframe ? b200_keyframe_features_in_area : b200_frame_features_in_area)(
+             (const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p, (const int32_t*)lv2.p, n_queries,
+             (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
         return rc;
     B200_LAUNCH(k_init_dist, (n_queries * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)qd.p, n_queries, (const ulonglong4*)d2.p, (const int*)cand.p,
                 (const int*)cnt.p, row_cap, (int*)dist.p);
@@ -1166,8 +1169,8 @@ int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, 
         return rc;
     B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, 0));
     if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
-    if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
-                                          (const int32_t*)lv2.p, n_queries, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+    if ((rc = b200_keyframe_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
+                                             (const int32_t*)lv2.p, n_queries, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
         return rc;
     B200_LAUNCH(k_radius_best, (n_queries * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)q3.p,
                 (const ulonglong4*)qd.p, (const int*)cand.p, (const int*)cnt.p, row_cap, n_queries, lt, chi2, (int*)bi.p, (int*)bd.p, (int*)ovf.p);
@@ -1222,8 +1225,8 @@ int b200_kf_search_points_host(const b200_keypoint* kps_un, const uint8_t* desc,
             return rc;
         B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, 0));
         if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
-        if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)dq.p,
-                                              (const int32_t*)dl2.p, n, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+        if ((rc = b200_keyframe_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)dq.p,
+                                                 (const int32_t*)dl2.p, n, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
             return rc;
         B200_LAUNCH(k_radius_best, (n * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)dq.p, (const ulonglong4*)qd.p,
                     (const int*)cand.p, (const int*)cnt.p, row_cap, n, lt, chi2, (int*)bi.p, (int*)bd.p, (int*)ovf.p);

@@ -178,3 +178,22 @@ def test_predict_scale_thresholds_equal_libm():
     ok = np.isfinite(r) & (r > 0)
     assert np.array_equal(got[ok], want[ok])
     assert got[-3] == 0 and got[-1] == 0                           # ratio 0 / NaN: level 0 (such points fail the distance tests anyway)
+
+
+@pytest.mark.skipif(oracle.ref_match() is None, reason="oracle/_ref/libref_match.so not built (needs /root/reference)")
+def test_live_reference_with_distorted_image_bounds(monkeypatch):
+    """non-integer image bounds (a distorted camera, src/Frame.cc:390-416): the KeyFrame keeps them as int (include/KeyFrame.h:211-214), so IsInImage
+    and the origin of KeyFrame::GetFeaturesInArea truncate while the grid itself was built from the float bounds"""
+    monkeypatch.setattr(m2, "BOUNDS", np.array([-3.7, 643.6, -2.4, 482.9], np.float32))
+    R, O = oracle.ref_match(), oracle.lib()
+    c = m2.keyframe_points_inputs(seed=14)
+    a = m2.run_fuse(R, "ref", c, 3.0); b = m2.run_fuse(O, "oracle", c, 3.0)
+    assert a[0] == b[0] and a[0] > 200 and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    c = m2.keyframe_points_inputs(seed=16, sim3=True)
+    a = m2.run_fuse_sim3(R, "ref", c, 4.0); b = m2.run_fuse_sim3(O, "oracle", c, 4.0)
+    assert a[0] == b[0] and a[0] > 200 and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    a = m2.run_loop(R, "ref", c, 10); b = m2.run_loop(O, "oracle", c, 10)
+    assert a[0] == b[0] and a[0] > 100 and np.array_equal(a[1], b[1])
+    c = m2.sim3_inputs(seed=18)
+    a = m2.run_sim3(R, "ref", c, 7.5); b = m2.run_sim3(O, "oracle", c, 7.5)
+    assert a[0] == b[0] and a[0] > 100 and np.array_equal(a[1], b[1])
