@@ -10,9 +10,9 @@ pytestmark = pytest.mark.skipif(oracle.ref() is None, reason="oracle/_ref not bu
 
 
 @pytest.mark.parametrize("idx,w,h,nf", [(2, 640, 480, 1000), (3, 640, 480, 2000), (11, 960, 540, 1000), (12, 333, 257, 500),
-                                       (13, 200, 150, 300), (14, 1280, 720, 2000)])
+                                       (13, 200, 150, 300), (14, 1280, 720, 2000), (15, 1920, 1080, 4000), (16, 640, 480, 1000)])
 def test_restatement_equals_reference(idx, w, h, nf):
-    img = synth.make_frame(idx, w, h)
+    img = synth.make_frame(idx, w, h, markers=20 if idx == 16 else 0)      # 15: the C5 frame size; 16: a frame with planted markers (C3)
     k, d = oracle.orb_extract(img, nf)
     k2, d2 = oracle.ref_orb_extract(img, nf)
     assert len(k) == len(k2)
