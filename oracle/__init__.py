@@ -73,6 +73,20 @@ def ref_match():
     return _ref_match
 
 
+_ref_mappoint = None
+
+
+def ref_mappoint():
+    """The reference's own src/MapPoint.cc + include/MapPoint.h (and ORBmatcher.cc) on stand-in KeyFrame / Frame / Map, or None when never built."""
+    global _ref_mappoint
+    if _ref_mappoint is None:
+        path = os.path.join(HERE, "_ref", "libref_mappoint.so")
+        if not os.path.exists(path):
+            return None
+        _ref_mappoint = C.CDLL(path)
+    return _ref_mappoint
+
+
 _ref_aruco = None
 
 

@@ -52,6 +52,7 @@ public:
     void create(int r, int c, int t) { if (!(data && r == rows && c == cols && t == tp)) alloc(r, c, t); }
     void release() { rows = cols = 0; step = 0; data = 0; buf.reset(); }
     static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
+    void copyTo(Mat& dst) const;                               // src/MapPoint.cc:39 Pos.copyTo(mWorldPos)
     int type() const { return tp; }
     bool empty() const { return data == 0 || rows * cols == 0; }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
@@ -84,6 +85,8 @@ public:
         return s;
     }
 };
+
+inline void Mat::copyTo(Mat& dst) const { dst = clone(); }
 
 static inline Mat operator*(const Mat& a, const Mat& b) {
     assert(a.cols == b.rows);

@@ -7,7 +7,13 @@
 // checked against a brute-force definition) and the MapPoint getters.  Every grid query the matcher makes is recorded (g_ref_trace), so
 // tests can hand the product path the very same queries.
 #pragma once
+// REF_REAL_MAPPOINT (oracle/_ref/libref_mappoint.so): the reference's own include/MapPoint.h + src/MapPoint.cc are compiled as well, so only KeyFrame,
+// Frame and Map are stand-ins and the MapPoint below is left out
+#ifndef REF_REAL_MAPPOINT
 #define MAPPOINT_H
+#else
+#define MAP_H
+#endif
 #define KEYFRAME_H
 #define FRAME_H
 #include <algorithm>
@@ -34,6 +40,7 @@ namespace ORB_SLAM2 {
 class KeyFrame;
 class Frame;
 
+#ifndef REF_REAL_MAPPOINT
 class MapPoint {
 public:
     // tracking variables (include/MapPoint.h:95-101)
@@ -71,6 +78,16 @@ public:
     void Replace(MapPoint* pMP) { replaced = pMP; bad = true; }
 };
 
+#else
+class MapPoint;
+class Map {
+public:
+    std::mutex mMutexPointCreation;
+    std::vector<MapPoint*> erased;
+    void EraseMapPoint(MapPoint* p) { erased.push_back(p); }
+};
+#endif
+
 // shared by the Frame and KeyFrame stand-ins: keypoints, descriptors, the 64x48 grid behind GetFeaturesInArea
 struct RefGrid {
     std::vector<cv::KeyPoint> keysUn;
@@ -99,6 +116,9 @@ public:
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     float mbf = 0, mb = 0;
     int N = 0;
+    long unsigned int mnId = 0;
+    cv::Mat mOw;
+    cv::Mat GetCameraCenter() { return mOw.clone(); }
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight, mvDepth;
     DBoW2::BowVector mBowVec;
@@ -139,11 +159,22 @@ public:
 
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    long unsigned int mnId = 0;
+    long int mnFrameId = 0;
+    bool bad = false;
+    bool isBad() { return bad; }
+    void EraseMapPointMatch(const size_t& idx) { mvpMapPoints[idx] = nullptr; }
+    void EraseMapPointMatch(MapPoint* pMP) { for (auto& p : mvpMapPoints) if (p == pMP) p = nullptr; }
+    void ReplaceMapPointMatch(const size_t& idx, MapPoint* pMP) { mvpMapPoints[idx] = pMP; }
+#ifndef REF_REAL_MAPPOINT
     std::set<MapPoint*> GetMapPoints() {
         std::set<MapPoint*> s;
         for (MapPoint* p : mvpMapPoints) if (p && !p->isBad()) s.insert(p);
         return s;
     }
+#else
+    std::set<MapPoint*> GetMapPoints();                            // defined where MapPoint is complete (oracle/ref_mappoint_wrap.cpp)
+#endif
     void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
     cv::Mat GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
     cv::Mat GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
