@@ -394,6 +394,57 @@ class ORBmatcher:
                                                           self._device))
         return n, m12[:len(k1)]
 
+    def FuseReal(self, kps_un, desc, bounds4, cam4, Tcw, held_state, held_nobs, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, mp_nobs, th=3.0):
+        """Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) with the outcome statements (ORBmatcher.cc:957-976) applied the way the reference's
+        REAL MapPoint / KeyFrame objects behave: MapPoint::Replace (MapPoint.cc:192-236) re-points the keyframe's slot at the survivor and hands it the
+        observation, AddObservation / AddMapPoint (MapPoint.cc:110-121) fill an empty slot, so a later point of the same call meets whoever holds the slot by
+        then.  Same scene arguments as Fuse (every point observes at most this keyframe).  Returns dict(n = nFused, slot [n_kf] = holder of each feature
+        afterwards (-1 nobody, 1000000 + j the keyframe's own point j, m list point m), mp_bad, held_bad, mp_nobs = Observations() afterwards)."""
+        st = np.asarray(mp_state, np.uint8); nobs = np.asarray(mp_nobs, np.int32).copy()
+        hs = np.asarray(held_state, np.uint8); hn = np.asarray(held_nobs, np.int32).copy()
+        valid, bi, bd = self.search_points(kps_un, desc, bounds4, kfgeom.pose_from_T(Tcw), cam4, mp_pos, mp_normal, mp_minmax, mp_desc, st != 1, th, chi2=5.99)
+        n_kf = len(hs)
+        slot = np.where(hs > 0, 1000000 + np.arange(n_kf), -1).astype(np.int64)
+        held_bad = hs == 2; mp_bad = st == 2
+        in_kf = {}                                                   # list point -> feature it observes in this keyframe
+        nf = 0
+
+        def is_bad(who):
+            return held_bad[who - 1000000] if who >= 1000000 else mp_bad[who]
+
+        def observations(who):
+            return hn[who - 1000000] if who >= 1000000 else nobs[who]
+
+        def replace(x, y):
+            """x->Replace(y): x dies; its observation of this keyframe goes to y, or the slot is cleared when y already observes the keyframe"""
+            xi = x - 1000000 if x >= 1000000 else in_kf.get(x)
+            if x >= 1000000:
+                held_bad[x - 1000000] = True
+            else:
+                mp_bad[x] = True
+            if xi is None:
+                return
+            y_in = True if y >= 1000000 else (y in in_kf)
+            if not y_in:
+                slot[xi] = y; in_kf[y] = xi; nobs[y] += 1
+            else:
+                slot[xi] = -1
+        for m in np.nonzero(valid)[0]:
+            idx, dist = int(bi[m]), int(bd[m])
+            if mp_bad[m] or m in in_kf or dist > self.TH_LOW:
+                continue
+            owner = int(slot[idx])
+            if owner >= 0:
+                if not is_bad(owner):
+                    if observations(owner) > observations(m):
+                        replace(m, owner)
+                    else:
+                        replace(owner, m)
+            else:
+                slot[idx] = m; in_kf[m] = idx; nobs[m] += 1
+            nf += 1
+        return dict(n=nf, slot=slot.astype(np.int32), mp_bad=mp_bad.astype(np.uint8), held_bad=held_bad.astype(np.uint8), mp_nobs=nobs)
+
     def Fuse(self, kps_un, desc, bounds4, cam4, Tcw, held_state, held_nobs, mp_state, mp_pos, mp_normal, mp_desc, mp_minmax, mp_nobs, th=3.0):
         """Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th = 3.0) (ORBmatcher.h:76, ORBmatcher.cc:831-981) on arrays.  Keyframe: features,
         pose, held_state [n] 0 none / 1 good / 2 bad point at that feature with held_nobs observations.  Map point m: mp_state 0 NULL / 1 good / 2 bad /

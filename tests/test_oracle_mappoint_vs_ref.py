@@ -127,3 +127,27 @@ def test_golden_file_is_current(golden, tmp_path):
     write_golden(path)
     g = np.load(path)
     assert all(np.array_equal(g[k], golden[k]) for k in g.files)
+
+
+@pytest.mark.skipif(oracle.ref_mappoint() is None, reason="oracle/_ref/libref_mappoint.so not built (needs /root/reference)")
+def test_fuse_outcome_on_real_mappoints(monkeypatch):
+    """ORBmatcher::Fuse run by the reference on REAL MapPoint objects (Replace re-points keyframe slots, AddObservation counts) against the mirror's FuseReal:
+    final holder of every keyframe feature, bad flags and observation counts.  The mirror's device search is answered by the CPU oracle here."""
+    import match_cases as mc
+    from test_oracle_match2_vs_ref import _OracleSearches
+    R = oracle.ref_mappoint()
+    for seed, th in ((4, 3.0), (24, 3.0), (25, 6.0)):
+        c = m2.keyframe_points_inputs(seed=seed)
+        c["mp_state"] = np.where(c["mp_state"] == 3, 1, c["mp_state"]).astype(np.uint8)      # the scene's "already observed" points name no real slot
+        n, m = len(c["k"]), len(c["mp_desc"])
+        # several points per keypoint, so that slots are hit more than once in one call
+        slot = np.zeros(n, np.int32); mb = np.zeros(m, np.uint8); hb = np.zeros(n, np.uint8); no = np.zeros(m, np.int32)
+        nf = R.ref_fuse_real(P(c["k"]), P(c["d"]), n, P(mc.BOUNDS), P(mc.CAM4), P(c["T"]), P(c["held_state"]), P(c["held_nobs"]), m, P(c["mp_state"]),
+                             P(c["mp_pos"]), P(c["mp_normal"]), P(c["mp_desc"]), P(c["mp_minmax"]), P(c["mp_nobs"]), C.c_float(th), P(slot), P(mb), P(hb), P(no))
+        got = _OracleSearches(0.6, True).FuseReal(c["k"], c["d"], mc.BOUNDS, mc.CAM4, c["T"], c["held_state"], c["held_nobs"], c["mp_state"], c["mp_pos"],
+                                                  c["mp_normal"], c["mp_desc"], c["mp_minmax"], c["mp_nobs"], th)
+        assert got["n"] == nf and nf > 200
+        assert np.array_equal(got["slot"], slot) and np.array_equal(got["mp_bad"], mb) and np.array_equal(got["held_bad"], hb)
+        live = c["mp_state"] > 0
+        assert np.array_equal(got["mp_nobs"][live], no[live])
+        assert (slot >= 0).sum() > (c["held_state"] > 0).sum() and (slot[(slot >= 0) & (slot < 1000000)] >= 0).sum() > 100
