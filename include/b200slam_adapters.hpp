@@ -553,6 +553,15 @@ public:
     }
 #endif
     bool isValid() const { return fx != 0 && fy != 0; }
+    // void CameraParameters::resize(cv::Size size) (cameraparameters.cpp:158-173), as a copy: float factors, fx cx by width, fy cy by height
+    CameraParameters resized(int w, int h) const {
+        CameraParameters c = *this;
+        if (w == width && h == height) return c;
+        const float AxFactor = float(w) / float(width), AyFactor = float(h) / float(height);
+        c.fx *= AxFactor; c.cx *= AxFactor; c.fy *= AyFactor; c.cy *= AyFactor;
+        c.width = w; c.height = h;
+        return c;
+    }
     void cam9(float* out) const { out[0] = fx; out[1] = fy; out[2] = cx; out[3] = cy; for (int i = 0; i < 5; i++) out[4 + i] = dist[i]; }
 };
 
@@ -601,10 +610,18 @@ public:
     }
 };
 
+enum DetectionMode : int { DM_NORMAL = 0, DM_FAST = 1, DM_VIDEO_FAST = 2 };                      // markerdetector.h:67 (namespace scope, as src/Frame.cc:134 spells it)
+enum CornerRefinementMethod : int { CORNER_SUBPIX = 0, CORNER_LINES = 1, CORNER_NONE = 2 };      // markerdetector.h:76
+
 class MarkerDetector {
 public:
-    enum DetectionMode { DM_NORMAL = 0, DM_FAST = 1, DM_VIDEO_FAST = 2 };
-    enum CornerRefinementMethod { CORNER_SUBPIX = 0, CORNER_LINES = 1, CORNER_NONE = 2 };
+    // MarkerDetector::Params (markerdetector.h:85-200), the one member src/Frame.cc:135 touches
+    struct Params {
+        void setCornerRefinementMethod(CornerRefinementMethod m) {                                   // markerdetector.h:129
+            if (m != CORNER_LINES) throw std::runtime_error("b200slam: only CORNER_LINES is supported");
+        }
+    };
+    Params& getParameters() { return params_; }                                                      // markerdetector.h:320
 
     MarkerDetector() : dict_("ALL_DICTS"), h_(nullptr), w_(0), ht_(0), device_(0) {}
     explicit MarkerDetector(const std::string& dict_name, int device = 0) : dict_(dict_name), h_(nullptr), w_(0), ht_(0), device_(device) {}
@@ -648,7 +665,11 @@ public:
             for (int k = 0; k < 4; k++) out[i].push_back(cv::Point2f(m[i].xy[2 * k], m[i].xy[2 * k + 1]));
         }
         if (n > 0 && camParams.isValid() && markerSizeMeters > 0) {
-            float cam[9]; camParams.cam9(cam);
+            // markerdetector_impl.cpp detect(input, markers, camParams, size, ...): "if (camParams.CamSize != input.size() && camParams.isValid() &&
+            // markerSizeMeters > 0) { cp_aux = camParams; cp_aux.resize(input.size()); ... }" - always taken in the reference, whose CamSize is the
+            // hard-coded 1280 x 720 of src/Frame.cc:132 whatever the camera delivers
+            const CameraParameters cp = (camParams.width > 0 && camParams.height > 0) ? camParams.resized(input.cols, input.rows) : camParams;
+            float cam[9]; cp.cam9(cam);
             std::vector<b200_marker_pose> p(n);
             b200slam_detail::check(b200_aruco_pose_host(m.data(), n, markerSizeMeters, cam, p.data(), device_));
             for (int i = 0; i < n; i++) out[i].setPose(p[i], markerSizeMeters);
@@ -665,6 +686,7 @@ private:
     }
     std::string dict_;
     b200_aruco_t h_; int w_, ht_, device_;
+    Params params_;
 };
 
 }  // namespace aruco

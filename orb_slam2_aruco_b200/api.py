@@ -564,6 +564,17 @@ class CameraParameters:
     def isValid(self):
         return self.CameraMatrix[0, 0] != 0 and self.CameraMatrix[1, 1] != 0
 
+    def resized(self, width, height):
+        """CameraParameters::resize(cv::Size) (cameraparameters.cpp:158-173) as a copy: float factors, fx cx scaled by the width ratio, fy cy by the height
+        ratio.  MarkerDetector::detect applies it whenever CamSize differs from the image (markerdetector_impl.cpp, detect(input, markers, camParams, ...)) -
+        always, in the reference, whose CamSize is the hard-coded 1280 x 720 of src/Frame.cc:132."""
+        if self.CamSize is None or tuple(self.CamSize) == (width, height):
+            return self
+        ax = np.float32(width) / np.float32(self.CamSize[0]); ay = np.float32(height) / np.float32(self.CamSize[1])
+        K = self.CameraMatrix.copy()
+        K[0, 0] *= ax; K[0, 2] *= ax; K[1, 1] *= ay; K[1, 2] *= ay
+        return CameraParameters(K, self.Distorsion, (width, height))
+
     def cam9(self):
         K = self.CameraMatrix
         return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2], *self.Distorsion], np.float32)
@@ -667,7 +678,7 @@ class MarkerDetector:
         m, c = self.detect_batch(image[None])
         out = [Marker(r["id"], r["xy"]) for r in m[0, :c[0]]]
         if camera_params is not None and camera_params.isValid() and marker_size > 0 and out:
-            poses = self.estimate_poses(m[0, :c[0]], marker_size, camera_params)
+            poses = self.estimate_poses(m[0, :c[0]], marker_size, camera_params.resized(image.shape[1], image.shape[0]))
             for mk, p in zip(out, poses):
                 mk.Rvec, mk.Tvec, mk.Rvec2, mk.Tvec2 = p["rvec"].copy(), p["tvec"].copy(), p["rvec2"].copy(), p["tvec2"].copy()
                 mk.err1, mk.err2, mk.ssize = float(p["err1"]), float(p["err2"]), float(marker_size)

@@ -22,8 +22,8 @@ int main(int argc, char** argv) {
         extractor(im, cv::Mat(), keys, desc);                             // Frame.cc:203
         aruco::MarkerDetector detector;
         detector.setDictionary(argv[4], 0.f);                             // Frame.cc:133
-        detector.setDetectionMode(aruco::MarkerDetector::DM_NORMAL);      // Frame.cc:134
-        detector.setCornerRefinementMethod(aruco::MarkerDetector::CORNER_LINES);
+        detector.setDetectionMode(aruco::DetectionMode::DM_NORMAL);       // Frame.cc:134, spelled as there
+        detector.getParameters().setCornerRefinementMethod(aruco::CornerRefinementMethod::CORNER_LINES);      // Frame.cc:135
         aruco::CameraParameters cam;                                      // Frame.cc:132: setParams(mK, mDistCoef, Size(1280,720))
         const float distortion[5] = {0.2624f, -0.9531f, -0.0054f, 0.0026f, 1.1633f};
         cam.setParams(517.3f, 516.5f, 318.6f, 255.3f, distortion, 5, 1280, 720);
@@ -106,6 +106,8 @@ int main(int argc, char** argv) {
         for (auto& m : markers) { fwrite(&m.id, 4, 1, o); for (auto& p : m) { fwrite(&p.x, 4, 1, o); fwrite(&p.y, 4, 1, o); } }
         fwrite(matches.data(), 4, matches.size(), o);
         for (auto& m : markers) { fwrite(m.Rvec, 4, 3, o); fwrite(m.Tvec, 4, 3, o); fwrite(&m.err1, 4, 1, o); fwrite(&m.err2, 4, 1, o); fwrite(&m.ssize, 4, 1, o); }
+        float cam_used[9]; cam.resized(w, h).cam9(cam_used);             // what detect() handed to the pose step (CameraParameters::resize, cameraparameters.cpp:158-173)
+        fwrite(cam_used, 4, 9, o);
         fclose(o);
         printf("levels=%d scale0=%g keys=%zu markers=%zu matches=%d\n", extractor.GetLevels(), extractor.GetScaleFactors()[1], keys.size(), markers.size(), nm);
     } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 1; }

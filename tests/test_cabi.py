@@ -88,3 +88,17 @@ def test_keyframe_side_entry_points_validate_and_refuse_without_gpu(built_lib):
     assert L.b200_match_kf_radius_host(p(z), p(zb), 1, p(z), p(z), p(zi), p(zb), 1, p(z), 8, C.c_double(5.99), p(zi), p(zi), 0) == _lib.ENODEV
     assert L.b200_kf_project_host(p(z), p(z), p(z), None, None, p(z), p(z), p(z), None, p(z), 1, 3.0, p(z), p(z), 8, p(zb), p(z), p(zi), 0) == _lib.ENODEV
     assert L.b200_match_for_triangulation_host(p(z), p(zb), 1, p(z), p(zb), 1, p(zi), p(zi), p(zi), p(zi), 1, p(z), p(z), p(z), p(z), 8, 1, 50, p(zi), 0) == _lib.ENODEV
+
+
+def test_camera_parameters_resize_like_the_reference():
+    """CameraParameters::resize (cameraparameters.cpp:158-173), applied by detect() whenever CamSize differs from the image - in the reference always,
+    its CamSize being the hard-coded 1280 x 720 of src/Frame.cc:132: float factors, fx cx by the width ratio, fy cy by the height ratio"""
+    from orb_slam2_aruco_b200.api import CameraParameters
+    cp = CameraParameters([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], [0.2624, -0.9531, -0.0054, 0.0026, 1.1633], (1280, 720))
+    r = cp.resized(640, 480)
+    ax, ay = np.float32(640) / np.float32(1280), np.float32(480) / np.float32(720)
+    assert r.CamSize == (640, 480) and cp.CamSize == (1280, 720)
+    assert r.cam9()[:4].tolist() == [np.float32(517.3) * ax, np.float32(516.5) * ay, np.float32(318.6) * ax, np.float32(255.3) * ay]
+    assert np.array_equal(r.cam9()[4:], cp.cam9()[4:])
+    assert cp.resized(1280, 720) is cp and r.resized(640, 480) is r
+    assert CameraParameters([[500, 0, 320], [0, 500, 240], [0, 0, 1]]).resized(64, 48).CamSize is None       # no CamSize: used as given
