@@ -610,6 +610,52 @@ public:
     }
 };
 
+// std::vector<std::pair<cv::Mat,double> > aruco::solvePnP(objPoints, imgPoints, cameraMatrix, distCoeffs) (ippe.h:14-15, ippe.cpp:72-88): both IPPE
+// solutions of one marker, smaller reprojection error first, as (4 x 4 [R | t] float, error).  src/Frame.cc:155-177 calls it per marker with the ORIGINAL
+// mK / mDistCoef (detect() itself used the camera resized to the image) and tests v2pose[0].second / v2pose[1].second < 0.7.
+// solvePnPSquare is the array form (marker side length, 4 image points, fx fy cx cy k1 k2 p1 p2 k3); poses row-major 4 x 4.
+struct PnPSolution { float T[16]; double error; };
+inline std::vector<PnPSolution> solvePnPSquare(float markerSize, const cv::Point2f imgPoints[4], const float cam9[9], int device = 0) {
+    b200_marker m; m.id = 0;
+    for (int k = 0; k < 4; k++) { m.xy[2 * k] = imgPoints[k].x; m.xy[2 * k + 1] = imgPoints[k].y; }
+    b200_marker_pose p;
+    b200slam_detail::check(b200_aruco_pose_host(&m, 1, markerSize, cam9, &p, device));
+    std::vector<PnPSolution> out(2);
+    for (int s = 0; s < 2; s++) {
+        const float* r = s ? p.rvec2 : p.rvec; const float* t = s ? p.tvec2 : p.tvec;
+        const double th = std::sqrt((double)r[0] * r[0] + (double)r[1] * r[1] + (double)r[2] * r[2]);      // Rodrigues (getRTMatrix, ippe.cpp:16-60)
+        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (th > 1e-12) {
+            const double x = r[0] / th, y = r[1] / th, z = r[2] / th, c = std::cos(th), sn = std::sin(th), c1 = 1 - c;
+            const double Rr[9] = {c + c1 * x * x, c1 * x * y - sn * z, c1 * x * z + sn * y, c1 * x * y + sn * z, c + c1 * y * y, c1 * y * z - sn * x,
+                                  c1 * x * z - sn * y, c1 * y * z + sn * x, c + c1 * z * z};
+            for (int i = 0; i < 9; i++) R[i] = Rr[i];
+        }
+        float* T = out[s].T;
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T[4 * i + j] = (float)R[3 * i + j]; T[4 * i + 3] = t[i]; }
+        T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+        out[s].error = s ? p.err2 : p.err1;
+    }
+    return out;
+}
+#ifndef B200SLAM_NO_OPENCV
+inline std::vector<std::pair<cv::Mat, double> > solvePnP(const std::vector<cv::Point3f>& objPoints, const std::vector<cv::Point2f>& imgPoints,
+                                                         const cv::Mat& cameraMatrix, const cv::Mat& distCoeffs) {
+    if (objPoints.size() != 4 || imgPoints.size() != 4) throw std::runtime_error("b200slam: aruco::solvePnP expects the 4 corners of one marker");
+    const float size = objPoints[1].x - objPoints[0].x;            // Marker::get3DPoints order (marker.cpp:358-366), as src/Frame.cc:157-160 builds it
+    if (!(size > 0) || objPoints[0].y != objPoints[1].y || objPoints[2].x != objPoints[1].x || objPoints[3].x != objPoints[0].x)
+        throw std::runtime_error("b200slam: aruco::solvePnP supports the canonical marker square only");
+    cv::Mat k32, d32;
+    cameraMatrix.convertTo(k32, CV_32F); distCoeffs.convertTo(d32, CV_32F);
+    float cam9[9] = {k32.at<float>(0, 0), k32.at<float>(1, 1), k32.at<float>(0, 2), k32.at<float>(1, 2), 0, 0, 0, 0, 0};
+    for (int i = 0; i < (int)d32.total() && i < 5; i++) cam9[4 + i] = d32.ptr<float>(0)[i];
+    const std::vector<PnPSolution> sol = solvePnPSquare(size, imgPoints.data(), cam9);
+    std::vector<std::pair<cv::Mat, double> > out;
+    for (size_t s = 0; s < sol.size(); s++) out.push_back(std::make_pair(cv::Mat(4, 4, CV_32F, (void*)sol[s].T).clone(), sol[s].error));
+    return out;
+}
+#endif
+
 enum DetectionMode : int { DM_NORMAL = 0, DM_FAST = 1, DM_VIDEO_FAST = 2 };                      // markerdetector.h:67 (namespace scope, as src/Frame.cc:134 spells it)
 enum CornerRefinementMethod : int { CORNER_SUBPIX = 0, CORNER_LINES = 1, CORNER_NONE = 2 };      // markerdetector.h:76
 

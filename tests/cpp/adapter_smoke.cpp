@@ -26,7 +26,8 @@ int main(int argc, char** argv) {
         detector.getParameters().setCornerRefinementMethod(aruco::CornerRefinementMethod::CORNER_LINES);      // Frame.cc:135
         aruco::CameraParameters cam;                                      // Frame.cc:132: setParams(mK, mDistCoef, Size(1280,720))
         const float distortion[5] = {0.2624f, -0.9531f, -0.0054f, 0.0026f, 1.1633f};
-        cam.setParams(517.3f, 516.5f, 318.6f, 255.3f, distortion, 5, 1280, 720);
+        // CamSize: the image size unless given (argv[6], argv[7]); src/Frame.cc:132 hard-codes 1280 x 720, which makes detect() resize the camera
+        cam.setParams(517.3f, 516.5f, 318.6f, 255.3f, distortion, 5, argc > 7 ? atoi(argv[6]) : w, argc > 7 ? atoi(argv[7]) : h);
         std::vector<aruco::Marker> markers = detector.detect(im, cam, 0.187f);   // Frame.cc:142 (mMarkerSize = 0.187, Frame.cc:131)
         ORB_SLAM2::ORBmatcher matcher(0.7f, true);                        // Tracking.cc:917
         std::vector<int> matches;
@@ -106,8 +107,19 @@ int main(int argc, char** argv) {
         for (auto& m : markers) { fwrite(&m.id, 4, 1, o); for (auto& p : m) { fwrite(&p.x, 4, 1, o); fwrite(&p.y, 4, 1, o); } }
         fwrite(matches.data(), 4, matches.size(), o);
         for (auto& m : markers) { fwrite(m.Rvec, 4, 3, o); fwrite(m.Tvec, 4, 3, o); fwrite(&m.err1, 4, 1, o); fwrite(&m.err2, 4, 1, o); fwrite(&m.ssize, 4, 1, o); }
+        // src/Frame.cc:155-177: aruco::solvePnP per marker with the ORIGINAL camera, the ratio of the two reprojection errors is the quality test
+        float cam_orig[9]; cam.cam9(cam_orig);
+        std::vector<float> errs;
+        for (auto& m : markers) {
+            const cv::Point2f c4[4] = {m[0], m[1], m[2], m[3]};
+            try {                                                        // judged by tests/test_zz_reference_replay_gpu.py, not here
+                const std::vector<aruco::PnPSolution> v2pose = aruco::solvePnPSquare(0.187f, c4, cam_orig);
+                errs.push_back((float)v2pose[0].error); errs.push_back((float)v2pose[1].error);
+            } catch (const std::exception&) { errs.push_back(-1.f); errs.push_back(-1.f); }
+        }
         float cam_used[9]; cam.resized(w, h).cam9(cam_used);             // what detect() handed to the pose step (CameraParameters::resize, cameraparameters.cpp:158-173)
         fwrite(cam_used, 4, 9, o);
+        fwrite(errs.data(), 4, errs.size(), o);
         fclose(o);
         printf("levels=%d scale0=%g keys=%zu markers=%zu matches=%d\n", extractor.GetLevels(), extractor.GetScaleFactors()[1], keys.size(), markers.size(), nm);
     } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 1; }

@@ -52,3 +52,71 @@ def test_keyframe_searches_with_distorted_image_bounds(built_lib, monkeypatch):
     got = M.SearchBySim3(c["k1"], c["d1"], c["T1"], c["st1"], c["p1"], c["d1"], c["mm1"], c["k2"], c["d2"], c["T2"], c["st2"], c["p2"], c["d2"], c["mm2"],
                          B, mc.CAM4, c["m12"], float(c["s12"]), c["R12"], c["t12"], 7.5)
     assert got[0] == want[0] and np.array_equal(got[1], want[1]) and got[0] > 100
+
+
+def test_adapter_solvepnp_with_the_original_camera(built_lib, tmp_path):
+    """src/Frame.cc:155-177 calls aruco::solvePnP(v3d, v2d, mK, mDistCoef) per marker with the ORIGINAL camera (detect() used the resized one) and tests
+    v2pose[0].second / v2pose[1].second < 0.7: the adapter's solvePnPSquare against the IPPE oracle for that camera"""
+    import ctypes as C
+    import subprocess
+    import oracle
+    from orb_slam2_aruco_b200 import synth
+    from test_adapters_gpu import build_adapter_smoke
+    exe = build_adapter_smoke(str(tmp_path))
+    img = synth.make_frame(31, markers=20)
+    raw = os.path.join(str(tmp_path), "f.raw"); out = os.path.join(str(tmp_path), "o.bin")
+    img.tofile(raw)
+    r = subprocess.run([exe, raw, "640", "480", "ARUCO_MIP_25h7", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    buf = open(out, "rb").read()
+    nk, nmk, nm, dist = np.frombuffer(buf[:16], np.int32)
+    o = 16 + 28 * nk + 32 * nk
+    mk = np.frombuffer(buf[o:o + 36 * nmk], oracle.MARKER_DTYPE)
+    o += 36 * nmk + 4 * nk + 36 * nmk + 36
+    errs = np.frombuffer(buf[o:o + 8 * nmk], np.float32).reshape(nmk, 2)
+    assert len(buf) == o + 8 * nmk and nmk >= 15
+    cam9 = np.array([np.float32(v) for v in (517.3, 516.5, 318.6, 255.3, 0.2624, -0.9531, -0.0054, 0.0026, 1.1633)], np.float64)
+    for i in range(nmk):
+        out14 = np.zeros(14)
+        oracle.lib().oracle_ippe_marker_pose(np.ascontiguousarray(mk["xy"][i]).ctypes.data_as(C.c_void_p), C.c_float(0.187),
+                                             cam9.ctypes.data_as(C.c_void_p), out14.ctypes.data_as(C.c_void_p))
+        e1, e2 = out14[6], out14[13]                                # rvec1 tvec1 err1 rvec2 tvec2 err2
+        assert abs(errs[i, 0] - e1) <= 1e-4 * max(1e-3, e2) and abs(errs[i, 1] - e2) <= 1e-4 * max(1e-3, e2)
+        if abs(e1 / e2 - 0.7) > 1e-3:
+            assert (errs[i, 0] / errs[i, 1] < 0.7) == (e1 / e2 < 0.7)
+
+
+def test_adapter_detect_resizes_the_camera_like_the_reference(built_lib, tmp_path):
+    """CamSize 1280 x 720 (src/Frame.cc:132) against a 640 x 480 frame: detect() resizes the camera (cameraparameters.cpp:158-173) before the pose step.
+    With that camera the two IPPE solutions often have almost equal reprojection errors on these frames, so a marker may come back with the solutions
+    in either order; each reported pose must be one of the oracle's two."""
+    import ctypes as C
+    import subprocess
+    import oracle
+    from orb_slam2_aruco_b200 import synth
+    from test_adapters_gpu import build_adapter_smoke
+    exe = build_adapter_smoke(str(tmp_path))
+    img = synth.make_frame(31, markers=20)
+    raw = os.path.join(str(tmp_path), "f.raw"); out = os.path.join(str(tmp_path), "o.bin")
+    img.tofile(raw)
+    r = subprocess.run([exe, raw, "640", "480", "ARUCO_MIP_25h7", out, "1280", "720"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    buf = open(out, "rb").read()
+    nk, nmk, nm, dist = np.frombuffer(buf[:16], np.int32)
+    o = 16 + 28 * nk + 32 * nk
+    mk = np.frombuffer(buf[o:o + 36 * nmk], oracle.MARKER_DTYPE); o += 36 * nmk + 4 * nk
+    poses = np.frombuffer(buf[o:o + 36 * nmk], np.float32).reshape(nmk, 9); o += 36 * nmk
+    cam_used = np.frombuffer(buf[o:o + 36], np.float32)
+    ax, ay = np.float32(640) / np.float32(1280), np.float32(480) / np.float32(720)
+    want_cam = np.array([np.float32(517.3) * ax, np.float32(516.5) * ay, np.float32(318.6) * ax, np.float32(255.3) * ay,
+                         0.2624, -0.9531, -0.0054, 0.0026, 1.1633], np.float32)
+    assert np.allclose(cam_used, want_cam, rtol=1e-6, atol=0)
+    cam9 = cam_used.astype(np.float64)
+    for i in range(nmk):
+        out14 = np.zeros(14)
+        oracle.lib().oracle_ippe_marker_pose(np.ascontiguousarray(mk["xy"][i]).ctypes.data_as(C.c_void_p), C.c_float(0.187),
+                                             cam9.ctypes.data_as(C.c_void_p), out14.ctypes.data_as(C.c_void_p))
+        first = np.abs(poses[i, :6] - out14[:6]).max() <= 1e-4 * max(1, np.abs(out14[:6]).max())
+        second = np.abs(poses[i, :6] - out14[7:13]).max() <= 1e-4 * max(1, np.abs(out14[7:13]).max())
+        tie = abs(out14[6] - out14[13]) <= 1e-3 * out14[13]
+        assert first or (tie and second), (i, poses[i, :6], out14)
