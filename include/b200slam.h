@@ -260,6 +260,10 @@ int b200_aruco_pose_host(const b200_marker* markers, int n_markers, float marker
  * cam9 = fx fy cx cy k1 k2 p1 p2 k3 (HOST).  k1 == 0 copies the keypoints like the reference. */
 int b200_frame_undistort(const b200_keypoint* kps, const int32_t* counts, int n_batch, int cap, const float* cam9,
                          b200_keypoint* kps_un, int device, void* stream);
+/* Frame::UndistortArucoCorners (src/Frame.cc:388-416): cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) over the 4 * NA marker corners of
+ * a frame - the same kernel as the keypoints.  xy / xy_un [n][2] HOST (may alias).  k1 == 0: the points are copied and no device is needed (the
+ * reference returns early and leaves mvArucoUn alone). */
+int b200_frame_undistort_points_host(const float* xy, int n, const float* cam9, float* xy_un, int device);
 /* Frame::ComputeImageBounds (src/Frame.cc:418-447): bounds4 = mnMinX mnMaxX mnMinY mnMaxY (HOST output). */
 int b200_frame_image_bounds(int width, int height, const float* cam9, float* bounds4, int device);
 /* Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:183-198, 332-343): the 64 x 48 grid of every frame as a CSR list,

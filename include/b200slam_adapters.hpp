@@ -610,6 +610,12 @@ public:
     }
 };
 
+// void Frame::UndistortArucoCorners() (src/Frame.cc:388-416) on what it reads and writes: the frame's markers and the camera -> mvArucoUn (4 * NA points,
+// marker-major).  Like the reference it leaves mvArucoUn untouched when k1 == 0.
+class CameraParameters;
+class Marker;
+inline void UndistortArucoCorners(const std::vector<Marker>& mvMarkers, const CameraParameters& cam, std::vector<cv::Point2f>& mvArucoUn, int device = 0);
+
 // std::vector<std::pair<cv::Mat,double> > aruco::solvePnP(objPoints, imgPoints, cameraMatrix, distCoeffs) (ippe.h:14-15, ippe.cpp:72-88): both IPPE
 // solutions of one marker, smaller reprojection error first, as (4 x 4 [R | t] float, error).  src/Frame.cc:155-177 calls it per marker with the ORIGINAL
 // mK / mDistCoef (detect() itself used the camera resized to the image) and tests v2pose[0].second / v2pose[1].second < 0.7.
@@ -658,6 +664,18 @@ inline std::vector<std::pair<cv::Mat, double> > solvePnP(const std::vector<cv::P
 
 enum DetectionMode : int { DM_NORMAL = 0, DM_FAST = 1, DM_VIDEO_FAST = 2 };                      // markerdetector.h:67 (namespace scope, as src/Frame.cc:134 spells it)
 enum CornerRefinementMethod : int { CORNER_SUBPIX = 0, CORNER_LINES = 1, CORNER_NONE = 2 };      // markerdetector.h:76
+
+inline void UndistortArucoCorners(const std::vector<Marker>& mvMarkers, const CameraParameters& cam, std::vector<cv::Point2f>& mvArucoUn, int device) {
+    if (cam.dist[0] == 0.0f) return;                               // src/Frame.cc:391-394
+    const int n = 4 * (int)mvMarkers.size();
+    std::vector<float> xy((size_t)2 * n + 2), un((size_t)2 * n + 2);
+    for (size_t i = 0; i < mvMarkers.size(); i++)
+        for (int j = 0; j < 4; j++) { xy[2 * (4 * i + j)] = mvMarkers[i][j].x; xy[2 * (4 * i + j) + 1] = mvMarkers[i][j].y; }
+    float cam9[9]; cam.cam9(cam9);
+    b200slam_detail::check(b200_frame_undistort_points_host(xy.data(), n, cam9, un.data(), device));
+    mvArucoUn.resize(n);
+    for (int i = 0; i < n; i++) mvArucoUn[i] = cv::Point2f(un[2 * i], un[2 * i + 1]);
+}
 
 class MarkerDetector {
 public:

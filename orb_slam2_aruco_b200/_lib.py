@@ -80,6 +80,7 @@ def lib():
         L.b200_voc_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
         L.b200_voc_transform_host.argtypes = [vp, vp, i32, i32, vp, vp, vp]
         L.b200_frame_undistort.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
+        L.b200_frame_undistort_points_host.argtypes = [vp, i32, vp, vp, i32]
         L.b200_frame_image_bounds.argtypes = [i32, i32, vp, vp, i32]
         L.b200_frame_assign_grid.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, vp]
         L.b200_frame_features_in_area.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]

@@ -793,6 +793,19 @@ class FrameGrid:
         s = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
         check(lib().b200_frame_undistort(ptr(kps), ptr(counts), B, cap, ptr(self.cam9), ptr(kps_un), self._device, s))
 
+    def undistort_aruco_corners(self, markers):
+        """Frame::UndistortArucoCorners (src/Frame.cc:388-416): the 4 * NA corners of a frame's markers (MARKER_DTYPE records or Marker objects) through
+        cv::undistortPoints(..., mK, mDistCoef, cv::Mat(), mK) on the device -> mvArucoUn as a [4 * NA, 2] float32 array.  With k1 == 0 the reference
+        returns before touching mvArucoUn; here the corners come back unchanged."""
+        if len(markers) and not isinstance(markers, np.ndarray):
+            xy = np.array([m.corners for m in markers], np.float32).reshape(-1, 2)
+        else:
+            xy = np.ascontiguousarray(np.asarray(markers)["xy"], np.float32).reshape(-1, 2) if len(markers) else np.zeros((0, 2), np.float32)
+        xy = np.ascontiguousarray(xy)
+        out = np.empty_like(xy)
+        check(lib().b200_frame_undistort_points_host(ptr(xy), len(xy), ptr(self.cam9), ptr(out), self._device))
+        return out
+
     def assign(self, kps_un, counts, cell_start, cell_items, stream=None):
         """cell_start [B][64*48+1], cell_items [B][cap] int32 on the device"""
         B, cap = int(kps_un.shape[0]), int(kps_un.shape[1])

@@ -181,6 +181,33 @@ int b200_frame_undistort(const b200_keypoint* kps, const int32_t* counts, int n_
     return B200_OK;
 }
 
+int b200_frame_undistort_points_host(const float* xy, int n, const float* cam9, float* xy_un, int device) {
+    if (n < 0) return fail(B200_EINVAL, "negative %s", "size");
+    FrameCam c;
+    int rc = make_cam(cam9, c);
+    if (rc) return rc;
+    if (n == 0) return B200_OK;
+    if (!xy || !xy_un) return fail(B200_EINVAL, "null %s", "pointer");
+    if (!c.distorted) { if (xy_un != xy) memcpy(xy_un, xy, (size_t)n * 8); return B200_OK; }      // mDistCoef.at<float>(0) == 0: the points as they are
+    if ((rc = use_device(device))) return rc;
+    std::vector<b200_keypoint> h((size_t)n);
+    memset(h.data(), 0, (size_t)n * sizeof(b200_keypoint));
+    for (int i = 0; i < n; i++) { h[i].x = xy[2 * i]; h[i].y = xy[2 * i + 1]; }
+    b200_keypoint* d = nullptr; int* dc = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, (size_t)n * sizeof(b200_keypoint));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), (size_t)n * sizeof(b200_keypoint), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc, &n, 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        B200_LAUNCH(k_undistort, (unsigned)((n + 255) / 256), 256, 0, 0, d, dc, 1, n, c, d);
+        e = cudaMemcpy(h.data(), d, (size_t)n * sizeof(b200_keypoint), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d); cudaFree(dc);
+    if (e != cudaSuccess) return fail(B200_ECUDA, "undistort points: %s", cudaGetErrorString(e));
+    for (int i = 0; i < n; i++) { xy_un[2 * i] = h[i].x; xy_un[2 * i + 1] = h[i].y; }
+    return B200_OK;
+}
+
 int b200_frame_image_bounds(int width, int height, const float* cam9, float* bounds4, int device) {
     if (!bounds4 || width < 1 || height < 1) return fail(B200_EINVAL, "bad %s", "arguments");
     FrameCam c;

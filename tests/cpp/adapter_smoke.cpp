@@ -117,9 +117,12 @@ int main(int argc, char** argv) {
                 errs.push_back((float)v2pose[0].error); errs.push_back((float)v2pose[1].error);
             } catch (const std::exception&) { errs.push_back(-1.f); errs.push_back(-1.f); }
         }
+        std::vector<cv::Point2f> arucoUn;                                // Frame.cc:149 UndistortArucoCorners(); checked in tests/test_zz_reference_replay_gpu.py
+        try { aruco::UndistortArucoCorners(markers, cam, arucoUn); } catch (const std::exception&) { arucoUn.clear(); }
         float cam_used[9]; cam.resized(w, h).cam9(cam_used);             // what detect() handed to the pose step (CameraParameters::resize, cameraparameters.cpp:158-173)
         fwrite(cam_used, 4, 9, o);
         fwrite(errs.data(), 4, errs.size(), o);
+        for (auto& p : arucoUn) { fwrite(&p.x, 4, 1, o); fwrite(&p.y, 4, 1, o); }
         fclose(o);
         printf("levels=%d scale0=%g keys=%zu markers=%zu matches=%d\n", extractor.GetLevels(), extractor.GetScaleFactors()[1], keys.size(), markers.size(), nm);
     } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 1; }

@@ -102,3 +102,18 @@ def test_camera_parameters_resize_like_the_reference():
     assert np.array_equal(r.cam9()[4:], cp.cam9()[4:])
     assert cp.resized(1280, 720) is cp and r.resized(640, 480) is r
     assert CameraParameters([[500, 0, 320], [0, 500, 240], [0, 0, 1]]).resized(64, 48).CamSize is None       # no CamSize: used as given
+
+
+def test_undistort_aruco_corners_without_distortion_needs_no_device(built_lib):
+    """Frame::UndistortArucoCorners (src/Frame.cc:388-416) returns early when k1 == 0: the corners are used as they are - no device involved; with
+    distortion the call needs the GPU like everything else"""
+    import torch
+    from orb_slam2_aruco_b200 import _lib
+    xy = np.arange(16, dtype=np.float32).reshape(8, 2) * 7.25
+    out = np.zeros_like(xy)
+    cam = np.array([500, 500, 320, 240, 0, 0, 0, 0, 0], np.float32)
+    assert built_lib.b200_frame_undistort_points_host(xy.ctypes.data, 8, cam.ctypes.data, out.ctypes.data, 0) == 0 and np.array_equal(out, xy)
+    assert built_lib.b200_frame_undistort_points_host(xy.ctypes.data, -1, cam.ctypes.data, out.ctypes.data, 0) == _lib.EINVAL
+    if not torch.cuda.is_available():
+        cam[4] = 0.1
+        assert built_lib.b200_frame_undistort_points_host(xy.ctypes.data, 8, cam.ctypes.data, out.ctypes.data, 0) == _lib.ENODEV

@@ -74,7 +74,15 @@ def test_adapter_solvepnp_with_the_original_camera(built_lib, tmp_path):
     mk = np.frombuffer(buf[o:o + 36 * nmk], oracle.MARKER_DTYPE)
     o += 36 * nmk + 4 * nk + 36 * nmk + 36
     errs = np.frombuffer(buf[o:o + 8 * nmk], np.float32).reshape(nmk, 2)
-    assert len(buf) == o + 8 * nmk and nmk >= 15
+    assert len(buf) >= o + 8 * nmk and nmk >= 15
+    # Frame::UndistortArucoCorners through the C++ adapter: the same bits as the oracle's cv::undistortPoints restatement
+    un = np.frombuffer(buf[o + 8 * nmk:], np.float32).reshape(-1, 2)
+    assert len(un) == 4 * nmk
+    kin = np.zeros(4 * nmk, oracle.KP_DTYPE); kin["x"] = mk["xy"].reshape(-1, 2)[:, 0]; kin["y"] = mk["xy"].reshape(-1, 2)[:, 1]
+    want_un = np.zeros(4 * nmk, oracle.KP_DTYPE)
+    cam64 = np.array([np.float32(v) for v in (517.3, 516.5, 318.6, 255.3, 0.2624, -0.9531, -0.0054, 0.0026, 1.1633)], np.float64)
+    oracle.lib().oracle_undistort_keypoints(kin.ctypes.data_as(C.c_void_p), len(kin), cam64.ctypes.data_as(C.c_void_p), want_un.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(un[:, 0].view(np.uint32), want_un["x"].view(np.uint32)) and np.array_equal(un[:, 1].view(np.uint32), want_un["y"].view(np.uint32))
     cam9 = np.array([np.float32(v) for v in (517.3, 516.5, 318.6, 255.3, 0.2624, -0.9531, -0.0054, 0.0026, 1.1633)], np.float64)
     for i in range(nmk):
         out14 = np.zeros(14)
@@ -120,3 +128,24 @@ def test_adapter_detect_resizes_the_camera_like_the_reference(built_lib, tmp_pat
         second = np.abs(poses[i, :6] - out14[7:13]).max() <= 1e-4 * max(1, np.abs(out14[7:13]).max())
         tie = abs(out14[6] - out14[13]) <= 1e-3 * out14[13]
         assert first or (tie and second), (i, poses[i, :6], out14)
+
+
+def test_undistort_aruco_corners_bit_exact(built_lib, golden_dir):
+    """Frame::UndistortArucoCorners (src/Frame.cc:388-416): the marker corners of a frame through the keypoint undistortion kernel, against the oracle
+    (cv::undistortPoints restatement, bit-exact against cv2 golden vectors)"""
+    import ctypes as C
+    import oracle
+    from orb_slam2_aruco_b200.api import CameraParameters, FrameGrid
+    g = np.load(os.path.join(golden_dir, "aruco_ref.npz"))
+    xy = np.ascontiguousarray(g["c0.xy"], np.float32).reshape(-1, 2)                  # the reference detector's corners of the first golden frame
+    cam = np.array([517.3, 516.5, 318.6, 255.3, 0.2624, -0.9531, -0.0054, 0.0026, 1.1633], np.float32)
+    fg = FrameGrid(640, 480, CameraParameters([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], cam[4:9]))
+    mk = np.zeros(len(xy) // 4, oracle.MARKER_DTYPE); mk["xy"] = xy.reshape(-1, 8)
+    got = fg.undistort_aruco_corners(mk)
+    kin = np.zeros(len(xy), oracle.KP_DTYPE); kin["x"] = xy[:, 0]; kin["y"] = xy[:, 1]
+    want = np.zeros(len(xy), oracle.KP_DTYPE)
+    cam64 = np.ascontiguousarray(cam, np.float64)
+    oracle.lib().oracle_undistort_keypoints(kin.ctypes.data_as(C.c_void_p), len(kin), cam64.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+    assert got.shape == xy.shape and len(xy) >= 60
+    assert np.array_equal(got[:, 0].view(np.uint32), want["x"].view(np.uint32)) and np.array_equal(got[:, 1].view(np.uint32), want["y"].view(np.uint32))
+    assert np.abs(got - xy).max() > 0.5                              # the distortion moves corners visibly
