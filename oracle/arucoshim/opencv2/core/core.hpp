@@ -101,6 +101,7 @@ public:
     Mat(Size s, int t) : rows(0), cols(0), step(0), data(nullptr), type_(0) { create(s.height, s.width, t); }
     Mat(int r, int c, int t, const Scalar& sc) : rows(0), cols(0), step(0), data(nullptr), type_(0) { create(r, c, t); setTo(sc); }
     void create(Size sz, int t) { create(sz.height, sz.width, t); }
+    Mat(const Mat& m, const Rect& r) : rows(r.height), cols(r.width), step(m.step), data(m.data + (size_t)r.y * m.step + (size_t)r.x * esz(m.type_)), type_(m.type_), buf_(m.buf_) {}
     Mat(int r, int c, int t, void* p, size_t st = 0) : rows(r), cols(c), step(st ? st : (size_t)c * esz(t)), data((uchar*)p), type_(t) {}
     static size_t esz(int t) { return t == CV_8UC1 ? 1 : t == CV_8UC3 ? 3 : t == CV_64F ? 8 : 4; }
     void create(int r, int c, int t) {
@@ -137,7 +138,21 @@ public:
         return *this;
     }
     // pose algebra (Marker::calculateExtrinsics, CameraParameters): declared so that marker.cpp compiles, never executed without camera parameters
-    void convertTo(Mat&, int) const { throw std::runtime_error("oracle/arucoshim: Mat::convertTo is not on the reference's configured path"); }
+    double get(int y, int x) const {
+        return type_ == CV_8UC1 ? (double)at<uchar>(y, x) : type_ == CV_32SC1 ? (double)at<int>(y, x) : type_ == CV_32FC1 ? (double)at<float>(y, x) : at<double>(y, x);
+    }
+    void convertTo(Mat& dst, int t) const {                        // single-channel cast (CameraParameters::setParams, cameraparameters.cpp:84,90)
+        Mat out(rows, cols, t);
+        for (int y = 0; y < rows; y++)
+            for (int x = 0; x < cols; x++) {
+                const double v = get(y, x);
+                if (t == CV_32FC1) out.at<float>(y, x) = (float)v; else if (t == CV_64F) out.at<double>(y, x) = v;
+                else if (t == CV_32SC1) out.at<int>(y, x) = (int)std::lrint(v); else if (t == CV_8UC1) out.at<uchar>(y, x) = (uchar)std::min(255.0, std::max(0.0, std::nearbyint(v)));
+                else throw std::runtime_error("oracle/arucoshim: Mat::convertTo: type");
+            }
+        dst = out;
+    }
+    int depth() const { return type_; }
     static Mat eye(int, int, int) { throw std::runtime_error("oracle/arucoshim: Mat::eye is not on the reference's configured path"); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * esz(type_); m.cols = b - a; return m; }
@@ -253,6 +268,7 @@ static inline void warpPerspective(const Mat& src, Mat& dst, const Mat& M, Size 
     cvprim::warp_perspective_linear(src.data, src.cols, src.rows, src.step, out.data, dsize.width, dsize.height, out.step, M.ptr<double>(0));
     dst = out;
 }
+static inline int countNonZero(const Mat& m) { int n = 0; for (int y = 0; y < m.rows; y++) for (int x = 0; x < m.cols; x++) n += m.get(y, x) != 0; return n; }
 static inline void minMaxIdx(const Mat& m, double* mn, double* mx) {
     double a = 255, b = 0;
     for (int y = 0; y < m.rows; y++) for (int x = 0; x < m.cols; x++) { const double v = m.at<uchar>(y, x); if (v < a) a = v; if (v > b) b = v; }

@@ -5,8 +5,9 @@
 // statement; the OpenCV primitives it calls (adaptiveThreshold, findContours, approxPolyDP, isContourConvex, resize, getPerspectiveTransform,
 // warpPerspective, threshold, solve) are the cv2-pinned restatements of oracle/cvprim_aruco.h.  Configured exactly as src/Frame.cc:133-139 does.
 // Pins oracle/aruco_oracle.cpp (tests/test_oracle_aruco_vs_ref.py, tests/golden/aruco_ref.npz).
-// cameraparameters.cpp and ippe.cpp (pose algebra: Rodrigues, inv, SVD) are not compiled: detect() runs without camera parameters here, as the pose is a
-// separate row of the scope table (oracle/ippe_oracle.cpp, pinned to cv2's IPPE); the few members the linked sources name are defined below.
+// cameraparameters.cpp is compiled too (CameraParameters::setParams / resize are the reference's).  ippe.cpp (pose algebra: Rodrigues, inv, SVD) is not:
+// detect() runs without camera parameters here, the pose is a separate row of the scope table (oracle/ippe_oracle.cpp, pinned to cv2's IPPE); the few
+// members the linked sources name are defined below.
 #include <atomic>
 #include <thread>
 #include "cameraparameters.h"
@@ -16,9 +17,6 @@
 #include "../oracle.h"
 
 namespace aruco {
-CameraParameters::CameraParameters() {}
-CameraParameters::CameraParameters(const CameraParameters& CI) : CameraMatrix(CI.CameraMatrix), Distorsion(CI.Distorsion), CamSize(CI.CamSize) {}
-void CameraParameters::resize(cv::Size) { throw std::runtime_error("CameraParameters::resize is not part of the stand-in (detect runs without camera parameters)"); }
 void solvePnP(const std::vector<cv::Point3f>&, const std::vector<cv::Point2f>&, cv::InputArray, cv::InputArray, cv::Mat&, cv::Mat&) {
     throw std::runtime_error("aruco::solvePnP (ippe.cpp) is not part of the stand-in");
 }
@@ -72,6 +70,20 @@ int ref_aruco_detect_batch(const uint8_t* imgs, int n, int w, int h, int row_str
     work();
     for (auto& t : pool) t.join();
     return 0;
+}
+
+// CameraParameters(K, D, Size(cam_w, cam_h)) then resize(Size(w, h)) (cameraparameters.cpp:50-54, 75-95, 158-173) - what MarkerDetector::detect does to the
+// camera whenever CamSize differs from the image.  cam4 = fx fy cx cy in / out.
+int ref_camera_resize(const float* cam4, const float* dist5, int cam_w, int cam_h, int w, int h, float* cam4_out) {
+    cv::Mat K = cv::Mat::zeros(3, 3, CV_32FC1), D(1, 5, CV_32FC1);
+    K.at<float>(0, 0) = cam4[0]; K.at<float>(1, 1) = cam4[1]; K.at<float>(0, 2) = cam4[2]; K.at<float>(1, 2) = cam4[3]; K.at<float>(2, 2) = 1.f;
+    for (int i = 0; i < 5; i++) D.at<float>(0, i) = dist5[i];
+    aruco::CameraParameters cp(K, D, cv::Size(cam_w, cam_h));
+    aruco::CameraParameters aux = cp;                              // as detect(): CameraParameters cp_aux = camParams; cp_aux.resize(input.size());
+    aux.resize(cv::Size(w, h));
+    cam4_out[0] = aux.CameraMatrix.at<float>(0, 0); cam4_out[1] = aux.CameraMatrix.at<float>(1, 1);
+    cam4_out[2] = aux.CameraMatrix.at<float>(0, 2); cam4_out[3] = aux.CameraMatrix.at<float>(1, 2);
+    return aux.CamSize.width == w && aux.CamSize.height == h && cp.CamSize.width == cam_w ? 0 : -1;
 }
 
 }  // extern "C"

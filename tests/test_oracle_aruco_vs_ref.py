@@ -65,3 +65,22 @@ def test_live_reference_sweep():
         assert np.array_equal(a["id"], b["id"]) and np.array_equal(a["xy"].view(np.uint32), b["xy"].view(np.uint32)), (seed, w, h, dn)
         n += len(a)
     assert n > 500
+
+
+@pytest.mark.skipif(oracle.ref_aruco() is None, reason="oracle/_ref/libref_aruco.so not built (needs /root/reference)")
+def test_camera_resize_equals_the_reference_s_cameraparameters():
+    """CameraParameters::setParams + resize of the reference's own cameraparameters.cpp (what MarkerDetector::detect applies when CamSize differs from the
+    image) against the adapters' CameraParameters.resized: identical float bits"""
+    import ctypes as C
+    from orb_slam2_aruco_b200.api import CameraParameters
+    R = oracle.ref_aruco()
+    rng = np.random.default_rng(3)
+    for cam_size, size in (((1280, 720), (640, 480)), ((1280, 720), (1920, 1080)), ((640, 480), (1280, 720)), ((1280, 720), (1280, 720)), ((1000, 750), (333, 257))):
+        for _ in range(20):
+            cam = np.array([rng.uniform(300, 900), rng.uniform(300, 900), rng.uniform(200, 700), rng.uniform(100, 500)], np.float32)
+            d = rng.normal(0, 0.3, 5).astype(np.float32)
+            out = np.zeros(4, np.float32)
+            assert R.ref_camera_resize(cam.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), cam_size[0], cam_size[1], size[0], size[1],
+                                       out.ctypes.data_as(C.c_void_p)) == 0
+            cp = CameraParameters([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], d, cam_size).resized(*size)
+            assert np.array_equal(cp.cam9()[:4].view(np.uint32), out.view(np.uint32)) and np.array_equal(cp.cam9()[4:], d)
