@@ -684,6 +684,28 @@ class MarkerDetector:
                 mk.err1, mk.err2, mk.ssize = float(p["err1"]), float(p["err2"]), float(marker_size)
         return out
 
+    @staticmethod
+    def rt_matrix(rvec, tvec):
+        """getRTMatrix(Rvec, Tvec, CV_32F) (ippe.cpp:16-60): 4 x 4 [R | t] from a Rodrigues vector and a translation"""
+        r = np.asarray(rvec, np.float64).reshape(3); th = float(np.sqrt((r * r).sum()))
+        R = np.eye(3)
+        if th > 1e-12:
+            k = r / th
+            K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+            R = np.cos(th) * np.eye(3) + (1 - np.cos(th)) * np.outer(k, k) + np.sin(th) * K
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = R.astype(np.float32); T[:3, 3] = np.asarray(tvec, np.float32).reshape(3)
+        return T
+
+    def solvePnP(self, marker_size, img_points, camera_params):
+        """aruco::solvePnP(objPoints, imgPoints, cameraMatrix, distCoeffs) (ippe.h:14-15, ippe.cpp:72-88) for the canonical marker square of side
+        marker_size: [(T1, err1), (T2, err2)], the solution of smaller reprojection error first.  src/Frame.cc:155-177 calls it per marker with the
+        ORIGINAL mK / mDistCoef (detect() used the camera resized to the image) and tests err1 / err2 < 0.7."""
+        mk = np.zeros(1, MARKER_DTYPE)
+        mk["xy"][0] = np.asarray(img_points, np.float32).reshape(8)
+        p = self.estimate_poses(mk, marker_size, camera_params)[0]
+        return [(self.rt_matrix(p["rvec"], p["tvec"]), float(p["err1"])), (self.rt_matrix(p["rvec2"], p["tvec2"]), float(p["err2"]))]
+
     def estimate_poses(self, markers, marker_size, camera_params):
         """both IPPE poses + reprojection errors of an array of markers (aruco::solvePnP, ippe.cpp:72-88; the ratio
         err1 / err2 < 0.7 is the reference's test for a good marker, src/Frame.cc:172-174)"""

@@ -117,3 +117,16 @@ def test_undistort_aruco_corners_without_distortion_needs_no_device(built_lib):
     if not torch.cuda.is_available():
         cam[4] = 0.1
         assert built_lib.b200_frame_undistort_points_host(xy.ctypes.data, 8, cam.ctypes.data, out.ctypes.data, 0) == _lib.ENODEV
+
+
+def test_rt_matrix_equals_cv2_rodrigues():
+    """the 4 x 4 pose matrices aruco::solvePnP returns (getRTMatrix, ippe.cpp:16-60) are built on the host from the device's Rodrigues vectors"""
+    cv2 = pytest.importorskip("cv2")
+    from orb_slam2_aruco_b200.api import MarkerDetector
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        r = rng.normal(0, 1.5, 3); t = rng.normal(0, 2, 3)
+        T = MarkerDetector.rt_matrix(r, t)
+        R, _ = cv2.Rodrigues(r.reshape(3, 1))
+        assert T.dtype == np.float32 and np.abs(T[:3, :3] - R).max() < 1e-6 and np.array_equal(T[:3, 3], t.astype(np.float32)) and T[3].tolist() == [0, 0, 0, 1]
+    assert np.array_equal(MarkerDetector.rt_matrix(np.zeros(3), np.zeros(3)), np.eye(4, dtype=np.float32))
