@@ -463,6 +463,24 @@ protected:
 
 namespace ORB_SLAM2 {
 
+// Frame::UndistortKeyPoints (src/Frame.cc:357-388) and Frame::ComputeImageBounds (src/Frame.cc:418-447) on what they read and write; cam9 = fx fy cx cy
+// k1 k2 p1 p2 k3 (mK and mDistCoef).  With k1 == 0 the keypoints are copied / the bounds are the image rectangle, like the reference.  (The grid itself,
+// AssignFeaturesToGrid + GetFeaturesInArea, lives on the device behind the matcher entry points and b200_frame_assign_grid / b200_frame_features_in_area.)
+inline void UndistortKeyPoints(const std::vector<cv::KeyPoint>& mvKeys, const float cam9[9], std::vector<cv::KeyPoint>& mvKeysUn, int device = 0) {
+    const int n = (int)mvKeys.size();
+    mvKeysUn = mvKeys;                                             // size, angle, response, octave are kept (Frame.cc:383-387)
+    if (n == 0 || cam9[4] == 0.0f) return;
+    std::vector<float> xy((size_t)2 * n), un((size_t)2 * n);
+    for (int i = 0; i < n; i++) { xy[2 * i] = mvKeys[i].pt.x; xy[2 * i + 1] = mvKeys[i].pt.y; }
+    b200slam_detail::check(b200_frame_undistort_points_host(xy.data(), n, cam9, un.data(), device));
+    for (int i = 0; i < n; i++) { mvKeysUn[i].pt.x = un[2 * i]; mvKeysUn[i].pt.y = un[2 * i + 1]; }
+}
+inline void ComputeImageBounds(int width, int height, const float cam9[9], float& mnMinX, float& mnMaxX, float& mnMinY, float& mnMaxY, int device = 0) {
+    float b[4];
+    b200slam_detail::check(b200_frame_image_bounds(width, height, cam9, b, device));
+    mnMinX = b[0]; mnMaxX = b[1]; mnMinY = b[2]; mnMaxY = b[3];
+}
+
 // ORB_SLAM2::ORBVocabulary (include/ORBVocabulary.h:31 = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>): the two calls the reference
 // makes, loadFromTextFile (System.cc:80) and transform(features, BowVector, FeatureVector, 4) (Frame.cc:353, KeyFrame.cc ComputeBoW).
 // The per-descriptor tree descent runs on the device (b200_voc_transform); the two std::maps are assembled from its output arrays

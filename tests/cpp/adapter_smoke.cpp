@@ -117,6 +117,16 @@ int main(int argc, char** argv) {
                 errs.push_back((float)v2pose[0].error); errs.push_back((float)v2pose[1].error);
             } catch (const std::exception&) { errs.push_back(-1.f); errs.push_back(-1.f); }
         }
+        {   // Frame::ComputeImageBounds / UndistortKeyPoints through the adapters: without distortion the image rectangle and the keypoints themselves
+            const float pinhole[9] = {517.3f, 516.5f, 318.6f, 255.3f, 0, 0, 0, 0, 0};
+            float x0, x1, y0, y1;
+            ORB_SLAM2::ComputeImageBounds(w, h, pinhole, x0, x1, y0, y1);
+            std::vector<cv::KeyPoint> un;
+            ORB_SLAM2::UndistortKeyPoints(keys, pinhole, un);
+            if (x0 != 0.f || x1 != (float)w || y0 != 0.f || y1 != (float)h || un.size() != keys.size() || (keys.size() && un[0].pt.x != keys[0].pt.x)) {
+                fprintf(stderr, "ComputeImageBounds / UndistortKeyPoints without distortion\n"); return 1;
+            }
+        }
         std::vector<cv::Point2f> arucoUn;                                // Frame.cc:149 UndistortArucoCorners(); checked in tests/test_zz_reference_replay_gpu.py
         try { aruco::UndistortArucoCorners(markers, cam, arucoUn); } catch (const std::exception&) { arucoUn.clear(); }
         float cam_used[9]; cam.resized(w, h).cam9(cam_used);             // what detect() handed to the pose step (CameraParameters::resize, cameraparameters.cpp:158-173)
