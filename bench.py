@@ -3,6 +3,11 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C3|C2]
 
+The ONE JSON line carries the C3 headline (below) and, under `extra_workloads`, the other configurations of BASELINE.json measured in the same
+process: C1 (single-frame latency through the C++ adapters; N=1 only), C4 and C5 (per-GPU shards of configs[3] / [4], at every N), and a
+match-rich C3 variant (every frame a perturbed view of the reference scene).  At N>1 rank 0 checks the COLLATED buffers of other ranks' frames
+against the CPU oracle after the timed loop and refuses to print a line on a mismatch.
+
 A "step" is one pass of the hot path over one batch of synthetic frames:
   C3 (default; BASELINE.json configs[2], the configuration the metric "frames/sec (extract+aruco+match)" names):
      batch=256 640x480, ORB extract (1000 features, 8 levels) + ArUco detect (ARUCO_MIP_25h7, 20 planted markers)
@@ -41,11 +46,15 @@ WORKLOADS = {
                     "+ brute-force match vs 1000-descriptor reference set",
                metric="frames/sec (extract+aruco+match)", batch=256, w=640, h=480, nfeatures=1000, markers=20, match=True),
 }
-WORKLOADS["C4"] = dict(name="C4: 256 of the 2048 synthetic 1280x720 frames per GPU, extract (2000 feat, 8 levels) + ArUco (ARUCO_MIP_25h7, 20 markers/frame) "
-                            "+ brute-force match vs 1000-descriptor reference set",
+WORKLOADS["C4"] = dict(name="C4: 256 of the 2048 synthetic 1280x720 frames per GPU (the 8-GPU shard of BASELINE configs[3]), extract (2000 feat, 8 levels) + ArUco "
+                            "(ARUCO_MIP_25h7, 20 markers/frame) + brute-force match vs 1000-descriptor reference set",
                        metric="frames/sec (extract+aruco+match)", batch=256, w=1280, h=720, nfeatures=2000, markers=20, match=True, frames_distinct=32)
-WORKLOADS["C5"] = dict(name="C5: 128 of the 8192 synthetic 1920x1080 frames per GPU, extract (4000 feat, 8 levels) + ArUco + brute-force match",
-                       metric="frames/sec (extract+aruco+match)", batch=128, w=1920, h=1080, nfeatures=4000, markers=20, match=True, frames_distinct=16)
+WORKLOADS["C5"] = dict(name="C5: 1024 of the 8192 synthetic 1920x1080 frames per GPU (the 8-GPU shard of BASELINE configs[4]) in 8 sub-batches of 128, extract "
+                            "(4000 feat, 8 levels) + ArUco + brute-force match",
+                       metric="frames/sec (extract+aruco+match)", batch=128, sub=8, w=1920, h=1080, nfeatures=4000, markers=20, match=True, frames_distinct=16)
+WORKLOADS["C3R"] = dict(name="C3 match-rich: batch=256 640x480, every frame a perturbed view (rotation <= 3 deg, shift <= 8 px, fresh noise) of the scene the "
+                             "1000-descriptor reference set comes from (~300 matches per frame instead of ~10), extract + ArUco + brute-force match",
+                        metric="frames/sec (extract+aruco+match)", batch=256, w=640, h=480, nfeatures=1000, markers=20, match=True, views=True)
 SIGMA_P = {(640, 480): 950532, (1280, 720): 2853088, (1920, 1080): 6419321}      # pixels over the 8 ORB levels
 
 
@@ -53,14 +62,18 @@ def frames_for(wl, rank, batch=None):
     """deterministic synthetic frames; cached under /tmp because numpy generation takes ~50-150 ms per frame"""
     from orb_slam2_aruco_b200 import synth
     n = batch or wl["batch"]
-    path = "/tmp/b200_frames_v2_%dx%d_m%d_r%d_n%d.npy" % (wl["w"], wl["h"], wl["markers"], rank, n)
+    path = "/tmp/b200_frames_v3_%dx%d_m%d_r%d_n%d%s.npy" % (wl["w"], wl["h"], wl["markers"], rank, n, "_views" if wl.get("views") else "")
     if os.path.exists(path):
         try:
             return np.load(path)
         except Exception:
             pass
     distinct = min(n, wl.get("frames_distinct", n))          # the large workloads repeat a few distinct frames (numpy generation is slow)
-    imgs = synth.make_batch(distinct, wl["w"], wl["h"], wl["markers"], DICT, first=rank * 100000)
+    if wl.get("views"):
+        scene = synth.make_frame(0, wl["w"], wl["h"], wl["markers"], DICT)
+        imgs = np.stack([synth.make_view(scene, rank * 100000 + i) for i in range(distinct)])
+    else:
+        imgs = synth.make_batch(distinct, wl["w"], wl["h"], wl["markers"], DICT, first=rank * 100000)
     if distinct < n:
         imgs = np.concatenate([imgs] * ((n + distinct - 1) // distinct))[:n]
     try:
@@ -71,9 +84,9 @@ def frames_for(wl, rank, batch=None):
 
 
 def reference_scene(wl):
-    """the frame the match reference set is extracted from: frame 0's scene shifted by (5, 3) px"""
+    """the frame the match reference set is extracted from: frame 0's scene shifted by (5, 3) px and rotated by 3 degrees"""
     from orb_slam2_aruco_b200 import synth
-    return np.roll(synth.make_frame(0, wl["w"], wl["h"], wl["markers"], DICT), (3, 5), axis=(0, 1))
+    return synth.make_view(synth.make_frame(0, wl["w"], wl["h"], wl["markers"], DICT), 0, rot_deg=3.0, shift=(5.0, 3.0), noise_sigma=0.0)
 
 
 class ClockSampler(threading.Thread):
@@ -162,7 +175,7 @@ def ncu_traffic(kernel, wl, batch):
     return None
 
 
-def cpu_reference_run(imgs, wl, nthreads, ref_set=None):
+def cpu_reference_run(imgs, wl, nthreads, ref_set=None, DICT=DICT):
     """the reference CPU path on `imgs` with nthreads threads; returns (seconds, kind, description)"""
     import oracle
     n, h, w = imgs.shape
@@ -244,6 +257,294 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+class Ctx:
+    pass
+
+
+class Workload:
+    """handles, resident inputs, packed result slots and streams of one workload on this rank"""
+
+    def __init__(self, ctx, wl):
+        import torch
+        from orb_slam2_aruco_b200 import shard
+        from orb_slam2_aruco_b200.api import MarkerDetector, ORBextractor, ORBmatcher
+        self.ctx, self.wl = ctx, wl
+        dev, local, rank, world = ctx.dev, ctx.local, ctx.rank, ctx.world
+        self.B, self.W, self.H, self.nsub = wl["batch"], wl["w"], wl["h"], wl.get("sub", 1)
+        B = self.B
+        self.imgs_np = frames_for(wl, rank)                            # one sub-batch worth of distinct host frames
+        self.ex = ORBextractor(wl["nfeatures"], 1.2, 8, 20, 7, self.W, self.H, B, device=local)
+        self.det = MarkerDetector(DICT, self.W, self.H, B, device=local) if wl["markers"] else None
+        self.matcher = ORBmatcher(0.7, True, device=local) if wl["match"] else None
+        self.cap, self.mcap = self.ex.cap, (self.det.cap if self.det else 0)
+        one = torch.from_numpy(self.imgs_np).to(dev)
+        # all frames of a step resident in HBM: nsub sub-batches (C5: 8 x 128 frames = 2.1 GB; the 16 distinct frames repeat)
+        self.d_imgs = one if self.nsub == 1 else one.unsqueeze(0).repeat(self.nsub, 1, 1, 1).reshape(self.nsub * B, self.H, self.W).contiguous()
+        self.pack = shard.SlotPack(B, self.cap, max(self.mcap, 1), device=dev, detector=self.det is not None, matcher=self.matcher is not None)
+        self.v = self.pack.views
+        self.ref_np = None
+        if wl["match"]:          # reference set for the matcher: <= 1000 descriptors of the reference scene, extracted with the CUDA extractor
+            rk, rd = self.ex(reference_scene(wl))
+            self.ref_np = (np.ascontiguousarray(rd[:1000]), np.ascontiguousarray(rk[:1000]))
+            self.d_rdesc = torch.from_numpy(self.ref_np[0]).to(dev)
+            self.d_rkps = torch.from_numpy(self.ref_np[1].view(np.uint8).reshape(-1, 28).copy()).to(dev)
+            self.n_ref = len(self.ref_np[0])
+        prio = [int(v) for v in os.environ.get("B200_BENCH_PRIO", "0,-1").split(",")]      # detector stream at high priority (latency-bound kernels start early)
+        self.s_main = torch.cuda.Stream(device=dev, priority=prio[0])
+        self.s_aux = torch.cuda.Stream(device=dev, priority=prio[1])
+        self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
+        self.ev_fork, self.ev_join, self.ev_bulk, self.ev_tail, self.ev_done = (torch.cuda.Event() for _ in range(5))
+        self.coll_bulk = self.coll_tail = None
+        if world > 1 and rank == 0:      # the consumer's receive buffers: [sub-batch][rank][bytes]
+            self.coll_bulk = torch.zeros((self.nsub, world, self.pack.bulk_bytes), dtype=torch.uint8, device=dev)
+            self.coll_tail = torch.zeros((self.nsub, world, self.pack.total_bytes - self.pack.bulk_bytes), dtype=torch.uint8, device=dev)
+
+    def step(self):
+        ctx, v = self.ctx, self.v
+        for sub in range(self.nsub):
+            imgs = self.d_imgs[sub * self.B:(sub + 1) * self.B]
+            if self.det is not None:                      # detector on its own stream, concurrently with extractor + matcher
+                self.ev_fork.record(self.s_main)
+                self.s_aux.wait_event(self.ev_fork)
+                self.det.detect_batch_device(imgs, v["markers"], v["marker_counts"], self.s_aux)
+                self.ev_join.record(self.s_aux)
+            self.ex.extract_batch_device(imgs, v["kps"], v["desc"], v["counts"], self.s_main)
+            if ctx.world > 1:                             # bulk (keypoints + descriptors + counts) leaves for rank 0 while the matcher runs
+                self.ev_bulk.record(self.s_main)
+                self.s_comm.wait_event(self.ev_bulk)
+                ctx.collator.gather([self.pack.bulk], [self.coll_bulk[sub]] if ctx.rank == 0 else None, 0, self.s_comm)
+            if self.matcher is not None:
+                self.matcher.SearchByBoW_device(self.d_rdesc, self.d_rkps, self.n_ref, v["desc"], v["kps"], v["counts"], v["matches"], v["n_matches"], self.s_main)
+            if self.det is not None:
+                self.s_main.wait_event(self.ev_join)
+            if ctx.world > 1:                             # tail (markers + matches) after the join; the step ends when both transfers have landed
+                self.ev_tail.record(self.s_main)
+                self.s_comm.wait_event(self.ev_tail)
+                ctx.collator.gather([self.pack.tail], [self.coll_tail[sub]] if ctx.rank == 0 else None, 0, self.s_comm)
+                self.ev_done.record(self.s_comm)
+                self.s_main.wait_event(self.ev_done)
+
+    def totals(self):
+        v = self.v
+        nkp = int(v["counts"].sum().item())
+        nmk = int(v["marker_counts"].sum().item()) if self.det else 0
+        nmatch = int(v["n_matches"].sum().item()) if self.matcher else 0
+        return nkp, nmk, nmatch
+
+
+def sync_all(ctx):
+    import torch
+    torch.cuda.synchronize(ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        torch.cuda.synchronize(ctx.dev)
+
+
+def max_over_ranks(ctx, values):
+    import torch
+    t = torch.tensor(values, dtype=torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def timed_resident(ctx, wk, steps, warmup, profile=False):
+    """W untimed warm-up steps, then exactly `steps` steps, each bracketed by CUDA events on the launching stream with an untimed L2 flush in
+    front; barrier + synchronize on both sides; returns (sum of event ms on this rank, launches, extractor stage ms, frames of the stage launch)"""
+    import torch
+    from orb_slam2_aruco_b200 import _lib
+    for _ in range(warmup):
+        wk.step()
+    sync_all(ctx)
+    if profile:
+        wk.ex.set_profile(True)
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stage, stage_frames = np.zeros(4, np.float64), 0
+    sync_all(ctx)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        with torch.cuda.stream(wk.s_main):
+            ctx.flush.fill_(i & 0xff)          # evict the batch from L2 (not timed)
+            ev[i][0].record(wk.s_main)
+        wk.step()
+        ev[i][1].record(wk.s_main)
+        wk.s_main.synchronize()
+        if profile:
+            stage += wk.ex.stage_ms()
+            stage_frames = wk.ex.stage_frames()
+    sync_all(ctx)
+    wall = time.perf_counter() - t0
+    launches = _lib.launch_count() - launches0
+    if profile:
+        wk.ex.set_profile(False)
+    return float(sum(a.elapsed_time(b) for a, b in ev)), int(launches), stage, stage_frames, wall
+
+
+def timed_e2e(ctx, wk, steps):
+    """the reference-facing host API: pinned host frames in, pinned host results out (b200_frontend_host), and at N > 1 the collation of every
+    rank's results into rank 0's HOST buffers (b200_frontend_collate_host) - all inside the timed region.  Returns (seconds, h2d, d2h bytes/step)."""
+    import torch
+    from orb_slam2_aruco_b200.api import FrontEnd
+    fe = FrontEnd(wk.ex, wk.det, wk.matcher)
+    B = wk.B
+    h_imgs = torch.from_numpy(wk.imgs_np).pin_memory()
+    out = fe.alloc_outputs(B, pinned=True)
+    root_out = fe.alloc_outputs(B * ctx.world, pinned=True) if ctx.world > 1 and ctx.rank == 0 else None
+    rd, rk = wk.ref_np if wk.ref_np else (None, None)
+
+    def one():
+        for _ in range(wk.nsub):
+            fe.process_batch(h_imgs.numpy(), rd, rk, out=out)
+            if ctx.world > 1:
+                fe.collate_host(ctx.collator, root_out, 0)
+    for _ in range(2):
+        one()
+    sync_all(ctx)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize(ctx.dev)
+    secs = time.perf_counter() - t0
+    nkp = wk.totals()[0]
+    assert int(out["counts"].sum()) == nkp, "host path and device path disagree"
+    if root_out is not None:
+        assert int(root_out["counts"][:B].sum()) == nkp, "collated host buffers do not start with rank 0's results"
+    cap, mcap = wk.cap, wk.mcap
+    d2h = B * cap * 60 + B * 4 + (B * mcap * 36 + B * 4 if wk.det else 0) + (B * cap * 4 + B * 4 if wk.matcher else 0)
+    return secs, int(B * wk.W * wk.H) * wk.nsub, int(d2h) * wk.nsub * (ctx.world if ctx.rank == 0 and ctx.world > 1 else 1)
+
+
+def check_collated(ctx, wk):
+    """N > 1, after the timed loop: what rank 0 RECEIVED is compared (1) byte-for-byte checksums of every rank's packed slots, (2) with the CPU
+    oracle on sample frames of OTHER ranks (keypoints, descriptor bits, marker ids / corners, match indices).  Raises on any mismatch: no
+    bench line is printed for a collation that delivers wrong data."""
+    import torch
+    dist = ctx.dist
+    sub = wk.nsub - 1                                            # the pack holds the last sub-batch of the last step
+    mine = torch.stack([wk.pack.bulk.to(torch.int64).sum(), wk.pack.tail.to(torch.int64).sum()])
+    sums = [torch.zeros_like(mine) for _ in range(ctx.world)]
+    dist.all_gather(sums, mine)
+    if ctx.rank != 0:
+        return None
+    import oracle
+    for r in range(ctx.world):
+        got = torch.stack([wk.coll_bulk[sub, r].to(torch.int64).sum(), wk.coll_tail[sub, r].to(torch.int64).sum()])
+        if not torch.equal(got, sums[r]):
+            raise SystemExit("collated slots of rank %d differ from what that rank produced (checksum)" % r)
+    checked = []
+    for r in sorted({1, ctx.world - 1}):
+        host = torch.cat([wk.coll_bulk[sub, r], wk.coll_tail[sub, r]]).cpu().numpy()
+        o = wk.pack.numpy_views(host)
+        frames = frames_for(wk.wl, r)
+        for f in sorted({0, wk.B // 2 + 1, wk.B - 1}):
+            img = frames[f]
+            k2, d2 = oracle.orb_extract(img, wk.wl["nfeatures"])
+            n = int(o["counts"][f])
+            ok = n == len(k2) and np.array_equal(o["desc"][f, :n], d2) and all(
+                np.array_equal(o["kps"][f, :n][name].view(np.uint32), k2[name].view(np.uint32)) for name in k2.dtype.names)
+            if ok and wk.det is not None:
+                want = oracle.aruco_detect(img, DICT)
+                m = int(o["marker_counts"][f])
+                ok = m == len(want) and np.array_equal(o["markers"][f, :m]["id"], want["id"]) and (m == 0 or float(np.abs(o["markers"][f, :m]["xy"] - want["xy"]).max()) <= 1e-4)
+            if ok and wk.matcher is not None:
+                n2, m2 = oracle.search_by_bow_bf(wk.ref_np[0], wk.ref_np[1]["angle"], d2, k2["angle"], 0.7, True)
+                ok = int(o["n_matches"][f]) == n2 and np.array_equal(o["matches"][f, :n], m2)
+            if not ok:
+                raise SystemExit("collated results of rank %d frame %d differ from the CPU oracle" % (r, f))
+            checked.append([r, f])
+    return {"checksums": "all %d ranks equal" % ctx.world, "oracle_frames_rank_frame": checked, "result": "bit-exact (corners <= 1e-4 px)"}
+
+
+def workload_line(ctx, wl, steps, warmup, do_e2e=True, headline=False):
+    """measure one workload; returns the dict rank 0 prints (None on other ranks)"""
+    wk = Workload(ctx, wl)
+    B, W, H, nsub = wk.B, wk.W, wk.H, wk.nsub
+    traffic_before = ctx.collator.traffic() if ctx.world > 1 else (0, 0)
+    total_ms, launches, stage, stage_frames, wall = timed_resident(ctx, wk, steps, warmup, profile=True)
+    nkp, nmk, nmatch = wk.totals()
+    traffic0 = ctx.collator.traffic() if ctx.world > 1 else (0, 0)
+    parity = check_collated(ctx, wk) if ctx.world > 1 else None
+    e2e_s, h2d, d2h = float("nan"), 0, 0
+    if do_e2e:
+        e2e_s, h2d, d2h = timed_e2e(ctx, wk, steps)
+    total_ms, e2e_ms = max_over_ranks(ctx, [total_ms, e2e_s * 1000.0])
+    if ctx.rank != 0:
+        return None
+    frames = B * nsub * ctx.world * steps
+    fps = frames / (total_ms / 1000.0)
+    peak, peak_src = peaks()
+    sp = SIGMA_P.get((W, H), int(3.0942 * W * H))
+    fast_bytes = (sp + 4 * int(10000 * W * H / 307200)) * stage_frames      # k_fast: every level pixel read once + ~10k candidate slots written / frame,
+    fast_ms = stage[1] / steps                                              # for the frames of the timed launch (large batches run as two half-batch launches)
+    achieved = fast_bytes / (fast_ms / 1000.0) / 1e9 if fast_ms > 0 else 0.0
+    b_frame = 2 * sp + 60 * (nkp / B)                                       # SURVEY.md 8d: B_ext
+    if wk.det:
+        b_frame += 3.333 * W * H + 36 * (nmk / B)                           # B_aru
+    if wk.matcher:
+        b_frame += 36 * (nkp / B + 1000) + 4 * (nkp / B)                    # B_mat
+    line = {
+        "metric": wl["metric"], "value": fps, "unit": "frames/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": wl["name"], "frames_per_gpu": B * nsub, "l2": "flushed between steps (256 MiB fill, untimed)",
+                   "timing": "CUDA events on the launching stream, one pair per step, max over ranks",
+                   "streams": "extractor + matcher on the launching stream, detector on a second, higher-priority stream",
+                   "collate": ("gather-to-root of the packed result slots through the library's own NCCL communicator (b200_collate_gather, grouped ncclSend/ncclRecv), two "
+                               "transfers per %s inside the step: keypoints + descriptors + counts while the matcher runs, markers + matches after the join"
+                               % ("sub-batch" if nsub > 1 else "step")) if ctx.world > 1 else "none (1 GPU)"},
+        "e2e": {"value": frames / (e2e_ms / 1000.0) if do_e2e else None, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "b200_frontend_host (pinned host buffers, chunked H2D overlapped with compute)" +
+                       ("; then b200_frontend_collate_host: every rank's results gathered over NCCL and downloaded into rank 0's host buffers" if ctx.world > 1 else "")},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("k_fast", wl, stage_frames), "peak_source": peak_src, "ms_per_launch": fast_ms,
+                     "algorithmic_bytes_per_launch": int(fast_bytes), "frames_per_launch": int(stage_frames),
+                     "extractor_stage_ms": {"pyramid": stage[0] / steps, "fast": stage[1] / steps, "quadtree": stage[2] / steps, "describe": stage[3] / steps},
+                     "whole_step": {"algorithmic_bytes_per_frame": b_frame, "achieved_gbs": fps / ctx.world * b_frame / 1e9,
+                                    "frac": fps / ctx.world * b_frame / 1e9 / peak}},
+        "wall_s_timed_region": wall,
+        "per_frame": {"keypoints": nkp / B, "markers": nmk / B, "matches": nmatch / B},
+    }
+    if ctx.world > 1:
+        line["collated_parity"] = parity
+        line["nvlink"] = {"bytes_received_by_rank0_per_step": int((traffic0[1] - traffic_before[1]) // max(1, steps + warmup)),
+                          "bytes_sent_per_other_rank_per_step": int(wk.pack.total_bytes) * nsub,
+                          "note": "payload of the grouped ncclSend/ncclRecv (b200_collate_traffic); only rank 0 receives"}
+    if not headline:
+        for k in ("higher_is_better", "scaling", "vs_baseline", "dtype", "data"):
+            line.pop(k)
+    return line
+
+
+def c1_line(ctx):
+    """C1 (BASELINE.json configs[0]): ONE 640x480 frame per call through the C++ adapters' ORBextractor::operator() + MarkerDetector::detect()
+    (tools/c1_latency.cpp, the calls of src/Frame.cc:91,142), median latency of 200 calls, beside the 1-thread CPU reference on the same frames"""
+    from orb_slam2_aruco_b200 import build as b, synth
+    exe = b.C1_EXE
+    if not os.path.exists(exe):
+        b.build_tools()
+    nfr = 8
+    frames = synth.make_batch(nfr, 640, 480, 20, "ARUCO", first=500000)
+    path = "/tmp/b200_c1_frames.raw"
+    frames.tofile(path)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx.local)))
+    r = subprocess.run([exe, path, "640", "480", str(nfr), "ARUCO", "1000", "200", "20"], capture_output=True, text=True, timeout=300, env=env)
+    if r.returncode != 0:
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    wl = dict(nfeatures=1000, markers=20, match=False, batch=nfr)
+    cpu_reference_run(frames[:2], wl, 1, None, DICT="ARUCO")
+    secs, kind, what = cpu_reference_run(frames, wl, 1, None, DICT="ARUCO")
+    d.update({"workload": "C1: single 640x480 gray frame per call, 8 levels, 1000 ORB features, dictionary ARUCO (20 planted markers): ORB_SLAM2::ORBextractor::operator() + "
+                          "aruco::MarkerDetector::detect(image, camParams, 0.187) through include/b200slam_adapters.hpp, host image in, std::vector<cv::KeyPoint> / cv::Mat / "
+                          "std::vector<aruco::Marker> (with IPPE poses) out",
+              "metric": "latency per frame (ms), median of 200 calls after 20 warm-up calls", "frames_per_s": 1000.0 / d["latency_ms_median"],
+              "cpu_reference": {"latency_ms": 1000.0 * secs / nfr, "cores": 1, "kind": kind, "sample": "%d frames, 1 thread; %s" % (nfr, what)},
+              "speedup_vs_cpu_reference_1_thread": (1000.0 * secs / nfr) / d["latency_ms_median"]})
+    return d
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,6 +554,8 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-API leg")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (no extra_workloads)")
+    ap.add_argument("--extras", default="C4,C5,C3R,C1", help="comma list of extra workloads measured after the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     wl = WORKLOADS[args.workload]
@@ -261,184 +564,63 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from orb_slam2_aruco_b200 import _lib
-    from orb_slam2_aruco_b200.api import FrontEnd, MarkerDetector, ORBextractor, ORBmatcher
+    from orb_slam2_aruco_b200 import shard
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = Ctx()
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx.dist = dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
+    torch.cuda.set_device(ctx.local)
+    ctx.dev = torch.device("cuda", ctx.local)
+    ctx.collator = None
+    if ctx.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=ctx.dev)       # plumbing only: rendezvous, barriers, max over ranks
+        ctx.collator = shard.Collator.from_torch_distributed(ctx.local)      # the data path: the library's own NCCL communicator
+    ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.dev)    # > 126 MB L2
 
-    B, W, H = wl["batch"], wl["w"], wl["h"]
-    imgs_np = frames_for(wl, rank)
-    ex = ORBextractor(wl["nfeatures"], 1.2, 8, 20, 7, W, H, B, device=local)
-    det = MarkerDetector(DICT, W, H, B, device=local) if wl["markers"] else None
-    matcher = ORBmatcher(0.7, True, device=local) if wl["match"] else None
-    cap, mcap = ex.cap, 64
-    d_imgs = torch.from_numpy(imgs_np).to(dev)
-    d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device=dev)
-    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
-    d_counts = torch.zeros((B,), dtype=torch.int32, device=dev)
-    d_markers = torch.zeros((B, mcap, 9), dtype=torch.float32, device=dev)
-    d_mcounts = torch.zeros((B,), dtype=torch.int32, device=dev)
-    d_match = torch.zeros((B, cap), dtype=torch.int32, device=dev)
-    d_nmatch = torch.zeros((B,), dtype=torch.int32, device=dev)
-    # reference set for the matcher: <= 1000 descriptors of the shifted scene, extracted with the CUDA extractor
-    ref_np = None
-    if wl["match"]:
-        rk, rd = ex(reference_scene(wl))
-        ref_np = (np.ascontiguousarray(rd[:1000]), np.ascontiguousarray(rk[:1000]))
-        d_rdesc = torch.from_numpy(ref_np[0]).to(dev)
-        d_rkps = torch.from_numpy(ref_np[1].view(np.uint8).reshape(-1, 28).copy()).to(dev)
-        n_ref = len(ref_np[0])
-    prio = [int(v) for v in os.environ.get("B200_BENCH_PRIO", "0,-1").split(",")]      # detector stream at high priority (latency-bound kernels start early)
-    s_main = torch.cuda.Stream(device=dev, priority=prio[0])
-    s_aux = torch.cuda.Stream(device=dev, priority=prio[1])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    outs = {"kps": d_kps, "desc": d_desc, "counts": d_counts}
-    if det:
-        outs.update(markers=d_markers, marker_counts=d_mcounts)
-    if matcher:
-        outs.update(matches=d_match, n_matches=d_nmatch)
-    from orb_slam2_aruco_b200 import shard
-    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
-
-    collated = shard.alloc_collated(outs, world) if world > 1 else {}
-
-    def step():
-        works = []
-        if det is not None:                      # detector on its own stream, concurrently with extractor + matcher
-            ev_fork.record(s_main)
-            s_aux.wait_event(ev_fork)
-            det.detect_batch_device(d_imgs, d_markers, d_mcounts, s_aux)
-            ev_join.record(s_aux)
-        ex.extract_batch_device(d_imgs, d_kps, d_desc, d_counts, s_main)
-        if world > 1:                            # every rank ends up with all B*world result slots (rank 0 is the consumer): the bulk
-            with torch.cuda.stream(s_main):      # (keypoints + descriptors) is gathered while the matcher runs
-                works += shard.collate_into({k: outs[k] for k in ("kps", "desc", "counts")}, collated, async_op=True)
-        if matcher is not None:
-            matcher.SearchByBoW_device(d_rdesc, d_rkps, n_ref, d_desc, d_kps, d_counts, d_match, d_nmatch, s_main)
-        if det is not None:
-            s_main.wait_event(ev_join)
-        if world > 1:
-            with torch.cuda.stream(s_main):
-                works += shard.collate_into({k: v for k, v in outs.items() if k not in ("kps", "desc", "counts")}, collated, async_op=True)
-                for w in works:
-                    w.wait()
-
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-    ex.set_profile(True)
-    launches0 = _lib.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(ctx.local)
+    if ctx.rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage = np.zeros(4, np.float64)
-    sync_all()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        with torch.cuda.stream(s_main):
-            flush.fill_(i & 0xff)          # evict the batch from L2 (not timed)
-            ev[i][0].record(s_main)
-        step()
-        ev[i][1].record(s_main)
-        s_main.synchronize()
-        stage += ex.stage_ms()
-        stage_frames = ex.stage_frames()
-    sync_all()
-    t_wall = time.perf_counter() - t_wall0
-    launches = _lib.launch_count() - launches0
-    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
-    ex.set_profile(False)
-    nkp = int(d_counts.sum().item())
-    nmk = int(d_mcounts.sum().item()) if det else 0
-    nmatch = int(d_nmatch.sum().item()) if matcher else 0
-
-    # ---- end to end through the reference-facing host-pointer C-ABI (pinned buffers) ----------------
-    e2e_s = float("nan")
-    if not args.no_e2e:
-        fe = FrontEnd(ex, det, matcher)
-        h_imgs = torch.from_numpy(imgs_np).pin_memory()
-        out = fe.alloc_outputs(B, pinned=True)
-        for _ in range(2):
-            fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            fe.process_batch(h_imgs.numpy(), ref_np[0] if ref_np else None, ref_np[1] if ref_np else None, out=out)
-        torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
-        assert int(out["counts"].sum()) == nkp, "host path and device path disagree"
-    if rank == 0:
+    line = workload_line(ctx, wl, args.steps, args.warmup, do_e2e=not args.no_e2e, headline=True)
+    if ctx.rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-
-    # ---- max over ranks ----------------------------------------------------------------------------
-    t = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
-    frames = B * world * args.steps
-    fps = frames / (total_ms / 1000.0)
-    e2e_fps = frames / (e2e_ms / 1000.0)
-
-    if rank == 0:
-        peak, peak_src = peaks()
-        sp = SIGMA_P.get((W, H), int(3.0942 * W * H))
-        fast_bytes = (sp + 4 * int(10000 * W * H / 307200)) * stage_frames              # k_fast: every level pixel read once + ~10k candidate slots written / frame,
-                                                                  # for the frames of the timed launch (large batches run as two half-batch launches)
-        fast_ms = stage[1] / args.steps
-        achieved = fast_bytes / (fast_ms / 1000.0) / 1e9
-        b_frame = 2 * sp + 60 * (nkp / B)                         # B_ext
-        if det:
-            b_frame += 3.333 * W * H + 36 * (nmk / B)             # B_aru
-        if matcher:
-            b_frame += 36 * (nkp / B + 1000) + 4 * (nkp / B)      # B_mat
-        d2h = B * cap * 60 + B * 4 + (B * mcap * 36 + B * 4 if det else 0) + (B * cap * 4 + B * 4 if matcher else 0)
-        line = {
-            "metric": wl["metric"], "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": wl["name"], "frames_per_gpu": B, "l2": "flushed between steps (256 MiB fill, untimed)",
-                       "timing": "CUDA events on the launching stream, one pair per step, max over ranks",
-                       "streams": "extractor + matcher on the launching stream, detector on a second, higher-priority stream",
-                       "collate": "nccl all_gather_into_tensor of the fixed result slots inside the step; keypoints + descriptors gathered while the matcher runs" if world > 1 else "none (1 GPU)"},
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H), "d2h_bytes_per_step": int(d2h),
-                    "api": "b200_frontend_host (pinned host buffers, chunked H2D overlapped with compute)"},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("k_fast", wl, stage_frames), "peak_source": peak_src, "ms_per_launch": fast_ms,
-                         "algorithmic_bytes_per_launch": int(fast_bytes), "frames_per_launch": int(stage_frames),
-                         "extractor_stage_ms": {"pyramid": stage[0] / args.steps, "fast": stage[1] / args.steps,
-                                                "quadtree": stage[2] / args.steps, "describe": stage[3] / args.steps},
-                         "whole_step": {"algorithmic_bytes_per_frame": b_frame, "achieved_gbs": fps / world * b_frame / 1e9,
-                                        "frac": fps / world * b_frame / 1e9 / peak}},
-            "clocks": sampler.summary(),
-            "wall_s_timed_region": t_wall,
-            "per_frame": {"keypoints": nkp / B, "markers": nmk / B, "matches": nmatch / B},
-        }
-        if not args.no_cpu_baseline and world == 1:
+        line["clocks"] = sampler.summary()
+        if not args.no_cpu_baseline and ctx.world == 1:
+            B, W, H = wl["batch"], wl["w"], wl["h"]
             sample = max(16, min(B, 256 * 640 * 480 // (W * H)))    # ~10 s of single-thread CPU work whatever the frame size
             ref_set = cpu_ref_set(wl) if wl["match"] else None
-            secs, kind, what = cpu_reference_run(imgs_np[:sample], wl, 1, ref_set)
+            secs, kind, what = cpu_reference_run(frames_for(wl, 0)[:sample], wl, 1, ref_set)
             line["cpu_baseline"] = {"value": sample / secs, "unit": "frames/s", "cores": 1, "kind": kind,
                                     "sample": "first %d of the %d frames, 1 thread; %s" % (sample, B, what)}
+    extras = {}
+    if not args.no_extras and args.workload == "C3":
+        for name in [e for e in args.extras.split(",") if e]:
+            try:
+                if name == "C1":
+                    if ctx.world == 1:
+                        extras["C1"] = c1_line(ctx)
+                    continue
+                r = workload_line(ctx, WORKLOADS[name], 3, 3, do_e2e=not args.no_e2e)
+                if ctx.rank == 0:
+                    extras[name] = r
+            except SystemExit:
+                raise                                        # a collation that delivers wrong data prints nothing
+            except Exception as e:                           # an extra must not take the headline down with it
+                if ctx.world > 1:
+                    raise
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            torch.cuda.empty_cache()
+    if ctx.rank == 0:
+        if extras:
+            line["extra_workloads"] = extras
         print(json.dumps(line))
-    if world > 1:
+    if ctx.world > 1:
+        ctx.collator.close()
         dist.destroy_process_group()
 
 

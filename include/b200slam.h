@@ -63,6 +63,7 @@ typedef struct b200_marker_pose {
 typedef struct b200_orb_s*   b200_orb_t;
 typedef struct b200_aruco_s* b200_aruco_t;
 typedef struct b200_voc_s*   b200_voc_t;
+typedef struct b200_collate_s* b200_collate_t;
 
 const char* b200_last_error(void);
 /* number of CUDA kernel launches issued by this library in the calling process so far */
@@ -227,6 +228,7 @@ int b200_match_candidates_host(const uint8_t* query_desc, int nq, const uint8_t*
  * window = max(3, 15*w/1920) made odd), CORNER_LINES refinement, minSize 0, no error correction. */
 int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_width, int max_height, int max_batch, int device);
 int b200_aruco_destroy(b200_aruco_t h);
+/* marker capacity per frame of every marker buffer (a library constant; h may be NULL) */
 int b200_aruco_max_markers(b200_aruco_t h);
 /* markers [n][cap] sorted by id per frame (cap = b200_aruco_max_markers()), counts [n]. */
 int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
@@ -297,6 +299,33 @@ int b200_voc_num_words(b200_voc_t h);
  * Frame::ComputeBoW (src/Frame.cc:348-355) builds mBowVec / mFeatVec from these (b200slam_adapters.hpp: transform). */
 int b200_voc_transform(b200_voc_t h, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id, void* stream);
 int b200_voc_transform_host(b200_voc_t h, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id);
+
+
+/* ---------------------------------------------------------------- multi-GPU collation -- */
+/* The reference is a single process; the B200 build shards a batch of frames over the GPUs of a node (contiguous blocks of frames per rank, one
+ * process per GPU, no data-path collective) and has ONE exchange step: the fixed-size per-frame result slots travel to the consumer rank over
+ * NCCL (NVLink 5 / NVSwitch).  NCCL is bound at run time (dlopen libnccl.so.2); without it these calls fail with B200_ENODEV and everything
+ * else keeps working.  The communicator belongs to the library: rank 0 obtains an id, the host hands its 128 bytes to every rank (any
+ * transport: a file, MPI, torch.distributed's store), every rank creates its handle. */
+int b200_collate_unique_id(uint8_t* id128);
+int b200_collate_create(b200_collate_t* out, const uint8_t* id128, int rank, int world, int device);
+int b200_collate_destroy(b200_collate_t h);
+int b200_collate_rank(b200_collate_t h);
+int b200_collate_world(b200_collate_t h);
+int b200_collate_nccl_version(void);                       /* e.g. 22809; 0 when NCCL could not be loaded */
+/* Gather-to-root of n_buffers DEVICE buffers inside one NCCL group (grouped ncclSend / ncclRecv; the root's own block is a device copy).
+ * send[b]: this rank's buffer of bytes[b] bytes (same sizes on every rank); recv[b] (root only): world * bytes[b] bytes, rank-major.
+ * Only enqueues work on `stream`. */
+int b200_collate_gather(b200_collate_t h, int n_buffers, const void* const* send, void* const* recv, const int64_t* bytes, int root, void* stream);
+/* The all-gather form (every rank receives every block); recv on every rank. */
+int b200_collate_allgather(b200_collate_t h, int n_buffers, const void* const* send, void* const* recv, const int64_t* bytes, void* stream);
+/* payload bytes this rank has sent / received through the handle so far (the NVLink traffic of the SCALE report) */
+int b200_collate_traffic(b200_collate_t h, int64_t* bytes_sent, int64_t* bytes_received);
+/* Sharded front end: every rank has run b200_frontend_host on its own block of n frames (same n, geometry and options everywhere); the
+ * device-resident copies of those results are gathered at `root` in ONE NCCL group and downloaded there into HOST buffers laid out rank-major,
+ * [world][n][...] with the per-rank layout of b200_frontend_host's outputs.  Non-root ranks pass NULL outputs.  Synchronous. */
+int b200_frontend_collate_host(b200_orb_t orb, b200_collate_t c, int root, b200_keypoint* kps_all, uint8_t* desc_all, int32_t* counts_all,
+                               b200_marker* markers_all, int32_t* marker_counts_all, int32_t* match_all, int32_t* n_matches_all);
 
 #ifdef __cplusplus
 }

@@ -764,6 +764,9 @@ private:
         if (h_ && w <= w_ && h <= ht_) return;
         if (h_) { b200_aruco_destroy(h_); h_ = nullptr; }
         w_ = w > w_ ? w : w_; ht_ = h > ht_ ? h : ht_;
+        // the reference's default-constructed detector searches several dictionaries at once; src/Frame.cc:133 always calls setDictionary first
+        if (dict_ == "ALL_DICTS") throw std::runtime_error("b200slam: multi-dictionary ALL_DICTS detection is not on the reference's configured path "
+                                                           "(src/Frame.cc:133): call setDictionary(name) before detect");
         b200slam_detail::check(b200_aruco_create(&h_, dict_.c_str(), w_, ht_, 1, device_));
     }
     std::string dict_;

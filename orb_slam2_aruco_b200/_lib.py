@@ -85,6 +85,15 @@ def lib():
         L.b200_frame_assign_grid.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, vp]
         L.b200_frame_features_in_area.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
         L.b200_keyframe_features_in_area.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
+        L.b200_collate_unique_id.argtypes = [vp]
+        L.b200_collate_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
+        L.b200_collate_destroy.argtypes = [vp]
+        L.b200_collate_rank.argtypes = [vp]
+        L.b200_collate_world.argtypes = [vp]
+        L.b200_collate_gather.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+        L.b200_collate_allgather.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.b200_collate_traffic.argtypes = [vp, vp, vp]
+        L.b200_frontend_collate_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -647,6 +647,11 @@ class MarkerDetector:
 
     def _create(self, w, h, b):
         self.close()
+        if self._dict == "ALL_DICTS":
+            # the reference's default-constructed detector searches several dictionaries at once (dictionary_based.cpp setParams); its configured
+            # path never does: src/Frame.cc:133 always calls setDictionary(System::mArucoDic) before the first detect
+            raise B200Error(_lib.EINVAL, "multi-dictionary ALL_DICTS detection is not on the reference's configured path (src/Frame.cc:133): "
+                                         "call setDictionary(name) or pass dict_name before detect")
         hnd = C.c_void_p()
         check(lib().b200_aruco_create(C.byref(hnd), self._dict.encode(), w, h, b, self._device))
         self._h = hnd
@@ -757,7 +762,7 @@ class FrontEnd:
         if self.extractor._h is None:
             raise B200Error(_lib.EINVAL, "create the extractor with max_width/max_height/max_batch (or run one frame) first")
         cap = self.extractor.cap
-        mcap = 64
+        mcap = self.detector.cap if self.detector is not None and self.detector._h is not None else check(lib().b200_aruco_max_markers(None))
 
         def mk(shape, dtype):
             if pinned:
@@ -795,6 +800,17 @@ class FrontEnd:
             self.matcher.mfNNratio if do_match else 0.0, int(self.matcher.mbCheckOrientation) if do_match else 0,
             ptr(out["matches"]) if do_match else None, ptr(out["n_matches"]) if do_match else None))
         return out
+
+
+    def collate_host(self, collator, root_out=None, root=0):
+        """sharded front end: after process_batch on every rank, the device-resident results travel to `root` in one NCCL group
+        (b200_frontend_collate_host) and land in root_out, host arrays laid out [world][n][...] (alloc_outputs(world * n) on the root)."""
+        o = root_out
+        check(lib().b200_frontend_collate_host(
+            self.extractor._h, collator._h, int(root), ptr(o["kps"]) if o else None, ptr(o["desc"]) if o else None, ptr(o["counts"]) if o else None,
+            ptr(o["markers"]) if o and self.detector is not None else None, ptr(o["marker_counts"]) if o and self.detector is not None else None,
+            ptr(o["matches"]) if o and self.matcher is not None else None, ptr(o["n_matches"]) if o and self.matcher is not None else None))
+        return o
 
 
 class FrameGrid:

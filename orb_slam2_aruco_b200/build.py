@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200slam.so")
-SOURCES = ["common.cu", "orb.cu", "match.cu", "aruco.cu", "pose.cu", "frame.cu", "bow.cu"]
+SOURCES = ["common.cu", "orb.cu", "match.cu", "aruco.cu", "pose.cu", "frame.cu", "bow.cu", "collate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false"]
 
@@ -22,7 +22,11 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200slam.h")]
+    if not os.path.exists(C1_EXE):
+        return True
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b200slam.h"),
+                                                                 os.path.join(HERE, "..", "include", "b200slam_adapters.hpp"),
+                                                                 os.path.join(HERE, "..", "tools", "c1_latency.cpp")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -47,7 +51,22 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    build_tools()
     return LIB
+
+
+C1_EXE = os.path.join(HERE, "c1_latency.bin")
+
+
+def build_tools():
+    """host programs over the C++ adapters (g++, header only): the C1 single-frame latency driver bench.py runs"""
+    root = os.path.join(HERE, "..")
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tools", "c1_latency.cpp"), "-o", C1_EXE,
+           "-L", HERE, "-l:libb200slam.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return C1_EXE
 
 
 if __name__ == "__main__":

@@ -1258,7 +1258,7 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     const DictTable* dt = nullptr;
     for (const auto& d : kDicts) if (std::string(d.name) == dict_name) dt = &d;
     if (!dt) return fail(B200_EINVAL, "unknown dictionary '%s'", dict_name);
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     b200_aruco_s* h = new (std::nothrow) b200_aruco_s();
     if (!h) return B200_ENOMEM;
@@ -1285,7 +1285,7 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
 
 int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
-    cudaSetDevice(h->device);
+    DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
     cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
@@ -1297,7 +1297,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
 int b200_aruco_batch_capacity(b200_aruco_t h) { return h ? h->max_batch : 0; }
 
 int b200_aruco_max_markers(b200_aruco_t h) {
-    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    (void)h;                       // a library-wide constant: NULL asks for it without a handle
     return kMaxMarkers;
 }
 
@@ -1309,7 +1309,7 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     if (base < 0 || base + n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
     if (n == 0) return B200_OK;
     if (!markers || !counts) return fail(B200_EINVAL, "null %s", "output pointer");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     if (w < 8 || hh < 8) { B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4, st)); return B200_OK; }
@@ -1383,7 +1383,7 @@ int b200_aruco_detect(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh,
 // device-pointer calls since the last check (B200_ECAPACITY), clearing the flag.
 int b200_aruco_check(b200_aruco_t h, void* stream) {
     if (!h) return fail(B200_EINVAL, "null %s", "handle");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     int err = 0;
@@ -1402,7 +1402,7 @@ int b200_aruco_check(b200_aruco_t h, void* stream) {
 int b200_aruco_debug(b200_aruco_t h, int frame, int32_t* out4, float* corners, int32_t* ids, int cap) {
     if (!h || !out4) return fail(B200_EINVAL, "null %s", "argument");
     if (frame < 0 || frame >= h->max_batch) return fail(B200_EINVAL, "no such %s", "frame");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     B200_CUDA(cudaDeviceSynchronize());
     const int B = h->max_batch;
@@ -1432,7 +1432,7 @@ int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int w, in
     if (n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
     if (n == 0) return B200_OK;
     if (!markers || !counts || (!imgs && w > 0 && hh > 0)) return fail(B200_EINVAL, "null %s", "pointer");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     if (w < 8 || hh < 8) { for (int i = 0; i < n; i++) counts[i] = 0; return B200_OK; }
     const size_t fb = (size_t)w * hh;

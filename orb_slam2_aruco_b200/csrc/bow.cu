@@ -58,7 +58,7 @@ int b200_voc_create(b200_voc_t* out, int k, int L, int n_nodes, const int32_t* p
     *out = nullptr;
     if (k < 1 || k > 20 || L < 1 || L > 10 || n_nodes < 2 || !parent || !is_leaf || !node_desc || !node_weight)      // loadFromTextFile's sanity check (:1359)
         return fail(B200_EINVAL, "bad %s", "vocabulary");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     // children in file order (m_nodes[pid].children.push_back(nid)), word ids in order of leaf appearance
     std::vector<int> cnt(n_nodes, 0), beg(n_nodes + 1, 0), fill(n_nodes, 0), children(n_nodes - 1);
@@ -95,7 +95,7 @@ int b200_voc_create(b200_voc_t* out, int k, int L, int n_nodes, const int32_t* p
 
 int b200_voc_destroy(b200_voc_t h) {
     if (!h) return B200_OK;
-    cudaSetDevice(h->device);
+    DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_nodes); cudaFree(h->d_children); cudaFree(h->d_desc); cudaFree(h->d_weight);
     delete h;
     return B200_OK;
@@ -106,7 +106,7 @@ int b200_voc_num_words(b200_voc_t h) { return h ? h->n_words : fail(B200_EINVAL,
 int b200_voc_transform(b200_voc_t h, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id, void* stream) {
     if (!h) return fail(B200_EINVAL, "null %s", "handle");
     if (n < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     if (n == 0) return B200_OK;
     if (!desc || !word_id || !weight || !node_id) return fail(B200_EINVAL, "null %s", "pointer");
@@ -120,7 +120,7 @@ int b200_voc_transform(b200_voc_t h, const uint8_t* desc, int n, int levelsup, i
 int b200_voc_transform_host(b200_voc_t h, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight, int32_t* node_id) {
     if (!h) return fail(B200_EINVAL, "null %s", "handle");
     if (n < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     if (n == 0) return B200_OK;
     if (!desc || !word_id || !weight || !node_id) return fail(B200_EINVAL, "null %s", "pointer");

@@ -32,6 +32,23 @@ int use_device(int device) {
     return B200_OK;
 }
 
+namespace {
+struct ThreadStreams {
+    cudaStream_t s[64];
+    ThreadStreams() { for (auto& x : s) x = nullptr; }
+    ~ThreadStreams() { for (auto& x : s) if (x) cudaStreamDestroy(x); }       // at thread exit; errors (context already gone) are ignored
+};
+thread_local ThreadStreams t_streams;
+}
+
+cudaStream_t thread_stream(int device) {
+    if (device < 0 || device >= 64) return cudaStreamPerThread;
+    if (!t_streams.s[device]) {
+        if (cudaStreamCreateWithFlags(&t_streams.s[device], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return cudaStreamPerThread; }
+    }
+    return t_streams.s[device];
+}
+
 }  // namespace b200
 
 extern "C" {

@@ -33,10 +33,28 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
     do {                                                                                         \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                              \
         b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        cudaError_t _le = cudaGetLastError();        /* an invalid configuration never reaches the device: report it here */ \
+        if (_le != cudaSuccess) {                                                                \
+            snprintf(b200::g_err, sizeof(b200::g_err), "%s:%d launch of %s -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(_le)); \
+            return B200_ECUDA;                                                                   \
+        }                                                                                        \
     } while (0)
 
 // Select the device and make sure it is a Blackwell B200-class part; no CPU fallback exists.
 int use_device(int device);
+
+// Every C-ABI entry point selects the handle's device for its own duration only: the calling thread's current device is put back on
+// return (a multi-GPU host, e.g. a torch process, keeps allocating where it was).
+struct DeviceScope {
+    int prev;
+    DeviceScope() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceScope() { int cur = -1; if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); }
+};
+
+// The _host entry points are called from the reference's three threads (Tracking, LocalMapping, LoopClosing): each calling thread
+// works on its own non-blocking stream per device (created on first use) and waits for that stream only, so a LocalMapping Fuse never
+// stalls the tracking thread's extractor, and nothing runs on the legacy default stream.
+cudaStream_t thread_stream(int device);
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 

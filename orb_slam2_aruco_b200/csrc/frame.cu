@@ -172,7 +172,7 @@ int b200_frame_undistort(const b200_keypoint* kps, const int32_t* counts, int n_
     FrameCam c;
     int rc = make_cam(cam9, c);
     if (rc) return rc;
-    if ((rc = use_device(device))) return rc;
+    DeviceScope _ds; if ((rc = use_device(device))) return rc;
     if (n_batch == 0 || cap == 0) return B200_OK;
     if (!kps || !counts || !kps_un) return fail(B200_EINVAL, "null %s", "pointer");
     const long long total = (long long)n_batch * cap;
@@ -189,7 +189,7 @@ int b200_frame_undistort_points_host(const float* xy, int n, const float* cam9, 
     if (n == 0) return B200_OK;
     if (!xy || !xy_un) return fail(B200_EINVAL, "null %s", "pointer");
     if (!c.distorted) { if (xy_un != xy) memcpy(xy_un, xy, (size_t)n * 8); return B200_OK; }      // mDistCoef.at<float>(0) == 0: the points as they are
-    if ((rc = use_device(device))) return rc;
+    DeviceScope _ds; if ((rc = use_device(device))) return rc;
     std::vector<b200_keypoint> h((size_t)n);
     memset(h.data(), 0, (size_t)n * sizeof(b200_keypoint));
     for (int i = 0; i < n; i++) { h[i].x = xy[2 * i]; h[i].y = xy[2 * i + 1]; }
@@ -214,7 +214,7 @@ int b200_frame_image_bounds(int width, int height, const float* cam9, float* bou
     int rc = make_cam(cam9, c);
     if (rc) return rc;
     if (!c.distorted) { bounds4[0] = 0.f; bounds4[1] = (float)width; bounds4[2] = 0.f; bounds4[3] = (float)height; return B200_OK; }
-    if ((rc = use_device(device))) return rc;
+    DeviceScope _ds; if ((rc = use_device(device))) return rc;
     b200_keypoint h[4] = {};
     h[1].x = (float)width; h[2].y = (float)height; h[3].x = (float)width; h[3].y = (float)height;
     b200_keypoint* d = nullptr; int* dc = nullptr;
@@ -237,7 +237,7 @@ int b200_frame_assign_grid(const b200_keypoint* kps_un, const int32_t* counts, i
                            int32_t* cell_start, int32_t* cell_items, int device, void* stream) {
     if (n_batch < 0 || cap < 0) return fail(B200_EINVAL, "negative %s", "size");
     if (!bounds4 || !(bounds4[1] > bounds4[0]) || !(bounds4[3] > bounds4[2])) return fail(B200_EINVAL, "bad image %s", "bounds");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     if (n_batch == 0) return B200_OK;
     if (!kps_un || !counts || !cell_start || !cell_items) return fail(B200_EINVAL, "null %s", "pointer");
@@ -252,7 +252,7 @@ static int features_in_area_impl(const b200_keypoint* kps_un, const int32_t* cel
                                  int32_t* out_idx, int32_t* out_count, int row_cap, int device, void* stream, bool keyframe_origin) {
     if (n_queries < 0 || row_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
     if (!bounds4 || !(bounds4[1] > bounds4[0]) || !(bounds4[3] > bounds4[2])) return fail(B200_EINVAL, "bad image %s", "bounds");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     if (n_queries == 0) return B200_OK;
     if (!kps_un || !cell_start || !cell_items || !queries_xyr || !query_levels || !out_idx || !out_count) return fail(B200_EINVAL, "null %s", "pointer");

@@ -255,8 +255,9 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
 }
 
 __global__ void k_hamming_matrix(const ulonglong4* __restrict__ a, int na, const ulonglong4* __restrict__ b, int nb, int* __restrict__ dist) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-    if (j < nb && i < na) dist[(long long)i * nb + j] = hamming256(a[i], b[j]);
+    // rows on grid.x (2^31 - 1 blocks), 256-column blocks on grid.y: a map-sized `na` must not hit the 65535 limit of grid.y / grid.z
+    const int i = blockIdx.x;
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < nb; j += gridDim.y * blockDim.x) dist[(long long)i * nb + j] = hamming256(a[i], b[j]);
 }
 
 // candidate-list core: warp per query
@@ -786,8 +787,19 @@ k_kf_project(const float* __restrict__ pos, const float* __restrict__ normal, co
     } else { q3[3 * i] = u; q3[3 * i + 1] = v; q3[3 * i + 2] = __fmul_rn(g.th, g.sf[lv]); }
 }
 
-struct MatchScratch { uint32_t* topk; size_t cap; int device; };
-static thread_local MatchScratch g_ms = {nullptr, 0, -1};
+// top-K scratch of the device-pointer matcher: one buffer per (device, stream) of the calling thread, so that two asynchronous calls a thread
+// enqueues on different streams never share top-K lists; the chunked front end (base / total slots) owns the entry keyed by its first stream.
+struct MatchScratch { uint32_t* topk; size_t cap; int device; cudaStream_t stream; };
+struct MatchScratchSet {
+    std::vector<MatchScratch> v;
+    ~MatchScratchSet() { for (auto& m : v) if (m.topk) cudaFree(m.topk); }       // thread exit; errors after context teardown are ignored
+    MatchScratch& get(int device, cudaStream_t st) {
+        for (auto& m : v) if (m.device == device && m.stream == st) return m;
+        v.push_back(MatchScratch{nullptr, 0, device, st});
+        return v.back();
+    }
+};
+static thread_local MatchScratchSet g_ms_set;
 
 }  // namespace b200
 
@@ -803,7 +815,7 @@ static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int re
     // different streams (the chunks of b200_frontend_host) do not share top-K lists
     if (n_batch < 0 || n_ref < 0 || frame_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
     if (frame_cap > 65535) return fail(B200_ECAPACITY, "frame_cap above %s", "65535");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     if (n_batch == 0) return B200_OK;
     if (!n_frame || !match_ref_idx || !n_matches || (n_ref > 0 && (!ref_desc || !ref_angle)) || (frame_cap > 0 && (!frame_desc || !frame_angle)))
@@ -811,11 +823,12 @@ static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int re
     if (((uintptr_t)ref_desc | (uintptr_t)frame_desc) & 31) return fail(B200_EINVAL, "descriptor arrays must be %s", "32-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t need = std::max<size_t>((size_t)std::max(total, base + n_batch) * std::max(n_ref, 1) * kTopK * 4, 16);
-    if (g_ms.device != device || g_ms.cap < need) {
-        if (g_ms.topk) cudaFree(g_ms.topk);
+    MatchScratch& g_ms = g_ms_set.get(device, total > 0 ? (cudaStream_t)(uintptr_t)1 : st);     // ranged calls (b200_frontend_host) share one slotted buffer
+    if (g_ms.cap < need) {
+        if (g_ms.topk) cudaFree(g_ms.topk);                     // cudaFree waits for the device: no launch still reads the old block
         g_ms.topk = nullptr; g_ms.cap = 0;
         B200_CUDA(cudaMalloc((void**)&g_ms.topk, need));
-        g_ms.cap = need; g_ms.device = device;
+        g_ms.cap = need;
     }
     uint32_t* topk = g_ms.topk + (size_t)base * std::max(n_ref, 1) * kTopK;
     const int nf_pad = (frame_cap + 31) & ~31;
@@ -872,12 +885,30 @@ int b200_match_bf_kp_range(const uint8_t* ref_desc, const b200_keypoint* ref_kps
 }
 
 namespace {
+// stream-ordered scratch of the _host entry points: everything a call allocates, copies and launches goes to the calling thread's own stream
+// (thread_stream), so concurrent calls from the reference's three threads neither serialise on the legacy default stream nor wait for each other
+thread_local cudaStream_t t_ts = nullptr;
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t n) { B200_CUDA(cudaMalloc(&p, std::max<size_t>(n, 32))); return B200_OK; }
-    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; if (n) B200_CUDA(cudaMemcpy(p, h, n, cudaMemcpyHostToDevice)); return B200_OK; }
+    ~DevBuf() { if (p) cudaFreeAsync(p, t_ts); }
+    int alloc(size_t n) { B200_CUDA(cudaMallocAsync(&p, std::max<size_t>(n, 32), t_ts)); return B200_OK; }
+    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; if (n) B200_CUDA(cudaMemcpyAsync(p, h, n, cudaMemcpyHostToDevice, t_ts)); return B200_OK; }
 };
+// the default memory pool gives freed blocks back to the driver at every synchronisation unless told to keep them
+int host_call_stream(int device, cudaStream_t* ts) {
+    static std::atomic<int> pool_set[64];
+    if (device >= 0 && device < 64 && !pool_set[device].load(std::memory_order_acquire)) {
+        cudaMemPool_t pool;
+        B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_set[device].store(1, std::memory_order_release);
+    }
+    *ts = t_ts = thread_stream(device);
+    return B200_OK;
+}
+// device -> host copy that is complete when it returns, whatever kind of host memory the caller passed
+#define B200_D2H(dst, src, n) do { B200_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, ts)); B200_CUDA(cudaStreamSynchronize(ts)); } while (0)
 }
 
 int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
@@ -885,8 +916,10 @@ int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_re
                        float ratio, int th_low, int check_ori, float histo_factor,
                        int32_t* match_ref_idx, int32_t* n_matches, int device) {
     if (n_batch < 0 || n_ref < 0 || frame_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n_batch == 0) return B200_OK;
     DevBuf rd, ra, fd, fa, nf, mi, nm;
     if ((rc = rd.upload(ref_desc, (size_t)n_ref * 32)) || (rc = ra.upload(ref_angle, (size_t)n_ref * 4)) ||
@@ -894,11 +927,11 @@ int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_re
         (rc = nf.upload(n_frame, (size_t)n_batch * 4)) || (rc = mi.alloc((size_t)n_batch * frame_cap * 4)) || (rc = nm.alloc((size_t)n_batch * 4)))
         return rc;
     if ((rc = b200_match_bf((const uint8_t*)rd.p, (const float*)ra.p, n_ref, (const uint8_t*)fd.p, (const float*)fa.p, (const int32_t*)nf.p,
-                            n_batch, frame_cap, ratio, th_low, check_ori, histo_factor, (int32_t*)mi.p, (int32_t*)nm.p, device, nullptr)))
+                            n_batch, frame_cap, ratio, th_low, check_ori, histo_factor, (int32_t*)mi.p, (int32_t*)nm.p, device, ts)))
         return rc;
-    B200_CUDA(cudaDeviceSynchronize());
-    if (frame_cap) B200_CUDA(cudaMemcpy(match_ref_idx, mi.p, (size_t)n_batch * frame_cap * 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(n_matches, nm.p, (size_t)n_batch * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaStreamSynchronize(ts));
+    if (frame_cap) B200_D2H(match_ref_idx, mi.p, (size_t)n_batch * frame_cap * 4);
+    B200_D2H(n_matches, nm.p, (size_t)n_batch * 4);
     return B200_OK;
 }
 
@@ -906,8 +939,10 @@ int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8
                                        const b200_keypoint* kps2_un, const uint8_t* desc2, int n2, const float* bounds4,
                                        float* prev_matched, int window, float ratio, int check_ori, int32_t* matches12, int device) {
     if (n1 < 0 || n2 < 0 || window < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n1 == 0) return 0;
     if (!kps1_un || !desc1 || !prev_matched || !matches12 || !bounds4 || (n2 > 0 && (!kps2_un || !desc2))) return fail(B200_EINVAL, "null %s", "pointer");
     if (n2 == 0) { for (int i = 0; i < n1; i++) matches12[i] = -1; return 0; }
@@ -921,21 +956,21 @@ int b200_match_for_initialization_host(const b200_keypoint* kps1_un, const uint8
         (rc = m12.alloc((size_t)n1 * 4)) || (rc = m21.alloc((size_t)n2 * 4)) || (rc = mdist.alloc((size_t)n2 * 4)) || (rc = rotbin.alloc((size_t)n1)) ||
         (rc = res.alloc(8)))
         return rc;
-    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)un_cnt.p, 1, n2, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
-    B200_LAUNCH(k_init_queries, (n1 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k1.p, n1, (const float*)prev.p, (float)window, (float*)q3.p, (int*)lv2.p);
+    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)un_cnt.p, 1, n2, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, ts))) return rc;
+    B200_LAUNCH(k_init_queries, (n1 + 255) / 256, 256, 0, ts, (const b200_keypoint*)k1.p, n1, (const float*)prev.p, (float)window, (float*)q3.p, (int*)lv2.p);
     if ((rc = b200_frame_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
-                                          (const int32_t*)lv2.p, n1, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+                                          (const int32_t*)lv2.p, n1, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, ts)))
         return rc;
-    B200_LAUNCH(k_init_dist, (n1 * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)d1.p, n1, (const ulonglong4*)d2.p, (const int*)cand.p, (const int*)cnt.p,
+    B200_LAUNCH(k_init_dist, (n1 * 32 + 255) / 256, 256, 0, ts, (const ulonglong4*)d1.p, n1, (const ulonglong4*)d2.p, (const int*)cand.p, (const int*)cnt.p,
                 row_cap, (int*)dist.p);
-    B200_LAUNCH(k_init_resolve, 1, 32, 0, 0, (const b200_keypoint*)k1.p, n1, (const b200_keypoint*)k2.p, n2, (const int*)cand.p, (const int*)cnt.p,
+    B200_LAUNCH(k_init_resolve, 1, 32, 0, ts, (const b200_keypoint*)k1.p, n1, (const b200_keypoint*)k2.p, n2, (const int*)cand.p, (const int*)cnt.p,
                 (const int*)dist.p, row_cap, ratio, 50, check_ori, (float*)prev.p, (int*)m12.p, (int*)m21.p, (int*)mdist.p, (unsigned char*)rotbin.p, (int*)res.p);
-    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaStreamSynchronize(ts));
     int r2[2] = {0, 0};
-    B200_CUDA(cudaMemcpy(r2, res.p, 8, cudaMemcpyDeviceToHost));
+    B200_D2H(r2, res.p, 8);
     if (r2[1]) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
-    B200_CUDA(cudaMemcpy(matches12, m12.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(prev_matched, prev.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost));
+    B200_D2H(matches12, m12.p, (size_t)n1 * 4);
+    B200_D2H(prev_matched, prev.p, (size_t)n1 * 8);
     return r2[0];
 }
 
@@ -946,8 +981,10 @@ int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* de
     if (n_frame < 0 || n_queries < 0 || mode < 0 || mode > 2) return fail(B200_EINVAL, "bad %s", "sizes or mode");
     const bool keyframe = mode == 2;                            // SearchByProjection(KeyFrame*, Scw, ...): mode 1 over KeyFrame::GetFeaturesInArea
     if (keyframe) mode = 1;
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n_frame > 0 && (!kps_un || !desc || !occupied || !assign || !bounds4)) return fail(B200_EINVAL, "null %s", "frame pointer");
     for (int i = 0; i < n_frame; i++) assign[i] = -1;
     if (n_queries == 0 || n_frame == 0) return 0;
@@ -961,22 +998,22 @@ int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* de
         (rc = cand.alloc((size_t)n_queries * row_cap * 4)) || (rc = cnt.alloc((size_t)n_queries * 4)) || (rc = dist.alloc((size_t)n_queries * row_cap * 4)) ||
         (rc = asg.alloc((size_t)n_frame * 4)) || (rc = eb.alloc((size_t)n_queries * 4)) || (rc = ei.alloc((size_t)n_queries * 4)) || (rc = res.alloc(8)))
         return rc;
-    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_frame, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
+    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_frame, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, ts))) return rc;
     if ((rc = (keyframe ? b200_keyframe_features_in_area : b200_frame_features_in_area)(
              (const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p, (const int32_t*)lv2.p, n_queries,
-             (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+             (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, ts)))
         return rc;
-    B200_LAUNCH(k_init_dist, (n_queries * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)qd.p, n_queries, (const ulonglong4*)d2.p, (const int*)cand.p,
+    B200_LAUNCH(k_init_dist, (n_queries * 32 + 255) / 256, 256, 0, ts, (const ulonglong4*)qd.p, n_queries, (const ulonglong4*)d2.p, (const int*)cand.p,
                 (const int*)cnt.p, row_cap, (int*)dist.p);
-    B200_LAUNCH(k_proj_resolve, 1, 32, 0, 0, (const b200_keypoint*)k2.p, n_frame, (const int*)cand.p, (const int*)cnt.p, (const int*)dist.p, row_cap,
+    B200_LAUNCH(k_proj_resolve, 1, 32, 0, ts, (const b200_keypoint*)k2.p, n_frame, (const int*)cand.p, (const int*)cnt.p, (const int*)dist.p, row_cap,
                 (const float*)qa.p, (const unsigned char*)qo.p, n_queries, mode, ratio, th_high, check_ori, (unsigned char*)occ.p, (int*)asg.p, (int*)eb.p, (int*)ei.p,
                 (int*)res.p);
-    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaStreamSynchronize(ts));
     int r2[2] = {0, 0};
-    B200_CUDA(cudaMemcpy(r2, res.p, 8, cudaMemcpyDeviceToHost));
+    B200_D2H(r2, res.p, 8);
     if (r2[1]) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
-    B200_CUDA(cudaMemcpy(assign, asg.p, (size_t)n_frame * 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(occupied, occ.p, (size_t)n_frame, cudaMemcpyDeviceToHost));
+    B200_D2H(assign, asg.p, (size_t)n_frame * 4);
+    B200_D2H(occupied, occ.p, (size_t)n_frame);
     return r2[0];
 }
 
@@ -985,8 +1022,10 @@ int b200_match_by_bow_host(const uint8_t* q_desc, const float* q_angle, int n_q,
                            int mode, float ratio, int th_low, int check_ori, int32_t* out, int device) {
     if (th_low <= 0) th_low = 50;                               // TH_LOW, ORBmatcher.cc:39
     if (n_q < 0 || n_c < 0 || n_groups < 0 || (mode != 0 && mode != 1)) return fail(B200_EINVAL, "bad %s", "sizes or mode");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     const int n_out = mode == 0 ? n_c : n_q;
     if (n_out > 0 && !out) return fail(B200_EINVAL, "null %s", "output pointer");
     for (int i = 0; i < n_out; i++) out[i] = -1;
@@ -1013,23 +1052,25 @@ int b200_match_by_bow_host(const uint8_t* q_desc, const float* q_angle, int n_q,
         (rc = dist.alloc((size_t)std::max(total, 1ll) * 4)) || (rc = taken.alloc((size_t)n_c)) || (rc = o.alloc((size_t)n_out * 4)) ||
         (rc = eb.alloc((size_t)nq * 4)) || (rc = ei.alloc((size_t)nq * 4)) || (rc = res.alloc(8)))
         return rc;
-    B200_CUDA(cudaMemsetAsync(taken.p, 0, (size_t)n_c, 0));
-    B200_LAUNCH(k_bow_dist, (nq * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)dq.p, (const ulonglong4*)dc.p, (const int*)qi.p, (const int*)qg.p,
+    B200_CUDA(cudaMemsetAsync(taken.p, 0, (size_t)n_c, ts));
+    B200_LAUNCH(k_bow_dist, (nq * 32 + 255) / 256, 256, 0, ts, (const ulonglong4*)dq.p, (const ulonglong4*)dc.p, (const int*)qi.p, (const int*)qg.p,
                 (const int*)gco.p, (const int*)ci.p, (const int*)qo.p, nq, (int*)dist.p);
-    B200_LAUNCH(k_bow_resolve, 1, 32, 0, 0, (const float*)aq.p, (const float*)ac.p, (const int*)qi.p, (const int*)qg.p, (const int*)gco.p, (const int*)ci.p,
+    B200_LAUNCH(k_bow_resolve, 1, 32, 0, ts, (const float*)aq.p, (const float*)ac.p, (const int*)qi.p, (const int*)qg.p, (const int*)gco.p, (const int*)ci.p,
                 (const int*)qo.p, (const int*)dist.p, nq, mode, ratio, th_low, check_ori, (unsigned char*)taken.p, n_out, (int*)o.p, (int*)eb.p, (int*)ei.p,
                 (int*)res.p);
-    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaStreamSynchronize(ts));
     int r = 0;
-    B200_CUDA(cudaMemcpy(&r, res.p, 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(out, o.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost));
+    B200_D2H(&r, res.p, 4);
+    B200_D2H(out, o.p, (size_t)n_out * 4);
     return r;
 }
 
 int b200_distinctive_descriptors_host(const uint8_t* desc, const int32_t* ofs, int n_points, int32_t* best_idx, uint8_t* out_desc, int device) {
     if (n_points < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n_points == 0) return B200_OK;
     if (!ofs || !best_idx) return fail(B200_EINVAL, "null %s", "pointer");
     int max_n = 0;
@@ -1046,28 +1087,30 @@ int b200_distinctive_descriptors_host(const uint8_t* desc, const int32_t* ofs, i
     if ((rc = dd.upload(desc, (size_t)std::max(total, 1) * 32)) || (rc = dofs.upload(ofs, (size_t)(n_points + 1) * 4)) || (rc = db.alloc((size_t)n_points * 4)) ||
         (out_desc && (rc = dout.alloc((size_t)n_points * 32))))
         return rc;
-    if (out_desc) B200_CUDA(cudaMemsetAsync(dout.p, 0, (size_t)n_points * 32, 0));
+    if (out_desc) B200_CUDA(cudaMemsetAsync(dout.p, 0, (size_t)n_points * 32, ts));
     if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_LAUNCH(k_distinctive, (n_points + kMedoidWarps - 1) / kMedoidWarps, kMedoidWarps * 32, smem, 0, (const ulonglong4*)dd.p, (const int*)dofs.p, n_points,
+    B200_LAUNCH(k_distinctive, (n_points + kMedoidWarps - 1) / kMedoidWarps, kMedoidWarps * 32, smem, ts, (const ulonglong4*)dd.p, (const int*)dofs.p, n_points,
                 row_cap, (int*)db.p, out_desc ? (ulonglong4*)dout.p : nullptr);
-    B200_CUDA(cudaDeviceSynchronize());
-    B200_CUDA(cudaMemcpy(best_idx, db.p, (size_t)n_points * 4, cudaMemcpyDeviceToHost));
-    if (out_desc) B200_CUDA(cudaMemcpy(out_desc, dout.p, (size_t)n_points * 32, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaStreamSynchronize(ts));
+    B200_D2H(best_idx, db.p, (size_t)n_points * 4);
+    if (out_desc) B200_D2H(out_desc, dout.p, (size_t)n_points * 32);
     return B200_OK;
 }
 
 int b200_hamming_matrix_host(const uint8_t* a, int na, const uint8_t* b, int nb, int32_t* dist, int device) {
     if (na < 0 || nb < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (na == 0 || nb == 0) return B200_OK;
     if (!a || !b || !dist) return fail(B200_EINVAL, "null %s", "pointer");
     DevBuf da, db, dd;
     if ((rc = da.upload(a, (size_t)na * 32)) || (rc = db.upload(b, (size_t)nb * 32)) || (rc = dd.alloc((size_t)na * nb * 4))) return rc;
-    dim3 grid((nb + 255) / 256, na);
-    B200_LAUNCH(k_hamming_matrix, grid, 256, 0, 0, (const ulonglong4*)da.p, na, (const ulonglong4*)db.p, nb, (int*)dd.p);
-    B200_CUDA(cudaDeviceSynchronize());
-    B200_CUDA(cudaMemcpy(dist, dd.p, (size_t)na * nb * 4, cudaMemcpyDeviceToHost));
+    dim3 grid(na, std::min((nb + 255) / 256, 65535));
+    B200_LAUNCH(k_hamming_matrix, grid, 256, 0, ts, (const ulonglong4*)da.p, na, (const ulonglong4*)db.p, nb, (int*)dd.p);
+    B200_CUDA(cudaStreamSynchronize(ts));
+    B200_D2H(dist, dd.p, (size_t)na * nb * 4);
     return B200_OK;
 }
 
@@ -1075,8 +1118,10 @@ int b200_match_candidates_host(const uint8_t* query_desc, int nq, const uint8_t*
                                const int32_t* cand_ofs, const int32_t* cand, int32_t* out_best_idx,
                                int32_t* out_best_dist, int32_t* out_second_dist, int device) {
     if (nq < 0 || nt < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (nq == 0) return B200_OK;
     if (!query_desc || !cand_ofs || !out_best_idx || !out_best_dist || !out_second_dist) return fail(B200_EINVAL, "null %s", "pointer");
     const int total = cand_ofs[nq];
@@ -1086,12 +1131,12 @@ int b200_match_candidates_host(const uint8_t* query_desc, int nq, const uint8_t*
     if ((rc = dq.upload(query_desc, (size_t)nq * 32)) || (rc = dt.upload(train_desc, (size_t)nt * 32)) || (rc = dofs.upload(cand_ofs, (size_t)(nq + 1) * 4)) ||
         (rc = dc.upload(cand, (size_t)total * 4)) || (rc = o1.alloc((size_t)nq * 4)) || (rc = o2.alloc((size_t)nq * 4)) || (rc = o3.alloc((size_t)nq * 4)))
         return rc;
-    B200_LAUNCH(k_match_candidates, (nq * 32 + 255) / 256, 256, 0, 0, (const ulonglong4*)dq.p, nq, (const ulonglong4*)dt.p, (const int*)dofs.p, (const int*)dc.p,
+    B200_LAUNCH(k_match_candidates, (nq * 32 + 255) / 256, 256, 0, ts, (const ulonglong4*)dq.p, nq, (const ulonglong4*)dt.p, (const int*)dofs.p, (const int*)dc.p,
                 (int*)o1.p, (int*)o2.p, (int*)o3.p);
-    B200_CUDA(cudaDeviceSynchronize());
-    B200_CUDA(cudaMemcpy(out_best_idx, o1.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(out_best_dist, o2.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(out_second_dist, o3.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaStreamSynchronize(ts));
+    B200_D2H(out_best_idx, o1.p, (size_t)nq * 4);
+    B200_D2H(out_best_dist, o2.p, (size_t)nq * 4);
+    B200_D2H(out_second_dist, o3.p, (size_t)nq * 4);
     return B200_OK;
 }
 
@@ -1101,8 +1146,10 @@ int b200_match_for_triangulation_host(const b200_keypoint* kps1_un, const uint8_
                                       int check_ori, int th_low, int32_t* matches12, int device) {
     if (th_low <= 0) th_low = 50;                               // TH_LOW, ORBmatcher.cc:39
     if (n1 < 0 || n2 < 0 || n_groups < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n1 > 0 && !matches12) return fail(B200_EINVAL, "null %s", "output pointer");
     for (int i = 0; i < n1; i++) matches12[i] = -1;
     if (n_groups == 0 || n1 == 0 || n2 == 0) return 0;
@@ -1129,15 +1176,15 @@ int b200_match_for_triangulation_host(const b200_keypoint* kps1_un, const uint8_
         (rc = qg.upload(q_grp.data(), (size_t)nq * 4)) || (rc = gco.upload(grp_c_ofs, (size_t)(n_groups + 1) * 4)) || (rc = ci.upload(c_idx, (size_t)nc * 4)) ||
         (rc = m12.alloc((size_t)n1 * 4)) || (rc = rb.alloc((size_t)n1)) || (rc = res.alloc(4)))
         return rc;
-    B200_CUDA(cudaMemsetAsync(m12.p, 0xff, (size_t)n1 * 4, 0));
-    B200_CUDA(cudaMemsetAsync(rb.p, 0xff, (size_t)n1, 0));
-    B200_LAUNCH(k_triang, (nq * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k1.p, (const ulonglong4*)d1.p, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p,
+    B200_CUDA(cudaMemsetAsync(m12.p, 0xff, (size_t)n1 * 4, ts));
+    B200_CUDA(cudaMemsetAsync(rb.p, 0xff, (size_t)n1, ts));
+    B200_LAUNCH(k_triang, (nq * 32 + 255) / 256, 256, 0, ts, (const b200_keypoint*)k1.p, (const ulonglong4*)d1.p, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p,
                 (const int*)qi.p, (const int*)qg.p, (const int*)gco.p, (const int*)ci.p, nq, g, th_low, (int*)m12.p, (unsigned char*)rb.p);
-    B200_LAUNCH(k_triang_finish, 1, 256, 0, 0, (int*)m12.p, (const unsigned char*)rb.p, n1, check_ori, (int*)res.p);
-    B200_CUDA(cudaDeviceSynchronize());
+    B200_LAUNCH(k_triang_finish, 1, 256, 0, ts, (int*)m12.p, (const unsigned char*)rb.p, n1, check_ori, (int*)res.p);
+    B200_CUDA(cudaStreamSynchronize(ts));
     int r = 0;
-    B200_CUDA(cudaMemcpy(&r, res.p, 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(matches12, m12.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost));
+    B200_D2H(&r, res.p, 4);
+    B200_D2H(matches12, m12.p, (size_t)n1 * 4);
     return r;
 }
 
@@ -1145,8 +1192,10 @@ int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, 
                               const uint8_t* q_desc, int n_queries, const float* inv_level_sigma2, int nlevels, double chi2, int32_t* best_idx,
                               int32_t* best_dist, int device) {
     if (n_kf < 0 || n_queries < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n_queries == 0) return B200_OK;
     if (!best_idx || !best_dist) return fail(B200_EINVAL, "null %s", "output pointer");
     for (int q = 0; q < n_queries; q++) { best_idx[q] = -1; best_dist[q] = 256; }
@@ -1167,19 +1216,19 @@ int b200_match_kf_radius_host(const b200_keypoint* kps_un, const uint8_t* desc, 
         (rc = cand.alloc((size_t)n_queries * row_cap * 4)) || (rc = cnt.alloc((size_t)n_queries * 4)) || (rc = bi.alloc((size_t)n_queries * 4)) ||
         (rc = bd.alloc((size_t)n_queries * 4)) || (rc = ovf.alloc(4)))
         return rc;
-    B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, 0));
-    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
+    B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, ts));
+    if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, ts))) return rc;
     if ((rc = b200_keyframe_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)q3.p,
-                                             (const int32_t*)lv2.p, n_queries, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+                                             (const int32_t*)lv2.p, n_queries, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, ts)))
         return rc;
-    B200_LAUNCH(k_radius_best, (n_queries * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)q3.p,
+    B200_LAUNCH(k_radius_best, (n_queries * 32 + 255) / 256, 256, 0, ts, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)q3.p,
                 (const ulonglong4*)qd.p, (const int*)cand.p, (const int*)cnt.p, row_cap, n_queries, lt, chi2, (int*)bi.p, (int*)bd.p, (int*)ovf.p);
-    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaStreamSynchronize(ts));
     int o = 0;
-    B200_CUDA(cudaMemcpy(&o, ovf.p, 4, cudaMemcpyDeviceToHost));
+    B200_D2H(&o, ovf.p, 4);
     if (o) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
-    B200_CUDA(cudaMemcpy(best_idx, bi.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(best_dist, bd.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost));
+    B200_D2H(best_idx, bi.p, (size_t)n_queries * 4);
+    B200_D2H(best_dist, bd.p, (size_t)n_queries * 4);
     return B200_OK;
 }
 
@@ -1202,8 +1251,10 @@ int b200_kf_search_points_host(const b200_keypoint* kps_un, const uint8_t* desc,
                                const uint8_t* skip, int n, float th, const float* scale_factors, const float* inv_level_sigma2, const float* level_thresholds,
                                int nlevels, double chi2, uint8_t* valid, int32_t* best_idx, int32_t* best_dist, float* q_xyr, int32_t* level, int device) {
     if (n < 0 || n_kf < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n == 0) return B200_OK;
     if (!pos || !minmax || !q_desc || !valid || !best_idx || !best_dist || (n_kf > 0 && (!kps_un || !desc)) || (chi2 > 0 && !inv_level_sigma2))
         return fail(B200_EINVAL, "null %s", "pointer");
@@ -1217,31 +1268,31 @@ int b200_kf_search_points_host(const b200_keypoint* kps_un, const uint8_t* desc,
         (skip && (rc = dsk.upload(skip, (size_t)n))) || (rc = dv.alloc((size_t)n)) || (rc = dq.alloc((size_t)n * 12)) || (rc = dl.alloc((size_t)n * 4)) ||
         (rc = dl2.alloc((size_t)n * 8)) || (rc = qd.upload(q_desc, (size_t)n * 32)) || (rc = bi.alloc((size_t)n * 4)) || (rc = bd.alloc((size_t)n * 4)) || (rc = ovf.alloc(4)))
         return rc;
-    B200_LAUNCH(k_kf_project, (n + 255) / 256, 256, 0, 0, (const float*)dp.p, (const float*)dn.p, (const float*)dm.p, n, g, (unsigned char*)dv.p, (float*)dq.p, (int*)dl.p,
+    B200_LAUNCH(k_kf_project, (n + 255) / 256, 256, 0, ts, (const float*)dp.p, (const float*)dn.p, (const float*)dm.p, n, g, (unsigned char*)dv.p, (float*)dq.p, (int*)dl.p,
                 (const unsigned char*)dsk.p, (int*)dl2.p);
     if (n_kf > 0) {
         if ((rc = k2.upload(kps_un, (size_t)n_kf * sizeof(b200_keypoint))) || (rc = d2.upload(desc, (size_t)n_kf * 32)) || (rc = ncnt.upload(&n_kf, 4)) ||
             (rc = cs.alloc((size_t)(64 * 48 + 1) * 4)) || (rc = ci.alloc((size_t)n_kf * 4)) || (rc = cand.alloc((size_t)n * row_cap * 4)) || (rc = cnt.alloc((size_t)n * 4)))
             return rc;
-        B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, 0));
-        if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, nullptr))) return rc;
+        B200_CUDA(cudaMemsetAsync(ovf.p, 0, 4, ts));
+        if ((rc = b200_frame_assign_grid((const b200_keypoint*)k2.p, (const int32_t*)ncnt.p, 1, n_kf, bounds4, (int32_t*)cs.p, (int32_t*)ci.p, device, ts))) return rc;
         if ((rc = b200_keyframe_features_in_area((const b200_keypoint*)k2.p, (const int32_t*)cs.p, (const int32_t*)ci.p, bounds4, (const float*)dq.p,
-                                                 (const int32_t*)dl2.p, n, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, nullptr)))
+                                                 (const int32_t*)dl2.p, n, (int32_t*)cand.p, (int32_t*)cnt.p, row_cap, device, ts)))
             return rc;
-        B200_LAUNCH(k_radius_best, (n * 32 + 255) / 256, 256, 0, 0, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)dq.p, (const ulonglong4*)qd.p,
+        B200_LAUNCH(k_radius_best, (n * 32 + 255) / 256, 256, 0, ts, (const b200_keypoint*)k2.p, (const ulonglong4*)d2.p, (const float*)dq.p, (const ulonglong4*)qd.p,
                     (const int*)cand.p, (const int*)cnt.p, row_cap, n, lt, chi2, (int*)bi.p, (int*)bd.p, (int*)ovf.p);
     }
-    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaStreamSynchronize(ts));
     if (n_kf > 0) {
         int o = 0;
-        B200_CUDA(cudaMemcpy(&o, ovf.p, 4, cudaMemcpyDeviceToHost));
+        B200_D2H(&o, ovf.p, 4);
         if (o) return fail(B200_ECAPACITY, "more than %s candidates in one search window", "4096");
-        B200_CUDA(cudaMemcpy(best_idx, bi.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-        B200_CUDA(cudaMemcpy(best_dist, bd.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        B200_D2H(best_idx, bi.p, (size_t)n * 4);
+        B200_D2H(best_dist, bd.p, (size_t)n * 4);
     } else for (int i = 0; i < n; i++) { best_idx[i] = -1; best_dist[i] = 256; }
-    B200_CUDA(cudaMemcpy(valid, dv.p, (size_t)n, cudaMemcpyDeviceToHost));
-    if (q_xyr) B200_CUDA(cudaMemcpy(q_xyr, dq.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
-    if (level) B200_CUDA(cudaMemcpy(level, dl.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    B200_D2H(valid, dv.p, (size_t)n);
+    if (q_xyr) B200_D2H(q_xyr, dq.p, (size_t)n * 12);
+    if (level) B200_D2H(level, dl.p, (size_t)n * 4);
     return B200_OK;
 }
 
@@ -1249,8 +1300,10 @@ int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, co
                          const float* pos, const float* normal, const float* minmax, int n, float th, const float* scale_factors,
                          const float* level_thresholds, int nlevels, uint8_t* valid, float* q_xyr, int32_t* level, int device) {
     if (n < 0 || nlevels < 1 || nlevels > 16) return fail(B200_EINVAL, "bad %s", "sizes");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
     if (n == 0) return B200_OK;
     if (!pos || !minmax || !valid || !q_xyr || !level) return fail(B200_EINVAL, "null %s", "pointer");
     ProjGeom g;
@@ -1259,11 +1312,11 @@ int b200_kf_project_host(const float* Rcw, const float* tcw, const float* Ow, co
     if ((rc = dp.upload(pos, (size_t)n * 12)) || (normal && (rc = dn.upload(normal, (size_t)n * 12))) || (rc = dm.upload(minmax, (size_t)n * 8)) ||
         (rc = dv.alloc((size_t)n)) || (rc = dq.alloc((size_t)n * 12)) || (rc = dl.alloc((size_t)n * 4)))
         return rc;
-    B200_LAUNCH(k_kf_project, (n + 255) / 256, 256, 0, 0, (const float*)dp.p, (const float*)dn.p, (const float*)dm.p, n, g, (unsigned char*)dv.p, (float*)dq.p, (int*)dl.p);
-    B200_CUDA(cudaDeviceSynchronize());
-    B200_CUDA(cudaMemcpy(valid, dv.p, (size_t)n, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(q_xyr, dq.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(level, dl.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    B200_LAUNCH(k_kf_project, (n + 255) / 256, 256, 0, ts, (const float*)dp.p, (const float*)dn.p, (const float*)dm.p, n, g, (unsigned char*)dv.p, (float*)dq.p, (int*)dl.p);
+    B200_CUDA(cudaStreamSynchronize(ts));
+    B200_D2H(valid, dv.p, (size_t)n);
+    B200_D2H(q_xyr, dq.p, (size_t)n * 12);
+    B200_D2H(level, dl.p, (size_t)n * 4);
     return B200_OK;
 }
 

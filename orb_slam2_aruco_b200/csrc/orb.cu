@@ -1050,6 +1050,9 @@ struct b200_orb_s {
     cudaStream_t copy_stream; cudaEvent_t ev_copy[2];
     cudaStream_t down_stream; cudaEvent_t ev_done[2];
     cudaStream_t stream2, aux_stream2; cudaEvent_t ev_aux2, ev_ref;       // second stream set: odd chunks of b200_frontend_host
+    // last b200_frontend_host call (b200_frontend_collate_host gathers its device-resident results) and the root's receive buffers
+    int fe_n, fe_mcap, fe_aruco, fe_match;
+    uint8_t* d_coll[7]; size_t cap_coll[7];
     // last call (debug taps)
     const uint8_t* last_imgs; long long last_row_stride, last_frame_stride; int last_n, last_base;
 };
@@ -1366,7 +1369,7 @@ int b200_orb_create(b200_orb_t* out, int nfeatures, float scale_factor, int nlev
     if (nfeatures < 0 || nlevels < 1 || nlevels > kMaxLevels || !(scale_factor > 1.f) || ini_th < 1 || min_th < 1 || ini_th > 254 || min_th > ini_th ||
         max_w < 1 || max_h < 1 || max_batch < 1)
         return fail(B200_EINVAL, "bad %s parameters", "extractor");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     b200_orb_s* h = new (std::nothrow) b200_orb_s();
     if (!h) return B200_ENOMEM;
@@ -1396,7 +1399,7 @@ int b200_orb_create(b200_orb_t* out, int nfeatures, float scale_factor, int nlev
 
 int b200_orb_destroy(b200_orb_t h) {
     if (!h) return B200_OK;
-    cudaSetDevice(h->device);
+    DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_pyr); cudaFree(h->d_tab); cudaFree(h->d_cells); cudaFree(h->d_slots); cudaFree(h->d_cellcnt);
     cudaFree(h->d_keysA); cudaFree(h->d_keysB); cudaFree(h->d_lvlres); cudaFree(h->d_lvlcnt); cudaFree(h->d_err);
     cudaFree(h->d_in); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
@@ -1414,6 +1417,7 @@ int b200_orb_destroy(b200_orb_t h) {
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     cudaFree(h->d_markers); cudaFree(h->d_mcounts); cudaFree(h->d_match); cudaFree(h->d_nmatch); cudaFree(h->d_refdesc); cudaFree(h->d_refkps);
+    for (int b = 0; b < 7; b++) cudaFree(h->d_coll[b]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B200_OK;
@@ -1445,7 +1449,7 @@ int b200_orb_extract(b200_orb_t h, const uint8_t* imgs, int n, int w, int hh, in
     int rc = check_args(h, imgs, n, w, hh, rs, fs);
     if (rc) return rc;
     if (!counts || !kps || !desc) return fail(B200_EINVAL, "null %s", "output pointer");
-    if ((rc = use_device(h->device))) return rc;
+    DeviceScope _ds; if ((rc = use_device(h->device))) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     if (n == 0) return B200_OK;
     if (w == 0 || hh == 0) { B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4, st)); return B200_OK; }   // empty image: no keypoints (ORBextractor.cc:1046)
@@ -1484,7 +1488,7 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
     if (aruco && (!markers || !marker_counts)) return fail(B200_EINVAL, "null %s", "marker output pointer");
     const bool do_match = ref_desc != nullptr;
     if (do_match && (!ref_kps || !match_ref_idx || !n_matches || n_ref < 0)) return fail(B200_EINVAL, "bad %s", "matcher arguments");
-    if ((rc = use_device(h->device))) return rc;
+    DeviceScope _ds; if ((rc = use_device(h->device))) return rc;
     if (n == 0) return B200_OK;
     if (w == 0 || hh == 0) {
         for (int i = 0; i < n; i++) { counts[i] = 0; if (aruco) marker_counts[i] = 0; if (do_match) n_matches[i] = 0; }
@@ -1623,6 +1627,41 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
         if (aruco) { back(markers, o_mk, mk_bytes); back(marker_counts, o_mc, ct_bytes); }
         if (do_match) { back(match_ref_idx, o_ma, ma_bytes); back(n_matches, o_nm, ct_bytes); }
     }
+    h->fe_n = n; h->fe_mcap = mcap; h->fe_aruco = aruco ? 1 : 0; h->fe_match = do_match ? 1 : 0;
+    return B200_OK;
+}
+
+// Sharded front end: every rank has run b200_frontend_host on its own contiguous block of n frames (same n, geometry and
+// options on every rank).  The device-resident copies of those results are gathered at `root` in ONE NCCL group (b200_collate_gather: rank 0
+// is the only consumer, nobody else receives a byte) and the root downloads them rank-major into host buffers [world][n][...] laid out like
+// b200_frontend_host's outputs.  Non-root ranks pass NULL outputs.  Returns when the transfer has completed on the calling rank.
+int b200_frontend_collate_host(b200_orb_t h, b200_collate_t c, int root, b200_keypoint* kps_all, uint8_t* desc_all, int32_t* counts_all,
+                               b200_marker* markers_all, int32_t* marker_counts_all, int32_t* match_all, int32_t* n_matches_all) {
+    if (!h || !c) return fail(B200_EINVAL, "null %s", "handle");
+    if (h->fe_n <= 0) return fail(B200_EINVAL, "no b200_frontend_host call %s", "to collate");
+    const int world = b200_collate_world(c), rank = b200_collate_rank(c);
+    if (root < 0 || root >= world) return fail(B200_EINVAL, "bad %s", "root");
+    DeviceScope _ds; int rc = use_device(h->device);
+    if (rc) return rc;
+    const int n = h->fe_n, cap = b200_orb_max_keypoints(h), mcap = h->fe_mcap;
+    const void* send[7] = {h->d_kps, h->d_desc, h->d_counts, h->d_markers, h->d_mcounts, h->d_match, h->d_nmatch};
+    void* host[7] = {kps_all, desc_all, counts_all, markers_all, marker_counts_all, match_all, n_matches_all};
+    int64_t bytes[7] = {(int64_t)n * cap * (int64_t)sizeof(b200_keypoint), (int64_t)n * cap * 32, (int64_t)n * 4,
+                        h->fe_aruco ? (int64_t)n * mcap * (int64_t)sizeof(b200_marker) : 0, h->fe_aruco ? (int64_t)n * 4 : 0,
+                        h->fe_match ? (int64_t)n * cap * 4 : 0, h->fe_match ? (int64_t)n * 4 : 0};
+    void* recv[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (rank == root)
+        for (int b = 0; b < 7; b++) {
+            if (!bytes[b]) continue;
+            if (!host[b]) return fail(B200_EINVAL, "the root needs every %s", "output buffer");
+            if ((rc = ensure(h->d_coll[b], h->cap_coll[b], (size_t)bytes[b] * world))) return rc;
+            recv[b] = h->d_coll[b];
+        }
+    if ((rc = b200_collate_gather(c, 7, send, recv, bytes, root, h->stream))) return rc;
+    if (rank == root)
+        for (int b = 0; b < 7; b++)
+            if (bytes[b]) B200_CUDA(cudaMemcpyAsync(host[b], h->d_coll[b], (size_t)bytes[b] * world, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
     return B200_OK;
 }
 
@@ -1653,7 +1692,7 @@ int b200_orb_get_stage_ms(b200_orb_t h, float* ms4) {
 int b200_orb_get_pyramid(b200_orb_t h, int frame, int level, uint8_t* out, int* w_l, int* h_l) {
     if (!h || !out) return fail(B200_EINVAL, "null %s", "argument");
     if (!h->last_imgs || frame < 0 || frame >= h->last_n || level < 0 || level >= h->nlevels) return fail(B200_EINVAL, "no such %s", "frame/level");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     const LevelGeom& L = h->geom.L[level];
     std::vector<uint8_t> img((size_t)L.w * L.h);
@@ -1678,7 +1717,7 @@ int b200_orb_get_pyramid(b200_orb_t h, int frame, int level, uint8_t* out, int* 
 int b200_orb_get_candidates(b200_orb_t h, int frame, int level, int32_t* xys, int cap) {
     if (!h || !xys) return fail(B200_EINVAL, "null %s", "argument");
     if (!h->last_imgs || frame < 0 || frame >= h->last_n || level < 0 || level >= h->nlevels) return fail(B200_EINVAL, "no such %s", "frame/level");
-    int rc = use_device(h->device);
+    DeviceScope _ds; int rc = use_device(h->device);
     if (rc) return rc;
     const OrbGeom& g = h->geom;
     const LevelGeom& L = g.L[level];

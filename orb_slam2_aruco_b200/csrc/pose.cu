@@ -290,7 +290,7 @@ int b200_aruco_pose(const b200_marker* markers, const int32_t* counts, int n_bat
     if (n_batch < 0 || marker_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
     if (!(marker_size > 0)) return fail(B200_EINVAL, "markerSize<=0: invalid %s", "markerSize");             // marker.cpp:328
     if (!cam9 || !(cam9[0] != 0) || !(cam9[1] != 0)) return fail(B200_EINVAL, "invalid camera %s", "parameters");     // marker.cpp:309
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     if (n_batch == 0 || marker_cap == 0) return B200_OK;
     if (!markers || !counts || !poses) return fail(B200_EINVAL, "null %s", "pointer");
@@ -305,7 +305,7 @@ int b200_aruco_pose(const b200_marker* markers, const int32_t* counts, int n_bat
 
 int b200_aruco_pose_host(const b200_marker* markers, int n_markers, float marker_size, const float* cam9, b200_marker_pose* poses, int device) {
     if (n_markers < 0) return fail(B200_EINVAL, "negative %s", "size");
-    int rc = use_device(device);
+    DeviceScope _ds; int rc = use_device(device);
     if (rc) return rc;
     if (n_markers == 0) return B200_OK;
     if (!markers || !poses) return fail(B200_EINVAL, "null %s", "pointer");

@@ -147,12 +147,20 @@ class MapFile:
     def observations(self):
         """per map point: [(keyframe position, feature index)] in keyframe load order - MapPoint::AddObservation as LoadKeyFrame calls it
         (Map.cc:521-529).  The reference iterates its std::map<KeyFrame*, size_t> in POINTER order, which no file can pin; load order is
-        the deterministic choice, and it only matters when two observations tie on the median distance."""
+        the deterministic choice, and it only matters when two observations tie on the median distance.  AddObservation returns early when the
+        keyframe already observes the point (MapPoint.cc:122-124): a keyframe listing the same map point at two features contributes its FIRST
+        feature only.  mp_idx is resolved in file order here; Map::Load resolves it through GetAllMapPoints(), a std::set<MapPoint*> in pointer
+        order (Map.cc:428-433, 521-529), which equals file order only while the allocator hands out ascending addresses."""
         obs = [[] for _ in range(len(self.map_points))]
         for k, kf in enumerate(self.keyframes):
             idx = kf["features"]["mp_idx"]
+            seen = set()
             for i in np.nonzero(idx != ULONG_MAX)[0]:
-                obs[int(idx[i])].append((k, int(i)))
+                p = int(idx[i])
+                if p in seen:
+                    continue
+                seen.add(p)
+                obs[p].append((k, int(i)))
         return obs
 
 

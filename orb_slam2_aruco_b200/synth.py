@@ -188,3 +188,30 @@ def make_batch(n, w=640, h=480, markers=0, dict_name="ARUCO_MIP_25h7", first=0):
     for i in range(n):
         out[i] = make_frame(first + i, w, h, markers, dict_name)
     return out
+
+
+def make_view(scene, index, max_rot_deg=3.0, max_shift=8.0, noise_sigma=2.0, rot_deg=None, shift=None):
+    """A perturbed view of `scene` (u8 [h, w]): in-plane rotation about the image centre, translation, fresh sensor noise - the camera moved a little.
+    Bilinear resampling in float64 with reflected borders; view `index` uses Generator(PCG64(20270000 + index)) unless rot_deg / shift are given."""
+    rng = np.random.Generator(np.random.PCG64(20270000 + int(index)))
+    h, w = scene.shape
+    a = np.deg2rad(float(rng.uniform(-max_rot_deg, max_rot_deg)) if rot_deg is None else float(rot_deg))
+    tx, ty = (rng.uniform(-max_shift, max_shift, size=2) if shift is None else shift)
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    ca, sa = np.cos(a), np.sin(a)
+    X = ca * (xs - cx - tx) + sa * (ys - cy - ty) + cx          # inverse map: output pixel -> scene position
+    Y = -sa * (xs - cx - tx) + ca * (ys - cy - ty) + cy
+    x0 = np.floor(X); y0 = np.floor(Y)
+    fx = X - x0; fy = Y - y0
+
+    def refl(i, n):
+        i = np.abs(i.astype(np.int64))
+        i = np.where(i >= n, 2 * (n - 1) - i, i)
+        return np.clip(i, 0, n - 1)
+    xa, xb, ya, yb = refl(x0, w), refl(x0 + 1, w), refl(y0, h), refl(y0 + 1, h)
+    src = scene.astype(np.float64)
+    v = (src[ya, xa] * (1 - fx) + src[ya, xb] * fx) * (1 - fy) + (src[yb, xa] * (1 - fx) + src[yb, xb] * fx) * fy
+    if noise_sigma > 0:
+        v = v + np.floor(rng.normal(0.0, noise_sigma, size=(h, w)) + 0.5)
+    return np.clip(np.floor(v + 0.5), 0, 255).astype(np.uint8)

@@ -69,3 +69,57 @@ def test_collate_single_process_is_identity():
     x = fake_slots(0, 4)
     y = shard.collate(x, 4)
     assert all(torch.equal(x[k], y[k]) for k in x)
+
+
+def test_slot_pack_layout():
+    """the packed result slots: aligned, non-overlapping sections whose views have the shapes the kernels write"""
+    p = shard.SlotPack(4, 1024, 64)
+    spans = sorted(p.offsets.values())
+    assert all(o % 256 == 0 for o, _ in spans) and all(a[0] + a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    assert p.bulk_bytes == p.offsets["markers"][0] and p.total_bytes >= spans[-1][0] + spans[-1][1]
+    assert tuple(p.views["kps"].shape) == (4, 1024, 7) and tuple(p.views["desc"].shape) == (4, 1024, 32) and tuple(p.views["matches"].shape) == (4, 1024)
+    p.views["counts"][:] = torch.tensor([1, 2, 3, 4], dtype=torch.int32)
+    p.views["markers"][2, 5, 0] = 7.0
+    host = p.buf.numpy()
+    nv = p.numpy_views(host)
+    assert nv["counts"].tolist() == [1, 2, 3, 4] and nv["markers"][2, 5]["id"].view(np.float32) == 7.0 and nv["kps"].shape == (4, 1024)
+    q = shard.SlotPack(2, 100, 64, detector=False, matcher=False)            # extract-only: the tail is empty
+    assert q.total_bytes == q.bulk_bytes and "markers" not in q.views
+
+
+def _pack_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, cap = 3, 6
+    pack = shard.SlotPack(n, cap, 2)
+    slots = fake_slots(rank * n, (rank + 1) * n, cap)
+    pack.views["counts"].copy_(slots["counts"]); pack.views["kps"].copy_(slots["kps"]); pack.views["desc"].copy_(slots["desc"])
+    pack.views["matches"].fill_(rank + 10)
+    root_bulk = torch.zeros((world, pack.bulk_bytes), dtype=torch.uint8) if rank == 0 else None
+    root_tail = torch.zeros((world, pack.total_bytes - pack.bulk_bytes), dtype=torch.uint8) if rank == 0 else None
+    w1 = shard.gather_packed(pack.bulk, root_bulk, 0, async_op=True)            # two transfers per step, like bench.py
+    w2 = shard.gather_packed(pack.tail, root_tail, 0, async_op=True)
+    w1.wait(); w2.wait()
+    ok = True
+    if rank == 0:
+        for r in range(world):
+            v = pack.views_of(torch.cat([root_bulk[r], root_tail[r]]))
+            want = fake_slots(r * n, (r + 1) * n, cap)
+            ok = ok and all(torch.equal(v[k], want[k]) for k in want) and bool((v["matches"] == r + 10).all())
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_gather_to_root_world2_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pack_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] for r in res)
