@@ -166,7 +166,8 @@ int b200_distinctive_descriptors_host(const uint8_t* desc, const int32_t* ofs, i
  * The loop-closing SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (include/ORBmatcher.h:52, src/ORBmatcher.cc:294-407) is mode 1 with
  * check_ori = 0, th_high = TH_LOW (50), q_levels = (nPredictedLevel - 1, nPredictedLevel), occupied = "vpMatched[i] != NULL", q_observed = 1;
  * pass mode 2 for it: mode 1 with the keyframe's grid origin (b200_keyframe_features_in_area).
- * assign [n_frame] out = query index assigned to that frame keypoint or -1 (F.mvpMapPoints[bestIdx] = pMP).  Returns nmatches. */
+ * assign [n_frame] out = query index assigned to that frame keypoint (F.mvpMapPoints[bestIdx] = pMP), -1 = untouched, -2 = assigned during the call and
+ * then cleared by the rotation histogram (the reference stores NULL there, src/ORBmatcher.cc:1459-1467).  Returns nmatches. */
 int b200_match_by_projection_host(const b200_keypoint* kps_un, const uint8_t* desc, int n_frame, const float* bounds4, uint8_t* occupied,
                                   const float* q_xyr, const int32_t* q_levels, const uint8_t* q_desc, const float* q_angle, const uint8_t* q_observed,
                                   int n_queries, int mode, float ratio, int check_ori, int th_high, int32_t* assign, int device);
@@ -242,6 +243,10 @@ int b200_aruco_check(b200_aruco_t h, void* stream);
 int b200_aruco_debug(b200_aruco_t h, int frame, int32_t* out4, float* corners, int32_t* ids, int cap);
 int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int width, int height, int64_t row_stride, int64_t frame_stride,
                            b200_marker* markers, int32_t* counts);
+/* aruco::Marker::contourPoints (Thirdparty/aruco/aruco/marker.h:59; copied from the candidate at markerdetector_impl.cpp:6759-6772): the border of output
+ * marker `index` of frame `frame` of the LAST detect call on the handle, in the reference's point order.  xy [cap][2] int32 (HOST); returns the number
+ * of points of the border (the array receives min(cap, that) of them). */
+int b200_aruco_get_contour(b200_aruco_t h, int frame, int index, int32_t* xy, int cap);
 
 
 /* ---------------------------------------------------------------- marker pose -------------------- */

@@ -73,6 +73,21 @@ def ref_match():
     return _ref_match
 
 
+_adapter_match = None
+
+
+def adapter_match():
+    """The PRODUCT's signature-exact ORB_SLAM2::ORBmatcher (include/b200slam_orbmatcher.hpp over libb200slam.so) behind the same wrapper and stand-in objects as
+    ref_match() (oracle/ref_match_wrap.cpp built with -DB200_ADAPTER_MATCHER), or None when it was never built.  Needs a GPU to compute anything."""
+    global _adapter_match
+    if _adapter_match is None:
+        path = os.path.join(HERE, "_ref", "libadapter_match.so")
+        if not os.path.exists(path):
+            return None
+        _adapter_match = C.CDLL(path)
+    return _adapter_match
+
+
 _ref_mappoint = None
 
 

@@ -3,7 +3,14 @@
 // touches) into oracle/_ref/libref_match.so.  Flat arrays in, the matcher's answers out, plus the trace of every Frame::GetFeaturesInArea query the
 // matcher made (so the product path can be given the very same projections).  Used by tests/test_oracle_vs_ref.py to pin oracle/match_oracle.cpp
 // and by tests/golden/make_match_golden.py to write tests/golden/match_ref.npz, which travels to the GPU box.
+// The same file builds oracle/_ref/libadapter_match.so with -DB200_ADAPTER_MATCHER: then the matcher behind these entry points is the PRODUCT's
+// signature-exact ORB_SLAM2::ORBmatcher (include/b200slam_orbmatcher.hpp over libb200slam.so) - every call below is spelled the way the reference's call
+// sites spell it, so the two libraries answer the same questions and tests/test_orbmatcher_exact_gpu.py compares them.
+#ifdef B200_ADAPTER_MATCHER
+#include "b200slam_orbmatcher.hpp"
+#else
 #include "ORBmatcher.h"          // the reference's own header (slam_types.h is force-included in front of it)
+#endif
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -247,6 +254,8 @@ void set_keyframe(KeyFrame& kf, const oracle_keypoint* k, const uint8_t* d, int 
     kf.mnMinX = (int)bounds4[0]; kf.mnMaxX = (int)bounds4[1]; kf.mnMinY = (int)bounds4[2]; kf.mnMaxY = (int)bounds4[3];
     kf.fx = cam4[0]; kf.fy = cam4[1]; kf.cx = cam4[2]; kf.cy = cam4[3];
     if (T) kf.Tcw = mat44(T);
+    // the float bounds every KeyFrame truncates (include/KeyFrame.h:211-214) are Frame's statics (include/Frame.h:191-194)
+    Frame::mnMinX = bounds4[0]; Frame::mnMaxX = bounds4[1]; Frame::mnMinY = bounds4[2]; Frame::mnMaxY = bounds4[3];
     kf.grid.build(kf.mvKeysUn, bounds4);
 }
 void set_points(std::vector<MapPoint>& pts, int n_mp, const uint8_t* state, const float* pos, const float* normal, const uint8_t* desc, const float* minmax,

@@ -606,6 +606,7 @@ def search_by_projection(kps_un, desc, bounds4, occupied, q_xyr, q_levels, q_des
     b = np.ascontiguousarray(bounds4, np.float32)
     n = check(lib().b200_match_by_projection_host(ptr(k), ptr(d), len(k), ptr(b), ptr(occ), ptr(q3), ptr(lv), ptr(qd), ptr(qa), ptr(qo), len(q3), int(mode),
                                                   float(nnratio), int(bool(check_ori)), int(th_high), ptr(assign), int(device)))
+    assign[assign == -2] = -1              # -2 = matched, then cleared by the rotation histogram: no match either way (the C++ adapter needs the difference)
     return n, assign, occ
 
 

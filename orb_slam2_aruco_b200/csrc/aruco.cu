@@ -1002,7 +1002,8 @@ constexpr int kFinWarps = 8;
 __global__ void __launch_bounds__(kFinWarps * 32)
 k_finalize(const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, const int* __restrict__ nkept,
            const Decoded* __restrict__ dec0, const ContourDesc* __restrict__ desc0, const short2* __restrict__ pts0,
-           float* __restrict__ scratch0, b200_marker* __restrict__ out0, int* __restrict__ counts, int out_cap, int* __restrict__ err) {
+           float* __restrict__ scratch0, b200_marker* __restrict__ out0, int* __restrict__ counts, int out_cap, int* __restrict__ err,
+           int* __restrict__ mcontour0) {
     __shared__ int s_idx[kMaxCand], s_id[kMaxCand], s_perim[kMaxCand], s_n, s_m;
     __shared__ float s_c[kMaxCand][8];
     __shared__ unsigned char s_rm[kMaxCand];
@@ -1137,6 +1138,7 @@ k_finalize(const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, 
         if (lane == 0) {
             out[mi].id = s_id[i];
             for (int k = 0; k < 8; k++) out[mi].xy[k] = c[k];
+            mcontour0[(long long)f * kMaxMarkers + mi] = kept[s_src[i]].contour;        // aruco::Marker::contourPoints (b200_aruco_get_contour)
         }
     }
 }
@@ -1166,6 +1168,7 @@ struct b200_aruco_s {
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
+    int* d_mcontour;                          // [max_batch][kMaxMarkers]: the border (ContourDesc index) every output marker came from
 };
 
 namespace {
@@ -1274,6 +1277,8 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     ok = ok && cudaMalloc((void**)&h->d_wpatch, (size_t)kMaxWarp * kMaxWarp * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_whist, sizeof(uint16_t) * 256 * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_wlevel, sizeof(int) * kMaxCand * B) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_mcontour, sizeof(int) * kMaxMarkers * (size_t)B) == cudaSuccess;
+    if (ok) cudaMemset(h->d_mcontour, 0xff, sizeof(int) * kMaxMarkers * (size_t)B);
     ok = ok && cudaMalloc((void**)&h->d_ncont, 7 * B * 4 + 4) == cudaSuccess;
     if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
     h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_nsurv2 = h->d_nfetch + B; h->d_err = h->d_nsurv2 + B;
@@ -1287,7 +1292,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1369,7 +1374,7 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     B200_LAUNCH(k_otsu, dim3(kMaxCand / 128, n), 128, 0, st, g, d_nkept, d_whist, d_wlevel);
     B200_LAUNCH(k_decode<1>, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec, d_wpatch, d_whist, d_wlevel);
     B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, d_kept, d_nkept, d_dec, d_desc, d_pts, d_scratch,
-                markers, counts, kMaxMarkers, h->d_err);
+                markers, counts, kMaxMarkers, h->d_err, h->d_mcontour + (size_t)base * kMaxMarkers);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -1423,6 +1428,30 @@ int b200_aruco_debug(b200_aruco_t h, int frame, int32_t* out4, float* corners, i
     }
     out4[3] = nm;
     return B200_OK;
+}
+
+// aruco::Marker::contourPoints (Thirdparty/aruco/aruco/marker.h:59; the detector copies the candidate's border into the marker at
+// markerdetector_impl.cpp:6759-6772): the border of output marker `index` of frame slot `frame` of the LAST detect call, in the reference's
+// point order (Suzuki border following from the canonical start).  xy [cap][2] int32; returns the number of points of the border.
+int b200_aruco_get_contour(b200_aruco_t h, int frame, int index, int32_t* xy, int cap) {
+    if (!h || (!xy && cap > 0)) return fail(B200_EINVAL, "null %s", "argument");
+    if (frame < 0 || frame >= h->max_batch || index < 0 || index >= kMaxMarkers) return fail(B200_EINVAL, "no such %s", "frame / marker");
+    DeviceScope _ds; int rc = use_device(h->device);
+    if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    int ci = -1;
+    B200_CUDA(cudaMemcpy(&ci, h->d_mcontour + (size_t)frame * kMaxMarkers + index, 4, cudaMemcpyDeviceToHost));
+    if (ci < 0 || ci >= h->geom.max_contours) return fail(B200_EINVAL, "no such %s", "marker in the last call");
+    ContourDesc cd;
+    B200_CUDA(cudaMemcpy(&cd, h->d_desc + (size_t)frame * h->geom.max_contours + ci, sizeof(cd), cudaMemcpyDeviceToHost));
+    if (cd.len <= 0 || cd.off < 0 || (long long)cd.off + cd.len > h->geom.max_points) return fail(B200_EINVAL, "stale %s", "contour");
+    const int m = std::min(cd.len, cap);
+    if (m > 0) {
+        std::vector<short2> p(m);
+        B200_CUDA(cudaMemcpy(p.data(), h->d_pts + (size_t)frame * h->geom.max_points + cd.off, sizeof(short2) * m, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) { xy[2 * i] = p[i].x; xy[2 * i + 1] = p[i].y; }
+    }
+    return cd.len;
 }
 
 int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,

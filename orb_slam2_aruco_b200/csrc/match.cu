@@ -468,7 +468,7 @@ k_proj_resolve(const b200_keypoint* __restrict__ k2, int n2, const int* __restri
         int removed = 0;
         for (int e = lane; e < nent; e += 32) {
             const int bin = ent_bin[e];
-            if (bin != a && bin != b && bin != c) { assign[ent_idx[e]] = -1; removed++; }
+            if (bin != a && bin != b && bin != c) { assign[ent_idx[e]] = -2; removed++; }     // -2: assigned, then cleared (the reference stores NULL there)
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
