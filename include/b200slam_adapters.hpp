@@ -31,6 +31,7 @@
 #else
 namespace cv {
 struct Point2f { float x, y; Point2f(float _x = 0, float _y = 0) : x(_x), y(_y) {} };
+struct Point { int x, y; Point(int _x = 0, int _y = 0) : x(_x), y(_y) {} };
 struct KeyPoint { Point2f pt; float size, angle, response; int octave, class_id; };
 static const int CV_8UC1_ = 0;
 #define CV_8U 0
@@ -109,7 +110,17 @@ public:
         d.create(n, 32, CV_8U);
 #endif
         for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), &desc_[(size_t)i * 32], 32);
+        if (fillImagePyramid) fillPyramid();
     }
+
+    // public member of the reference (include/ORBextractor.h:85): the level images of the LAST call.  Only the stereo path reads it (src/Frame.cc:456), so it
+    // is filled on request: set fillImagePyramid (one device-to-host copy per level and call) or call ComputePyramidMember() after operator().  Every entry is
+    // the level's (w_l + 38) x (h_l + 38) buffer with the 19-px REFLECT_101 border, and mvImagePyramidOffset = 19: the reference's entries are ROIs at (19, 19)
+    // of exactly such buffers (src/ORBextractor.cc:1107-1132); with real OpenCV use mvImagePyramid[l](cv::Rect(19, 19, w_l, h_l)).
+    std::vector<cv::Mat> mvImagePyramid;
+    bool fillImagePyramid = false;
+    static const int mvImagePyramidOffset = 19;
+    void ComputePyramidMember() { fillPyramid(); }
 
     int inline GetLevels() { return nlevels_; }
     float inline GetScaleFactor() { return scale_; }
@@ -133,6 +144,16 @@ public:
     }
 
 private:
+    void fillPyramid() {
+        mvImagePyramid.resize(nlevels_);
+        std::vector<unsigned char> buf((size_t)(w_ + 38) * (ht_ + 38));
+        for (int l = 0; l < nlevels_; l++) {
+            int wl = 0, hl = 0;
+            b200slam_detail::check(b200_orb_get_pyramid(h_, 0, l, buf.data(), &wl, &hl));
+            mvImagePyramid[l].create(hl + 38, wl + 38, CV_8U);
+            for (int y = 0; y < hl + 38; y++) std::memcpy(mvImagePyramid[l].ptr(y), &buf[(size_t)y * (wl + 38)], (size_t)wl + 38);
+        }
+    }
     void ensure(int w, int h) {
         if (h_ && w <= w_ && h <= ht_) return;
         if (h_) { b200_orb_destroy(h_); h_ = nullptr; }
@@ -158,9 +179,17 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0) : mfNNratio(nnratio), mbCheckOrientation(checkOri), device_(device) {}
 
     // Computes the Hamming distance between two ORB descriptors (ORBmatcher.h:44)
+    // One pair stays on the host (a popcount over four 64-bit words): the reference calls it O(N^2) times per map point (src/MapPoint.cc:310);
+    // the batched forms are b200_hamming_matrix_host and ComputeDistinctiveDescriptors below.
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
-        int32_t d = 0;
-        b200slam_detail::check(b200_hamming_matrix_host(a.ptr(0), 1, b.ptr(0), 1, &d, 0));
+        const unsigned char* pa = a.ptr(0);
+        const unsigned char* pb = b.ptr(0);
+        int d = 0;
+        for (int i = 0; i < 4; i++) {
+            uint64_t x, y;
+            std::memcpy(&x, pa + 8 * i, 8); std::memcpy(&y, pb + 8 * i, 8);
+            d += __builtin_popcountll(x ^ y);
+        }
         return d;
     }
 
@@ -593,6 +622,8 @@ public:
 #else
     float Rvec[3], Tvec[3];
 #endif
+    std::string dict_info;                 // additional info about the dictionary (marker.h:57): Dictionary::getName() of the table the id came from
+    std::vector<cv::Point> contourPoints;  // points of the contour (marker.h:59), copied from the candidate's border (markerdetector_impl.cpp:6759-6772)
     float pose2_rvec[3], pose2_tvec[3], err1, err2;      // the second IPPE solution and both reprojection errors (Frame.cc:155-177)
     Marker() : id(-1), ssize(-1), err1(-1), err2(-1) {
 #ifdef B200SLAM_NO_OPENCV
@@ -742,9 +773,17 @@ public:
         int32_t n = 0;
         b200slam_detail::check(b200_aruco_detect_host(h_, input.data, 1, input.cols, input.rows, (int64_t)input.step, (int64_t)input.step * input.rows, m.data(), &n));
         std::vector<Marker> out(n);
+        std::vector<int32_t> cp;
         for (int i = 0; i < n; i++) {
             out[i].id = m[i].id;
             for (int k = 0; k < 4; k++) out[i].push_back(cv::Point2f(m[i].xy[2 * k], m[i].xy[2 * k + 1]));
+            out[i].dict_info = dict_;                                                                // Dictionary::getName() (dictionary.cpp:118-231)
+            int len = b200_aruco_get_contour(h_, 0, i, nullptr, 0);                                  // markerdetector_impl.cpp:6759-6772
+            b200slam_detail::check(len);
+            cp.resize((size_t)2 * len + 2);
+            b200slam_detail::check(b200_aruco_get_contour(h_, 0, i, cp.data(), len));
+            out[i].contourPoints.resize(len);
+            for (int j = 0; j < len; j++) out[i].contourPoints[j] = cv::Point(cp[2 * j], cp[2 * j + 1]);
         }
         if (n > 0 && camParams.isValid() && markerSizeMeters > 0) {
             // markerdetector_impl.cpp detect(input, markers, camParams, size, ...): "if (camParams.CamSize != input.size() && camParams.isValid() &&

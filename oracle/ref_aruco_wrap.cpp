@@ -9,6 +9,7 @@
 // detect() runs without camera parameters here, the pose is a separate row of the scope table (oracle/ippe_oracle.cpp, pinned to cv2's IPPE); the few
 // members the linked sources name are defined below.
 #include <atomic>
+#include <cstring>
 #include <thread>
 #include "cameraparameters.h"
 #include "ippe.h"
@@ -53,6 +54,28 @@ int ref_aruco_detect(const uint8_t* img, int w, int h, int stride, const char* d
     aruco::MarkerDetector det;
     configure(det, dict_name);
     return run(det, img, w, h, stride, out, cap);
+}
+
+// the same call, returning also what else the reference stores in every aruco::Marker (marker.h:57-59): dict_info (names [cap][32]) and contourPoints
+// (contour_ofs [cap + 1] offsets into contour_xy [xy_cap][2]).  Pins the adapter's Marker::contourPoints / dict_info (tests/test_adapters_gpu.py).
+int ref_aruco_detect_contours(const uint8_t* img, int w, int h, int stride, const char* dict_name, oracle_marker* out, int cap, char* names,
+                              int32_t* contour_ofs, int32_t* contour_xy, int xy_cap) {
+    aruco::MarkerDetector det;
+    configure(det, dict_name);
+    cv::Mat m(h, w, CV_8UC1, (void*)img, (size_t)stride);
+    std::vector<aruco::Marker> ms = det.detect(m);
+    int n = 0, pts = 0;
+    contour_ofs[0] = 0;
+    for (size_t i = 0; i < ms.size() && n < cap; i++, n++) {
+        out[n].id = ms[i].id;
+        for (int k = 0; k < 4; k++) { out[n].xy[2 * k] = ms[i][k].x; out[n].xy[2 * k + 1] = ms[i][k].y; }
+        memset(names + 32 * n, 0, 32);
+        strncpy(names + 32 * n, ms[i].dict_info.c_str(), 31);
+        for (size_t j = 0; j < ms[i].contourPoints.size(); j++, pts++)
+            if (pts < xy_cap) { contour_xy[2 * pts] = ms[i].contourPoints[j].x; contour_xy[2 * pts + 1] = ms[i].contourPoints[j].y; }
+        contour_ofs[n + 1] = pts;
+    }
+    return n;
 }
 
 // batch driver for the CPU reference arm of bench.py: one detector object per worker thread (the reference keeps one static instance, src/Frame.cc:41),

@@ -783,9 +783,10 @@ class FrontEnd:
             images = np.ascontiguousarray(images)
         n, h, w = images.shape
         ex, det = self.extractor, self.detector
-        ex._ensure(w, h, n)
+        # batches above 256 frames stream through two 128-frame scratch regions (b200_frontend_host): the handles never need more than 256 slots
+        ex._ensure(w, h, min(n, 256))
         if det is not None:
-            det._ensure(w, h, n)
+            det._ensure(w, h, min(n, 256))
         if out is None:
             out = self.alloc_outputs(n)
         do_match = ref_desc is not None and self.matcher is not None

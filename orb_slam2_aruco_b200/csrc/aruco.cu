@@ -29,6 +29,7 @@
 //   k_finalize    CTA per frame: stable sort by id, duplicate removal (8159-8311), CORNER_LINES refinement with the
 //                 float one-sided Jacobi SVD of cv::solve(DECOMP_SVD) (8979-12049)
 #include "common.h"
+#include <atomic>
 #include <math.h>
 #include <float.h>
 #include <algorithm>
@@ -416,6 +417,240 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
             const Step st = next_step(mask[p], s);
             const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
             p += dy * g.bpitch + dx; x += dx; y += dy;
+            s = (st.d + 4) & 7;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A2, shared-memory form (the default whenever the frame's bit image fits): the walks above cost one dependent L2 / HBM load per border
+// step, so their kernels last as long as the longest border times the memory latency.  The thresholded image is one BIT per pixel:
+// 41 KB at 640 x 480, 124 KB at 1280 x 720.  One CTA per frame stages it in shared memory as OVERLAPPED words - word k of a row holds
+// pixels 30k - 1 .. 30k + 30, so every pixel has a word in which it sits at bit 1 .. 30 and its 3 x 3 neighbourhood is three shifts of
+// three words (rows above / at / below) - and then runs every phase against shared memory:
+//   0. stage: mask bytes -> bits (non-zero test + multiply gather), transitions (foreground with a zero West / East neighbour) appended to
+//      the frame's list, overlapped words by funnel shifts
+//   1. backward check of every transition (phase B1 above), survivors to the second list
+//   2. forward walkers over the survivors (phase B2 above), contours longer than 70 points recorded
+//   3. the recorded borders are walked once more to write their points (k_emit above)
+// The step logic (next_step / prev_step / step_key) is the one above; only the source of the 8-neighbour mask differs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCtThreads = 512;
+constexpr int kCtWarps = kCtThreads / 32;
+
+// 8-neighbour mask (bit d = neighbour in direction d) of the pixel at bit `pos` (1 .. 30) of overlapped word `a`; pw = words per row
+__device__ __forceinline__ int ow_mask(const uint32_t* __restrict__ ow, int a, int pos, int pw) {
+    const unsigned t = (ow[a - pw] >> (pos - 1)) & 7u, m = (ow[a] >> (pos - 1)) & 7u, b = (ow[a + pw] >> (pos - 1)) & 7u;
+    return (int)(((m >> 2) & 1u) | ((__brev(t) >> 29) << 1) | ((m & 1u) << 4) | (b << 5));
+}
+
+struct OwPos { int p, a, pos; };      // p: index into the padded mask image (raster key); (a, pos): the same pixel in the overlapped bit image
+
+__device__ __forceinline__ OwPos ow_from_p(int p, int bpitch, int pw) {
+    OwPos o;
+    const int row = p / bpitch, x = p - row * bpitch - kMaskPad;       // row = y + 1
+    const int k = (x * 34953) >> 20;                                   // x / 30 for x < 2^15
+    o.p = p; o.a = row * pw + k; o.pos = x - 30 * k + 1;
+    return o;
+}
+
+__device__ __forceinline__ void ow_move(OwPos& o, int d, int bpitch, int pw) {
+    const int dx = ((0x901A >> (2 * d)) & 3) - 1, dy = ((0xA901 >> (2 * d)) & 3) - 1;
+    o.p += dy * bpitch + dx;
+    o.a += dy * pw;
+    o.pos += dx;
+    if (o.pos == 0) { o.pos = 30; o.a -= 1; } else if (o.pos == 31) { o.pos = 1; o.a += 1; }
+}
+
+__global__ void __launch_bounds__(kCtThreads)
+k_contours(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, int pw, int npw,
+           int* __restrict__ cand0, int* __restrict__ ncand, int max_cand, int* __restrict__ surv0, int* __restrict__ nsurv,
+           ContourDesc* __restrict__ desc0, int* __restrict__ ncont, int* __restrict__ npts, short2* __restrict__ pts0, int* __restrict__ err) {
+    extern __shared__ __align__(16) uint32_t ct_raw[];
+    __shared__ int s_ncand, s_nsurv, s_fetch, s_ncont, s_npts;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    uint32_t* ow = ct_raw;                                   // [(h + 2)][pw]
+    uint32_t* prow = ct_raw + (g.h + 2) * pw + warp * (npw + 4);           // per warp: one plain bit row with a zero word in front and behind
+    int* cand = cand0 + (long long)f * max_cand;
+    int* surv = surv0 + (long long)f * max_cand;
+    ContourDesc* desc = desc0 + (long long)f * g.max_contours;
+    if (tid == 0) { s_ncand = 0; s_nsurv = 0; s_fetch = 0; s_ncont = 0; s_npts = 0; }
+    for (int i = tid; i < pw; i += kCtThreads) { ow[i] = 0u; ow[(g.h + 1) * pw + i] = 0u; }
+    if (lane < 4) { prow[0] = 0u; prow[npw + 1 + (lane & 1)] = 0u; prow[npw + 3] = 0u; }
+    __syncthreads();
+    // ---- phase 0: bits, transitions, overlapped words; one row per warp and iteration
+    for (int y = warp; y < g.h; y += kCtWarps) {
+        const uint8_t* mrow = mask + (long long)(y + 1) * g.bpitch + kMaskPad;
+        for (int j = lane; j < npw; j += 32) {
+            unsigned bits = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int x = 32 * j + 4 * q;
+                if (x < g.w) {                                   // bytes past the width inside the last word are zero (padding)
+                    const uint32_t m = *reinterpret_cast<const uint32_t*>(mrow + x);
+                    const uint32_t nz = ((((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u) >> 7;
+                    bits |= ((nz * 0x00204081u) >> 21 & 0xfu) << (4 * q);
+                }
+            }
+            prow[1 + j] = bits;
+        }
+        __syncwarp();
+        // transitions of this row (phase A above): foreground with a zero West (outer start) / East (hole start) neighbour
+        int base_row = 0;
+        for (int j0 = 0; j0 < npw; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned w = 0, co = 0, ch = 0;
+            if (j < npw) {
+                w = prow[1 + j];
+                co = w & ~((w << 1) | (prow[j] >> 31));
+                ch = w & ~((w >> 1) | (prow[2 + j] << 31));
+            }
+            const int k = __popc(co) + __popc(ch);
+            int sc = k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+            const int tot = __shfl_sync(0xffffffffu, sc, 31);
+            if (tot) {
+                if (lane == 0) base_row = atomicAdd(&s_ncand, tot);
+                base_row = __shfl_sync(0xffffffffu, base_row, 0);
+                int idx = base_row + sc - k;
+                if (idx + k > max_cand) { if (k) atomicExch(err, 8); }
+                else {
+                    const int P0 = (y + 1) * g.bpitch + kMaskPad + 32 * j;
+                    unsigned both = co | ch;
+                    while (both) {
+                        const int b = __ffs(both) - 1;
+                        both &= both - 1;
+                        if (co & (1u << b)) cand[idx++] = P0 + b;
+                        if (ch & (1u << b)) cand[idx++] = (P0 + b) | (1 << 30);
+                    }
+                }
+            }
+        }
+        for (int k = lane; k < pw; k += 32) {
+            const int o = 30 * k + 31, j = o >> 5;               // bit offset of pixel 30k - 1 in the row that starts with the zero word
+            ow[(y + 1) * pw + k] = __funnelshift_r(prow[j], prow[j + 1], o & 31);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    const int ns = min(s_ncand, max_cand);
+    const int limit = 4 * g.max_points;
+    // ---- phase 1: backward check (k_probe_b1)
+    for (int i0 = 0; i0 < ns; i0 += kCtThreads) {
+        const int i = i0 + tid;
+        bool keep = false;
+        int e = 0;
+        if (i < ns) {
+            e = cand[i];
+            const bool hole = (e >> 30) & 1;
+            const int P = e & 0x3fffffff;
+            OwPos o = ow_from_p(P, g.bpitch, pw);
+            const int m0 = ow_mask(ow, o.a, o.pos, pw);
+            const int from = hole ? 7 : 3;
+            const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
+            if (rot != 0) {
+                const int s0 = (from + 1 + (31 - __clz(rot))) & 7;
+                const int mykey = P + (hole ? 1 : 0);
+                const Step st = next_step(m0, s0);
+                if (!(step_key(P, s0, st.k) < mykey)) {
+                    int s = s0, n = 0;
+                    for (;;) {
+                        const int d = (s + 4) & 7;
+                        ow_move(o, s, g.bpitch, pw);
+                        int sq, kq;
+                        prev_step(ow_mask(ow, o.a, o.pos, pw), d, sq, kq);
+                        s = sq;
+                        if (o.p == P && s == s0) { keep = true; break; }
+                        const int key = step_key(o.p, s, kq);
+                        if (key < mykey) break;
+                        if (key != 0x7fffffff) { keep = true; break; }
+                        if (++n > limit) { atomicExch(err, 3); break; }
+                    }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nsurv, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) surv[base + __popc(m & ((1u << lane) - 1))] = e;
+        }
+    }
+    __syncthreads();
+    const int nsv = min(s_nsurv, max_cand);
+    // ---- phase 2: forward walkers (k_probe_b), lanes refill in batches
+    {
+        int P = 0, s0 = 0, mykey = 0, s = 0, n = 0;
+        OwPos o; o.p = 0; o.a = pw; o.pos = 1;
+        bool busy = false, exhausted = false;
+        for (;;) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+            if (!exhausted && (__popc(idle) >= 8 || idle == 0xffffffffu)) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_fetch, __popc(idle));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + __popc(idle) >= nsv) exhausted = true;
+                if (!busy) {
+                    const int i = base + __popc(idle & ((1u << lane) - 1));
+                    if (i < nsv) {
+                        const int e = surv[i];
+                        const bool hole = (e >> 30) & 1;
+                        P = e & 0x3fffffff;
+                        o = ow_from_p(P, g.bpitch, pw);
+                        const int m0 = ow_mask(ow, o.a, o.pos, pw);
+                        const int from = hole ? 7 : 3;
+                        const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
+                        s0 = (from + 1 + (31 - __clz(rot))) & 7;
+                        mykey = P + (hole ? 1 : 0);
+                        s = s0; n = 0; busy = true;
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, busy)) { if (exhausted) break; else continue; }
+            if (busy) {
+                const Step st = next_step(ow_mask(ow, o.a, o.pos, pw), s);
+                if (n > 0 && step_key(o.p, s, st.k) < mykey) busy = false;
+                else {
+                    ow_move(o, st.d, g.bpitch, pw);
+                    s = (st.d + 4) & 7;
+                    n++;
+                    if (o.p == P && s == s0) {
+                        busy = false;
+                        if (n > kMinContour) {
+                            const int idx = atomicAdd(&s_ncont, 1);
+                            if (idx >= g.max_contours) atomicExch(err, 4);
+                            else {
+                                const int off = atomicAdd(&s_npts, n);
+                                ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off;
+                                if (off + n > g.max_points) { atomicExch(err, 5); c.len = 0; c.off = 0; }      // the call fails; keep the slot harmless
+                                desc[idx] = c;
+                            }
+                        }
+                    } else if (n > limit) { atomicExch(err, 3); busy = false; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: the points of the recorded borders (k_emit)
+    const int nc = min(s_ncont, g.max_contours);
+    if (tid == 0) { ncont[f] = s_ncont; npts[f] = s_npts; ncand[f] = s_ncand; nsurv[f] = s_nsurv; }
+    short2* pts = pts0 + (long long)f * g.max_points;
+    for (int i = tid; i < nc; i += kCtThreads) {
+        const ContourDesc c = desc[i];
+        if (c.len <= 0 || c.off + c.len > g.max_points) continue;
+        short2* out = pts + c.off;
+        OwPos o = ow_from_p(c.start, g.bpitch, pw);
+        int s = c.s0;
+        int x = c.start % g.bpitch - kMaskPad, y = c.start / g.bpitch - 1;
+        for (int n = 0; n < c.len; n++) {
+            out[n] = make_short2((short)x, (short)y);
+            const Step st = next_step(ow_mask(ow, o.a, o.pos, pw), s);
+            x += ((0x901A >> (2 * st.d)) & 3) - 1; y += ((0xA901 >> (2 * st.d)) & 3) - 1;
+            ow_move(o, st.d, g.bpitch, pw);
             s = (st.d + 4) & 7;
         }
     }
@@ -1345,9 +1580,20 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
         dim3 gp((g.lw[l] + 31) / 32, (g.lh[l] + 7) / 8, n);
         B200_LAUNCH(k_halfpyr, gp, blk, 0, st, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
     }
+    // contour following: against the frame's bit image in shared memory when it fits (one CTA per frame), else the global-memory walkers
+    const int ct_pw = (w + 1) / 30 + 1, ct_npw = (w + 31) / 32;
+    const size_t ct_smem = ((size_t)(hh + 2) * ct_pw + (size_t)kCtWarps * (ct_npw + 4)) * 4;
+    static const bool ct_global = getenv("B200_CONTOURS_GLOBAL") != nullptr;
+    const bool ct_shared = !ct_global && ct_smem <= 200 * 1024 && w < 32768 / 2;
+    if (ct_shared) {
+        static std::atomic<size_t> ct_smem_set(0);
+        if (ct_smem > 48 * 1024 && ct_smem > ct_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_contours, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem)); ct_smem_set.store(ct_smem); }
+        B200_LAUNCH(k_contours, n, kCtThreads, ct_smem, st, d_mask, g, ct_pw, ct_npw, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, d_desc, d_ncont, d_npts,
+                    d_pts, h->d_err);
+    }
     dim3 gm((w + 127) / 128, (hh + 7) / 8, n);
-    B200_LAUNCH(k_probe_a, gm, blk, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, h->d_err);
-    {
+    if (!ct_shared) B200_LAUNCH(k_probe_a, gm, blk, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, h->d_err);
+    if (!ct_shared) {
         dim3 g1(16, n);
         B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err);
         // persistent CTAs; frames are the fast grid index.  A border occupies ONE lane for its whole length and every step is a dependent
@@ -1361,7 +1607,7 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
     {
         dim3 ge(4, n);
-        B200_LAUNCH(k_emit, ge, 128, 0, st, d_mask, g, d_desc, d_ncont, d_pts);
+        if (!ct_shared) B200_LAUNCH(k_emit, ge, 128, 0, st, d_mask, g, d_desc, d_ncont, d_pts);
         dim3 gq(48, n);
         B200_LAUNCH(k_quads, gq, kQuadWarps * 32, 0, st, g, d_desc, d_ncont, d_pts, d_cand, d_ncand, h->d_err);
     }

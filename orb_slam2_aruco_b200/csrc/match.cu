@@ -13,6 +13,7 @@
 //                    top-K lists (exact; a list that runs dry while a match is still possible triggers a
 //                    warp-wide rescan of the whole row), then the rotation histogram filter.
 #include "common.h"
+#include <atomic>
 
 namespace b200 {
 
@@ -78,6 +79,187 @@ k_match_topk(const ulonglong4* __restrict__ ref_desc, int n_ref,
             }
             if (lane == 0) out[k] = m;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same top-K lists from the 5th-generation tensor cores.  Hamming(a, b) = |a| + |b| - 2 a.b over 256-bit descriptors is a dense binary
+// contraction: with the bits expanded to 0 / 1 bytes, a.b is an int8 GEMM with exact int32 accumulators (tcgen05.mma kind::i8, M = 128
+// reference rows x N = 128 frame descriptors x K = 256 per tile, 8 instructions of K = 32), and the POPC-bound inner loop above (8 POPC per
+// pair on the 16-lane XU pipe) disappears.  One CTA = one frame x 128 reference rows, 256 threads:
+//   * operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices; 128 bytes to the
+//     next K chunk, 2048 bytes to the next 8 rows); the expansion writes them directly (nibble * 0x00204081 & 0x01010101 = 4 bytes)
+//   * two TMEM accumulator buffers of 128 columns and two B tiles: the MMAs of tile t + 1 are issued (one elected thread, tcgen05.commit
+//     on an mbarrier) before the epilogue of tile t starts
+//   * epilogue: thread (row, half) reads its 64 int32 dot products with tcgen05.ld.32x32b, forms |b| - 2 a.b, compares with dstar - |a|
+//     and inserts the few survivors into its sorted K-list; the two halves of a row are merged through shared memory
+// The lists are bit-identical to k_match_topk's (the K smallest keys dist << 16 | index below dstar), so k_match_resolve is unchanged.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMmaThreads = 256, kMmaM = 128, kMmaN = 128;
+constexpr int kMmaLbo = 128, kMmaSbo = 2048, kMmaTile = 32768;            // bytes: next K chunk, next 8-row group, one expanded 128 x 256 tile
+constexpr int kMmaSmem = 3 * kMmaTile + 4096 + 2 * kMmaN * 4 + kMmaM * 4 + kMmaM * kTopK * 4 + 64;
+
+__device__ __forceinline__ uint32_t mma_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 128 raw descriptors (32 bytes each, shared memory) -> 128 x 256 bytes of 0 / 1 in the UMMA K-major no-swizzle layout
+__device__ __forceinline__ void mma_expand(const unsigned char* __restrict__ raw, unsigned char* __restrict__ dst, int tid) {
+    for (int idx = tid; idx < kMmaM * 16; idx += kMmaThreads) {
+        const int r = idx & (kMmaM - 1), c = idx >> 7;                  // descriptor, 16-bit chunk
+        const unsigned bits = reinterpret_cast<const unsigned short*>(raw)[r * 16 + c];
+        uint4 v;
+        v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+        v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+        v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+        v.w = ((bits >> 12) * 0x00204081u) & 0x01010101u;
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * kMmaSbo + c * kMmaLbo + (r & 7) * 16) = v;
+    }
+}
+
+__device__ __forceinline__ unsigned long long mma_desc(uint32_t saddr) {
+    // UMMA shared-memory descriptor: start address, leading (K) and stride (M / N) byte offsets in 16-byte units, version 1 (sm_100), no swizzle
+    const uint32_t lo = ((saddr >> 4) & 0x3fffu) | ((uint32_t)(kMmaLbo >> 4) << 16);
+    const uint32_t hi = (uint32_t)(kMmaSbo >> 4) | (1u << 14);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(kMmaThreads)
+k_match_mma(const ulonglong4* __restrict__ ref_desc, int n_ref, const ulonglong4* __restrict__ frame_desc, const int* __restrict__ n_frame,
+            int frame_cap, uint32_t* __restrict__ topk, int dstar) {
+    extern __shared__ __align__(1024) unsigned char mm_raw[];
+    unsigned char* sA = mm_raw;
+    unsigned char* sB = mm_raw + kMmaTile;                               // two tiles
+    unsigned char* sRaw = mm_raw + 3 * kMmaTile;
+    int* s_nb = reinterpret_cast<int*>(sRaw + 4096);                      // [2][128]
+    int* s_na = s_nb + 2 * kMmaN;
+    uint32_t* s_merge = reinterpret_cast<uint32_t*>(s_na + kMmaM);       // [128][kTopK]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_merge + kMmaM * kTopK);     // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.y, m0 = blockIdx.x * kMmaM;
+    const int nf = min(n_frame[f], frame_cap);
+    const int ntiles = (nf + kMmaN - 1) / kMmaN;
+    const uint4* fd = reinterpret_cast<const uint4*>(frame_desc + (long long)f * frame_cap);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(mma_smem_u32(s_tmem)), "r"(2 * kMmaN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mma_smem_u32(&s_bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mma_smem_u32(&s_bar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- A: this CTA's 128 reference rows (rows past n_ref are zero), expanded once
+    {
+        const uint4* rd = reinterpret_cast<const uint4*>(ref_desc + m0);
+        const int row = tid >> 1;
+        reinterpret_cast<uint4*>(sRaw)[tid] = (m0 + row < n_ref) ? rd[tid] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    if (tid < kMmaM) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(sRaw) + tid * 8;
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) c += __popc(w[k]);
+        s_na[tid] = c;
+    }
+    mma_expand(sRaw, sA, tid);
+    __syncthreads();                                                    // sRaw is free again; s_tmem is visible
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *s_tmem;
+    const uint32_t idesc = (2u << 4) | ((uint32_t)(kMmaN >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);     // D = S32, A = B = u8 K-major, N, M
+    const unsigned long long descA = mma_desc(mma_smem_u32(sA));
+
+    // stage + expand frame tile t into B buffer t & 1 (descriptors past nf: zero rows, |b| = 10000 so that they never qualify)
+    auto load_b = [&](int t) {
+        const int i0 = t * kMmaN, row = tid >> 1;
+        reinterpret_cast<uint4*>(sRaw)[tid] = (i0 + row < nf) ? fd[(long long)i0 * 2 + tid] : make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if (tid < kMmaN) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(sRaw) + tid * 8;
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) c += __popc(w[k]);
+            s_nb[(t & 1) * kMmaN + tid] = (i0 + tid < nf) ? c : 10000;
+        }
+        mma_expand(sRaw, sB + (t & 1) * kMmaTile, tid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async proxy
+    };
+    auto issue = [&](int t) {                                           // one thread: 8 x (128 x 128 x 32) into TMEM buffer t & 1
+        const unsigned long long descB = mma_desc(mma_smem_u32(sB + (t & 1) * kMmaTile));
+        const uint32_t d_tmem = tmem + (uint32_t)((t & 1) * kMmaN);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned long long a = descA + (unsigned long long)(k * 2 * kMmaLbo >> 4), b = descB + (unsigned long long)(k * 2 * kMmaLbo >> 4);
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}"
+                         :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(k), "r"(0u) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mma_smem_u32(&s_bar[t & 1])) : "memory");
+    };
+
+    uint32_t tk[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; k++) tk[k] = 0xffffffffu;
+    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int thr = dstar - s_na[row], na = s_na[row];
+    if (ntiles > 0) {
+        load_b(0);
+        __syncthreads();
+        if (tid == 0) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); issue(0); }
+    }
+    for (int t = 0; t < ntiles; t++) {
+        if (t + 1 < ntiles) load_b(t + 1);                              // its buffers were last used by tile t - 1, whose MMAs and epilogue are done
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t + 1 < ntiles && tid == 0) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); issue(t + 1); }
+        {   // wait for tile t's accumulators
+            const uint32_t bar = mma_smem_u32(&s_bar[t & 1]), parity = (uint32_t)((t >> 1) & 1);
+            asm volatile("{\n.reg .pred p;\nMM_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MM_DONE;\nbra MM_WAIT;\nMM_DONE:\n}"
+                         :: "r"(bar), "r"(parity) : "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int* nb = s_nb + (t & 1) * kMmaN + half * 64;
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((t & 1) * kMmaN + half * 64);
+#pragma unroll
+        for (int part = 0; part < 2; part++) {
+            uint32_t r[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                         "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                           "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+                           "=r"(r[31])
+                         : "r"(taddr + (uint32_t)(32 * part)) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int ibase = t * kMmaN + half * 64 + 32 * part;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int4 n4 = *reinterpret_cast<const int4*>(nb + 32 * part + j);
+                const int v0 = n4.x - 2 * (int)r[j], v1 = n4.y - 2 * (int)r[j + 1], v2 = n4.z - 2 * (int)r[j + 2], v3 = n4.w - 2 * (int)r[j + 3];
+                if (v0 < thr) topk_insert(tk, ((uint32_t)(v0 + na) << 16) | (uint32_t)(ibase + j));
+                if (v1 < thr) topk_insert(tk, ((uint32_t)(v1 + na) << 16) | (uint32_t)(ibase + j + 1));
+                if (v2 < thr) topk_insert(tk, ((uint32_t)(v2 + na) << 16) | (uint32_t)(ibase + j + 2));
+                if (v3 < thr) topk_insert(tk, ((uint32_t)(v3 + na) << 16) | (uint32_t)(ibase + j + 3));
+            }
+        }
+    }
+    // ---- merge the two column halves of every row, write the lists
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (half == 1) {
+#pragma unroll
+        for (int k = 0; k < kTopK; k++) s_merge[row * kTopK + k] = tk[k];
+    }
+    __syncthreads();
+    if (half == 0 && m0 + row < n_ref) {
+#pragma unroll
+        for (int k = 0; k < kTopK; k++) topk_insert(tk, s_merge[row * kTopK + k]);
+        uint32_t* out = topk + ((long long)f * n_ref + m0 + row) * kTopK;
+#pragma unroll
+        for (int k = 0; k < kTopK; k += 4) *reinterpret_cast<uint4*>(out + k) = make_uint4(tk[k], tk[k + 1], tk[k + 2], tk[k + 3]);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(2 * kMmaN) : "memory");
     }
 }
 
@@ -842,9 +1024,18 @@ static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int re
         const size_t smem = (size_t)4 * nf_pad * 8;
         if (smem > 200 * 1024) return fail(B200_ECAPACITY, "frame_cap too large for the %s", "shared-memory descriptor planes");
         B200_CUDA(cudaFuncSetAttribute(k_match_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((n_ref + kRefPerCta - 1) / kRefPerCta, n_batch);
-        B200_LAUNCH(k_match_topk, grid, kMatchWarps * 32, smem, st, (const ulonglong4*)ref_desc, n_ref, (const ulonglong4*)frame_desc,
-                    n_frame, frame_cap, topk, dstar);
+        // tensor-core distance stage (k_match_mma) unless B200_MATCH_POPC asks for the popcount kernel; both write the same lists
+        static const bool match_popc = getenv("B200_MATCH_POPC") != nullptr;
+        if (!match_popc && frame_cap < 65536) {
+            static std::atomic<int> mma_attr(0);
+            if (!mma_attr.load()) { B200_CUDA(cudaFuncSetAttribute(k_match_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmem)); mma_attr.store(1); }
+            dim3 grid((n_ref + kMmaM - 1) / kMmaM, n_batch);
+            B200_LAUNCH(k_match_mma, grid, kMmaThreads, kMmaSmem, st, (const ulonglong4*)ref_desc, n_ref, (const ulonglong4*)frame_desc, n_frame, frame_cap, topk, dstar);
+        } else {
+            dim3 grid((n_ref + kRefPerCta - 1) / kRefPerCta, n_batch);
+            B200_LAUNCH(k_match_topk, grid, kMatchWarps * 32, smem, st, (const ulonglong4*)ref_desc, n_ref, (const ulonglong4*)frame_desc,
+                        n_frame, frame_cap, topk, dstar);
+        }
     }
     size_t smem2 = (size_t)((((frame_cap + 31) / 32) + 3) & ~3) * 4 + (size_t)((frame_cap + 15) & ~15) + 16;
     const size_t tk_bytes = (size_t)n_ref * kTopK * 4 + ((size_t)n_ref + frame_cap) * 4;     // top-K lists + both angle arrays

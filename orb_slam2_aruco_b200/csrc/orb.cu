@@ -43,6 +43,7 @@ struct LevelGeom {
     int box_w, box_h;         // TMA box of k_fast: (largest cell ROI of the level + 15 columns of alignment slack) rounded up to 16 x largest ROI height
     float scale;              // mvScaleFactor[l]
     float size;               // keypoint size = (int)(31*scale)
+    long long soff; int spitch;   // the level inside a frame's score map (k_fast_score -> k_fast_nms): byte offset and row pitch
 };
 
 struct OrbGeom {
@@ -52,6 +53,8 @@ struct OrbGeom {
     long long pyr_frame_stride;
     int res_per_frame;        // sum of kp_cap
     int ini_th, min_th;
+    int store_th;             // scores below min(iniThFAST, minThFAST) are stored as 0 in the score map
+    long long score_frame_stride;
     LevelGeom L[kMaxLevels];
 };
 
@@ -419,6 +422,235 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
         }
         if (lane == 0) cellcnt[(long long)f * g.total_cells + blockIdx.x] = run;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (dense form, the default): the FAST score is threshold independent and the cells' interiors tile the level, so the work splits
+// into a perfectly regular part and a tiny per-cell part.
+//
+// k_fast_score: the score of EVERY pixel of a 64 x 32 tile, no pretest, no queues, no divergence.  The (64 + 6) x (32 + 6) pixel
+// region arrives as one TMA box (96 x 38 bytes: the box starts at the tile's x rounded down to 16, which puts the first pixel at byte
+// 13 and every 4-pixel group on a word).  A thread owns an aligned group of four pixels = two pixel pairs in u16x2 registers; per
+// row it reads 3 words from each of the 7 rows it touches and takes the 17 circle / centre values of both pairs out of them with one
+// PRMT each (a zero register supplies the high bytes; the four straddling positions need one AND more).  Subtracting the centre
+// commutes with min / max, so the arcs run on the raw pixel values: 2 x (16 + 16) min3 / max3 for "min over 9 contiguous" of both
+// polarities, 2 x 8 for the outer max / min, then score = max(maxmin - v, v - minmax) - 1.  Scores below minThFAST become 0; the
+// four bytes of a thread are one coalesced 32-bit store into the level's score map.  Lanes 16-31 work two rows below lanes 0-15:
+// with the 96-byte tile pitch that shifts their words by 16 banks, so no shared-memory load has a conflict.
+//
+// k_fast_nms: one warp per cell (ORBextractor.cc:789-829).  The cell interior's scores are staged into shared memory with a zero ring
+// (neighbours outside the interior count 0, as cv::FAST on the cell ROI treats them).  A pixel with score >= T can never lose against a
+// neighbour below T, so NMS is "strictly greater than the 8 raw neighbours" for every threshold; every lane scans a contiguous raster run
+// of words, tests only the bytes >= T (iniThFAST first, minThFAST only when the cell stays empty), and a warp prefix turns the per-lane
+// keep masks into the raster-ordered candidate slots the quadtree reads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScTW = 64, kScTH = 32;                 // score tile (pixels)
+constexpr int kScBoxW = 96, kScBoxH = kScTH + 6;      // TMA box: 13 bytes of alignment slack + 64 + 2 x 3 halo -> 83, rounded up to 96
+constexpr int kScThreads = 128;
+
+struct ScoreTile { short level, tx, ty, pad; };       // tile origin in level coordinates: x = 16 + 64 tx, y = 16 + 32 ty
+
+// pixel pair at column offset DX from the thread's word: PAIR 0 = pixels 0, 1 of the group, PAIR 1 = pixels 2, 3; (wm, w0, wp) = the words
+// left of / at / right of the group in that row.  Result: the two pixel values zero-extended to u16x2.
+template <int PAIR, int DX>
+__device__ __forceinline__ unsigned sc_take(unsigned wm, unsigned w0, unsigned wp) {
+    constexpr int o = 2 * PAIR + DX;                  // byte offset of the pair's first pixel relative to w0's byte 0: -3 .. 5
+    if (o == -3) return __byte_perm(wm, 0u, 0x4241);
+    if (o == -2) return __byte_perm(wm, 0u, 0x4342);
+    if (o == -1) return __byte_perm(wm, w0, 0x0403) & 0x00ff00ffu;
+    if (o == 0) return __byte_perm(w0, 0u, 0x4140);
+    if (o == 1) return __byte_perm(w0, 0u, 0x4241);
+    if (o == 2) return __byte_perm(w0, 0u, 0x4342);
+    if (o == 3) return __byte_perm(w0, wp, 0x0403) & 0x00ff00ffu;
+    if (o == 4) return __byte_perm(wp, 0u, 0x4140);
+    return __byte_perm(wp, 0u, 0x4241);               // o == 5
+}
+
+// 0xffff in every half word of x that is negative (prmt's sign-replicate mode on bytes 1 and 3), else 0
+__device__ __forceinline__ unsigned sign_spread16x2(unsigned x) {
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0xbb99u));
+    return r;
+}
+
+// score of one pixel pair from its 16 circle values (raw u16x2) and the centre; s16x2, may be negative for flat neighbourhoods
+__device__ __forceinline__ unsigned sc_score_pair(const unsigned (&c)[16], unsigned v) {
+    unsigned t1[16], u1[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        t1[j] = __vimin3_s16x2(c[j], c[(j + 1) & 15], c[(j + 2) & 15]);
+        u1[j] = __vimax3_s16x2(c[j], c[(j + 1) & 15], c[(j + 2) & 15]);
+    }
+    unsigned t2[16], u2[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        t2[j] = __vimin3_s16x2(t1[j], t1[(j + 3) & 15], t1[(j + 6) & 15]);       // min over positions j .. j + 8
+        u2[j] = __vimax3_s16x2(u1[j], u1[(j + 3) & 15], u1[(j + 6) & 15]);
+    }
+    unsigned a = __vimax3_s16x2(t2[0], t2[1], t2[2]), b = __vimax3_s16x2(t2[3], t2[4], t2[5]), d = __vimax3_s16x2(t2[6], t2[7], t2[8]);
+    unsigned e = __vimax3_s16x2(t2[9], t2[10], t2[11]), f = __vimax3_s16x2(t2[12], t2[13], t2[14]);
+    a = __vimax3_s16x2(a, b, d); e = __vimax3_s16x2(e, f, t2[15]);
+    const unsigned maxmin = __vmaxs2(a, e);
+    a = __vimin3_s16x2(u2[0], u2[1], u2[2]); b = __vimin3_s16x2(u2[3], u2[4], u2[5]); d = __vimin3_s16x2(u2[6], u2[7], u2[8]);
+    e = __vimin3_s16x2(u2[9], u2[10], u2[11]); f = __vimin3_s16x2(u2[12], u2[13], u2[14]);
+    a = __vimin3_s16x2(a, b, d); e = __vimin3_s16x2(e, f, u2[15]);
+    const unsigned minmax = __vmins2(a, e);
+    // max(maxmin - v, v - minmax) - 1
+    return __vadd2(__vmaxs2(__vsub2(maxmin, v), __vsub2(v, minmax)), 0xffffffffu);
+}
+
+template <int PAIR>
+__device__ __forceinline__ unsigned sc_pair(const unsigned (&wm)[7], const unsigned (&w0)[7], const unsigned (&wp)[7]) {
+    // rows: index 0 .. 6 = dy -3 .. +3.  circle: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+    unsigned c[16];
+    c[0] = sc_take<PAIR, 0>(wm[6], w0[6], wp[6]);   c[1] = sc_take<PAIR, 1>(wm[6], w0[6], wp[6]);   c[2] = sc_take<PAIR, 2>(wm[5], w0[5], wp[5]);
+    c[3] = sc_take<PAIR, 3>(wm[4], w0[4], wp[4]);   c[4] = sc_take<PAIR, 3>(wm[3], w0[3], wp[3]);   c[5] = sc_take<PAIR, 3>(wm[2], w0[2], wp[2]);
+    c[6] = sc_take<PAIR, 2>(wm[1], w0[1], wp[1]);   c[7] = sc_take<PAIR, 1>(wm[0], w0[0], wp[0]);   c[8] = sc_take<PAIR, 0>(wm[0], w0[0], wp[0]);
+    c[9] = sc_take<PAIR, -1>(wm[0], w0[0], wp[0]);  c[10] = sc_take<PAIR, -2>(wm[1], w0[1], wp[1]); c[11] = sc_take<PAIR, -3>(wm[2], w0[2], wp[2]);
+    c[12] = sc_take<PAIR, -3>(wm[3], w0[3], wp[3]); c[13] = sc_take<PAIR, -3>(wm[4], w0[4], wp[4]); c[14] = sc_take<PAIR, -2>(wm[5], w0[5], wp[5]);
+    c[15] = sc_take<PAIR, -1>(wm[6], w0[6], wp[6]);
+    return sc_score_pair(c, sc_take<PAIR, 0>(wm[3], w0[3], wp[3]));
+}
+
+__global__ void __launch_bounds__(kScThreads)
+k_fast_score(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride, const uint8_t* __restrict__ pyr,
+             const __grid_constant__ OrbGeom g, const __grid_constant__ FastMaps maps, int tma_level0, int scratch_base,
+             const ScoreTile* __restrict__ tiles, uint8_t* __restrict__ score0) {
+    __shared__ __align__(128) unsigned char tile[kScBoxW * kScBoxH];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const ScoreTile td = tiles[blockIdx.x];
+    const int f = blockIdx.y;
+    const LevelGeom& lg = g.L[td.level];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bx0 = kScTW * td.tx, by0 = 13 + kScTH * td.ty;          // box origin; pixel (16 + 64 tx + i, 16 + 32 ty + j) sits at tile (16 + i, 3 + j)
+    const bool use_tma = td.level > 0 || tma_level0;
+    if (use_tma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar)), "r"(kScBoxW * kScBoxH) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&maps.m[td.level])), "r"(bx0), "r"(by0),
+                            "r"(td.level > 0 ? scratch_base + f : f), "r"(smem_u32(&s_bar)) : "memory");
+        }
+        __syncthreads();                              // the barrier word is initialised before anybody polls it
+        asm volatile("{\n.reg .pred p;\nSC_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra SC_DONE;\nbra SC_WAIT;\nSC_DONE:\n}"
+                     :: "r"(smem_u32(&s_bar)) : "memory");
+    } else {
+        // caller frames whose pointer / strides are not 16-byte multiples cannot be described by a tensor map: byte-wise staging, zero outside
+        const uint8_t* base = img0 + (long long)f * img_frame_stride;
+        for (int i = tid; i < kScBoxW * kScBoxH; i += kScThreads) {
+            const int ty = i / kScBoxW, tx = i - ty * kScBoxW, x = bx0 + tx, y = by0 + ty;
+            tile[i] = (x < lg.w && y < lg.h) ? base[(long long)y * img_row_stride + x] : (unsigned char)0;
+        }
+        __syncthreads();
+    }
+    const int half = lane >> 4, q = lane & 15;
+    const int X = 16 + kScTW * td.tx + 4 * q;                         // level x of the group's first pixel
+    uint8_t* out = score0 + (long long)f * g.score_frame_stride + lg.soff;
+    const unsigned minp = (unsigned)g.store_th * 0x10001u;
+    // warp w: rows 8w + {0, 1, 4, 5} for lanes 0-15 and the rows two below ({2, 3, 6, 7}) for lanes 16-31
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {
+        const int r = 8 * warp + (it & 1) + 4 * (it >> 1) + 2 * half;
+        const int Y = 16 + kScTH * td.ty + r;
+        if (Y >= lg.h - 16 || X >= lg.w - 16) continue;               // warp-divergent only in edge tiles
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + r * kScBoxW) + 4 + q;       // row dy = -3 of the group's word
+        unsigned wm[7], w0[7], wp[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) { wm[k] = row[k * (kScBoxW / 4) - 1]; w0[k] = row[k * (kScBoxW / 4)]; wp[k] = row[k * (kScBoxW / 4) + 1]; }
+        unsigned sa = sc_pair<0>(wm, w0, wp), sb = sc_pair<1>(wm, w0, wp);
+        // scores below the stored threshold (and negative ones) become 0: the sign of (score - th) spread over the half word
+        const unsigned da = __vsub2(sa, minp), db = __vsub2(sb, minp);
+        sa &= ~sign_spread16x2(da); sb &= ~sign_spread16x2(db);
+        *reinterpret_cast<uint32_t*>(out + (long long)Y * lg.spitch + X) = __byte_perm(sa, sb, 0x6420);
+    }
+}
+
+constexpr int kNmsWarps = 8;
+
+__global__ void __launch_bounds__(kNmsWarps * 32)
+k_fast_nms(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells, const uint8_t* __restrict__ score0, int warp_smem_words,
+           uint32_t* __restrict__ slots, int* __restrict__ cellcnt) {
+    extern __shared__ __align__(16) uint32_t nms_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cell = blockIdx.x * kNmsWarps + warp, f = blockIdx.y;
+    if (cell >= g.total_cells) return;
+    const CellDesc cd = cells[cell];
+    const LevelGeom& lg = g.L[cd.level];
+    uint32_t* tw = nms_raw + warp * warp_smem_words;
+    const int iw = cd.rw - 6, ih = cd.rh - 6;
+    const int xi = cd.x0 + 3, yi = cd.y0 + 3;                        // first interior pixel (level coordinates)
+    const int xa = (xi - 1) & ~3;                                    // the tile's first column: a word boundary left of the ring column
+    const int wpr = (xi + iw + 1 - xa + 3) >> 2;                     // words per tile row (interior + both ring columns)
+    const unsigned rcp = (65536u + wpr - 1) / wpr;                   // i / wpr == (i * rcp) >> 16 for i * wpr < 65536
+    const int rows = ih + 2, nw = rows * wpr;
+    const uint8_t* src = score0 + (long long)f * g.score_frame_stride + lg.soff + (long long)(yi - 1) * lg.spitch + xa;
+    // stage: interior bytes from the score map, zero everywhere else (ring rows, ring columns, alignment slack)
+    for (int i = lane; i < nw; i += 32) {
+        const int r = (int)(((unsigned)i * rcp) >> 16), wc = i - r * wpr;
+        unsigned v = 0;
+        if (r >= 1 && r <= ih) {
+            v = *reinterpret_cast<const uint32_t*>(src + (long long)r * lg.spitch + 4 * wc);
+            const int lo = xi - (xa + 4 * wc), hi = (xa + 4 * wc + 4) - (xi + iw);        // bytes to clear at the low / high end
+            if (lo > 0) v = lo >= 4 ? 0u : v & (0xffffffffu << (8 * lo));
+            if (hi > 0) v = hi >= 4 ? 0u : v & (0xffffffffu >> (8 * hi));
+        }
+        tw[i] = v;
+    }
+    __syncwarp();
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tw);
+    const int P = 4 * wpr;                                           // tile pitch in bytes
+    const int nwi = ih * wpr;                                        // words of the interior rows, raster order
+    const int nchunk = (nwi + 511) >> 9, K = (nwi + 32 * nchunk - 1) / (32 * nchunk);       // <= 16 words per lane and chunk
+    uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
+    int T = g.ini_th, total = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        total = 0;
+        const unsigned Tb = (unsigned)(0x80 - T) * 0x01010101u;
+        for (int c = 0; c < nchunk; c++) {
+            const int w_beg = (c * 32 + lane) * K;
+            unsigned long long keep = 0ull;
+            for (int j = 0; j < K; j++) {
+                const int wi = w_beg + j;
+                if (wi >= nwi) break;
+                const unsigned w = tw[wpr + wi];
+                // bytes >= T (T <= 127: carry out of the low 7 bits, or the top bit itself); T > 127 cannot carry, test the top bit path only
+                unsigned m = T <= 128 ? ((((w & 0x7f7f7f7fu) + Tb) | w) & 0x80808080u) : 0u;
+                if (T > 128) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) if ((int)((w >> (8 * b)) & 255u) >= T) m |= 0x80u << (8 * b);
+                }
+                while (m) {
+                    const int b = (__ffs(m) - 1) >> 3;
+                    m &= m - 1;
+                    const uint8_t* sp = tb + 4 * (wpr + wi) + b;
+                    const int s = sp[0];
+                    if (s > sp[-1] && s > sp[1] && s > sp[-P - 1] && s > sp[-P] && s > sp[-P + 1] && s > sp[P - 1] && s > sp[P] && s > sp[P + 1])
+                        keep |= 1ull << (4 * j + b);
+                }
+            }
+            const int cnt = __popcll(keep);
+            int sc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+            int pos = total + sc - cnt;
+            total += __shfl_sync(0xffffffffu, sc, 31);
+            while (keep) {
+                const int bit = __ffsll((long long)keep) - 1;
+                keep &= keep - 1;
+                const int wi = w_beg + (bit >> 2), b = bit & 3;
+                const int r = (int)(((unsigned)wi * rcp) >> 16), wc = wi - r * wpr;
+                const int x = xa + 4 * wc + b, y = yi + r;          // level coordinates
+                // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
+                if (pos < cd.cap) out[pos] = (uint32_t)(x - 16) | ((uint32_t)(y - 16) << 12) | ((uint32_t)tb[4 * (wpr + wi) + b] << 24);
+                pos++;
+            }
+        }
+        if (total > 0 || pass == 1 || g.min_th >= g.ini_th) break;
+        T = g.min_th;                                                // nothing at iniThFAST: the whole cell again at minThFAST (ORBextractor.cc:809-816)
+    }
+    if (lane == 0) cellcnt[(long long)f * g.total_cells + cell] = total;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1032,6 +1264,7 @@ struct b200_orb_s {
     OrbGeom geom;
     std::vector<CellDesc> cells;
     int pool_cap;
+    FastMaps smaps; std::vector<ScoreTile> tiles; ScoreTile* d_tiles; size_t cap_tiles; uint8_t* d_score; size_t cap_score; int nms_warp_words;   // dense FAST: score tiles, score map
     FastSmemGeom fsg; size_t fast_smem; FastMaps maps; DescMaps dmaps; FastMaps pmaps;      // pmaps.m[l]: source level l - 1 with level l's pyramid box      // maps.m[l > 0]: level l of the pyramid buffer; m[0] is encoded per call
     // device buffers
     uint8_t* d_pyr; ResizeEntry* d_tab; CellDesc* d_cells; uint32_t* d_slots; int* d_cellcnt;
@@ -1192,6 +1425,26 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
         if (L.w > 4095 || L.h > 4095) return fail(B200_EINVAL, "level larger than %s", "4095 px (12-bit packed coordinates)");
     }
     g.total_cells = (int)h->cells.size();
+    {   // dense FAST: score map layout, score tiles over [16, w - 16) x [16, h - 16) of every level, and the per-warp tile of k_fast_nms
+        long long sofs = 0;
+        h->tiles.clear();
+        for (int l = 0; l < h->nlevels; l++) {
+            LevelGeom& L = g.L[l];
+            L.spitch = (int)align_up(L.w, 16); L.soff = sofs;
+            sofs += align_up((long long)L.spitch * L.h, 256);
+            if (L.ncells == 0) continue;
+            for (int ty = 0; 16 + kScTH * ty < L.h - 16; ty++)
+                for (int tx = 0; 16 + kScTW * tx < L.w - 16; tx++) { ScoreTile t; t.level = (short)l; t.tx = (short)tx; t.ty = (short)ty; t.pad = 0; h->tiles.push_back(t); }
+        }
+        g.score_frame_stride = std::max<long long>(sofs, 256);
+        g.store_th = std::min(h->ini_th, h->min_th);
+        int words = 16;
+        for (const CellDesc& c : h->cells) {
+            const int iw = c.rw - 6, ih = c.rh - 6, xi = c.x0 + 3, xa = (xi - 1) & ~3, wpr = (xi + iw + 1 - xa + 3) >> 2;
+            words = std::max(words, (ih + 2) * wpr);
+        }
+        h->nms_warp_words = (words + 3) & ~3;
+    }
     {   // TMA boxes and the shared-memory carve-up of k_fast
         FastSmemGeom& sgm = h->fsg;
         sgm.tile_bytes = 128; sgm.qcap = 8; sgm.keepw = 3;
@@ -1234,6 +1487,9 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
     if ((rc = ensure(h->d_keysA, h->cap_keysA, slots_bytes))) return rc;
     if ((rc = ensure(h->d_keysB, h->cap_keysB, slots_bytes))) return rc;
     if ((rc = ensure(h->d_cellcnt, h->cap_cellcnt, std::max<size_t>((size_t)g.total_cells * B * 4, 4)))) return rc;
+    if ((rc = ensure(h->d_score, h->cap_score, (size_t)g.score_frame_stride * B))) return rc;
+    if ((rc = ensure(h->d_tiles, h->cap_tiles, std::max<size_t>(h->tiles.size(), 1) * sizeof(ScoreTile)))) return rc;
+    if (!h->tiles.empty()) B200_CUDA(cudaMemcpy(h->d_tiles, h->tiles.data(), h->tiles.size() * sizeof(ScoreTile), cudaMemcpyHostToDevice));
     if ((rc = ensure(h->d_lvlres, h->cap_lvlres, (size_t)res * B * 4))) return rc;
     if (!h->d_lvlcnt) B200_CUDA(cudaMalloc((void**)&h->d_lvlcnt, (size_t)kMaxLevels * B * 4));
     if (!h->d_err) { B200_CUDA(cudaMalloc((void**)&h->d_err, 4)); B200_CUDA(cudaMemset(h->d_err, 0, 4)); }
@@ -1242,6 +1498,7 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
     for (int l = 1; l < h->nlevels; l++) {
         const LevelGeom& L = g.L[l];
         if ((rc = make_tile_map(&h->maps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, L.box_w, L.box_h))) return rc;
+        if ((rc = make_tile_map(&h->smaps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, kScBoxW, kScBoxH))) return rc;
         if ((rc = make_tile_map(&h->dmaps.m[l], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, kPatchPitch, kPatchW))) return rc;
         if (l + 1 < h->nlevels && g.L[l + 1].pbox_w <= 256 && g.L[l + 1].pbox_h <= 256 &&
             (rc = make_tile_map(&h->pmaps.m[l + 1], h->d_pyr + L.offset, L.w, L.h, h->max_batch, L.pitch, g.pyr_frame_stride, g.L[l + 1].pbox_w, g.L[l + 1].pbox_h)))
@@ -1317,11 +1574,26 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
         if (tma0) {
             int rc = make_tile_map(&h->maps.m[0], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, g.L[0].box_w, g.L[0].box_h);
             if (!rc) rc = make_tile_map(&h->dmaps.m[0], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, kPatchPitch, kPatchW);
+            if (!rc) rc = make_tile_map(&h->smaps.m[0], imgs, g.L[0].w, g.L[0].h, n, rs, fs0, kScBoxW, kScBoxH);
             if (rc) return rc;
         }
         tma0_used = tma0;
         const int tp = g.L[0].box_w;
-        if (tp == 64) B200_LAUNCH(k_fast<64>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
+        // Two forms of K2, both bit-exact.  Default: the per-cell kernel (pretest + queues + paired scoring).  B200_FAST_DENSE=1: the dense score map +
+        // per-cell NMS (k_fast_score + k_fast_nms).  Measured on a B200, 256 frames of 640 x 480 (profiles/r2_fast_variants.md): 1.01 ms against
+        // 0.76 + 0.43 ms - the dense form issues 40 % fewer instructions, but 78 % of them (VIMNMX3 / PRMT / LOP3) go to the ALU pipe, which accepts one
+        // warp instruction every other cycle per sub-partition, while the per-cell form spreads its work over the ALU, FMA and LSU pipes.
+        static const bool fast_dense = getenv("B200_FAST_DENSE") != nullptr;
+        if (fast_dense) {
+            uint8_t* d_score = h->d_score + (size_t)base * g.score_frame_stride;
+            dim3 gs((unsigned)h->tiles.size(), n);
+            B200_LAUNCH(k_fast_score, gs, kScThreads, 0, st, imgs, rs, fs, d_pyr, g, h->smaps, tma0, base, h->d_tiles, d_score);
+            const size_t nsm = (size_t)h->nms_warp_words * 4 * kNmsWarps;
+            static std::atomic<size_t> nms_smem_set(0);
+            if (nsm > 48 * 1024 && nsm > nms_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_fast_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsm)); nms_smem_set.store(nsm); }
+            dim3 gn((g.total_cells + kNmsWarps - 1) / kNmsWarps, n);
+            B200_LAUNCH(k_fast_nms, gn, kNmsWarps * 32, nsm, st, g, h->d_cells, d_score, h->nms_warp_words, d_slots, d_cellcnt);
+        } else if (tp == 64) B200_LAUNCH(k_fast<64>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
         else if (tp == 80) B200_LAUNCH(k_fast<80>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
         else B200_LAUNCH(k_fast<96>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
     }
@@ -1347,10 +1619,20 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
     return B200_OK;
 }
 
-int check_args(b200_orb_s* h, const void* imgs, int n, int w, int hh, long long rs, long long fs) {
+// frames per pipeline stage of b200_frontend_host.  Small chunks multiply the latency-bound kernels (quadtree, contour walk, greedy resolve take
+// as long for 32 frames as for 256), large ones expose the first upload: half the batch, at most kFrontendChunk
+int frontend_chunk(int n) {
+    static const int env_chunk = [] { const char* e = getenv("B200_FRONTEND_CHUNK"); return e ? atoi(e) : 0; }();
+    return env_chunk > 0 ? env_chunk : (n <= 16 ? n : std::min(kFrontendChunk, std::max(32, (n + 1) / 2)));
+}
+
+// scratch_frames: how many frame slots of scratch the call needs (the whole batch for the device-pointer calls; two pipeline chunks for
+// b200_frontend_host, whose even and odd chunks alternate between two slot regions)
+int check_args(b200_orb_s* h, const void* imgs, int n, int w, int hh, long long rs, long long fs, int scratch_frames = -1) {
     if (!h) return fail(B200_EINVAL, "null %s", "handle");
     if (n < 0 || w < 0 || hh < 0) return fail(B200_EINVAL, "negative %s", "size");
-    if (n > h->max_batch || w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
+    if ((scratch_frames < 0 ? n : scratch_frames) > h->max_batch || w > h->max_w || hh > h->max_h)
+        return fail(B200_ECAPACITY, "batch/image larger than the handle's %s", "capacity");
     if (n > 0 && w > 0 && hh > 0) {
         if (!imgs) return fail(B200_EINVAL, "null %s", "image pointer");
         if (rs < w || (n > 1 && fs < rs * (hh - 1) + w)) return fail(B200_EINVAL, "bad %s", "strides");
@@ -1417,6 +1699,7 @@ int b200_orb_destroy(b200_orb_t h) {
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     cudaFree(h->d_markers); cudaFree(h->d_mcounts); cudaFree(h->d_match); cudaFree(h->d_nmatch); cudaFree(h->d_refdesc); cudaFree(h->d_refkps);
+    cudaFree(h->d_score); cudaFree(h->d_tiles);
     for (int b = 0; b < 7; b++) cudaFree(h->d_coll[b]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1482,7 +1765,8 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
                        b200_marker* markers, int32_t* marker_counts,
                        const uint8_t* ref_desc, const b200_keypoint* ref_kps, int n_ref, float ratio, int check_ori,
                        int32_t* match_ref_idx, int32_t* n_matches) {
-    int rc = check_args(h, imgs, n, w, hh, rs, fs);
+    // a batch larger than the handle's capacity streams through two alternating scratch regions of one pipeline chunk each
+    int rc = check_args(h, imgs, n, w, hh, rs, fs, n <= (h ? h->max_batch : 0) ? n : 2 * frontend_chunk(n));
     if (rc) return rc;
     if (!counts || !kps || !desc) return fail(B200_EINVAL, "null %s", "output pointer");
     if (aruco && (!markers || !marker_counts)) return fail(B200_EINVAL, "null %s", "marker output pointer");
@@ -1552,13 +1836,12 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
         return B200_OK;
     };
     static const int env_chunk = [] { const char* e = getenv("B200_FRONTEND_CHUNK"); return e ? atoi(e) : 0; }();
-    // chunk: frames per pipeline stage.  Small chunks multiply the latency-bound kernels (quadtree, contour walk, greedy resolve take
-    // as long for 32 frames as for 256), large ones expose the first upload: half the batch, at most kFrontendChunk
-    const int chunk = env_chunk > 0 ? env_chunk : (n <= 16 ? n : std::min(kFrontendChunk, std::max(32, (n + 1) / 2)));
+    const int chunk = frontend_chunk(n);
+    const bool streamed = n > h->max_batch;           // scratch slots: the frame index itself, or two alternating chunk-sized regions
     // detector scratch slots: the whole batch when the handle is large enough, else two alternating chunk-sized regions, else one region
     // (then every detector call is serialised on the first auxiliary stream)
     const int acap = aruco ? b200_aruco_batch_capacity(aruco) : 0;
-    const int amode = !aruco ? 0 : acap >= n ? 2 : acap >= 2 * chunk ? 1 : 0;
+    const int amode = !aruco ? 0 : (acap >= n && !streamed) ? 2 : acap >= 2 * chunk ? 1 : 0;
     if (aruco && acap < std::min(chunk, n)) return fail(B200_ECAPACITY, "detector handle smaller than one pipeline chunk (%s frames)", "128");
     int ci = 0;
     // the first chunk is small so that compute starts after a short upload; the second one completes the regular grid
@@ -1596,12 +1879,14 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
             B200_CUDA(cudaEventRecord(ev_auxs[ci & 1], as));
             B200_CUDA(cudaStreamWaitEvent(ds, ev_auxs[ci & 1], 0));
         }
+        const int sbase = streamed ? (ci & 1) * chunk : f0;                 // chunks ci and ci + 2 share a region and a stream set: stream order keeps them apart
         if ((rc = enqueue(h, dst, nf, w, hh, w, (long long)frame_bytes, h->d_kps + (size_t)f0 * cap, h->d_desc + (size_t)f0 * cap * 32,
-                          h->d_counts + f0, cap, st, f0)))
+                          h->d_counts + f0, cap, st, sbase)))
             return rc;
         if (do_match &&
             (rc = b200_match_bf_kp_range(h->d_refdesc, h->d_refkps, n_ref, h->d_desc + (size_t)f0 * cap * 32, h->d_kps + (size_t)f0 * cap, h->d_counts + f0, nf, cap,
-                                         ratio, 50, check_ori, 30.0f / 360.0f, h->d_match + (size_t)f0 * cap, h->d_nmatch + f0, h->device, st, f0, n)))
+                                         ratio, 50, check_ori, 30.0f / 360.0f, h->d_match + (size_t)f0 * cap, h->d_nmatch + f0, h->device, st, sbase,
+                                         streamed ? 2 * chunk : n)))
             return rc;
         // this chunk's result slots go home on the download stream while the next chunk is being processed
         B200_CUDA(cudaEventRecord(h->ev_done[ci & 1], st));

@@ -6,6 +6,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <string>
+
+// level 0 of the pyramid member: the input image sits at offset (19, 19) of its bordered buffer (src/ORBextractor.cc:1127)
+static int l0_check(const cv::Mat& L0, const cv::Mat& im) {
+    for (int y = 0; y < im.rows; y++) if (memcmp(L0.ptr(y + 19) + 19, im.ptr(y), im.cols)) return 1;
+    return 0;
+}
 
 int main(int argc, char** argv) {
     if (argc < 6) { fprintf(stderr, "usage: %s in.raw w h dict out.bin\n", argv[0]); return 2; }
@@ -134,6 +142,30 @@ int main(int argc, char** argv) {
         fwrite(errs.data(), 4, errs.size(), o);
         for (auto& p : arucoUn) { fwrite(&p.x, 4, 1, o); fwrite(&p.y, 4, 1, o); }
         fclose(o);
+        {   // aruco::Marker::contourPoints / dict_info (marker.h:57-59) -> <out>.contours: per marker a 32-byte name, the point count and the points
+            FILE* oc = fopen((std::string(argv[5]) + ".contours").c_str(), "wb");
+            for (auto& m : markers) {
+                char name[32] = {0};
+                strncpy(name, m.dict_info.c_str(), 31);
+                const int len = (int)m.contourPoints.size();
+                fwrite(name, 1, 32, oc); fwrite(&len, 4, 1, oc);
+                for (auto& p : m.contourPoints) { fwrite(&p.x, 4, 1, oc); fwrite(&p.y, 4, 1, oc); }
+            }
+            fclose(oc);
+        }
+        {   // the public member mvImagePyramid (ORBextractor.h:85) against the accessor the pyramid tests pin to the oracle
+            extractor.ComputePyramidMember();
+            std::vector<int> ws, hs;
+            const std::vector<std::vector<unsigned char> > pyr = extractor.ImagePyramid(&ws, &hs);
+            if ((int)extractor.mvImagePyramid.size() != extractor.GetLevels()) { fprintf(stderr, "mvImagePyramid size\n"); return 1; }
+            for (int l = 0; l < extractor.GetLevels(); l++) {
+                const cv::Mat& L = extractor.mvImagePyramid[l];
+                if (L.cols != ws[l] + 38 || L.rows != hs[l] + 38) { fprintf(stderr, "mvImagePyramid[%d] is %d x %d\n", l, L.cols, L.rows); return 1; }
+                for (int y = 0; y < L.rows; y++)
+                    if (memcmp(L.ptr(y), &pyr[l][(size_t)y * L.cols], L.cols)) { fprintf(stderr, "mvImagePyramid[%d] row %d\n", l, y); return 1; }
+            }
+            if (l0_check(extractor.mvImagePyramid[0], im)) { fprintf(stderr, "mvImagePyramid[0] interior != input image\n"); return 1; }
+        }
         printf("levels=%d scale0=%g keys=%zu markers=%zu matches=%d\n", extractor.GetLevels(), extractor.GetScaleFactors()[1], keys.size(), markers.size(), nm);
     } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 1; }
     return 0;

@@ -66,3 +66,34 @@ def test_adapters_match_oracle(built_lib, tmp_path):
                                              cam9.ctypes.data_as(C.c_void_p), out14.ctypes.data_as(C.c_void_p))
         assert np.abs(poses[i, :6] - out14[:6]).max() <= 2e-6 * max(1, np.abs(out14[:6]).max())
         assert poses[i, 6] <= poses[i, 7] and poses[i, 8] == np.float32(0.187)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(oracle.ref_aruco() is None, reason="oracle/_ref/libref_aruco.so not built (needs /root/reference)")
+def test_marker_contour_points_and_dict_info_equal_the_reference(built_lib, tmp_path):
+    """aruco::Marker::contourPoints / dict_info (marker.h:57-59) as the adapter's detect() fills them against the reference's own detector
+    (markerdetector_impl.cpp:6752-6772): same border, same point order, same dictionary name; the same run checks the public member
+    ORBextractor::mvImagePyramid (ORBextractor.h:85) inside the C++ program"""
+    import ctypes as C
+    exe = build_adapter_smoke(str(tmp_path))
+    for seed, dname in ((31, "ARUCO_MIP_25h7"), (77, "ARUCO")):
+        img = synth.make_frame(seed, markers=20, dict_name=dname)
+        raw = os.path.join(str(tmp_path), "f.raw"); out = os.path.join(str(tmp_path), "o.bin")
+        img.tofile(raw)
+        r = subprocess.run([exe, raw, "640", "480", dname, out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        buf = open(out + ".contours", "rb").read()
+        cap = 64
+        mk = np.zeros(cap, oracle.MARKER_DTYPE); names = np.zeros((cap, 32), np.uint8); ofs = np.zeros(cap + 1, np.int32); xy = np.zeros((1 << 16, 2), np.int32)
+        vp = C.c_void_p
+        n = oracle.ref_aruco().ref_aruco_detect_contours(img.ctypes.data_as(vp), 640, 480, 640, dname.encode(), mk.ctypes.data_as(vp), cap, names.ctypes.data_as(vp),
+                                                         ofs.ctypes.data_as(vp), xy.ctypes.data_as(vp), len(xy))
+        assert n >= 15
+        o = 0
+        for i in range(n):
+            name = buf[o:o + 32].split(b"\0")[0].decode(); o += 32
+            ln = int(np.frombuffer(buf[o:o + 4], np.int32)[0]); o += 4
+            pts = np.frombuffer(buf[o:o + 8 * ln], np.int32).reshape(ln, 2); o += 8 * ln
+            assert name == bytes(names[i]).split(b"\0")[0].decode() == dname
+            assert ln == ofs[i + 1] - ofs[i] > 70 and np.array_equal(pts, xy[ofs[i]:ofs[i + 1]])
+        assert o == len(buf)
