@@ -247,6 +247,9 @@ int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int width
  * marker `index` of frame `frame` of the LAST detect call on the handle, in the reference's point order.  xy [cap][2] int32 (HOST); returns the number
  * of points of the border (the array receives min(cap, that) of them). */
 int b200_aruco_get_contour(b200_aruco_t h, int frame, int index, int32_t* xy, int cap);
+/* The borders of the first n_markers output markers of that frame in ONE round trip: ofs [n_markers + 1] (HOST), marker m owns points
+ * xy [ofs[m] .. ofs[m + 1]) of xy [xy_cap][2]; returns the total number of points (pass xy_cap = 0 to ask for it first). */
+int b200_aruco_get_contours(b200_aruco_t h, int frame, int n_markers, int32_t* ofs, int32_t* xy, int xy_cap);
 
 
 /* ---------------------------------------------------------------- marker pose -------------------- */

@@ -773,17 +773,26 @@ public:
         int32_t n = 0;
         b200slam_detail::check(b200_aruco_detect_host(h_, input.data, 1, input.cols, input.rows, (int64_t)input.step, (int64_t)input.step * input.rows, m.data(), &n));
         std::vector<Marker> out(n);
-        std::vector<int32_t> cp;
         for (int i = 0; i < n; i++) {
             out[i].id = m[i].id;
             for (int k = 0; k < 4; k++) out[i].push_back(cv::Point2f(m[i].xy[2 * k], m[i].xy[2 * k + 1]));
             out[i].dict_info = dict_;                                                                // Dictionary::getName() (dictionary.cpp:118-231)
-            int len = b200_aruco_get_contour(h_, 0, i, nullptr, 0);                                  // markerdetector_impl.cpp:6759-6772
-            b200slam_detail::check(len);
-            cp.resize((size_t)2 * len + 2);
-            b200slam_detail::check(b200_aruco_get_contour(h_, 0, i, cp.data(), len));
-            out[i].contourPoints.resize(len);
-            for (int j = 0; j < len; j++) out[i].contourPoints[j] = cv::Point(cp[2 * j], cp[2 * j + 1]);
+        }
+        if (n > 0 && fillContourPoints) {                                                            // markerdetector_impl.cpp:6759-6772, one round trip for all markers
+            std::vector<int32_t> ofs((size_t)n + 1, 0);
+            contour_xy_.resize((size_t)2 * contour_cap_ + 2);
+            int total = b200_aruco_get_contours(h_, 0, n, ofs.data(), contour_xy_.data(), contour_cap_);
+            b200slam_detail::check(total);
+            if (total > contour_cap_) {                                                              // grow once, fetch again
+                contour_cap_ = total;
+                contour_xy_.resize((size_t)2 * contour_cap_ + 2);
+                b200slam_detail::check(b200_aruco_get_contours(h_, 0, n, ofs.data(), contour_xy_.data(), contour_cap_));
+            }
+            for (int i = 0; i < n; i++) {
+                const int len = ofs[i + 1] - ofs[i];
+                out[i].contourPoints.resize(len);
+                for (int j = 0; j < len; j++) out[i].contourPoints[j] = cv::Point(contour_xy_[2 * (ofs[i] + j)], contour_xy_[2 * (ofs[i] + j) + 1]);
+            }
         }
         if (n > 0 && camParams.isValid() && markerSizeMeters > 0) {
             // markerdetector_impl.cpp detect(input, markers, camParams, size, ...): "if (camParams.CamSize != input.size() && camParams.isValid() &&
@@ -811,6 +820,9 @@ private:
     std::string dict_;
     b200_aruco_t h_; int w_, ht_, device_;
     Params params_;
+    std::vector<int32_t> contour_xy_; int contour_cap_ = 16384;
+public:
+    bool fillContourPoints = true;            // aruco::Marker::contourPoints (marker.h:59); nothing on the reference's path reads it (src/ has no use): switch off to save the copy
 };
 
 }  // namespace aruco

@@ -1378,6 +1378,38 @@ k_finalize(const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, 
     }
 }
 
+// packs the borders of a frame's output markers back to back: offsets by one warp scan, points copied by the whole CTA
+__global__ void __launch_bounds__(256)
+k_pack_contours(const __grid_constant__ ArucoGeom g, const int* __restrict__ mcontour, int n_markers, const ContourDesc* __restrict__ desc,
+                const short2* __restrict__ pts, int* __restrict__ ofs, short2* __restrict__ out) {
+    __shared__ int s_ofs[kMaxMarkers + 1], s_src[kMaxMarkers];
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        int run = 0;
+        for (int m0 = 0; m0 < n_markers; m0 += 32) {
+            const int m = m0 + tid;
+            int len = 0, src = 0;
+            if (m < n_markers) {
+                const int ci = mcontour[m];
+                if (ci >= 0 && ci < g.max_contours) { const ContourDesc c = desc[ci]; if (c.len > 0 && c.off >= 0 && c.off + c.len <= g.max_points) { len = c.len; src = c.off; } }
+            }
+            int sc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (tid >= o) sc += t; }
+            if (m < n_markers) { s_ofs[m] = run + sc - len; s_src[m] = src; }
+            run += __shfl_sync(0xffffffffu, sc, 31);
+        }
+        if (tid == 0) s_ofs[n_markers] = run;
+    }
+    __syncthreads();
+    for (int m = tid; m <= n_markers; m += blockDim.x) ofs[m] = s_ofs[m];
+    if (s_ofs[n_markers] > g.max_points) return;
+    for (int m = 0; m < n_markers; m++) {
+        const int len = s_ofs[m + 1] - s_ofs[m];
+        for (int i = tid; i < len; i += blockDim.x) out[s_ofs[m] + i] = pts[s_src[m] + i];
+    }
+}
+
 }  // namespace b200
 
 // =================================================================================================
@@ -1404,6 +1436,7 @@ struct b200_aruco_s {
     // staging for the host API
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
     int* d_mcontour;                          // [max_batch][kMaxMarkers]: the border (ContourDesc index) every output marker came from
+    void* d_pack;                             // staging of b200_aruco_get_contours: offsets + packed points of one frame
 };
 
 namespace {
@@ -1527,7 +1560,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1583,8 +1616,12 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     // contour following: against the frame's bit image in shared memory when it fits (one CTA per frame), else the global-memory walkers
     const int ct_pw = (w + 1) / 30 + 1, ct_npw = (w + 31) / 32;
     const size_t ct_smem = ((size_t)(hh + 2) * ct_pw + (size_t)kCtWarps * (ct_npw + 4)) * 4;
-    static const bool ct_global = getenv("B200_CONTOURS_GLOBAL") != nullptr;
-    const bool ct_shared = !ct_global && ct_smem <= 200 * 1024 && w < 32768 / 2;
+    // Default: the global-memory walkers (k_probe_a / b1 / b + k_emit), many CTAs per frame.  B200_CONTOURS_SHARED=1: k_contours, one CTA per frame against the
+    // bit image in shared memory.  Measured on a B200 (profiles/r2f_variants.txt, r2i): the same 256 x 640 x 480 step time (4.47 vs 4.51 ms: the step is bound by
+    // pipe throughput, and building the 8-neighbour mask from three bit rows costs ~12 ALU instructions where the global form does one load), slower at
+    // 1280 x 720 (124 KB of shared memory: one CTA per SM) and 3x slower for a single frame (one CTA does the whole frame: 2.3 vs 0.8 ms per detect call).
+    static const bool ct_want_shared = getenv("B200_CONTOURS_SHARED") != nullptr;
+    const bool ct_shared = ct_want_shared && ct_smem <= 200 * 1024 && w < 32768 / 2;
     if (ct_shared) {
         static std::atomic<size_t> ct_smem_set(0);
         if (ct_smem > 48 * 1024 && ct_smem > ct_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_contours, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem)); ct_smem_set.store(ct_smem); }
@@ -1698,6 +1735,40 @@ int b200_aruco_get_contour(b200_aruco_t h, int frame, int index, int32_t* xy, in
         for (int i = 0; i < m; i++) { xy[2 * i] = p[i].x; xy[2 * i + 1] = p[i].y; }
     }
     return cd.len;
+}
+
+// All contours of a frame's markers in one round trip (the adapter's detect() fills every Marker::contourPoints): k_pack_contours gathers the
+// borders of the n_markers output markers into one packed block, then two copies bring offsets and points home.
+// ofs [n_markers + 1] (HOST): marker m owns xy [ofs[m] .. ofs[m + 1]) of xy [xy_cap][2] int32.  Returns the total number of points.
+int b200_aruco_get_contours(b200_aruco_t h, int frame, int n_markers, int32_t* ofs, int32_t* xy, int xy_cap) {
+    if (!h || !ofs || (!xy && xy_cap > 0)) return fail(B200_EINVAL, "null %s", "argument");
+    if (frame < 0 || frame >= h->max_batch || n_markers < 0 || n_markers > kMaxMarkers) return fail(B200_EINVAL, "no such %s", "frame / marker count");
+    DeviceScope _ds; int rc = use_device(h->device);
+    if (rc) return rc;
+    ofs[0] = 0;
+    if (n_markers == 0) return 0;
+    cudaStream_t st = h->stream;
+    if (!h->d_pack) {
+        B200_CUDA(cudaMalloc((void**)&h->d_pack, sizeof(int) * (kMaxMarkers + 1) + sizeof(short2) * (size_t)h->geom.max_points));
+    }
+    int* d_ofs = reinterpret_cast<int*>(h->d_pack);
+    short2* d_pp = reinterpret_cast<short2*>(d_ofs + kMaxMarkers + 1);
+    B200_LAUNCH(k_pack_contours, 1, 256, 0, st, h->geom, h->d_mcontour + (size_t)frame * kMaxMarkers, n_markers,
+                h->d_desc + (size_t)frame * h->geom.max_contours, h->d_pts + (size_t)frame * h->geom.max_points, d_ofs, d_pp);
+    int hofs[kMaxMarkers + 1];
+    B200_CUDA(cudaMemcpyAsync(hofs, d_ofs, sizeof(int) * (n_markers + 1), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    const int total = hofs[n_markers];
+    if (total < 0 || total > h->geom.max_points) return fail(B200_EINVAL, "stale %s", "contours");
+    for (int m = 0; m <= n_markers; m++) ofs[m] = hofs[m];
+    const int take = std::min(total, xy_cap);
+    if (take > 0) {
+        std::vector<short2> p(take);
+        B200_CUDA(cudaMemcpyAsync(p.data(), d_pp, sizeof(short2) * take, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < take; i++) { xy[2 * i] = p[i].x; xy[2 * i + 1] = p[i].y; }
+    }
+    return total;
 }
 
 int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int w, int hh, int64_t rs, int64_t fs,

@@ -124,21 +124,14 @@ int b200_voc_transform_host(b200_voc_t h, const uint8_t* desc, int n, int levels
     if (rc) return rc;
     if (n == 0) return B200_OK;
     if (!desc || !word_id || !weight || !node_id) return fail(B200_EINVAL, "null %s", "pointer");
-    uint8_t* dd = nullptr; int* dw = nullptr; double* dwt = nullptr; int* dn = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dd, 32 * (size_t)n);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dw, 4 * (size_t)n);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dwt, 8 * (size_t)n);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dn, 4 * (size_t)n);
-    if (e == cudaSuccess) e = cudaMemcpy(dd, desc, 32 * (size_t)n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        rc = b200_voc_transform(h, dd, n, levelsup, dw, dwt, dn, nullptr);
-        if (!rc) e = cudaMemcpy(word_id, dw, 4 * (size_t)n, cudaMemcpyDeviceToHost);
-        if (!rc && e == cudaSuccess) e = cudaMemcpy(weight, dwt, 8 * (size_t)n, cudaMemcpyDeviceToHost);
-        if (!rc && e == cudaSuccess) e = cudaMemcpy(node_id, dn, 4 * (size_t)n, cudaMemcpyDeviceToHost);
-    }
-    cudaFree(dd); cudaFree(dw); cudaFree(dwt); cudaFree(dn);
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(B200_ECUDA, "vocabulary transform: %s", cudaGetErrorString(e));
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(h->device, &ts))) return rc;
+    DevBuf dd, dw, dwt, dn;
+    if ((rc = dd.upload(desc, 32 * (size_t)n)) || (rc = dw.alloc(4 * (size_t)n)) || (rc = dwt.alloc(8 * (size_t)n)) || (rc = dn.alloc(4 * (size_t)n))) return rc;
+    if ((rc = b200_voc_transform(h, (const uint8_t*)dd.p, n, levelsup, (int32_t*)dw.p, (double*)dwt.p, (int32_t*)dn.p, ts))) return rc;
+    B200_D2H(word_id, dw.p, 4 * (size_t)n);
+    B200_D2H(weight, dwt.p, 8 * (size_t)n);
+    B200_D2H(node_id, dn.p, 4 * (size_t)n);
     return B200_OK;
 }
 

@@ -49,6 +49,21 @@ cudaStream_t thread_stream(int device) {
     return t_streams.s[device];
 }
 
+thread_local cudaStream_t t_ts = nullptr;
+
+int host_call_stream(int device, cudaStream_t* ts) {
+    static std::atomic<int> pool_set[64];
+    if (device >= 0 && device < 64 && !pool_set[device].load(std::memory_order_acquire)) {
+        cudaMemPool_t pool;
+        B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_set[device].store(1, std::memory_order_release);
+    }
+    *ts = t_ts = thread_stream(device);
+    return B200_OK;
+}
+
 }  // namespace b200
 
 extern "C" {

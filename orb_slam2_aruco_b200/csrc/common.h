@@ -56,6 +56,20 @@ struct DeviceScope {
 // stalls the tracking thread's extractor, and nothing runs on the legacy default stream.
 cudaStream_t thread_stream(int device);
 
+// stream-ordered scratch of the _host entry points: everything a call allocates, copies and launches goes to the calling thread's own stream
+// (thread_stream), so concurrent calls from the reference's three threads neither serialise on the legacy default stream nor wait for each other
+extern thread_local cudaStream_t t_ts;
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, t_ts); }
+    int alloc(size_t n) { B200_CUDA(cudaMallocAsync(&p, n > 32 ? n : 32, t_ts)); return B200_OK; }
+    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; if (n) B200_CUDA(cudaMemcpyAsync(p, h, n, cudaMemcpyHostToDevice, t_ts)); return B200_OK; }
+};
+// selects the calling thread's stream for `device` (and keeps the device's default memory pool from giving blocks back at every synchronisation)
+int host_call_stream(int device, cudaStream_t* ts);
+// device -> host copy that is complete when it returns, whatever kind of host memory the caller passed
+#define B200_D2H(dst, src, n) do { B200_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, ts)); B200_CUDA(cudaStreamSynchronize(ts)); } while (0)
+
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // round-half-even of a float (cvRound semantics) on the host side

@@ -193,17 +193,12 @@ int b200_frame_undistort_points_host(const float* xy, int n, const float* cam9, 
     std::vector<b200_keypoint> h((size_t)n);
     memset(h.data(), 0, (size_t)n * sizeof(b200_keypoint));
     for (int i = 0; i < n; i++) { h[i].x = xy[2 * i]; h[i].y = xy[2 * i + 1]; }
-    b200_keypoint* d = nullptr; int* dc = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, (size_t)n * sizeof(b200_keypoint));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, 4);
-    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), (size_t)n * sizeof(b200_keypoint), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(dc, &n, 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        B200_LAUNCH(k_undistort, (unsigned)((n + 255) / 256), 256, 0, 0, d, dc, 1, n, c, d);
-        e = cudaMemcpy(h.data(), d, (size_t)n * sizeof(b200_keypoint), cudaMemcpyDeviceToHost);
-    }
-    cudaFree(d); cudaFree(dc);
-    if (e != cudaSuccess) return fail(B200_ECUDA, "undistort points: %s", cudaGetErrorString(e));
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
+    DevBuf d, dc;
+    if ((rc = d.upload(h.data(), (size_t)n * sizeof(b200_keypoint))) || (rc = dc.upload(&n, 4))) return rc;
+    B200_LAUNCH(k_undistort, (unsigned)((n + 255) / 256), 256, 0, ts, (b200_keypoint*)d.p, (int*)dc.p, 1, n, c, (b200_keypoint*)d.p);
+    B200_D2H(h.data(), d.p, (size_t)n * sizeof(b200_keypoint));
     for (int i = 0; i < n; i++) { xy_un[2 * i] = h[i].x; xy_un[2 * i + 1] = h[i].y; }
     return B200_OK;
 }
@@ -217,18 +212,13 @@ int b200_frame_image_bounds(int width, int height, const float* cam9, float* bou
     DeviceScope _ds; if ((rc = use_device(device))) return rc;
     b200_keypoint h[4] = {};
     h[1].x = (float)width; h[2].y = (float)height; h[3].x = (float)width; h[3].y = (float)height;
-    b200_keypoint* d = nullptr; int* dc = nullptr;
     const int four = 4;
-    cudaError_t e = cudaMalloc((void**)&d, sizeof(h));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, 4);
-    if (e == cudaSuccess) e = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(dc, &four, 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        B200_LAUNCH(k_undistort, 1, 256, 0, 0, d, dc, 1, 4, c, d);
-        e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    }
-    cudaFree(d); cudaFree(dc);
-    if (e != cudaSuccess) return fail(B200_ECUDA, "image bounds: %s", cudaGetErrorString(e));
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
+    DevBuf d, dc;
+    if ((rc = d.upload(h, sizeof(h))) || (rc = dc.upload(&four, 4))) return rc;
+    B200_LAUNCH(k_undistort, 1, 256, 0, ts, (b200_keypoint*)d.p, (int*)dc.p, 1, 4, c, (b200_keypoint*)d.p);
+    B200_D2H(h, d.p, sizeof(h));
     bounds4[0] = fminf(h[0].x, h[2].x); bounds4[1] = fmaxf(h[1].x, h[3].x); bounds4[2] = fminf(h[0].y, h[1].y); bounds4[3] = fmaxf(h[2].y, h[3].y);
     return B200_OK;
 }

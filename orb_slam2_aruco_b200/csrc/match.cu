@@ -1075,33 +1075,6 @@ int b200_match_bf_kp_range(const uint8_t* ref_desc, const b200_keypoint* ref_kps
                          n_frame, n_batch, frame_cap, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, device, stream, base, total);
 }
 
-namespace {
-// stream-ordered scratch of the _host entry points: everything a call allocates, copies and launches goes to the calling thread's own stream
-// (thread_stream), so concurrent calls from the reference's three threads neither serialise on the legacy default stream nor wait for each other
-thread_local cudaStream_t t_ts = nullptr;
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFreeAsync(p, t_ts); }
-    int alloc(size_t n) { B200_CUDA(cudaMallocAsync(&p, std::max<size_t>(n, 32), t_ts)); return B200_OK; }
-    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; if (n) B200_CUDA(cudaMemcpyAsync(p, h, n, cudaMemcpyHostToDevice, t_ts)); return B200_OK; }
-};
-// the default memory pool gives freed blocks back to the driver at every synchronisation unless told to keep them
-int host_call_stream(int device, cudaStream_t* ts) {
-    static std::atomic<int> pool_set[64];
-    if (device >= 0 && device < 64 && !pool_set[device].load(std::memory_order_acquire)) {
-        cudaMemPool_t pool;
-        B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long keep = ~0ull;
-        B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_set[device].store(1, std::memory_order_release);
-    }
-    *ts = t_ts = thread_stream(device);
-    return B200_OK;
-}
-// device -> host copy that is complete when it returns, whatever kind of host memory the caller passed
-#define B200_D2H(dst, src, n) do { B200_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, ts)); B200_CUDA(cudaStreamSynchronize(ts)); } while (0)
-}
-
 int b200_match_bf_host(const uint8_t* ref_desc, const float* ref_angle, int n_ref,
                        const uint8_t* frame_desc, const float* frame_angle, const int32_t* n_frame, int n_batch, int frame_cap,
                        float ratio, int th_low, int check_ori, float histo_factor,

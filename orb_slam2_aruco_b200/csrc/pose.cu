@@ -309,19 +309,12 @@ int b200_aruco_pose_host(const b200_marker* markers, int n_markers, float marker
     if (rc) return rc;
     if (n_markers == 0) return B200_OK;
     if (!markers || !poses) return fail(B200_EINVAL, "null %s", "pointer");
-    b200_marker* dm = nullptr; int32_t* dc = nullptr; b200_marker_pose* dp = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dm, sizeof(b200_marker) * n_markers);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, 4);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dp, sizeof(b200_marker_pose) * n_markers);
-    if (e == cudaSuccess) e = cudaMemcpy(dm, markers, sizeof(b200_marker) * n_markers, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(dc, &n_markers, 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        rc = b200_aruco_pose(dm, dc, 1, n_markers, marker_size, cam9, dp, device, nullptr);
-        if (!rc) e = cudaMemcpy(poses, dp, sizeof(b200_marker_pose) * n_markers, cudaMemcpyDeviceToHost);
-    }
-    cudaFree(dm); cudaFree(dc); cudaFree(dp);
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(B200_ECUDA, "pose: %s", cudaGetErrorString(e));
+    cudaStream_t ts = nullptr;
+    if ((rc = host_call_stream(device, &ts))) return rc;
+    DevBuf dm, dc, dp;
+    if ((rc = dm.upload(markers, sizeof(b200_marker) * n_markers)) || (rc = dc.upload(&n_markers, 4)) || (rc = dp.alloc(sizeof(b200_marker_pose) * n_markers))) return rc;
+    if ((rc = b200_aruco_pose((const b200_marker*)dm.p, (const int32_t*)dc.p, 1, n_markers, marker_size, cam9, (b200_marker_pose*)dp.p, device, ts))) return rc;
+    B200_D2H(poses, dp.p, sizeof(b200_marker_pose) * n_markers);
     return B200_OK;
 }
 
