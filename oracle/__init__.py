@@ -88,6 +88,20 @@ def adapter_match():
     return _adapter_match
 
 
+_ref_ippe = None
+
+
+def ref_ippe():
+    """The reference's own pose solver (Thirdparty/aruco/aruco/ippe.cpp on oracle/ippeshim, oracle/ref_ippe_wrap.cpp), or None when never built."""
+    global _ref_ippe
+    if _ref_ippe is None:
+        path = os.path.join(HERE, "_ref", "libref_ippe.so")
+        if not os.path.exists(path):
+            return None
+        _ref_ippe = C.CDLL(path)
+    return _ref_ippe
+
+
 _ref_mappoint = None
 
 

@@ -74,3 +74,28 @@ def test_invalid_arguments(built_lib):
     assert np.allclose(p["tvec"], [0, 0, 1], atol=1e-6) and np.allclose(p["rvec"], 0, atol=1e-6)
     assert len(det.estimate_poses(mk[:0], 0.2, cp)) == 0
     det.close()
+
+
+def test_poses_equal_the_reference_s_own_solver(built_lib, golden_dir):
+    """tests/golden/ippe_ref.npz: answers of Thirdparty/aruco/aruco/ippe.cpp itself (compiled unmodified into oracle/_ref/libref_ippe.so, written by
+    tests/golden/make_ippe_ref_golden.py) - k_pose must give the same two poses and errors (float outputs of a double pipeline: 2e-6)"""
+    g = np.load(os.path.join(golden_dir, "ippe_ref.npz"))
+    det = MarkerDetector("ARUCO_MIP_25h7")
+    corners, cams, sizes, want = g["corners"], g["cams"], g["sizes"], g["poses"]
+    done = 0
+    for cam in np.unique(cams, axis=0):
+        for size in np.unique(sizes):
+            sel = np.nonzero((cams == cam).all(1) & (sizes == size))[0]
+            if len(sel) == 0:
+                continue
+            cp = CameraParameters([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], cam[4:9])
+            mk = np.zeros(len(sel), MARKER_DTYPE)
+            mk["xy"] = corners[sel].reshape(len(sel), 8)
+            poses = det.estimate_poses(mk, float(size), cp)
+            for j, i in enumerate(sel):
+                p, w = poses[j], want[i]
+                assert close(p["rvec"], w[0:3]) and close(p["tvec"], w[3:6]) and close(p["rvec2"], w[7:10]) and close(p["tvec2"], w[10:13]), i
+                assert abs(p["err1"] - w[6]) <= 1e-5 * max(1, w[6]) and abs(p["err2"] - w[13]) <= 1e-5 * max(1, w[13])
+                done += 1
+    assert done == len(corners)
+    det.close()
