@@ -170,6 +170,125 @@ k_athresh(const uint8_t* __restrict__ img, long long row_stride, long long frame
 }
 
 // ------------------------------------------------------------------------------------------------
+// A1, register form (the default): the same threshold and the same 8-neighbour mask as k_athresh, without shared memory.
+// A warp owns a band of 128 columns (lane = one aligned word = 4 columns) and walks down a strip of kAt2Rows rows:
+//   * vertical window sums of the lane's four columns as running sums in two u16x2 registers (even / odd columns), one word load for the row that
+//     enters and one for the row that leaves.  sm_100a has a packed 16-bit add (VIADD.16x2) but no packed subtract, so the leaving row is added as its
+//     complement (~x = -x - 1): after k steps every sum is k too small, the same k in every column, and the threshold constant of the row absorbs it
+//   * horizontal window sums of the four columns from the lanes one (windows <= 7) or two (<= 15) to the left and right: shuffles of the two
+//     registers, then adds of pairs that are either a neighbour's register or one PRMT across two of them
+//   * v + 7 <= rint(S / bs^2)  <=>  S >= bs^2 (v + 7) - (bs^2 - 1) / 2 (both sides integers; checked for every S and v, tests/test_aruco_oracle.py), with
+//     all pixels biased by -128 so that both sides fit signed 16 bits: IMAD on the packed centre pixels, VIADD.16x2 of the row constant, and
+//     min.u16x2((max.s16x2(S, thr) ^ S), 1) is 1 exactly where S < thr
+//   * the binary words of the lanes left and right arrive with two more shuffles; three rows of them give the mask bytes as in k_athresh.
+// Lanes outside the image replicate the border columns (BORDER_REPLICATE), rows likewise; the first / last H + 1 lanes of a band are halo.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAt2Warps = 4, kAt2Rows = 64;
+
+__device__ __forceinline__ unsigned add16x2(unsigned a, unsigned b) { unsigned d; asm("add.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned max_s16x2(unsigned a, unsigned b) { unsigned d; asm("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned min_u16x2(unsigned a, unsigned b) { unsigned d; asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned hi_lo16(unsigned lo, unsigned hi) { return __byte_perm(lo, hi, 0x5432); }       // (lo.hi16, hi.lo16)
+
+// column pair (V(c0 + J), V(c0 + J + 2)) of the lane whose first column is c0; A[m + H] = (V0, V2), B[m + H] = (V1, V3) of lane + m
+template <int J, int H>
+__device__ __forceinline__ unsigned at2_pair(const unsigned (&A)[2 * H + 1], const unsigned (&B)[2 * H + 1]) {
+    constexpr int m = J >= 0 ? J / 4 : -((-J + 3) / 4);
+    constexpr int q = J - 4 * m;
+    if constexpr (q == 0) return A[m + H];
+    else if constexpr (q == 1) return B[m + H];
+    else if constexpr (q == 2) return hi_lo16(A[m + H], A[m + H + 1]);
+    else return hi_lo16(B[m + H], B[m + H + 1]);
+}
+template <int J, int JE, int H> struct At2Sum {
+    static __device__ __forceinline__ unsigned run(const unsigned (&A)[2 * H + 1], const unsigned (&B)[2 * H + 1]) { return add16x2(at2_pair<J, H>(A, B), At2Sum<J + 1, JE, H>::run(A, B)); }
+};
+template <int JE, int H> struct At2Sum<JE, JE, H> {
+    static __device__ __forceinline__ unsigned run(const unsigned (&A)[2 * H + 1], const unsigned (&B)[2 * H + 1]) { return at2_pair<JE, H>(A, B); }
+};
+
+// FASTW: every lane of the warp reads aligned words inside the image (all warps but those of the first / last band and of unaligned images)
+template <int R, bool FASTW>
+__device__ __forceinline__ void at2_strip(const uint8_t* __restrict__ src, int row_stride, const ArucoGeom& g, uint8_t* __restrict__ mrow,
+                                          int ys, int ye, int c0, int lane, bool fast) {
+    constexpr int BS = 2 * R + 1, AREA = BS * BS, H = R <= 3 ? 1 : 2;
+    const int x0 = min(max(c0, 0), g.w - 1), x1 = min(max(c0 + 1, 0), g.w - 1), x2 = min(max(c0 + 2, 0), g.w - 1), x3 = min(max(c0 + 3, 0), g.w - 1);
+    unsigned colmask = 0;                                             // 0x01 in every byte whose column lies in the image
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (c0 + b >= 0 && c0 + b < g.w) colmask |= 1u << (8 * b);
+    const int hm1 = g.h - 1;
+    auto load = [&](int y) -> unsigned {
+        const uint8_t* row = src + (unsigned)(min(max(y, 0), hm1) * row_stride);
+        if (FASTW || fast) return *reinterpret_cast<const uint32_t*>(row + c0);
+        return (unsigned)row[x0] | ((unsigned)row[x1] << 8) | ((unsigned)row[x2] << 16) | ((unsigned)row[x3] << 24);
+    };
+    // vertical sums of binary row ys - 1: rows ys - 1 - R .. ys - 1 + R, every pixel biased by -128
+    unsigned VA = (unsigned)((65536 - 128 * BS) & 0xffff) * 0x10001u, VB = VA;
+#pragma unroll
+    for (int k = -R; k <= R; k++) {
+        const unsigned w = load(ys - 1 + k);
+        VA = add16x2(VA, __byte_perm(w, 0u, 0x4240)); VB = add16x2(VB, __byte_perm(w, 0u, 0x4341));
+    }
+    int ck = (7 * AREA - (AREA - 1) / 2 - 128 * AREA) & 0xffff;       // threshold constant of the row (16 bits), minus BS per vertical step
+    unsigned al = 0, ac = 0, ar = 0, bl = 0, bc = 0, br = 0;          // binary words (left lane, own, right lane) of rows yb - 2 and yb - 1
+    const bool out_lane = lane >= H + 1 && lane <= 30 - H && c0 < g.w;
+    unsigned wc = load(ys - 1), wn = load(ys + R), wo = load(ys - 1 - R);     // centre row of this step; the rows that enter / leave after it
+#pragma unroll 1
+    for (int yb = ys - 1; yb <= ye; yb++) {
+        const unsigned wc2 = load(yb + 1), wn2 = load(yb + R + 2), wo2 = load(yb + 1 - R);      // the next step's rows, in flight during this one
+        // horizontal window sums
+        unsigned A[2 * H + 1], B[2 * H + 1];
+        A[H] = VA; B[H] = VB;
+#pragma unroll
+        for (int m = 1; m <= H; m++) {
+            A[H - m] = __shfl_up_sync(0xffffffffu, VA, m); B[H - m] = __shfl_up_sync(0xffffffffu, VB, m);
+            A[H + m] = __shfl_down_sync(0xffffffffu, VA, m); B[H + m] = __shfl_down_sync(0xffffffffu, VB, m);
+        }
+        const unsigned M = At2Sum<-R + 1, R, H>::run(A, B);
+        const unsigned S02 = add16x2(M, at2_pair<-R, H>(A, B)), S13 = add16x2(M, at2_pair<R + 1, H>(A, B));
+        // threshold
+        const unsigned Ck = (unsigned)ck * 0x10001u;
+        const unsigned t02 = add16x2(__byte_perm(wc, 0u, 0x4240) * (unsigned)AREA, Ck), t13 = add16x2(__byte_perm(wc, 0u, 0x4341) * (unsigned)AREA, Ck);
+        const unsigned n02 = min_u16x2(max_s16x2(S02, t02) ^ S02, 0x10001u), n13 = min_u16x2(max_s16x2(S13, t13) ^ S13, 0x10001u);       // 1 = background
+        const unsigned bin = (yb >= 0 && yb <= hm1) ? ((__byte_perm(n02, n13, 0x6240) ^ 0x01010101u) & colmask) : 0u;
+        const unsigned cl = __shfl_up_sync(0xffffffffu, bin, 1), cr = __shfl_down_sync(0xffffffffu, bin, 1);
+        // mask row yb - 1 from the binary rows yb - 2 (a), yb - 1 (b), yb (c)
+        if (yb >= ys + 1 && out_lane) {
+            const uint32_t W = __funnelshift_r(bl, bc, 24), E = __funnelshift_r(bc, br, 8);
+            const uint32_t NW = __funnelshift_r(al, ac, 24), NE = __funnelshift_r(ac, ar, 8);
+            const uint32_t SW = __funnelshift_r(cl, bin, 24), SE = __funnelshift_r(bin, cr, 8);
+            uint32_t m = E + 2u * NE + 4u * ac + 8u * NW + 16u * W + 32u * SW + 64u * bin + 128u * SE;
+            m &= bc * 255u;
+            *reinterpret_cast<uint32_t*>(mrow + (unsigned)(yb * g.bpitch)) = m;     // row yb - 1 lives at (yb - 1 + 1) * bpitch
+        }
+        al = bl; ac = bc; ar = br; bl = cl; bc = bin; br = cr;
+        // slide the vertical window down by one row (the last step's slide is unused)
+        const unsigned nwo = ~wo;
+        VA = add16x2(add16x2(VA, __byte_perm(wn, 0u, 0x4240)), __byte_perm(nwo, 0u, 0x4240) | 0xff00ff00u);
+        VB = add16x2(add16x2(VB, __byte_perm(wn, 0u, 0x4341)), __byte_perm(nwo, 0u, 0x4341) | 0xff00ff00u);
+        ck = (ck - BS) & 0xffff;
+        wc = wc2; wn = wn2; wo = wo2;
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kAt2Warps * 32)
+k_athresh2(const uint8_t* __restrict__ img, long long row_stride, long long frame_stride, const __grid_constant__ ArucoGeom g, uint8_t* __restrict__ mask) {
+    constexpr int H = R <= 3 ? 1 : 2, NOUT = 30 - 2 * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.z;
+    const int ys = (blockIdx.y * kAt2Warps + warp) * kAt2Rows;
+    if (ys >= g.h) return;
+    const int ye = min(ys + kAt2Rows, g.h);
+    const int c0 = (blockIdx.x * NOUT + lane - (H + 1)) * 4;          // image column of the lane's first pixel
+    const uint8_t* src = img + (long long)f * frame_stride;
+    const bool fast = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)row_stride) & 3) == 0 && c0 >= 0 && c0 + 3 < g.w;
+    uint8_t* mrow = mask + (long long)f * g.bframe + c0 + kMaskPad;
+    if (__all_sync(0xffffffffu, fast)) at2_strip<R, true>(src, (int)row_stride, g, mrow, ys, ye, c0, lane, true);
+    else at2_strip<R, false>(src, (int)row_stride, g, mrow, ys, ye, c0, lane, fast);
+}
+
+// ------------------------------------------------------------------------------------------------
 // pyramid by 1/2 (markerdetector_impl.cpp:1300-1466): cv::resize(INTER_LINEAR) == 2x2 area mean when both
 // factors are exactly 2, else the generic 11-bit fixed-point bilinear (coefficients computed in-kernel in double/float
 // exactly like the host table of the ORB pyramid).
@@ -1606,7 +1725,21 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
         *d_nsurv = h->d_nsurv + base, *d_nfetch = h->d_nfetch + base, *d_nsurv2 = h->d_nsurv2 + base;
     dim3 blk(32, 8);
     dim3 gt((w + kThrTW - 1) / kThrTW, (hh + kThrTH - 1) / kThrTH, n);
-    B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, d_mask);
+    static const bool athresh_smem = getenv("B200_ATHRESH_SMEM") != nullptr;      // the round-1 kernel (shared-memory box sums), kept for comparison
+    if (athresh_smem || rs * (long long)hh >= (1ll << 31)) B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, d_mask);      // (k_athresh2 keeps row offsets in 32 bits)
+    else {
+        const int R = g.win >> 1, nout = 4 * (30 - 2 * (R <= 3 ? 1 : 2));
+        dim3 g2((w + nout - 1) / nout, ((hh + kAt2Rows - 1) / kAt2Rows + kAt2Warps - 1) / kAt2Warps, n);
+        switch (R) {
+            case 1: B200_LAUNCH(k_athresh2<1>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+            case 2: B200_LAUNCH(k_athresh2<2>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+            case 3: B200_LAUNCH(k_athresh2<3>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+            case 4: B200_LAUNCH(k_athresh2<4>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+            case 5: B200_LAUNCH(k_athresh2<5>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+            case 6: B200_LAUNCH(k_athresh2<6>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+            default: B200_LAUNCH(k_athresh2<7>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+        }
+    }
     for (int l = 1; l < g.nlev; l++) {
         const uint8_t* src = l == 1 ? imgs : d_pyr + g.loff[l - 1];
         const long long srs = l == 1 ? rs : g.lpitch[l - 1], sfs = l == 1 ? fs : g.pyr_frame;

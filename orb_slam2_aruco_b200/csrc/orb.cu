@@ -425,6 +425,222 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, warp-per-cell form (B200_FAST_WARP=1).  The same three stages as k_fast above with the same arithmetic, but ONE warp owns a cell from the TMA box to the
+// candidate slots, so nothing in it is a CTA barrier, an atomic on a shared flag or a loop that four warps repeat: the per-line ncu profile of k_fast
+// (profiles/r2n_fast_lines.txt) spends 4800 warp instructions per cell, about 1000 of them in prologues and clears every warp executes and as many in
+// ballots and queue bookkeeping per pretest row.  Here
+//   * the pretest keeps its verdicts in a 64-bit register mask per lane (4 bits per row the lane visits) and the survivors are compacted once per 16
+//     rows-of-lanes: one warp scan of the popcounts, then every lane writes its own entries
+//   * survivor queue and corner list have fixed sizes (kFwQ, kFwC): survivors beyond the queue are scored in further rounds of the same compaction; a
+//     cell with more than kFwC corners falls back to an NMS sweep over the whole score tile
+//   * NMS hits are an OR into the row's keep words, and the raster-ordered emission is the warp's own scan.
+// A CTA is kFwWarps independent warps (cells blockIdx.x * kFwWarps ...), each with its own mbarrier and its own slice of dynamic shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFwWarps = 4;
+constexpr int kFwQ = 512;                    // survivor queue entries per warp
+constexpr int kFwC = 256;                    // corner list entries per warp
+
+template <int TP>
+__global__ void __launch_bounds__(kFwWarps * 32)
+k_fastw(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
+        const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ FastMaps maps,
+        int tile_bytes, int keepw, int warp_bytes, int tma_level0, int scratch_base,
+        const CellDesc* __restrict__ cells, uint32_t* __restrict__ slots, int* __restrict__ cellcnt) {
+    extern __shared__ __align__(1024) unsigned char fs_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[kFwWarps];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci = blockIdx.x * kFwWarps + warp;
+    if (ci >= g.total_cells) return;
+    const CellDesc cd = cells[ci];
+    const int f = blockIdx.y;
+    const LevelGeom& lg = g.L[cd.level];
+    constexpr int tp = TP;
+    uint8_t* tile = fs_raw + (size_t)warp * warp_bytes;                                 // [box_h][tp], column = ox + ROI column
+    uint8_t* score = tile + tile_bytes;                                                 // same geometry
+    uint16_t* q = reinterpret_cast<uint16_t*>(score + tile_bytes);                      // survivors: y << 8 | tile column
+    uint16_t* cq = q + kFwQ;                                                            // corners
+    uint32_t* keep = reinterpret_cast<uint32_t*>(cq + kFwC);                            // [ih][3] bit index = interior column
+
+    const int rw = cd.rw, rh = cd.rh;
+    const bool use_tma = cd.level > 0 || tma_level0;
+    const int ox = cd.x0 & 15;
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    if (use_tma) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(TP * lg.box_h) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&maps.m[cd.level])), "r"((int)cd.x0 - ox), "r"((int)cd.y0),
+                            "r"(cd.level > 0 ? scratch_base + f : f), "r"(bar) : "memory");
+        }
+    } else {
+        const uint8_t* base = img0 + (long long)f * img_frame_stride + (long long)cd.y0 * img_row_stride + cd.x0;
+        for (int y = 0; y < rh; y++)
+            for (int x = lane; x < rw; x += 32) tile[y * tp + ox + x] = base[(long long)y * img_row_stride + x];
+    }
+    {   // meanwhile: clear the score tile and the keep words
+        uint4* sc4 = reinterpret_cast<uint4*>(score);
+        for (int i = lane; i < (rh * tp) >> 4; i += 32) sc4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int iw = rw - 6, ih = rh - 6;               // interior
+    const int tc0 = ox + 3, tc1 = tc0 + iw;           // interior tile columns [tc0, tc1)
+    const int g_lo = tc0 >> 2, ngroups = ((tc1 - 1) >> 2) - g_lo + 1;      // aligned 4-pixel groups that hold interior pixels (<= 18)
+    const int rpi = 32 / ngroups;                     // rows per warp iteration
+    const int my_sub = lane / ngroups, my_g = g_lo + lane - my_sub * ngroups;
+    const bool my_on = my_sub < rpi;
+    unsigned valid_e = 0, valid_o = 0;
+    {
+        const int c = 4 * my_g;
+        if (c >= tc0 && c < tc1) valid_e |= 0x0000ffffu;
+        if (c + 2 >= tc0 && c + 2 < tc1) valid_e |= 0xffff0000u;
+        if (c + 1 >= tc0 && c + 1 < tc1) valid_o |= 0x0000ffffu;
+        if (c + 3 >= tc0 && c + 3 < tc1) valid_o |= 0xffff0000u;
+    }
+    const unsigned lt = (1u << lane) - 1;
+    __syncwarp();
+    if (use_tma)
+        asm volatile("{\n.reg .pred p;\nFASTW_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra FASTW_DONE;\nbra FASTW_WAIT;\nFASTW_DONE:\n}"
+                     :: "r"(bar) : "memory");
+
+    int T = g.ini_th;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = lane; i < ih * 3; i += 32) keep[i] = 0u;
+        const unsigned Tp = (unsigned)T * 0x10001u, Tn = (unsigned)(0x10000 - T) * 0x10001u;
+        int nc = 0;                                   // corners (score >= T) found so far; > kFwC = the list overflowed
+        for (int yb = 0; yb < ih; yb += 16 * rpi) {   // block of up to 16 warp iterations = 64 verdict bits per lane
+            // 1. pretest
+            unsigned mlo = 0, mhi = 0;
+            const uint32_t* r = reinterpret_cast<const uint32_t*>(tile + (yb + my_sub + 3) * tp) + my_g;
+            constexpr int rp = tp >> 2;
+#pragma unroll 2
+            for (int it = 0; it < 16; it++) {
+                const int y = yb + it * rpi + my_sub;
+                if (yb + it * rpi >= ih) break;
+                if (my_on && y < ih) {
+                    const uint32_t* rr = r + it * rpi * rp;
+                    const uint32_t wl = rr[-1], wc = rr[0], wr = rr[1], wn = rr[-3 * rp], ws = rr[3 * rp];
+                    const unsigned ce = pair_e(wc), co = pair_o(wc), le = pair_e(wl), lo = pair_o(wl), re = pair_e(wr), ro = pair_o(wr);
+                    const unsigned me = fast_pretest_pair(ce, pair_e(wn), pair_e(ws), sh16(co, ro), lo, Tp, Tn) & valid_e;
+                    const unsigned mo = fast_pretest_pair(co, pair_o(wn), pair_o(ws), re, sh16(le, ce), Tp, Tn) & valid_o;
+                    const unsigned bits = ((me & 0xffffu) ? 1u : 0u) | ((mo & 0xffffu) ? 2u : 0u) | ((me >> 16) ? 4u : 0u) | ((mo >> 16) ? 8u : 0u);
+                    if (it < 8) mlo |= bits << (4 * it); else mhi |= bits << (4 * it - 32);
+                }
+            }
+            // 2. compaction + scoring in rounds of kFwQ survivors
+            const int cnt = __popc(mlo) + __popc(mhi);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int r0 = 0; r0 < total; r0 += kFwQ) {
+                {
+                    int rank = incl - cnt - r0;
+                    unsigned a = mlo, b = mhi;
+                    const int ent0 = ((yb + my_sub) << 8) | (4 * my_g);
+                    while (a | b) {
+                        int bit;
+                        if (a) { bit = __ffs(a) - 1; a &= a - 1; } else { bit = 32 + __ffs(b) - 1; b &= b - 1; }
+                        if (rank >= 0 && rank < kFwQ) q[rank] = (uint16_t)(ent0 + (((bit >> 2) * rpi) << 8) + (bit & 3));
+                        rank++;
+                    }
+                }
+                __syncwarp();
+                const int nq = min(kFwQ, total - r0);
+                for (int i0 = 0; i0 < nq; i0 += 64) {
+                    const int i = i0 + 2 * lane;
+                    int s0 = 0, s1 = 0, ea = 0, eb = 0;
+                    if (i < nq) {
+                        const unsigned e2 = *reinterpret_cast<const unsigned*>(q + i);
+                        ea = e2 & 0xffffu; eb = i + 1 < nq ? (int)(e2 >> 16) : ea;
+                        const uint8_t* pa = tile + ((ea >> 8) + 3) * tp + (ea & 255);
+                        const uint8_t* pb = tile + ((eb >> 8) + 3) * tp + (eb & 255);
+                        unsigned d[16];
+#define B200_LD2(j, off) d[j] = (unsigned)pa[off] | ((unsigned)pb[off] << 16)
+                        B200_LD2(0, 3 * tp); B200_LD2(1, 3 * tp + 1); B200_LD2(2, 2 * tp + 2); B200_LD2(3, tp + 3);
+                        B200_LD2(4, 3); B200_LD2(5, -tp + 3); B200_LD2(6, -2 * tp + 2); B200_LD2(7, -3 * tp + 1);
+                        B200_LD2(8, -3 * tp); B200_LD2(9, -3 * tp - 1); B200_LD2(10, -2 * tp - 2); B200_LD2(11, -tp - 3);
+                        B200_LD2(12, -3); B200_LD2(13, tp - 3); B200_LD2(14, 2 * tp - 2); B200_LD2(15, 3 * tp - 1);
+#undef B200_LD2
+                        const unsigned nV = __vneg2((unsigned)pa[0] | ((unsigned)pb[0] << 16));
+#pragma unroll
+                        for (int j = 0; j < 16; j++) d[j] = __vadd2(d[j], nV);
+                        const unsigned sc2 = fast_score_pair(d);
+                        s0 = (int)(short)(sc2 & 0xffffu); s1 = (int)sc2 >> 16;
+                        if (i + 1 >= nq) s1 = 0;
+                    }
+                    const bool k0 = s0 >= T, k1 = s1 >= T;
+                    if (k0) score[((ea >> 8) + 3) * tp + (ea & 255)] = (uint8_t)s0;
+                    if (k1) score[((eb >> 8) + 3) * tp + (eb & 255)] = (uint8_t)s1;
+                    const unsigned c0 = __ballot_sync(0xffffffffu, k0), c1 = __ballot_sync(0xffffffffu, k1);
+                    if (c0 | c1) {
+                        const int p0 = nc + __popc(c0 & lt), p1 = nc + __popc(c0) + __popc(c1 & lt);
+                        if (k0 && p0 < kFwC) cq[p0] = (uint16_t)ea;
+                        if (k1 && p1 < kFwC) cq[p1] = (uint16_t)eb;
+                        nc += __popc(c0) + __popc(c1);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // 3. NMS -> keep bits
+        __syncwarp();
+        bool any = false;
+        if (nc <= kFwC) {
+            for (int i = lane; i < nc; i += 32) {
+                const int e = cq[i], y = e >> 8, c = e & 255;
+                const uint8_t* sp = score + (y + 3) * tp + c;
+                const int sc = sp[0];
+                if (sc > sp[-1] && sc > sp[1] && sc > sp[-tp - 1] && sc > sp[-tp] && sc > sp[-tp + 1] && sc > sp[tp - 1] && sc > sp[tp] && sc > sp[tp + 1]) {
+                    const int x = c - tc0;
+                    atomicOr(&keep[y * 3 + (x >> 5)], 1u << (x & 31));
+                    any = true;
+                }
+            }
+        } else {
+            for (int i = lane; i < iw * ih; i += 32) {
+                const int y = i / iw, x = i - y * iw;
+                const uint8_t* sp = score + (y + 3) * tp + tc0 + x;
+                const int sc = sp[0];
+                if (sc >= T && sc > sp[-1] && sc > sp[1] && sc > sp[-tp - 1] && sc > sp[-tp] && sc > sp[-tp + 1] && sc > sp[tp - 1] && sc > sp[tp] && sc > sp[tp + 1]) {
+                    atomicOr(&keep[y * 3 + (x >> 5)], 1u << (x & 31));
+                    any = true;
+                }
+            }
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (any || pass == 1 || g.min_th >= g.ini_th) break;
+        T = g.min_th;                                 // nothing at iniThFAST: the whole cell again at minThFAST (scores already in the tile stay valid)
+    }
+    __syncwarp();
+    {   // raster-ordered emission: keep words in (row, chunk) order
+        uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
+        const int nkw = ih * 3;
+        int run = 0;
+        for (int w0 = 0; w0 < nkw; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t m = wi < nkw ? keep[wi] : 0u;
+            const int c = __popc(m);
+            int sc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+            int pos = run + sc - c;
+            const int y = wi / 3, ch = wi - y * 3;
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int x = ch * 32 + bit;
+                if (pos < cd.cap) out[pos] = (uint32_t)(x + 3 + cd.sx) | ((uint32_t)(y + 3 + cd.sy) << 12) | ((uint32_t)score[(y + 3) * tp + tc0 + x] << 24);
+                pos++;
+            }
+            run += __shfl_sync(0xffffffffu, sc, 31);
+        }
+        if (lane == 0) cellcnt[(long long)f * g.total_cells + ci] = run;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2 (dense form, the default): the FAST score is threshold independent and the cells' interiors tile the level, so the work splits
 // into a perfectly regular part and a tiny per-cell part.
 //
@@ -569,87 +785,105 @@ k_fast_score(const uint8_t* __restrict__ img0, long long img_row_stride, long lo
 
 constexpr int kNmsWarps = 8;
 
+// One warp per cell, one LANE per interior row (lanes 0 and 31 hold the rows above / below a block of 30), the row's scores in registers as aligned words split
+// into even / odd pixel pairs (u16x2).  "Strictly greater than the eight neighbours" is separable: h3 = max(left, centre, right) and h2 = max(left, right) per
+// row inside the lane, the rows above and below arrive with two shuffles per register, and the verdict of a pixel is the sign of
+// (max(h3 above, h3 below, h2) - s) & (T - 1 - s).  Scores outside the interior are masked to zero when the words are loaded (cv::FAST on the cell ROI never
+// sees them), so no ring has to be staged anywhere.  A pixel >= T never loses against a neighbour below T, which makes the test independent of the threshold:
+// iniThFAST first, minThFAST only when the cell stays empty (ORBextractor.cc:809-816).  The keep bits of a row are one nibble per word; a warp prefix over
+// their popcounts gives every row its first candidate slot, and the rows write their keys in raster order.
+template <int NW>
+__device__ __forceinline__ int nms_cell(const uint8_t* __restrict__ src, int spitch, int xi, int yi, int iw, int ih, int ini_th, int min_th, int lane,
+                                        uint32_t* __restrict__ out, int cap) {
+    const int xa = xi & ~3;                                           // first word
+    const int lo_clear = xi - xa;                                     // bytes of word 0 left of the interior
+    const int xe = xi + iw;                                           // one past the interior
+    int total = 0;
+    int T = ini_th;
+    for (int pass = 0; pass < 2; pass++) {
+        total = 0;
+        const unsigned Tm1 = (unsigned)(T - 1) * 0x10001u;
+        for (int rb = 0; rb < ih; rb += 30) {
+            __syncwarp();                                             // (tells the compiler the lanes are converged: plain SHFL instead of a collective per shuffle)
+            const int r = rb + lane - 1;                              // interior row of this lane
+            const bool row_on = r >= 0 && r < ih;
+            unsigned E[NW + 1], O[NW + 1];
+            const uint8_t* rowp = src + (long long)(yi + r) * spitch + xa;
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                unsigned w = 0;
+                if (row_on && xa + 4 * j < xe) {
+                    w = *reinterpret_cast<const uint32_t*>(rowp + 4 * j);
+                    if (j == 0 && lo_clear) w &= 0xffffffffu << (8 * lo_clear);
+                    const int hi = xa + 4 * j + 4 - xe;               // bytes past the interior
+                    if (hi > 0) w &= 0xffffffffu >> (8 * hi);
+                }
+                E[j] = __byte_perm(w, 0u, 0x4240); O[j] = __byte_perm(w, 0u, 0x4341);
+            }
+            E[NW] = 0u; O[NW] = 0u;
+            unsigned km[NW];                                          // keep masks: bit 8 b + 7 = pixel 4 j + b of the row
+            unsigned cnt = 0;
+            const bool emit = lane >= 1 && lane <= 30 && row_on;
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                const unsigned lfE = sh16(j ? O[j - 1] : 0u, O[j]);   // pixels (4j - 1, 4j + 1): left neighbours of the even pair
+                const unsigned rtO = sh16(E[j], E[j + 1]);            // pixels (4j + 2, 4j + 4): right neighbours of the odd pair
+                const unsigned h3E = __vimax3_s16x2(E[j], lfE, O[j]), h3O = __vimax3_s16x2(O[j], E[j], rtO);
+                const unsigned h2E = __vmaxs2(lfE, O[j]), h2O = __vmaxs2(E[j], rtO);
+                const unsigned upE = __shfl_up_sync(0xffffffffu, h3E, 1), dnE = __shfl_down_sync(0xffffffffu, h3E, 1);
+                const unsigned upO = __shfl_up_sync(0xffffffffu, h3O, 1), dnO = __shfl_down_sync(0xffffffffu, h3O, 1);
+                // m = max(eight neighbours, T - 1); keep <=> s > m <=> s + ~m >= 0 per half word (s + ~m = s - m - 1)
+                const unsigned mE = __vmaxs2(__vimax3_s16x2(upE, dnE, h2E), Tm1), mO = __vmaxs2(__vimax3_s16x2(upO, dnO, h2O), Tm1);
+                unsigned tE, tO;
+                asm("add.s16x2 %0, %1, %2;" : "=r"(tE) : "r"(E[j]), "r"(~mE));
+                asm("add.s16x2 %0, %1, %2;" : "=r"(tO) : "r"(O[j]), "r"(~mO));
+                // sign bytes in pixel order (E.lo, O.lo, E.hi, O.hi); a clear sign = keep
+                km[j] = emit ? (~__byte_perm(tE, tO, 0x7351) & 0x80808080u) : 0u;
+                cnt = __dp4a(km[j] >> 7, 0x01010101u, cnt);
+            }
+            int sc = (int)cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+            int pos = total + sc - (int)cnt;
+            total += __shfl_sync(0xffffffffu, sc, 31);
+            if (cnt) {
+#pragma unroll
+                for (int j = 0; j < NW; j++) {
+                    unsigned m = km[j];
+                    while (m) {
+                        const int b = (__ffs(m) - 1) >> 3;
+                        m &= m - 1;
+                        const int x = xa + 4 * j + b, y = yi + r;    // level coordinates
+                        // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
+                        if (pos < cap) out[pos] = (uint32_t)(x - 16) | ((uint32_t)(y - 16) << 12) | ((uint32_t)rowp[4 * j + b] << 24);
+                        pos++;
+                    }
+                }
+            }
+        }
+        if (total > 0 || pass == 1 || min_th >= ini_th) break;
+        T = min_th;
+    }
+    return total;
+}
+
 __global__ void __launch_bounds__(kNmsWarps * 32)
-k_fast_nms(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells, const uint8_t* __restrict__ score0, int warp_smem_words,
+k_fast_nms(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells, const uint8_t* __restrict__ score0,
            uint32_t* __restrict__ slots, int* __restrict__ cellcnt) {
-    extern __shared__ __align__(16) uint32_t nms_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cell = blockIdx.x * kNmsWarps + warp, f = blockIdx.y;
     if (cell >= g.total_cells) return;
     const CellDesc cd = cells[cell];
     const LevelGeom& lg = g.L[cd.level];
-    uint32_t* tw = nms_raw + warp * warp_smem_words;
     const int iw = cd.rw - 6, ih = cd.rh - 6;
     const int xi = cd.x0 + 3, yi = cd.y0 + 3;                        // first interior pixel (level coordinates)
-    const int xa = (xi - 1) & ~3;                                    // the tile's first column: a word boundary left of the ring column
-    const int wpr = (xi + iw + 1 - xa + 3) >> 2;                     // words per tile row (interior + both ring columns)
-    const unsigned rcp = (65536u + wpr - 1) / wpr;                   // i / wpr == (i * rcp) >> 16 for i * wpr < 65536
-    const int rows = ih + 2, nw = rows * wpr;
-    const uint8_t* src = score0 + (long long)f * g.score_frame_stride + lg.soff + (long long)(yi - 1) * lg.spitch + xa;
-    // stage: interior bytes from the score map, zero everywhere else (ring rows, ring columns, alignment slack)
-    for (int i = lane; i < nw; i += 32) {
-        const int r = (int)(((unsigned)i * rcp) >> 16), wc = i - r * wpr;
-        unsigned v = 0;
-        if (r >= 1 && r <= ih) {
-            v = *reinterpret_cast<const uint32_t*>(src + (long long)r * lg.spitch + 4 * wc);
-            const int lo = xi - (xa + 4 * wc), hi = (xa + 4 * wc + 4) - (xi + iw);        // bytes to clear at the low / high end
-            if (lo > 0) v = lo >= 4 ? 0u : v & (0xffffffffu << (8 * lo));
-            if (hi > 0) v = hi >= 4 ? 0u : v & (0xffffffffu >> (8 * hi));
-        }
-        tw[i] = v;
-    }
-    __syncwarp();
-    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tw);
-    const int P = 4 * wpr;                                           // tile pitch in bytes
-    const int nwi = ih * wpr;                                        // words of the interior rows, raster order
-    const int nchunk = (nwi + 511) >> 9, K = (nwi + 32 * nchunk - 1) / (32 * nchunk);       // <= 16 words per lane and chunk
+    const uint8_t* src = score0 + (long long)f * g.score_frame_stride + lg.soff;
     uint32_t* out = slots + (long long)f * g.slots_per_frame + cd.slot;
-    int T = g.ini_th, total = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        total = 0;
-        const unsigned Tb = (unsigned)(0x80 - T) * 0x01010101u;
-        for (int c = 0; c < nchunk; c++) {
-            const int w_beg = (c * 32 + lane) * K;
-            unsigned long long keep = 0ull;
-            for (int j = 0; j < K; j++) {
-                const int wi = w_beg + j;
-                if (wi >= nwi) break;
-                const unsigned w = tw[wpr + wi];
-                // bytes >= T (T <= 127: carry out of the low 7 bits, or the top bit itself); T > 127 cannot carry, test the top bit path only
-                unsigned m = T <= 128 ? ((((w & 0x7f7f7f7fu) + Tb) | w) & 0x80808080u) : 0u;
-                if (T > 128) {
-#pragma unroll
-                    for (int b = 0; b < 4; b++) if ((int)((w >> (8 * b)) & 255u) >= T) m |= 0x80u << (8 * b);
-                }
-                while (m) {
-                    const int b = (__ffs(m) - 1) >> 3;
-                    m &= m - 1;
-                    const uint8_t* sp = tb + 4 * (wpr + wi) + b;
-                    const int s = sp[0];
-                    if (s > sp[-1] && s > sp[1] && s > sp[-P - 1] && s > sp[-P] && s > sp[-P + 1] && s > sp[P - 1] && s > sp[P] && s > sp[P + 1])
-                        keep |= 1ull << (4 * j + b);
-                }
-            }
-            const int cnt = __popcll(keep);
-            int sc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
-            int pos = total + sc - cnt;
-            total += __shfl_sync(0xffffffffu, sc, 31);
-            while (keep) {
-                const int bit = __ffsll((long long)keep) - 1;
-                keep &= keep - 1;
-                const int wi = w_beg + (bit >> 2), b = bit & 3;
-                const int r = (int)(((unsigned)wi * rcp) >> 16), wc = wi - r * wpr;
-                const int x = xa + 4 * wc + b, y = yi + r;          // level coordinates
-                // key = x | y << 12 | score << 24, coordinates relative to the 16-px border like the reference's vToDistributeKeys
-                if (pos < cd.cap) out[pos] = (uint32_t)(x - 16) | ((uint32_t)(y - 16) << 12) | ((uint32_t)tb[4 * (wpr + wi) + b] << 24);
-                pos++;
-            }
-        }
-        if (total > 0 || pass == 1 || g.min_th >= g.ini_th) break;
-        T = g.min_th;                                                // nothing at iniThFAST: the whole cell again at minThFAST (ORBextractor.cc:809-816)
-    }
+    const int nww = ((xi + iw + 3) >> 2) - (xi >> 2);                // aligned words that hold interior pixels
+    int total;
+    if (nww <= 9) total = nms_cell<9>(src, lg.spitch, xi, yi, iw, ih, g.ini_th, g.min_th, lane, out, cd.cap);
+    else if (nww <= 10) total = nms_cell<10>(src, lg.spitch, xi, yi, iw, ih, g.ini_th, g.min_th, lane, out, cd.cap);
+    else total = nms_cell<18>(src, lg.spitch, xi, yi, iw, ih, g.ini_th, g.min_th, lane, out, cd.cap);
     if (lane == 0) cellcnt[(long long)f * g.total_cells + cell] = total;
 }
 
@@ -1579,20 +1813,36 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
         }
         tma0_used = tma0;
         const int tp = g.L[0].box_w;
-        // Two forms of K2, both bit-exact.  Default: the per-cell kernel (pretest + queues + paired scoring).  B200_FAST_DENSE=1: the dense score map +
-        // per-cell NMS (k_fast_score + k_fast_nms).  Measured on a B200, 256 frames of 640 x 480 (profiles/r2_fast_variants.md): 1.01 ms against
-        // 0.76 + 0.43 ms - the dense form issues 40 % fewer instructions, but 78 % of them (VIMNMX3 / PRMT / LOP3) go to the ALU pipe, which accepts one
-        // warp instruction every other cycle per sub-partition, while the per-cell form spreads its work over the ALU, FMA and LSU pipes.
+        // Three forms of K2, all bit-exact (the same tests run against each).  Default: k_fast, one CTA per cell (pretest + queues + paired scoring).
+        // B200_FAST_DENSE=1: dense score map + per-cell NMS (k_fast_score + k_fast_nms).  B200_FAST_WARP=1: k_fastw, one warp per cell.
+        // Measured on a B200, 256 frames of 640 x 480 (profiles/r2_fast_variants.md): 1.14 ms / 1006 M warp instructions for k_fast,
+        // 0.76 + 0.37 ms / 503 M + 220 M for the dense pair (78 % of the score kernel's instructions are VIMNMX3 / PRMT on the ALU pipe, which issues
+        // at 0.6 of the FFMA rate, tools/pipe_probe2.cu), and 802 M instructions but a longer run time for k_fastw (one warp per cell leaves too
+        // little parallelism to hide its shared-memory round trips).  On the synthetic frames 32 % of all pixels pass the compass pretest at
+        // iniThFAST and 8 % are corners, so none of the forms can skip much work.
         static const bool fast_dense = getenv("B200_FAST_DENSE") != nullptr;
+        static const bool fast_warp = getenv("B200_FAST_WARP") != nullptr;
         if (fast_dense) {
             uint8_t* d_score = h->d_score + (size_t)base * g.score_frame_stride;
             dim3 gs((unsigned)h->tiles.size(), n);
             B200_LAUNCH(k_fast_score, gs, kScThreads, 0, st, imgs, rs, fs, d_pyr, g, h->smaps, tma0, base, h->d_tiles, d_score);
-            const size_t nsm = (size_t)h->nms_warp_words * 4 * kNmsWarps;
-            static std::atomic<size_t> nms_smem_set(0);
-            if (nsm > 48 * 1024 && nsm > nms_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_fast_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsm)); nms_smem_set.store(nsm); }
             dim3 gn((g.total_cells + kNmsWarps - 1) / kNmsWarps, n);
-            B200_LAUNCH(k_fast_nms, gn, kNmsWarps * 32, nsm, st, g, h->d_cells, d_score, h->nms_warp_words, d_slots, d_cellcnt);
+            B200_LAUNCH(k_fast_nms, gn, kNmsWarps * 32, 0, st, g, h->d_cells, d_score, d_slots, d_cellcnt);
+        } else if (fast_warp) {
+            const int keepw = h->fsg.keepw, tb = h->fsg.tile_bytes;
+            const int warp_bytes = (int)align_up(2 * tb + (kFwQ + kFwC) * 2 + keepw * 4, 128);
+            const size_t smem = (size_t)warp_bytes * kFwWarps;
+            static std::atomic<size_t> fw_smem_set(0);
+            if (smem > 48 * 1024 && smem > fw_smem_set.load()) {
+                B200_CUDA(cudaFuncSetAttribute(k_fastw<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200_CUDA(cudaFuncSetAttribute(k_fastw<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200_CUDA(cudaFuncSetAttribute(k_fastw<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                fw_smem_set.store(smem);
+            }
+            dim3 gw((g.total_cells + kFwWarps - 1) / kFwWarps, n);
+            if (tp == 64) B200_LAUNCH(k_fastw<64>, gw, kFwWarps * 32, smem, st, imgs, rs, fs, d_pyr, g, h->maps, tb, keepw, warp_bytes, tma0, base, h->d_cells, d_slots, d_cellcnt);
+            else if (tp == 80) B200_LAUNCH(k_fastw<80>, gw, kFwWarps * 32, smem, st, imgs, rs, fs, d_pyr, g, h->maps, tb, keepw, warp_bytes, tma0, base, h->d_cells, d_slots, d_cellcnt);
+            else B200_LAUNCH(k_fastw<96>, gw, kFwWarps * 32, smem, st, imgs, rs, fs, d_pyr, g, h->maps, tb, keepw, warp_bytes, tma0, base, h->d_cells, d_slots, d_cellcnt);
         } else if (tp == 64) B200_LAUNCH(k_fast<64>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
         else if (tp == 80) B200_LAUNCH(k_fast<80>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
         else B200_LAUNCH(k_fast<96>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
