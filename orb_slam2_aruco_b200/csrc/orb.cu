@@ -71,6 +71,7 @@ struct ResizeEntry { int ofs; short c0, c1; };
 
 __device__ signed char g_pattern[256 * 4];       // rBRIEF pairs, transposed on upload: [k(8)][coord(4)][byte i(32)] (lane-indexed => global, not constant)
 __constant__ int c_umax[16];
+__device__ uint32_t g_disc[31 * 8];               // byte masks of the radius-15 disc: row v + 15, word j <-> u = -15 + 4j .. -12 + 4j (IC_Angle)
 
 // ------------------------------------------------------------------------------------------------
 // K1: pyramid level from the previous level.  cv::resize INTER_LINEAR u8 fixed point (SURVEY A-1).
@@ -1261,7 +1262,7 @@ constexpr int kPatchR = 21;                  // 18 (max rotated pattern reach) +
 constexpr int kPatchW = 2 * kPatchR + 1;     // 43
 constexpr int kBlurW = 37;
 constexpr int kPatchPitch = 64;              // = TMA box width: patch column 0 sits at byte ox = x0 & 15
-constexpr int kHTPitch = 44;                 // u16 pitch of the transposed horizontally filtered patch: HT[c][r]
+constexpr int kHTPitch = 46;                 // u16 pitch of the transposed horizontally filtered patch: HT[c][r]; 23 words: odd, so a column per lane is conflict-free
 constexpr int kHTCols = 40;
 
 struct DescMaps { CUtensorMap m[kMaxLevels]; };
@@ -1330,19 +1331,9 @@ k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long
            b200_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ counts, int out_cap) {
     __shared__ __align__(128) uint8_t s_patch[kDescWarps][(kPatchW * kPatchPitch + 127) / 128 * 128];       // TMA destinations: 128-byte aligned
     __shared__ __align__(16) uint16_t s_ht[kDescWarps][kHTCols * kHTPitch];
-    __shared__ uint32_t s_disc[31 * 8];                       // byte masks of the radius-15 disc: row v + 15, word j <-> u = -15 + 4j .. -12 + 4j
     __shared__ __align__(8) unsigned long long s_bar[kDescWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 31 * 8; i += kDescWarps * 32) {
-        const int um = c_umax[abs((i >> 3) - 15)];
-        uint32_t m = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int u = -15 + 4 * (i & 7) + k; if (abs(u) <= um) m |= 0xffu << (8 * k); }
-        s_disc[i] = m;
-    }
-    __syncthreads();
-
     const int f = blockIdx.y;
     const int k = blockIdx.x * kDescWarps + warp;            // keypoint index inside the frame (levels concatenated)
     const int* lc = lvlcnt + (long long)f * g.nlevels;
@@ -1396,7 +1387,7 @@ k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long
         for (int t = lane; t < 31 * 8; t += 32) {
             const int v = (t >> 3) - kHalfPatch, j = t & 7;
             const uint32_t* w = P32 + (v + kPatchR) * (kPatchPitch / 4) + wb + j;
-            const uint32_t px = __funnelshift_r(w[0], w[1], sh) & s_disc[t];
+            const uint32_t px = __funnelshift_r(w[0], w[1], sh) & __ldg(&g_disc[t]);
             const int u0 = -kHalfPatch + 4 * j;
             const int ucoef = (u0 & 0xff) | (((u0 + 1) & 0xff) << 8) | (((u0 + 2) & 0xff) << 16) | (((u0 + 3) & 0xff) << 24);
             m10 = dp4a_us(px, ucoef, m10);
@@ -1407,37 +1398,64 @@ k_describe(const uint8_t* __restrict__ img0, long long img_row_stride, long long
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // Gaussian, horizontal pass over 43 rows x 40 columns (37 used): task = (row, group of 4 outputs); HT[c][r] = sum_k K[k] P[r][c + k]
+    // Gaussian, horizontal pass over 43 rows x 40 columns (37 used): lane = (row pair, group of 4 outputs), fixed for the whole pass; the two rows'
+    // sums of a column go out as ONE word of the transposed tile, HT[c][2 rp .. 2 rp + 1] (row 43 does not exist: it repeats row 42 and is never used)
     uint16_t* HT = s_ht[warp];
     {
         const unsigned K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
-        const int wb = ox >> 2;
-        for (int idx = lane; idx < kPatchW * 10; idx += 32) {
-            const int r = idx / 10, gq = idx - r * 10;
-            const uint32_t* w = P32 + r * (kPatchPitch / 4) + wb + gq;
-            const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];                  // (the last word may lie past the patch: unused bytes)
-            const uint32_t w0 = __funnelshift_r(a0, a1, sh8), w1 = __funnelshift_r(a1, a2, sh8), w2 = __funnelshift_r(a2, a3, sh8);
+        const int gq = lane % 10, rsub = lane / 10;
+        uint32_t* HT32 = reinterpret_cast<uint32_t*>(HT) + 4 * gq * (kHTPitch / 2);
+        const uint32_t* wbase = P32 + (ox >> 2) + gq;
+        if (rsub < 3) {
+#pragma unroll 2
+            for (int rp = rsub; rp < 22; rp += 3) {
+                const uint32_t* wa = wbase + (2 * rp) * (kPatchPitch / 4);
+                const uint32_t* wb2 = wbase + min(2 * rp + 1, kPatchW - 1) * (kPatchPitch / 4);
+                const uint32_t a0 = wa[0], a1 = wa[1], a2 = wa[2], a3 = wa[3], b0 = wb2[0], b1 = wb2[1], b2 = wb2[2], b3 = wb2[3];
+                const uint32_t u0 = __funnelshift_r(a0, a1, sh8), u1 = __funnelshift_r(a1, a2, sh8), u2 = __funnelshift_r(a2, a3, sh8);
+                const uint32_t v0 = __funnelshift_r(b0, b1, sh8), v1 = __funnelshift_r(b1, b2, sh8), v2 = __funnelshift_r(b2, b3, sh8);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t a4 = __funnelshift_r(w0, w1, 8 * i), b4 = __funnelshift_r(w1, w2, 8 * i);
-                HT[(4 * gq + i) * kHTPitch + r] = (uint16_t)__dp4a(a4, K0, __dp4a(b4, K1, 0u));
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t ha = __dp4a(__funnelshift_r(u0, u1, 8 * i), K0, __dp4a(__funnelshift_r(u1, u2, 8 * i), K1, 0u));
+                    const uint32_t hb = __dp4a(__funnelshift_r(v0, v1, 8 * i), K0, __dp4a(__funnelshift_r(v1, v2, 8 * i), K1, 0u));
+                    HT32[i * (kHTPitch / 2) + rp] = ha + (hb << 16);
+                }
             }
         }
     }
     __syncwarp();
-    // vertical pass: task = (column c, row pair p): Bl[2p][c], Bl[2p + 1][c] from HT[c][2p .. 2p + 7] (four aligned words)
+    // vertical pass: lane = column, walking down the row pairs with a sliding window of four words (rows 2p .. 2p + 7):
+    // Bl[2p][c], Bl[2p + 1][c] from 8 dp2a; the odd pitch of HT keeps the 32 columns on 32 banks
     uint8_t* Bl = P;                     // the source patch is dead once HT exists: reuse its storage
     {
         const unsigned K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8), K6 = 18u, K6h = 18u << 24;
         const uint32_t* HT32 = reinterpret_cast<const uint32_t*>(HT);
-        for (int t = lane; t < kBlurW * 19; t += 32) {
-            const int c = t / 19, p = t - c * 19;
-            const uint32_t* w = HT32 + c * (kHTPitch / 2) + p;
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-            unsigned e = __dp2a_lo(w0, K01, 32768u); e = __dp2a_lo(w1, K23, e); e = __dp2a_lo(w2, K45, e); e = __dp2a_lo(w3, K6, e);
-            unsigned o = __dp2a_lo(sh16(w0, w1), K01, 32768u); o = __dp2a_lo(sh16(w1, w2), K23, o); o = __dp2a_lo(sh16(w2, w3), K45, o); o = __dp2a_hi(w3, K6h, o);
-            Bl[(2 * p) * kBlurW + c] = (uint8_t)(e >> 16);
-            if (2 * p + 1 < kBlurW) Bl[(2 * p + 1) * kBlurW + c] = (uint8_t)(o >> 16);
+        {
+            const uint32_t* w = HT32 + lane * (kHTPitch / 2);
+            uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            uint32_t s01 = sh16(w0, w1), s12 = sh16(w1, w2);
+#pragma unroll
+            for (int pp = 0; pp < 19; pp++) {
+                const uint32_t w3 = w[pp + 3];
+                const uint32_t s23 = sh16(w2, w3);
+                unsigned e = __dp2a_lo(w0, K01, 32768u); e = __dp2a_lo(w1, K23, e); e = __dp2a_lo(w2, K45, e); e = __dp2a_lo(w3, K6, e);
+                unsigned o = __dp2a_lo(s01, K01, 32768u); o = __dp2a_lo(s12, K23, o); o = __dp2a_lo(s23, K45, o); o = __dp2a_hi(w3, K6h, o);
+                Bl[(2 * pp) * kBlurW + lane] = (uint8_t)(e >> 16);
+                if (2 * pp + 1 < kBlurW) Bl[(2 * pp + 1) * kBlurW + lane] = (uint8_t)(o >> 16);
+                w0 = w1; w1 = w2; w2 = w3; s01 = s12; s12 = s23;
+            }
+        }
+        // columns 32 .. 36: lane = (column, every sixth row pair)
+        if (lane < 30) {
+            const int c = 32 + lane % 5;
+            for (int pp = lane / 5; pp < 19; pp += 6) {
+                const uint32_t* w = HT32 + c * (kHTPitch / 2) + pp;
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+                unsigned e = __dp2a_lo(w0, K01, 32768u); e = __dp2a_lo(w1, K23, e); e = __dp2a_lo(w2, K45, e); e = __dp2a_lo(w3, K6, e);
+                unsigned o = __dp2a_lo(sh16(w0, w1), K01, 32768u); o = __dp2a_lo(sh16(w1, w2), K23, o); o = __dp2a_lo(sh16(w2, w3), K45, o); o = __dp2a_hi(w3, K6h, o);
+                Bl[(2 * pp) * kBlurW + c] = (uint8_t)(e >> 16);
+                if (2 * pp + 1 < kBlurW) Bl[(2 * pp + 1) * kBlurW + c] = (uint8_t)(o >> 16);
+            }
         }
     }
     __syncwarp();
@@ -1761,6 +1779,14 @@ int upload_constants() {
         umax[v] = v0; ++v0;
     }
     B200_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+    uint32_t disc[31 * 8];
+    for (int i = 0; i < 31 * 8; i++) {
+        const int um = umax[abs((i >> 3) - 15)];
+        uint32_t m = 0;
+        for (int k = 0; k < 4; k++) { const int u = -15 + 4 * (i & 7) + k; if (abs(u) <= um) m |= 0xffu << (8 * k); }
+        disc[i] = m;
+    }
+    B200_CUDA(cudaMemcpyToSymbol(g_disc, disc, sizeof(disc)));
     return B200_OK;
 }
 
