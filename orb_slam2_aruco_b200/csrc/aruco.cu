@@ -60,7 +60,8 @@ struct ArucoGeom {
     int ncodes;
 };
 
-struct ContourDesc { int start; int s0; int len; int key; int off; };   // start: index into the padded binary image
+struct ContourDesc { int start; int s0; int len; int key; int off; };
+struct SegNode { int next, len, key, off; };       // a surviving transition as a node of its border's ring: successor, steps to it, raster key, first point slot (-1: not emitted)   // start: index into the padded binary image
 struct Candidate { int cx[4], cy[4]; int key; int contour; };
 struct Kept { float c[8]; int contour; };
 struct Decoded { int id, nrot; };
@@ -407,7 +408,7 @@ k_probe_a(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
 // left edge after one step).  Survivors are appended to the second list with one atomic per warp.
 __global__ void __launch_bounds__(256)
 k_probe_b1(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ cand, const int* __restrict__ ncand,
-           int max_cand, int* __restrict__ surv, int* __restrict__ nsurv, int* __restrict__ err) {
+           int max_cand, int* __restrict__ surv, int* __restrict__ nsurv, int* __restrict__ err, int* __restrict__ smap0 = nullptr, uint32_t* __restrict__ sbits0 = nullptr, int sbits_words = 0) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int ns = min(ncand[f], max_cand);
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
@@ -453,7 +454,15 @@ k_probe_b1(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom 
             int base = 0;
             if (lane == 0) base = atomicAdd(nsurv + f, __popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) out[base + __popc(m & ((1u << lane) - 1))] = e;
+            if (keep) {
+                const int idx = base + __popc(m & ((1u << lane) - 1));
+                out[idx] = e;
+                if (smap0) {                                   // ring form: the survivor is found by the raster key of its step
+                    const int key = (e & 0x3fffffff) + ((e >> 30) & 1);
+                    smap0[(long long)f * g.bframe + key] = idx + 1;
+                    atomicOr(sbits0 + (long long)f * sbits_words + (key >> 5), 1u << (key & 31));
+                }
+            }
         }
     }
 }
@@ -538,6 +547,202 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
             p += dy * g.bpitch + dx; x += dx; y += dy;
             s = (st.d + 4) & 7;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ring form of phases B2 + emit (B200_CONTOURS_RING=1; bit-exact, slower: see the numbers at the end of this comment).  k_probe_b lets one lane follow a border from its start all the way round, and k_emit follows it a
+// second time: two chains of dependent loads as long as the longest border (~1000 steps of ~300 cycles on the 640 x 480 frames).  Here nobody
+// walks further than to the next survivor of phase B1:
+//   k_seg    thread per survivor: forwards until the step of another survivor (found through smap, indexed by the raster key of the step) -> the
+//            border becomes a ring of nodes {successor, steps to it, key}.  Every border step is walked exactly once
+//   k_ring   thread per node: hop round the ring summing lengths; meeting a smaller key means "not the raster-first transition" (most nodes stop
+//            after one or two hops).  The node that comes back to itself is Suzuki's start: it books the contour and its point range exactly like
+//            k_probe_b and goes round once more to hand every node its first point slot
+//   k_emit2  thread per node: walks its own segment once more and writes the points; clears its smap entry for the next call.
+// Measured on a B200, 256 frames of 640 x 480: k_probe_b1 0.32 + k_seg 0.79 + k_link 0.06 + k_ring 0.45 + k_emit2 0.66 ms against 0.20 + 0.88 + 0.36 ms for
+// the end-to-end walkers.  Phase B1 keeps the transitions of the DESCENDING side of a border only, so the longest segment is still half of the longest
+// border (the chain of dependent loads shrinks by 2, not by 100), and with segments that uneven a static split over lanes leaves 3/4 of the lane-steps idle.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void probe_start(const uint8_t* __restrict__ mask, int e, int& P, int& s0, int& mykey) {
+    const bool hole = (e >> 30) & 1;
+    P = e & 0x3fffffff;
+    const int m0 = mask[P];
+    const int from = hole ? 7 : 3;
+    const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
+    s0 = (from + 1 + (31 - __clz(rot))) & 7;                            // rot != 0: phase B1 kept it
+    mykey = P + (hole ? 1 : 0);
+}
+
+// raster key of a survivor list entry
+__device__ __forceinline__ int entry_key(int e) { return (e & 0x3fffffff) + ((e >> 30) & 1); }
+
+// All the kernels that walk are flattened state machines: a lane owns the survivors tid, tid + T, ... of its frame, performs ONE dependent step per loop
+// iteration and moves on to its next survivor in the iteration in which it finishes one.  A warp iteration costs the latencies of all the divergent paths
+// some lane takes, so the loops are written so that the only load anybody WAITS for is the step's own (mask byte / node): the next item's list entry and
+// start mask are fetched one item ahead, and the survivor test of a transition is a bit in a 41 KB per-frame bitmap loaded together with the mask byte;
+// the index of the survivor that ends a segment is looked up afterwards by k_link, one independent load per node.
+// (Measured on the way, 256 frames, k_seg + k_ring (+ k_emit2): thread-per-item loops 0.79 + 1.36 ms - a warp runs as long as its longest item;
+// k_probe_b's batch refill through an atomic counter 0.63 + 0.65 + 0.40 ms - items are 3-4 steps long and a refill costs a round trip; flattened
+// but with the int map lookup, list entry and start mask loaded in line 0.97 + 0.63 + 0.68 ms - four dependent loads per warp iteration.)
+// node = next (or, between k_seg and k_link, the raster key that ended the segment) : 22 | steps to it : 20 | own raster key : 22
+__device__ __forceinline__ unsigned long long node_pack(int next, int len, int key) { return ((unsigned long long)(unsigned)next << 42) | ((unsigned long long)(unsigned)len << 22) | (unsigned)key; }
+__device__ __forceinline__ int node_next(unsigned long long v) { return (int)(v >> 42); }
+__device__ __forceinline__ int node_len(unsigned long long v) { return (int)(v >> 22) & 0xfffff; }
+__device__ __forceinline__ int node_key(unsigned long long v) { return (int)v & 0x3fffff; }
+constexpr int kNodeBits = 22, kNodeMaxLen = (1 << 20) - 1;
+
+__device__ __forceinline__ int start_dir(int m0, int e) {            // Suzuki's first neighbour search of the probe e on its own mask byte
+    const int from = ((e >> 30) & 1) ? 7 : 3;
+    const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
+    return (from + 1 + (31 - __clz(rot))) & 7;
+}
+
+__global__ void __launch_bounds__(128)
+k_seg(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ surv, const int* __restrict__ nsurv,
+      int max_cand, const uint32_t* __restrict__ sbits0, int sbits_words, unsigned long long* __restrict__ nodes0, int* __restrict__ off0, int* __restrict__ err) {
+    const int f = blockIdx.x, T = gridDim.y * blockDim.x;
+    const int ns = min(nsurv[f], max_cand);
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    const uint32_t* sbits = sbits0 + (long long)f * sbits_words;
+    const int* list = surv + (long long)f * max_cand;
+    unsigned long long* nodes = nodes0 + (long long)f * max_cand;
+    int* off = off0 + (long long)f * max_cand;
+    int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    int e = list[i], e_pf = i + T < ns ? list[i + T] : 0;
+    int m = mask[e & 0x3fffffff], m_pf = mask[e_pf & 0x3fffffff];
+    int p = e & 0x3fffffff, s = start_dir(m, e), n = 0;
+    for (;;) {
+        const unsigned long long bw = *reinterpret_cast<const unsigned long long*>(sbits + ((p >> 5) & ~1));      // bits of p and p + 1 (p + 1 may cross into the odd word)
+        const unsigned bw2 = (p & 63) == 63 ? sbits[(p >> 5) + 1] : 0u;
+        if (n > 0) m = mask[p];
+        const Step st = next_step(m, s);
+        const int key = step_key(p, s, st.k);
+        bool hit = false;
+        if (n > 0 && key != 0x7fffffff) hit = key == p ? (bw >> (p & 63)) & 1ull : ((p & 63) == 63 ? bw2 & 1u : (bw >> ((p & 63) + 1)) & 1ull);
+        if (!hit) {
+            p += dir_delta(st.d, g.bpitch);
+            s = (st.d + 4) & 7;
+            if (++n >= kNodeMaxLen) { atomicExch(err, 3); hit = true; }
+        }
+        if (hit) {
+            nodes[i] = node_pack(key == 0x7fffffff ? entry_key(e) : key, n, entry_key(e));
+            off[i] = -1;
+            i += T;
+            if (i >= ns) break;
+            e = e_pf; m = m_pf;
+            p = e & 0x3fffffff; s = start_dir(m, e); n = 0;
+            e_pf = i + T < ns ? list[i + T] : 0;
+            m_pf = mask[e_pf & 0x3fffffff];
+        }
+    }
+}
+
+// segment-ending raster key -> survivor index
+__global__ void __launch_bounds__(256)
+k_link(const int* __restrict__ nsurv, int max_cand, const int* __restrict__ smap0, long long bframe, unsigned long long* __restrict__ nodes0) {
+    const int f = blockIdx.y;
+    const int ns = min(nsurv[f], max_cand);
+    unsigned long long* nodes = nodes0 + (long long)f * max_cand;
+    const int* smap = smap0 + (long long)f * bframe;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+        const unsigned long long v = nodes[i];
+        nodes[i] = node_pack(smap[node_next(v)] - 1, node_len(v), node_key(v));
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_ring(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ surv, const int* __restrict__ nsurv,
+       int max_cand, const unsigned long long* __restrict__ nodes0, int* __restrict__ off0, ContourDesc* __restrict__ desc,
+       int* __restrict__ ncont, int* __restrict__ npts, int* __restrict__ err) {
+    const int f = blockIdx.x, T = gridDim.y * blockDim.x;
+    const int ns = min(nsurv[f], max_cand);
+    const unsigned long long* nodes = nodes0 + (long long)f * max_cand;
+    int* off = off0 + (long long)f * max_cand;
+    const int limit = 4 * g.max_points;
+    int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    unsigned long long me = nodes[i], me_pf = i + T < ns ? nodes[i + T] : 0ull;
+    int j = node_next(me), total = node_len(me), hops = 0, o = -1;     // o >= 0: second time round, handing out point slots
+    for (;;) {
+        bool done = false;
+        if (j != i || o >= 0) {
+            const unsigned long long nj = nodes[j];
+            if (o >= 0) { off[j] = o; o += node_len(nj); j = node_next(nj); done = j == i; }
+            else if (node_key(nj) < node_key(me)) done = true;        // not the raster-first transition of this border
+            else {
+                total += node_len(nj); j = node_next(nj);
+                if (++hops > ns || total > limit) { atomicExch(err, 3); done = true; }
+            }
+        } else {                                                      // back home: Suzuki's start
+            done = true;
+            if (total > kMinContour) {
+                const int idx = atomicAdd(ncont + f, 1);
+                if (idx >= g.max_contours) atomicExch(err, 4);
+                else {
+                    const int o0 = atomicAdd(npts + f, total);
+                    if (o0 + total > g.max_points) atomicExch(err, 5);
+                    else {
+                        const int e = surv[(long long)f * max_cand + i], P = e & 0x3fffffff;
+                        ContourDesc c; c.start = P; c.s0 = start_dir(mask0[(long long)f * g.bframe + P], e); c.len = total; c.key = node_key(me); c.off = o0;
+                        desc[(long long)f * g.max_contours + idx] = c;
+                        o = o0; done = false;                         // j == i: the first slot is the start's own
+                    }
+                }
+            }
+        }
+        if (done) {
+            i += T;
+            if (i >= ns) break;
+            me = me_pf; j = node_next(me); total = node_len(me); hops = 0; o = -1;
+            me_pf = i + T < ns ? nodes[i + T] : 0ull;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_emit2(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ surv, const int* __restrict__ nsurv,
+        int max_cand, int* __restrict__ smap0, uint32_t* __restrict__ sbits0, int sbits_words, const unsigned long long* __restrict__ nodes0,
+        const int* __restrict__ off0, short2* __restrict__ pts) {
+    const int f = blockIdx.x, T = gridDim.y * blockDim.x;
+    const int ns = min(nsurv[f], max_cand);
+    const uint8_t* mask = mask0 + (long long)f * g.bframe;
+    int* smap = smap0 + (long long)f * g.bframe;
+    uint32_t* sbits = sbits0 + (long long)f * sbits_words;
+    const int* list = surv + (long long)f * max_cand;
+    const unsigned long long* nodes = nodes0 + (long long)f * max_cand;
+    const int* off = off0 + (long long)f * max_cand;
+    int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    // item state one ahead: list entry, first point slot, node, start mask byte
+    int e_pf = list[i], o_pf = off[i], m_pf = mask[e_pf & 0x3fffffff];
+    unsigned long long v_pf = nodes[i];
+    int p = 0, s = 0, x = 0, y = 0, left = 0, m = 0;
+    short2* out = nullptr;
+    bool first = false;
+    for (;;) {
+        if (left == 0) {                                              // take the prefetched item, prefetch the one after
+            if (i >= ns) break;
+            const int e = e_pf, o = o_pf; const unsigned long long v = v_pf; m = m_pf;
+            const int key = node_key(v);
+            smap[key] = 0; sbits[key >> 5] = 0u;                      // leave the maps empty for the next call
+            i += T;
+            if (i < ns) { e_pf = list[i]; o_pf = off[i]; v_pf = nodes[i]; m_pf = mask[e_pf & 0x3fffffff]; }
+            if (o < 0 || node_len(v) == 0) continue;
+            p = e & 0x3fffffff; s = start_dir(m, e); left = node_len(v);
+            x = p % g.bpitch - kMaskPad; y = p / g.bpitch - 1;
+            out = pts + (long long)f * g.max_points + o;
+            first = true;
+        }
+        if (!first) m = mask[p];
+        first = false;
+        *out++ = make_short2((short)x, (short)y);
+        const Step st = next_step(m, s);
+        const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
+        p += dy * g.bpitch + dx; x += dx; y += dy;
+        s = (st.d + 4) & 7;
+        --left;
     }
 }
 
@@ -1550,6 +1755,8 @@ struct b200_aruco_s {
     Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
     int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_nfetch, *d_err;
     int* d_surv2; int* d_nsurv2; size_t cap_surv2;
+    int* d_smap; unsigned long long* d_nodes; uint32_t* d_sbits; int sbits_words; size_t cap_smap, cap_nodes, cap_sbits;      // ring form of the border walks: raster key -> survivor; {successor, steps to it} per survivor
+    int *d_nfetch2, *d_nfetch3;
     uint8_t* d_wpatch; uint16_t* d_whist; int* d_wlevel;    // warped patches, their histograms and Otsu levels: [B][256][...]      // transitions that survive the backward check (phase B1)
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
@@ -1629,6 +1836,14 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     h->max_surv = std::max(1024, w * hh);              // transition list: at most two entries per foreground pixel
     if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int) * (size_t)h->max_surv * B))) return rc;
     if ((rc = ensure_buf(h->d_surv2, h->cap_surv2, sizeof(int) * (size_t)h->max_surv * B))) return rc;
+    if (getenv("B200_CONTOURS_RING")) {                    // buffers of the ring form of the border walks (12 bytes per pixel), only when it is selected
+        if ((rc = ensure_buf(h->d_smap, h->cap_smap, sizeof(int) * (size_t)g.bframe * B))) return rc;
+        B200_CUDA(cudaMemset(h->d_smap, 0, sizeof(int) * (size_t)g.bframe * B));      // k_emit2 leaves it zero again after every call
+        if ((rc = ensure_buf(h->d_nodes, h->cap_nodes, sizeof(unsigned long long) * (size_t)h->max_surv * B))) return rc;
+        h->sbits_words = (int)((g.bframe + 63) / 64 * 2 + 2);        // survivor bitmap: one bit per raster key, read as 64-bit words
+        if ((rc = ensure_buf(h->d_sbits, h->cap_sbits, sizeof(uint32_t) * (size_t)h->sbits_words * B))) return rc;
+        B200_CUDA(cudaMemset(h->d_sbits, 0, sizeof(uint32_t) * (size_t)h->sbits_words * B));
+    }
     if ((rc = ensure_buf(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame * B))) return rc;
     if ((rc = ensure_buf(h->d_desc, h->cap_desc, sizeof(ContourDesc) * (size_t)g.max_contours * B))) return rc;
     if ((rc = ensure_buf(h->d_pts, h->cap_pts, sizeof(short2) * (size_t)g.max_points * B))) return rc;
@@ -1666,10 +1881,10 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     ok = ok && cudaMalloc((void**)&h->d_wlevel, sizeof(int) * kMaxCand * B) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_mcontour, sizeof(int) * kMaxMarkers * (size_t)B) == cudaSuccess;
     if (ok) cudaMemset(h->d_mcontour, 0xff, sizeof(int) * kMaxMarkers * (size_t)B);
-    ok = ok && cudaMalloc((void**)&h->d_ncont, 7 * B * 4 + 4) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_ncont, 9 * B * 4 + 4) == cudaSuccess;
     if (!ok) { b200_aruco_destroy(h); return fail(B200_ECUDA, "%s failed", "allocation"); }
-    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_nsurv2 = h->d_nfetch + B; h->d_err = h->d_nsurv2 + B;
-    cudaMemset(h->d_ncont, 0, 7 * B * 4 + 4);
+    h->d_npts = h->d_ncont + B; h->d_ncand = h->d_npts + B; h->d_nkept = h->d_ncand + B; h->d_nsurv = h->d_nkept + B; h->d_nfetch = h->d_nsurv + B; h->d_nsurv2 = h->d_nfetch + B; h->d_nfetch2 = h->d_nsurv2 + B; h->d_nfetch3 = h->d_nfetch2 + B; h->d_err = h->d_nfetch3 + B;
+    cudaMemset(h->d_ncont, 0, 9 * B * 4 + 4);
     if ((rc = aruco_geometry(h, max_w, max_h))) { b200_aruco_destroy(h); return rc; }
     *out = h;
     return B200_OK;
@@ -1679,7 +1894,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_smap); cudaFree(h->d_nodes); cudaFree(h->d_sbits); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1710,7 +1925,7 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     if ((rc = aruco_geometry(h, w, hh))) return rc;
     const ArucoGeom& g = h->geom;
     // the seven per-frame counter arrays are one [7][max_batch] block: clear this call's columns
-    B200_CUDA(cudaMemset2DAsync(h->d_ncont + base, (size_t)h->max_batch * 4, 0, (size_t)n * 4, 7, st));
+    B200_CUDA(cudaMemset2DAsync(h->d_ncont + base, (size_t)h->max_batch * 4, 0, (size_t)n * 4, 9, st));
     uint8_t* d_mask = h->d_mask + (size_t)base * g.bframe;
     uint8_t* d_pyr = h->d_pyr + (size_t)base * g.pyr_frame;
     int* d_surv = h->d_surv + (size_t)base * h->max_surv;
@@ -1765,19 +1980,31 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     if (!ct_shared) B200_LAUNCH(k_probe_a, gm, blk, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, h->d_err);
     if (!ct_shared) {
         dim3 g1(16, n);
-        B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err);
-        // persistent CTAs; frames are the fast grid index.  A border occupies ONE lane for its whole length and every step is a dependent
-        // load, so the kernel is latency bound: measured alone at 256 frames, 1 / 2 / 4 / 6 / 9 CTAs per frame -> 1.47 / 1.01 / 0.80 / 0.75 / 0.77 ms.
-        // Its CTAs hold their SM slots for the whole kernel, so next to the extractor's dense kernels the best step time is at ~3 per frame
-        // (5.09 ms with 11, 4.75 ms with 3, detector stream at high priority)
+        static const bool walk = getenv("B200_CONTOURS_RING") == nullptr;          // default: k_probe_b + k_emit follow every border end to end; B200_CONTOURS_RING=1: the ring form
+        // persistent CTAs; frames are the fast grid index.  Every step is a dependent load, so the kernels are latency bound; their CTAs hold their SM slots
+        // for the whole kernel, so next to the extractor's dense kernels about 3 per frame is best at 256 frames (B200_PROBE_CTAS overrides)
         static const int env_gb = [] { const char* e = getenv("B200_PROBE_CTAS"); return e ? atoi(e) : 0; }();
         dim3 gb(n, env_gb > 0 ? env_gb : std::max(1, std::min(64, (148 * 6) / n)));
-        B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
+        // the ring form packs a node into 64 bits (22-bit indices and keys): larger frames than 4 M mask bytes take the end-to-end walkers
+        if (walk || !h->d_smap || g.bframe >= (1ll << kNodeBits) || h->max_surv >= (1 << kNodeBits)) {
+            B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err, (int*)nullptr, (uint32_t*)nullptr, 0);
+            B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
+            dim3 ge(4, n);
+            B200_LAUNCH(k_emit, ge, 128, 0, st, d_mask, g, d_desc, d_ncont, d_pts);
+        } else {
+            // d_surv (the transition list) is dead once phase B1 has run: it becomes the nodes' first-point-slot array
+            int* d_smap = h->d_smap + (size_t)base * g.bframe;
+            unsigned long long* d_nodes = h->d_nodes + (size_t)base * h->max_surv;
+            uint32_t* d_sbits = h->d_sbits + (size_t)base * h->sbits_words;
+            B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err, d_smap, d_sbits, h->sbits_words);
+            B200_LAUNCH(k_seg, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_sbits, h->sbits_words, d_nodes, d_surv, h->d_err);
+            B200_LAUNCH(k_link, g1, 256, 0, st, d_nsurv2, h->max_surv, d_smap, g.bframe, d_nodes);
+            B200_LAUNCH(k_ring, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nodes, d_surv, d_desc, d_ncont, d_npts, h->d_err);
+            B200_LAUNCH(k_emit2, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_smap, d_sbits, h->sbits_words, d_nodes, d_surv, d_pts);
+        }
     }
     // contour counts are only known on the device: size the per-contour grids for the capacity and let idle threads exit
     {
-        dim3 ge(4, n);
-        if (!ct_shared) B200_LAUNCH(k_emit, ge, 128, 0, st, d_mask, g, d_desc, d_ncont, d_pts);
         dim3 gq(48, n);
         B200_LAUNCH(k_quads, gq, kQuadWarps * 32, 0, st, g, d_desc, d_ncont, d_pts, d_cand, d_ncand, h->d_err);
     }

@@ -187,8 +187,7 @@ k_pyramid_tma(const __grid_constant__ CUtensorMap smap, int zbase, int box_w, in
 //   3. 3x3 NMS (strict >, neighbours outside the cell interior count 0) over the corner queues -> per-row bit masks
 // then a raster-ordered compaction of the surviving pixels into the cell's candidate slots.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 128;
-constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastMinWarps = 2;           // k_fast runs with 2, 3 or 4 warps per cell; the queues are sized for 2
 
 struct FastSmemGeom {                        // dynamic shared memory carve-up, sized by the host for the largest box in use
     int tile_bytes;                          // max over levels of box_w * box_h, rounded up to 128
@@ -235,8 +234,8 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&d)[16]) {
 }
 
 // TP: tile pitch in bytes = TMA box width, a compile-time constant so that every circle offset is an immediate
-template <int TP>
-__global__ void __launch_bounds__(kFastThreads, 10)
+template <int TP, int NT>
+__global__ void __launch_bounds__(NT, 1280 / NT)
 k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img_frame_stride,
        const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ FastMaps maps,
        const FastSmemGeom sg, int tma_level0, int scratch_base,
@@ -244,7 +243,7 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
     extern __shared__ __align__(1024) unsigned char fs_raw[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_any;
-    __shared__ int s_nc[kFastWarps];
+    __shared__ int s_nc[(NT / 32)];
 
     const CellDesc cd = cells[blockIdx.x];
     const int f = blockIdx.y;
@@ -253,7 +252,7 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
     uint8_t* tile = fs_raw;                                                             // [box_h][tp], column = ox + ROI column
     uint8_t* score = fs_raw + sg.tile_bytes;                                            // same geometry
     uint16_t* q_all = reinterpret_cast<uint16_t*>(fs_raw + 2 * sg.tile_bytes);          // per-warp pixel queues: y << 8 | tile column
-    uint32_t* keep = reinterpret_cast<uint32_t*>(q_all + kFastWarps * sg.qcap);
+    uint32_t* keep = reinterpret_cast<uint32_t*>(q_all + (NT / 32) * sg.qcap);
 
     const int rw = cd.rw, rh = cd.rh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -271,12 +270,12 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
     } else {
         // caller frames whose pointer / strides are not 16-byte multiples cannot be described by a tensor map: byte-wise staging
         const uint8_t* base = img0 + (long long)f * img_frame_stride + (long long)cd.y0 * img_row_stride + cd.x0;
-        for (int y = warp; y < rh; y += kFastWarps)
+        for (int y = warp; y < rh; y += (NT / 32))
             for (int x = lane; x < rw; x += 32) tile[y * tp + ox + x] = base[(long long)y * img_row_stride + x];
     }
     {   // meanwhile: clear the score tile
         uint4* sc4 = reinterpret_cast<uint4*>(score);
-        for (int i = tid; i < (rh * tp) >> 4; i += kFastThreads) sc4[i] = make_uint4(0u, 0u, 0u, 0u);      // tp is a multiple of 16
+        for (int i = tid; i < (rh * tp) >> 4; i += NT) sc4[i] = make_uint4(0u, 0u, 0u, 0u);      // tp is a multiple of 16
     }
     const int iw = rw - 6, ih = rh - 6;               // interior
     const int tc0 = ox + 3, tc1 = tc0 + iw;           // interior tile columns [tc0, tc1)
@@ -303,12 +302,12 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
 
     int T = g.ini_th;
     for (int pass = 0; pass < 2; pass++) {
-        for (int i = tid; i < ih * 3; i += kFastThreads) keep[i] = 0u;
+        for (int i = tid; i < ih * 3; i += NT) keep[i] = 0u;
         if (tid == 0) s_any = 0;
         const unsigned Tp = (unsigned)T * 0x10001u, Tn = (unsigned)(0x10000 - T) * 0x10001u;
         // 1. pretest + enqueue (warp-private queue)
         int nq = 0;
-        for (int y0 = warp * rpi; y0 < ih; y0 += kFastWarps * rpi) {
+        for (int y0 = warp * rpi; y0 < ih; y0 += (NT / 32) * rpi) {
             const int y = y0 + my_sub;
             unsigned me = 0, mo = 0;
             if (my_on && y < ih) {
@@ -377,10 +376,10 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
         if (lane == 0) s_nc[warp] = nc;
         __syncthreads();
         // 3. NMS of the corners -> keep bits (bit index = interior column); the warps share all four corner lists
-        for (int w = 0; w < kFastWarps; w++) {
+        for (int w = 0; w < (NT / 32); w++) {
             const int ncw = s_nc[w];
             const uint16_t* qc = q_all + w * sg.qcap;
-            for (int i = tid; i < ncw; i += kFastThreads) {
+            for (int i = tid; i < ncw; i += NT) {
                 const int e = qc[i], y = e >> 8, c = e & 255;
                 const uint8_t* sp = score + (y + 3) * tp + c;
                 const int sc = sp[0];
@@ -1707,7 +1706,7 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
                 const CellDesc& cd = h->cells[L.cell_base + c];
                 mrw = std::max(mrw, (int)cd.rw); mrh = std::max(mrh, (int)cd.rh);
                 const int iw = cd.rw - 6, ih = cd.rh - 6, tc0 = (cd.x0 & 15) + 3, ng = ((tc0 + iw - 1) >> 2) - (tc0 >> 2) + 1, rpi = 32 / std::min(ng, 32);
-                const int rows_w = (ih + kFastWarps * rpi - 1) / (kFastWarps * rpi) * rpi;          // rows one warp pretests
+                const int rows_w = (ih + kFastMinWarps * rpi - 1) / (kFastMinWarps * rpi) * rpi;          // rows one warp pretests
                 sgm.qcap = std::max(sgm.qcap, (rows_w * 4 * ng + 7) & ~7);
                 sgm.keepw = std::max(sgm.keepw, ih * 3);
             }
@@ -1721,7 +1720,7 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
             g.L[l].box_w = tp;
             sgm.tile_bytes = std::max(sgm.tile_bytes, (int)align_up((long long)tp * g.L[l].box_h, 128));
         }
-        h->fast_smem = (size_t)2 * sgm.tile_bytes + (size_t)kFastWarps * sgm.qcap * 2 + (size_t)sgm.keepw * 4;
+        h->fast_smem = (size_t)2 * sgm.tile_bytes + (size_t)sgm.keepw * 4;       // + warps * qcap * 2 at launch
     }
     g.slots_per_frame = slot;
     g.pyr_frame_stride = std::max<long long>(pyr_ofs, 256);
@@ -1869,9 +1868,16 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
             if (tp == 64) B200_LAUNCH(k_fastw<64>, gw, kFwWarps * 32, smem, st, imgs, rs, fs, d_pyr, g, h->maps, tb, keepw, warp_bytes, tma0, base, h->d_cells, d_slots, d_cellcnt);
             else if (tp == 80) B200_LAUNCH(k_fastw<80>, gw, kFwWarps * 32, smem, st, imgs, rs, fs, d_pyr, g, h->maps, tb, keepw, warp_bytes, tma0, base, h->d_cells, d_slots, d_cellcnt);
             else B200_LAUNCH(k_fastw<96>, gw, kFwWarps * 32, smem, st, imgs, rs, fs, d_pyr, g, h->maps, tb, keepw, warp_bytes, tma0, base, h->d_cells, d_slots, d_cellcnt);
-        } else if (tp == 64) B200_LAUNCH(k_fast<64>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
-        else if (tp == 80) B200_LAUNCH(k_fast<80>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
-        else B200_LAUNCH(k_fast<96>, grid, kFastThreads, h->fast_smem, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt);
+        } else {
+            static const int nt = [] { const char* e = getenv("B200_FAST_THREADS"); const int v = e ? atoi(e) : 128; return v == 64 || v == 96 ? v : 128; }();
+            static const int pad = [] { const char* e = getenv("B200_FAST_SMEM_PAD"); return e ? atoi(e) : 0; }();
+            const size_t sm = h->fast_smem + (size_t)(nt / 32) * h->fsg.qcap * 2 + (size_t)pad;
+#define B200_FAST_GO(TPV, NTV) B200_LAUNCH((k_fast<TPV, NTV>), grid, NTV, sm, st, imgs, rs, fs, d_pyr, g, h->maps, h->fsg, tma0, base, h->d_cells, d_slots, d_cellcnt)
+#define B200_FAST_TP(NTV) do { if (tp == 64) B200_FAST_GO(64, NTV); else if (tp == 80) B200_FAST_GO(80, NTV); else B200_FAST_GO(96, NTV); } while (0)
+            if (nt == 64) B200_FAST_TP(64); else if (nt == 96) B200_FAST_TP(96); else B200_FAST_TP(128);
+#undef B200_FAST_TP
+#undef B200_FAST_GO
+        }
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[2], st));
     {
