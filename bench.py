@@ -282,6 +282,14 @@ class Workload:
         self.d_imgs = one if self.nsub == 1 else one.unsqueeze(0).repeat(self.nsub, 1, 1, 1).reshape(self.nsub * B, self.H, self.W).contiguous()
         self.pack = shard.SlotPack(B, self.cap, max(self.mcap, 1), device=dev, detector=self.det is not None, matcher=self.matcher is not None)
         self.v = self.pack.views
+        # sub-batched workloads (C5) alternate between TWO sets of handles, result slots and streams, like b200_frontend_host does with its chunks:
+        # the latency-bound tail of one sub-batch (quadtree at 4000 features, contour walks, greedy resolve) runs under the dense kernels of the next
+        self.sets = [dict(ex=self.ex, det=self.det, pack=self.pack)]
+        if self.nsub > 1 and os.environ.get("B200_BENCH_ONE_SET") is None:
+            ex2 = ORBextractor(wl["nfeatures"], 1.2, 8, 20, 7, self.W, self.H, B, device=local)
+            det2 = MarkerDetector(DICT, self.W, self.H, B, device=local) if wl["markers"] else None
+            pack2 = shard.SlotPack(B, self.cap, max(self.mcap, 1), device=dev, detector=self.det is not None, matcher=self.matcher is not None)
+            self.sets.append(dict(ex=ex2, det=det2, pack=pack2))
         self.ref_np = None
         if wl["match"]:          # reference set for the matcher: <= 1000 descriptors of the reference scene, extracted with the CUDA extractor
             rk, rd = self.ex(reference_scene(wl))
@@ -290,39 +298,51 @@ class Workload:
             self.d_rkps = torch.from_numpy(self.ref_np[1].view(np.uint8).reshape(-1, 28).copy()).to(dev)
             self.n_ref = len(self.ref_np[0])
         prio = [int(v) for v in os.environ.get("B200_BENCH_PRIO", "0,-1").split(",")]      # detector stream at high priority (latency-bound kernels start early)
-        self.s_main = torch.cuda.Stream(device=dev, priority=prio[0])
-        self.s_aux = torch.cuda.Stream(device=dev, priority=prio[1])
+        for st in self.sets:
+            st["s_main"] = torch.cuda.Stream(device=dev, priority=prio[0])
+            st["s_aux"] = torch.cuda.Stream(device=dev, priority=prio[1])
+            st["ev_fork"], st["ev_join"], st["ev_bulk"], st["ev_tail"], st["ev_done"], st["ev_end"] = (torch.cuda.Event() for _ in range(6))
+        self.s_main, self.s_aux = self.sets[0]["s_main"], self.sets[0]["s_aux"]
         self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
-        self.ev_fork, self.ev_join, self.ev_bulk, self.ev_tail, self.ev_done = (torch.cuda.Event() for _ in range(5))
+        self.ev_begin = torch.cuda.Event()
         self.coll_bulk = self.coll_tail = None
         if world > 1 and rank == 0:      # the consumer's receive buffers: [sub-batch][rank][bytes]
             self.coll_bulk = torch.zeros((self.nsub, world, self.pack.bulk_bytes), dtype=torch.uint8, device=dev)
             self.coll_tail = torch.zeros((self.nsub, world, self.pack.total_bytes - self.pack.bulk_bytes), dtype=torch.uint8, device=dev)
 
     def step(self):
-        ctx, v = self.ctx, self.v
+        """one pass over all sub-batches; enqueued on the sets' streams, begins and ends on self.s_main (the stream the timing events are recorded on)"""
+        ctx = self.ctx
+        if len(self.sets) > 1:
+            self.ev_begin.record(self.s_main)
+            self.sets[1]["s_main"].wait_event(self.ev_begin)
         for sub in range(self.nsub):
+            st = self.sets[sub % len(self.sets)]
+            v, ex, det, s_main, s_aux = st["pack"].views, st["ex"], st["det"], st["s_main"], st["s_aux"]
             imgs = self.d_imgs[sub * self.B:(sub + 1) * self.B]
-            if self.det is not None:                      # detector on its own stream, concurrently with extractor + matcher
-                self.ev_fork.record(self.s_main)
-                self.s_aux.wait_event(self.ev_fork)
-                self.det.detect_batch_device(imgs, v["markers"], v["marker_counts"], self.s_aux)
-                self.ev_join.record(self.s_aux)
-            self.ex.extract_batch_device(imgs, v["kps"], v["desc"], v["counts"], self.s_main)
+            if det is not None:                           # detector on its own stream, concurrently with extractor + matcher
+                st["ev_fork"].record(s_main)
+                s_aux.wait_event(st["ev_fork"])
+                det.detect_batch_device(imgs, v["markers"], v["marker_counts"], s_aux)
+                st["ev_join"].record(s_aux)
+            ex.extract_batch_device(imgs, v["kps"], v["desc"], v["counts"], s_main)
             if ctx.world > 1:                             # bulk (keypoints + descriptors + counts) leaves for rank 0 while the matcher runs
-                self.ev_bulk.record(self.s_main)
-                self.s_comm.wait_event(self.ev_bulk)
-                ctx.collator.gather([self.pack.bulk], [self.coll_bulk[sub]] if ctx.rank == 0 else None, 0, self.s_comm)
+                st["ev_bulk"].record(s_main)
+                self.s_comm.wait_event(st["ev_bulk"])
+                ctx.collator.gather([st["pack"].bulk], [self.coll_bulk[sub]] if ctx.rank == 0 else None, 0, self.s_comm)
             if self.matcher is not None:
-                self.matcher.SearchByBoW_device(self.d_rdesc, self.d_rkps, self.n_ref, v["desc"], v["kps"], v["counts"], v["matches"], v["n_matches"], self.s_main)
-            if self.det is not None:
-                self.s_main.wait_event(self.ev_join)
-            if ctx.world > 1:                             # tail (markers + matches) after the join; the step ends when both transfers have landed
-                self.ev_tail.record(self.s_main)
-                self.s_comm.wait_event(self.ev_tail)
-                ctx.collator.gather([self.pack.tail], [self.coll_tail[sub]] if ctx.rank == 0 else None, 0, self.s_comm)
-                self.ev_done.record(self.s_comm)
-                self.s_main.wait_event(self.ev_done)
+                self.matcher.SearchByBoW_device(self.d_rdesc, self.d_rkps, self.n_ref, v["desc"], v["kps"], v["counts"], v["matches"], v["n_matches"], s_main)
+            if det is not None:
+                s_main.wait_event(st["ev_join"])
+            if ctx.world > 1:                             # tail (markers + matches) after the join; the sub-batch ends when both transfers have landed
+                st["ev_tail"].record(s_main)
+                self.s_comm.wait_event(st["ev_tail"])
+                ctx.collator.gather([st["pack"].tail], [self.coll_tail[sub]] if ctx.rank == 0 else None, 0, self.s_comm)
+                st["ev_done"].record(self.s_comm)
+                s_main.wait_event(st["ev_done"])
+        if len(self.sets) > 1:
+            self.sets[1]["ev_end"].record(self.sets[1]["s_main"])
+            self.s_main.wait_event(self.sets[1]["ev_end"])
 
     def totals(self):
         v = self.v
@@ -442,8 +462,9 @@ def check_collated(ctx, wk):
     bench line is printed for a collation that delivers wrong data."""
     import torch
     dist = ctx.dist
-    sub = wk.nsub - 1                                            # the pack holds the last sub-batch of the last step
-    mine = torch.stack([wk.pack.bulk.to(torch.int64).sum(), wk.pack.tail.to(torch.int64).sum()])
+    sub = wk.nsub - 1                                            # the pack of its set holds the last sub-batch of the last step
+    last = wk.sets[sub % len(wk.sets)]["pack"]
+    mine = torch.stack([last.bulk.to(torch.int64).sum(), last.tail.to(torch.int64).sum()])
     sums = [torch.zeros_like(mine) for _ in range(ctx.world)]
     dist.all_gather(sums, mine)
     if ctx.rank != 0:
@@ -510,7 +531,7 @@ def workload_line(ctx, wl, steps, warmup, do_e2e=True, headline=False):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": wl["name"], "frames_per_gpu": B * nsub, "l2": "flushed between steps (256 MiB fill, untimed)",
                    "timing": "CUDA events on the launching stream, one pair per step, max over ranks",
-                   "streams": "extractor + matcher on the launching stream, detector on a second, higher-priority stream",
+                   "streams": "extractor + matcher on the launching stream, detector on a second, higher-priority stream" + ("; sub-batches alternate between two sets of handles, result slots and streams" if len(wk.sets) > 1 else ""),
                    "collate": ("gather-to-root of the packed result slots through the library's own NCCL communicator (b200_collate_gather, grouped ncclSend/ncclRecv), two "
                                "transfers per %s inside the step: keypoints + descriptors + counts while the matcher runs, markers + matches after the join"
                                % ("sub-batch" if nsub > 1 else "step")) if ctx.world > 1 else "none (1 GPU)"},

@@ -2023,8 +2023,9 @@ int b200_orb_extract(b200_orb_t h, const uint8_t* imgs, int n, int w, int hh, in
     const int cap = b200_orb_max_keypoints(h);
     if (h->geom.res_per_frame > cap) return fail(B200_ECAPACITY, "aspect ratio beyond %s", "4.5:1");
     // output rows use the caller-visible capacity as pitch; the internal level-result block is indexed by res_per_frame
-    // (running large batches as two halves on two streams, so that one half's quadtree overlaps the other's dense kernels, was measured:
-    // 4.536 -> 4.505 ms per 256-frame step, not worth the extra streams)
+    // (running large batches as two halves on two streams, so that one half's quadtree overlaps the other's dense kernels, was measured twice:
+    // 4.536 -> 4.505 ms per 256-frame C3 step, and no change at 2000 / 4000 features (C4 9.82 -> 9.85 ms, C5 121.5 -> 121.5 ms per step): not kept.
+    // What does pay at C5 is overlapping whole sub-batches on two sets of handles, as b200_frontend_host does with its chunks: +32 %)
     return enqueue(h, imgs, n, w, hh, rs, fs, kps, desc, counts, cap, st);
 }
 
