@@ -52,6 +52,18 @@ def test_load_reads_the_layout_map_save_writes(tmp_path):
     assert np.allclose(m.pose(1)[:3, :3], [[0, 0, 1], [1, 0, 0], [0, 1, 0]], atol=1e-7)
 
 
+def test_a_keyframe_listing_one_map_point_twice_contributes_its_first_feature_only(tmp_path):
+    """MapPoint::AddObservation returns early when the keyframe already observes the point (src/MapPoint.cc:122-124): the second feature of the
+    same keyframe adds no descriptor row to ComputeDistinctiveDescriptors (round-1 advisor finding)"""
+    path, raw, desc = _hand_packed(tmp_path)
+    m = mf.MapFile.load(path)
+    f0 = m.keyframes[0]["features"]
+    f0["mp_idx"][1] = 1                                   # keyframe 0 now lists map point 1 at features 0 AND 1
+    assert m.observations() == [[], [(0, 0), (1, 0)]]
+    f0["mp_idx"][0] = ULONG_MAX                            # ... and with the first one gone, the second becomes the observation
+    assert m.observations() == [[], [(0, 1), (1, 0)]]
+
+
 def test_truncated_and_corrupt_files_are_refused(tmp_path):
     path, raw, _ = _hand_packed(tmp_path)
     for cut in (4, 30, 100, len(raw) - 3):

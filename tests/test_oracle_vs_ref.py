@@ -34,3 +34,27 @@ def test_pyramid_with_border_equals_reference():
         ref = oracle.ref_orb_pyramid_level(img, level)
         mine = oracle.border_reflect101(oracle.orb_pyramid_level(img, level), 19)
         assert np.array_equal(ref, mine)
+
+
+def test_canonical_cos_sin_leaves_no_descriptor_bit_different_from_the_box_s_libm():
+    """Canonical choice 2 of DESIGN.md section 2: oracle/_ref binds cosf / sinf of ORBextractor.cc:113 to (float)cos((double)x).  The same reference
+    source linked against THIS box's libm (oracle/_ref/libref_orb_native_libm.so) must give the same keypoints and the same descriptor bits, or the
+    canonicalisation stops being harmless: asserted here, not only reported by tools/ref_sweeps.py."""
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_orb_native_libm.so")
+    if not os.path.exists(path):
+        pytest.skip("libref_orb_native_libm.so not built")
+    native = C.CDLL(path)
+    bits = kps = 0
+    for idx in range(20, 28):
+        img = np.ascontiguousarray(synth.make_frame(idx, 640, 480, markers=10 if idx & 1 else 0))
+        k, d = oracle.ref_orb_extract(img, 1000)
+        cap = 1000 + 3 * 8 + 64
+        raw = np.zeros((cap, 7), np.float32); d2 = np.zeros((cap, 32), np.uint8)
+        n = native.ref_orb_extract(img.ctypes.data_as(C.c_void_p), 640, 480, 640, 1000, C.c_float(1.2), 8, 20, 7,
+                                   raw.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p), cap)
+        assert n == len(k)
+        assert np.array_equal(raw[:n, 0], k["x"]) and np.array_equal(raw[:n, 1], k["y"]) and np.array_equal(raw[:n, 3], k["angle"])
+        bits += int(np.unpackbits(d ^ d2[:n]).sum()); kps += n
+    assert kps > 7000 and bits == 0
