@@ -551,7 +551,8 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ring form of phases B2 + emit (B200_CONTOURS_RING=1; bit-exact, slower: see the numbers at the end of this comment).  k_probe_b lets one lane follow a border from its start all the way round, and k_emit follows it a
+// Ring form of phases B2 + emit: the default for batches of up to kRingFrames frames, where latency counts (single frame: detector 0.84 -> 0.73 ms;
+// 32 frames 1.56 -> 1.46 ms); bit-exact; slower than the end-to-end walkers on large batches, see the numbers at the end of this comment.  k_probe_b lets one lane follow a border from its start all the way round, and k_emit follows it a
 // second time: two chains of dependent loads as long as the longest border (~1000 steps of ~300 cycles on the 640 x 480 frames).  Here nobody
 // walks further than to the next survivor of phase B1:
 //   k_seg    thread per survivor: forwards until the step of another survivor (found through smap, indexed by the raster key of the step) -> the
@@ -591,6 +592,7 @@ __device__ __forceinline__ int node_next(unsigned long long v) { return (int)(v 
 __device__ __forceinline__ int node_len(unsigned long long v) { return (int)(v >> 22) & 0xfffff; }
 __device__ __forceinline__ int node_key(unsigned long long v) { return (int)v & 0x3fffff; }
 constexpr int kNodeBits = 22, kNodeMaxLen = (1 << 20) - 1;
+constexpr int kRingFrames = 32;      // batches up to this size take the ring form (measured crossover against the end-to-end walkers: ~48 frames of 640 x 480)
 
 __device__ __forceinline__ int start_dir(int m0, int e) {            // Suzuki's first neighbour search of the probe e on its own mask byte
     const int from = ((e >> 30) & 1) ? 7 : 3;
@@ -1755,7 +1757,7 @@ struct b200_aruco_s {
     Candidate* d_cand; Kept* d_kept; Decoded* d_dec;
     int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_nfetch, *d_err;
     int* d_surv2; int* d_nsurv2; size_t cap_surv2;
-    int* d_smap; unsigned long long* d_nodes; uint32_t* d_sbits; int sbits_words; size_t cap_smap, cap_nodes, cap_sbits;      // ring form of the border walks: raster key -> survivor; {successor, steps to it} per survivor
+    int* d_smap; unsigned long long* d_nodes; uint32_t* d_sbits; int sbits_words; size_t cap_smap, cap_nodes, cap_sbits; int ring_slots, ring_mode;      // ring form of the border walks: raster key -> survivor; {successor, steps to it} per survivor
     int *d_nfetch2, *d_nfetch3;
     uint8_t* d_wpatch; uint16_t* d_whist; int* d_wlevel;    // warped patches, their histograms and Otsu levels: [B][256][...]      // transitions that survive the backward check (phase B1)
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
@@ -1836,13 +1838,20 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     h->max_surv = std::max(1024, w * hh);              // transition list: at most two entries per foreground pixel
     if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int) * (size_t)h->max_surv * B))) return rc;
     if ((rc = ensure_buf(h->d_surv2, h->cap_surv2, sizeof(int) * (size_t)h->max_surv * B))) return rc;
-    if (getenv("B200_CONTOURS_RING")) {                    // buffers of the ring form of the border walks (12 bytes per pixel), only when it is selected
-        if ((rc = ensure_buf(h->d_smap, h->cap_smap, sizeof(int) * (size_t)g.bframe * B))) return rc;
-        B200_CUDA(cudaMemset(h->d_smap, 0, sizeof(int) * (size_t)g.bframe * B));      // k_emit2 leaves it zero again after every call
-        if ((rc = ensure_buf(h->d_nodes, h->cap_nodes, sizeof(unsigned long long) * (size_t)h->max_surv * B))) return rc;
-        h->sbits_words = (int)((g.bframe + 63) / 64 * 2 + 2);        // survivor bitmap: one bit per raster key, read as 64-bit words
-        if ((rc = ensure_buf(h->d_sbits, h->cap_sbits, sizeof(uint32_t) * (size_t)h->sbits_words * B))) return rc;
-        B200_CUDA(cudaMemset(h->d_sbits, 0, sizeof(uint32_t) * (size_t)h->sbits_words * B));
+    {   // buffers of the ring form of the border walks (12 bytes per pixel and frame slot): it serves batches of up to kRingFrames frames, so that is
+        // how many slots it gets (B200_CONTOURS_RING=1 forces it for every batch size, =0 disables it)
+        const char* e = getenv("B200_CONTOURS_RING");
+        h->ring_mode = e ? atoi(e) : -1;
+        h->ring_slots = h->ring_mode == 0 ? 0 : h->ring_mode == 1 ? (int)B : (int)std::min<size_t>(B, kRingFrames);
+        if (h->ring_slots > 0 && g.bframe < (1ll << kNodeBits) && h->max_surv < (1 << kNodeBits)) {
+            const size_t R = (size_t)h->ring_slots;
+            if ((rc = ensure_buf(h->d_smap, h->cap_smap, sizeof(int) * (size_t)g.bframe * R))) return rc;
+            B200_CUDA(cudaMemset(h->d_smap, 0, sizeof(int) * (size_t)g.bframe * R));      // k_emit2 leaves it zero again after every call
+            if ((rc = ensure_buf(h->d_nodes, h->cap_nodes, sizeof(unsigned long long) * (size_t)h->max_surv * R))) return rc;
+            h->sbits_words = (int)((g.bframe + 63) / 64 * 2 + 2);        // survivor bitmap: one bit per raster key, read as 64-bit words
+            if ((rc = ensure_buf(h->d_sbits, h->cap_sbits, sizeof(uint32_t) * (size_t)h->sbits_words * R))) return rc;
+            B200_CUDA(cudaMemset(h->d_sbits, 0, sizeof(uint32_t) * (size_t)h->sbits_words * R));
+        } else h->ring_slots = 0;
     }
     if ((rc = ensure_buf(h->d_pyr, h->cap_pyr, (size_t)g.pyr_frame * B))) return rc;
     if ((rc = ensure_buf(h->d_desc, h->cap_desc, sizeof(ContourDesc) * (size_t)g.max_contours * B))) return rc;
@@ -1980,13 +1989,14 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     if (!ct_shared) B200_LAUNCH(k_probe_a, gm, blk, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, h->d_err);
     if (!ct_shared) {
         dim3 g1(16, n);
-        static const bool walk = getenv("B200_CONTOURS_RING") == nullptr;          // default: k_probe_b + k_emit follow every border end to end; B200_CONTOURS_RING=1: the ring form
+        // small batches (latency): the ring form, whose chains of dependent loads are half as long; large batches (throughput): the end-to-end walkers
+        const bool walk = !(h->ring_slots > 0 && base + n <= h->ring_slots && (h->ring_mode == 1 || n <= kRingFrames));
         // persistent CTAs; frames are the fast grid index.  Every step is a dependent load, so the kernels are latency bound; their CTAs hold their SM slots
         // for the whole kernel, so next to the extractor's dense kernels about 3 per frame is best at 256 frames (B200_PROBE_CTAS overrides)
         static const int env_gb = [] { const char* e = getenv("B200_PROBE_CTAS"); return e ? atoi(e) : 0; }();
         dim3 gb(n, env_gb > 0 ? env_gb : std::max(1, std::min(64, (148 * 6) / n)));
         // the ring form packs a node into 64 bits (22-bit indices and keys): larger frames than 4 M mask bytes take the end-to-end walkers
-        if (walk || !h->d_smap || g.bframe >= (1ll << kNodeBits) || h->max_surv >= (1 << kNodeBits)) {
+        if (walk) {
             B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err, (int*)nullptr, (uint32_t*)nullptr, 0);
             B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
             dim3 ge(4, n);
