@@ -274,13 +274,13 @@ __device__ __forceinline__ void at2_strip(const uint8_t* __restrict__ src, int r
 
 template <int R>
 __global__ void __launch_bounds__(kAt2Warps * 32)
-k_athresh2(const uint8_t* __restrict__ img, long long row_stride, long long frame_stride, const __grid_constant__ ArucoGeom g, uint8_t* __restrict__ mask) {
+k_athresh2(const uint8_t* __restrict__ img, long long row_stride, long long frame_stride, const __grid_constant__ ArucoGeom g, uint8_t* __restrict__ mask, int strip_rows) {
     constexpr int H = R <= 3 ? 1 : 2, NOUT = 30 - 2 * H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.z;
-    const int ys = (blockIdx.y * kAt2Warps + warp) * kAt2Rows;
+    const int ys = (blockIdx.y * kAt2Warps + warp) * strip_rows;
     if (ys >= g.h) return;
-    const int ye = min(ys + kAt2Rows, g.h);
+    const int ye = min(ys + strip_rows, g.h);
     const int c0 = (blockIdx.x * NOUT + lane - (H + 1)) * 4;          // image column of the lane's first pixel
     const uint8_t* src = img + (long long)f * frame_stride;
     const bool fast = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)row_stride) & 3) == 0 && c0 >= 0 && c0 + 3 < g.w;
@@ -1953,15 +1953,16 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     if (athresh_smem || rs * (long long)hh >= (1ll << 31)) B200_LAUNCH(k_athresh, gt, blk, 0, st, imgs, rs, fs, g, d_mask);      // (k_athresh2 keeps row offsets in 32 bits)
     else {
         const int R = g.win >> 1, nout = 4 * (30 - 2 * (R <= 3 ? 1 : 2));
-        dim3 g2((w + nout - 1) / nout, ((hh + kAt2Rows - 1) / kAt2Rows + kAt2Warps - 1) / kAt2Warps, n);
+        const int rows = n >= 16 ? kAt2Rows : 16;          // few frames: shorter strips, four times as many warps (the window warm-up is paid more often)
+        dim3 g2((w + nout - 1) / nout, ((hh + rows - 1) / rows + kAt2Warps - 1) / kAt2Warps, n);
         switch (R) {
-            case 1: B200_LAUNCH(k_athresh2<1>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
-            case 2: B200_LAUNCH(k_athresh2<2>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
-            case 3: B200_LAUNCH(k_athresh2<3>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
-            case 4: B200_LAUNCH(k_athresh2<4>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
-            case 5: B200_LAUNCH(k_athresh2<5>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
-            case 6: B200_LAUNCH(k_athresh2<6>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
-            default: B200_LAUNCH(k_athresh2<7>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask); break;
+            case 1: B200_LAUNCH(k_athresh2<1>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
+            case 2: B200_LAUNCH(k_athresh2<2>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
+            case 3: B200_LAUNCH(k_athresh2<3>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
+            case 4: B200_LAUNCH(k_athresh2<4>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
+            case 5: B200_LAUNCH(k_athresh2<5>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
+            case 6: B200_LAUNCH(k_athresh2<6>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
+            default: B200_LAUNCH(k_athresh2<7>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
         }
     }
     for (int l = 1; l < g.nlev; l++) {
