@@ -37,6 +37,7 @@ struct LevelGeom {
     int cell_base, ncells;    // cells of this level inside the frame's cell list
     long long slot_base;      // first candidate slot of this level (entries) inside the frame's slot block
     int nini; float hx;       // DistributeOctTree initial nodes
+    int xsplit;               // two initial nodes (16:9 frames): smallest x with (int)(x / hx) >= 1
     int kp_cap, kp_base;      // result capacity of this level, base inside the frame's level-result block
     int xtab, ytab;           // offsets into the resize tables
     int pbox_w, pbox_h;       // TMA box of k_pyramid_tma over the SOURCE level (l - 1): largest source region one 128 x 64 output tile reads
@@ -1089,7 +1090,79 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
     // ---- initial nodes (ORBextractor.cc:543-570): key -> node (int)(x / hX); stable gather from the cell slots
     const int nini = lg.nini;
     int total = 0;
-    if (nini >= 1) {
+    auto make_node = [&](int ni, int beg, int end) {
+        const int k = end - beg;
+        if (k <= 0) return;                   // empty initial nodes are erased right away (ORBextractor.cc:581-582)
+        const int id = qt_alloc(w);
+        if (lane == 0) {
+            QtNode c;
+            c.x0 = (short)(int)__fmul_rn(lg.hx, (float)ni); c.x1 = (short)(int)__fmul_rn(lg.hx, (float)(ni + 1));
+            c.y0 = 0; c.y1 = (short)(lg.h - 2 * kMinBorder);
+            c.beg = beg; c.end = end; c.prev = c.next = -1; c.seq = w.seq; c.no_more = (k == 1); c.buf = 0; c.pad0 = c.pad1 = 0;
+            w.pool[id] = c;
+        }
+        __syncwarp();
+        qt_push_back(w, id, lane);
+        w.seq++;
+    };
+    if (nini == 2) {
+        // two initial nodes (16:9 frames): (int)(x / hX) is monotone in x, so node 1 starts at the host-computed column xsplit and no key needs a
+        // division.  Pass 1 counts node 0 (node 1 begins behind it), pass 2 places both nodes' keys in cell order; the two per-cell counts travel
+        // through one scan as a packed pair.  (The per-node form below read every key four times and divided each time: 38 % of this kernel's
+        // stall samples at 1920 x 1080.)
+        const unsigned xb = (unsigned)lg.xsplit;
+        int tot0 = 0;
+        for (int c0 = 0; c0 < lg.ncells; c0 += 32) {
+            const int c = c0 + lane;
+            int n = 0, slot = 0;
+            if (c < lg.ncells) { n = min(cc[c], cl[c].cap); slot = cl[c].slot; }
+            const uint32_t* src = S + slot;
+            int mine0 = 0;
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = k0 + u < n ? src[k0 + u] : 0xfffu;
+#pragma unroll
+                for (int u = 0; u < 4; u++) mine0 += (v[u] & 0xfff) < xb;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine0 += __shfl_xor_sync(0xffffffffu, mine0, o);
+            tot0 += mine0;
+        }
+        int run0 = 0, run1 = tot0;
+        for (int c0 = 0; c0 < lg.ncells; c0 += 32) {
+            const int c = c0 + lane;
+            int n = 0, slot = 0;
+            if (c < lg.ncells) { n = min(cc[c], cl[c].cap); slot = cl[c].slot; }
+            const uint32_t* src = S + slot;
+            int mine0 = 0;
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = k0 + u < n ? src[k0 + u] : 0xfffu;
+#pragma unroll
+                for (int u = 0; u < 4; u++) mine0 += (v[u] & 0xfff) < xb;
+            }
+            const unsigned mine = (unsigned)mine0 | ((unsigned)(n - mine0) << 16);      // a cell holds at most 324 keys: 32 cells fit 16 bits
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            uint32_t* d0 = A + run0 + (int)((incl - mine) & 0xffffu);
+            uint32_t* d1 = A + run1 + (int)((incl - mine) >> 16);
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = k0 + u < n ? src[k0 + u] : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (k0 + u < n) { if ((v[u] & 0xfff) < xb) *d0++ = v[u]; else *d1++ = v[u]; }
+            }
+            const unsigned all = __shfl_sync(0xffffffffu, incl, 31);
+            run0 += (int)(all & 0xffffu); run1 += (int)(all >> 16);
+        }
+        make_node(0, 0, tot0);
+        make_node(1, tot0, run1);
+        total = run1;
+    } else if (nini >= 1) {
         int run = 0;
         for (int ni = 0; ni < nini; ni++) {
             const int beg = run;
@@ -1115,7 +1188,7 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
                     run += __shfl_sync(0xffffffffu, incl, 31);
                 }
             } else {
-                // several initial nodes (16:9 frames have two): node ni takes the keys with (int)(x / hX) == ni in cell order.  Same
+                // three or more initial nodes (wider than 5:2): node ni takes the keys with (int)(x / hX) == ni in cell order.  Same
                 // lane-per-cell scheme, run once per node: a counting sweep is not needed because the nodes are filled one after the
                 // other (run continues where the previous node ended)
                 for (int c0 = 0; c0 < lg.ncells; c0 += 32) {
@@ -1145,20 +1218,7 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
                     run += __shfl_sync(0xffffffffu, incl, 31);
                 }
             }
-            const int k = run - beg;
-            if (k > 0) {                      // empty initial nodes are erased right away (ORBextractor.cc:581-582)
-                const int id = qt_alloc(w);
-                if (lane == 0) {
-                    QtNode c;
-                    c.x0 = (short)(int)__fmul_rn(lg.hx, (float)ni); c.x1 = (short)(int)__fmul_rn(lg.hx, (float)(ni + 1));
-                    c.y0 = 0; c.y1 = (short)(lg.h - 2 * kMinBorder);
-                    c.beg = beg; c.end = run; c.prev = c.next = -1; c.seq = w.seq; c.no_more = (k == 1); c.buf = 0; c.pad0 = c.pad1 = 0;
-                    w.pool[id] = c;
-                }
-                __syncwarp();
-                qt_push_back(w, id, lane);
-                w.seq++;
-            }
+            make_node(ni, beg, run);
         }
         total = run;
     }
@@ -1667,7 +1727,12 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
                 }
             }
             const int nini = (int)roundf((float)(maxBX - minB) / (float)(maxBY - minB));
-            if (nini >= 1) { L.nini = nini; L.hx = (float)(maxBX - minB) / nini; }
+            if (nini >= 1) {
+                L.nini = nini; L.hx = (float)(maxBX - minB) / nini;
+                int xs = 0;
+                while (xs < 4096 && (int)((float)xs / L.hx) < 1) xs++;      // float division like the kernel's __fdiv_rn: monotone in x
+                L.xsplit = xs;
+            }
         }
         L.ncells = (int)h->cells.size() - L.cell_base;
         L.kp_cap = L.quota + 3 + 4 * std::max(L.nini, 1);
