@@ -952,7 +952,7 @@ __device__ __forceinline__ int qt_erase(QtWarp& w, int id, int lane) {   // retu
 // Returns the four child counts (warp-uniform) and fills child boxes.
 // `pre` (valid when has_pre): this node's keys, one per lane, fetched while the previous node was being divided (nodes of at most 32 keys)
 __device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint32_t* bufB, int lane,
-                                          int cnt[4], int& mx, int& my, uint32_t pre = 0u, bool has_pre = false) {
+                                          int cnt[4], int& mx, int& my, const uint32_t (&pre)[4], bool has_pre) {
     const int halfX = (nd.x1 - nd.x0 + 1) >> 1;      // ceil((float)(UR.x-UL.x)/2) for non-negative ints
     const int halfY = (nd.y1 - nd.y0 + 1) >> 1;
     mx = nd.x0 + halfX; my = nd.y0 + halfY;
@@ -960,19 +960,35 @@ __device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint3
     uint32_t* dst = nd.buf ? bufA : bufB;
     const int n = nd.end - nd.beg;
     cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
-    if (n <= 32) {                                    // common case: one register-resident pass
-        const bool valid = lane < n;
-        const uint32_t key = has_pre ? pre : (valid ? src[nd.beg + lane] : 0u);
-        const int q = valid ? (((int)(key & 0xfff) >= mx) + 2 * ((int)((key >> 12) & 0xfff) >= my)) : 4;
-        unsigned m[4];
+    if (n <= 128) {                                   // common case: the node's keys sit in four registers per lane, counted and scattered from there
+        uint32_t key[4]; int q[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { m[k] = __ballot_sync(0xffffffffu, q == k); cnt[k] = __popc(m[k]); }
-        if (valid) {
-            int ofs = nd.beg;
+        for (int u = 0; u < 4; u++) {
+            const bool valid = 32 * u + lane < n;
+            key[u] = has_pre ? pre[u] : (valid ? src[nd.beg + 32 * u + lane] : 0u);
+            q[u] = valid ? (((int)(key[u] & 0xfff) >= mx) + 2 * ((int)((key[u] >> 12) & 0xfff) >= my)) : 4;
+        }
+        unsigned m[4][4];                             // [u][k]
 #pragma unroll
-            for (int k = 0; k < 4; k++) { if (k < q) ofs += cnt[k]; }
-            unsigned mm = q == 0 ? m[0] : q == 1 ? m[1] : q == 2 ? m[2] : m[3];
-            dst[ofs + __popc(mm & ((1u << lane) - 1))] = key;
+        for (int u = 0; u < 4; u++) {
+            if (32 * u < n) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { m[u][k] = __ballot_sync(0xffffffffu, q[u] == k); cnt[k] += __popc(m[u][k]); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) m[u][k] = 0u;
+            }
+        }
+        int run[4];
+        run[0] = nd.beg; run[1] = run[0] + cnt[0]; run[2] = run[1] + cnt[1]; run[3] = run[2] + cnt[2];
+        const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (q[u] == k) dst[run[k] + __popc(m[u][k] & lt)] = key[u];
+                run[k] += __popc(m[u][k]);
+            }
         }
     } else {
         // both passes fetch 4 x 32 keys per round trip (the keys live in global scratch: latency, not bandwidth, is the cost)
@@ -1009,13 +1025,16 @@ __device__ __forceinline__ void qt_divide(const QtNode nd, uint32_t* bufA, uint3
 }
 
 // start fetching the keys of node `id` (if it is small enough for the register path): the load is in flight while the current node is divided
-__device__ __forceinline__ bool qt_prefetch(const QtWarp& w, int id, const uint32_t* bufA, const uint32_t* bufB, int lane, uint32_t& key) {
-    key = 0u;
+__device__ __forceinline__ bool qt_prefetch(const QtWarp& w, int id, const uint32_t* bufA, const uint32_t* bufB, int lane, uint32_t (&key)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) key[u] = 0u;
     if (id < 0) return false;
     const QtNode nd = w.pool[id];
     const int n = nd.end - nd.beg;
-    if (n > 32) return false;
-    if (lane < n) key = (nd.buf ? bufB : bufA)[nd.beg + lane];
+    if (n > 128) return false;
+    const uint32_t* src = (nd.buf ? bufB : bufA) + nd.beg;
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (32 * u + lane < n) key[u] = src[32 * u + lane];
     return true;
 }
 
@@ -1046,6 +1065,62 @@ __device__ __forceinline__ int qt_add_children(QtWarp& w, const QtNode nd, const
         beg += k;
     }
     return added;
+}
+
+// qt_add_children + qt_erase of the parent in one step with two warp barriers instead of ten: lanes 0..3 write one child each (node record, links
+// among the new children, entry of the `big` list), lane 4 re-links the old list head; then the parent is unlinked and its slot goes back to the
+// free list.  Same list order as four push_fronts in the order n1..n4: [n4, n3, n2, n1, old head, ...]; same creation sequence numbers.
+__device__ __forceinline__ int qt_split(QtWarp& w, int it, const QtNode nd, const int cnt[4], int mx, int my, int lane, int& nbig) {
+    int re[4], rb[4], ne = 0, nb = 0;                 // rank among the non-empty / the big children
+#pragma unroll
+    for (int q = 0; q < 4; q++) { re[q] = ne; rb[q] = nb; ne += cnt[q] > 0; nb += cnt[q] > 1; }
+    int ids[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) ids[q] = cnt[q] > 0 ? (int)w.freelist[w.nfree - 1 - re[q]] : -1;
+    const int old_head = w.head;
+    int lo = -1, hi = -1;                              // lowest / highest non-empty child
+#pragma unroll
+    for (int q = 3; q >= 0; q--) if (cnt[q] > 0) lo = q;
+#pragma unroll
+    for (int q = 0; q < 4; q++) if (cnt[q] > 0) hi = q;
+    if (lane < 4) {
+        const int q = lane;
+        const int k = q == 0 ? cnt[0] : q == 1 ? cnt[1] : q == 2 ? cnt[2] : cnt[3];
+        if (k > 0) {
+            const int beg = nd.beg + (q > 0 ? cnt[0] : 0) + (q > 1 ? cnt[1] : 0) + (q > 2 ? cnt[2] : 0);
+            const int myrank = q == 0 ? re[0] : q == 1 ? re[1] : q == 2 ? re[2] : re[3];
+            const int id = q == 0 ? ids[0] : q == 1 ? ids[1] : q == 2 ? ids[2] : ids[3];
+            int nxt = old_head, prv = -1;              // next = the non-empty child below me (or the old head), prev = the one above me
+#pragma unroll
+            for (int j = 0; j < 4; j++) { if (j < q && cnt[j] > 0) nxt = ids[j]; }
+#pragma unroll
+            for (int j = 3; j >= 0; j--) { if (j > q && cnt[j] > 0) prv = ids[j]; }
+            QtNode c;
+            c.x0 = (q & 1) ? (short)mx : nd.x0; c.x1 = (q & 1) ? nd.x1 : (short)mx;
+            c.y0 = (q & 2) ? (short)my : nd.y0; c.y1 = (q & 2) ? nd.y1 : (short)my;
+            c.beg = beg; c.end = beg + k; c.prev = (short)prv; c.next = (short)nxt; c.seq = w.seq + myrank;
+            c.no_more = (k == 1); c.buf = nd.buf ^ 1; c.pad0 = c.pad1 = 0;
+            w.pool[id] = c;
+            if (k > 1) {
+                const int bi = nbig + (q == 0 ? rb[0] : q == 1 ? rb[1] : q == 2 ? rb[2] : rb[3]);
+                w.big_cnt[bi] = k; w.big_seq[bi] = c.seq; w.big_id[bi] = (short)id;
+            }
+        }
+    } else if (lane == 4 && ne > 0 && old_head >= 0) w.pool[old_head].prev = (short)ids[lo < 0 ? 0 : lo];
+    if (ne > 0) { w.head = ids[hi < 0 ? 0 : hi]; w.size += ne; w.seq += ne; w.nfree -= ne; nbig += nb; }
+    __syncwarp();
+    // unlink the parent
+    const int p = w.pool[it].prev, n = w.pool[it].next;
+    if (lane == 0) {
+        if (p >= 0) w.pool[p].next = (short)n;
+        if (n >= 0) w.pool[n].prev = (short)p;
+        w.freelist[w.nfree] = (short)it;
+    }
+    if (p < 0) w.head = n;
+    if (n < 0) w.tail = p;
+    w.size--; w.nfree++;
+    __syncwarp();
+    return nb;
 }
 
 __global__ void __launch_bounds__(kQtWarps * 32)
@@ -1230,19 +1305,20 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
         int nbig = 0, n_expand = 0;
         int it = w.head;
         while (it >= 0 && w.pool[it].no_more) it = w.pool[it].next;
-        uint32_t pre; bool has_pre = qt_prefetch(w, it, A, B, lane, pre);
+        uint32_t pre[4]; bool has_pre = qt_prefetch(w, it, A, B, lane, pre);
         while (it >= 0) {
             const QtNode nd = w.pool[it];
             __syncwarp();
             if (w.nfree < 4) { if (lane == 0) atomicExch(errflag, 1); finish = true; break; }
             int nx = nd.next;                                   // the next node that can still be divided: its keys are requested now
             while (nx >= 0 && w.pool[nx].no_more) nx = w.pool[nx].next;
-            uint32_t pre_n; const bool has_n = qt_prefetch(w, nx, A, B, lane, pre_n);
+            uint32_t pre_n[4]; const bool has_n = qt_prefetch(w, nx, A, B, lane, pre_n);
             int cnt[4], mx, my;
             qt_divide(nd, A, B, lane, cnt, mx, my, pre, has_pre);
-            n_expand += qt_add_children(w, nd, cnt, mx, my, lane, nbig);
-            qt_erase(w, it, lane);
-            it = nx; pre = pre_n; has_pre = has_n;
+            n_expand += qt_split(w, it, nd, cnt, mx, my, lane, nbig);
+            it = nx; has_pre = has_n;
+#pragma unroll
+            for (int u = 0; u < 4; u++) pre[u] = pre_n[u];
         }
         if (finish) break;
         if (w.size >= N || w.size == prev_size) finish = true;
@@ -1264,18 +1340,19 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
                 }
                 __syncwarp();
                 nbig = 0;
-                uint32_t pre; bool has_pre = qt_prefetch(w, m > 0 ? w.prv_id[w.order[0]] : -1, A, B, lane, pre);
+                uint32_t pre[4]; bool has_pre = qt_prefetch(w, m > 0 ? w.prv_id[w.order[0]] : -1, A, B, lane, pre);
                 for (int j = 0; j < m; j++) {
                     const int id = w.prv_id[w.order[j]];
                     const QtNode nd = w.pool[id];
                     __syncwarp();
                     if (w.nfree < 4) { if (lane == 0) atomicExch(errflag, 1); finish = true; break; }
-                    uint32_t pre_n; const bool has_n = qt_prefetch(w, j + 1 < m ? w.prv_id[w.order[j + 1]] : -1, A, B, lane, pre_n);
+                    uint32_t pre_n[4]; const bool has_n = qt_prefetch(w, j + 1 < m ? w.prv_id[w.order[j + 1]] : -1, A, B, lane, pre_n);
                     int cnt[4], mx, my;
                     qt_divide(nd, A, B, lane, cnt, mx, my, pre, has_pre);
-                    qt_add_children(w, nd, cnt, mx, my, lane, nbig);
-                    qt_erase(w, id, lane);
-                    pre = pre_n; has_pre = has_n;
+                    qt_split(w, id, nd, cnt, mx, my, lane, nbig);
+                    has_pre = has_n;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) pre[u] = pre_n[u];
                     if (w.size >= N) break;
                 }
                 if (w.size >= N || w.size == prev2) finish = true;
