@@ -14,6 +14,7 @@
 //   k_describe                one warp per keypoint: IC_Angle, 7x7 Gaussian on a 43x43 patch, rBRIEF
 //                             (ORBextractor.cc:77-147,1085-1101)
 #include "common.h"
+#include <chrono>
 #include <cuda.h>          // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through the runtime (no -lcuda)
 #include <math.h>
 #include <algorithm>
@@ -2268,6 +2269,8 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
     const int acap = aruco ? b200_aruco_batch_capacity(aruco) : 0;
     const int amode = !aruco ? 0 : (acap >= n && !streamed) ? 2 : acap >= 2 * chunk ? 1 : 0;
     if (aruco && acap < std::min(chunk, n)) return fail(B200_ECAPACITY, "detector handle smaller than one pipeline chunk (%s frames)", "128");
+    static const bool trace = getenv("B200_FRONTEND_TRACE") != nullptr;       // host time spent enqueueing, printed per call
+    const auto t_enq0 = std::chrono::steady_clock::now();
     int ci = 0;
     // the first chunk is small so that compute starts after a short upload; the second one completes the regular grid
     const int first = (env_chunk <= 0 && chunk >= 64 && n > chunk) ? chunk / 4 : chunk;
@@ -2325,10 +2328,16 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
                          (rc = down(n_matches, o_nm, h->d_nmatch, (size_t)f0 * 4, (size_t)nf * 4)))) return rc;
     }
     // (the debug taps b200_orb_get_pyramid / _get_candidates now refer to the LAST chunk)
+    const auto t_enq1 = std::chrono::steady_clock::now();
     // the download stream has waited for every chunk of both stream sets: the error flags are final when it drains
     int err = 0;
     B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, ds));
     B200_CUDA(cudaStreamSynchronize(ds));
+    if (trace) {
+        const auto t_enq2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "b200_frontend_host: n=%d chunks=%d enqueue %.3f ms, wait %.3f ms\n", n, ci, std::chrono::duration<double, std::milli>(t_enq1 - t_enq0).count(),
+                std::chrono::duration<double, std::milli>(t_enq2 - t_enq1).count());
+    }
     if (err) { cudaMemset(h->d_err, 0, 4); return fail(B200_ECAPACITY, "quadtree scratch overflow (%s)", err == 1 ? "node pool" : "result slots"); }
     if (aruco && (rc = b200_aruco_check(aruco, ds))) return rc;
     if (!out_pinned) {
