@@ -905,6 +905,7 @@ struct QtNode {
 };
 
 constexpr int kQtWarps = 4;
+constexpr int kQtSmemKeys = 4096;       // per-warp capacity of the shared-memory key buffers of k_quadtree<true> (2 x 16 KB)
 
 struct QtWarp {          // per-warp view of its shared memory
     QtNode* pool; short* freelist; int nfree;
@@ -1124,11 +1125,14 @@ __device__ __forceinline__ int qt_split(QtWarp& w, int it, const QtNode nd, cons
     return nb;
 }
 
+// SMEMKEYS (small batches, where the L2 round trips of the key traffic are the whole run time): a level whose keys fit `key_cap` keeps both key
+// buffers in shared memory behind the node pool; larger levels use the global scratch as always.
+template <bool SMEMKEYS>
 __global__ void __launch_bounds__(kQtWarps * 32)
 k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells,
            const uint32_t* __restrict__ slots, const int* __restrict__ cellcnt,
            uint32_t* __restrict__ keysA, uint32_t* __restrict__ keysB,
-           uint32_t* __restrict__ lvlres, int* __restrict__ lvlcnt, int nframes, int pool_cap, int* __restrict__ errflag) {
+           uint32_t* __restrict__ lvlres, int* __restrict__ lvlcnt, int nframes, int pool_cap, int* __restrict__ errflag, int key_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int prob = blockIdx.x * kQtWarps + warp;
@@ -1138,8 +1142,10 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
     const LevelGeom& lg = g.L[level];
 
     // carve this warp's shared memory
-    const size_t per_warp = (size_t)pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64;
+    const size_t per_warp = (size_t)pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64 + (SMEMKEYS ? (size_t)key_cap * 8 : 0);
     unsigned char* sm = smem_raw + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(sm);       // SMEMKEYS: [2][key_cap] in front of the pool
+    if (SMEMKEYS) sm += (size_t)key_cap * 8;
     QtWarp w;
     w.pool = reinterpret_cast<QtNode*>(sm); sm += (size_t)pool_cap * sizeof(QtNode);
     w.big_cnt = reinterpret_cast<int*>(sm); sm += (size_t)pool_cap * 4;
@@ -1159,6 +1165,13 @@ k_quadtree(const __grid_constant__ OrbGeom g, const CellDesc* __restrict__ cells
     const uint32_t* S = slots + (long long)f * g.slots_per_frame;
     const int* cc = cellcnt + (long long)f * g.total_cells + lg.cell_base;
     const CellDesc* cl = cells + lg.cell_base;
+    if (SMEMKEYS) {                           // how many keys does this level hold?  (the gather below must know its destination first)
+        int tk = 0;
+        for (int c = lane; c < lg.ncells; c += 32) tk += min(cc[c], cl[c].cap);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tk += __shfl_xor_sync(0xffffffffu, tk, o);
+        if (tk <= key_cap) { A = skeys; B = skeys + key_cap; }
+    }
     const int N = lg.quota;
     int* out_cnt = lvlcnt + (long long)f * g.nlevels + level;
     uint32_t* out = lvlres + (long long)f * g.res_per_frame + lg.kp_base;
@@ -2025,12 +2038,23 @@ int enqueue(b200_orb_s* h, const uint8_t* imgs, int n, int w, int hh, long long 
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[2], st));
     {
         const int nprob = n * g.nlevels;
-        const size_t per_warp = ((size_t)h->pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64 + 15) & ~(size_t)15;
+        // up to 64 frames (one wave of CTAs): key buffers of up to kQtSmemKeys keys per level live in shared memory
+        const int key_cap = n <= 64 ? kQtSmemKeys : 0;
+        const size_t per_warp = ((size_t)h->pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64 + (size_t)key_cap * 8 + 15) & ~(size_t)15;
         const size_t smem = per_warp * kQtWarps;
-        static std::atomic<size_t> qt_smem_set(0);
-        if (smem > qt_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); qt_smem_set.store(smem); }
-        B200_LAUNCH(k_quadtree, (nprob + kQtWarps - 1) / kQtWarps, kQtWarps * 32, smem, st, g, h->d_cells, d_slots, d_cellcnt,
-                    d_keysA, d_keysB, d_lvlres, d_lvlcnt, n, h->pool_cap, h->d_err);
+        if (key_cap && smem <= 200 * 1024) {
+            static std::atomic<size_t> qts_smem_set(0);
+            if (smem > qts_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); qts_smem_set.store(smem); }
+            B200_LAUNCH(k_quadtree<true>, (nprob + kQtWarps - 1) / kQtWarps, kQtWarps * 32, smem, st, g, h->d_cells, d_slots, d_cellcnt,
+                        d_keysA, d_keysB, d_lvlres, d_lvlcnt, n, h->pool_cap, h->d_err, key_cap);
+        } else {
+            const size_t per_warp0 = ((size_t)h->pool_cap * (sizeof(QtNode) + 2 + 2 * (4 + 4 + 2) + 2) + 64 + 15) & ~(size_t)15;
+            const size_t smem0 = per_warp0 * kQtWarps;
+            static std::atomic<size_t> qt_smem_set(0);
+            if (smem0 > qt_smem_set.load()) { B200_CUDA(cudaFuncSetAttribute(k_quadtree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)); qt_smem_set.store(smem0); }
+            B200_LAUNCH(k_quadtree<false>, (nprob + kQtWarps - 1) / kQtWarps, kQtWarps * 32, smem0, st, g, h->d_cells, d_slots, d_cellcnt,
+                        d_keysA, d_keysB, d_lvlres, d_lvlcnt, n, h->pool_cap, h->d_err, 0);
+        }
     }
     if (h->profile) B200_CUDA(cudaEventRecord(h->ev[3], st));
     {
