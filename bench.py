@@ -583,7 +583,9 @@ def c1_line(ctx):
                           "std::vector<aruco::Marker> (with IPPE poses) out",
               "metric": "latency per frame (ms), median of 200 calls after 20 warm-up calls", "frames_per_s": 1000.0 / d["latency_ms_median"],
               "cpu_reference": {"latency_ms": 1000.0 * secs / nfr, "cores": 1, "kind": kind, "sample": "%d frames, 1 thread; %s" % (nfr, what)},
-              "speedup_vs_cpu_reference_1_thread": (1000.0 * secs / nfr) / d["latency_ms_median"]})
+              "speedup_vs_cpu_reference_1_thread": (1000.0 * secs / nfr) / d["latency_ms_median"],
+              "one_call": "one_call_ms_median = the same frame through ONE b200_frontend_host call (n = 1: extractor and detector concurrently on two streams) plus "
+                          "b200_aruco_pose_host: what replacing the two calls of Frame::Frame by one gives; plain arrays out (no std::vector / cv::Mat assembly)"})
     return d
 
 
