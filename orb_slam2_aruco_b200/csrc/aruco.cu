@@ -1558,7 +1558,7 @@ __device__ __forceinline__ FMin warp_argmin_first(float v, int i) {
     FMin r; r.v = v; r.i = i; return r;
 }
 
-constexpr int kFinWarps = 8;
+constexpr int kFinWarps = 20;       // at most; batches above 32 frames launch 8 warps per frame (latency of the refinement against SM slots for the other kernels)
 
 __global__ void __launch_bounds__(kFinWarps * 32)
 k_finalize(const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, const int* __restrict__ nkept,
@@ -1609,7 +1609,7 @@ k_finalize(const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, 
     const int m = s_m;
     b200_marker* out = out0 + (long long)f * out_cap;
     // CORNER_LINES refinement (8979-12049): one warp per marker
-    for (int mi = warp; mi < m; mi += kFinWarps) {
+    for (int mi = warp; mi < m; mi += (int)(blockDim.x >> 5)) {
         const int i = s_final[mi];
         const ContourDesc cd = desc0[(long long)f * g.max_contours + kept[s_src[i]].contour];
         const short2* cp = pts0 + (long long)f * g.max_points + cd.off;
@@ -2027,7 +2027,7 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     B200_LAUNCH(k_decode<0>, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec, d_wpatch, d_whist, d_wlevel);
     B200_LAUNCH(k_otsu, dim3(kMaxCand / 128, n), 128, 0, st, g, d_nkept, d_whist, d_wlevel);
     B200_LAUNCH(k_decode<1>, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec, d_wpatch, d_whist, d_wlevel);
-    B200_LAUNCH(k_finalize, n, kFinWarps * 32, 0, st, g, d_kept, d_nkept, d_dec, d_desc, d_pts, d_scratch,
+    B200_LAUNCH(k_finalize, n, (n <= 32 ? kFinWarps : 8) * 32, 0, st, g, d_kept, d_nkept, d_dec, d_desc, d_pts, d_scratch,
                 markers, counts, kMaxMarkers, h->d_err, h->d_mcontour + (size_t)base * kMaxMarkers);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
