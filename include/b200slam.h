@@ -263,6 +263,15 @@ int b200_aruco_pose(const b200_marker* markers, const int32_t* counts, int n_bat
 /* Same for a host array of n_markers markers (the adapter's detect(image, cameraParams, markerSize) and aruco::solvePnP). */
 int b200_aruco_pose_host(const b200_marker* markers, int n_markers, float marker_size, const float* cam9,
                          b200_marker_pose* poses, int device);
+/* One frame, everything aruco::MarkerDetector::detect(image, camParams, markerSizeMeters) returns (markerdetector.h:277-278, src/Frame.cc:142), with a
+ * single synchronisation: markers [b200_aruco_max_markers()] sorted by id and their count; with cam9 != NULL the IPPE poses [b200_aruco_max_markers()]
+ * of marker.cpp:322-343 computed on the device from the detector's device output; with contour_ofs != NULL ([count + 1] offsets) the markers' contour
+ * points (aruco::Marker::contourPoints, markerdetector_impl.cpp:6759-6772) as x, y pairs in contour_xy [contour_cap pairs].  Returns the total number of
+ * contour points (0 without contours; when it exceeds contour_cap only contour_cap points were copied: grow and call b200_aruco_get_contours), or a
+ * negative error code.  The handle needs max_batch >= 1. */
+int b200_aruco_detect_frame_host(b200_aruco_t h, const uint8_t* img, int width, int height, int64_t row_stride, b200_marker* markers, int32_t* count,
+                                 float marker_size, const float* cam9, b200_marker_pose* poses,
+                                 int32_t* contour_ofs, int32_t* contour_xy, int contour_cap);
 
 
 /* ---------------------------------------------------------------- frame grid -------- */

@@ -770,19 +770,32 @@ public:
         ensure(input.cols, input.rows);
         const int cap = b200_aruco_max_markers(h_);
         std::vector<b200_marker> m(cap);
+        std::vector<b200_marker_pose> p(cap);
         int32_t n = 0;
-        b200slam_detail::check(b200_aruco_detect_host(h_, input.data, 1, input.cols, input.rows, (int64_t)input.step, (int64_t)input.step * input.rows, m.data(), &n));
+        // markerdetector_impl.cpp detect(input, markers, camParams, size, ...): "if (camParams.CamSize != input.size() && camParams.isValid() &&
+        // markerSizeMeters > 0) { cp_aux = camParams; cp_aux.resize(input.size()); ... }" - always taken in the reference, whose CamSize is the
+        // hard-coded 1280 x 720 of src/Frame.cc:132 whatever the camera delivers
+        const bool want_pose = camParams.isValid() && markerSizeMeters > 0;
+        float cam[9];
+        if (want_pose) {
+            const CameraParameters cp = (camParams.width > 0 && camParams.height > 0) ? camParams.resized(input.cols, input.rows) : camParams;
+            cp.cam9(cam);
+        }
+        // markers, poses (marker.cpp:322-343 -> ippe.cpp, on the device for all markers at once) and contour points (markerdetector_impl.cpp:6759-6772)
+        // in ONE library call with one synchronisation
+        std::vector<int32_t> ofs((size_t)cap + 1, 0);
+        if (fillContourPoints) contour_xy_.resize((size_t)2 * contour_cap_ + 2);
+        int total = b200_aruco_detect_frame_host(h_, input.data, input.cols, input.rows, (int64_t)input.step, m.data(), &n, markerSizeMeters,
+                                                 want_pose ? cam : nullptr, p.data(), fillContourPoints ? ofs.data() : nullptr,
+                                                 fillContourPoints ? contour_xy_.data() : nullptr, fillContourPoints ? contour_cap_ : 0);
+        b200slam_detail::check(total);
         std::vector<Marker> out(n);
         for (int i = 0; i < n; i++) {
             out[i].id = m[i].id;
             for (int k = 0; k < 4; k++) out[i].push_back(cv::Point2f(m[i].xy[2 * k], m[i].xy[2 * k + 1]));
             out[i].dict_info = dict_;                                                                // Dictionary::getName() (dictionary.cpp:118-231)
         }
-        if (n > 0 && fillContourPoints) {                                                            // markerdetector_impl.cpp:6759-6772, one round trip for all markers
-            std::vector<int32_t> ofs((size_t)n + 1, 0);
-            contour_xy_.resize((size_t)2 * contour_cap_ + 2);
-            int total = b200_aruco_get_contours(h_, 0, n, ofs.data(), contour_xy_.data(), contour_cap_);
-            b200slam_detail::check(total);
+        if (n > 0 && fillContourPoints) {
             if (total > contour_cap_) {                                                              // grow once, fetch again
                 contour_cap_ = total;
                 contour_xy_.resize((size_t)2 * contour_cap_ + 2);
@@ -794,16 +807,7 @@ public:
                 for (int j = 0; j < len; j++) out[i].contourPoints[j] = cv::Point(contour_xy_[2 * (ofs[i] + j)], contour_xy_[2 * (ofs[i] + j) + 1]);
             }
         }
-        if (n > 0 && camParams.isValid() && markerSizeMeters > 0) {
-            // markerdetector_impl.cpp detect(input, markers, camParams, size, ...): "if (camParams.CamSize != input.size() && camParams.isValid() &&
-            // markerSizeMeters > 0) { cp_aux = camParams; cp_aux.resize(input.size()); ... }" - always taken in the reference, whose CamSize is the
-            // hard-coded 1280 x 720 of src/Frame.cc:132 whatever the camera delivers
-            const CameraParameters cp = (camParams.width > 0 && camParams.height > 0) ? camParams.resized(input.cols, input.rows) : camParams;
-            float cam[9]; cp.cam9(cam);
-            std::vector<b200_marker_pose> p(n);
-            b200slam_detail::check(b200_aruco_pose_host(m.data(), n, markerSizeMeters, cam, p.data(), device_));
-            for (int i = 0; i < n; i++) out[i].setPose(p[i], markerSizeMeters);
-        }
+        if (want_pose) for (int i = 0; i < n; i++) out[i].setPose(p[i], markerSizeMeters);
         return out;
     }
 

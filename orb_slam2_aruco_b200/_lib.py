@@ -76,6 +76,7 @@ def lib():
         L.b200_aruco_get_contours.argtypes = [vp, i32, i32, vp, vp, i32]
         L.b200_aruco_pose.argtypes = [vp, vp, i32, i32, f32, vp, vp, i32, vp]
         L.b200_aruco_pose_host.argtypes = [vp, i32, f32, vp, vp, i32]
+        L.b200_aruco_detect_frame_host.argtypes = [vp, vp, i32, i32, i64, vp, vp, f32, vp, vp, vp, vp, i32]
         L.b200_voc_create.argtypes = [C.POINTER(vp), i32, i32, i32, vp, vp, vp, vp, i32]
         L.b200_voc_destroy.argtypes = [vp]
         L.b200_voc_num_words.argtypes = [vp]

@@ -1706,10 +1706,11 @@ k_finalize(const __grid_constant__ ArucoGeom g, const Kept* __restrict__ kept0, 
 
 // packs the borders of a frame's output markers back to back: offsets by one warp scan, points copied by the whole CTA
 __global__ void __launch_bounds__(256)
-k_pack_contours(const __grid_constant__ ArucoGeom g, const int* __restrict__ mcontour, int n_markers, const ContourDesc* __restrict__ desc,
-                const short2* __restrict__ pts, int* __restrict__ ofs, short2* __restrict__ out) {
+k_pack_contours(const __grid_constant__ ArucoGeom g, const int* __restrict__ mcontour, int n_markers_host, const int* __restrict__ n_markers_dev,
+                const ContourDesc* __restrict__ desc, const short2* __restrict__ pts, int* __restrict__ ofs, short2* __restrict__ out, int out_cap) {
     __shared__ int s_ofs[kMaxMarkers + 1], s_src[kMaxMarkers];
     const int tid = threadIdx.x;
+    const int n_markers = n_markers_dev ? min(*n_markers_dev, kMaxMarkers) : n_markers_host;       // the count may only exist on the device yet
     if (tid < 32) {
         int run = 0;
         for (int m0 = 0; m0 < n_markers; m0 += 32) {
@@ -1732,7 +1733,7 @@ k_pack_contours(const __grid_constant__ ArucoGeom g, const int* __restrict__ mco
     if (s_ofs[n_markers] > g.max_points) return;
     for (int m = 0; m < n_markers; m++) {
         const int len = s_ofs[m + 1] - s_ofs[m];
-        for (int i = tid; i < len; i += blockDim.x) out[s_ofs[m] + i] = pts[s_src[m] + i];
+        for (int i = tid; i < len; i += blockDim.x) if (s_ofs[m] + i < out_cap) out[s_ofs[m] + i] = pts[s_src[m] + i];
     }
 }
 
@@ -1765,6 +1766,7 @@ struct b200_aruco_s {
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
     int* d_mcontour;                          // [max_batch][kMaxMarkers]: the border (ContourDesc index) every output marker came from
     void* d_pack;                             // staging of b200_aruco_get_contours: offsets + packed points of one frame
+    void* d_poses; void* h_pack; size_t h_pack_cap;      // b200_aruco_detect_frame_host: device poses, pinned staging of the packed points
 };
 
 namespace {
@@ -1903,7 +1905,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_smap); cudaFree(h->d_nodes); cudaFree(h->d_sbits); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_smap); cudaFree(h->d_nodes); cudaFree(h->d_sbits); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack); cudaFree(h->d_poses); if (h->h_pack) cudaFreeHost(h->h_pack);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -2124,8 +2126,8 @@ int b200_aruco_get_contours(b200_aruco_t h, int frame, int n_markers, int32_t* o
     }
     int* d_ofs = reinterpret_cast<int*>(h->d_pack);
     short2* d_pp = reinterpret_cast<short2*>(d_ofs + kMaxMarkers + 1);
-    B200_LAUNCH(k_pack_contours, 1, 256, 0, st, h->geom, h->d_mcontour + (size_t)frame * kMaxMarkers, n_markers,
-                h->d_desc + (size_t)frame * h->geom.max_contours, h->d_pts + (size_t)frame * h->geom.max_points, d_ofs, d_pp);
+    B200_LAUNCH(k_pack_contours, 1, 256, 0, st, h->geom, h->d_mcontour + (size_t)frame * kMaxMarkers, n_markers, (const int*)nullptr,
+                h->d_desc + (size_t)frame * h->geom.max_contours, h->d_pts + (size_t)frame * h->geom.max_points, d_ofs, d_pp, h->geom.max_points);
     int hofs[kMaxMarkers + 1];
     B200_CUDA(cudaMemcpyAsync(hofs, d_ofs, sizeof(int) * (n_markers + 1), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
@@ -2175,6 +2177,89 @@ int b200_aruco_detect_host(b200_aruco_t h, const uint8_t* imgs, int n, int w, in
         return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 9 ? err : 0]);
     }
     return B200_OK;
+}
+
+
+// One frame, everything aruco::MarkerDetector::detect(image, camParams, markerSize) returns, with ONE synchronisation: markers, the IPPE poses
+// (cam9 != NULL: marker.cpp:322-343 on the device, straight from the detector's device output) and the markers' contour points
+// (contour_ofs != NULL: markerdetector_impl.cpp:6759-6772).  Returns the total number of contour points (0 without contours), which may exceed
+// contour_cap (then only contour_cap points were copied: fetch again with b200_aruco_get_contours), or a negative error code.
+int b200_aruco_detect_frame_host(b200_aruco_t h, const uint8_t* img, int w, int hh, int64_t rs, b200_marker* markers, int32_t* count,
+                                 float marker_size, const float* cam9, b200_marker_pose* poses,
+                                 int32_t* contour_ofs, int32_t* contour_xy, int contour_cap) {
+    if (!h) return fail(B200_EINVAL, "null %s", "handle");
+    if (w < 0 || hh < 0 || contour_cap < 0) return fail(B200_EINVAL, "negative %s", "size");
+    if (w > h->max_w || hh > h->max_h) return fail(B200_ECAPACITY, "image larger than the handle's %s", "capacity");
+    if (!markers || !count || (!img && w > 0 && hh > 0) || (cam9 && !poses) || (contour_ofs && !contour_xy && contour_cap > 0)) return fail(B200_EINVAL, "null %s", "pointer");
+    DeviceScope _ds; int rc = use_device(h->device);
+    if (rc) return rc;
+    *count = 0;
+    if (contour_ofs) contour_ofs[0] = 0;
+    if (w < 8 || hh < 8) return 0;
+    const size_t fb = (size_t)w * hh;
+    if ((rc = ensure_buf(h->d_in, h->cap_in, fb))) return rc;
+    if (h->cap_out < 1) {
+        cudaFree(h->d_out); cudaFree(h->d_counts); h->d_out = nullptr; h->d_counts = nullptr; h->cap_out = 0;
+        B200_CUDA(cudaMalloc((void**)&h->d_out, sizeof(b200_marker) * kMaxMarkers * (size_t)h->max_batch));
+        B200_CUDA(cudaMalloc((void**)&h->d_counts, 4 * (size_t)h->max_batch));
+        h->cap_out = h->max_batch;
+    }
+    if (!h->d_pack) B200_CUDA(cudaMalloc((void**)&h->d_pack, sizeof(int) * (kMaxMarkers + 1) + sizeof(short2) * (size_t)h->geom.max_points));
+    if (!h->d_poses) B200_CUDA(cudaMalloc((void**)&h->d_poses, sizeof(b200_marker_pose) * kMaxMarkers));
+    cudaStream_t st = h->stream;
+    B200_CUDA(cudaMemcpy2DAsync(h->d_in, w, img, rs, w, (size_t)hh, cudaMemcpyHostToDevice, st));
+    if ((rc = b200_aruco_detect(h, h->d_in, 1, w, hh, w, (int64_t)fb, h->d_out, h->d_counts, st))) return rc;
+    B200_CUDA(cudaMemcpyAsync(markers, h->d_out, sizeof(b200_marker) * kMaxMarkers, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(count, h->d_counts, 4, cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    B200_CUDA(cudaMemcpyAsync(&err, h->d_err, 4, cudaMemcpyDeviceToHost, st));
+    if (cam9) {
+        if ((rc = b200_aruco_pose(h->d_out, h->d_counts, 1, kMaxMarkers, marker_size, cam9, (b200_marker_pose*)h->d_poses, h->device, st))) return rc;
+        B200_CUDA(cudaMemcpyAsync(poses, h->d_poses, sizeof(b200_marker_pose) * kMaxMarkers, cudaMemcpyDeviceToHost, st));
+    }
+    int hofs[kMaxMarkers + 1];
+    const int take_cap = std::min(contour_cap, h->geom.max_points);
+    if (contour_ofs) {
+        int* d_ofs = reinterpret_cast<int*>(h->d_pack);
+        short2* d_pp = reinterpret_cast<short2*>(d_ofs + kMaxMarkers + 1);
+        B200_LAUNCH(k_pack_contours, 1, 256, 0, st, h->geom, h->d_mcontour, 0, (const int*)h->d_counts, h->d_desc, h->d_pts, d_ofs, d_pp, take_cap);
+        B200_CUDA(cudaMemcpyAsync(hofs, d_ofs, sizeof(int) * (kMaxMarkers + 1), cudaMemcpyDeviceToHost, st));
+        if (take_cap > 0) {
+            if (h->h_pack_cap < (size_t)take_cap) {
+                if (h->h_pack) cudaFreeHost(h->h_pack);
+                h->h_pack = nullptr; h->h_pack_cap = 0;
+                B200_CUDA(cudaMallocHost((void**)&h->h_pack, sizeof(short2) * (size_t)take_cap));
+                h->h_pack_cap = take_cap;
+            }
+            // the number of points is only known on the device: a fixed, small upper bound travels (a marker's border has a few hundred points)
+            B200_CUDA(cudaMemcpyAsync(h->h_pack, d_pp, sizeof(short2) * (size_t)std::min(take_cap, 8192), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (err) {
+        cudaMemset(h->d_err, 0, 4);
+        static const char* what[] = {"", "", "", "border longer than the point budget", "too many contours", "contour point budget", "more than 256 quads", "more than 64 markers", "transition survivor list"};
+        return fail(B200_ECAPACITY, "detector scratch overflow: %s", what[err < 9 ? err : 0]);
+    }
+    int total = 0;
+    if (contour_ofs) {
+        const int nm = std::min(*count, kMaxMarkers);
+        total = hofs[nm];
+        if (total < 0 || total > h->geom.max_points) return fail(B200_EINVAL, "stale %s", "contours");
+        for (int m = 0; m <= nm; m++) contour_ofs[m] = hofs[m];
+        const int have = std::min(std::min(total, take_cap), 8192);
+        const short2* p = reinterpret_cast<const short2*>(h->h_pack);
+        for (int i = 0; i < have; i++) { contour_xy[2 * i] = p[i].x; contour_xy[2 * i + 1] = p[i].y; }
+        if (total > have && have < std::min(total, contour_cap)) {            // more points than the fixed transfer carried: the rest with a second copy
+            const int more = std::min(total, take_cap) - have;
+            std::vector<short2> q(more);
+            const short2* d_pp = reinterpret_cast<const short2*>(reinterpret_cast<int*>(h->d_pack) + kMaxMarkers + 1);
+            B200_CUDA(cudaMemcpyAsync(q.data(), d_pp + have, sizeof(short2) * (size_t)more, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            for (int i = 0; i < more; i++) { contour_xy[2 * (have + i)] = q[i].x; contour_xy[2 * (have + i) + 1] = q[i].y; }
+        }
+    }
+    return total;
 }
 
 }  // extern "C"
