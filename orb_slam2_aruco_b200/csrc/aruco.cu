@@ -1766,6 +1766,7 @@ struct b200_aruco_s {
     uint8_t* d_in; size_t cap_in; b200_marker* d_out; int* d_counts; size_t cap_out;
     int* d_mcontour;                          // [max_batch][kMaxMarkers]: the border (ContourDesc index) every output marker came from
     void* d_pack;                             // staging of b200_aruco_get_contours: offsets + packed points of one frame
+    cudaStream_t pyr_stream; cudaEvent_t ev_pyr_fork, ev_pyr_join;      // the half pyramid runs beside the contour kernels (only k_decode reads it)
     void* d_poses; void* h_pack; size_t h_pack_cap;      // b200_aruco_detect_frame_host: device poses, pinned staging of the packed points
 };
 
@@ -1881,6 +1882,8 @@ int b200_aruco_create(b200_aruco_t* out, const char* dict_name, int max_w, int m
     h->device = device; h->max_w = max_w; h->max_h = max_h; h->max_batch = max_batch; h->cur_w = h->cur_h = -1;
     h->dict = dict_name; h->nbits = dt->nbits; h->ncodes = dt->n;
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->pyr_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_pyr_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_pyr_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_codes, sizeof(unsigned long long) * dt->n) == cudaSuccess;
     ok = ok && cudaMemcpy(h->d_codes, dt->codes, sizeof(unsigned long long) * dt->n, cudaMemcpyHostToDevice) == cudaSuccess;
     const size_t B = (size_t)max_batch;
@@ -1908,6 +1911,9 @@ int b200_aruco_destroy(b200_aruco_t h) {
     cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_smap); cudaFree(h->d_nodes); cudaFree(h->d_sbits); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack); cudaFree(h->d_poses); if (h->h_pack) cudaFreeHost(h->h_pack);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->pyr_stream) cudaStreamDestroy(h->pyr_stream);
+    if (h->ev_pyr_fork) cudaEventDestroy(h->ev_pyr_fork);
+    if (h->ev_pyr_join) cudaEventDestroy(h->ev_pyr_join);
     delete h;
     return B200_OK;
 }
@@ -1967,12 +1973,16 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
             default: B200_LAUNCH(k_athresh2<7>, g2, kAt2Warps * 32, 0, st, imgs, rs, fs, g, d_mask, rows); break;
         }
     }
+    // the half pyramid is read by k_decode only: it runs on the handle's second stream beside the contour kernels and joins in front of k_decode
+    B200_CUDA(cudaEventRecord(h->ev_pyr_fork, st));
+    B200_CUDA(cudaStreamWaitEvent(h->pyr_stream, h->ev_pyr_fork, 0));
     for (int l = 1; l < g.nlev; l++) {
         const uint8_t* src = l == 1 ? imgs : d_pyr + g.loff[l - 1];
         const long long srs = l == 1 ? rs : g.lpitch[l - 1], sfs = l == 1 ? fs : g.pyr_frame;
         dim3 gp((g.lw[l] + 31) / 32, (g.lh[l] + 7) / 8, n);
-        B200_LAUNCH(k_halfpyr, gp, blk, 0, st, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
+        B200_LAUNCH(k_halfpyr, gp, blk, 0, h->pyr_stream, src, srs, sfs, g.lw[l - 1], g.lh[l - 1], d_pyr + g.loff[l], g.lpitch[l], g.pyr_frame, g.lw[l], g.lh[l]);
     }
+    B200_CUDA(cudaEventRecord(h->ev_pyr_join, h->pyr_stream));
     // contour following: against the frame's bit image in shared memory when it fits (one CTA per frame), else the global-memory walkers
     const int ct_pw = (w + 1) / 30 + 1, ct_npw = (w + 31) / 32;
     const size_t ct_smem = ((size_t)(hh + 2) * ct_pw + (size_t)kCtWarps * (ct_npw + 4)) * 4;
@@ -2026,6 +2036,7 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
     uint8_t* d_wpatch = h->d_wpatch + (size_t)base * kMaxCand * kMaxWarp * kMaxWarp;
     uint16_t* d_whist = h->d_whist + (size_t)base * kMaxCand * 256;
     int* d_wlevel = h->d_wlevel + (size_t)base * kMaxCand;
+    B200_CUDA(cudaStreamWaitEvent(st, h->ev_pyr_join, 0));
     B200_LAUNCH(k_decode<0>, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec, d_wpatch, d_whist, d_wlevel);
     B200_LAUNCH(k_otsu, dim3(kMaxCand / 128, n), 128, 0, st, g, d_nkept, d_whist, d_wlevel);
     B200_LAUNCH(k_decode<1>, gd, 128, 0, st, imgs, rs, fs, d_pyr, g, d_kept, d_nkept, h->d_codes, d_dec, d_wpatch, d_whist, d_wlevel);
