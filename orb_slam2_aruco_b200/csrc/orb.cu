@@ -1871,6 +1871,7 @@ int set_geometry(b200_orb_s* h, int w, int h_img) {
         // one tile pitch for all levels (k_fast is instantiated for 64, 80 and 96 bytes)
         int tp = 64;
         for (int l = 0; l < h->nlevels; l++) tp = std::max(tp, g.L[l].box_w);
+        { static const int env_tp = [] { const char* e = getenv("B200_FAST_TP"); return e ? atoi(e) : 0; }(); if (env_tp > tp) tp = env_tp; }
         tp = tp <= 64 ? 64 : tp <= 80 ? 80 : 96;
         for (int l = 0; l < h->nlevels; l++) {
             g.L[l].box_w = tp;
