@@ -1040,14 +1040,18 @@ k_quads(const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ des
     // 2. initial slices (start of the last hop, farthest point from it)
     if (!le_eps) {
         const int s_start = pos % count, s_end = (rstart + s_start) % count;
-        stack[0] = s_end; stack[1] = s_start;      // right slice  [s_end -> s_start]
-        stack[2] = s_start; stack[3] = s_end;      // slice        [s_start -> s_end], processed first
+        if (lane == 0) {
+            stack[0] = s_end; stack[1] = s_start;      // right slice  [s_end -> s_start]
+            stack[2] = s_start; stack[3] = s_end;      // slice        [s_start -> s_end], processed first
+        }
         top = 2;
-    } else { vx[0] = sp.x; vy[0] = sp.y; nv = 1; }
+    } else { if (lane == 0) { vx[0] = sp.x; vy[0] = sp.y; } nv = 1; }
+    __syncwarp();
     // 3. subdivision
     while (top > 0) {
         top--;
         const int a = stack[2 * top], b = stack[2 * top + 1];
+        __syncwarp();                                              // all lanes hold the slice before lane 0 reuses its stack slots
         const short2 start_pt = P[a], end_pt = P[b];
         int nint = b - a - 1; if (nint < 0) nint += count;         // interior points a+1 .. b-1 (cyclic)
         bool le = true;

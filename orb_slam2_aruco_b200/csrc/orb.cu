@@ -393,7 +393,9 @@ k_fast(const uint8_t* __restrict__ img0, long long img_row_stride, long long img
             }
         }
         __syncthreads();
-        if (s_any || pass == 1 || g.min_th >= g.ini_th) break;
+        const int any = s_any;
+        __syncthreads();                              // everybody has read the flag before thread 0 clears it for the next pass
+        if (any || pass == 1 || g.min_th >= g.ini_th) break;
         // nothing at iniThFAST: the whole cell again at minThFAST (a superset of the pixels examined so far; the scores already
         // in the tile stay valid)
         T = g.min_th;
