@@ -60,7 +60,9 @@ struct ArucoGeom {
     int ncodes;
 };
 
-struct ContourDesc { int start; int s0; int len; int key; int off; };
+struct ContourDesc { int start; int s0; int len; int key; int off; int ck; };   // start: index into the padded binary image; ck: first checkpoint of the border in the frame's checkpoint pool, or -1
+constexpr int kCkStride = 256;       // a walker that follows a border records its state every kCkStride steps (k_probe_b) ...
+constexpr int kCkPerBorder = 16;     // ... at most this many times: k_emit then writes the border's points with one thread per stretch
 struct SegNode { int next, len, key, off; };       // a surviving transition as a node of its border's ring: successor, steps to it, raster key, first point slot (-1: not emitted)   // start: index into the padded binary image
 struct Candidate { int cx[4], cy[4]; int key; int contour; };
 struct Kept { float c[8]; int contour; };
@@ -470,11 +472,15 @@ k_probe_b1(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom 
 // Phase B2 (persistent warps over the survivors; lanes refill in batches so that the refill code runs rarely and every lane
 // spends its iterations in the same loop body): FORWARDS until back home (=> it is Suzuki's start: the border is recorded
 // with its length if > 70 points) or until a transition that the raster scan sees earlier shows up (=> abort).
+constexpr int kWalkSteps = 4;
+
 __global__ void __launch_bounds__(128)
 k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const int* __restrict__ surv, const int* __restrict__ nsurv,
           int max_cand, int* __restrict__ nfetch, ContourDesc* __restrict__ desc, int* __restrict__ ncont, int* __restrict__ npts,
-          int* __restrict__ err) {
+          int* __restrict__ err, int walk_steps, int* __restrict__ ckalloc, int* __restrict__ ckpool0, int ck_cap) {
     const int f = blockIdx.x, lane = threadIdx.x & 31;
+    int* ckpool = ckpool0 + (long long)f * (ck_cap + ck_cap / kCkPerBorder);      // checkpoints, then one owner (border index) per block
+    int ckb = -1;                                      // this walk's block of checkpoints in the frame's pool (-1: none yet, -2: pool exhausted)
     const int ns = min(nsurv[f], max_cand);
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
     const int* list = surv + (long long)f * max_cand;
@@ -500,11 +506,14 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
                     const unsigned rot = (((unsigned)m0 | ((unsigned)m0 << 8)) >> (from + 1)) & 0xffu;
                     s0 = (from + 1 + (31 - __clz(rot))) & 7;                // rot != 0: phase B1 kept it
                     mykey = P + (hole ? 1 : 0);
-                    p = P; s = s0; n = 0; busy = true;
+                    p = P; s = s0; n = 0; busy = true; ckb = -1;
                 }
             }
         }
         if (!__any_sync(0xffffffffu, busy)) { if (exhausted) break; else continue; }
+        // four steps per refill check: the two ballots and the refill test are paid once per four dependent loads
+#pragma unroll 1
+        for (int rep = 0; rep < walk_steps; rep++)
         if (busy) {
             const Step st = next_step(mask[p], s);
             if (n > 0 && step_key(p, s, st.k) < mykey) busy = false;
@@ -512,6 +521,10 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
                 p += dir_delta(st.d, g.bpitch);
                 s = (st.d + 4) & 7;
                 n++;
+                if ((n & (kCkStride - 1)) == 0 && n <= kCkStride * kCkPerBorder && ckb != -2) {      // state after n steps, for k_emit's stretches
+                    if (ckb < 0) { const int b = atomicAdd(ckalloc + f, kCkPerBorder); ckb = b + kCkPerBorder <= ck_cap ? b : -2; if (ckb >= 0) ckpool[ck_cap + b / kCkPerBorder] = -1; }
+                    if (ckb >= 0) ckpool[ckb + n / kCkStride - 1] = p | (s << 27);
+                }
                 if (p == P && s == s0) {
                     busy = false;
                     if (n > kMinContour) {
@@ -520,7 +533,7 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
                         else {
                             const int off = atomicAdd(npts + f, n);
                             if (off + n > g.max_points) atomicExch(err, 5);
-                            else { ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off; desc[(long long)f * g.max_contours + idx] = c; }
+                            else { ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off; c.ck = ckb >= 0 ? ckb : -1; desc[(long long)f * g.max_contours + idx] = c; if (ckb >= 0) ckpool[ck_cap + ckb / kCkPerBorder] = idx; }
                         }
                     }
                 } else if (n > limit) { atomicExch(err, 3); busy = false; }
@@ -529,23 +542,56 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
     }
 }
 
+constexpr int kEmitCtasA = 4;        // k_emit: CTAs per frame that take one border per thread; the CTAs behind them take the checkpointed stretches
+
 __global__ void __launch_bounds__(128)
 k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, const ContourDesc* __restrict__ desc,
-       const int* __restrict__ ncont, short2* __restrict__ pts) {
+       const int* __restrict__ ncont, short2* __restrict__ pts, const int* __restrict__ ckalloc, const int* __restrict__ ckpool0, int ck_cap) {
+    // Part A (blockIdx.x < kEmitCtasA), one thread per border: its first kCkStride points when the walker that found it left checkpoints, else all of
+    // them.  Part B, one thread per checkpoint of the frame's pool: the stretch that starts at the state k_probe_b recorded there (the last stretch of a
+    // border runs to its end).  Only walks of 256 steps and more allocate checkpoints, so part B is a few hundred threads per frame, and no thread of
+    // either part follows more than kCkStride points of a border shorter than kCkStride * (kCkPerBorder + 1).
     const int f = blockIdx.y;
-    const int nc = min(ncont[f], g.max_contours);
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
-        const ContourDesc c = desc[(long long)f * g.max_contours + i];
-        short2* out = pts + (long long)f * g.max_points + c.off;
-        int p = c.start, s = c.s0;
-        int x = c.start % g.bpitch - kMaskPad, y = c.start / g.bpitch - 1;
-        for (int n = 0; n < c.len; n++) {
-            out[n] = make_short2((short)x, (short)y);
-            const Step st = next_step(mask[p], s);
-            const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
-            p += dy * g.bpitch + dx; x += dx; y += dy;
-            s = (st.d + 4) & 7;
+    const int* ckpool = ckpool0 + (long long)f * (ck_cap + ck_cap / kCkPerBorder);
+    int p, s, n0, n1;
+    short2* out;
+    if (blockIdx.x < kEmitCtasA) {
+        const int nc = min(ncont[f], g.max_contours);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += kEmitCtasA * blockDim.x) {
+            const ContourDesc c = desc[(long long)f * g.max_contours + i];
+            p = c.start; s = c.s0; n0 = 0; n1 = (c.ck >= 0 && c.len > kCkStride) ? kCkStride : c.len;
+            out = pts + (long long)f * g.max_points + c.off;
+            int x = p % g.bpitch - kMaskPad, y = p / g.bpitch - 1;
+            for (int n = n0; n < n1; n++) {
+                out[n] = make_short2((short)x, (short)y);
+                const Step st = next_step(mask[p], s);
+                const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
+                p += dy * g.bpitch + dx; x += dx; y += dy;
+                s = (st.d + 4) & 7;
+            }
+        }
+    } else {
+        const int nck = min(ckalloc[f], ck_cap);                     // allocated checkpoint slots (blocks of kCkPerBorder)
+        for (int t = (blockIdx.x - kEmitCtasA) * blockDim.x + threadIdx.x; t < nck; t += (gridDim.x - kEmitCtasA) * blockDim.x) {
+            const int b = t / kCkPerBorder * kCkPerBorder, k = t - b;                  // checkpoint k of block b = the state after (k + 1) * kCkStride steps
+            const int owner = ckpool[ck_cap + b / kCkPerBorder];                       // border the block belongs to (-1: its walker gave up)
+            if (owner < 0) continue;
+            const ContourDesc c = desc[(long long)f * g.max_contours + owner];
+            n0 = (k + 1) * kCkStride;
+            if (c.ck != b || n0 >= c.len) continue;
+            n1 = (k == kCkPerBorder - 1) ? c.len : min(c.len, n0 + kCkStride);
+            const int v = ckpool[b + k];
+            p = v & 0x7ffffff; s = v >> 27;
+            out = pts + (long long)f * g.max_points + c.off;
+            int x = p % g.bpitch - kMaskPad, y = p / g.bpitch - 1;
+            for (int n = n0; n < n1; n++) {
+                out[n] = make_short2((short)x, (short)y);
+                const Step st = next_step(mask[p], s);
+                const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
+                p += dy * g.bpitch + dx; x += dx; y += dy;
+                s = (st.d + 4) & 7;
+            }
         }
     }
 }
@@ -687,7 +733,7 @@ k_ring(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
                     if (o0 + total > g.max_points) atomicExch(err, 5);
                     else {
                         const int e = surv[(long long)f * max_cand + i], P = e & 0x3fffffff;
-                        ContourDesc c; c.start = P; c.s0 = start_dir(mask0[(long long)f * g.bframe + P], e); c.len = total; c.key = node_key(me); c.off = o0;
+                        ContourDesc c; c.start = P; c.s0 = start_dir(mask0[(long long)f * g.bframe + P], e); c.len = total; c.key = node_key(me); c.off = o0; c.ck = -1;
                         desc[(long long)f * g.max_contours + idx] = c;
                         o = o0; done = false;                         // j == i: the first slot is the start's own
                     }
@@ -950,7 +996,7 @@ k_contours(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom 
                             if (idx >= g.max_contours) atomicExch(err, 4);
                             else {
                                 const int off = atomicAdd(&s_npts, n);
-                                ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off;
+                                ContourDesc c; c.start = P; c.s0 = s0; c.len = n; c.key = mykey; c.off = off; c.ck = -1;
                                 if (off + n > g.max_points) { atomicExch(err, 5); c.len = 0; c.off = 0; }      // the call fails; keep the slot harmless
                                 desc[idx] = c;
                             }
@@ -1763,7 +1809,8 @@ struct b200_aruco_s {
     int *d_ncont, *d_npts, *d_ncand, *d_nkept, *d_nsurv, *d_nfetch, *d_err;
     int* d_surv2; int* d_nsurv2; size_t cap_surv2;
     int* d_smap; unsigned long long* d_nodes; uint32_t* d_sbits; int sbits_words; size_t cap_smap, cap_nodes, cap_sbits; int ring_slots, ring_mode;      // ring form of the border walks: raster key -> survivor; {successor, steps to it} per survivor
-    int *d_nfetch2, *d_nfetch3;
+    int *d_nfetch2, *d_nfetch3;      // d_nfetch2: per-frame allocator of the checkpoint pool
+    int* d_ckpool; int ck_cap; size_t cap_ckpool;
     uint8_t* d_wpatch; uint16_t* d_whist; int* d_wlevel;    // warped patches, their histograms and Otsu levels: [B][256][...]      // transitions that survive the backward check (phase B1)
     size_t cap_mask, cap_pyr, cap_desc, cap_pts, cap_scratch, cap_surv;
     // staging for the host API
@@ -1845,6 +1892,8 @@ int aruco_geometry(b200_aruco_s* h, int w, int hh) {
     h->max_surv = std::max(1024, w * hh);              // transition list: at most two entries per foreground pixel
     if ((rc = ensure_buf(h->d_surv, h->cap_surv, sizeof(int) * (size_t)h->max_surv * B))) return rc;
     if ((rc = ensure_buf(h->d_surv2, h->cap_surv2, sizeof(int) * (size_t)h->max_surv * B))) return rc;
+    h->ck_cap = std::max(1024, w * hh / 16) / kCkPerBorder * kCkPerBorder;       // checkpoints of the borders that are followed for 256 steps and more
+    if ((rc = ensure_buf(h->d_ckpool, h->cap_ckpool, sizeof(int) * (size_t)(h->ck_cap + h->ck_cap / kCkPerBorder) * B))) return rc;
     {   // buffers of the ring form of the border walks (12 bytes per pixel and frame slot): it serves batches of up to kRingFrames frames, so that is
         // how many slots it gets (B200_CONTOURS_RING=1 forces it for every batch size, =0 disables it)
         const char* e = getenv("B200_CONTOURS_RING");
@@ -1912,7 +1961,7 @@ int b200_aruco_destroy(b200_aruco_t h) {
     if (!h) return B200_OK;
     DeviceScope _ds; cudaSetDevice(h->device);
     cudaFree(h->d_codes); cudaFree(h->d_surv); cudaFree(h->d_mask); cudaFree(h->d_pyr); cudaFree(h->d_desc); cudaFree(h->d_pts);
-    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_smap); cudaFree(h->d_nodes); cudaFree(h->d_sbits); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack); cudaFree(h->d_poses); if (h->h_pack) cudaFreeHost(h->h_pack);
+    cudaFree(h->d_scratch); cudaFree(h->d_cand); cudaFree(h->d_kept); cudaFree(h->d_dec); cudaFree(h->d_ncont); cudaFree(h->d_surv2); cudaFree(h->d_ckpool); cudaFree(h->d_smap); cudaFree(h->d_nodes); cudaFree(h->d_sbits); cudaFree(h->d_wpatch); cudaFree(h->d_whist); cudaFree(h->d_wlevel); cudaFree(h->d_mcontour); cudaFree(h->d_pack); cudaFree(h->d_poses); if (h->h_pack) cudaFreeHost(h->h_pack);
     cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->pyr_stream) cudaStreamDestroy(h->pyr_stream);
@@ -2011,13 +2060,17 @@ int b200_aruco_detect_range(b200_aruco_t h, const uint8_t* imgs, int n, int w, i
         // persistent CTAs; frames are the fast grid index.  Every step is a dependent load, so the kernels are latency bound; their CTAs hold their SM slots
         // for the whole kernel, so next to the extractor's dense kernels about 3 per frame is best at 256 frames (B200_PROBE_CTAS overrides)
         static const int env_gb = [] { const char* e = getenv("B200_PROBE_CTAS"); return e ? atoi(e) : 0; }();
+        // Checkpointed emission (B200_EMIT_CKPT=1): k_emit 0.345 -> 0.173 ms and the detector alone 2.24 -> 2.09 ms per 256 frames, but the C3 step, where the
+        // detector shares the SMs with the extractor, goes from 3.84 to 3.89-3.93 ms (measured twice, 20 steps each): off by default.
+        static const bool no_ckpt = getenv("B200_EMIT_CKPT") == nullptr;
+        static const int walk_steps = [] { const char* e = getenv("B200_WALK_STEPS"); const int v = e ? atoi(e) : kWalkSteps; return v > 0 ? v : kWalkSteps; }();
         dim3 gb(n, env_gb > 0 ? env_gb : std::max(1, std::min(64, (148 * 6) / n)));
         // the ring form packs a node into 64 bits (22-bit indices and keys): larger frames than 4 M mask bytes take the end-to-end walkers
         if (walk) {
             B200_LAUNCH(k_probe_b1, g1, 256, 0, st, d_mask, g, d_surv, d_nsurv, h->max_surv, d_surv2, d_nsurv2, h->d_err, (int*)nullptr, (uint32_t*)nullptr, 0);
-            B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err);
-            dim3 ge(4, n);
-            B200_LAUNCH(k_emit, ge, 128, 0, st, d_mask, g, d_desc, d_ncont, d_pts);
+            B200_LAUNCH(k_probe_b, gb, 128, 0, st, d_mask, g, d_surv2, d_nsurv2, h->max_surv, d_nfetch, d_desc, d_ncont, d_npts, h->d_err, walk_steps, h->d_nfetch2 + base, h->d_ckpool + (size_t)base * (h->ck_cap + h->ck_cap / kCkPerBorder), no_ckpt ? 0 : h->ck_cap);
+            dim3 ge(kEmitCtasA + 4, n);
+            B200_LAUNCH(k_emit, ge, 128, 0, st, d_mask, g, d_desc, d_ncont, d_pts, h->d_nfetch2 + base, h->d_ckpool + (size_t)base * (h->ck_cap + h->ck_cap / kCkPerBorder), no_ckpt ? 0 : h->ck_cap);
         } else {
             // d_surv (the transition list) is dead once phase B1 has run: it becomes the nodes' first-point-slot array
             int* d_smap = h->d_smap + (size_t)base * g.bframe;
