@@ -2300,7 +2300,8 @@ int b200_frontend_host(b200_orb_t h, b200_aruco_t aruco, const uint8_t* imgs, in
     const auto t_enq0 = std::chrono::steady_clock::now();
     int ci = 0;
     // the first chunk is small so that compute starts after a short upload; the second one completes the regular grid
-    const int first = (env_chunk <= 0 && chunk >= 64 && n > chunk) ? chunk / 4 : chunk;
+    static const int env_first = [] { const char* e = getenv("B200_FRONTEND_FIRST"); return e ? atoi(e) : 0; }();
+    const int first = (env_first > 0 && env_first < chunk && n > env_first) ? env_first : (env_chunk <= 0 && chunk >= 64 && n > chunk) ? chunk / 4 : chunk;
     for (int f0 = 0, nf = 0; f0 < n; f0 += nf, ci++) {
         nf = std::min(ci == 0 ? first : (ci == 1 && first != chunk) ? chunk - first : chunk, n - f0);
         uint8_t* dst = h->d_in + (size_t)f0 * frame_bytes;
