@@ -279,24 +279,27 @@ __device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int&
 
 constexpr int kHistoLen = 30;      // HISTO_LENGTH, ORBmatcher.cc:39
 
-__global__ void __launch_bounds__(32)
+constexpr int kResolveThreads = 256;
+
+__global__ void __launch_bounds__(kResolveThreads)
 k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict__ ref_angle, int ref_astride, int n_ref,
                 const ulonglong4* __restrict__ frame_desc, const float* __restrict__ frame_angle, int frame_astride,
                 const int* __restrict__ n_frame, int frame_cap, const uint32_t* __restrict__ topk,
                 float ratio, int th_low, int check_ori, float histo_factor,
                 int* __restrict__ match_ref_idx, int* __restrict__ n_matches, int stage_topk) {
     extern __shared__ __align__(16) unsigned int s_mem[];
-    const int f = blockIdx.x, lane = threadIdx.x;
+    // kResolveThreads threads stage the frame's lists and angles and clear the outputs (a single warp spent most of this kernel waiting for its own
+    // serial global loads); the replay itself is warp 0's
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
     const int nf = min(n_frame[f], frame_cap);
     unsigned int* taken = s_mem;                               // bitmap over frame keypoints
     const int words = (frame_cap + 31) / 32;
     unsigned char* bin_of = reinterpret_cast<unsigned char*>(s_mem + ((words + 3) & ~3));    // 16-byte aligned sections   // rotation bin of each matched frame keypoint
     __shared__ int histo[kHistoLen];
-    for (int i = lane; i < words; i += 32) taken[i] = 0;
-    if (lane < kHistoLen) histo[lane] = 0;
+    for (int i = tid; i < words; i += nthr) taken[i] = 0;
+    if (tid < kHistoLen) histo[tid] = 0;
     int* mout = match_ref_idx + (long long)f * frame_cap;
-    for (int i = lane; i < frame_cap; i += 32) mout[i] = -1;
-    __syncwarp();
+    for (int i = tid; i < frame_cap; i += nthr) mout[i] = -1;
     const ulonglong4* fd = frame_desc + (long long)f * frame_cap;
     const float* fa = frame_angle + (long long)f * frame_cap * frame_astride;
     // this frame's top-K lists: staged in shared memory when they fit (the loop below is a serial dependency chain)
@@ -305,17 +308,18 @@ k_match_resolve(const ulonglong4* __restrict__ ref_desc, const float* __restrict
         // (uint4 copies: the lists are 16-byte records; the angles of both sides follow so that a commit never waits on HBM)
         uint4* s_tk = reinterpret_cast<uint4*>(bin_of + ((frame_cap + 15) & ~15));
         const uint4* g_tk = reinterpret_cast<const uint4*>(tk_base);
-        for (int i = lane; i < n_ref * (kTopK / 4); i += 32) s_tk[i] = g_tk[i];
+        for (int i = tid; i < n_ref * (kTopK / 4); i += nthr) s_tk[i] = g_tk[i];
         tk_base = reinterpret_cast<const uint32_t*>(s_tk);
         if (check_ori) {
             float* s_ra = reinterpret_cast<float*>(s_tk + n_ref * (kTopK / 4));
             float* s_fa = s_ra + n_ref;
-            for (int i = lane; i < n_ref; i += 32) s_ra[i] = ref_angle[(long long)i * ref_astride];
-            for (int i = lane; i < nf; i += 32) s_fa[i] = fa[(long long)i * frame_astride];
+            for (int i = tid; i < n_ref; i += nthr) s_ra[i] = ref_angle[(long long)i * ref_astride];
+            for (int i = tid; i < nf; i += nthr) s_fa[i] = fa[(long long)i * frame_astride];
             ref_angle = s_ra; ref_astride = 1; fa = s_fa; frame_astride = 1;
         }
-        __syncwarp();
     }
+    __syncthreads();
+    if (tid >= 32) return;
     // The reference loop is serial in r, but the only state it carries is the "taken" set, which changes on accepted
     // matches only.  So 32 consecutive r are evaluated speculatively, one per lane, against the current set.  The lanes are
     // then committed in order: the first lane that accepts a match (or needs the exact rescan) is resolved, and only the
@@ -1042,7 +1046,7 @@ static int match_bf_impl(const uint8_t* ref_desc, const float* ref_angle, int re
     const int stage_topk = smem2 + tk_bytes <= 160 * 1024;
     if (stage_topk) smem2 += tk_bytes;
     B200_CUDA(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem2, 1024)));
-    B200_LAUNCH(k_match_resolve, n_batch, 32, smem2, st, (const ulonglong4*)ref_desc, ref_angle, ref_astride, n_ref, (const ulonglong4*)frame_desc,
+    B200_LAUNCH(k_match_resolve, n_batch, kResolveThreads, smem2, st, (const ulonglong4*)ref_desc, ref_angle, ref_astride, n_ref, (const ulonglong4*)frame_desc,
                 frame_angle, frame_astride, n_frame, frame_cap, topk, ratio, th_low, check_ori, histo_factor, match_ref_idx, n_matches, stage_topk);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
