@@ -8,8 +8,9 @@
 // whose summation order differs between a serial loop and a warp reduction).
 //
 // Pipeline for a batch of n frames (per-tile / per-border / per-candidate kernels, no serial raster scan):
-//   k_athresh     adaptiveThreshold MEAN_C BINARY_INV (markerdetector_impl.cpp:2984): separable running box sums in smem,
-//                 fused with the 8-neighbour foreground mask of every pixel (the binary image itself is never stored)
+//   k_athresh2    adaptiveThreshold MEAN_C BINARY_INV (markerdetector_impl.cpp:2984): packed 16-bit running window sums in registers,
+//                 fused with the 8-neighbour foreground mask of every pixel (the binary image itself is never stored); k_athresh is
+//                 the round-1 shared-memory form
 //   k_halfpyr     image pyramid by exact 1/2 (2x2 mean; odd sizes: fixed-point bilinear) (1300-1466)
 //   k_probe_a     cv::findContours RETR_LIST/CHAIN_APPROX_NONE (3108) without a raster scan: every 0->1 / 1->0 transition
 //                 pixel is listed (byte-parallel tests on mask words)
@@ -19,6 +20,8 @@
 //                 transition, i.e. Suzuki's start; the border is recorded with its length) or meet a transition the raster scan
 //                 would have seen earlier (=> abort)
 //   k_emit        borders longer than 70 points are followed once more and written as point lists
+//   (batches of up to 32 frames: k_seg / k_link / k_ring / k_emit2 instead of k_probe_b / k_emit - the ring form, whose chains of
+//    dependent loads end at the next surviving transition)
 //   k_quads       warp per border: cv::approxPolyDP(eps = 0.05*len, closed) + isContourConvex (3253-3292)
 //   k_prefilter   CTA per frame: candidate order = reverse discovery order, corner orientation, too-near pairs,
 //                 frame-border rejection (4349-5070)
@@ -795,7 +798,7 @@ k_emit2(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// A2, shared-memory form (the default whenever the frame's bit image fits): the walks above cost one dependent L2 / HBM load per border
+// A2, shared-memory form (B200_CONTOURS_SHARED=1, when the frame's bit image fits): the walks above cost one dependent L2 / HBM load per border
 // step, so their kernels last as long as the longest border times the memory latency.  The thresholded image is one BIT per pixel:
 // 41 KB at 640 x 480, 124 KB at 1280 x 720.  One CTA per frame stages it in shared memory as OVERLAPPED words - word k of a row holds
 // pixels 30k - 1 .. 30k + 30, so every pixel has a word in which it sits at bit 1 .. 30 and its 3 x 3 neighbourhood is three shifts of

@@ -1,5 +1,5 @@
-// match.cu -- B200-native ORB descriptor matching (sm_100a): 256-bit Hamming as 4 x __popcll, best /
-// second-best ratio test, 30-bin rotation-consistency histogram.
+// match.cu -- B200-native ORB descriptor matching (sm_100a): 256-bit Hamming as an int8 GEMM on tcgen05 / TMEM (k_match_mma; 4 x __popcll in
+// k_match_topk and the small kernels), best / second-best ratio test, 30-bin rotation-consistency histogram.
 //
 // Behavioural contract: ORB_SLAM2::ORBmatcher (reference src/ORBmatcher.cc): DescriptorDistance
 // (1651-1667), SearchByBoW(KeyFrame,Frame) (159-292) with one all-inclusive vocabulary node (== brute
@@ -7,8 +7,8 @@
 //
 // The reference's loop is greedy: reference descriptor r only looks at frame descriptors that no earlier
 // r has taken.  Split:
-//   k_match_topk     warp per (frame, r): all n_frame distances, keeps the K smallest (dist<<16|idx) keys
-//                    (frame descriptors staged once per CTA in shared memory as 4 u64 planes)
+//   k_match_mma      CTA per (frame, 128 reference rows): all distances through tcgen05.mma.kind::i8, the K smallest (dist<<16|idx) keys per row
+//   k_match_topk     the same lists by popcount, warp per (frame, r) (B200_MATCH_POPC=1; frame descriptors staged once per CTA as 4 u64 planes)
 //   k_match_resolve  warp per frame: replays r = 0..n_ref-1 in order against a "taken" bitmap using the
 //                    top-K lists (exact; a list that runs dry while a match is still possible triggers a
 //                    warp-wide rescan of the whole row), then the rotation histogram filter.

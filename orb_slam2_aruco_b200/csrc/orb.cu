@@ -8,8 +8,9 @@
 //
 // Pipeline for a batch of n frames (everything stays in HBM/L2, 10 launches):
 //   k_pyramid_tma x (nlevels-1)   level l from level l-1, fixed-point bilinear, source tile by TMA (ORBextractor.cc:1107-1132)
-//   k_fast                    one CTA per (cell, frame): u8 tile in smem, score of every pixel, 3x3 NMS,
-//                             ini/min threshold fallback, raster-ordered compaction (ORBextractor.cc:765-829)
+//   k_fast                    one CTA per (cell, frame): u8 tile in smem by TMA, compass pretest, packed scoring of the survivors, 3x3 NMS,
+//                             ini/min threshold fallback, raster-ordered compaction (ORBextractor.cc:765-829); two more forms of this stage
+//                             (dense score map + per-cell NMS, one warp per cell) sit behind switches with their measured numbers
 //   k_quadtree                one warp per (frame, level): DistributeOctTree (ORBextractor.cc:539-763)
 //   k_describe                one warp per keypoint: IC_Angle, 7x7 Gaussian on a 43x43 patch, rBRIEF
 //                             (ORBextractor.cc:77-147,1085-1101)
@@ -645,7 +646,7 @@ k_fastw(const uint8_t* __restrict__ img0, long long img_row_stride, long long im
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 (dense form, the default): the FAST score is threshold independent and the cells' interiors tile the level, so the work splits
+// K2 (dense form, B200_FAST_DENSE=1): the FAST score is threshold independent and the cells' interiors tile the level, so the work splits
 // into a perfectly regular part and a tiny per-cell part.
 //
 // k_fast_score: the score of EVERY pixel of a 64 x 32 tile, no pretest, no queues, no divergence.  The (64 + 6) x (32 + 6) pixel
