@@ -372,6 +372,17 @@ __device__ __forceinline__ int dir_delta(int d, int pitch) {
     return dy * pitch + dx;
 }
 
+// (neighbour mask, back direction) -> direction taken | transition class << 3 | pixel delta << 8, for the whole CTA (ends with a barrier)
+__device__ __forceinline__ void fill_step_table(int* s_step, int bpitch) {
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+        const int m = i >> 3, sb = i & 7;
+        const Step st = next_step(m, sb);
+        const int key = m ? step_key(0, sb, st.k) : 0x7fffffff;
+        s_step[i] = (st.d & 7) | ((key == 0 ? 1 : key == 1 ? 2 : 0) << 3) | (dir_delta(st.d & 7, bpitch) << 8);
+    }
+    __syncthreads();
+}
+
 // Phase A (thread per aligned 4-pixel word of the mask image): list every transition pixel -- foreground with a zero West
 // neighbour (0->1, possible outer-border start) or a zero East neighbour (1->0, possible hole-border start).  The tests
 // run byte-parallel on the word; transitions are sparse, so the few hits are appended with a CTA-aggregated atomic.
@@ -488,6 +499,10 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
     const int* list = surv + (long long)f * max_cand;
     const int limit = 4 * g.max_points;
+    // the whole step as one table lookup: (neighbour mask, back direction) -> direction taken | transition class << 3 | pixel delta << 8
+    // (class 1: the raster scan sees this step at its pixel, 2: at the next pixel; next_step + step_key + dir_delta are ~25 dependent instructions)
+    __shared__ int s_step[256 * 8];
+    fill_step_table(s_step, g.bpitch);
     int P = 0, s0 = 0, mykey = 0, p = 0, s = 0, n = 0;
     bool busy = false, exhausted = false;
     for (;;) {
@@ -518,11 +533,12 @@ k_probe_b(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g
 #pragma unroll 1
         for (int rep = 0; rep < walk_steps; rep++)
         if (busy) {
-            const Step st = next_step(mask[p], s);
-            if (n > 0 && step_key(p, s, st.k) < mykey) busy = false;
+            const int e = s_step[((int)mask[p] << 3) | s];
+            const int kc = (e >> 3) & 3;
+            if (n > 0 && kc && p + kc - 1 < mykey) busy = false;
             else {
-                p += dir_delta(st.d, g.bpitch);
-                s = (st.d + 4) & 7;
+                p += e >> 8;
+                s = (e + 4) & 7;
                 n++;
                 if ((n & (kCkStride - 1)) == 0 && n <= kCkStride * kCkPerBorder && ckb != -2) {      // state after n steps, for k_emit's stretches
                     if (ckb < 0) { const int b = atomicAdd(ckalloc + f, kCkPerBorder); ckb = b + kCkPerBorder <= ck_cap ? b : -2; if (ckb >= 0) ckpool[ck_cap + b / kCkPerBorder] = -1; }
@@ -554,6 +570,8 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
     // them.  Part B, one thread per checkpoint of the frame's pool: the stretch that starts at the state k_probe_b recorded there (the last stretch of a
     // border runs to its end).  Only walks of 256 steps and more allocate checkpoints, so part B is a few hundred threads per frame, and no thread of
     // either part follows more than kCkStride points of a border shorter than kCkStride * (kCkPerBorder + 1).
+    __shared__ int s_step[256 * 8];
+    fill_step_table(s_step, g.bpitch);
     const int f = blockIdx.y;
     const uint8_t* mask = mask0 + (long long)f * g.bframe;
     const int* ckpool = ckpool0 + (long long)f * (ck_cap + ck_cap / kCkPerBorder);
@@ -568,10 +586,10 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
             int x = p % g.bpitch - kMaskPad, y = p / g.bpitch - 1;
             for (int n = n0; n < n1; n++) {
                 out[n] = make_short2((short)x, (short)y);
-                const Step st = next_step(mask[p], s);
-                const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
-                p += dy * g.bpitch + dx; x += dx; y += dy;
-                s = (st.d + 4) & 7;
+                const int e = s_step[((int)mask[p] << 3) | s];
+                const int d = e & 7, dx = ((0x901A >> (2 * d)) & 3) - 1, dy = ((0xA901 >> (2 * d)) & 3) - 1;
+                p += e >> 8; x += dx; y += dy;
+                s = (d + 4) & 7;
             }
         }
     } else {
@@ -590,10 +608,10 @@ k_emit(const uint8_t* __restrict__ mask0, const __grid_constant__ ArucoGeom g, c
             int x = p % g.bpitch - kMaskPad, y = p / g.bpitch - 1;
             for (int n = n0; n < n1; n++) {
                 out[n] = make_short2((short)x, (short)y);
-                const Step st = next_step(mask[p], s);
-                const int dx = ((0x901A >> (2 * st.d)) & 3) - 1, dy = ((0xA901 >> (2 * st.d)) & 3) - 1;
-                p += dy * g.bpitch + dx; x += dx; y += dy;
-                s = (st.d + 4) & 7;
+                const int e = s_step[((int)mask[p] << 3) | s];
+                const int d = e & 7, dx = ((0x901A >> (2 * d)) & 3) - 1, dy = ((0xA901 >> (2 * d)) & 3) - 1;
+                p += e >> 8; x += dx; y += dy;
+                s = (d + 4) & 7;
             }
         }
     }
