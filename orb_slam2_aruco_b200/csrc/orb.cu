@@ -919,17 +919,7 @@ struct QtWarp {          // per-warp view of its shared memory
 };
 
 __device__ __forceinline__ int qt_alloc(QtWarp& w) { return w.freelist[--w.nfree]; }
-__device__ __forceinline__ void qt_free(QtWarp& w, int id, int lane) { if (lane == 0) w.freelist[w.nfree] = (short)id; w.nfree++; __syncwarp(); }
 
-__device__ __forceinline__ void qt_push_front(QtWarp& w, int id, int lane) {
-    if (lane == 0) {
-        w.pool[id].prev = -1; w.pool[id].next = (short)w.head;
-        if (w.head >= 0) w.pool[w.head].prev = (short)id;
-    }
-    if (w.head < 0) w.tail = id;
-    w.head = id; w.size++;
-    __syncwarp();
-}
 __device__ __forceinline__ void qt_push_back(QtWarp& w, int id, int lane) {
     if (lane == 0) {
         w.pool[id].next = -1; w.pool[id].prev = (short)w.tail;
@@ -938,19 +928,6 @@ __device__ __forceinline__ void qt_push_back(QtWarp& w, int id, int lane) {
     if (w.tail < 0) w.head = id;
     w.tail = id; w.size++;
     __syncwarp();
-}
-__device__ __forceinline__ int qt_erase(QtWarp& w, int id, int lane) {   // returns the successor
-    const int p = w.pool[id].prev, n = w.pool[id].next;
-    __syncwarp();
-    if (lane == 0) {
-        if (p >= 0) w.pool[p].next = (short)n;
-        if (n >= 0) w.pool[n].prev = (short)p;
-    }
-    if (p < 0) w.head = n;
-    if (n < 0) w.tail = p;
-    w.size--;
-    qt_free(w, id, lane);
-    return n;
 }
 
 // DivideNode (ORBextractor.cc:481-537): stable 4-way partition of the node's key range into the other buffer.
@@ -1043,36 +1020,9 @@ __device__ __forceinline__ bool qt_prefetch(const QtWarp& w, int id, const uint3
     return true;
 }
 
-// create the non-empty children of `nd` at the list front in the order n1..n4 (ORBextractor.cc:606-665);
-// children with more than one key are appended to the `big` list.  Returns how many big children were added.
-__device__ __forceinline__ int qt_add_children(QtWarp& w, const QtNode nd, const int cnt[4], int mx, int my, int lane, int& nbig) {
-    int added = 0;
-    int beg = nd.beg;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int k = cnt[q];
-        if (k > 0) {
-            const int id = qt_alloc(w);
-            if (lane == 0) {
-                QtNode c;
-                c.x0 = (q & 1) ? (short)mx : nd.x0; c.x1 = (q & 1) ? nd.x1 : (short)mx;
-                c.y0 = (q & 2) ? (short)my : nd.y0; c.y1 = (q & 2) ? nd.y1 : (short)my;
-                c.beg = beg; c.end = beg + k; c.prev = c.next = -1; c.seq = w.seq;
-                c.no_more = (k == 1); c.buf = nd.buf ^ 1; c.pad0 = c.pad1 = 0;
-                w.pool[id] = c;
-                if (k > 1) { w.big_cnt[nbig] = k; w.big_seq[nbig] = w.seq; w.big_id[nbig] = (short)id; }
-            }
-            __syncwarp();
-            qt_push_front(w, id, lane);
-            w.seq++;
-            if (k > 1) { nbig++; added++; }
-        }
-        beg += k;
-    }
-    return added;
-}
 
-// qt_add_children + qt_erase of the parent in one step with two warp barriers instead of ten: lanes 0..3 write one child each (node record, links
+// The non-empty children of `nd` go to the list front in the order n1..n4 (ORBextractor.cc:606-665; children with more than one key are appended to
+// the `big` list) and the parent leaves the list, in one step with two warp barriers: lanes 0..3 write one child each (node record, links
 // among the new children, entry of the `big` list), lane 4 re-links the old list head; then the parent is unlinked and its slot goes back to the
 // free list.  Same list order as four push_fronts in the order n1..n4: [n4, n3, n2, n1, old head, ...]; same creation sequence numbers.
 __device__ __forceinline__ int qt_split(QtWarp& w, int it, const QtNode nd, const int cnt[4], int mx, int my, int lane, int& nbig) {
